@@ -1,0 +1,124 @@
+"""ctypes mirrors of the POD types in include/dfpsr_b200.h.
+
+Shared by the product binding (dfpsr_b200/lib.py), the oracle binding and the reference wrapper binding
+(tests/ only), so that the same scene description can be handed to all three.
+"""
+import ctypes as C
+
+import numpy as np
+
+PACK_RGBA, PACK_BGRA, PACK_ARGB, PACK_ABGR = 0, 1, 2, 3
+FILTER_SOLID, FILTER_ALPHA = 0, 1
+SAMPLER_NEAREST, SAMPLER_LINEAR = 0, 1
+MAP_XOR_PATTERN, MAP_AFFINE, MAP_CONSTANT = 0, 1, 2
+
+
+class Transform3D(C.Structure):
+    _fields_ = [("position", C.c_float * 3), ("xAxis", C.c_float * 3), ("yAxis", C.c_float * 3), ("zAxis", C.c_float * 3)]
+
+    @staticmethod
+    def identity():
+        return Transform3D.make((0, 0, 0), ((1, 0, 0), (0, 1, 0), (0, 0, 1)))
+
+    @staticmethod
+    def make(position, axes):
+        t = Transform3D()
+        t.position[:] = [float(np.float32(v)) for v in position]
+        t.xAxis[:] = [float(np.float32(v)) for v in axes[0]]
+        t.yAxis[:] = [float(np.float32(v)) for v in axes[1]]
+        t.zAxis[:] = [float(np.float32(v)) for v in axes[2]]
+        return t
+
+
+class Matrix3x3(C.Structure):
+    _fields_ = [("xAxis", C.c_float * 3), ("yAxis", C.c_float * 3), ("zAxis", C.c_float * 3)]
+
+
+class Camera(C.Structure):
+    _fields_ = [
+        ("perspective", C.c_int32),
+        ("location", Transform3D),
+        ("widthSlope", C.c_float), ("heightSlope", C.c_float), ("invWidthSlope", C.c_float), ("invHeightSlope", C.c_float),
+        ("imageWidth", C.c_float), ("imageHeight", C.c_float), ("nearClip", C.c_float), ("farClip", C.c_float),
+        ("cullPlaneCount", C.c_int32), ("clipPlaneCount", C.c_int32),
+        ("cullPlanes", (C.c_float * 4) * 6),
+        ("clipPlanes", (C.c_float * 4) * 6),
+    ]
+
+
+class Polygon(C.Structure):
+    _fields_ = [("pointIndices", C.c_int32 * 4), ("texCoords", (C.c_float * 4) * 4), ("colors", (C.c_float * 4) * 4)]
+
+
+POLYGON_DTYPE = np.dtype([("pointIndices", np.int32, (4,)), ("texCoords", np.float32, (4, 4)), ("colors", np.float32, (4, 4))])
+assert POLYGON_DTYPE.itemsize == 144 and C.sizeof(Polygon) == 144
+
+
+class ProjectedPoint(C.Structure):
+    _fields_ = [("cs", C.c_float * 3), ("is_", C.c_float * 2), ("pad_", C.c_int32), ("flat", C.c_int64 * 2)]
+
+
+PROJECTED_DTYPE = np.dtype([("cs", np.float32, (3,)), ("is", np.float32, (2,)), ("pad", np.int32), ("flat", np.int64, (2,))])
+assert PROJECTED_DTYPE.itemsize == 40 and C.sizeof(ProjectedPoint) == 40
+
+TRIANGLE_DTYPE = np.dtype([("pos", PROJECTED_DTYPE, (3,)), ("colors", np.float32, (3, 4)), ("texCoords", np.float32, (3, 4))])
+assert TRIANGLE_DTYPE.itemsize == 216
+
+
+class Image(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("width", C.c_int32), ("height", C.c_int32), ("stride", C.c_int32), ("packOrder", C.c_int32)]
+
+    @staticmethod
+    def null():
+        return Image(None, 0, 0, 0, 0)
+
+
+class Texture(C.Structure):
+    _fields_ = [
+        ("data", C.c_void_p),
+        ("log2width", C.c_uint32), ("log2height", C.c_uint32), ("maxMipLevel", C.c_uint32),
+        ("startOffset", C.c_uint32), ("maxLevelMask", C.c_uint32), ("totalPixels", C.c_uint32),
+    ]
+
+
+class OrthoView(C.Structure):
+    _fields_ = [("normalToWorldSpace", Matrix3x3), ("screenDepthToLightSpace", Matrix3x3), ("lightSpaceToScreenDepth", Matrix3x3)]
+
+
+class Model(C.Structure):
+    _fields_ = [
+        ("points", C.c_void_p), ("pointCount", C.c_int32),
+        ("polygons", C.c_void_p), ("polygonCount", C.c_int32),
+        ("filter", C.c_int32),
+        ("diffuse", Texture), ("light", Texture),
+        ("minBound", C.c_float * 3), ("maxBound", C.c_float * 3),
+    ]
+
+
+class SpriteDraw(C.Structure):
+    _fields_ = [("sourceHeight", Image), ("sourceA", Image), ("sourceB", Image), ("left", C.c_int32), ("top", C.c_int32), ("heightOffset", C.c_float)]
+
+
+class HostModel(C.Structure):
+    _fields_ = [
+        ("points", C.c_void_p), ("pointCount", C.c_int32),
+        ("polygons", C.c_void_p), ("polygonCount", C.c_int32),
+        ("filter", C.c_int32),
+        ("diffusePixels", C.c_void_p), ("diffuseLayout", Texture),
+        ("lightPixels", C.c_void_p), ("lightLayout", Texture),
+        ("minBound", C.c_float * 3), ("maxBound", C.c_float * 3),
+    ]
+
+
+def camera_params(perspective, location, width, height, width_slope=1.0, near=0.01, far=1000.0):
+    """A camera POD holding only the constructor arguments; derived fields are filled by
+    dfpsr_camera_create_* (product), orc_camera_create (oracle) or ref_camera_fill (reference)."""
+    c = Camera()
+    c.perspective = 1 if perspective else 0
+    c.location = location
+    c.imageWidth = float(width)
+    c.imageHeight = float(height)
+    c.widthSlope = float(np.float32(width_slope))
+    c.nearClip = float(np.float32(near))
+    c.farClip = float(np.float32(far))
+    return c

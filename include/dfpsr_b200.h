@@ -1,0 +1,286 @@
+/*
+ * dfpsr_b200.h — C ABI of the B200-native rendering hot path.
+ *
+ * Every entry point replaces one host-side loop of Dawoodoz/DFPSR (the reference), cited as
+ * "ref: <file>:<line>" relative to /root/reference/Source. The reference is a C++14 library, so its
+ * "FFI" for this path is the C++ API itself (rendererAPI.h, modelAPI.h, drawAPI.h, filterAPI.h,
+ * SDK/SpriteEngine/lightAPI.h). The `dsr::` shim under dfpsr_b200/host/ re-exposes those C++ names
+ * on top of this ABI; INTEGRATION.md shows the binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no C++ or torch types.
+ *   - every function returns 0 on success, non-zero on error; dfpsr_last_error() gives the message
+ *     (thread local). There is NO CPU fallback: without a CUDA device every compute call fails.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream). Calls are asynchronous
+ *     on that stream unless the name ends in _host (those take HOST buffers, copy in, run the same
+ *     kernels, copy out and synchronise the stream before returning).
+ *   - images are descriptors over device memory: {data, width, height, stride in bytes, pack order}.
+ *     `data == NULL` means "image does not exist" (ref: api/imageAPI.h:96 image_exists).
+ */
+#ifndef DFPSR_B200_H
+#define DFPSR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DFPSR_B200_ABI_VERSION 1
+
+/* ---------------------------------------------------------------- POD mirrors */
+
+/* ref: implementation/image/PackOrder.h:37-42 (PackOrderIndex) */
+enum { DFPSR_PACK_RGBA = 0, DFPSR_PACK_BGRA = 1, DFPSR_PACK_ARGB = 2, DFPSR_PACK_ABGR = 3 };
+/* ref: implementation/render/constants.h:34 (Filter) */
+enum { DFPSR_FILTER_SOLID = 0, DFPSR_FILTER_ALPHA = 1 };
+/* ref: api/filterAPI.h:33-36 (Sampler) */
+enum { DFPSR_SAMPLER_NEAREST = 0, DFPSR_SAMPLER_LINEAR = 1 };
+
+/* ref: math/Transform3D.h:33-36 — position then the three matrix axes, 12 floats. */
+typedef struct dfpsr_transform3d {
+	float position[3];
+	float xAxis[3], yAxis[3], zAxis[3];
+} dfpsr_transform3d;
+
+/* ref: math/FMatrix3x3.h:33 */
+typedef struct dfpsr_matrix3x3 {
+	float xAxis[3], yAxis[3], zAxis[3];
+} dfpsr_matrix3x3;
+
+/* ref: implementation/render/Camera.h:128-150. Planes are {nx, ny, nz, offset} with normalised normals
+ * (ref: math/FPlane3D.h:36-45); filled by dfpsr_camera_create_*(). */
+typedef struct dfpsr_camera {
+	int32_t perspective;
+	dfpsr_transform3d location;
+	float widthSlope, heightSlope, invWidthSlope, invHeightSlope;
+	float imageWidth, imageHeight, nearClip, farClip;
+	int32_t cullPlaneCount, clipPlaneCount;
+	float cullPlanes[6][4];
+	float clipPlanes[6][4];
+} dfpsr_camera;
+
+/* ref: implementation/render/model/Model.h:54-58 (Polygon, 144 bytes, same field order). */
+typedef struct dfpsr_polygon {
+	int32_t pointIndices[4]; /* pointIndices[3] == -1 for triangles */
+	float texCoords[4][4];   /* u1, v1, u2, v2 per corner */
+	float colors[4][4];      /* r, g, b, a per corner, 0..1 */
+} dfpsr_polygon;
+
+/* ref: implementation/render/ProjectedPoint.h:33-50 (40 bytes). */
+typedef struct dfpsr_projected_point {
+	float cs[3];
+	float is[2];
+	int32_t pad_;
+	int64_t flat[2];
+} dfpsr_projected_point;
+
+/* One pre-projected triangle as given to renderer_giveTask_triangle (ref: api/rendererAPI.h:108-116). */
+typedef struct dfpsr_triangle {
+	dfpsr_projected_point pos[3];
+	float colors[3][4];
+	float texCoords[3][4];
+} dfpsr_triangle;
+
+/* Image view over DEVICE memory (ref: implementation/image/Image.h:58-183). stride in bytes. */
+typedef struct dfpsr_image {
+	void *data;
+	int32_t width, height;
+	int32_t stride;
+	int32_t packOrder; /* RGBA8 images only */
+} dfpsr_image;
+
+/* Mip pyramid in one u32 buffer, smallest level first (ref: implementation/image/Texture.h:42-95).
+ * data == NULL means "no texture". Use dfpsr_texture_layout() to fill the derived fields. */
+typedef struct dfpsr_texture {
+	const uint32_t *data; /* device pointer, totalPixels u32 */
+	uint32_t log2width, log2height, maxMipLevel;
+	uint32_t startOffset, maxLevelMask;
+	uint32_t totalPixels;
+} dfpsr_texture;
+
+/* The three matrices of OrthoView that the light passes read (ref: SDK/SpriteEngine/orthoAPI.h:52-77). */
+typedef struct dfpsr_ortho_view {
+	dfpsr_matrix3x3 normalToWorldSpace;
+	dfpsr_matrix3x3 screenDepthToLightSpace;
+	dfpsr_matrix3x3 lightSpaceToScreenDepth;
+} dfpsr_ortho_view;
+
+/* A model on the device: points (3 floats each) and polygons; one part (ref: Model.h:66-84). */
+typedef struct dfpsr_model {
+	const float *points;           /* device, 3 * pointCount floats */
+	int32_t pointCount;
+	const dfpsr_polygon *polygons; /* device */
+	int32_t polygonCount;
+	int32_t filter;
+	dfpsr_texture diffuse, light;
+	float minBound[3], maxBound[3]; /* model space, ref: Model.h:83 */
+} dfpsr_model;
+
+/* Per-pixel operations for filter_mapRgbaU8 / filter_generateRgbaU8. The reference takes a host
+ * lambda (ref: api/filterAPI.h:54-59); a device cannot run it, so the ABI enumerates device ops.
+ * params are int32. Results are saturated to 0..255 and packed in the target's pack order
+ * (ref: api/filterAPI.cpp:759-777, image_saturateAndPack). */
+enum {
+	/* (x & 255, y & 255, (x ^ y) & 255, 255) — BASELINE config 5 source pattern. No params. */
+	DFPSR_MAP_XOR_PATTERN = 0,
+	/* c' = src(x, y).c * mul[c] + add[c], source read with clamp-to-edge
+	 * (ref: api/imageAPI.h image_readPixel_clamp). params = mul[4], add[4]. */
+	DFPSR_MAP_AFFINE = 1,
+	/* constant colour params[0..3] */
+	DFPSR_MAP_CONSTANT = 2
+};
+
+/* ---------------------------------------------------------------- library */
+
+int dfpsr_abi_version(void);
+const char *dfpsr_last_error(void);
+/* Selects the CUDA device for the calling thread and creates its context state. */
+int dfpsr_init(int device);
+int dfpsr_device_count(void);
+/* Number of kernels this library has launched since the last reset (bench.py's gpu_launches). */
+uint64_t dfpsr_launch_count(void);
+void dfpsr_reset_launch_count(void);
+
+/* Device memory helpers for hosts that do not bring their own allocator. */
+int dfpsr_malloc(void **devicePtr, size_t bytes);
+int dfpsr_free(void *devicePtr);
+int dfpsr_malloc_host(void **pinnedPtr, size_t bytes);
+int dfpsr_free_host(void *pinnedPtr);
+int dfpsr_upload(void *devicePtr, const void *hostPtr, size_t bytes, void *stream);
+int dfpsr_download(void *hostPtr, const void *devicePtr, size_t bytes, void *stream);
+int dfpsr_upload_2d(void *devicePtr, size_t deviceStride, const void *hostPtr, size_t hostStride, size_t rowBytes, size_t rows, void *stream);
+int dfpsr_download_2d(void *hostPtr, size_t hostStride, const void *devicePtr, size_t deviceStride, size_t rowBytes, size_t rows, void *stream);
+int dfpsr_stream_synchronize(void *stream);
+
+/* ---------------------------------------------------------------- camera (host side, no GPU needed) */
+
+/* ref: implementation/render/Camera.h:144-150 Camera::createPerspective */
+int dfpsr_camera_create_perspective(dfpsr_camera *out, const dfpsr_transform3d *location, float imageWidth, float imageHeight, float widthSlope, float nearClip, float farClip);
+/* ref: implementation/render/Camera.h:152-156 Camera::createOrthogonal */
+int dfpsr_camera_create_orthogonal(dfpsr_camera *out, const dfpsr_transform3d *location, float imageWidth, float imageHeight, float halfWidth);
+/* ref: implementation/render/Camera.h:202-217 Camera::isBoxSeen — 0 hidden, 1 partial, 2 fully inside. */
+int dfpsr_camera_is_box_seen(const dfpsr_camera *camera, const float minBound[3], const float maxBound[3], const dfpsr_transform3d *modelToWorld);
+
+/* ---------------------------------------------------------------- textures */
+
+/* Fills log2/startOffset/maxLevelMask/totalPixels for a width x height texture with `resolutions`
+ * levels (ref: api/textureAPI.cpp:65-78 + implementation/image/Texture.h:63-91). width and height are
+ * rounded up to powers of two. data is left NULL. */
+int dfpsr_texture_layout(dfpsr_texture *out, int32_t width, int32_t height, int32_t resolutions);
+/* Box-filters every lower level from level 0 on the device (ref: api/textureAPI.cpp:44-87). */
+int dfpsr_texture_generate_pyramid(const dfpsr_texture *texture, void *stream);
+/* texture_create_RgbaU8(image, resolutions): bilinear resize of `image` into level 0 then pyramid
+ * (ref: api/textureAPI.cpp:89-110). `texture->data` must already point at totalPixels u32. */
+int dfpsr_texture_from_image(const dfpsr_texture *texture, const dfpsr_image *image, void *stream);
+
+/* ---------------------------------------------------------------- triangle pipeline */
+
+typedef struct dfpsr_renderer dfpsr_renderer;
+
+/* ref: api/rendererAPI.h:56-58 renderer_create / (handle release) */
+int dfpsr_renderer_create(dfpsr_renderer **out);
+int dfpsr_renderer_destroy(dfpsr_renderer *renderer);
+/* ref: api/rendererAPI.h:66 renderer_begin. Either image may have data == NULL. Calling begin twice
+ * without end is an error (ref: api/rendererAPI.cpp:152-154). */
+int dfpsr_renderer_begin(dfpsr_renderer *renderer, const dfpsr_image *color, const dfpsr_image *depth);
+/* ref: api/modelAPI.cpp:214-281 model_render_threaded / renderer_giveTask. Bound culling
+ * (Camera::isBoxSeen) is applied on the host exactly like the reference. Enqueues the projection and
+ * triangle set-up kernels on `stream`; nothing is drawn before dfpsr_renderer_end. */
+int dfpsr_renderer_give_task(dfpsr_renderer *renderer, const dfpsr_model *model, const dfpsr_transform3d *modelToWorld, const dfpsr_camera *camera, void *stream);
+/* ref: api/rendererAPI.h:108-116 renderer_giveTask_triangle, batched: `triangles` is a HOST array. */
+int dfpsr_renderer_give_task_triangles(dfpsr_renderer *renderer, const dfpsr_triangle *triangles, int32_t count, const dfpsr_texture *diffuse, const dfpsr_texture *light, int32_t filter, const dfpsr_camera *camera, void *stream);
+/* ref: api/rendererAPI.h:131 renderer_end → CommandQueue::execute (implementation/render/renderCore.cpp:449-480):
+ * bins the queued triangles to screen tiles and rasterises/shades every tile in submission order. */
+int dfpsr_renderer_end(dfpsr_renderer *renderer, void *stream);
+/* Number of draw commands (post-clipping triangles) the last frame produced; synchronises `stream`. */
+int dfpsr_renderer_last_command_count(dfpsr_renderer *renderer, int64_t *count, void *stream);
+
+/* ref: api/modelAPI.cpp:197-201 model_render — begin + give_task + end on a private renderer. */
+int dfpsr_model_render(const dfpsr_model *model, const dfpsr_transform3d *modelToWorld, const dfpsr_image *color, const dfpsr_image *depth, const dfpsr_camera *camera, void *stream);
+/* ref: api/modelAPI.cpp:202-206 model_renderDepth (1x1 aligned depth-only path, renderCore.cpp:343-443). */
+int dfpsr_model_render_depth(const dfpsr_model *model, const dfpsr_transform3d *modelToWorld, const dfpsr_image *depth, const dfpsr_camera *camera, void *stream);
+/* Many independent views of one model in one submission (BASELINE config 4): view i renders with
+ * cameras[i] into colors[i]/depths[i]. Equivalent to `count` calls of dfpsr_model_render. When
+ * `clear` is non-zero every target is first cleared to colour 0 / depth 0.0f as the SDK terrain loop does
+ * (ref: SDK/terrain/main.cpp:397-402). Arrays are HOST arrays of descriptors. */
+int dfpsr_model_render_views(const dfpsr_model *model, const dfpsr_transform3d *modelToWorld, const dfpsr_image *colors, const dfpsr_image *depths, const dfpsr_camera *cameras, int32_t count, int32_t clear, void *stream);
+/* ref: api/modelAPI.cpp:238-242 — the projection loop alone (exposed for parity tests): out[i] = worldToScreen(M * p[i]). */
+int dfpsr_project_points(const float *points, int32_t count, const dfpsr_transform3d *modelToWorld, const dfpsr_camera *camera, dfpsr_projected_point *outDevice, void *stream);
+
+/* ---------------------------------------------------------------- 2D draw calls on the path */
+
+/* ref: api/imageAPI.cpp:167-185 image_fill → api/drawAPI.cpp:72-174 draw_rectangle. */
+int dfpsr_image_fill_rgba(const dfpsr_image *image, int32_t red, int32_t green, int32_t blue, int32_t alpha, void *stream);
+int dfpsr_image_fill_f32(const dfpsr_image *image, float value, void *stream);
+/* ref: api/drawAPI.cpp:492-538, :906-924 draw_copy (RgbaU8→RgbaU8 incl. pack-order conversion; F32→F32). */
+int dfpsr_draw_copy_rgba(const dfpsr_image *target, const dfpsr_image *source, int32_t left, int32_t top, void *stream);
+int dfpsr_draw_copy_f32(const dfpsr_image *target, const dfpsr_image *source, int32_t left, int32_t top, void *stream);
+/* ref: api/drawAPI.cpp:834-904, :962-979 draw_higher on F32 heights with 0, 1 or 2 RGBA8 payload images
+ * (targetA/sourceA and targetB/sourceB may be NULL together). */
+int dfpsr_draw_higher(const dfpsr_image *targetHeight, const dfpsr_image *sourceHeight, const dfpsr_image *targetA, const dfpsr_image *sourceA, const dfpsr_image *targetB, const dfpsr_image *sourceB, int32_t left, int32_t top, float sourceHeightOffset, void *stream);
+
+/* One sprite placement for the batched compositor: sources live in an atlas on the device. */
+typedef struct dfpsr_sprite_draw {
+	dfpsr_image sourceHeight, sourceA, sourceB;
+	int32_t left, top;
+	float heightOffset;
+} dfpsr_sprite_draw;
+/* `count` draw_higher calls applied in array order (ref: SDK/SpriteEngine/spriteAPI.cpp:316-323, :525-539
+ * — BackgroundBlock::draw loops drawSprite over the octree result). HOST array. */
+int dfpsr_draw_higher_batch(const dfpsr_image *targetHeight, const dfpsr_image *targetA, const dfpsr_image *targetB, const dfpsr_sprite_draw *draws, int32_t count, void *stream);
+
+/* ---------------------------------------------------------------- Sandbox deferred light */
+
+/* ref: SDK/SpriteEngine/lightAPI.cpp:23-74 setDirectedLight (add = 0) / addDirectedLight (add = 1). */
+int dfpsr_light_directed(const dfpsr_ortho_view *view, const dfpsr_image *light, const dfpsr_image *normal, const float direction[3], float intensity, const int32_t colorRgb[3], int32_t add, void *stream);
+/* ref: SDK/SpriteEngine/lightAPI.cpp:76-285 addPointLight. shadowCubeMap may be NULL (no shadows);
+ * otherwise a width x 6*width F32 image rendered by dfpsr_model_render_depth (spriteAPI.cpp:351-401). */
+int dfpsr_light_point(const dfpsr_ortho_view *view, const int32_t worldCenter[2], const dfpsr_image *light, const dfpsr_image *normal, const dfpsr_image *height, const float position[3], float radius, float intensity, const int32_t colorRgb[3], const dfpsr_image *shadowCubeMap, void *stream);
+/* ref: SDK/SpriteEngine/lightAPI.cpp:287-323 blendLight. */
+int dfpsr_light_blend(const dfpsr_image *color, const dfpsr_image *diffuse, const dfpsr_image *light, void *stream);
+
+/* ---------------------------------------------------------------- filters */
+
+/* ref: api/filterAPI.cpp:852-860 filter_resize(ImageRgbaU8): `target` (newWidth x newHeight, RGBA order,
+ * not a sub-image) receives the stretched `source`. sourceIsSubImage mirrors image_isSubImage(source),
+ * which selects the reference's code path and therefore its rounding (filterAPI.cpp:262-279).
+ * scratch: device buffer of dfpsr_filter_resize_scratch_bytes() bytes, only used for two-pass up-scaling. */
+size_t dfpsr_filter_resize_scratch_bytes(int32_t sourceWidth, int32_t sourceHeight, int32_t newWidth, int32_t newHeight);
+int dfpsr_filter_resize(const dfpsr_image *target, const dfpsr_image *source, int32_t sampler, int32_t sourceIsSubImage, void *scratch, void *stream);
+/* ref: api/filterAPI.cpp:759-782 filter_mapRgbaU8 / filter_generateRgbaU8 with a device op. */
+int dfpsr_filter_map(const dfpsr_image *target, int32_t op, const int32_t *params, int32_t paramCount, const dfpsr_image *source, int32_t startX, int32_t startY, void *stream);
+/* ref: api/filterAPI.cpp:724-757, :872-876 filter_blockMagnify. */
+int dfpsr_filter_block_magnify(const dfpsr_image *target, const dfpsr_image *source, int32_t pixelWidth, int32_t pixelHeight, void *stream);
+
+/* ---------------------------------------------------------------- host-buffer entry points (end to end) */
+
+/* The same operations taking HOST images, as the reference API does: host→device copies, kernels,
+ * device→host copies, stream synchronised on return. Used by the dsr:: shim and by bench.py's e2e leg. */
+typedef struct dfpsr_host_model {
+	const float *points; int32_t pointCount;
+	const dfpsr_polygon *polygons; int32_t polygonCount;
+	int32_t filter;
+	const uint32_t *diffusePixels; /* whole pyramid, layout from dfpsr_texture_layout; may be NULL */
+	dfpsr_texture diffuseLayout;
+	const uint32_t *lightPixels;
+	dfpsr_texture lightLayout;
+	float minBound[3], maxBound[3];
+} dfpsr_host_model;
+
+typedef struct dfpsr_session dfpsr_session;
+/* A session owns device mirrors of host objects so that repeated frames only move what changed. */
+int dfpsr_session_create(dfpsr_session **out);
+int dfpsr_session_destroy(dfpsr_session *session);
+/* Uploads (or re-uploads) a model's geometry and textures; returns a model slot id >= 0 in *slot. */
+int dfpsr_session_upload_model(dfpsr_session *session, const dfpsr_host_model *model, int32_t *slot);
+/* Clears (colour 0, depth 0), renders model `slot` and downloads colour (and depth if depthHost != NULL)
+ * into HOST buffers — one SDK terrain frame (ref: SDK/terrain/main.cpp:397-421). */
+int dfpsr_session_render_frame_host(dfpsr_session *session, int32_t slot, const dfpsr_transform3d *modelToWorld, const dfpsr_camera *camera, uint32_t *colorHost, int32_t colorStride, float *depthHost, int32_t depthStride, int32_t width, int32_t height, int32_t packOrder, int32_t uploadGeometry, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif

@@ -1,0 +1,908 @@
+/*
+ * dfpsr_oracle.c — TEST INFRASTRUCTURE: plain-C restatement of the reference's hot-path algorithm.
+ * See dfpsr_oracle.h for scope and parity status (pinned against the compiled reference).
+ *
+ * Style: straight-line scalar code, one function per reference routine, each citing the reference
+ * file:line it follows (paths relative to /root/reference/Source/DFPSR unless they start with SDK/).
+ * Build with -ffp-contract=off: the reference is built in ISO C++ mode, i.e. without FMA contraction.
+ * Floating point follows the reference's SCALAR flavour (exact 1/x), see SURVEY.md §8c.
+ */
+#include "dfpsr_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <float.h>
+
+typedef struct { float x, y, z; } v3;
+
+static v3 v3_make(float x, float y, float z) { v3 r = {x, y, z}; return r; }
+static v3 v3_from(const float *p) { return v3_make(p[0], p[1], p[2]); }
+static float v3_dot(v3 a, v3 b) { return (a.x * b.x) + (a.y * b.y) + (a.z * b.z); } /* math/FVector.h:74 */
+
+/* math/FVector.h:113-120 */
+static v3 v3_normalize(v3 v) {
+	float l = sqrtf(v.x * v.x + v.y * v.y + v.z * v.z);
+	if (l == 0.0f) { return v3_make(0.0f, 0.0f, 1.0f); }
+	return v3_make(v.x / l, v.y / l, v.z / l);
+}
+
+/* math/FMatrix3x3.h:52-58 */
+static v3 mat_transform(const float *xa, const float *ya, const float *za, v3 p) {
+	return v3_make(
+	  p.x * xa[0] + p.y * ya[0] + p.z * za[0],
+	  p.x * xa[1] + p.y * ya[1] + p.z * za[1],
+	  p.x * xa[2] + p.y * ya[2] + p.z * za[2]);
+}
+/* math/FMatrix3x3.h:63-69 */
+static v3 mat_transform_transposed(const float *xa, const float *ya, const float *za, v3 p) {
+	return v3_make(
+	  p.x * xa[0] + p.y * xa[1] + p.z * xa[2],
+	  p.x * ya[0] + p.y * ya[1] + p.z * ya[2],
+	  p.x * za[0] + p.y * za[1] + p.z * za[2]);
+}
+/* math/Transform3D.h:41-43 */
+static v3 transform_point(const dfpsr_transform3d *t, v3 p) {
+	v3 r = mat_transform(t->xAxis, t->yAxis, t->zAxis, p);
+	return v3_make(r.x + t->position[0], r.y + t->position[1], r.z + t->position[2]);
+}
+/* math/Transform3D.h:50-52 */
+static v3 transform_point_transposed_inverse(const dfpsr_transform3d *t, v3 p) {
+	return mat_transform_transposed(t->xAxis, t->yAxis, t->zAxis, v3_make(p.x - t->position[0], p.y - t->position[1], p.z - t->position[2]));
+}
+
+/* ------------------------------------------------------------------------------------------- camera */
+
+static void set_plane(float *dst, v3 normal, float offset) { /* math/FPlane3D.h:36 */
+	v3 n = v3_normalize(normal);
+	dst[0] = n.x; dst[1] = n.y; dst[2] = n.z; dst[3] = offset;
+}
+
+/* implementation/render/Camera.h:56-72 */
+static int frustum_perspective(float planes[6][4], float nearClip, float farClip, float widthSlope, float heightSlope) {
+	set_plane(planes[0], v3_make(-1.0f, 0.0f, -widthSlope), 0.0f);
+	set_plane(planes[1], v3_make(1.0f, 0.0f, -widthSlope), 0.0f);
+	set_plane(planes[2], v3_make(0.0f, 1.0f, -heightSlope), 0.0f);
+	set_plane(planes[3], v3_make(0.0f, -1.0f, -heightSlope), 0.0f);
+	set_plane(planes[4], v3_make(0.0f, 0.0f, -1.0f), -nearClip);
+	set_plane(planes[5], v3_make(0.0f, 0.0f, 1.0f), farClip);
+	return farClip == INFINITY ? 5 : 6;
+}
+/* implementation/render/Camera.h:47-55 */
+static int frustum_orthogonal(float planes[6][4], float halfWidth, float halfHeight) {
+	set_plane(planes[0], v3_make(-1.0f, 0.0f, 0.0f), halfWidth);
+	set_plane(planes[1], v3_make(1.0f, 0.0f, 0.0f), halfWidth);
+	set_plane(planes[2], v3_make(0.0f, 1.0f, 0.0f), halfHeight);
+	set_plane(planes[3], v3_make(0.0f, -1.0f, 0.0f), halfHeight);
+	return 4;
+}
+
+/* implementation/render/Camera.h:113-156 */
+void orc_camera_create(dfpsr_camera *c) {
+	const float cullRatio = 1.0001f, clipRatio = 2.0f;
+	memset(c->cullPlanes, 0, sizeof(c->cullPlanes));
+	memset(c->clipPlanes, 0, sizeof(c->clipPlanes));
+	if (c->perspective) {
+		float widthSlope = c->widthSlope;
+		float heightSlope = widthSlope * c->imageHeight / c->imageWidth;
+		c->heightSlope = heightSlope;
+		c->cullPlaneCount = frustum_perspective(c->cullPlanes, c->nearClip, c->farClip, widthSlope * cullRatio, heightSlope * cullRatio);
+		c->clipPlaneCount = frustum_perspective(c->clipPlanes, c->nearClip, c->farClip, widthSlope * clipRatio, heightSlope * clipRatio);
+	} else {
+		float halfWidth = c->widthSlope;
+		float halfHeight = halfWidth * c->imageHeight / c->imageWidth;
+		c->heightSlope = halfHeight;
+		c->nearClip = -FLT_MAX;
+		c->farClip = INFINITY;
+		c->cullPlaneCount = frustum_orthogonal(c->cullPlanes, halfWidth * cullRatio, halfHeight * cullRatio);
+		c->clipPlaneCount = frustum_orthogonal(c->clipPlanes, halfWidth * clipRatio, halfHeight * clipRatio);
+	}
+	c->invWidthSlope = 0.5f / c->widthSlope;
+	c->invHeightSlope = 0.5f / c->heightSlope;
+}
+
+typedef struct { v3 cs; float isx, isy; int64_t fx, fy; } ppoint;
+
+/* implementation/render/Camera.h:160-187 */
+static ppoint camera_to_screen(const dfpsr_camera *c, v3 cs) {
+	ppoint r;
+	r.cs = cs;
+	if (c->perspective) {
+		float invDepth;
+		if (cs.z > 0.0f) { invDepth = 1.0f / cs.z; } else { invDepth = 0.0f; }
+		float centerShear = cs.z * 0.5f;
+		float preX = (cs.x * c->invWidthSlope + centerShear) * c->imageWidth;
+		float preY = (-cs.y * c->invHeightSlope + centerShear) * c->imageHeight;
+		r.isx = preX * invDepth;
+		r.isy = preY * invDepth;
+	} else {
+		r.isx = (cs.x * c->invWidthSlope + 0.5f) * c->imageWidth;
+		r.isy = (-cs.y * c->invHeightSlope + 0.5f) * c->imageHeight;
+	}
+	float subX = r.isx * 256.0f, subY = r.isy * 256.0f; /* constants.h:40 unitsPerPixel */
+	r.fx = (int64_t)subX;
+	r.fy = (int64_t)subY;
+	return r;
+}
+
+static ppoint world_to_screen(const dfpsr_camera *c, v3 world) { /* Camera.h:157, :188 */
+	return camera_to_screen(c, transform_point_transposed_inverse(&c->location, world));
+}
+
+static int plane_inside(const float *plane, v3 p) { /* math/FPlane3D.h:39-45 */
+	return (v3_dot(v3_from(plane), p) - plane[3]) <= 0.0f;
+}
+
+/* implementation/render/Camera.h:73-95 + :202-217 */
+int orc_camera_is_box_seen(const dfpsr_camera *c, const float *mn, const float *mx, const dfpsr_transform3d *m2w) {
+	v3 corners[8];
+	for (int i = 0; i < 8; i++) {
+		v3 p = v3_make((i & 1) ? mx[0] : mn[0], (i & 2) ? mx[1] : mn[1], (i & 4) ? mx[2] : mn[2]);
+		corners[i] = transform_point_transposed_inverse(&c->location, transform_point(m2w, p));
+	}
+	int anyOutside = 0;
+	for (int s = 0; s < c->cullPlaneCount; s++) {
+		int anyInside = 0;
+		for (int p = 0; p < 8; p++) {
+			if (plane_inside(c->cullPlanes[s], corners[p])) { anyInside = 1; } else { anyOutside = 1; }
+		}
+		if (!anyInside) { return 0; }
+	}
+	return anyOutside ? 1 : 2;
+}
+
+static void ppoint_export(dfpsr_projected_point *o, const ppoint *p) {
+	o->cs[0] = p->cs.x; o->cs[1] = p->cs.y; o->cs[2] = p->cs.z;
+	o->is[0] = p->isx; o->is[1] = p->isy; o->pad_ = 0;
+	o->flat[0] = p->fx; o->flat[1] = p->fy;
+}
+static ppoint ppoint_import(const dfpsr_projected_point *p) {
+	ppoint r;
+	r.cs = v3_from(p->cs); r.isx = p->is[0]; r.isy = p->is[1]; r.fx = p->flat[0]; r.fy = p->flat[1];
+	return r;
+}
+
+/* api/modelAPI.cpp:238-242 */
+void orc_project_points(const float *points, int32_t count, const dfpsr_transform3d *m2w, const dfpsr_camera *camera, dfpsr_projected_point *out) {
+	for (int32_t i = 0; i < count; i++) {
+		ppoint p = world_to_screen(camera, transform_point(m2w, v3_from(points + 3 * i)));
+		ppoint_export(out + i, &p);
+	}
+}
+
+/* ------------------------------------------------------------------------------------------- textures */
+
+/* api/textureAPI.cpp:30-41 */
+static uint32_t find_log2_size(uint32_t size) {
+	for (uint32_t l = 0; l < 15; l++) { if ((1u << l) >= size) { return l; } }
+	return 15;
+}
+
+/* api/textureAPI.cpp:65-78 + implementation/image/Texture.h:63-102 */
+void orc_texture_layout(dfpsr_texture *out, int32_t width, int32_t height, int32_t resolutions) {
+	uint32_t log2w = find_log2_size((uint32_t)width), log2h = find_log2_size((uint32_t)height);
+	uint32_t maxMip = (uint32_t)(resolutions - 1);
+	if (maxMip > log2w) { maxMip = log2w; }
+	if (maxMip > log2h) { maxMip = log2h; }
+	if (maxMip > 15) { maxMip = 15; }
+	uint32_t highest = 1u << (log2w + log2h);
+	uint64_t pixelCount = 0;
+	uint32_t levelCount = highest;
+	for (int32_t level = (int32_t)maxMip; level >= 0; level--) { pixelCount |= levelCount; levelCount >>= 2; }
+	out->data = NULL;
+	out->log2width = log2w; out->log2height = log2h; out->maxMipLevel = maxMip;
+	out->startOffset = (uint32_t)pixelCount & ~highest;
+	out->maxLevelMask = highest - 1;
+	out->totalPixels = (uint32_t)pixelCount;
+}
+
+static uint32_t tex_layer_offset(const dfpsr_texture *t, uint32_t mip) { /* api/textureAPI.h:79-85 */
+	return t->startOffset & (t->maxLevelMask >> (2 * mip));
+}
+
+/* api/textureAPI.cpp:44-87 */
+void orc_texture_generate_pyramid(uint32_t *px, const dfpsr_texture *t) {
+	for (uint32_t level = 1; level <= t->maxMipLevel; level++) {
+		uint32_t tw = 1u << (t->log2width - level), th = 1u << (t->log2height - level);
+		const uint32_t *src = px + tex_layer_offset(t, level - 1);
+		uint32_t *dst = px + tex_layer_offset(t, level);
+		uint32_t sw = tw * 2;
+		for (uint32_t y = 0; y < th; y++) {
+			for (uint32_t x = 0; x < tw; x++) {
+				uint32_t a = src[(2 * y) * sw + 2 * x], b = src[(2 * y) * sw + 2 * x + 1];
+				uint32_t c = src[(2 * y + 1) * sw + 2 * x], d = src[(2 * y + 1) * sw + 2 * x + 1];
+				uint32_t out = 0;
+				for (int s = 0; s < 32; s += 8) {
+					out |= ((((a >> s) & 255u) + ((b >> s) & 255u) + ((c >> s) & 255u) + ((d >> s) & 255u)) / 4u) << s;
+				}
+				dst[y * tw + x] = out;
+			}
+		}
+	}
+}
+
+/* api/textureAPI.h:253-263 weightColors, on 16-bit lane pairs */
+static uint32_t weight_colors(uint32_t colorA, uint32_t weightA, uint32_t colorB, uint32_t weightB) {
+	uint32_t lowA = colorA & 0x00FF00FFu, lowB = colorB & 0x00FF00FFu;
+	uint32_t highA = (colorA & 0xFF00FF00u) >> 8, highB = (colorB & 0xFF00FF00u) >> 8;
+	/* 16-bit lanes: products <= 255 * 256 so the two lanes never carry into each other */
+	uint32_t low = (((lowA & 0xFFFFu) * weightA + (lowB & 0xFFFFu) * weightB) & 0xFFFFu)
+	             | (((((lowA >> 16) * weightA + (lowB >> 16) * weightB)) & 0xFFFFu) << 16);
+	uint32_t high = (((highA & 0xFFFFu) * weightA + (highB & 0xFFFFu) * weightB) & 0xFFFFu)
+	              | (((((highA >> 16) * weightA + (highB >> 16) * weightB)) & 0xFFFFu) << 16);
+	return ((low >> 8) & 0x00FF00FFu) | (high & 0xFF00FF00u);
+}
+
+/* api/textureAPI.h:342-438 texture_sample_bilinear<SQUARE=false, SINGLE_LAYER, MIP_INSIDE=true, HIGHEST_RESOLUTION> */
+static uint32_t tex_sample_bilinear(const dfpsr_texture *t, float u, float v, uint32_t mip) {
+	uint32_t scaleU = (256u << t->log2width) >> mip;
+	uint32_t scaleV = (256u << t->log2height) >> mip;
+	uint32_t subX = (uint32_t)((u + 256.0f) * (float)scaleU) - 128u;
+	uint32_t subY = (uint32_t)((v + 256.0f) * (float)scaleV) - 128u;
+	uint32_t wx = subX & 0xFF, wy = subY & 0xFF;
+	uint32_t left = subX >> 8, top = subY >> 8;
+	uint32_t maskX = ((1u << t->log2width) - 1u) >> mip, maskY = ((1u << t->log2height) - 1u) >> mip;
+	uint32_t right = (left + 1) & maskX, bottom = (top + 1) & maskY;
+	left &= maskX; top &= maskY;
+	uint32_t log2Stride = t->log2width - mip;
+	const uint32_t *data = t->data + tex_layer_offset(t, mip);
+	uint32_t c00 = data[(top << log2Stride) | left], c10 = data[(top << log2Stride) | right];
+	uint32_t c01 = data[(bottom << log2Stride) | left], c11 = data[(bottom << log2Stride) | right];
+	/* api/textureAPI.h:315-326 texture_interpolate_color_bilinear */
+	uint32_t upper = weight_colors(c00, 256u - wx, c10, wx);
+	uint32_t lower = weight_colors(c01, 256u - wx, c11, wx);
+	return weight_colors(upper, 256u - wy, lower, wy);
+}
+
+/* api/textureAPI.h:472-495: one level per quad from lanes 0, 1, 2 */
+static uint32_t tex_mip_level(const dfpsr_texture *t, const float *u, const float *v) {
+	float offsetUX = fabsf(u[0] - u[1]), offsetUY = fabsf(u[0] - u[2]);
+	float offsetVX = fabsf(v[0] - v[1]), offsetVY = fabsf(v[0] - v[2]);
+	float offsetU = (offsetUX > offsetUY ? offsetUX : offsetUY) * (float)(1u << t->log2width);
+	float offsetV = (offsetVX > offsetVY ? offsetVX : offsetVY) * (float)(1u << t->log2height);
+	float offset = offsetU > offsetV ? offsetU : offsetV;
+	uint32_t result = 0;
+	if (offset > 2.0f) { result = 1; }
+	if (offset > 4.0f) { result = 2; }
+	if (offset > 8.0f) { result = 3; }
+	if (offset > 16.0f) { result = 4; }
+	if (result > t->maxMipLevel) { result = t->maxMipLevel; }
+	return result;
+}
+
+/* ------------------------------------------------------------------------------------------- triangle set-up */
+
+typedef struct { int32_t l, t, w, h; } irect;
+static irect irect_make(int32_t l, int32_t t, int32_t w, int32_t h) { irect r = {l, t, w, h}; return r; }
+static int irect_overlaps(irect a, irect b) { /* math/IRect.h:77 */
+	return a.l < b.l + b.w && a.l + a.w > b.l && a.t < b.t + b.h && a.t + a.h > b.t;
+}
+static int32_t imin(int32_t a, int32_t b) { return a < b ? a : b; }
+static int32_t imax(int32_t a, int32_t b) { return a > b ? a : b; }
+static irect irect_cut(irect a, irect b) { /* math/IRect.h:56-66 */
+	if (!irect_overlaps(a, b)) { return irect_make(0, 0, 0, 0); }
+	int32_t l = imax(a.l, b.l), t = imax(a.t, b.t), r = imin(a.l + a.w, b.l + b.w), bo = imin(a.t + a.h, b.t + b.h);
+	return irect_make(l, t, r - l, bo - t);
+}
+
+/* implementation/render/ITriangle2D.cpp:31-43 */
+static irect triangle_bound(const ppoint *p) {
+	int32_t rx[3], ry[3];
+	for (int i = 0; i < 3; i++) {
+		rx[i] = (int32_t)((p[i].fx + 128) / 256);
+		ry[i] = (int32_t)((p[i].fy + 128) / 256);
+	}
+	int32_t l = imin(rx[0], imin(rx[1], rx[2])) - 1, t = imin(ry[0], imin(ry[1], ry[2])) - 1;
+	int32_t r = imax(rx[0], imax(rx[1], rx[2])) + 1, b = imax(ry[0], imax(ry[1], ry[2])) + 1;
+	return irect_make(l, t, r - l, b - t);
+}
+
+/* implementation/render/ITriangle2D.cpp:55-60 */
+static int is_frontfacing(const ppoint *p) {
+	return ((p[2].fx - p[0].fx) * (p[1].fy - p[0].fy)) + ((p[2].fy - p[0].fy) * (p[0].fx - p[1].fx)) < 0;
+}
+
+typedef struct { int32_t left, right; } row_interval;
+
+/* implementation/render/ITriangle2D.cpp:86-150 cutConvexEdge, one row at a time in closed form
+ * (limit is decremented by offsetY once per row there; the int64 arithmetic is exact so this is identical). */
+static void cut_convex_edge(int64_t sx, int64_t sy, int64_t ex, int64_t ey, row_interval *rows, irect bound) {
+	int32_t leftBound = bound.l, topBound = bound.t, rightBound = bound.l + bound.w, bottomBound = bound.t + bound.h;
+	int64_t originX = 128 + (int64_t)bound.l * 256;
+	int64_t originY = 128 + (int64_t)bound.t * 256;
+	int64_t threshold = (sx > ex || (sx == ex && sy > ey)) ? -1 : 0;
+	int64_t normalX = ey - sy, normalY = sx - ex;
+	int64_t offsetX = normalX * 256, offsetY = normalY * 256;
+	int64_t valueOrigin = ((originX - sx) * normalX) + ((originY - sy) * normalY);
+	if (normalX != 0) {
+		int64_t limit0 = threshold - valueOrigin + (offsetX * leftBound);
+		for (int32_t y = topBound; y < bottomBound; y++) {
+			int64_t limit = limit0 - offsetY * (int64_t)(y - topBound);
+			if (normalX < 0) {
+				int32_t leftSide = imin(imax(leftBound, (int32_t)((limit + 1) / offsetX + 1)), rightBound);
+				rows[y - topBound].left = imax(rows[y - topBound].left, leftSide);
+			} else {
+				int32_t rightSide = imin(imax(leftBound, (int32_t)(limit / offsetX + 1)), rightBound);
+				rows[y - topBound].right = imin(rows[y - topBound].right, rightSide);
+			}
+		}
+	} else if (normalY != 0) {
+		for (int32_t y = topBound; y < bottomBound; y++) {
+			int64_t valueRow = valueOrigin + offsetY * (int64_t)(y - topBound);
+			if (valueRow > threshold) {
+				rows[y - topBound].left = rightBound;
+				rows[y - topBound].right = leftBound;
+			}
+		}
+	}
+}
+
+/* implementation/render/ITriangle2D.cpp:152-169 */
+static void rasterize_triangle(const ppoint *p, row_interval *rows, irect bound) {
+	int degenerate = (p[0].fx == p[1].fx && p[0].fy == p[1].fy) || (p[1].fx == p[2].fx && p[1].fy == p[2].fy) || (p[2].fx == p[0].fx && p[2].fy == p[0].fy);
+	for (int32_t r = 0; r < bound.h; r++) {
+		rows[r].left = degenerate ? bound.l + bound.w : bound.l;
+		rows[r].right = degenerate ? bound.l : bound.l + bound.w;
+	}
+	if (!degenerate) {
+		for (int i = 0; i < 3; i++) {
+			int j = (i + 1) % 3;
+			cut_convex_edge(p[i].fx, p[i].fy, p[j].fx, p[j].fy, rows, bound);
+		}
+	}
+}
+
+typedef struct { int affine; float start[3], dx[3], dy[3]; } projection;
+
+/* implementation/render/ITriangle2D.cpp:182-300 */
+static projection get_projection(const ppoint *p, const float *subB, const float *subC, int perspective) {
+	float offsetX[3], offsetY[3], mult[3], normalX[3], normalY[3], targetWeight[3];
+	for (int i = 0; i < 3; i++) {
+		int j = (i + 1) % 3;
+		offsetX[i] = p[j].isy - p[i].isy;
+		offsetY[i] = p[i].isx - p[j].isx;
+	}
+	for (int i = 0; i < 3; i++) {
+		int o = (i + 2) % 3;
+		float other = ((p[o].isx - p[i].isx) * offsetX[i]) + ((p[o].isy - p[i].isy) * offsetY[i]);
+		mult[o] = (other == 0.0f) ? 0.0f : 1.0f / other;
+	}
+	for (int i = 0; i < 3; i++) {
+		normalX[i] = offsetX[i] * mult[i];
+		normalY[i] = offsetY[i] * mult[i];
+	}
+	for (int i = 0; i < 3; i++) {
+		int o = (i + 2) % 3;
+		targetWeight[o] = p[i].isx * -normalX[i] + p[i].isy * -normalY[i];
+	}
+	float adx[3] = {normalX[1], normalX[2], normalX[0]};
+	float ady[3] = {normalY[1], normalY[2], normalY[0]};
+	projection r;
+	if (!perspective) {
+		float W[3] = {p[0].cs.z, p[1].cs.z, p[2].cs.z};
+		r.affine = 1;
+		r.start[0] = W[0] * targetWeight[0] + W[1] * targetWeight[1] + W[2] * targetWeight[2];
+		r.start[1] = targetWeight[0] * subB[0] + targetWeight[1] * subB[1] + targetWeight[2] * subB[2];
+		r.start[2] = targetWeight[0] * subC[0] + targetWeight[1] * subC[1] + targetWeight[2] * subC[2];
+		r.dx[0] = W[0] * adx[0] + W[1] * adx[1] + W[2] * adx[2];
+		r.dx[1] = adx[0] * subB[0] + adx[1] * subB[1] + adx[2] * subB[2];
+		r.dx[2] = adx[0] * subC[0] + adx[1] * subC[1] + adx[2] * subC[2];
+		r.dy[0] = W[0] * ady[0] + W[1] * ady[1] + W[2] * ady[2];
+		r.dy[1] = ady[0] * subB[0] + ady[1] * subB[1] + ady[2] * subB[2];
+		r.dy[2] = ady[0] * subC[0] + ady[1] * subC[1] + ady[2] * subC[2];
+	} else {
+		float IW[3] = {1.0f / p[0].cs.z, 1.0f / p[1].cs.z, 1.0f / p[2].cs.z};
+		r.affine = 0;
+		r.start[0] = IW[0] * targetWeight[0] + IW[1] * targetWeight[1] + IW[2] * targetWeight[2];
+		r.start[1] = IW[0] * targetWeight[0] * subB[0] + IW[1] * targetWeight[1] * subB[1] + IW[2] * targetWeight[2] * subB[2];
+		r.start[2] = IW[0] * targetWeight[0] * subC[0] + IW[1] * targetWeight[1] * subC[1] + IW[2] * targetWeight[2] * subC[2];
+		r.dx[0] = IW[0] * adx[0] + IW[1] * adx[1] + IW[2] * adx[2];
+		r.dx[1] = IW[0] * adx[0] * subB[0] + IW[1] * adx[1] * subB[1] + IW[2] * adx[2] * subB[2];
+		r.dx[2] = IW[0] * adx[0] * subC[0] + IW[1] * adx[1] * subC[1] + IW[2] * adx[2] * subC[2];
+		r.dy[0] = IW[0] * ady[0] + IW[1] * ady[1] + IW[2] * ady[2];
+		r.dy[1] = IW[0] * ady[0] * subB[0] + IW[1] * ady[1] * subB[1] + IW[2] * ady[2] * subB[2];
+		r.dy[2] = IW[0] * ady[0] * subC[0] + IW[1] * ady[1] * subC[1] + IW[2] * ady[2] * subC[2];
+	}
+	return r;
+}
+
+/* implementation/render/ITriangle2D.h:82-100: start + dx * (x + 0.5) + dy * (y + 0.5), left to right */
+static void projection_at(const projection *p, int32_t x, int32_t y, float *out) {
+	float fx = (float)x + 0.5f, fy = (float)y + 0.5f;
+	for (int k = 0; k < 3; k++) { out[k] = p->start[k] + (p->dx[k] * fx) + (p->dy[k] * fy); }
+}
+
+/* ------------------------------------------------------------------------------------------- shader */
+
+typedef struct {
+	int hasDiffuse, hasLight, hasFade, colorless;
+	float red[3], green[3], blue[3], alpha[3]; /* already scaled, shader/RgbaMultiply.h:45-60 */
+	float u1[3], v1[3], u2[3], v2[3];
+	const dfpsr_texture *diffuse, *light;
+} shader_data;
+
+static int almost_zero(float v) { return v > -0.001f && v < 0.001f; } /* shader/fillerTemplates.h:37 */
+static int almost_one(float v) { return v > 0.999f && v < 1.001f; }
+static int almost_zero3(const float *c) { return almost_zero(c[0]) && almost_zero(c[1]) && almost_zero(c[2]); }
+static int almost_one3(const float *c) { return almost_one(c[0]) && almost_one(c[1]) && almost_one(c[2]); }
+static int almost_same3(const float *c) { return almost_zero(c[0] - c[1]) && almost_zero(c[0] - c[2]) && almost_zero(c[1] - c[2]); }
+
+/* shader/RgbaMultiply.h:37-60, :110-116. colors/texCoords are [corner][channel]. */
+static void shader_setup(shader_data *s, const float colors[3][4], const float tex[3][4], const dfpsr_texture *diffuse, const dfpsr_texture *light) {
+	s->diffuse = diffuse; s->light = light;
+	s->hasDiffuse = diffuse != NULL && diffuse->data != NULL;
+	s->hasLight = light != NULL && light->data != NULL;
+	float scale = 255.0f;
+	if (s->hasDiffuse) { scale *= 1.0f / 255.0f; }
+	if (s->hasLight) { scale *= 1.0f / 255.0f; }
+	for (int c = 0; c < 3; c++) {
+		s->red[c] = colors[c][0] * scale; s->green[c] = colors[c][1] * scale;
+		s->blue[c] = colors[c][2] * scale; s->alpha[c] = colors[c][3] * scale;
+		s->u1[c] = tex[c][0]; s->v1[c] = tex[c][1]; s->u2[c] = tex[c][2]; s->v2[c] = tex[c][3];
+	}
+	s->hasFade = !(almost_same3(s->red) && almost_same3(s->green) && almost_same3(s->blue) && almost_same3(s->alpha));
+	s->colorless = almost_one3(s->red) && almost_one3(s->green) && almost_one3(s->blue) && almost_one3(s->alpha);
+}
+
+/* shader/shaderMethods.h:39-44 */
+static float interpolate(const float *d, float wa, float wb, float wc) {
+	return d[0] * wa + d[1] * wb + d[2] * wc;
+}
+
+static void unpack_rgba(uint32_t c, float *r, float *g, float *b, float *a) { /* shader/shaderTypes.h:39-43 */
+	*r = (float)(c & 255u); *g = (float)((c >> 8) & 255u); *b = (float)((c >> 16) & 255u); *a = (float)(c >> 24);
+}
+
+static void sample_quad(const dfpsr_texture *t, int highestResolution, const float *cu, const float *cv, const float *wa, const float *wb, const float *wc, float out[4][4]) {
+	float u[4], v[4];
+	for (int l = 0; l < 4; l++) { u[l] = interpolate(cu, wa[l], wb[l], wc[l]); v[l] = interpolate(cv, wa[l], wb[l], wc[l]); }
+	uint32_t mip = highestResolution ? 0u : tex_mip_level(t, u, v); /* shader/shaderMethods.h:63-83 */
+	for (int l = 0; l < 4; l++) {
+		uint32_t c = tex_sample_bilinear(t, u[l], v[l], mip);
+		unpack_rgba(c, &out[l][0], &out[l][1], &out[l][2], &out[l][3]);
+	}
+}
+
+/* shader/RgbaMultiply.h:75-106 getPixels_2x2; out[lane][r,g,b,a] */
+static void shade_quad(const shader_data *s, const float *wa, const float *wb, const float *wc, float out[4][4]) {
+	if (s->hasDiffuse && !s->hasLight && s->colorless && !s->hasFade) {
+		sample_quad(s->diffuse, 0, s->u1, s->v1, wa, wb, wc, out);
+	} else if (s->hasLight && !s->hasDiffuse && s->colorless && !s->hasFade) {
+		sample_quad(s->light, 1, s->u2, s->v2, wa, wb, wc, out);
+	} else {
+		for (int l = 0; l < 4; l++) {
+			if (s->hasFade) {
+				out[l][0] = interpolate(s->red, wa[l], wb[l], wc[l]);
+				out[l][1] = interpolate(s->green, wa[l], wb[l], wc[l]);
+				out[l][2] = interpolate(s->blue, wa[l], wb[l], wc[l]);
+				out[l][3] = interpolate(s->alpha, wa[l], wb[l], wc[l]);
+			} else {
+				out[l][0] = s->red[0]; out[l][1] = s->green[0]; out[l][2] = s->blue[0]; out[l][3] = s->alpha[0];
+			}
+		}
+		float sampled[4][4];
+		if (s->hasDiffuse) {
+			sample_quad(s->diffuse, 0, s->u1, s->v1, wa, wb, wc, sampled);
+			for (int l = 0; l < 4; l++) { for (int c = 0; c < 4; c++) { out[l][c] = out[l][c] * sampled[l][c]; } }
+		}
+		if (s->hasLight) {
+			sample_quad(s->light, 1, s->u2, s->v2, wa, wb, wc, sampled);
+			for (int l = 0; l < 4; l++) { for (int c = 0; c < 4; c++) { out[l][c] = out[l][c] * sampled[l][c]; } }
+		}
+	}
+}
+
+static const int packIndex[4][4] = { /* implementation/image/PackOrder.h:85-96: byte index of r, g, b, a */
+	{0, 1, 2, 3}, {2, 1, 0, 3}, {1, 2, 3, 0}, {3, 2, 1, 0}
+};
+
+static uint32_t saturated_byte(float v) { /* PackOrder.h:186-197: clampUpper 255.1 then truncate */
+	float c = v < 255.1f ? v : 255.1f;
+	return (uint32_t)c;
+}
+
+static uint32_t pack_float_color(const float *rgba, int order) { /* PackOrder.h:204-213 */
+	const int *ix = packIndex[order];
+	return (saturated_byte(rgba[0]) << (8 * ix[0])) | (saturated_byte(rgba[1]) << (8 * ix[1]))
+	     | (saturated_byte(rgba[2]) << (8 * ix[2])) | (saturated_byte(rgba[3]) << (8 * ix[3]));
+}
+
+static void unpack_ordered(uint32_t c, int order, float *rgba) { /* shader/shaderTypes.h:44-48 */
+	const int *ix = packIndex[order];
+	for (int k = 0; k < 4; k++) { rgba[k] = (float)((c >> (8 * ix[k])) & 255u); }
+}
+
+/* ------------------------------------------------------------------------------------------- fill */
+
+typedef struct {
+	const dfpsr_image *color, *depth; /* either may be NULL */
+	int colorWrite, depthRead, depthWrite, alphaFilter, affine;
+	int32_t maxHeight;
+} fill_mode;
+
+static uint32_t *color_px(const dfpsr_image *im, int32_t x, int32_t y) { return (uint32_t*)((uint8_t*)im->data + (size_t)y * im->stride) + x; }
+static float *depth_px(const dfpsr_image *im, int32_t x, int32_t y) { return (float*)((uint8_t*)im->data + (size_t)y * im->stride) + x; }
+
+/* shader/fillerTemplates.h:139-187 fillQuadSuper + :190-244 fillRowSuper body for ONE quad.
+ * upper/lower: the running (depth, B, C) plane values for lane 0 and lane 2; lanes 1 and 3 are +dx. */
+static void fill_quad(const fill_mode *m, const shader_data *s, int clipSides, int32_t x, int32_t y1, const float *lanes /* [3][4] */, row_interval upperRow, row_interval lowerRow) {
+	int32_t y2 = y1 + 1;
+	int32_t px[4] = {x, x + 1, x, x + 1};
+	int32_t py[4] = {y1, y1, y2, y2};
+	float depth[4], wa[4], wb[4], wc[4];
+	for (int l = 0; l < 4; l++) {
+		depth[l] = lanes[0 * 4 + l];
+		if (m->affine) {
+			wb[l] = lanes[1 * 4 + l];
+			wc[l] = lanes[2 * 4 + l];
+		} else {
+			float linearDepth = 1.0f / lanes[0 * 4 + l]; /* scalar-flavour reciprocal, base/simd.h:4064-4067 */
+			wb[l] = lanes[1 * 4 + l] * linearDepth;
+			wc[l] = lanes[2 * 4 + l] * linearDepth;
+		}
+		wa[l] = 1.0f - (wb[l] + wc[l]);
+	}
+	/* fillerTemplates.h:93-138 */
+	int vis[4];
+	for (int l = 0; l < 4; l++) {
+		int clip = 1;
+		if (clipSides) {
+			row_interval row = (l < 2) ? upperRow : lowerRow;
+			clip = px[l] >= row.left && px[l] < row.right;
+		}
+		int front = 1;
+		if (m->depthRead) {
+			if (clipSides && !clip) { front = 0; }
+			else {
+				float old = *depth_px(m->depth, px[l], py[l]);
+				front = m->affine ? (depth[l] < old) : (depth[l] > old);
+			}
+		}
+		vis[l] = clip && front;
+	}
+	if (!(vis[0] || vis[1] || vis[2] || vis[3])) { return; }
+	if (m->colorWrite) {
+		float colors[4][4];
+		shade_quad(s, wa, wb, wc, colors);
+		int order = m->color->packOrder;
+		for (int l = 0; l < 4; l++) {
+			if (m->alphaFilter) {
+				float opacity = colors[l][3] * (1.0f / 255.0f);
+				/* clippedRead: lanes that are not visible read 0 when clipping sides; inner quads read all four */
+				uint32_t target = (vis[l] || !clipSides) ? *color_px(m->color, px[l], py[l]) : 0u;
+				float dst[4];
+				unpack_ordered(target, order, dst);
+				float inv = 1.0f - opacity;
+				for (int c = 0; c < 4; c++) { colors[l][c] = (colors[l][c] * opacity) + (dst[c] * inv); }
+			}
+			if (vis[l]) { *color_px(m->color, px[l], py[l]) = pack_float_color(colors[l], order); }
+		}
+	}
+	if (m->depthWrite) {
+		for (int l = 0; l < 4; l++) { if (vis[l]) { *depth_px(m->depth, px[l], py[l]) = depth[l]; } }
+	}
+}
+
+static uint32_t round_up_even(uint32_t x) { return (x + 1u) & ~1u; }
+static uint32_t round_down_even(uint32_t x) { return x & ~1u; }
+
+/* shader/fillerTemplates.h:247-385 fillShapeSuper */
+static void fill_shape(const fill_mode *m, const shader_data *s, const projection *proj, int32_t startRow, int32_t rowCount, const row_interval *rows) {
+	float dx2[3] = {proj->dx[0] * 2.0f, proj->dx[1] * 2.0f, proj->dx[2] * 2.0f};
+	for (int32_t y1 = startRow; y1 < startRow + rowCount; y1 += 2) {
+		int32_t y2 = y1 + 1;
+		row_interval upperRow = rows[y1 - startRow], lowerRow = rows[y2 - startRow];
+		int32_t outerStart = imin(upperRow.left, lowerRow.left), outerEnd = imax(upperRow.right, lowerRow.right);
+		int32_t innerStart = imax(upperRow.left, lowerRow.left), innerEnd = imin(upperRow.right, lowerRow.right);
+		int32_t outerBlockStart = (int32_t)round_down_even((uint32_t)outerStart), outerBlockEnd = (int32_t)round_up_even((uint32_t)outerEnd);
+		int32_t innerBlockStart = (int32_t)round_up_even((uint32_t)innerStart), innerBlockEnd = (int32_t)round_down_even((uint32_t)innerEnd);
+		if (y2 >= m->maxHeight) { lowerRow.right = lowerRow.left; }
+		int hasTop = upperRow.right > upperRow.left, hasBottom = lowerRow.right > lowerRow.left;
+		if (!(hasTop || hasBottom)) { continue; }
+		float upper[3], lower[3];
+		projection_at(proj, outerBlockStart, y1, upper);
+		for (int k = 0; k < 3; k++) { lower[k] = upper[k] + proj->dy[k]; }
+		float lanes[12];
+		if (innerBlockEnd <= innerBlockStart) {
+			for (int32_t x = outerBlockStart; x < outerBlockEnd; x += 2) {
+				for (int k = 0; k < 3; k++) { lanes[k * 4 + 0] = upper[k]; lanes[k * 4 + 1] = upper[k] + proj->dx[k]; lanes[k * 4 + 2] = lower[k]; lanes[k * 4 + 3] = lower[k] + proj->dx[k]; }
+				fill_quad(m, s, 1, x, y1, lanes, upperRow, lowerRow);
+				for (int k = 0; k < 3; k++) { upper[k] = upper[k] + dx2[k]; lower[k] = lower[k] + dx2[k]; }
+			}
+		} else {
+			for (int32_t x = outerBlockStart; x < innerBlockStart; x += 2) {
+				for (int k = 0; k < 3; k++) { lanes[k * 4 + 0] = upper[k]; lanes[k * 4 + 1] = upper[k] + proj->dx[k]; lanes[k * 4 + 2] = lower[k]; lanes[k * 4 + 3] = lower[k] + proj->dx[k]; }
+				fill_quad(m, s, 1, x, y1, lanes, upperRow, lowerRow);
+				for (int k = 0; k < 3; k++) { upper[k] = upper[k] + dx2[k]; lower[k] = lower[k] + dx2[k]; }
+			}
+			/* full quads: the four lanes advance independently by repeated addition (fillRowSuper) */
+			int32_t quadCount = (innerBlockEnd - innerBlockStart) / 2;
+			for (int k = 0; k < 3; k++) { lanes[k * 4 + 0] = upper[k]; lanes[k * 4 + 1] = upper[k] + proj->dx[k]; lanes[k * 4 + 2] = lower[k]; lanes[k * 4 + 3] = lower[k] + proj->dx[k]; }
+			for (int32_t x = innerBlockStart; x < innerBlockEnd; x += 2) {
+				fill_quad(m, s, 0, x, y1, lanes, upperRow, lowerRow);
+				for (int k = 0; k < 3; k++) { for (int l = 0; l < 4; l++) { lanes[k * 4 + l] = lanes[k * 4 + l] + dx2[k]; } }
+			}
+			for (int k = 0; k < 3; k++) { upper[k] = upper[k] + (dx2[k] * (float)quadCount); lower[k] = lower[k] + (dx2[k] * (float)quadCount); }
+			for (int32_t x = innerBlockEnd; x < outerBlockEnd; x += 2) {
+				for (int k = 0; k < 3; k++) { lanes[k * 4 + 0] = upper[k]; lanes[k * 4 + 1] = upper[k] + proj->dx[k]; lanes[k * 4 + 2] = lower[k]; lanes[k * 4 + 3] = lower[k] + proj->dx[k]; }
+				fill_quad(m, s, 1, x, y1, lanes, upperRow, lowerRow);
+				for (int k = 0; k < 3; k++) { upper[k] = upper[k] + dx2[k]; lower[k] = lower[k] + dx2[k]; }
+			}
+		}
+	}
+}
+
+typedef struct {
+	const dfpsr_image *color, *depth;
+	int32_t width, height;
+	const dfpsr_camera *camera;
+	int filter;
+	shader_data shader;
+	int64_t commands;
+} draw_context;
+
+/* implementation/render/renderCore.cpp:203-217 executeTriangleDrawing + shader/fillerTemplates.h:387-441 fillShape */
+static void execute_triangle(draw_context *ctx, const ppoint *p, const float *subB, const float *subC) {
+	ctx->commands++;
+	irect clip = irect_make(0, 0, ctx->width, ctx->height);
+	irect whole = triangle_bound(p);
+	if (!irect_overlaps(whole, clip)) { return; }
+	irect un = irect_cut(whole, clip);
+	int32_t alignedTop = (un.t / 2) * 2, alignedBottom = ((un.t + un.h + 1) / 2) * 2; /* ITriangle2D.cpp:70-75 (non-negative) */
+	irect bound = irect_make(un.l, alignedTop, un.w, alignedBottom - alignedTop);
+	row_interval *rows = (row_interval*)malloc(sizeof(row_interval) * (size_t)bound.h);
+	rasterize_triangle(p, rows, bound);
+	projection proj = get_projection(p, subB, subC, ctx->camera->perspective);
+	int hasColor = ctx->color != NULL && ctx->color->data != NULL, hasDepth = ctx->depth != NULL && ctx->depth->data != NULL;
+	fill_mode m;
+	m.color = ctx->color; m.depth = ctx->depth; m.affine = proj.affine;
+	m.maxHeight = ctx->height;
+	m.alphaFilter = 0;
+	if (hasDepth && hasColor) {
+		if (ctx->filter != DFPSR_FILTER_SOLID) { m.colorWrite = 1; m.depthRead = 1; m.depthWrite = 0; m.alphaFilter = 1; }
+		else { m.colorWrite = 1; m.depthRead = 1; m.depthWrite = 1; }
+	} else if (hasDepth) {
+		m.colorWrite = 0; m.depthRead = 1; m.depthWrite = 1;
+	} else {
+		m.colorWrite = 1; m.depthRead = 0; m.depthWrite = 0; m.alphaFilter = ctx->filter != DFPSR_FILTER_SOLID;
+	}
+	fill_shape(&m, &ctx->shader, &proj, bound.t, bound.h, rows);
+	free(rows);
+}
+
+/* ------------------------------------------------------------------------------------------- cull / clip */
+
+enum { VIS_HIDDEN = 0, VIS_FULL = 1, VIS_PARTIAL = 2 };
+
+/* implementation/render/renderCore.cpp:172-198 */
+static int triangle_visibility(const ppoint *p, const dfpsr_camera *c, int clipFrustum) {
+	int planeCount = clipFrustum ? c->clipPlaneCount : c->cullPlaneCount;
+	const float (*planes)[4] = clipFrustum ? c->clipPlanes : c->cullPlanes;
+	int outside[3][6];
+	for (int k = 0; k < 3; k++) { for (int s = 0; s < planeCount; s++) { outside[k][s] = !plane_inside(planes[s], p[k].cs); } }
+	for (int s = 0; s < planeCount; s++) { if (outside[0][s] && outside[1][s] && outside[2][s]) { return VIS_HIDDEN; } }
+	for (int k = 0; k < 3; k++) { for (int s = 0; s < planeCount; s++) { if (outside[k][s]) { return VIS_PARTIAL; } } }
+	return VIS_FULL;
+}
+
+typedef struct { v3 cs; float subB, subC; int state; float value; } sub_vertex;
+
+static float inverse_lerp(float a, float b, float value) { /* renderCore.cpp:52-59 */
+	float c = b - a;
+	if (c == 0.0f) { return 0.5f; }
+	return (value - a) / c;
+}
+
+static sub_vertex sub_lerp(const sub_vertex *a, const sub_vertex *b, float ratio) { /* renderCore.cpp:41-46 */
+	sub_vertex r;
+	float inv = 1.0f - ratio;
+	r.cs = v3_make(a->cs.x * inv + b->cs.x * ratio, a->cs.y * inv + b->cs.y * ratio, a->cs.z * inv + b->cs.z * ratio);
+	r.subB = a->subB * inv + b->subB * ratio;
+	r.subC = a->subC * inv + b->subC * ratio;
+	r.state = 0; r.value = 0.0f;
+	return r;
+}
+
+#define MAX_POINTS 9
+typedef struct { int count; sub_vertex v[MAX_POINTS]; } clipped_triangle;
+
+/* renderCore.cpp:104-169 ClippedTriangle::clip */
+static void clip_plane(clipped_triangle *t, const float *plane) {
+	enum { USE = 0, DELETE = 1, MODIFIED = 2 };
+	if (!(t->count >= 3 && t->count < MAX_POINTS)) { return; }
+	int outsideCount = 0, lastOutside = 0;
+	for (int v = 0; v < t->count; v++) {
+		float distance = v3_dot(v3_from(plane), t->v[v].cs) - plane[3];
+		t->v[v].value = distance;
+		if (distance > 0.0f) { outsideCount++; lastOutside = v; t->v[v].state = DELETE; } else { t->v[v].state = USE; }
+	}
+	if (outsideCount == 0) { return; }
+	if (outsideCount >= t->count) { t->count = 0; return; }
+	if (outsideCount == 1) {
+		int cur = lastOutside, prev = (lastOutside - 1 + t->count) % t->count, next = (lastOutside + 1) % t->count;
+		float r1 = inverse_lerp(t->v[prev].value, t->v[cur].value, 0.0f);
+		float r2 = inverse_lerp(t->v[cur].value, t->v[next].value, 0.0f);
+		sub_vertex cutStart = sub_lerp(&t->v[prev], &t->v[cur], r1);
+		sub_vertex cutEnd = sub_lerp(&t->v[cur], &t->v[next], r2);
+		t->v[lastOutside] = cutStart;
+		/* insertVertex(next, cutEnd), renderCore.cpp:87-99 */
+		if (t->count < MAX_POINTS) {
+			for (int v = t->count - 1; v >= next; v--) { t->v[v + 1] = t->v[v]; }
+			t->v[next] = cutEnd;
+			t->count++;
+		}
+	} else {
+		for (int cur = 0; cur < t->count; cur++) {
+			int prev = (cur - 1 + t->count) % t->count, next = (cur + 1) % t->count;
+			if (t->v[cur].state == DELETE) {
+				if (t->v[prev].state == USE) {
+					float r = inverse_lerp(t->v[prev].value, t->v[cur].value, 0.0f);
+					t->v[cur] = sub_lerp(&t->v[prev], &t->v[cur], r);
+					t->v[cur].state = MODIFIED;
+				} else if (t->v[next].state == USE) {
+					float r = inverse_lerp(t->v[cur].value, t->v[next].value, 0.0f);
+					t->v[cur] = sub_lerp(&t->v[cur], &t->v[next], r);
+					t->v[cur].state = MODIFIED;
+				}
+			}
+		}
+		if (outsideCount > 2) {
+			for (int v = t->count - 1; v >= 0; v--) {
+				if (t->v[v].state == DELETE) {
+					for (int k = v; k < t->count - 1; k++) { t->v[k] = t->v[k + 1]; }
+					t->count--;
+				}
+			}
+		}
+	}
+}
+
+static clipped_triangle clip_triangle(const ppoint *p, const dfpsr_camera *c) { /* renderCore.cpp:70-75, :245-250 */
+	clipped_triangle t;
+	memset(&t, 0, sizeof(t));
+	t.v[0].cs = p[0].cs; t.v[0].subB = 0.0f; t.v[0].subC = 0.0f;
+	t.v[1].cs = p[1].cs; t.v[1].subB = 1.0f; t.v[1].subC = 0.0f;
+	t.v[2].cs = p[2].cs; t.v[2].subB = 0.0f; t.v[2].subC = 1.0f;
+	t.count = 3;
+	for (int s = 0; s < c->clipPlaneCount; s++) { clip_plane(&t, c->clipPlanes[s]); }
+	return t;
+}
+
+/* implementation/render/renderCore.cpp:261-341 renderTriangleFromData + renderTriangleWithShader */
+static void render_triangle(draw_context *ctx, const ppoint *p, const float colors[3][4], const float tex[3][4], const dfpsr_texture *diffuse, const dfpsr_texture *light) {
+	const dfpsr_camera *c = ctx->camera;
+	if (triangle_visibility(p, c, 0) == VIS_HIDDEN) { return; }
+	float alphas[3] = {colors[0][3], colors[1][3], colors[2][3]};
+	if (ctx->filter == DFPSR_FILTER_ALPHA && almost_zero3(alphas)) { return; }
+	shader_setup(&ctx->shader, colors, tex, diffuse, light);
+	if (triangle_visibility(p, c, 1) == VIS_FULL) {
+		if (is_frontfacing(p)) {
+			float subB[3] = {0.0f, 1.0f, 0.0f}, subC[3] = {0.0f, 0.0f, 1.0f};
+			execute_triangle(ctx, p, subB, subC);
+		}
+	} else {
+		clipped_triangle t = clip_triangle(p, c);
+		for (int i = 0; i < t.count - 2; i++) { /* renderCore.cpp:252-257, :220-240 */
+			const sub_vertex *a = &t.v[0], *b = &t.v[1 + i], *cc = &t.v[2 + i];
+			float subB[3] = {a->subB, b->subB, cc->subB}, subC[3] = {a->subC, b->subC, cc->subC};
+			ppoint q[3] = {camera_to_screen(c, a->cs), camera_to_screen(c, b->cs), camera_to_screen(c, cc->cs)};
+			if (is_frontfacing(q)) { execute_triangle(ctx, q, subB, subC); }
+		}
+	}
+}
+
+static int context_init(draw_context *ctx, const dfpsr_image *color, const dfpsr_image *depth, const dfpsr_camera *camera, int filter) {
+	memset(ctx, 0, sizeof(*ctx));
+	ctx->color = color; ctx->depth = depth; ctx->camera = camera; ctx->filter = filter;
+	if (color != NULL && color->data != NULL) { ctx->width = color->width; ctx->height = color->height; } /* renderCore.cpp:289-310 */
+	else if (depth != NULL && depth->data != NULL) { ctx->width = depth->width; ctx->height = depth->height; }
+	else { return 0; }
+	return 1;
+}
+
+/* api/modelAPI.cpp:214-281 (== implementation/render/model/Model.cpp:135-197) */
+int64_t orc_model_render(const dfpsr_model *model, const dfpsr_transform3d *m2w, const dfpsr_image *color, const dfpsr_image *depth, const dfpsr_camera *camera) {
+	draw_context ctx;
+	if (!context_init(&ctx, color, depth, camera, model->filter)) { return 0; }
+	if (!orc_camera_is_box_seen(camera, model->minBound, model->maxBound, m2w)) { return 0; }
+	ppoint *projected = (ppoint*)malloc(sizeof(ppoint) * (size_t)(model->pointCount > 0 ? model->pointCount : 1));
+	for (int32_t i = 0; i < model->pointCount; i++) {
+		projected[i] = world_to_screen(camera, transform_point(m2w, v3_from(model->points + 3 * i)));
+	}
+	for (int32_t i = 0; i < model->polygonCount; i++) {
+		const dfpsr_polygon *poly = model->polygons + i;
+		int triangles = poly->pointIndices[3] != -1 ? 2 : 1;
+		for (int t = 0; t < triangles; t++) {
+			int ia = 0, ib = 1 + t, ic = 2 + t;
+			ppoint p[3] = {projected[poly->pointIndices[ia]], projected[poly->pointIndices[ib]], projected[poly->pointIndices[ic]]};
+			float colors[3][4], tex[3][4];
+			memcpy(colors[0], poly->colors[ia], 16); memcpy(colors[1], poly->colors[ib], 16); memcpy(colors[2], poly->colors[ic], 16);
+			memcpy(tex[0], poly->texCoords[ia], 16); memcpy(tex[1], poly->texCoords[ib], 16); memcpy(tex[2], poly->texCoords[ic], 16);
+			render_triangle(&ctx, p, colors, tex, &model->diffuse, &model->light);
+		}
+	}
+	free(projected);
+	return ctx.commands;
+}
+
+/* api/rendererAPI.cpp:503-519 */
+int64_t orc_render_triangles(const dfpsr_triangle *triangles, int32_t count, const dfpsr_texture *diffuse, const dfpsr_texture *light, int32_t filter, const dfpsr_image *color, const dfpsr_image *depth, const dfpsr_camera *camera) {
+	draw_context ctx;
+	if (!context_init(&ctx, color, depth, camera, filter)) { return 0; }
+	for (int32_t i = 0; i < count; i++) {
+		ppoint p[3] = {ppoint_import(&triangles[i].pos[0]), ppoint_import(&triangles[i].pos[1]), ppoint_import(&triangles[i].pos[2])};
+		render_triangle(&ctx, p, triangles[i].colors, triangles[i].texCoords, diffuse, light);
+	}
+	return ctx.commands;
+}
+
+/* ------------------------------------------------------------------------------------------- depth-only path */
+
+/* implementation/render/renderCore.cpp:343-398 */
+static void draw_triangle_depth(const dfpsr_image *depth, const dfpsr_camera *c, const ppoint *p) {
+	if (!is_frontfacing(p)) { return; }
+	irect clip = irect_make(0, 0, depth->width, depth->height);
+	irect whole = triangle_bound(p);
+	if (!irect_overlaps(whole, clip)) { return; }
+	irect un = irect_cut(whole, clip);
+	int32_t alignedTop = (un.t / 2) * 2, alignedBottom = ((un.t + un.h + 1) / 2) * 2;
+	irect bound = irect_make(un.l, alignedTop, un.w, alignedBottom - alignedTop);
+	row_interval *rows = (row_interval*)malloc(sizeof(row_interval) * (size_t)bound.h);
+	rasterize_triangle(p, rows, bound);
+	float zero[3] = {0.0f, 0.0f, 0.0f};
+	projection proj = get_projection(p, zero, zero, c->perspective);
+	for (int32_t y = bound.t; y < bound.t + bound.h; y++) {
+		if (y >= depth->height) { break; } /* the reference would write past an odd-height image here; targets are even */
+		row_interval row = rows[y - bound.t];
+		float w[3];
+		projection_at(&proj, row.left, y, w);
+		float value = w[0], dx = proj.dx[0];
+		for (int32_t x = row.left; x < row.right; x++) {
+			float *px = depth_px(depth, x, y);
+			if (proj.affine) { if (value < *px) { *px = value; } } else { if (value > *px) { *px = value; } }
+			value += dx;
+		}
+	}
+	free(rows);
+}
+
+/* implementation/render/renderCore.cpp:407-443 + model/Model.cpp:164-211 */
+void orc_model_render_depth(const dfpsr_model *model, const dfpsr_transform3d *m2w, const dfpsr_image *depth, const dfpsr_camera *camera) {
+	if (depth == NULL || depth->data == NULL) { return; }
+	if (!orc_camera_is_box_seen(camera, model->minBound, model->maxBound, m2w)) { return; }
+	ppoint *projected = (ppoint*)malloc(sizeof(ppoint) * (size_t)(model->pointCount > 0 ? model->pointCount : 1));
+	for (int32_t i = 0; i < model->pointCount; i++) {
+		projected[i] = world_to_screen(camera, transform_point(m2w, v3_from(model->points + 3 * i)));
+	}
+	for (int32_t i = 0; i < model->polygonCount; i++) {
+		const dfpsr_polygon *poly = model->polygons + i;
+		int triangles = poly->pointIndices[3] != -1 ? 2 : 1;
+		for (int t = 0; t < triangles; t++) {
+			ppoint p[3] = {projected[poly->pointIndices[0]], projected[poly->pointIndices[1 + t]], projected[poly->pointIndices[2 + t]]};
+			if (triangle_visibility(p, camera, 0) == VIS_HIDDEN) { continue; }
+			if (triangle_visibility(p, camera, 1) == VIS_FULL) {
+				draw_triangle_depth(depth, camera, p);
+			} else {
+				clipped_triangle ct = clip_triangle(p, camera);
+				for (int k = 0; k < ct.count - 2; k++) {
+					ppoint q[3] = {camera_to_screen(camera, ct.v[0].cs), camera_to_screen(camera, ct.v[1 + k].cs), camera_to_screen(camera, ct.v[2 + k].cs)};
+					draw_triangle_depth(depth, camera, q);
+				}
+			}
+		}
+	}
+	free(projected);
+}
+
+/* TEMP stubs until implemented */
+void orc_image_fill_rgba(const dfpsr_image *image, int32_t r, int32_t g, int32_t b, int32_t a) {}
+void orc_image_fill_f32(const dfpsr_image *image, float value) {}
+void orc_draw_copy_rgba(const dfpsr_image *target, const dfpsr_image *source, int32_t left, int32_t top) {}
+void orc_draw_copy_f32(const dfpsr_image *target, const dfpsr_image *source, int32_t left, int32_t top) {}
+void orc_draw_higher(const dfpsr_image *targetHeight, const dfpsr_image *sourceHeight, const dfpsr_image *targetA, const dfpsr_image *sourceA, const dfpsr_image *targetB, const dfpsr_image *sourceB, int32_t left, int32_t top, float offset) {}
+void orc_light_directed(const dfpsr_ortho_view *view, const dfpsr_image *light, const dfpsr_image *normal, const float *direction, float intensity, const int32_t *colorRgb, int32_t add) {}
+void orc_light_point(const dfpsr_ortho_view *view, const int32_t *worldCenter, const dfpsr_image *light, const dfpsr_image *normal, const dfpsr_image *height, const float *position, float radius, float intensity, const int32_t *colorRgb, const dfpsr_image *shadowCubeMap, int32_t laneCount) {}
+void orc_light_blend(const dfpsr_image *color, const dfpsr_image *diffuse, const dfpsr_image *light) {}
+void orc_filter_resize(const dfpsr_image *target, const dfpsr_image *source, int32_t sampler, int32_t sourceIsSubImage, uint32_t *scratch) {}
+void orc_filter_map(const dfpsr_image *target, int32_t op, const int32_t *params, const dfpsr_image *source, int32_t startX, int32_t startY) {}
+void orc_filter_block_magnify(const dfpsr_image *target, const dfpsr_image *source, int32_t pixelWidth, int32_t pixelHeight) {}

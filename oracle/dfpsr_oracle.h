@@ -1,0 +1,60 @@
+/*
+ * dfpsr_oracle.h — TEST INFRASTRUCTURE. CPU restatement (plain C) of the reference's algorithm for the
+ * rendering hot path, used only as the checker by tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline leg. The product (dfpsr_b200/) never links or loads it.
+ *
+ * Parity status: PINNED. Every function here is checked bit-for-bit against the compiled, unmodified
+ * reference (oracle/_ref/libdfpsr_ref_scalar.so, built by oracle/Makefile) by tests/test_oracle_vs_ref.py,
+ * and against the golden hashes committed in tests/golden/ (generated from the same reference build by
+ * tests/golden/make_golden.py). The reference's own unit tests do not cover this path.
+ *
+ * All images here are HOST memory described with dfpsr_image (data = host pointer).
+ */
+#ifndef DFPSR_ORACLE_H
+#define DFPSR_ORACLE_H
+
+#include "../include/dfpsr_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Camera::createPerspective / createOrthogonal from the constructor arguments already stored in *camera
+ * (perspective, location, imageWidth, imageHeight, widthSlope [= halfWidth when orthogonal], nearClip, farClip). */
+void orc_camera_create(dfpsr_camera *camera);
+int orc_camera_is_box_seen(const dfpsr_camera *camera, const float *minBound, const float *maxBound, const dfpsr_transform3d *modelToWorld);
+void orc_project_points(const float *points, int32_t count, const dfpsr_transform3d *modelToWorld, const dfpsr_camera *camera, dfpsr_projected_point *out);
+
+void orc_texture_layout(dfpsr_texture *out, int32_t width, int32_t height, int32_t resolutions);
+void orc_texture_generate_pyramid(uint32_t *pixels, const dfpsr_texture *layout);
+
+/* model_render / renderer_begin+giveTask+end (identical pixels). color and/or depth may have data == NULL.
+ * Returns the number of draw commands (triangles after culling/clipping/back-face removal). */
+int64_t orc_model_render(const dfpsr_model *model, const dfpsr_transform3d *modelToWorld, const dfpsr_image *color, const dfpsr_image *depth, const dfpsr_camera *camera);
+/* renderer_giveTask_triangle for pre-projected triangles. */
+int64_t orc_render_triangles(const dfpsr_triangle *triangles, int32_t count, const dfpsr_texture *diffuse, const dfpsr_texture *light, int32_t filter, const dfpsr_image *color, const dfpsr_image *depth, const dfpsr_camera *camera);
+/* model_renderDepth */
+void orc_model_render_depth(const dfpsr_model *model, const dfpsr_transform3d *modelToWorld, const dfpsr_image *depth, const dfpsr_camera *camera);
+
+void orc_image_fill_rgba(const dfpsr_image *image, int32_t r, int32_t g, int32_t b, int32_t a);
+void orc_image_fill_f32(const dfpsr_image *image, float value);
+void orc_draw_copy_rgba(const dfpsr_image *target, const dfpsr_image *source, int32_t left, int32_t top);
+void orc_draw_copy_f32(const dfpsr_image *target, const dfpsr_image *source, int32_t left, int32_t top);
+void orc_draw_higher(const dfpsr_image *targetHeight, const dfpsr_image *sourceHeight, const dfpsr_image *targetA, const dfpsr_image *sourceA, const dfpsr_image *targetB, const dfpsr_image *sourceB, int32_t left, int32_t top, float offset);
+
+/* laneCount: the reference's laneCountX_32Bit (4 for the SSE2/scalar builds, 8 for AVX2); it decides the
+ * alignment of the point light's rectangle and the grouping of its incremental position adds.
+ * rowsPerJob: 0 = one job for the whole rectangle (DISABLE_MULTI_THREADING build). */
+void orc_light_directed(const dfpsr_ortho_view *view, const dfpsr_image *light, const dfpsr_image *normal, const float *direction, float intensity, const int32_t *colorRgb, int32_t add);
+void orc_light_point(const dfpsr_ortho_view *view, const int32_t *worldCenter, const dfpsr_image *light, const dfpsr_image *normal, const dfpsr_image *height, const float *position, float radius, float intensity, const int32_t *colorRgb, const dfpsr_image *shadowCubeMap, int32_t laneCount);
+void orc_light_blend(const dfpsr_image *color, const dfpsr_image *diffuse, const dfpsr_image *light);
+
+/* filter_resize into an existing RGBA-order target; scratch must hold target.width * source.height u32. */
+void orc_filter_resize(const dfpsr_image *target, const dfpsr_image *source, int32_t sampler, int32_t sourceIsSubImage, uint32_t *scratch);
+void orc_filter_map(const dfpsr_image *target, int32_t op, const int32_t *params, const dfpsr_image *source, int32_t startX, int32_t startY);
+void orc_filter_block_magnify(const dfpsr_image *target, const dfpsr_image *source, int32_t pixelWidth, int32_t pixelHeight);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,438 @@
+// ref_wrap.cpp — TEST INFRASTRUCTURE, not product code.
+//
+// A flat C wrapper around the UNMODIFIED reference (Dawoodoz/DFPSR), compiled by oracle/Makefile from the
+// sources where they lie under /root/reference/Source into oracle/_ref/libdfpsr_ref_{sse,scalar}.so.
+// No reference source is copied: this file only #includes the reference's public headers and calls
+// its public API (model_render, renderer_*, draw_*, filter_*, lightAPI). It is used
+//   * by tests/ to pin the C restatement (oracle/dfpsr_oracle.c) and the CUDA path against the real thing,
+//   * by bench.py --impl reference / cpu_baseline as the timed CPU implementation.
+// The product (dfpsr_b200/) never links or loads it.
+#include "../include/dfpsr_b200.h"
+
+#include "DFPSR/includeFramework.h"
+#include "DFPSR/implementation/render/model/Model.h"
+#include "DFPSR/implementation/render/Camera.h"
+#include "DFPSR/api/rendererAPI.h"
+#include "SDK/SpriteEngine/lightAPI.h"
+#include "SDK/SpriteEngine/orthoAPI.h"
+
+#include <vector>
+#include <cstring>
+#include <chrono>
+
+using namespace dsr;
+
+namespace {
+
+struct AnyImage {
+	int kind = 0; // 1 = RgbaU8, 2 = F32
+	ImageRgbaU8 rgba;
+	AlignedImageRgbaU8 rgbaAligned; // only for whole images
+	OrderedImageRgbaU8 rgbaOrdered; // only for whole RGBA-order images
+	ImageF32 f32;
+	AlignedImageF32 f32Aligned; // only for whole images
+};
+
+std::vector<AnyImage> g_images;
+std::vector<TextureRgbaU8> g_textures;
+std::vector<Model> g_models;
+bool g_started = false;
+
+void ensureStarted() {
+	if (!g_started) {
+		heap_startingApplication();
+		g_started = true;
+	}
+}
+
+FVector3D v3(const float *p) { return FVector3D(p[0], p[1], p[2]); }
+
+Transform3D toTransform(const dfpsr_transform3d *t) {
+	return Transform3D(v3(t->position), FMatrix3x3(v3(t->xAxis), v3(t->yAxis), v3(t->zAxis)));
+}
+
+FMatrix3x3 toMatrix(const dfpsr_matrix3x3 &m) {
+	return FMatrix3x3(v3(m.xAxis), v3(m.yAxis), v3(m.zAxis));
+}
+
+Camera toCamera(const dfpsr_camera *c) {
+	Transform3D location = toTransform(&c->location);
+	if (c->perspective) {
+		return Camera::createPerspective(location, c->imageWidth, c->imageHeight, c->widthSlope, c->nearClip, c->farClip);
+	} else {
+		return Camera::createOrthogonal(location, c->imageWidth, c->imageHeight, c->widthSlope);
+	}
+}
+
+OrthoView toView(const dfpsr_ortho_view *v) {
+	OrthoView result;
+	result.normalToWorldSpace = toMatrix(v->normalToWorldSpace);
+	result.screenDepthToLightSpace = toMatrix(v->screenDepthToLightSpace);
+	result.lightSpaceToScreenDepth = toMatrix(v->lightSpaceToScreenDepth);
+	return result;
+}
+
+ImageRgbaU8 rgbaOrNull(int id) { return id >= 0 ? g_images[id].rgba : ImageRgbaU8(); }
+ImageF32 f32OrNull(int id) { return id >= 0 ? g_images[id].f32 : ImageF32(); }
+TextureRgbaU8 texOrNull(int id) { return id >= 0 ? g_textures[id] : TextureRgbaU8(); }
+
+void fromMatrix(dfpsr_matrix3x3 &out, const FMatrix3x3 &m) {
+	out.xAxis[0] = m.xAxis.x; out.xAxis[1] = m.xAxis.y; out.xAxis[2] = m.xAxis.z;
+	out.yAxis[0] = m.yAxis.x; out.yAxis[1] = m.yAxis.y; out.yAxis[2] = m.yAxis.z;
+	out.zAxis[0] = m.zAxis.x; out.zAxis[1] = m.zAxis.y; out.zAxis[2] = m.zAxis.z;
+}
+
+} // namespace
+
+extern "C" {
+
+// 0 = SSE2 (rcpps + Newton-Raphson reciprocal), 1 = scalar (exact 1/x). See Makefile.
+int ref_flavour() {
+	#ifdef USE_SSE2
+		return 0;
+	#else
+		return 1;
+	#endif
+}
+
+int ref_thread_count() { return getThreadCount(); }
+
+double ref_time_seconds() {
+	return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+void ref_free_all() {
+	g_models.clear();
+	g_textures.clear();
+	g_images.clear();
+}
+
+// Called at interpreter exit so that the reference's heap does not complain about a missing DSR_MAIN_CALLER.
+void ref_shutdown() {
+	if (g_started) {
+		heap_hardExitCleaning();
+		g_started = false;
+	}
+}
+
+// ---- images
+
+int ref_image_create_rgba(int w, int h, int packOrder) {
+	ensureStarted();
+	AnyImage img;
+	img.kind = 1;
+	if (packOrder == DFPSR_PACK_RGBA) {
+		img.rgbaOrdered = image_create_RgbaU8(w, h);
+		img.rgbaAligned = img.rgbaOrdered;
+	} else {
+		img.rgbaAligned = image_create_RgbaU8_native(w, h, (PackOrderIndex)packOrder);
+	}
+	img.rgba = img.rgbaAligned;
+	g_images.push_back(img);
+	return (int)g_images.size() - 1;
+}
+
+int ref_image_create_f32(int w, int h) {
+	ensureStarted();
+	AnyImage img;
+	img.kind = 2;
+	img.f32Aligned = image_create_F32(w, h);
+	img.f32 = img.f32Aligned;
+	g_images.push_back(img);
+	return (int)g_images.size() - 1;
+}
+
+int ref_image_sub(int id, int x, int y, int w, int h) {
+	AnyImage img;
+	img.kind = g_images[id].kind;
+	if (img.kind == 1) {
+		img.rgba = image_getSubImage(g_images[id].rgba, IRect(x, y, w, h));
+	} else {
+		img.f32 = image_getSubImage(g_images[id].f32, IRect(x, y, w, h));
+	}
+	g_images.push_back(img);
+	return (int)g_images.size() - 1;
+}
+
+int ref_image_width(int id) { return g_images[id].kind == 1 ? image_getWidth(g_images[id].rgba) : image_getWidth(g_images[id].f32); }
+int ref_image_height(int id) { return g_images[id].kind == 1 ? image_getHeight(g_images[id].rgba) : image_getHeight(g_images[id].f32); }
+int ref_image_stride(int id) { return g_images[id].kind == 1 ? image_getStride(g_images[id].rgba) : image_getStride(g_images[id].f32); }
+
+// Tight or strided host rows in/out (4 bytes per pixel for both kinds).
+void ref_image_write(int id, const void *src, int srcStride) {
+	const AnyImage &img = g_images[id];
+	int w = ref_image_width(id), h = ref_image_height(id);
+	for (int y = 0; y < h; y++) {
+		void *row = img.kind == 1 ? (void*)image_getSafePointer<uint32_t>(img.rgba, y).getUnsafe() : (void*)image_getSafePointer<float>(img.f32, y).getUnsafe();
+		memcpy(row, (const uint8_t*)src + (size_t)y * srcStride, (size_t)w * 4);
+	}
+}
+
+void ref_image_read(int id, void *dst, int dstStride) {
+	const AnyImage &img = g_images[id];
+	int w = ref_image_width(id), h = ref_image_height(id);
+	for (int y = 0; y < h; y++) {
+		const void *row = img.kind == 1 ? (const void*)image_getSafePointer<uint32_t>(img.rgba, y).getUnsafe() : (const void*)image_getSafePointer<float>(img.f32, y).getUnsafe();
+		memcpy((uint8_t*)dst + (size_t)y * dstStride, row, (size_t)w * 4);
+	}
+}
+
+void ref_image_fill_rgba(int id, int r, int g, int b, int a) { image_fill(g_images[id].rgba, ColorRgbaI32(r, g, b, a)); }
+void ref_image_fill_f32(int id, float v) { image_fill(g_images[id].f32, v); }
+
+// ---- textures
+
+// level0 is tight w*h RGBA-packed u32 with power-of-two w and h; lower levels are generated by the reference.
+int ref_texture_create(int w, int h, int levels, const uint32_t *level0) {
+	ensureStarted();
+	TextureRgbaU8 tex = texture_create_RgbaU8(w, h, levels);
+	int tw = texture_getMaxWidth(tex), th = texture_getMaxHeight(tex);
+	for (int y = 0; y < th && y < h; y++) {
+		SafePointer<uint32_t> target = texture_getSafePointer(tex, 0u, y);
+		memcpy(target.getUnsafe(), level0 + (size_t)y * w, (size_t)(w < tw ? w : tw) * 4);
+	}
+	texture_generatePyramid(tex);
+	g_textures.push_back(tex);
+	return (int)g_textures.size() - 1;
+}
+
+int ref_texture_from_image(int imageId, int levels) {
+	ensureStarted();
+	g_textures.push_back(texture_create_RgbaU8(g_images[imageId].rgba, levels));
+	return (int)g_textures.size() - 1;
+}
+
+// out: log2w, log2h, maxMip, startOffset, maxLevelMask, totalPixels
+void ref_texture_info(int id, uint32_t *out) {
+	const TextureRgbaU8 &t = g_textures[id];
+	out[0] = t.impl_log2width; out[1] = t.impl_log2height; out[2] = t.impl_maxMipLevel;
+	out[3] = t.impl_startOffset; out[4] = t.impl_maxLevelMask;
+	out[5] = t.impl_startOffset + (1u << (t.impl_log2width + t.impl_log2height));
+}
+
+void ref_texture_read(int id, uint32_t *out) {
+	uint32_t info[6];
+	ref_texture_info(id, info);
+	SafePointer<uint32_t> data = g_textures[id].impl_buffer.getSafe<uint32_t>("ref_texture_read");
+	memcpy(out, data.getUnsafe(), (size_t)info[5] * 4);
+}
+
+// ---- models
+
+int ref_model_create(const float *points, int pointCount, const dfpsr_polygon *polygons, int polygonCount, int filter, int diffuseTex, int lightTex) {
+	ensureStarted();
+	Model model = model_create();
+	model_setFilter(model, filter == DFPSR_FILTER_ALPHA ? Filter::Alpha : Filter::Solid);
+	for (int p = 0; p < pointCount; p++) {
+		model_addPoint(model, v3(points + 3 * p));
+	}
+	int part = model_addEmptyPart(model, U"part");
+	if (diffuseTex >= 0) { model_setDiffuseMap(model, part, g_textures[diffuseTex]); }
+	if (lightTex >= 0) { model_setLightMap(model, part, g_textures[lightTex]); }
+	List<Polygon> &target = model->partBuffer[part].polygonBuffer;
+	for (int i = 0; i < polygonCount; i++) {
+		const dfpsr_polygon &src = polygons[i];
+		Polygon polygon(src.pointIndices[0], src.pointIndices[1], src.pointIndices[2], src.pointIndices[3]);
+		polygon.pointIndices[3] = src.pointIndices[3];
+		for (int c = 0; c < 4; c++) {
+			polygon.texCoords[c] = FVector4D(src.texCoords[c][0], src.texCoords[c][1], src.texCoords[c][2], src.texCoords[c][3]);
+			polygon.colors[c] = FVector4D(src.colors[c][0], src.colors[c][1], src.colors[c][2], src.colors[c][3]);
+		}
+		target.push(polygon);
+	}
+	g_models.push_back(model);
+	return (int)g_models.size() - 1;
+}
+
+void ref_model_bounds(int model, float *minOut, float *maxOut) {
+	FVector3D mn, mx;
+	model_getBoundingBox(g_models[model], mn, mx);
+	minOut[0] = mn.x; minOut[1] = mn.y; minOut[2] = mn.z;
+	maxOut[0] = mx.x; maxOut[1] = mx.y; maxOut[2] = mx.z;
+}
+
+// mode 0: model_render (single thread, immediate). mode 1: renderer_begin / renderer_giveTask / renderer_end.
+void ref_model_render(int model, const dfpsr_transform3d *modelToWorld, int colorId, int depthId, const dfpsr_camera *camera, int mode) {
+	ImageRgbaU8 color = rgbaOrNull(colorId);
+	ImageF32 depth = f32OrNull(depthId);
+	Camera cam = toCamera(camera);
+	Transform3D m2w = toTransform(modelToWorld);
+	if (mode == 0) {
+		model_render(g_models[model], m2w, color, depth, cam);
+	} else {
+		static Renderer worker = renderer_create();
+		renderer_begin(worker, color, depth);
+		renderer_giveTask(worker, g_models[model], m2w, cam);
+		renderer_end(worker);
+	}
+}
+
+// Several models in one renderer_begin / renderer_end frame, in order.
+void ref_models_render_frame(const int *models, const dfpsr_transform3d *modelToWorld, int count, int colorId, int depthId, const dfpsr_camera *camera) {
+	ImageRgbaU8 color = rgbaOrNull(colorId);
+	ImageF32 depth = f32OrNull(depthId);
+	Camera cam = toCamera(camera);
+	static Renderer worker = renderer_create();
+	renderer_begin(worker, color, depth);
+	for (int i = 0; i < count; i++) {
+		renderer_giveTask(worker, g_models[models[i]], toTransform(modelToWorld + i), cam);
+	}
+	renderer_end(worker);
+}
+
+void ref_model_render_depth(int model, const dfpsr_transform3d *modelToWorld, int depthId, const dfpsr_camera *camera) {
+	ImageF32 depth = f32OrNull(depthId);
+	model_renderDepth(g_models[model], toTransform(modelToWorld), depth, toCamera(camera));
+}
+
+// The whole SDK terrain frame: clear colour+depth, begin, giveTask, end (SDK/terrain/main.cpp:397-421). Returns seconds.
+double ref_terrain_frame(int model, const dfpsr_transform3d *modelToWorld, int colorId, int depthId, const dfpsr_camera *camera) {
+	double t0 = ref_time_seconds();
+	image_fill(g_images[colorId].rgba, ColorRgbaI32(0, 0, 0, 0));
+	image_fill(g_images[depthId].f32, 0.0f);
+	ref_model_render(model, modelToWorld, colorId, depthId, camera, 1);
+	return ref_time_seconds() - t0;
+}
+
+void ref_project_points(const float *points, int count, const dfpsr_transform3d *modelToWorld, const dfpsr_camera *camera, dfpsr_projected_point *out) {
+	Camera cam = toCamera(camera);
+	Transform3D m2w = toTransform(modelToWorld);
+	for (int i = 0; i < count; i++) {
+		ProjectedPoint p = cam.worldToScreen(m2w.transformPoint(v3(points + 3 * i)));
+		out[i].cs[0] = p.cs.x; out[i].cs[1] = p.cs.y; out[i].cs[2] = p.cs.z;
+		out[i].is[0] = p.is.x; out[i].is[1] = p.is.y;
+		out[i].pad_ = 0;
+		out[i].flat[0] = p.flat.x; out[i].flat[1] = p.flat.y;
+	}
+}
+
+// Fills the derived fields of a camera POD from the reference's own Camera, for checking dfpsr_camera_create_*.
+void ref_camera_fill(dfpsr_camera *c) {
+	Camera cam = toCamera(c);
+	c->widthSlope = cam.widthSlope; c->heightSlope = cam.heightSlope;
+	c->invWidthSlope = cam.invWidthSlope; c->invHeightSlope = cam.invHeightSlope;
+	c->nearClip = cam.nearClip; c->farClip = cam.farClip;
+	c->cullPlaneCount = cam.getFrustumPlaneCount(false);
+	c->clipPlaneCount = cam.getFrustumPlaneCount(true);
+	for (int clip = 0; clip < 2; clip++) {
+		int n = cam.getFrustumPlaneCount(clip != 0);
+		for (int s = 0; s < n; s++) {
+			FPlane3D p = cam.getFrustumPlane(s, clip != 0);
+			float *dst = clip ? c->clipPlanes[s] : c->cullPlanes[s];
+			dst[0] = p.normal.x; dst[1] = p.normal.y; dst[2] = p.normal.z; dst[3] = p.offset;
+		}
+	}
+}
+
+int ref_camera_is_box_seen(const dfpsr_camera *c, const float *mn, const float *mx, const dfpsr_transform3d *modelToWorld) {
+	return toCamera(c).isBoxSeen(v3(mn), v3(mx), toTransform(modelToWorld));
+}
+
+// ---- draw
+
+void ref_draw_higher(int targetH, int sourceH, int targetA, int sourceA, int targetB, int sourceB, int left, int top, float offset) {
+	if (targetA < 0) {
+		// The height-only overload is declared (drawAPI.h:142) with a signature its definition (drawAPI.cpp:962)
+		// does not match, so it cannot be linked; give it throw-away payload images instead.
+		ImageRgbaU8 dummyTarget = image_create_RgbaU8(image_getWidth(g_images[targetH].f32), image_getHeight(g_images[targetH].f32));
+		ImageRgbaU8 dummySource = image_create_RgbaU8(image_getWidth(g_images[sourceH].f32), image_getHeight(g_images[sourceH].f32));
+		draw_higher(g_images[targetH].f32, g_images[sourceH].f32, dummyTarget, dummySource, left, top, offset);
+	} else if (targetB < 0) {
+		draw_higher(g_images[targetH].f32, g_images[sourceH].f32, g_images[targetA].rgba, g_images[sourceA].rgba, left, top, offset);
+	} else {
+		draw_higher(g_images[targetH].f32, g_images[sourceH].f32, g_images[targetA].rgba, g_images[sourceA].rgba, g_images[targetB].rgba, g_images[sourceB].rgba, left, top, offset);
+	}
+}
+
+void ref_draw_copy(int target, int source, int left, int top) {
+	if (g_images[target].kind == 1) {
+		draw_copy(g_images[target].rgba, g_images[source].rgba, left, top);
+	} else {
+		draw_copy(g_images[target].f32, g_images[source].f32, left, top);
+	}
+}
+
+// ---- Sandbox light
+
+// Views of the reference's own orthogonal system (SDK/sandbox/media/Ortho.ini: tilt -0.6, 150 px per tile).
+void ref_ortho_view(float cameraTilt, int pixelsPerTile, int viewIndex, dfpsr_ortho_view *out, int32_t *pixelOffsets /* xAxis.xy, zAxis.xy, yPixelsPerTile */) {
+	ensureStarted();
+	OrthoSystem system(cameraTilt, pixelsPerTile);
+	const OrthoView &v = system.view[viewIndex];
+	fromMatrix(out->normalToWorldSpace, v.normalToWorldSpace);
+	fromMatrix(out->screenDepthToLightSpace, v.screenDepthToLightSpace);
+	fromMatrix(out->lightSpaceToScreenDepth, v.lightSpaceToScreenDepth);
+	if (pixelOffsets) {
+		pixelOffsets[0] = v.pixelOffsetPerTileX.x; pixelOffsets[1] = v.pixelOffsetPerTileX.y;
+		pixelOffsets[2] = v.pixelOffsetPerTileZ.x; pixelOffsets[3] = v.pixelOffsetPerTileZ.y;
+		pixelOffsets[4] = v.yPixelsPerTile;
+	}
+}
+
+void ref_light_directed(const dfpsr_ortho_view *view, int light, int normal, const float *direction, float intensity, const int32_t *color, int add) {
+	OrthoView v = toView(view);
+	OrderedImageRgbaU8 lightImage = g_images[light].rgbaOrdered;
+	OrderedImageRgbaU8 normalImage = g_images[normal].rgbaOrdered;
+	if (add) {
+		addDirectedLight(v, lightImage, normalImage, v3(direction), intensity, ColorRgbI32(color[0], color[1], color[2]));
+	} else {
+		setDirectedLight(v, lightImage, normalImage, v3(direction), intensity, ColorRgbI32(color[0], color[1], color[2]));
+	}
+}
+
+void ref_light_point(const dfpsr_ortho_view *view, const int32_t *worldCenter, int light, int normal, int height, const float *position, float radius, float intensity, const int32_t *color, int cubeMap) {
+	OrthoView v = toView(view);
+	OrderedImageRgbaU8 lightImage = g_images[light].rgbaOrdered;
+	OrderedImageRgbaU8 normalImage = g_images[normal].rgbaOrdered;
+	AlignedImageF32 heightImage = g_images[height].f32Aligned;
+	if (cubeMap >= 0) {
+		AlignedImageF32 cube = g_images[cubeMap].f32Aligned;
+		addPointLight(v, IVector2D(worldCenter[0], worldCenter[1]), lightImage, normalImage, heightImage, v3(position), radius, intensity, ColorRgbI32(color[0], color[1], color[2]), cube);
+	} else {
+		addPointLight(v, IVector2D(worldCenter[0], worldCenter[1]), lightImage, normalImage, heightImage, v3(position), radius, intensity, ColorRgbI32(color[0], color[1], color[2]));
+	}
+}
+
+void ref_light_blend(int color, int diffuse, int light) {
+	AlignedImageRgbaU8 colorImage = g_images[color].rgbaAligned;
+	OrderedImageRgbaU8 diffuseImage = g_images[diffuse].rgbaOrdered;
+	OrderedImageRgbaU8 lightImage = g_images[light].rgbaOrdered;
+	blendLight(colorImage, diffuseImage, lightImage);
+}
+
+// ---- filters
+
+int ref_filter_resize(int source, int sampler, int newWidth, int newHeight) {
+	AnyImage img;
+	img.kind = 1;
+	img.rgbaOrdered = filter_resize(g_images[source].rgba, sampler == DFPSR_SAMPLER_LINEAR ? Sampler::Linear : Sampler::Nearest, newWidth, newHeight);
+	img.rgbaAligned = img.rgbaOrdered;
+	img.rgba = img.rgbaOrdered;
+	g_images.push_back(img);
+	return (int)g_images.size() - 1;
+}
+
+void ref_filter_map(int target, int op, const int32_t *params, int source, int startX, int startY) {
+	ImageRgbaU8 targetImage = g_images[target].rgba;
+	if (op == DFPSR_MAP_XOR_PATTERN) {
+		filter_mapRgbaU8(targetImage, [](int32_t x, int32_t y) -> ColorRgbaI32 {
+			return ColorRgbaI32(x & 255, y & 255, (x ^ y) & 255, 255);
+		}, startX, startY);
+	} else if (op == DFPSR_MAP_AFFINE) {
+		ImageRgbaU8 sourceImage = g_images[source].rgba;
+		filter_mapRgbaU8(targetImage, [sourceImage, params](int32_t x, int32_t y) -> ColorRgbaI32 {
+			ColorRgbaI32 s = image_readPixel_clamp(sourceImage, x, y);
+			return ColorRgbaI32(s.red * params[0] + params[4], s.green * params[1] + params[5], s.blue * params[2] + params[6], s.alpha * params[3] + params[7]);
+		}, startX, startY);
+	} else if (op == DFPSR_MAP_CONSTANT) {
+		filter_mapRgbaU8(targetImage, [params](int32_t x, int32_t y) -> ColorRgbaI32 {
+			return ColorRgbaI32(params[0], params[1], params[2], params[3]);
+		}, startX, startY);
+	}
+}
+
+void ref_filter_block_magnify(int target, int source, int pixelWidth, int pixelHeight) {
+	filter_blockMagnify(g_images[target].rgba, g_images[source].rgba, pixelWidth, pixelHeight);
+}
+
+} // extern "C"

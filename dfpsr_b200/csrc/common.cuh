@@ -1,0 +1,93 @@
+// common.cuh — shared plumbing for the sm_100a kernels: error handling, launch accounting, pixel packing.
+// Everything is compiled with -fmad=false: the reference is built without FMA contraction
+// (ISO C++ mode, SURVEY.md §7 hard part 1) and bit-exact parity depends on identical rounding.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/dfpsr_b200.h"
+
+namespace dfpsr {
+
+// ---- error reporting (thread-local message, int status across the C ABI)
+void set_error(const char *fmt, ...);
+extern thread_local char g_error[512];
+
+#define DFPSR_CHECK_CUDA(expr)                                                                         \
+	do {                                                                                               \
+		cudaError_t err_ = (expr);                                                                     \
+		if (err_ != cudaSuccess) {                                                                     \
+			dfpsr::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(err_), __FILE__, __LINE__); \
+			return 1;                                                                                  \
+		}                                                                                              \
+	} while (0)
+
+#define DFPSR_REQUIRE(cond, ...)              \
+	do {                                      \
+		if (!(cond)) {                        \
+			dfpsr::set_error(__VA_ARGS__);    \
+			return 1;                         \
+		}                                     \
+	} while (0)
+
+// ---- launch accounting: every kernel launch of this library goes through DFPSR_LAUNCH
+extern unsigned long long g_launches;
+int check_launch(const char *name);
+
+#define DFPSR_LAUNCH(kernel, grid, block, smem, stream, ...)                      \
+	do {                                                                          \
+		kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);               \
+		dfpsr::g_launches++;                                                      \
+		if (dfpsr::check_launch(#kernel)) { return 1; }                           \
+	} while (0)
+
+inline cudaStream_t as_stream(void *s) { return (cudaStream_t)s; }
+
+// Number of SMs of the current device (148 on B200); grids of persistent kernels are multiples of it.
+int sm_count();
+
+// Growable device buffer owned by a renderer / session.
+struct DeviceBuffer {
+	void *ptr = nullptr;
+	size_t capacity = 0;
+	int reserve(size_t bytes);
+	void release();
+};
+
+// ---- device helpers
+
+// Byte index of red, green, blue, alpha for each pack order (ref: implementation/image/PackOrder.h:85-96).
+__host__ __device__ inline uint32_t pack_shifts(int order) {
+	// four 8-bit fields: shift of red | green << 8 | blue << 16 | alpha << 24
+	switch (order) {
+		case DFPSR_PACK_BGRA: return 16u | (8u << 8) | (0u << 16) | (24u << 24);
+		case DFPSR_PACK_ARGB: return 8u | (16u << 8) | (24u << 16) | (0u << 24);
+		case DFPSR_PACK_ABGR: return 24u | (16u << 8) | (8u << 16) | (0u << 24);
+		default: return 0u | (8u << 8) | (16u << 16) | (24u << 24);
+	}
+}
+
+// ref: implementation/image/PackOrder.h:186-197 — clampUpper(x, 255.1) then truncating conversion.
+// The reference's scalar conversion wraps negative inputs; inputs on this path are never negative.
+__device__ __forceinline__ uint32_t saturated_byte(float v) {
+	float c = v < 255.1f ? v : 255.1f;
+	return (uint32_t)__float2int_rz(c);
+}
+
+__device__ __forceinline__ uint32_t pack_rgba_ordered(uint32_t r, uint32_t g, uint32_t b, uint32_t a, uint32_t shifts) {
+	return (r << (shifts & 31u)) | (g << ((shifts >> 8) & 31u)) | (b << ((shifts >> 16) & 31u)) | (a << ((shifts >> 24) & 31u));
+}
+
+template <typename T>
+__device__ __forceinline__ T *row_ptr(void *data, int32_t stride, int32_t y) {
+	return (T *)((uint8_t *)data + (size_t)y * (size_t)stride);
+}
+template <typename T>
+__device__ __forceinline__ const T *row_ptr(const void *data, int32_t stride, int32_t y) {
+	return (const T *)((const uint8_t *)data + (size_t)y * (size_t)stride);
+}
+
+} // namespace dfpsr

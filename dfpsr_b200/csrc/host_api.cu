@@ -1,0 +1,253 @@
+// host_api.cu — the non-kernel part of the C ABI: errors, device memory helpers, camera construction
+// (host arithmetic mirroring Camera.h), texture layout. Kernels live in raster.cu and pixel_ops.cu.
+#include "common.cuh"
+
+#include <math.h>
+#include <float.h>
+#include <stdarg.h>
+
+namespace dfpsr {
+
+thread_local char g_error[512] = "";
+unsigned long long g_launches = 0;
+
+void set_error(const char *fmt, ...) {
+	va_list args;
+	va_start(args, fmt);
+	vsnprintf(g_error, sizeof(g_error), fmt, args);
+	va_end(args);
+}
+
+int check_launch(const char *name) {
+	cudaError_t err = cudaGetLastError();
+	if (err != cudaSuccess) {
+		set_error("launch of %s failed: %s", name, cudaGetErrorString(err));
+		return 1;
+	}
+	return 0;
+}
+
+int sm_count() {
+	static int cached = 0;
+	if (cached == 0) {
+		int device = 0;
+		if (cudaGetDevice(&device) != cudaSuccess) { return 148; }
+		if (cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || cached <= 0) { cached = 148; }
+	}
+	return cached;
+}
+
+int DeviceBuffer::reserve(size_t bytes) {
+	if (bytes <= capacity) { return 0; }
+	size_t grown = capacity + capacity / 2;
+	if (grown < bytes) { grown = bytes; }
+	grown = (grown + 255) & ~(size_t)255;
+	void *fresh = nullptr;
+	cudaError_t err = cudaMalloc(&fresh, grown);
+	if (err != cudaSuccess) {
+		set_error("cudaMalloc of %zu bytes failed: %s", grown, cudaGetErrorString(err));
+		return 1;
+	}
+	if (ptr) { cudaFree(ptr); } // contents are per-frame scratch; nothing to preserve
+	ptr = fresh;
+	capacity = grown;
+	return 0;
+}
+
+void DeviceBuffer::release() {
+	if (ptr) { cudaFree(ptr); }
+	ptr = nullptr;
+	capacity = 0;
+}
+
+struct V3 { float x, y, z; };
+
+// ref: math/FVector.h:113-120
+static V3 normalize3(V3 v) {
+	float l = sqrtf(v.x * v.x + v.y * v.y + v.z * v.z);
+	if (l == 0.0f) { return V3{0.0f, 0.0f, 1.0f}; }
+	return V3{v.x / l, v.y / l, v.z / l};
+}
+
+static void set_plane(float *dst, V3 normal, float offset) { // ref: math/FPlane3D.h:36
+	V3 n = normalize3(normal);
+	dst[0] = n.x; dst[1] = n.y; dst[2] = n.z; dst[3] = offset;
+}
+
+// ref: implementation/render/Camera.h:56-72
+static int frustum_perspective(float planes[6][4], float nearClip, float farClip, float widthSlope, float heightSlope) {
+	set_plane(planes[0], V3{-1.0f, 0.0f, -widthSlope}, 0.0f);
+	set_plane(planes[1], V3{1.0f, 0.0f, -widthSlope}, 0.0f);
+	set_plane(planes[2], V3{0.0f, 1.0f, -heightSlope}, 0.0f);
+	set_plane(planes[3], V3{0.0f, -1.0f, -heightSlope}, 0.0f);
+	set_plane(planes[4], V3{0.0f, 0.0f, -1.0f}, -nearClip);
+	set_plane(planes[5], V3{0.0f, 0.0f, 1.0f}, farClip);
+	return farClip == INFINITY ? 5 : 6;
+}
+
+// ref: implementation/render/Camera.h:47-55
+static int frustum_orthogonal(float planes[6][4], float halfWidth, float halfHeight) {
+	set_plane(planes[0], V3{-1.0f, 0.0f, 0.0f}, halfWidth);
+	set_plane(planes[1], V3{1.0f, 0.0f, 0.0f}, halfWidth);
+	set_plane(planes[2], V3{0.0f, 1.0f, 0.0f}, halfHeight);
+	set_plane(planes[3], V3{0.0f, -1.0f, 0.0f}, halfHeight);
+	return 4;
+}
+
+static const float cullRatio = 1.0001f; // ref: Camera.h:113
+static const float clipRatio = 2.0f;    // ref: Camera.h:118
+
+} // namespace dfpsr
+
+using namespace dfpsr;
+
+extern "C" {
+
+int dfpsr_abi_version(void) { return DFPSR_B200_ABI_VERSION; }
+
+const char *dfpsr_last_error(void) { return g_error; }
+
+int dfpsr_device_count(void) {
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) { return 0; }
+	return n;
+}
+
+int dfpsr_init(int device) {
+	int n = 0;
+	cudaError_t err = cudaGetDeviceCount(&n);
+	DFPSR_REQUIRE(err == cudaSuccess && n > 0, "no CUDA device available (%s); dfpsr_b200 has no CPU fallback", cudaGetErrorString(err));
+	DFPSR_REQUIRE(device >= 0 && device < n, "device %d out of range (found %d)", device, n);
+	DFPSR_CHECK_CUDA(cudaSetDevice(device));
+	DFPSR_CHECK_CUDA(cudaFree(0));
+	return 0;
+}
+
+uint64_t dfpsr_launch_count(void) { return g_launches; }
+void dfpsr_reset_launch_count(void) { g_launches = 0; }
+
+int dfpsr_malloc(void **devicePtr, size_t bytes) {
+	DFPSR_CHECK_CUDA(cudaMalloc(devicePtr, bytes));
+	return 0;
+}
+int dfpsr_free(void *devicePtr) {
+	DFPSR_CHECK_CUDA(cudaFree(devicePtr));
+	return 0;
+}
+int dfpsr_malloc_host(void **pinnedPtr, size_t bytes) {
+	DFPSR_CHECK_CUDA(cudaMallocHost(pinnedPtr, bytes));
+	return 0;
+}
+int dfpsr_free_host(void *pinnedPtr) {
+	DFPSR_CHECK_CUDA(cudaFreeHost(pinnedPtr));
+	return 0;
+}
+int dfpsr_upload(void *devicePtr, const void *hostPtr, size_t bytes, void *stream) {
+	DFPSR_CHECK_CUDA(cudaMemcpyAsync(devicePtr, hostPtr, bytes, cudaMemcpyHostToDevice, as_stream(stream)));
+	return 0;
+}
+int dfpsr_download(void *hostPtr, const void *devicePtr, size_t bytes, void *stream) {
+	DFPSR_CHECK_CUDA(cudaMemcpyAsync(hostPtr, devicePtr, bytes, cudaMemcpyDeviceToHost, as_stream(stream)));
+	return 0;
+}
+int dfpsr_upload_2d(void *devicePtr, size_t deviceStride, const void *hostPtr, size_t hostStride, size_t rowBytes, size_t rows, void *stream) {
+	DFPSR_CHECK_CUDA(cudaMemcpy2DAsync(devicePtr, deviceStride, hostPtr, hostStride, rowBytes, rows, cudaMemcpyHostToDevice, as_stream(stream)));
+	return 0;
+}
+int dfpsr_download_2d(void *hostPtr, size_t hostStride, const void *devicePtr, size_t deviceStride, size_t rowBytes, size_t rows, void *stream) {
+	DFPSR_CHECK_CUDA(cudaMemcpy2DAsync(hostPtr, hostStride, devicePtr, deviceStride, rowBytes, rows, cudaMemcpyDeviceToHost, as_stream(stream)));
+	return 0;
+}
+int dfpsr_stream_synchronize(void *stream) {
+	DFPSR_CHECK_CUDA(cudaStreamSynchronize(as_stream(stream)));
+	return 0;
+}
+
+// ref: implementation/render/Camera.h:128-150
+int dfpsr_camera_create_perspective(dfpsr_camera *out, const dfpsr_transform3d *location, float imageWidth, float imageHeight, float widthSlope, float nearClip, float farClip) {
+	DFPSR_REQUIRE(out && location, "dfpsr_camera_create_perspective: null argument");
+	memset(out, 0, sizeof(*out));
+	float heightSlope = widthSlope * imageHeight / imageWidth;
+	out->perspective = 1;
+	out->location = *location;
+	out->widthSlope = widthSlope; out->heightSlope = heightSlope;
+	out->invWidthSlope = 0.5f / widthSlope; out->invHeightSlope = 0.5f / heightSlope;
+	out->imageWidth = imageWidth; out->imageHeight = imageHeight;
+	out->nearClip = nearClip; out->farClip = farClip;
+	out->cullPlaneCount = frustum_perspective(out->cullPlanes, nearClip, farClip, widthSlope * cullRatio, heightSlope * cullRatio);
+	out->clipPlaneCount = frustum_perspective(out->clipPlanes, nearClip, farClip, widthSlope * clipRatio, heightSlope * clipRatio);
+	return 0;
+}
+
+// ref: implementation/render/Camera.h:152-156
+int dfpsr_camera_create_orthogonal(dfpsr_camera *out, const dfpsr_transform3d *location, float imageWidth, float imageHeight, float halfWidth) {
+	DFPSR_REQUIRE(out && location, "dfpsr_camera_create_orthogonal: null argument");
+	memset(out, 0, sizeof(*out));
+	float halfHeight = halfWidth * imageHeight / imageWidth;
+	out->perspective = 0;
+	out->location = *location;
+	out->widthSlope = halfWidth; out->heightSlope = halfHeight;
+	out->invWidthSlope = 0.5f / halfWidth; out->invHeightSlope = 0.5f / halfHeight;
+	out->imageWidth = imageWidth; out->imageHeight = imageHeight;
+	out->nearClip = -FLT_MAX; out->farClip = INFINITY;
+	out->cullPlaneCount = frustum_orthogonal(out->cullPlanes, halfWidth * cullRatio, halfHeight * cullRatio);
+	out->clipPlaneCount = frustum_orthogonal(out->clipPlanes, halfWidth * clipRatio, halfHeight * clipRatio);
+	return 0;
+}
+
+// ref: implementation/render/Camera.h:73-95, :202-217
+int dfpsr_camera_is_box_seen(const dfpsr_camera *c, const float mn[3], const float mx[3], const dfpsr_transform3d *m2w) {
+	bool anyOutside = false;
+	V3 corners[8];
+	for (int i = 0; i < 8; i++) {
+		float px = (i & 1) ? mx[0] : mn[0], py = (i & 2) ? mx[1] : mn[1], pz = (i & 4) ? mx[2] : mn[2];
+		// modelToWorld.transformPoint (math/Transform3D.h:41-43)
+		float wx = (px * m2w->xAxis[0] + py * m2w->yAxis[0] + pz * m2w->zAxis[0]) + m2w->position[0];
+		float wy = (px * m2w->xAxis[1] + py * m2w->yAxis[1] + pz * m2w->zAxis[1]) + m2w->position[1];
+		float wz = (px * m2w->xAxis[2] + py * m2w->yAxis[2] + pz * m2w->zAxis[2]) + m2w->position[2];
+		// worldToCamera (math/Transform3D.h:50-52)
+		const dfpsr_transform3d &l = c->location;
+		float dx = wx - l.position[0], dy = wy - l.position[1], dz = wz - l.position[2];
+		corners[i] = V3{
+		  dx * l.xAxis[0] + dy * l.xAxis[1] + dz * l.xAxis[2],
+		  dx * l.yAxis[0] + dy * l.yAxis[1] + dz * l.yAxis[2],
+		  dx * l.zAxis[0] + dy * l.zAxis[1] + dz * l.zAxis[2]};
+	}
+	for (int s = 0; s < c->cullPlaneCount; s++) {
+		const float *pl = c->cullPlanes[s];
+		bool anyInside = false;
+		for (int p = 0; p < 8; p++) {
+			float d = ((pl[0] * corners[p].x) + (pl[1] * corners[p].y) + (pl[2] * corners[p].z)) - pl[3];
+			if (d <= 0.0f) { anyInside = true; } else { anyOutside = true; }
+		}
+		if (!anyInside) { return 0; }
+	}
+	return anyOutside ? 1 : 2;
+}
+
+// ref: api/textureAPI.cpp:30-41, :65-78; implementation/image/Texture.h:63-102
+int dfpsr_texture_layout(dfpsr_texture *out, int32_t width, int32_t height, int32_t resolutions) {
+	DFPSR_REQUIRE(out != nullptr, "dfpsr_texture_layout: null output");
+	DFPSR_REQUIRE(resolutions >= 1, "Tried to create a texture without any resolutions stored, which would be empty!");
+	DFPSR_REQUIRE(width >= 1 && height >= 1, "Tried to create a texture of %d x %d pixels, which would be empty!", width, height);
+	DFPSR_REQUIRE(width <= 32768 && height <= 32768, "Tried to create a texture of %d x %d pixels, which exceeds the maximum texture dimensions of 32768 x 32768 pixels!", width, height);
+	uint32_t log2w = 15, log2h = 15;
+	for (uint32_t l = 0; l < 15; l++) { if ((1u << l) >= (uint32_t)width) { log2w = l; break; } }
+	for (uint32_t l = 0; l < 15; l++) { if ((1u << l) >= (uint32_t)height) { log2h = l; break; } }
+	uint32_t maxMip = (uint32_t)(resolutions - 1);
+	if (maxMip > log2w) { maxMip = log2w; }
+	if (maxMip > log2h) { maxMip = log2h; }
+	if (maxMip > 15) { maxMip = 15; }
+	uint64_t highest = (uint64_t)1 << (log2w + log2h);
+	uint64_t pixelCount = 0, levelCount = highest;
+	for (int32_t level = (int32_t)maxMip; level >= 0; level--) { pixelCount |= levelCount; levelCount >>= 2; }
+	DFPSR_REQUIRE(pixelCount < 4294967296ull, "texture of %d x %d pixels cannot be indexed with 32-bit offsets", width, height);
+	out->data = nullptr;
+	out->log2width = log2w; out->log2height = log2h; out->maxMipLevel = maxMip;
+	out->startOffset = (uint32_t)(pixelCount & ~highest);
+	out->maxLevelMask = (uint32_t)(highest - 1);
+	out->totalPixels = (uint32_t)pixelCount;
+	return 0;
+}
+
+} // extern "C"

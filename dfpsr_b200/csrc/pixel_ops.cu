@@ -1,0 +1,673 @@
+// pixel_ops.cu — the bandwidth-bound per-pixel passes of the hot path on sm_100a:
+//   image_fill / draw_copy / draw_higher          ref: api/imageAPI.cpp:167-185, api/drawAPI.cpp:72-174, :492-539, :834-904
+//   directed light / point light / blend          ref: SDK/SpriteEngine/lightAPI.cpp:23-323
+//   filter_resize / filter_map / blockMagnify     ref: api/filterAPI.cpp:49-314, :724-782
+//   texture pyramid                               ref: api/textureAPI.cpp:44-110
+// Every kernel streams each pixel once with 16-byte accesses where rows are 16-byte aligned (4 pixels per
+// thread), otherwise 4-byte accesses; the arithmetic is the reference's, operation for operation
+// (-fmad=false), so integer passes are bit-exact and float passes match the reference's scalar build.
+#include "common.cuh"
+
+#include <math.h>
+
+namespace dfpsr {
+
+static const int PX = 4; // pixels per thread along x
+static inline dim3 grid_for(int32_t width, int32_t height, dim3 block) {
+	return dim3((unsigned)((width + PX * (int)block.x - 1) / (PX * (int)block.x)), (unsigned)((height + (int)block.y - 1) / (int)block.y));
+}
+static const dim3 BLOCK(64, 4);
+
+struct Img {
+	uint8_t *data;
+	int32_t width, height, stride, packOrder;
+};
+static inline Img img_of(const dfpsr_image *im) {
+	Img r;
+	if (im == nullptr) { r.data = nullptr; r.width = r.height = r.stride = r.packOrder = 0; return r; }
+	r.data = (uint8_t *)im->data; r.width = im->width; r.height = im->height; r.stride = im->stride; r.packOrder = im->packOrder;
+	return r;
+}
+__device__ __forceinline__ uint32_t *px_u32(const Img &im, int32_t x, int32_t y) { return (uint32_t *)(im.data + (size_t)y * (size_t)im.stride) + x; }
+__device__ __forceinline__ float *px_f32(const Img &im, int32_t x, int32_t y) { return (float *)(im.data + (size_t)y * (size_t)im.stride) + x; }
+__device__ __forceinline__ bool aligned16(const void *p) { return (((uintptr_t)p) & 15u) == 0; }
+
+// Loads / stores up to 4 consecutive 32-bit pixels starting at x (x is a multiple of 4 in image space).
+__device__ __forceinline__ void load4(const Img &im, int32_t x, int32_t y, int n, uint32_t *v) {
+	const uint32_t *p = px_u32(im, x, y);
+	if (n == 4 && aligned16(p)) { uint4 q = *(const uint4 *)p; v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; }
+	else { for (int i = 0; i < 4; i++) { v[i] = i < n ? p[i] : 0u; } }
+}
+__device__ __forceinline__ void store4(const Img &im, int32_t x, int32_t y, int n, const uint32_t *v) {
+	uint32_t *p = px_u32(im, x, y);
+	if (n == 4 && aligned16(p)) { *(uint4 *)p = make_uint4(v[0], v[1], v[2], v[3]); }
+	else { for (int i = 0; i < n; i++) { p[i] = v[i]; } }
+}
+
+__device__ __forceinline__ uint32_t repack(uint32_t c, uint32_t sourceShifts, uint32_t targetShifts) {
+	uint32_t r = (c >> (sourceShifts & 31u)) & 255u, g = (c >> ((sourceShifts >> 8) & 31u)) & 255u;
+	uint32_t b = (c >> ((sourceShifts >> 16) & 31u)) & 255u, a = (c >> ((sourceShifts >> 24) & 31u)) & 255u;
+	return pack_rgba_ordered(r, g, b, a, targetShifts);
+}
+
+// ------------------------------------------------------------------------------------------------ fill / copy / higher
+
+__global__ void __launch_bounds__(256) fill_kernel(Img target, uint32_t value) {
+	int32_t x = (blockIdx.x * blockDim.x + threadIdx.x) * PX, y = blockIdx.y * blockDim.y + threadIdx.y;
+	if (x >= target.width || y >= target.height) { return; }
+	uint32_t v[4] = {value, value, value, value};
+	store4(target, x, y, min(PX, target.width - x), v);
+}
+
+struct Intersection { int32_t tx, ty, sx, sy, w, h; };
+// ref: api/drawAPI.cpp:330-385 ImageIntersection
+static bool intersect(const Img &target, const Img &source, int32_t left, int32_t top, Intersection &out) {
+	int32_t x0 = left > 0 ? left : 0, y0 = top > 0 ? top : 0;
+	int32_t x1 = left + source.width < target.width ? left + source.width : target.width;
+	int32_t y1 = top + source.height < target.height ? top + source.height : target.height;
+	if (x1 <= x0 || y1 <= y0) { return false; }
+	out.tx = x0; out.ty = y0; out.sx = x0 - left; out.sy = y0 - top; out.w = x1 - x0; out.h = y1 - y0;
+	return true;
+}
+
+// convert: 0 = raw 32-bit copy, 1 = repack channels between pack orders
+__global__ void __launch_bounds__(256) copy_kernel(Img target, Img source, Intersection is, int convert) {
+	int32_t x = (blockIdx.x * blockDim.x + threadIdx.x) * PX, y = blockIdx.y * blockDim.y + threadIdx.y;
+	if (x >= is.w || y >= is.h) { return; }
+	int n = min(PX, is.w - x);
+	uint32_t ss = pack_shifts(source.packOrder), ts = pack_shifts(target.packOrder);
+	const uint32_t *s = px_u32(source, is.sx + x, is.sy + y);
+	uint32_t *t = px_u32(target, is.tx + x, is.ty + y);
+	if (n == 4 && aligned16(s) && aligned16(t)) {
+		uint4 q = *(const uint4 *)s;
+		if (convert) { q.x = repack(q.x, ss, ts); q.y = repack(q.y, ss, ts); q.z = repack(q.z, ss, ts); q.w = repack(q.w, ss, ts); }
+		*(uint4 *)t = q;
+	} else {
+		for (int i = 0; i < n; i++) { t[i] = convert ? repack(s[i], ss, ts) : s[i]; }
+	}
+}
+
+// ref: api/drawAPI.cpp:834-904
+__global__ void __launch_bounds__(256) higher_kernel(Img targetH, Img sourceH, Img targetA, Img sourceA, Img targetB, Img sourceB, Intersection is, float offset) {
+	int32_t x = (blockIdx.x * blockDim.x + threadIdx.x) * PX, y = blockIdx.y * blockDim.y + threadIdx.y;
+	if (x >= is.w || y >= is.h) { return; }
+	int n = min(PX, is.w - x);
+	for (int i = 0; i < n; i++) {
+		float newHeight = *px_f32(sourceH, is.sx + x + i, is.sy + y);
+		if (newHeight > -INFINITY) {
+			newHeight += offset;
+			float *t = px_f32(targetH, is.tx + x + i, is.ty + y);
+			if (newHeight > *t) {
+				*t = newHeight;
+				if (targetA.data) { *px_u32(targetA, is.tx + x + i, is.ty + y) = repack(*px_u32(sourceA, is.sx + x + i, is.sy + y), pack_shifts(sourceA.packOrder), pack_shifts(targetA.packOrder)); }
+				if (targetB.data) { *px_u32(targetB, is.tx + x + i, is.ty + y) = repack(*px_u32(sourceB, is.sx + x + i, is.sy + y), pack_shifts(sourceB.packOrder), pack_shifts(targetB.packOrder)); }
+			}
+		}
+	}
+}
+
+struct SpriteDev { Img sourceH, sourceA, sourceB; int32_t left, top; float offset; };
+
+// All sprites of a batch applied to one target tile in array order: each target pixel is read and written once.
+// ref: SDK/SpriteEngine/spriteAPI.cpp:316-323 drawSprite → draw_higher, called in a loop (:525-539, :726-733).
+__global__ void __launch_bounds__(256) higher_batch_kernel(Img targetH, Img targetA, Img targetB, const SpriteDev *__restrict__ sprites, int32_t count) {
+	int32_t x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+	int32_t tileL = blockIdx.x * 32, tileT = blockIdx.y * 8;
+	bool inside = x < targetH.width && y < targetH.height;
+	float h = 0.0f;
+	uint32_t a = 0, b = 0;
+	if (inside) {
+		h = *px_f32(targetH, x, y);
+		if (targetA.data) { a = *px_u32(targetA, x, y); }
+		if (targetB.data) { b = *px_u32(targetB, x, y); }
+	}
+	bool dirty = false;
+	uint32_t ta = pack_shifts(targetA.packOrder), tb = pack_shifts(targetB.packOrder);
+	for (int32_t s = 0; s < count; s++) {
+		const SpriteDev &sp = sprites[s];
+		// tile-uniform rejection
+		if (sp.left >= tileL + 32 || sp.left + sp.sourceH.width <= tileL || sp.top >= tileT + 8 || sp.top + sp.sourceH.height <= tileT) { continue; }
+		int32_t sx = x - sp.left, sy = y - sp.top;
+		if (inside && sx >= 0 && sy >= 0 && sx < sp.sourceH.width && sy < sp.sourceH.height) {
+			float newHeight = *px_f32(sp.sourceH, sx, sy);
+			if (newHeight > -INFINITY) {
+				newHeight += sp.offset;
+				if (newHeight > h) {
+					h = newHeight;
+					dirty = true;
+					if (targetA.data) { a = repack(*px_u32(sp.sourceA, sx, sy), pack_shifts(sp.sourceA.packOrder), ta); }
+					if (targetB.data) { b = repack(*px_u32(sp.sourceB, sx, sy), pack_shifts(sp.sourceB.packOrder), tb); }
+				}
+			}
+		}
+	}
+	if (dirty) {
+		*px_f32(targetH, x, y) = h;
+		if (targetA.data) { *px_u32(targetA, x, y) = a; }
+		if (targetB.data) { *px_u32(targetB, x, y) = b; }
+	}
+}
+
+// ------------------------------------------------------------------------------------------------ Sandbox light
+
+// ref: base/simd.h:2670 saturatedAddition on four bytes
+__device__ __forceinline__ uint32_t sat_add_bytes(uint32_t a, uint32_t b) { return __vaddus4(a, b); }
+
+// ref: SDK/SpriteEngine/lightAPI.cpp:52-56 — clampUpper 255.1, truncate, pack r | g << 8 | b << 16
+__device__ __forceinline__ uint32_t light_pack(float r, float g, float b) {
+	return saturated_byte(r) | (saturated_byte(g) << 8) | (saturated_byte(b) << 16);
+}
+
+// ref: SDK/SpriteEngine/lightAPI.cpp:23-68
+__global__ void __launch_bounds__(256) directed_kernel(Img light, Img normal, float rx, float ry, float rz, float colorR, float colorG, float colorB, int add) {
+	int32_t x = (blockIdx.x * blockDim.x + threadIdx.x) * PX, y = blockIdx.y * blockDim.y + threadIdx.y;
+	if (x >= light.width || y >= light.height) { return; }
+	int n = min(PX, light.width - x);
+	uint32_t nc[4], out[4], old[4] = {0, 0, 0, 0};
+	load4(normal, x, y, n, nc);
+	if (add) { load4(light, x, y, n, old); }
+#pragma unroll
+	for (int i = 0; i < 4; i++) {
+		float nx = (float)(nc[i] & 255u) - 128.0f, ny = (float)((nc[i] >> 8) & 255u) - 128.0f, nz = (float)((nc[i] >> 16) & 255u) - 128.0f;
+		float dot = (nx * rx) + (ny * ry) + (nz * rz);
+		float in = dot > 0.0f ? dot : 0.0f;
+		uint32_t packed = light_pack(in * colorR, in * colorG, in * colorB);
+		out[i] = add ? sat_add_bytes(old[i], packed) : packed;
+	}
+	store4(light, x, y, n, out);
+}
+
+// ref: SDK/SpriteEngine/lightAPI.cpp:287-323
+__global__ void __launch_bounds__(256) blend_kernel(Img color, Img diffuse, Img light) {
+	int32_t x = (blockIdx.x * blockDim.x + threadIdx.x) * PX, y = blockIdx.y * blockDim.y + threadIdx.y;
+	if (x >= color.width || y >= color.height) { return; }
+	int n = min(PX, color.width - x);
+	uint32_t d[4], l[4], out[4];
+	load4(diffuse, x, y, n, d);
+	load4(light, x, y, n, l);
+	const float scale = 0.0078125f; // 1 / 128
+	uint32_t shifts = pack_shifts(color.packOrder);
+#pragma unroll
+	for (int i = 0; i < 4; i++) {
+		float red = ((float)(d[i] & 255u) * (float)(l[i] & 255u)) * scale;
+		float green = ((float)((d[i] >> 8) & 255u) * (float)((l[i] >> 8) & 255u)) * scale;
+		float blue = ((float)((d[i] >> 16) & 255u) * (float)((l[i] >> 16) & 255u)) * scale;
+		out[i] = pack_rgba_ordered(saturated_byte(red), saturated_byte(green), saturated_byte(blue), 0u, shifts);
+	}
+	store4(color, x, y, n, out);
+}
+
+struct PointLightParams {
+	int32_t left, top, width, height; // lane-aligned rectangle (ref: lightAPI.cpp:76-105)
+	int32_t laneCount;
+	float baseX, baseY, baseZ;       // light-space offset of the rectangle's first pixel centre at height 0
+	float dxX, dxY, dxZ, dyX, dyY, dyZ, faceX, faceY, faceZ;
+	float colorR, colorG, colorB, reciprocalRadius;
+	int32_t shadow;
+	float cubeCenter;
+};
+
+// ref: SDK/SpriteEngine/lightAPI.cpp:107-139
+__device__ float shadow_transparency(const Img &cube, float halfWidth, float ox, float oy, float oz) {
+	int32_t width = cube.width;
+	float absX = ox < 0.0f ? -ox : ox, absY = oy < 0.0f ? -oy : oy, absZ = oz < 0.0f ? -oz : oz;
+	bool xIsLongest = absX > absY && absX > absZ;
+	bool yIsLongerThanZ = absY > absZ;
+	float depth = xIsLongest ? ox : (yIsLongerThanZ ? oy : oz);
+	float slopeUp = (yIsLongerThanZ && !xIsLongest) ? oz : oy;
+	float slopeSide = xIsLongest ? -oz : (yIsLongerThanZ ? -ox : ox);
+	int32_t viewOffset = width * (xIsLongest ? 0 : (yIsLongerThanZ ? 2 : 4));
+	if (depth < 0.0f) { depth = -depth; slopeSide = -slopeSide; viewOffset += width; }
+	float reciDepth = 1.0f / depth;
+	float scale = halfWidth * reciDepth;
+	int32_t sampleX = __float2int_rz(halfWidth + (slopeSide * scale));
+	int32_t sampleY = __float2int_rz(halfWidth - (slopeUp * scale));
+	int32_t maxPixel = width - 1;
+	sampleX = min(max(sampleX, 0), maxPixel);
+	sampleY = min(max(sampleY, 0), maxPixel);
+	float shadowReciDepth = *px_f32(cube, sampleX, sampleY + viewOffset);
+	return reciDepth * 1.02f > shadowReciDepth ? 1.0f : 0.0f;
+}
+
+// One CTA per image row of the light's rectangle. The reference walks the rectangle with running sums
+// (lightBaseRowX += dy per row, lightBasePixel += laneCount * dx per vector, lightAPI.cpp:196-268); the first
+// 3 * laneCount threads replay those sums for this row into shared memory, then all threads shade pixels.
+__global__ void __launch_bounds__(256) point_light_kernel(Img light, Img normal, Img height, Img cube, PointLightParams p) {
+	extern __shared__ float sChain[]; // [vector][component * laneCount + lane]
+	const int32_t y = p.top + (int32_t)blockIdx.x;
+	const int32_t lanes = p.laneCount, vectors = p.width / lanes;
+	if ((int32_t)threadIdx.x < 3 * lanes) {
+		int32_t comp = threadIdx.x / lanes, l = threadIdx.x % lanes;
+		float base = comp == 0 ? p.baseX : (comp == 1 ? p.baseY : p.baseZ);
+		float dx = comp == 0 ? p.dxX : (comp == 1 ? p.dxY : p.dxZ), dy = comp == 0 ? p.dyX : (comp == 1 ? p.dyY : p.dyZ);
+		// createGradient (ref: base/simd.h:474): lane 0 = start, lane 1 = start + inc, lane l = start + inc * l
+		float v = l == 0 ? base : (l == 1 ? base + dx : base + dx * (float)l);
+		for (int32_t r = 0; r < (int32_t)blockIdx.x; r++) { v += dy; }
+		float step = dx * (float)lanes;
+		for (int32_t k = 0; k < vectors; k++) { sChain[k * 3 * lanes + comp * lanes + l] = v; v += step; }
+	}
+	__syncthreads();
+	for (int32_t i = threadIdx.x; i < p.width; i += blockDim.x) {
+		int32_t x = p.left + i;
+		if (x >= light.width) { continue; } // lanes past the image width are row padding in the reference
+		int32_t k = i / lanes, l = i % lanes;
+		float h = *px_f32(height, x, y);
+		float ox = sChain[k * 3 * lanes + l] + (p.faceX * h);
+		float oy = sChain[k * 3 * lanes + lanes + l] + (p.faceY * h);
+		float oz = sChain[k * 3 * lanes + 2 * lanes + l] + (p.faceZ * h);
+		float sq = (ox * ox) + (oy * oy) + (oz * oz);
+		float lightRatio = sqrtf(sq) * p.reciprocalRadius;
+		if (1.0f < lightRatio) { lightRatio = 1.0f; }
+		uint32_t nc = *px_u32(normal, x, y);
+		float nx = ((float)(nc & 255u) - 128.0f) * (-1.0f / 128.0f), ny = ((float)((nc >> 8) & 255u) - 128.0f) * (-1.0f / 128.0f), nz = ((float)((nc >> 16) & 255u) - 128.0f) * (-1.0f / 128.0f);
+		float distanceIntensity = 1.0f - 2.0f * lightRatio + lightRatio * lightRatio;
+		// scalar-build reciprocalSquareRoot: the quotient is formed in double (ref: base/simd.h:4104, see oracle/dfpsr_oracle.c)
+		float rs = (float)(1.0 / sqrt((double)sq));
+		float dot = ((ox * rs) * nx) + ((oy * rs) * ny) + ((oz * rs) * nz);
+		float in = (dot > 0.0f ? dot : 0.0f) * distanceIntensity;
+		if (p.shadow) { in = in * shadow_transparency(cube, p.cubeCenter, ox, oy, oz); }
+		uint32_t *t = px_u32(light, x, y);
+		*t = sat_add_bytes(*t, light_pack(in * p.colorR, in * p.colorG, in * p.colorB));
+	}
+}
+
+// ------------------------------------------------------------------------------------------------ textures and filters
+
+// ref: api/textureAPI.cpp:44-63 downsample, one level
+__global__ void __launch_bounds__(256) downsample_kernel(const uint32_t *__restrict__ source, uint32_t *__restrict__ target, uint32_t targetWidth, uint32_t targetHeight) {
+	uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+	if (x >= targetWidth || y >= targetHeight) { return; }
+	uint32_t sw = targetWidth * 2;
+	uint2 top = *(const uint2 *)(source + (size_t)(2 * y) * sw + 2 * x), bottom = *(const uint2 *)(source + (size_t)(2 * y + 1) * sw + 2 * x);
+	uint32_t out = 0;
+#pragma unroll
+	for (int s = 0; s < 32; s += 8) {
+		out |= ((((top.x >> s) & 255u) + ((top.y >> s) & 255u) + ((bottom.x >> s) & 255u) + ((bottom.y >> s) & 255u)) / 4u) << s;
+	}
+	target[(size_t)y * targetWidth + x] = out;
+}
+
+struct Rgba { int32_t r, g, b, a; };
+
+// ref: api/imageAPI.h:284-290 image_readPixel_clamp → channels in RGBA order
+__device__ __forceinline__ Rgba read_clamp(const Img &im, int32_t x, int32_t y) {
+	x = min(max(x, 0), im.width - 1); y = min(max(y, 0), im.height - 1);
+	uint32_t c = *px_u32(im, x, y), s = pack_shifts(im.packOrder);
+	Rgba o = {(int32_t)((c >> (s & 31u)) & 255u), (int32_t)((c >> ((s >> 8) & 31u)) & 255u), (int32_t)((c >> ((s >> 16) & 31u)) & 255u), (int32_t)((c >> ((s >> 24) & 31u)) & 255u)};
+	return o;
+}
+__device__ __forceinline__ uint32_t saturate_and_pack(Rgba c, uint32_t shifts) { // ref: PackOrder.h:108-110
+	return pack_rgba_ordered((uint32_t)min(max(c.r, 0), 255), (uint32_t)min(max(c.g, 0), 255), (uint32_t)min(max(c.b, 0), 255), (uint32_t)min(max(c.a, 0), 255), shifts);
+}
+__device__ __forceinline__ Rgba lerp16(Rgba a, Rgba b, uint32_t ratioB) { // ref: api/filterAPI.cpp:86-88
+	uint32_t ra = 65536u - ratioB;
+	Rgba o = {(int32_t)(((uint32_t)a.r * ra + (uint32_t)b.r * ratioB) >> 16), (int32_t)(((uint32_t)a.g * ra + (uint32_t)b.g * ratioB) >> 16),
+	          (int32_t)(((uint32_t)a.b * ra + (uint32_t)b.b * ratioB) >> 16), (int32_t)(((uint32_t)a.a * ra + (uint32_t)b.a * ratioB) >> 16)};
+	return o;
+}
+// ref: api/filterAPI.cpp:49-63 mixColorsUniform (8-bit weights on packed colours)
+__device__ __forceinline__ uint32_t mix_uniform(uint32_t a, uint32_t b, uint32_t fineRatio) {
+	uint32_t ratio = fineRatio >> 8, inv = 256u - ratio;
+	uint32_t low = (a & 0x00FF00FFu) * inv + (b & 0x00FF00FFu) * ratio;
+	uint32_t high = ((a >> 8) & 0x00FF00FFu) * inv + ((b >> 8) & 0x00FF00FFu) * ratio;
+	return ((low >> 8) & 0x00FF00FFu) | (high & 0xFF00FF00u);
+}
+
+enum { RESIZE_VERTICAL_PACKED = 0, RESIZE_VERTICAL = 1, RESIZE_VERTICAL_NEAREST = 2, RESIZE_HORIZONTAL = 3, RESIZE_GENERAL = 4 };
+
+struct ResizeParams { int32_t offsetX, offsetY, startX, startY, bilinear, path; };
+
+// ref: api/filterAPI.cpp:118-259 — one thread per 4 target pixels of a row; the 16.16 read position is start + i * offset.
+__global__ void __launch_bounds__(256) resize_kernel(Img target, Img source, ResizeParams rp) {
+	int32_t x0 = (blockIdx.x * blockDim.x + threadIdx.x) * PX, y = blockIdx.y * blockDim.y + threadIdx.y;
+	if (x0 >= target.width || y >= target.height) { return; }
+	int n = min(PX, target.width - x0);
+	uint32_t shifts = pack_shifts(target.packOrder);
+	int32_t readY = rp.startY + y * rp.offsetY;
+	uint32_t sampleY = (uint32_t)(readY < 0 ? 0 : readY);
+	uint32_t upperY = sampleY >> 16, lowerRatio = sampleY & 65535u;
+	uint32_t out[4];
+	if (rp.path <= RESIZE_VERTICAL_NEAREST) {
+		uint32_t lowerY = upperY + 1;
+		if (upperY >= (uint32_t)source.height) { upperY = (uint32_t)source.height - 1; }
+		if (lowerY >= (uint32_t)source.height) { lowerY = (uint32_t)source.height - 1; }
+		if (rp.path == RESIZE_VERTICAL_PACKED) {
+			uint32_t up[4], lo[4];
+			load4(source, x0, (int32_t)upperY, n, up);
+			load4(source, x0, (int32_t)lowerY, n, lo);
+			for (int i = 0; i < 4; i++) { out[i] = mix_uniform(up[i], lo[i], lowerRatio); }
+		} else if (rp.path == RESIZE_VERTICAL) {
+			for (int i = 0; i < n; i++) { out[i] = saturate_and_pack(lerp16(read_clamp(source, x0 + i, (int32_t)upperY), read_clamp(source, x0 + i, (int32_t)lowerY), lowerRatio), shifts); }
+		} else {
+			load4(source, x0, (int32_t)upperY, n, out);
+		}
+	} else {
+		for (int i = 0; i < n; i++) {
+			int32_t readX = rp.startX + (x0 + i) * rp.offsetX;
+			uint32_t sampleX = (uint32_t)(readX < 0 ? 0 : readX);
+			int32_t leftX = (int32_t)(sampleX >> 16);
+			uint32_t rightRatio = sampleX & 65535u;
+			Rgba c;
+			if (rp.path == RESIZE_HORIZONTAL) {
+				c = rp.bilinear ? lerp16(read_clamp(source, leftX, y), read_clamp(source, leftX + 1, y), rightRatio) : read_clamp(source, leftX, y);
+			} else if (rp.bilinear) {
+				Rgba upper = lerp16(read_clamp(source, leftX, (int32_t)upperY), read_clamp(source, leftX + 1, (int32_t)upperY), rightRatio);
+				Rgba lower = lerp16(read_clamp(source, leftX, (int32_t)upperY + 1), read_clamp(source, leftX + 1, (int32_t)upperY + 1), rightRatio);
+				c = lerp16(upper, lower, lowerRatio);
+			} else {
+				c = read_clamp(source, leftX, (int32_t)upperY);
+			}
+			out[i] = saturate_and_pack(c, shifts);
+		}
+	}
+	store4(target, x0, y, n, out);
+}
+
+struct MapParams { int32_t op, startX, startY; int32_t p[8]; };
+
+// ref: api/filterAPI.cpp:759-777 with the enumerated device ops of dfpsr_b200.h
+__global__ void __launch_bounds__(256) map_kernel(Img target, Img source, MapParams mp) {
+	int32_t x0 = (blockIdx.x * blockDim.x + threadIdx.x) * PX, ty = blockIdx.y * blockDim.y + threadIdx.y;
+	if (x0 >= target.width || ty >= target.height) { return; }
+	int n = min(PX, target.width - x0);
+	uint32_t shifts = pack_shifts(target.packOrder);
+	uint32_t out[4];
+	int32_t y = ty + mp.startY;
+	uint32_t src[4];
+	bool direct = false;
+	if (mp.op == DFPSR_MAP_AFFINE) {
+		// fast path: the four reads are inside the source and contiguous
+		int32_t sx = x0 + mp.startX;
+		direct = n == 4 && sx >= 0 && sx + 3 < source.width && y >= 0 && y < source.height;
+		if (direct) { load4(source, sx, y, 4, src); }
+	}
+	uint32_t ss = pack_shifts(source.packOrder);
+	for (int i = 0; i < n; i++) {
+		int32_t x = x0 + i + mp.startX;
+		Rgba c = {0, 0, 0, 0};
+		if (mp.op == DFPSR_MAP_XOR_PATTERN) { c.r = x & 255; c.g = y & 255; c.b = (x ^ y) & 255; c.a = 255; }
+		else if (mp.op == DFPSR_MAP_AFFINE) {
+			Rgba s;
+			if (direct) { s.r = (int32_t)((src[i] >> (ss & 31u)) & 255u); s.g = (int32_t)((src[i] >> ((ss >> 8) & 31u)) & 255u); s.b = (int32_t)((src[i] >> ((ss >> 16) & 31u)) & 255u); s.a = (int32_t)((src[i] >> ((ss >> 24) & 31u)) & 255u); }
+			else { s = read_clamp(source, x, y); }
+			c.r = s.r * mp.p[0] + mp.p[4]; c.g = s.g * mp.p[1] + mp.p[5]; c.b = s.b * mp.p[2] + mp.p[6]; c.a = s.a * mp.p[3] + mp.p[7];
+		} else { c.r = mp.p[0]; c.g = mp.p[1]; c.b = mp.p[2]; c.a = mp.p[3]; }
+		out[i] = saturate_and_pack(c, shifts);
+	}
+	store4(target, x0, ty, n, out);
+}
+
+// ref: api/filterAPI.cpp:724-757 + :340-365
+__global__ void __launch_bounds__(256) magnify_kernel(Img target, Img source, int32_t pixelWidth, int32_t pixelHeight, int32_t clipWidth, int32_t clipHeight) {
+	int32_t x0 = (blockIdx.x * blockDim.x + threadIdx.x) * PX, y = blockIdx.y * blockDim.y + threadIdx.y;
+	if (x0 >= target.width || y >= target.height) { return; }
+	int n = min(PX, target.width - x0);
+	uint32_t ss = pack_shifts(source.packOrder), ts = pack_shifts(target.packOrder);
+	uint32_t out[4];
+	for (int i = 0; i < n; i++) {
+		int32_t x = x0 + i;
+		out[i] = 0;
+		if (x < clipWidth && y < clipHeight) {
+			out[i] = repack(*px_u32(source, min(x / pixelWidth, source.width - 1), min(y / pixelHeight, source.height - 1)), ss, ts);
+		}
+	}
+	store4(target, x0, y, n, out);
+}
+
+static bool exists(const dfpsr_image *im) { return im != nullptr && im->data != nullptr; }
+
+struct V3 { float x, y, z; };
+static V3 mat_transform(const dfpsr_matrix3x3 &m, V3 p) { // ref: math/FMatrix3x3.h:52-58
+	return V3{p.x * m.xAxis[0] + p.y * m.yAxis[0] + p.z * m.zAxis[0], p.x * m.xAxis[1] + p.y * m.yAxis[1] + p.z * m.zAxis[1], p.x * m.xAxis[2] + p.y * m.yAxis[2] + p.z * m.zAxis[2]};
+}
+static V3 mat_transform_transposed(const dfpsr_matrix3x3 &m, V3 p) { // ref: math/FMatrix3x3.h:63-69
+	return V3{p.x * m.xAxis[0] + p.y * m.xAxis[1] + p.z * m.xAxis[2], p.x * m.yAxis[0] + p.y * m.yAxis[1] + p.z * m.yAxis[2], p.x * m.zAxis[0] + p.y * m.zAxis[1] + p.z * m.zAxis[2]};
+}
+static V3 normalize3(V3 v) { // ref: math/FVector.h:113-120
+	float l = sqrtf(v.x * v.x + v.y * v.y + v.z * v.z);
+	if (l == 0.0f) { return V3{0.0f, 0.0f, 1.0f}; }
+	return V3{v.x / l, v.y / l, v.z / l};
+}
+
+static int resize_single(const Img &target, const Img &source, bool bilinear, bool simdAligned, cudaStream_t stream);
+
+} // namespace dfpsr
+
+using namespace dfpsr;
+
+extern "C" {
+
+int dfpsr_image_fill_rgba(const dfpsr_image *image, int32_t red, int32_t green, int32_t blue, int32_t alpha, void *stream) {
+	if (!exists(image)) { return 0; } // ref: api/drawAPI.cpp:162
+	auto clamp255 = [](int32_t v) { return (uint32_t)(v < 0 ? 0 : (v > 255 ? 255 : v)); };
+	uint32_t shifts = pack_shifts(image->packOrder);
+	uint32_t packed = (clamp255(red) << (shifts & 31u)) | (clamp255(green) << ((shifts >> 8) & 31u)) | (clamp255(blue) << ((shifts >> 16) & 31u)) | (clamp255(alpha) << ((shifts >> 24) & 31u));
+	Img t = img_of(image);
+	DFPSR_LAUNCH(fill_kernel, grid_for(t.width, t.height, BLOCK), BLOCK, 0, as_stream(stream), t, packed);
+	return 0;
+}
+
+int dfpsr_image_fill_f32(const dfpsr_image *image, float value, void *stream) {
+	if (!exists(image)) { return 0; }
+	uint32_t bits;
+	memcpy(&bits, &value, 4);
+	Img t = img_of(image);
+	DFPSR_LAUNCH(fill_kernel, grid_for(t.width, t.height, BLOCK), BLOCK, 0, as_stream(stream), t, bits);
+	return 0;
+}
+
+int dfpsr_draw_copy_rgba(const dfpsr_image *target, const dfpsr_image *source, int32_t left, int32_t top, void *stream) {
+	if (!exists(target) || !exists(source)) { return 0; } // ref: api/drawAPI.cpp:906-911
+	Img t = img_of(target), s = img_of(source);
+	Intersection is;
+	if (!intersect(t, s, left, top, is)) { return 0; }
+	DFPSR_LAUNCH(copy_kernel, grid_for(is.w, is.h, BLOCK), BLOCK, 0, as_stream(stream), t, s, is, t.packOrder != s.packOrder ? 1 : 0);
+	return 0;
+}
+
+int dfpsr_draw_copy_f32(const dfpsr_image *target, const dfpsr_image *source, int32_t left, int32_t top, void *stream) {
+	if (!exists(target) || !exists(source)) { return 0; }
+	Img t = img_of(target), s = img_of(source);
+	Intersection is;
+	if (!intersect(t, s, left, top, is)) { return 0; }
+	DFPSR_LAUNCH(copy_kernel, grid_for(is.w, is.h, BLOCK), BLOCK, 0, as_stream(stream), t, s, is, 0);
+	return 0;
+}
+
+int dfpsr_draw_higher(const dfpsr_image *targetHeight, const dfpsr_image *sourceHeight, const dfpsr_image *targetA, const dfpsr_image *sourceA, const dfpsr_image *targetB, const dfpsr_image *sourceB, int32_t left, int32_t top, float sourceHeightOffset, void *stream) {
+	// ref: api/drawAPI.cpp:962-979 — every image given to an overload must exist, otherwise nothing is drawn
+	if (!exists(targetHeight) || !exists(sourceHeight)) { return 0; }
+	bool wantA = targetA != nullptr || sourceA != nullptr, wantB = targetB != nullptr || sourceB != nullptr;
+	if (wantA && (!exists(targetA) || !exists(sourceA))) { return 0; }
+	if (wantB && (!exists(targetB) || !exists(sourceB))) { return 0; }
+	DFPSR_REQUIRE(!wantB || wantA, "draw_higher: a second payload image needs a first one");
+	Img th = img_of(targetHeight), sh = img_of(sourceHeight);
+	if (wantA) { DFPSR_REQUIRE(sourceA->width == sh.width && sourceA->height == sh.height, "draw_higher: sourceA and sourceHeight differ in size"); }
+	if (wantB) { DFPSR_REQUIRE(sourceB->width == sh.width && sourceB->height == sh.height, "draw_higher: sourceB and sourceHeight differ in size"); }
+	Intersection is;
+	if (!intersect(th, sh, left, top, is)) { return 0; }
+	DFPSR_LAUNCH(higher_kernel, grid_for(is.w, is.h, BLOCK), BLOCK, 0, as_stream(stream), th, sh, img_of(wantA ? targetA : nullptr), img_of(wantA ? sourceA : nullptr), img_of(wantB ? targetB : nullptr), img_of(wantB ? sourceB : nullptr), is, sourceHeightOffset);
+	return 0;
+}
+
+int dfpsr_draw_higher_batch(const dfpsr_image *targetHeight, const dfpsr_image *targetA, const dfpsr_image *targetB, const dfpsr_sprite_draw *draws, int32_t count, void *stream) {
+	if (!exists(targetHeight) || count <= 0) { return 0; }
+	DFPSR_REQUIRE(draws != nullptr, "draw_higher_batch: null draws");
+	static thread_local DeviceBuffer staging;
+	static thread_local SpriteDev *hostStaging = nullptr;
+	static thread_local size_t hostCapacity = 0;
+	if ((size_t)count > hostCapacity) {
+		if (hostStaging) { cudaFreeHost(hostStaging); }
+		hostCapacity = (size_t)count * 2;
+		DFPSR_CHECK_CUDA(cudaMallocHost((void **)&hostStaging, hostCapacity * sizeof(SpriteDev)));
+	}
+	if (staging.reserve((size_t)count * sizeof(SpriteDev))) { return 1; }
+	for (int32_t i = 0; i < count; i++) {
+		hostStaging[i].sourceH = img_of(&draws[i].sourceHeight);
+		hostStaging[i].sourceA = img_of(&draws[i].sourceA);
+		hostStaging[i].sourceB = img_of(&draws[i].sourceB);
+		hostStaging[i].left = draws[i].left; hostStaging[i].top = draws[i].top; hostStaging[i].offset = draws[i].heightOffset;
+	}
+	DFPSR_CHECK_CUDA(cudaMemcpyAsync(staging.ptr, hostStaging, (size_t)count * sizeof(SpriteDev), cudaMemcpyHostToDevice, as_stream(stream)));
+	Img th = img_of(targetHeight);
+	dim3 grid((unsigned)((th.width + 31) / 32), (unsigned)((th.height + 7) / 8));
+	DFPSR_LAUNCH(higher_batch_kernel, grid, 256, 0, as_stream(stream), th, img_of(exists(targetA) ? targetA : nullptr), img_of(exists(targetB) ? targetB : nullptr), (const SpriteDev *)staging.ptr, count);
+	// the pinned staging buffer is reused by the next call on this thread
+	DFPSR_CHECK_CUDA(cudaStreamSynchronize(as_stream(stream)));
+	return 0;
+}
+
+int dfpsr_light_directed(const dfpsr_ortho_view *view, const dfpsr_image *light, const dfpsr_image *normal, const float direction[3], float intensity, const int32_t colorRgb[3], int32_t add, void *stream) {
+	DFPSR_REQUIRE(view && exists(light) && exists(normal) && direction && colorRgb, "light_directed: null argument");
+	DFPSR_REQUIRE(light->width == normal->width && light->height == normal->height, "light_directed: light and normal buffers differ in size");
+	// ref: SDK/SpriteEngine/lightAPI.cpp:26-30 (host-side uniforms)
+	V3 n = normalize3(mat_transform_transposed(view->normalToWorldSpace, V3{direction[0], direction[1], direction[2]}));
+	float rx = -n.x * intensity * 2.0f, ry = -n.y * intensity * 2.0f, rz = -n.z * intensity * 2.0f;
+	float colorR = fmaxf(0.0f, (float)colorRgb[0] / 255.0f), colorG = fmaxf(0.0f, (float)colorRgb[1] / 255.0f), colorB = fmaxf(0.0f, (float)colorRgb[2] / 255.0f);
+	Img l = img_of(light);
+	DFPSR_LAUNCH(directed_kernel, grid_for(l.width, l.height, BLOCK), BLOCK, 0, as_stream(stream), l, img_of(normal), rx, ry, rz, colorR, colorG, colorB, add);
+	return 0;
+}
+
+int dfpsr_light_point(const dfpsr_ortho_view *view, const int32_t worldCenter[2], const dfpsr_image *light, const dfpsr_image *normal, const dfpsr_image *height, const float position[3], float radius, float intensity, const int32_t colorRgb[3], const dfpsr_image *shadowCubeMap, void *stream) {
+	DFPSR_REQUIRE(view && worldCenter && exists(light) && exists(normal) && exists(height) && position && colorRgb, "light_point: null argument");
+	const int32_t laneCount = 4; // laneCountX_32Bit of the reference's SSE2 and scalar builds
+	// ref: SDK/SpriteEngine/lightAPI.cpp:76-105 calculateBound
+	V3 S = mat_transform_transposed(view->normalToWorldSpace, V3{position[0], position[1], position[2]});
+	V3 rotated = mat_transform(view->lightSpaceToScreenDepth, S);
+	int32_t cx = (int32_t)rotated.x + worldCenter[0], cy = (int32_t)rotated.y + worldCenter[1];
+	int32_t pixelRadius = (int32_t)(radius * view->lightSpaceToScreenDepth.xAxis[0]);
+	if (cx < -pixelRadius || cx > light->width + pixelRadius || cy < -pixelRadius || cy > light->height + pixelRadius) { return 0; }
+	int32_t size = (int32_t)((float)pixelRadius * 2.0f);
+	int32_t l = cx - pixelRadius, t = cy - pixelRadius, r = l + size, b = t + size;
+	if (!(l < light->width && r > 0 && t < light->height && b > 0)) { return 0; }
+	l = l > 0 ? l : 0; t = t > 0 ? t : 0; r = r < light->width ? r : light->width; b = b < light->height ? b : light->height;
+	if (r <= l || b <= t) { return 0; }
+	l = (l / laneCount) * laneCount;
+	r = ((r + laneCount - 1) / laneCount) * laneCount;
+	PointLightParams p;
+	p.left = l; p.top = t; p.width = r - l; p.height = b - t; p.laneCount = laneCount;
+	// ref: lightAPI.cpp:190-206
+	V3 origin = mat_transform(view->screenDepthToLightSpace, V3{0.5f - (float)worldCenter[0] + (float)l, 0.5f - (float)worldCenter[1] + (float)t, 0.0f});
+	p.baseX = origin.x - S.x; p.baseY = origin.y - S.y; p.baseZ = origin.z - S.z;
+	p.dxX = view->screenDepthToLightSpace.xAxis[0]; p.dxY = view->screenDepthToLightSpace.xAxis[1]; p.dxZ = view->screenDepthToLightSpace.xAxis[2];
+	p.dyX = view->screenDepthToLightSpace.yAxis[0]; p.dyY = view->screenDepthToLightSpace.yAxis[1]; p.dyZ = view->screenDepthToLightSpace.yAxis[2];
+	p.faceX = view->screenDepthToLightSpace.zAxis[0]; p.faceY = view->screenDepthToLightSpace.zAxis[1]; p.faceZ = view->screenDepthToLightSpace.zAxis[2];
+	p.colorR = fmaxf(0.0f, (float)colorRgb[0] * intensity); p.colorG = fmaxf(0.0f, (float)colorRgb[1] * intensity); p.colorB = fmaxf(0.0f, (float)colorRgb[2] * intensity);
+	p.reciprocalRadius = 1.0f / radius;
+	p.shadow = exists(shadowCubeMap) ? 1 : 0;
+	p.cubeCenter = p.shadow ? (float)shadowCubeMap->width * 0.5f : 0.0f;
+	size_t smem = (size_t)(p.width / laneCount) * 3 * laneCount * sizeof(float);
+	if (smem > 48 * 1024) { DFPSR_CHECK_CUDA(cudaFuncSetAttribute(point_light_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); }
+	DFPSR_LAUNCH(point_light_kernel, p.height, 256, smem, as_stream(stream), img_of(light), img_of(normal), img_of(height), img_of(p.shadow ? shadowCubeMap : nullptr), p);
+	return 0;
+}
+
+int dfpsr_light_blend(const dfpsr_image *color, const dfpsr_image *diffuse, const dfpsr_image *light, void *stream) {
+	DFPSR_REQUIRE(exists(color) && exists(diffuse) && exists(light), "light_blend: null argument");
+	DFPSR_REQUIRE(color->width == diffuse->width && color->height == diffuse->height && color->width == light->width && color->height == light->height, "light_blend: buffers differ in size");
+	Img c = img_of(color);
+	DFPSR_LAUNCH(blend_kernel, grid_for(c.width, c.height, BLOCK), BLOCK, 0, as_stream(stream), c, img_of(diffuse), img_of(light));
+	return 0;
+}
+
+int dfpsr_texture_generate_pyramid(const dfpsr_texture *texture, void *stream) {
+	DFPSR_REQUIRE(texture != nullptr && texture->data != nullptr, "texture_generate_pyramid: texture does not exist");
+	uint32_t *px = (uint32_t *)texture->data;
+	for (uint32_t level = 1; level <= texture->maxMipLevel; level++) {
+		uint32_t tw = 1u << (texture->log2width - level), th = 1u << (texture->log2height - level);
+		const uint32_t *src = px + (texture->startOffset & (texture->maxLevelMask >> (2 * (level - 1))));
+		uint32_t *dst = px + (texture->startOffset & (texture->maxLevelMask >> (2 * level)));
+		dim3 block(32, 8), grid((tw + 31) / 32, (th + 7) / 8);
+		DFPSR_LAUNCH(downsample_kernel, grid, block, 0, as_stream(stream), src, dst, tw, th);
+	}
+	return 0;
+}
+
+size_t dfpsr_filter_resize_scratch_bytes(int32_t sourceWidth, int32_t sourceHeight, int32_t newWidth, int32_t newHeight) {
+	if (newWidth != sourceWidth && newHeight > sourceHeight) { return (size_t)newWidth * (size_t)sourceHeight * 4; }
+	return 0;
+}
+
+int dfpsr_filter_resize(const dfpsr_image *target, const dfpsr_image *source, int32_t sampler, int32_t sourceIsSubImage, void *scratch, void *stream) {
+	DFPSR_REQUIRE(exists(target) && exists(source), "filter_resize: null argument");
+	Img t = img_of(target), s = img_of(source);
+	bool bilinear = sampler == DFPSR_SAMPLER_LINEAR;
+	// ref: api/filterAPI.cpp:298-314 resizeToTarget
+	if (t.width != s.width && t.height > s.height) {
+		DFPSR_REQUIRE(scratch != nullptr, "filter_resize: up-scaling both dimensions needs the scratch buffer (dfpsr_filter_resize_scratch_bytes)");
+		Img temp;
+		temp.data = (uint8_t *)scratch; temp.width = t.width; temp.height = s.height; temp.stride = t.width * 4; temp.packOrder = t.packOrder;
+		if (resize_single(temp, s, bilinear, !sourceIsSubImage, as_stream(stream))) { return 1; }
+		return resize_single(t, temp, bilinear, true, as_stream(stream));
+	}
+	return resize_single(t, s, bilinear, !sourceIsSubImage, as_stream(stream));
+}
+
+int dfpsr_texture_from_image(const dfpsr_texture *texture, const dfpsr_image *image, void *stream) {
+	DFPSR_REQUIRE(texture != nullptr && texture->data != nullptr && exists(image), "texture_from_image: null argument");
+	// ref: api/textureAPI.cpp:89-110: resize into level 0, then the pyramid. The temporary of a two-pass up-scale
+	// is placed in the (not yet generated) lower levels when it fits, else the caller must pre-size with the layout.
+	dfpsr_image level0;
+	level0.data = (void *)(texture->data + texture->startOffset);
+	level0.width = 1 << texture->log2width; level0.height = 1 << texture->log2height;
+	level0.stride = level0.width * 4; level0.packOrder = DFPSR_PACK_RGBA;
+	size_t need = dfpsr_filter_resize_scratch_bytes(image->width, image->height, level0.width, level0.height);
+	static thread_local DeviceBuffer scratch;
+	if (need > 0 && scratch.reserve(need)) { return 1; }
+	if (dfpsr_filter_resize(&level0, image, DFPSR_SAMPLER_LINEAR, 0, scratch.ptr, stream)) { return 1; }
+	return dfpsr_texture_generate_pyramid(texture, stream);
+}
+
+int dfpsr_filter_map(const dfpsr_image *target, int32_t op, const int32_t *params, int32_t paramCount, const dfpsr_image *source, int32_t startX, int32_t startY, void *stream) {
+	if (!exists(target)) { return 0; } // ref: api/filterAPI.cpp:773
+	MapParams mp;
+	memset(&mp, 0, sizeof(mp));
+	mp.op = op; mp.startX = startX; mp.startY = startY;
+	int needed = op == DFPSR_MAP_AFFINE ? 8 : (op == DFPSR_MAP_CONSTANT ? 4 : 0);
+	DFPSR_REQUIRE(op >= DFPSR_MAP_XOR_PATTERN && op <= DFPSR_MAP_CONSTANT, "filter_map: unknown op %d", op);
+	DFPSR_REQUIRE(paramCount >= needed && (needed == 0 || params != nullptr), "filter_map: op %d needs %d parameters", op, needed);
+	for (int i = 0; i < needed; i++) { mp.p[i] = params[i]; }
+	DFPSR_REQUIRE(op != DFPSR_MAP_AFFINE || exists(source), "filter_map: the affine op needs a source image");
+	Img t = img_of(target);
+	DFPSR_LAUNCH(map_kernel, grid_for(t.width, t.height, BLOCK), BLOCK, 0, as_stream(stream), t, img_of(exists(source) ? source : nullptr), mp);
+	return 0;
+}
+
+int dfpsr_filter_block_magnify(const dfpsr_image *target, const dfpsr_image *source, int32_t pixelWidth, int32_t pixelHeight, void *stream) {
+	if (!exists(target) || !exists(source)) { return 0; } // ref: api/filterAPI.cpp:872-876
+	if (pixelWidth < 1) { pixelWidth = 1; }
+	if (pixelHeight < 1) { pixelHeight = 1; }
+	Img t = img_of(target), s = img_of(source);
+	int32_t clipWidth = t.width < s.width * pixelWidth ? t.width : s.width * pixelWidth; clipWidth -= clipWidth % pixelWidth;
+	int32_t clipHeight = t.height < s.height * pixelHeight ? t.height : s.height * pixelHeight; clipHeight -= clipHeight % pixelHeight;
+	DFPSR_LAUNCH(magnify_kernel, grid_for(t.width, t.height, BLOCK), BLOCK, 0, as_stream(stream), t, s, pixelWidth, pixelHeight, clipWidth, clipHeight);
+	return 0;
+}
+
+} // extern "C"
+
+namespace dfpsr {
+
+// ref: api/filterAPI.cpp:156-259 resize_optimized path selection (scaleRegion = whole target)
+static int resize_single(const Img &target, const Img &source, bool bilinear, bool simdAligned, cudaStream_t stream) {
+	bool sameWidth = source.width == target.width, sameHeight = source.height == target.height, samePack = target.packOrder == source.packOrder;
+	if (sameWidth && sameHeight) {
+		Intersection is{0, 0, 0, 0, target.width, target.height};
+		DFPSR_LAUNCH(copy_kernel, grid_for(is.w, is.h, BLOCK), BLOCK, 0, stream, target, source, is, samePack ? 0 : 1);
+		return 0;
+	}
+	ResizeParams rp;
+	rp.offsetX = (int32_t)(65536u * (uint32_t)source.width / (uint32_t)target.width);
+	rp.offsetY = (int32_t)(65536u * (uint32_t)source.height / (uint32_t)target.height);
+	rp.startX = rp.offsetX / 2; rp.startY = rp.offsetY / 2;
+	if (bilinear) { rp.startX -= 32768; rp.startY -= 32768; }
+	rp.bilinear = bilinear ? 1 : 0;
+	if (sameWidth && (samePack || bilinear)) { rp.path = bilinear ? (simdAligned ? RESIZE_VERTICAL_PACKED : RESIZE_VERTICAL) : RESIZE_VERTICAL_NEAREST; }
+	else if (sameHeight) { rp.path = RESIZE_HORIZONTAL; }
+	else { rp.path = RESIZE_GENERAL; }
+	DFPSR_LAUNCH(resize_kernel, grid_for(target.width, target.height, BLOCK), BLOCK, 0, stream, target, source, rp);
+	return 0;
+}
+
+} // namespace dfpsr

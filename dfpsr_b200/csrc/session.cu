@@ -1,0 +1,106 @@
+// session.cu — host-buffer entry points: the reference API works on host images, so a drop-in call has to
+// move the frame's inputs to the device and its result back. A session keeps device mirrors of models and of
+// the render targets so that a frame only moves what changed (geometry on request, the finished colour/depth out).
+#include "common.cuh"
+
+#include <vector>
+#include <new>
+
+using namespace dfpsr;
+
+namespace {
+
+struct ModelSlot {
+	DeviceBuffer points, polygons, diffuse, light;
+	dfpsr_host_model host{};
+	dfpsr_model device{};
+};
+
+} // namespace
+
+struct dfpsr_session {
+	std::vector<ModelSlot *> models;
+	dfpsr_renderer *renderer = nullptr;
+	DeviceBuffer color, depth;
+	~dfpsr_session() {
+		for (ModelSlot *m : models) {
+			m->points.release(); m->polygons.release(); m->diffuse.release(); m->light.release();
+			delete m;
+		}
+		if (renderer) { dfpsr_renderer_destroy(renderer); }
+		color.release(); depth.release();
+	}
+};
+
+static int upload_texture(DeviceBuffer &buffer, dfpsr_texture &device, const uint32_t *pixels, const dfpsr_texture &layout) {
+	device = layout;
+	device.data = nullptr;
+	if (pixels == nullptr) { return 0; }
+	if (buffer.reserve((size_t)layout.totalPixels * 4)) { return 1; }
+	DFPSR_CHECK_CUDA(cudaMemcpy(buffer.ptr, pixels, (size_t)layout.totalPixels * 4, cudaMemcpyHostToDevice));
+	device.data = (const uint32_t *)buffer.ptr;
+	return 0;
+}
+
+extern "C" {
+
+int dfpsr_session_create(dfpsr_session **out) {
+	DFPSR_REQUIRE(out != nullptr, "session_create: null output");
+	*out = new (std::nothrow) dfpsr_session();
+	DFPSR_REQUIRE(*out != nullptr, "out of host memory");
+	if (dfpsr_renderer_create(&(*out)->renderer)) { delete *out; *out = nullptr; return 1; }
+	return 0;
+}
+
+int dfpsr_session_destroy(dfpsr_session *session) {
+	delete session;
+	return 0;
+}
+
+int dfpsr_session_upload_model(dfpsr_session *session, const dfpsr_host_model *model, int32_t *slot) {
+	DFPSR_REQUIRE(session != nullptr && model != nullptr && slot != nullptr, "session_upload_model: null argument");
+	DFPSR_REQUIRE(model->pointCount >= 0 && model->polygonCount >= 0, "session_upload_model: negative counts");
+	ModelSlot *m = new (std::nothrow) ModelSlot();
+	DFPSR_REQUIRE(m != nullptr, "out of host memory");
+	m->host = *model;
+	if (m->points.reserve((size_t)model->pointCount * 12 + 16) || m->polygons.reserve((size_t)model->polygonCount * sizeof(dfpsr_polygon) + 16)) { delete m; return 1; }
+	DFPSR_CHECK_CUDA(cudaMemcpy(m->points.ptr, model->points, (size_t)model->pointCount * 12, cudaMemcpyHostToDevice));
+	DFPSR_CHECK_CUDA(cudaMemcpy(m->polygons.ptr, model->polygons, (size_t)model->polygonCount * sizeof(dfpsr_polygon), cudaMemcpyHostToDevice));
+	m->device.points = (const float *)m->points.ptr;
+	m->device.pointCount = model->pointCount;
+	m->device.polygons = (const dfpsr_polygon *)m->polygons.ptr;
+	m->device.polygonCount = model->polygonCount;
+	m->device.filter = model->filter;
+	if (upload_texture(m->diffuse, m->device.diffuse, model->diffusePixels, model->diffuseLayout)) { delete m; return 1; }
+	if (upload_texture(m->light, m->device.light, model->lightPixels, model->lightLayout)) { delete m; return 1; }
+	for (int k = 0; k < 3; k++) { m->device.minBound[k] = model->minBound[k]; m->device.maxBound[k] = model->maxBound[k]; }
+	session->models.push_back(m);
+	*slot = (int32_t)session->models.size() - 1;
+	return 0;
+}
+
+int dfpsr_session_render_frame_host(dfpsr_session *session, int32_t slot, const dfpsr_transform3d *modelToWorld, const dfpsr_camera *camera, uint32_t *colorHost, int32_t colorStride, float *depthHost, int32_t depthStride, int32_t width, int32_t height, int32_t packOrder, int32_t uploadGeometry, void *stream) {
+	DFPSR_REQUIRE(session != nullptr && modelToWorld != nullptr && camera != nullptr, "session_render_frame_host: null argument");
+	DFPSR_REQUIRE(slot >= 0 && slot < (int32_t)session->models.size(), "session_render_frame_host: model slot %d does not exist", slot);
+	DFPSR_REQUIRE(width > 0 && height > 0, "session_render_frame_host: empty target");
+	cudaStream_t s = as_stream(stream);
+	ModelSlot *m = session->models[slot];
+	if (uploadGeometry) {
+		DFPSR_CHECK_CUDA(cudaMemcpyAsync(m->points.ptr, m->host.points, (size_t)m->host.pointCount * 12, cudaMemcpyHostToDevice, s));
+		DFPSR_CHECK_CUDA(cudaMemcpyAsync(m->polygons.ptr, m->host.polygons, (size_t)m->host.polygonCount * sizeof(dfpsr_polygon), cudaMemcpyHostToDevice, s));
+	}
+	int32_t pitch = ((width * 4 + 255) / 256) * 256; // rows start on 256-byte boundaries: every 16-byte access is aligned
+	if (session->color.reserve((size_t)pitch * height) || session->depth.reserve((size_t)pitch * height)) { return 1; }
+	dfpsr_image color{session->color.ptr, width, height, pitch, packOrder};
+	dfpsr_image depth{session->depth.ptr, width, height, pitch, 0};
+	// image_fill(colour, 0) + image_fill(depth, 0) + renderer_begin (ref: SDK/terrain/main.cpp:397-416), fused into the tile kernel
+	if (dfpsr_renderer_begin_cleared(session->renderer, &color, &depth, 0u, 0.0f)) { return 1; }
+	if (dfpsr_renderer_give_task(session->renderer, &m->device, modelToWorld, camera, stream)) { return 1; }
+	if (dfpsr_renderer_end(session->renderer, stream)) { return 1; }
+	if (colorHost != nullptr) { DFPSR_CHECK_CUDA(cudaMemcpy2DAsync(colorHost, (size_t)colorStride, color.data, (size_t)pitch, (size_t)width * 4, (size_t)height, cudaMemcpyDeviceToHost, s)); }
+	if (depthHost != nullptr) { DFPSR_CHECK_CUDA(cudaMemcpy2DAsync(depthHost, (size_t)depthStride, depth.data, (size_t)pitch, (size_t)width * 4, (size_t)height, cudaMemcpyDeviceToHost, s)); }
+	DFPSR_CHECK_CUDA(cudaStreamSynchronize(s));
+	return 0;
+}
+
+} // extern "C"

@@ -76,9 +76,9 @@ def height_map(size=64, seed=7):
     rng = np.random.default_rng(seed)
     yy, xx = np.mgrid[0:size, 0:size]
     r = np.hypot((xx - size / 2 + 0.5) / (size / 2), (yy - size / 2 + 0.5) / (size / 2))
-    island = np.clip(1.15 - r * r * 1.35, 0.0, 1.0)
+    island = np.clip(1.6 - r * r * 1.0, 0.0, 1.0) * np.clip(1.25 - r * 0.75, 0.0, 1.0)
     noise = 0.6 * _value_noise(size, 4, rng) + 0.3 * _value_noise(size, 8, rng) + 0.1 * _value_noise(size, 16, rng)
-    h = np.clip(island * (0.25 + noise) * 1.3 - 0.12, 0.0, 1.0)
+    h = np.clip(island * (0.25 + noise) * 1.05 - 0.06, 0.0, 1.0)
     return np.round(h * 255).astype(np.uint8)
 
 
@@ -162,7 +162,7 @@ def tiny_triangle_scene(nx=1000, nz=999, seed=3):
 def top_down_camera(nx, nz, width, height):
     """Perspective camera above the centre of the tiny-triangle grid, looking straight down."""
     position = _v([nx * 0.5, nx * 0.5, -nz * 0.5])
-    axes = (_v([1, 0, 0]), _v([0, 0, -1]), _v([0, -1, 0]))  # x right, y = -world z (up on screen is -z), forward = down
+    axes = make_axis_system((0.0, -1.0, 0.0), (0.0, 0.0, 1.0))
     return abi.camera_params(True, abi.Transform3D.make(position, axes), width, height)
 
 

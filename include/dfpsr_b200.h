@@ -185,6 +185,9 @@ int dfpsr_renderer_destroy(dfpsr_renderer *renderer);
 /* ref: api/rendererAPI.h:66 renderer_begin. Either image may have data == NULL. Calling begin twice
  * without end is an error (ref: api/rendererAPI.cpp:152-154). */
 int dfpsr_renderer_begin(dfpsr_renderer *renderer, const dfpsr_image *color, const dfpsr_image *depth);
+/* image_fill(color, packedClearColor) + image_fill(depth, clearDepth) + renderer_begin fused (ref: SDK/terrain/main.cpp:397-416):
+ * the tile kernel starts every tile from the clear values instead of loading it, so the two clears cost no memory pass. */
+int dfpsr_renderer_begin_cleared(dfpsr_renderer *renderer, const dfpsr_image *color, const dfpsr_image *depth, uint32_t packedClearColor, float clearDepth);
 /* ref: api/modelAPI.cpp:214-281 model_render_threaded / renderer_giveTask. Bound culling
  * (Camera::isBoxSeen) is applied on the host exactly like the reference. Enqueues the projection and
  * triangle set-up kernels on `stream`; nothing is drawn before dfpsr_renderer_end. */

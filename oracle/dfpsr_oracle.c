@@ -14,6 +14,13 @@
 #include <string.h>
 #include <float.h>
 
+/* 1 / sqrt(x) of the reference's scalar build (base/simd.h:4104): `1.0f / sqrt(value)` inside namespace dsr resolves to
+ * ::sqrt(double) (checked with a static_assert against the reference headers), so the quotient is formed in double and
+ * rounded to float once. */
+#ifndef ORC_RSQRT
+#define ORC_RSQRT(x) ((float)(1.0 / sqrt((double)(x))))
+#endif
+
 typedef struct { float x, y, z; } v3;
 
 static v3 v3_make(float x, float y, float z) { v3 r = {x, y, z}; return r; }
@@ -894,15 +901,356 @@ void orc_model_render_depth(const dfpsr_model *model, const dfpsr_transform3d *m
 	free(projected);
 }
 
-/* TEMP stubs until implemented */
-void orc_image_fill_rgba(const dfpsr_image *image, int32_t r, int32_t g, int32_t b, int32_t a) {}
-void orc_image_fill_f32(const dfpsr_image *image, float value) {}
-void orc_draw_copy_rgba(const dfpsr_image *target, const dfpsr_image *source, int32_t left, int32_t top) {}
-void orc_draw_copy_f32(const dfpsr_image *target, const dfpsr_image *source, int32_t left, int32_t top) {}
-void orc_draw_higher(const dfpsr_image *targetHeight, const dfpsr_image *sourceHeight, const dfpsr_image *targetA, const dfpsr_image *sourceA, const dfpsr_image *targetB, const dfpsr_image *sourceB, int32_t left, int32_t top, float offset) {}
-void orc_light_directed(const dfpsr_ortho_view *view, const dfpsr_image *light, const dfpsr_image *normal, const float *direction, float intensity, const int32_t *colorRgb, int32_t add) {}
-void orc_light_point(const dfpsr_ortho_view *view, const int32_t *worldCenter, const dfpsr_image *light, const dfpsr_image *normal, const dfpsr_image *height, const float *position, float radius, float intensity, const int32_t *colorRgb, const dfpsr_image *shadowCubeMap, int32_t laneCount) {}
-void orc_light_blend(const dfpsr_image *color, const dfpsr_image *diffuse, const dfpsr_image *light) {}
-void orc_filter_resize(const dfpsr_image *target, const dfpsr_image *source, int32_t sampler, int32_t sourceIsSubImage, uint32_t *scratch) {}
-void orc_filter_map(const dfpsr_image *target, int32_t op, const int32_t *params, const dfpsr_image *source, int32_t startX, int32_t startY) {}
-void orc_filter_block_magnify(const dfpsr_image *target, const dfpsr_image *source, int32_t pixelWidth, int32_t pixelHeight) {}
+
+/* ------------------------------------------------------------------------------------------- 2D draw calls */
+
+static uint32_t pack_bytes_ordered(uint32_t r, uint32_t g, uint32_t b, uint32_t a, int order) {
+	const int *ix = packIndex[order];
+	return (r << (8 * ix[0])) | (g << (8 * ix[1])) | (b << (8 * ix[2])) | (a << (8 * ix[3]));
+}
+static int32_t clamp_i32(int32_t lo, int32_t v, int32_t hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+/* api/imageAPI.cpp:167-185 + api/drawAPI.cpp:72-174 (whole-image rectangle) */
+void orc_image_fill_rgba(const dfpsr_image *image, int32_t r, int32_t g, int32_t b, int32_t a) {
+	if (image == NULL || image->data == NULL) { return; }
+	uint32_t packed = pack_bytes_ordered((uint32_t)clamp_i32(0, r, 255), (uint32_t)clamp_i32(0, g, 255), (uint32_t)clamp_i32(0, b, 255), (uint32_t)clamp_i32(0, a, 255), image->packOrder);
+	for (int32_t y = 0; y < image->height; y++) { for (int32_t x = 0; x < image->width; x++) { *color_px(image, x, y) = packed; } }
+}
+void orc_image_fill_f32(const dfpsr_image *image, float value) {
+	if (image == NULL || image->data == NULL) { return; }
+	for (int32_t y = 0; y < image->height; y++) { for (int32_t x = 0; x < image->width; x++) { *depth_px(image, x, y) = value; } }
+}
+
+/* api/drawAPI.cpp:330-385 ImageIntersection: the part of source placed at (left, top) that lands inside target */
+typedef struct { int32_t tx, ty, sx, sy, w, h; } intersection;
+static int intersect(const dfpsr_image *target, const dfpsr_image *source, int32_t left, int32_t top, intersection *out) {
+	int32_t x0 = imax(left, 0), y0 = imax(top, 0);
+	int32_t x1 = imin(left + source->width, target->width), y1 = imin(top + source->height, target->height);
+	if (x1 <= x0 || y1 <= y0) { return 0; }
+	out->tx = x0; out->ty = y0; out->sx = x0 - left; out->sy = y0 - top; out->w = x1 - x0; out->h = y1 - y0;
+	return 1;
+}
+
+static uint32_t repack(uint32_t c, int sourceOrder, int targetOrder) { /* drawAPI.cpp:508-513 */
+	const int *s = packIndex[sourceOrder];
+	return pack_bytes_ordered((c >> (8 * s[0])) & 255u, (c >> (8 * s[1])) & 255u, (c >> (8 * s[2])) & 255u, (c >> (8 * s[3])) & 255u, targetOrder);
+}
+
+/* api/drawAPI.cpp:492-515 */
+void orc_draw_copy_rgba(const dfpsr_image *target, const dfpsr_image *source, int32_t left, int32_t top) {
+	intersection is;
+	if (target == NULL || source == NULL || target->data == NULL || source->data == NULL || !intersect(target, source, left, top, &is)) { return; }
+	for (int32_t y = 0; y < is.h; y++) {
+		for (int32_t x = 0; x < is.w; x++) {
+			*color_px(target, is.tx + x, is.ty + y) = repack(*color_px(source, is.sx + x, is.sy + y), source->packOrder, target->packOrder);
+		}
+	}
+}
+/* api/drawAPI.cpp:534-539 */
+void orc_draw_copy_f32(const dfpsr_image *target, const dfpsr_image *source, int32_t left, int32_t top) {
+	intersection is;
+	if (target == NULL || source == NULL || target->data == NULL || source->data == NULL || !intersect(target, source, left, top, &is)) { return; }
+	for (int32_t y = 0; y < is.h; y++) {
+		memcpy(depth_px(target, is.tx, is.ty + y), depth_px(source, is.sx, is.sy + y), (size_t)is.w * 4);
+	}
+}
+
+/* api/drawAPI.cpp:834-904 */
+void orc_draw_higher(const dfpsr_image *targetHeight, const dfpsr_image *sourceHeight, const dfpsr_image *targetA, const dfpsr_image *sourceA, const dfpsr_image *targetB, const dfpsr_image *sourceB, int32_t left, int32_t top, float offset) {
+	intersection is;
+	if (targetHeight == NULL || sourceHeight == NULL || targetHeight->data == NULL || sourceHeight->data == NULL) { return; }
+	if (!intersect(targetHeight, sourceHeight, left, top, &is)) { return; }
+	int hasA = targetA != NULL && targetA->data != NULL && sourceA != NULL && sourceA->data != NULL;
+	int hasB = targetB != NULL && targetB->data != NULL && sourceB != NULL && sourceB->data != NULL;
+	for (int32_t y = 0; y < is.h; y++) {
+		for (int32_t x = 0; x < is.w; x++) {
+			float newHeight = *depth_px(sourceHeight, is.sx + x, is.sy + y);
+			if (newHeight > -INFINITY) {
+				newHeight += offset;
+				float *t = depth_px(targetHeight, is.tx + x, is.ty + y);
+				if (newHeight > *t) {
+					*t = newHeight;
+					if (hasA) { *color_px(targetA, is.tx + x, is.ty + y) = repack(*color_px(sourceA, is.sx + x, is.sy + y), sourceA->packOrder, targetA->packOrder); }
+					if (hasB) { *color_px(targetB, is.tx + x, is.ty + y) = repack(*color_px(sourceB, is.sx + x, is.sy + y), sourceB->packOrder, targetB->packOrder); }
+				}
+			}
+		}
+	}
+}
+
+/* ------------------------------------------------------------------------------------------- Sandbox light */
+
+static v3 mat3_transform(const dfpsr_matrix3x3 *m, v3 p) { return mat_transform(m->xAxis, m->yAxis, m->zAxis, p); }
+static v3 mat3_transform_transposed(const dfpsr_matrix3x3 *m, v3 p) { return mat_transform_transposed(m->xAxis, m->yAxis, m->zAxis, p); }
+
+static uint8_t sat_add_u8(uint8_t a, uint8_t b) { uint32_t s = (uint32_t)a + (uint32_t)b; return (uint8_t)(s > 255u ? 255u : s); } /* base/simd.h:2670 */
+
+static uint32_t light_pack(float red, float green, float blue) { /* lightAPI.cpp:52-56 */
+	return saturated_byte(red) | (saturated_byte(green) << 8) | (saturated_byte(blue) << 16);
+}
+static uint32_t sat_add_packed(uint32_t a, uint32_t b) {
+	uint32_t r = 0;
+	for (int s = 0; s < 32; s += 8) { r |= (uint32_t)sat_add_u8((uint8_t)(a >> s), (uint8_t)(b >> s)) << s; }
+	return r;
+}
+
+/* SDK/SpriteEngine/lightAPI.cpp:23-68 */
+void orc_light_directed(const dfpsr_ortho_view *view, const dfpsr_image *light, const dfpsr_image *normal, const float *direction, float intensity, const int32_t *colorRgb, int32_t add) {
+	v3 n = v3_normalize(mat3_transform_transposed(&view->normalToWorldSpace, v3_from(direction)));
+	v3 rev = v3_make(-n.x * intensity * 2.0f, -n.y * intensity * 2.0f, -n.z * intensity * 2.0f);
+	float colorR = fmaxf(0.0f, (float)colorRgb[0] / 255.0f), colorG = fmaxf(0.0f, (float)colorRgb[1] / 255.0f), colorB = fmaxf(0.0f, (float)colorRgb[2] / 255.0f);
+	for (int32_t y = 0; y < light->height; y++) {
+		for (int32_t x = 0; x < light->width; x++) {
+			uint32_t nc = *color_px(normal, x, y);
+			float nx = (float)(nc & 255u) - 128.0f, ny = (float)((nc >> 8) & 255u) - 128.0f, nz = (float)((nc >> 16) & 255u) - 128.0f;
+			float dot = (nx * rev.x) + (ny * rev.y) + (nz * rev.z);
+			float in = dot > 0.0f ? dot : 0.0f;
+			uint32_t packed = light_pack(in * colorR, in * colorG, in * colorB);
+			uint32_t *t = color_px(light, x, y);
+			*t = add ? sat_add_packed(*t, packed) : packed;
+		}
+	}
+}
+
+/* SDK/SpriteEngine/lightAPI.cpp:107-139 */
+static float shadow_transparency(const dfpsr_image *cube, float halfWidth, v3 o) {
+	int32_t width = cube->width;
+	float absX = o.x < 0.0f ? -o.x : o.x, absY = o.y < 0.0f ? -o.y : o.y, absZ = o.z < 0.0f ? -o.z : o.z;
+	int xIsLongest = absX > absY && absX > absZ;
+	int yIsLongerThanZ = absY > absZ;
+	float depth = xIsLongest ? o.x : (yIsLongerThanZ ? o.y : o.z);
+	float slopeUp = (yIsLongerThanZ && !xIsLongest) ? o.z : o.y;
+	float slopeSide = xIsLongest ? -o.z : (yIsLongerThanZ ? -o.x : o.x);
+	int32_t viewOffset = width * (xIsLongest ? 0 : (yIsLongerThanZ ? 2 : 4));
+	int negativeSide = depth < 0.0f;
+	if (negativeSide) { depth = -depth; slopeSide = -slopeSide; viewOffset = viewOffset + width; }
+	float reciDepth = 1.0f / depth;
+	float scale = halfWidth * reciDepth;
+	int32_t sampleX = (int32_t)(halfWidth + (slopeSide * scale));
+	int32_t sampleY = (int32_t)(halfWidth - (slopeUp * scale));
+	int32_t maxPixel = width - 1;
+	sampleX = clamp_i32(0, sampleX, maxPixel);
+	sampleY = clamp_i32(0, sampleY, maxPixel);
+	float shadowReciDepth = *depth_px(cube, sampleX, sampleY + viewOffset);
+	return reciDepth * 1.02f > shadowReciDepth ? 1.0f : 0.0f;
+}
+
+/* SDK/SpriteEngine/lightAPI.cpp:76-105 calculateBound; returns 0 when empty */
+static int light_bound(const dfpsr_ortho_view *view, const int32_t *worldCenter, const dfpsr_image *light, v3 lightSpacePosition, float radius, int32_t alignment, irect *out) {
+	v3 rotated = mat3_transform(&view->lightSpaceToScreenDepth, lightSpacePosition);
+	int32_t cx = (int32_t)rotated.x + worldCenter[0], cy = (int32_t)rotated.y + worldCenter[1];
+	int32_t pixelRadius = (int32_t)(radius * view->lightSpaceToScreenDepth.xAxis[0]);
+	if (cx < -pixelRadius || cx > light->width + pixelRadius || cy < -pixelRadius || cy > light->height + pixelRadius) { return 0; }
+	int32_t size = (int32_t)((float)pixelRadius * 2.0f);
+	irect r = irect_cut(irect_make(0, 0, light->width, light->height), irect_make(cx - pixelRadius, cy - pixelRadius, size, size));
+	if (r.w > 0 && r.h > 0 && alignment > 1) {
+		int32_t left = (r.l / alignment) * alignment; /* non-negative */
+		int32_t right = ((r.l + r.w + alignment - 1) / alignment) * alignment;
+		r = irect_make(left, r.t, right - left, r.h);
+	}
+	*out = r;
+	return r.w > 0 && r.h > 0;
+}
+
+/* SDK/SpriteEngine/lightAPI.cpp:170-273, single job (DISABLE_MULTI_THREADING) */
+void orc_light_point(const dfpsr_ortho_view *view, const int32_t *worldCenter, const dfpsr_image *light, const dfpsr_image *normal, const dfpsr_image *height, const float *position, float radius, float intensity, const int32_t *colorRgb, const dfpsr_image *shadowCubeMap, int32_t laneCount) {
+	v3 S = mat3_transform_transposed(&view->normalToWorldSpace, v3_from(position));
+	irect bound;
+	if (!light_bound(view, worldCenter, light, S, radius, laneCount, &bound)) { return; }
+	v3 face = v3_from(view->screenDepthToLightSpace.zAxis);
+	float colorR = fmaxf(0.0f, (float)colorRgb[0] * intensity), colorG = fmaxf(0.0f, (float)colorRgb[1] * intensity), colorB = fmaxf(0.0f, (float)colorRgb[2] * intensity);
+	float reciprocalRadius = 1.0f / radius;
+	int shadow = shadowCubeMap != NULL && shadowCubeMap->data != NULL;
+	float cubeCenter = shadow ? (float)shadowCubeMap->width * 0.5f : 0.0f;
+	v3 t = mat3_transform(&view->screenDepthToLightSpace, v3_make(0.5f - (float)worldCenter[0] + (float)bound.l, 0.5f - (float)worldCenter[1] + (float)bound.t, 0.0f));
+	v3 base = v3_make(t.x - S.x, t.y - S.y, t.z - S.z);
+	v3 dx = v3_from(view->screenDepthToLightSpace.xAxis), dy = v3_from(view->screenDepthToLightSpace.yAxis);
+	/* createGradient (base/simd.h:474): lane l = start + increment * l (l = 2, 3, ... multiply first) */
+	float rowX[8], rowY[8], rowZ[8];
+	for (int l = 0; l < laneCount; l++) {
+		if (l == 0) { rowX[l] = base.x; rowY[l] = base.y; rowZ[l] = base.z; }
+		else if (l == 1) { rowX[l] = base.x + dx.x; rowY[l] = base.y + dx.y; rowZ[l] = base.z + dx.z; }
+		else { rowX[l] = base.x + dx.x * (float)l; rowY[l] = base.y + dx.y * (float)l; rowZ[l] = base.z + dx.z * (float)l; }
+	}
+	v3 dxX = v3_make(dx.x * (float)laneCount, dx.y * (float)laneCount, dx.z * (float)laneCount);
+	for (int32_t y = bound.t; y < bound.t + bound.h; y++) {
+		float px[8], py[8], pz[8];
+		for (int l = 0; l < laneCount; l++) { px[l] = rowX[l]; py[l] = rowY[l]; pz[l] = rowZ[l]; }
+		for (int32_t x = bound.l; x < bound.l + bound.w; x += laneCount) {
+			for (int l = 0; l < laneCount; l++) {
+				int32_t xx = x + l;
+				if (xx < light->width) { /* lanes past the width land in row padding in the reference */
+					float h = *depth_px(height, xx, y);
+					v3 o = v3_make(px[l] + (face.x * h), py[l] + (face.y * h), pz[l] + (face.z * h));
+					float sq = (o.x * o.x) + (o.y * o.y) + (o.z * o.z);
+					float len = sqrtf(sq);
+					float lightRatio = len * reciprocalRadius;
+					if (1.0f < lightRatio) { lightRatio = 1.0f; } /* min(1.0f, x): base/simd.h:2198-2215 */
+					uint32_t nc = *color_px(normal, xx, y);
+					float nx = ((float)(nc & 255u) - 128.0f) * (-1.0f / 128.0f), ny = ((float)((nc >> 8) & 255u) - 128.0f) * (-1.0f / 128.0f), nz = ((float)((nc >> 16) & 255u) - 128.0f) * (-1.0f / 128.0f);
+					float distanceIntensity = 1.0f - 2.0f * lightRatio + lightRatio * lightRatio;
+					float rs = ORC_RSQRT(sq);
+					float dot = ((o.x * rs) * nx) + ((o.y * rs) * ny) + ((o.z * rs) * nz);
+					float angleIntensity = dot > 0.0f ? dot : 0.0f;
+					float in = angleIntensity * distanceIntensity;
+					if (shadow) { in = in * shadow_transparency(shadowCubeMap, cubeCenter, o); }
+					uint32_t packed = light_pack(in * colorR, in * colorG, in * colorB);
+					uint32_t *target = color_px(light, xx, y);
+					*target = sat_add_packed(*target, packed);
+				}
+				px[l] += dxX.x; py[l] += dxX.y; pz[l] += dxX.z;
+			}
+		}
+		for (int l = 0; l < laneCount; l++) { rowX[l] += dy.x; rowY[l] += dy.y; rowZ[l] += dy.z; }
+	}
+}
+
+/* SDK/SpriteEngine/lightAPI.cpp:287-323 */
+void orc_light_blend(const dfpsr_image *color, const dfpsr_image *diffuse, const dfpsr_image *light) {
+	const float scale = (float)(1.0 / 128.0f);
+	for (int32_t y = 0; y < color->height; y++) {
+		for (int32_t x = 0; x < color->width; x++) {
+			uint32_t d = *color_px(diffuse, x, y), l = *color_px(light, x, y);
+			float red = ((float)(d & 255u) * (float)(l & 255u)) * scale;
+			float green = ((float)((d >> 8) & 255u) * (float)((l >> 8) & 255u)) * scale;
+			float blue = ((float)((d >> 16) & 255u) * (float)((l >> 16) & 255u)) * scale;
+			*color_px(color, x, y) = pack_bytes_ordered(saturated_byte(red), saturated_byte(green), saturated_byte(blue), 0u, color->packOrder);
+		}
+	}
+}
+
+/* ------------------------------------------------------------------------------------------- filters */
+
+typedef struct { int32_t r, g, b, a; } rgba_i32;
+
+static rgba_i32 read_clamp(const dfpsr_image *im, int32_t x, int32_t y) { /* api/imageAPI.h:284-290 */
+	uint32_t c = *color_px(im, clamp_i32(0, x, im->width - 1), clamp_i32(0, y, im->height - 1));
+	const int *ix = packIndex[im->packOrder];
+	rgba_i32 o = {(int32_t)((c >> (8 * ix[0])) & 255u), (int32_t)((c >> (8 * ix[1])) & 255u), (int32_t)((c >> (8 * ix[2])) & 255u), (int32_t)((c >> (8 * ix[3])) & 255u)};
+	return o;
+}
+static uint32_t saturate_and_pack(rgba_i32 c, int order) { /* PackOrder.h:108-110 */
+	return pack_bytes_ordered((uint32_t)clamp_i32(0, c.r, 255), (uint32_t)clamp_i32(0, c.g, 255), (uint32_t)clamp_i32(0, c.b, 255), (uint32_t)clamp_i32(0, c.a, 255), order);
+}
+static rgba_i32 lerp16(rgba_i32 a, rgba_i32 b, uint32_t ratioB) { /* filterAPI.cpp:86-88: (a * (65536 - w) + b * w) >> 16 in u32 */
+	uint32_t ra = 65536u - ratioB;
+	rgba_i32 o = {(int32_t)(((uint32_t)a.r * ra + (uint32_t)b.r * ratioB) >> 16), (int32_t)(((uint32_t)a.g * ra + (uint32_t)b.g * ratioB) >> 16),
+	              (int32_t)(((uint32_t)a.b * ra + (uint32_t)b.b * ratioB) >> 16), (int32_t)(((uint32_t)a.a * ra + (uint32_t)b.a * ratioB) >> 16)};
+	return o;
+}
+static uint32_t mix_colors_uniform(uint32_t a, uint32_t b, uint32_t fineRatio) { /* filterAPI.cpp:49-63 */
+	uint32_t ratio = (fineRatio >> 8) & 0xFFFFu, inv = (256u - ratio) & 0xFFFFu;
+	return weight_colors(a, inv, b, ratio);
+}
+
+/* api/filterAPI.cpp:156-259 resize_optimized + :118-154 resize_reference, scaleRegion = whole target */
+static void resize_single(const dfpsr_image *target, const dfpsr_image *source, int bilinear, int simdAligned) {
+	int32_t tw = target->width, th = target->height, sw = source->width, sh = source->height;
+	int sameWidth = sw == tw, sameHeight = sh == th, samePack = target->packOrder == source->packOrder;
+	if (sameWidth && sameHeight) { orc_draw_copy_rgba(target, source, 0, 0); return; }
+	int32_t offsetX = (int32_t)(65536u * (uint32_t)sw / (uint32_t)tw), offsetY = (int32_t)(65536u * (uint32_t)sh / (uint32_t)th);
+	int32_t startX = offsetX / 2, startY = offsetY / 2;
+	if (bilinear) { startX -= 32768; startY -= 32768; }
+	if (sameWidth && (samePack || bilinear)) {
+		int32_t readY = startY;
+		for (int32_t y = 0; y < th; y++) {
+			uint32_t sampleY = (uint32_t)(readY < 0 ? 0 : readY);
+			uint32_t upperY = sampleY >> 16, lowerY = upperY + 1;
+			if (upperY >= (uint32_t)sh) { upperY = (uint32_t)sh - 1; }
+			if (lowerY >= (uint32_t)sh) { lowerY = (uint32_t)sh - 1; }
+			uint32_t lowerRatio = sampleY & 65535u;
+			for (int32_t x = 0; x < tw; x++) {
+				if (bilinear) {
+					if (simdAligned) {
+						*color_px(target, x, y) = mix_colors_uniform(*color_px(source, x, (int32_t)upperY), *color_px(source, x, (int32_t)lowerY), lowerRatio);
+					} else {
+						*color_px(target, x, y) = saturate_and_pack(lerp16(read_clamp(source, x, (int32_t)upperY), read_clamp(source, x, (int32_t)lowerY), lowerRatio), target->packOrder);
+					}
+				} else {
+					*color_px(target, x, y) = *color_px(source, x, (int32_t)upperY);
+				}
+			}
+			readY += offsetY;
+		}
+	} else if (sameHeight) {
+		for (int32_t y = 0; y < th; y++) {
+			int32_t readX = startX;
+			for (int32_t x = 0; x < tw; x++) {
+				uint32_t sampleX = (uint32_t)(readX < 0 ? 0 : readX);
+				uint32_t leftX = sampleX >> 16, rightRatio = sampleX & 65535u;
+				rgba_i32 c = bilinear ? lerp16(read_clamp(source, (int32_t)leftX, y), read_clamp(source, (int32_t)leftX + 1, y), rightRatio) : read_clamp(source, (int32_t)leftX, y);
+				*color_px(target, x, y) = saturate_and_pack(c, target->packOrder);
+				readX += offsetX;
+			}
+		}
+	} else {
+		int32_t readY = startY;
+		for (int32_t y = 0; y < th; y++) {
+			uint32_t sampleY = (uint32_t)(readY < 0 ? 0 : readY);
+			uint32_t upperY = sampleY >> 16, lowerRatio = sampleY & 65535u;
+			int32_t readX = startX;
+			for (int32_t x = 0; x < tw; x++) {
+				uint32_t sampleX = (uint32_t)(readX < 0 ? 0 : readX);
+				uint32_t leftX = sampleX >> 16, rightRatio = sampleX & 65535u;
+				rgba_i32 c;
+				if (bilinear) { /* filterAPI.cpp:75-93 samplePixel */
+					rgba_i32 upper = lerp16(read_clamp(source, (int32_t)leftX, (int32_t)upperY), read_clamp(source, (int32_t)leftX + 1, (int32_t)upperY), rightRatio);
+					rgba_i32 lower = lerp16(read_clamp(source, (int32_t)leftX, (int32_t)upperY + 1), read_clamp(source, (int32_t)leftX + 1, (int32_t)upperY + 1), rightRatio);
+					c = lerp16(upper, lower, lowerRatio);
+				} else {
+					c = read_clamp(source, (int32_t)leftX, (int32_t)upperY);
+				}
+				*color_px(target, x, y) = saturate_and_pack(c, target->packOrder);
+				readX += offsetX;
+			}
+			readY += offsetY;
+		}
+	}
+}
+
+/* api/filterAPI.cpp:262-314, :852-860 */
+void orc_filter_resize(const dfpsr_image *target, const dfpsr_image *source, int32_t sampler, int32_t sourceIsSubImage, uint32_t *scratch) {
+	int bilinear = sampler == DFPSR_SAMPLER_LINEAR;
+	if (target->width != source->width && target->height > source->height) {
+		dfpsr_image temp = {scratch, target->width, source->height, target->width * 4, target->packOrder};
+		resize_single(&temp, source, bilinear, !sourceIsSubImage);
+		resize_single(target, &temp, bilinear, 1);
+	} else {
+		resize_single(target, source, bilinear, !sourceIsSubImage);
+	}
+}
+
+/* api/filterAPI.cpp:759-777 with the enumerated ops of dfpsr_b200.h */
+void orc_filter_map(const dfpsr_image *target, int32_t op, const int32_t *params, const dfpsr_image *source, int32_t startX, int32_t startY) {
+	if (target == NULL || target->data == NULL) { return; }
+	for (int32_t ty = 0; ty < target->height; ty++) {
+		for (int32_t tx = 0; tx < target->width; tx++) {
+			int32_t x = tx + startX, y = ty + startY;
+			rgba_i32 c = {0, 0, 0, 0};
+			if (op == DFPSR_MAP_XOR_PATTERN) { c.r = x & 255; c.g = y & 255; c.b = (x ^ y) & 255; c.a = 255; }
+			else if (op == DFPSR_MAP_AFFINE) {
+				rgba_i32 s = read_clamp(source, x, y);
+				c.r = s.r * params[0] + params[4]; c.g = s.g * params[1] + params[5]; c.b = s.b * params[2] + params[6]; c.a = s.a * params[3] + params[7];
+			} else if (op == DFPSR_MAP_CONSTANT) { c.r = params[0]; c.g = params[1]; c.b = params[2]; c.a = params[3]; }
+			*color_px(target, tx, ty) = saturate_and_pack(c, target->packOrder);
+		}
+	}
+}
+
+/* api/filterAPI.cpp:724-757 + :340-365 */
+void orc_filter_block_magnify(const dfpsr_image *target, const dfpsr_image *source, int32_t pixelWidth, int32_t pixelHeight) {
+	if (target == NULL || source == NULL || target->data == NULL || source->data == NULL) { return; }
+	if (pixelWidth < 1) { pixelWidth = 1; }
+	if (pixelHeight < 1) { pixelHeight = 1; }
+	int32_t clipWidth = imin(target->width, source->width * pixelWidth); clipWidth -= clipWidth % pixelWidth;
+	int32_t clipHeight = imin(target->height, source->height * pixelHeight); clipHeight -= clipHeight % pixelHeight;
+	for (int32_t y = 0; y < target->height; y++) {
+		for (int32_t x = 0; x < target->width; x++) {
+			uint32_t c = 0;
+			if (x < clipWidth && y < clipHeight) {
+				c = repack(*color_px(source, imin(x / pixelWidth, source->width - 1), imin(y / pixelHeight, source->height - 1)), source->packOrder, target->packOrder);
+			}
+			*color_px(target, x, y) = c;
+		}
+	}
+}

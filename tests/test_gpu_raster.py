@@ -1,0 +1,237 @@
+"""Parity of the CUDA triangle pipeline (through the C ABI) against the oracle: bit-exact colour and depth."""
+import ctypes as C
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import orcbind
+from dfpsr_b200 import abi, lib, scenes
+from gpuutil import CudaScene, assert_same_u32, bits, dev, host_f32, host_u32
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "raster.json")
+
+
+def test_project_points(cuda, oracle):
+    sc = scenes.terrain_scene()
+    cam_params = scenes.orbit_camera(5, 1920, 1080)
+    cam = lib.camera(cam_params)
+    assert bytes(cam) == bytes(orcbind.camera(cam_params))
+    m2w = abi.Transform3D.identity()
+    pts = dev(sc["points"].reshape(-1))
+    import torch
+    out = torch.zeros(len(sc["points"]) * 40, dtype=torch.uint8, device="cuda")
+    lib.check(cuda.dfpsr_project_points(pts.data_ptr(), len(sc["points"]), C.byref(m2w), C.byref(cam), out.data_ptr(), lib.stream_ptr()))
+    got = out.cpu().numpy().view(abi.PROJECTED_DTYPE)
+    expected = np.zeros(len(sc["points"]), abi.PROJECTED_DTYPE)
+    oracle.orc_project_points(orcbind.ptr(sc["points"]), len(sc["points"]), C.byref(m2w), C.byref(orcbind.camera(cam_params)), orcbind.ptr(expected))
+    for field in ("cs", "is", "flat"):
+        assert np.array_equal(got[field].view(np.uint8), expected[field].view(np.uint8)), field
+
+
+@pytest.mark.parametrize("frame", [0, 7, 23])
+def test_terrain_matches_oracle(cuda, oracle, frame):
+    sc = scenes.terrain_scene()
+    scene = CudaScene(sc["points"], sc["polygons"], diffuse_level0=sc["texture"], diffuse_levels=5)
+    w, h = 640, 360
+    cam = scenes.orbit_camera(frame, w, h)
+    c0, d0 = np.zeros((h, w), np.uint32), np.zeros((h, w), np.float32)
+    got_c, got_d = scene.render_cuda(cuda, cam, c0, d0)
+    exp_c, exp_d, commands = scene.render_oracle(oracle, cam, c0, d0)
+    assert commands > 500
+    assert_same_u32(bits(got_d), bits(exp_d), "depth")
+    assert_same_u32(got_c, exp_c, "colour")
+
+
+CASES = [
+    dict(textured=False, light=False, vcol=True, alpha=False, pack=0),
+    dict(textured=True, light=False, vcol=False, alpha=False, pack=0),
+    dict(textured=True, light=False, vcol=True, alpha=False, pack=1),
+    dict(textured=True, light=True, vcol=True, alpha=False, pack=2),
+    dict(textured=False, light=True, vcol=False, alpha=False, pack=3),
+    dict(textured=False, light=True, vcol=True, alpha=False, pack=0),
+    dict(textured=True, light=True, vcol=False, alpha=False, pack=0),
+    dict(textured=True, light=False, vcol=True, alpha=True, pack=0),
+    dict(textured=False, light=False, vcol=True, alpha=True, pack=1),
+    dict(textured=True, light=False, vcol=True, alpha=True, pack=0, use_depth=False),
+    dict(textured=True, light=False, vcol=True, alpha=False, pack=0, use_depth=False),
+    dict(textured=True, light=False, vcol=True, alpha=False, pack=0, use_color=False),
+    dict(textured=True, light=False, vcol=True, alpha=False, pack=0, persp=False),
+    dict(textured=False, light=False, vcol=True, alpha=True, pack=0, persp=False),
+    dict(textured=True, light=False, vcol=True, alpha=False, pack=0, far=float("inf")),
+    dict(textured=True, light=False, vcol=True, alpha=False, pack=0, far=5.0),
+]
+
+
+def soup_case(seed, textured, light, vcol, alpha, pack, use_color=True, use_depth=True, persp=True, far=1000.0, n=300, w=320, h=200):
+    soup = scenes.random_soup(n, seed, textured=textured or light, vertex_colors=vcol, alpha=alpha)
+    filt = abi.FILTER_ALPHA if alpha else abi.FILTER_SOLID
+    scene = CudaScene(soup["points"], soup["polygons"], filt,
+                      scenes.checker_texture(64, seed + 1) if textured else None, 4,
+                      scenes.checker_texture(32, seed + 2) if light else None, 1)
+    rng = np.random.default_rng(seed)
+    pos = (rng.random(3) * 2 - 1) * 2
+    target = (rng.random(3) * 2 - 1) * 3
+    cam = abi.camera_params(persp, scenes.look_at_transform(pos, target), w, h, width_slope=(1.0 if persp else 6.0), far=far)
+    color = rng.integers(0, 2 ** 32, (h, w), dtype=np.uint32) if use_color else None
+    depth = (np.zeros((h, w), np.float32) if persp else np.full((h, w), 1e9, np.float32)) if use_depth else None
+    return scene, cam, color, depth
+
+
+@pytest.mark.parametrize("case", range(len(CASES)))
+@pytest.mark.parametrize("seed", [0, 1])
+def test_random_soup_matches_oracle(cuda, oracle, case, seed):
+    """Triangles around and behind the camera: culling, near/side clipping, every shader variant, alpha filter,
+    light maps, all pack orders, colour-only / depth-only targets, orthogonal cameras, no / near far plane."""
+    cfg = CASES[case]
+    scene, cam, color, depth = soup_case(100 * case + seed, **cfg)
+    got_c, got_d = scene.render_cuda(cuda, cam, color, depth, cfg["pack"])
+    exp_c, exp_d, commands = scene.render_oracle(oracle, cam, color, depth, cfg["pack"])
+    assert commands > 10
+    if depth is not None:
+        assert_same_u32(bits(got_d), bits(exp_d), "depth")
+    if color is not None:
+        assert_same_u32(got_c, exp_c, "colour")
+
+
+def test_submission_order_across_models(cuda, oracle):
+    """Two models in one renderer_begin/end frame: the second (alpha-filtered) must blend over the first."""
+    a = scenes.random_soup(150, 11, textured=False)
+    b = scenes.random_soup(150, 12, textured=False, alpha=True)
+    sa = CudaScene(a["points"], a["polygons"], abi.FILTER_SOLID)
+    sb = CudaScene(b["points"], b["polygons"], abi.FILTER_ALPHA)
+    w, h = 256, 160
+    cam_params = abi.camera_params(True, scenes.look_at_transform((0.3, 0.1, -0.5), (0, 0, 2)), w, h)
+    cam = lib.camera(cam_params)
+    c0 = np.full((h, w), 0x80402010, np.uint32)
+    d0 = np.zeros((h, w), np.float32)
+    tc, td = dev(c0), dev(d0)
+    r = C.c_void_p()
+    lib.check(cuda.dfpsr_renderer_create(C.byref(r)))
+    ident = abi.Transform3D.identity()
+    lib.check(cuda.dfpsr_renderer_begin(r, C.byref(lib.image(tc)), C.byref(lib.image(td))))
+    assert cuda.dfpsr_renderer_begin(r, C.byref(lib.image(tc)), C.byref(lib.image(td))) != 0  # begin twice is an error
+    assert b"twice" in cuda.dfpsr_last_error()
+    lib.check(cuda.dfpsr_renderer_give_task(r, C.byref(sa.model.desc), C.byref(ident), C.byref(cam), lib.stream_ptr()))
+    lib.check(cuda.dfpsr_renderer_give_task(r, C.byref(sb.model.desc), C.byref(ident), C.byref(cam), lib.stream_ptr()))
+    lib.check(cuda.dfpsr_renderer_end(r, lib.stream_ptr()))
+    assert cuda.dfpsr_renderer_end(r, lib.stream_ptr()) != 0  # end without begin is an error
+    count = C.c_int64()
+    lib.check(cuda.dfpsr_renderer_last_command_count(r, C.byref(count), lib.stream_ptr()))
+    lib.check(cuda.dfpsr_renderer_destroy(r))
+    ec, ed, n1 = sa.render_oracle(oracle, cam_params, c0, d0)
+    ec, ed, n2 = sb.render_oracle(oracle, cam_params, ec, ed)
+    assert count.value == n1 + n2
+    assert_same_u32(bits(host_f32(td)), bits(ed), "depth")
+    assert_same_u32(host_u32(tc), ec, "colour")
+
+
+def test_begin_cleared_equals_fill_then_render(cuda, oracle):
+    sc = scenes.terrain_scene()
+    scene = CudaScene(sc["points"], sc["polygons"], diffuse_level0=sc["texture"], diffuse_levels=5)
+    w, h = 322, 182  # not a multiple of the tile size
+    cam_params = scenes.orbit_camera(3, w, h)
+    cam = lib.camera(cam_params)
+    rng = np.random.default_rng(1)
+    tc, td = dev(rng.integers(0, 2 ** 32, (h, w), dtype=np.uint32)), dev(rng.random((h, w)).astype(np.float32))
+    r = C.c_void_p()
+    lib.check(cuda.dfpsr_renderer_create(C.byref(r)))
+    ident = abi.Transform3D.identity()
+    lib.check(cuda.dfpsr_renderer_begin_cleared(r, C.byref(lib.image(tc)), C.byref(lib.image(td)), 0, 0.0))
+    lib.check(cuda.dfpsr_renderer_give_task(r, C.byref(scene.model.desc), C.byref(ident), C.byref(cam), lib.stream_ptr()))
+    lib.check(cuda.dfpsr_renderer_end(r, lib.stream_ptr()))
+    lib.check(cuda.dfpsr_renderer_destroy(r))
+    ec, ed, _ = scene.render_oracle(oracle, cam_params, np.zeros((h, w), np.uint32), np.zeros((h, w), np.float32))
+    assert_same_u32(bits(host_f32(td)), bits(ed), "depth")
+    assert_same_u32(host_u32(tc), ec, "colour")
+
+
+@pytest.mark.parametrize("persp", [True, False])
+def test_render_depth_matches_oracle(cuda, oracle, persp):
+    soup = scenes.random_soup(200, 9, textured=False)
+    scene = CudaScene(soup["points"], soup["polygons"])
+    cam_params = abi.camera_params(persp, scenes.look_at_transform((0.5, 0.2, -0.3), (1, 0.5, 2)), 256, 256, width_slope=(1.0 if persp else 5.0))
+    init = np.zeros((256, 256), np.float32) if persp else np.full((256, 256), 1e9, np.float32)
+    td = dev(init)
+    ident = abi.Transform3D.identity()
+    lib.check(cuda.dfpsr_model_render_depth(C.byref(scene.model.desc), C.byref(ident), C.byref(lib.image(td)), C.byref(lib.camera(cam_params)), lib.stream_ptr()))
+    expected = init.copy()
+    oracle.orc_model_render_depth(C.byref(scene.o_model), C.byref(ident), C.byref(orcbind.image_of(expected)), C.byref(orcbind.camera(cam_params)))
+    assert (expected != init).mean() > 0.2
+    assert_same_u32(bits(host_f32(td)), bits(expected), "depth")
+
+
+def test_pre_projected_triangles(cuda, oracle):
+    """renderer_giveTask_triangle: projected points come from the caller (host)."""
+    soup = scenes.random_soup(120, 21, textured=True)
+    w, h = 200, 120
+    cam_params = abi.camera_params(True, scenes.look_at_transform((0.1, 0.4, -0.2), (0.5, 0, 2)), w, h)
+    ocam = orcbind.camera(cam_params)
+    ident = abi.Transform3D.identity()
+    projected = np.zeros(len(soup["points"]), abi.PROJECTED_DTYPE)
+    oracle.orc_project_points(orcbind.ptr(soup["points"]), len(soup["points"]), C.byref(ident), C.byref(ocam), orcbind.ptr(projected))
+    tris = np.zeros(len(soup["polygons"]), abi.TRIANGLE_DTYPE)
+    idx = soup["polygons"]["pointIndices"][:, :3]
+    tris["pos"] = projected[idx]
+    tris["colors"] = soup["polygons"]["colors"][:, :3]
+    tris["texCoords"] = soup["polygons"]["texCoords"][:, :3]
+    tex0 = scenes.checker_texture(64, 3)
+    dtex = lib.DeviceTexture(tex0, 3)
+    obuf, otex = orcbind.build_texture(tex0, 3)
+    c0, d0 = np.zeros((h, w), np.uint32), np.zeros((h, w), np.float32)
+    tc, td = dev(c0), dev(d0)
+    r = C.c_void_p()
+    lib.check(cuda.dfpsr_renderer_create(C.byref(r)))
+    lib.check(cuda.dfpsr_renderer_begin(r, C.byref(lib.image(tc)), C.byref(lib.image(td))))
+    lib.check(cuda.dfpsr_renderer_give_task_triangles(r, tris.ctypes.data, len(tris), C.byref(dtex.desc), None, abi.FILTER_SOLID, C.byref(lib.camera(cam_params)), lib.stream_ptr()))
+    lib.check(cuda.dfpsr_renderer_end(r, lib.stream_ptr()))
+    lib.check(cuda.dfpsr_renderer_destroy(r))
+    ec, ed = c0.copy(), d0.copy()
+    oracle.orc_render_triangles(tris.ctypes.data, len(tris), C.byref(otex), None, abi.FILTER_SOLID, C.byref(orcbind.image_of(ec)), C.byref(orcbind.image_of(ed)), C.byref(ocam))
+    assert (ed > 0).mean() > 0.2
+    assert_same_u32(bits(host_f32(td)), bits(ed), "depth")
+    assert_same_u32(host_u32(tc), ec, "colour")
+
+
+def test_many_triangles_per_tile(cuda, oracle):
+    """More entries in one tile than the shared-memory sort window holds would need >16384; exercise a long list (several chunks)."""
+    soup = scenes.random_soup(3000, 31, extent=1.5, tri_size=1.0, textured=False)
+    scene = CudaScene(soup["points"], soup["polygons"])
+    w, h = 96, 64
+    cam = abi.camera_params(True, scenes.look_at_transform((0, 0, -4), (0, 0, 0)), w, h)
+    c0, d0 = np.zeros((h, w), np.uint32), np.zeros((h, w), np.float32)
+    got_c, got_d = scene.render_cuda(cuda, cam, c0, d0)
+    exp_c, exp_d, commands = scene.render_oracle(oracle, cam, c0, d0)
+    assert commands > 1000
+    assert_same_u32(bits(got_d), bits(exp_d), "depth")
+    assert_same_u32(got_c, exp_c, "colour")
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def test_terrain_1080p_golden(cuda):
+    """BASELINE config 1 at full size against hashes produced by the compiled reference (tests/golden/make_golden.py)."""
+    golden = json.load(open(GOLDEN))["terrain_1080p"]
+    sc = scenes.terrain_scene()
+    scene = CudaScene(sc["points"], sc["polygons"], diffuse_level0=sc["texture"], diffuse_levels=5)
+    for entry in golden:
+        cam = scenes.orbit_camera(entry["frame"], 1920, 1080)
+        c, d = scene.render_cuda(cuda, cam, np.zeros((1080, 1920), np.uint32), np.zeros((1080, 1920), np.float32))
+        assert sha(d) == entry["depth_sha256"], f"frame {entry['frame']} depth"
+        assert sha(c) == entry["color_sha256"], f"frame {entry['frame']} colour"
+
+
+def test_tiny_triangles_4k_golden(cuda):
+    """BASELINE config 3 (2 M tiny vertex-coloured triangles at 3840x2160) against the reference's hashes."""
+    golden = json.load(open(GOLDEN))["tiny_4k"]
+    sc = scenes.tiny_triangle_scene(golden["nx"], golden["nz"])
+    scene = CudaScene(sc["points"], sc["polygons"])
+    cam = scenes.top_down_camera(golden["nx"], golden["nz"], 3840, 2160)
+    c, d = scene.render_cuda(cuda, cam, np.zeros((2160, 3840), np.uint32), np.zeros((2160, 3840), np.float32))
+    assert sha(d) == golden["depth_sha256"]
+    assert sha(c) == golden["color_sha256"]

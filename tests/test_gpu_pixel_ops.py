@@ -83,9 +83,10 @@ def test_light_passes(cuda, oracle):
         e = light0.copy()
         oracle.orc_light_directed(C.byref(view), C.byref(OI(e)), C.byref(OI(normal)), orcbind.ptr(d), 0.8, orcbind.ptr(col), add)
         assert_same_u32(host_u32(tl), e, f"directed add={add}")
+    t_diffuse, t_light0, t_normal, t_height = dev(diffuse), dev(light0), dev(normal), dev(height)
     for pack in range(4):
         tc = dev(np.zeros((h, w), np.uint32))
-        lib.check(cuda.dfpsr_light_blend(C.byref(IM(tc, pack)), C.byref(IM(dev(diffuse))), C.byref(IM(dev(light0))), lib.stream_ptr()))
+        lib.check(cuda.dfpsr_light_blend(C.byref(IM(tc, pack)), C.byref(IM(t_diffuse)), C.byref(IM(t_light0)), lib.stream_ptr()))
         e = np.zeros((h, w), np.uint32)
         oracle.orc_light_blend(C.byref(OI(e, pack)), C.byref(OI(diffuse)), C.byref(OI(light0)))
         assert_same_u32(host_u32(tc), e, f"blend pack={pack}")
@@ -94,7 +95,7 @@ def test_light_passes(cuda, oracle):
         p, col = np.array(pos, np.float32), np.array([255, 180, 120], np.int32)
         tl = dev(light0)
         tcube = dev(cube) if use_cube else None
-        lib.check(cuda.dfpsr_light_point(C.byref(view), wc.ctypes.data, C.byref(IM(tl)), C.byref(IM(dev(normal))), C.byref(IM(dev(height))), p.ctypes.data, rad, 1.3, col.ctypes.data, C.byref(IM(tcube)), lib.stream_ptr()))
+        lib.check(cuda.dfpsr_light_point(C.byref(view), wc.ctypes.data, C.byref(IM(tl)), C.byref(IM(t_normal)), C.byref(IM(t_height)), p.ctypes.data, rad, 1.3, col.ctypes.data, C.byref(IM(tcube)), lib.stream_ptr()))
         e = light0.copy()
         oracle.orc_light_point(C.byref(view), orcbind.ptr(wc), C.byref(OI(e)), C.byref(OI(normal)), C.byref(OI(height)), orcbind.ptr(p), rad, 1.3, orcbind.ptr(col), C.byref(OI(cube if use_cube else None)), 4)
         assert_same_u32(host_u32(tl), e, f"point light {pos} r={rad} cube={use_cube}")
@@ -161,7 +162,8 @@ def test_texture_pyramid_and_from_image(cuda, oracle):
     lib.check(cuda.dfpsr_texture_layout(C.byref(desc), 100, 50, 4))
     px = torch.zeros(desc.totalPixels, dtype=torch.int32, device="cuda")
     desc.data = px.data_ptr()
-    lib.check(cuda.dfpsr_texture_from_image(C.byref(desc), C.byref(IM(dev(img))), lib.stream_ptr()))
+    t_img = dev(img)
+    lib.check(cuda.dfpsr_texture_from_image(C.byref(desc), C.byref(IM(t_img)), lib.stream_ptr()))
     ot = abi.Texture()
     oracle.orc_texture_layout(C.byref(ot), 100, 50, 4)
     ebuf = np.zeros(ot.totalPixels, np.uint32)

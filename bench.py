@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the rendering hot path (see BASELINE.json / SURVEY.md §8d).
+
+Workload (config.workload = "terrain_1080p_views"): BASELINE config 4 — a batch of independent 1920x1080 camera views of
+the terrain scene (config 1's scene: 4096 points, ~7.6 k triangles, 1024x1024 texture with 5 mip levels), each view into
+its own RGBA8 colour + F32 depth target, cleared and rendered through dfpsr_model_render_views. One step = `--views`
+views per GPU (default 256); ranks render disjoint view sets with no collective (weak scaling).
+  value   frames/s over all ranks, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e     the same views through the host-buffer entry point dfpsr_session_render_frame_host: geometry uploaded from
+          pinned host memory and the finished colour image downloaded every frame
+  --impl reference   the unmodified reference renderer (oracle/_ref, SSE2 build, its own worker threads) on the host CPU
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+WIDTH, HEIGHT = 1920, 1080
+# final colour+depth stores 8 B x 2 073 600 px + unique texture bytes (<= 5.59 MB) + geometry 0.60 MB
+ALGORITHMIC_BYTES_PER_FRAME = 8 * WIDTH * HEIGHT + 1396736 * 4 + (4096 * 12 + 3788 * 144)
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+
+    QUERY = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, device_index):
+        self.device_index, self.proc, self.lines = device_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.device_index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm, sm_max, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                sm_max = float(f[2])
+            except ValueError:
+                continue
+            for name, value in zip(names, f[5:9]):
+                if value.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": sm_max, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def reference_arm(args, rank):
+    """The reference's own CPU implementation of the workload (rank 0 only)."""
+    if rank != 0:
+        return
+    import refbind
+    from dfpsr_b200 import abi, scenes
+    sc = scenes.terrain_scene()
+    frames_per_step = 16
+    if refbind.available("sse"):
+        ref = refbind.Ref("sse")
+        kind, cores = "reference", max(min(ref.lib.ref_thread_count() - 1, 12), 1)
+        tex = ref.texture(sc["texture"], 5)
+        model = ref.model(sc["points"], sc["polygons"], diffuse=tex)
+        col, dep = ref.rgba(shape=(HEIGHT, WIDTH)), ref.f32(shape=(HEIGHT, WIDTH))
+        ident = abi.Transform3D.identity()
+
+        def frame(i):
+            cam = scenes.orbit_camera(i % args.views, WIDTH, HEIGHT, frames_per_lap=args.views)
+            ref.lib.ref_terrain_frame(model, C.byref(ident), col, dep, C.byref(cam))
+    else:
+        import orcbind
+        lib = orcbind.load()
+        kind, cores = "port", 1
+        buf, tex = orcbind.build_texture(sc["texture"], 5)
+        model, keep = orcbind.model_of(sc["points"], sc["polygons"], diffuse=tex)
+        c, d = np.zeros((HEIGHT, WIDTH), np.uint32), np.zeros((HEIGHT, WIDTH), np.float32)
+        ident = abi.Transform3D.identity()
+
+        def frame(i):
+            c[:] = 0
+            d[:] = 0
+            cam = orcbind.camera(scenes.orbit_camera(i % args.views, WIDTH, HEIGHT, frames_per_lap=args.views))
+            lib.orc_model_render(C.byref(model), C.byref(ident), C.byref(orcbind.image_of(c)), C.byref(orcbind.image_of(d)), C.byref(cam))
+    n = 0
+    for _ in range(args.warmup):
+        for _ in range(frames_per_step):
+            frame(n)
+            n += 1
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        for _ in range(frames_per_step):
+            frame(n)
+            n += 1
+    elapsed = time.perf_counter() - t0
+    fps = args.steps * frames_per_step / elapsed
+    sample = f"{frames_per_step} consecutive orbit views per step (of the {args.views}-view batch), image_fill x2 + renderer_begin/giveTask/end each, host memory"
+    print(json.dumps({
+        "impl": "reference", "metric": "frames/s at 1920x1080, terrain view batch", "value": fps, "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * elapsed / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "terrain_1080p_views", "views_per_step_per_gpu": args.views, "width": WIDTH, "height": HEIGHT},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "mpix_per_s": fps * WIDTH * HEIGHT / 1e6,
+    }))
+
+
+def cpu_baseline(views, seconds=12.0):
+    """The reference (SSE2 build, multi-threaded) on this box's host cores, bounded sample of the same workload."""
+    import refbind
+    from dfpsr_b200 import abi, scenes
+    if not refbind.available("sse"):
+        return None
+    ref = refbind.Ref("sse")
+    sc = scenes.terrain_scene()
+    tex = ref.texture(sc["texture"], 5)
+    model = ref.model(sc["points"], sc["polygons"], diffuse=tex)
+    col, dep = ref.rgba(shape=(HEIGHT, WIDTH)), ref.f32(shape=(HEIGHT, WIDTH))
+    ident = abi.Transform3D.identity()
+    for i in range(3):
+        ref.lib.ref_terrain_frame(model, C.byref(ident), col, dep, C.byref(scenes.orbit_camera(i, WIDTH, HEIGHT, frames_per_lap=views)))
+    t0, n = time.perf_counter(), 0
+    while time.perf_counter() - t0 < seconds:
+        ref.lib.ref_terrain_frame(model, C.byref(ident), col, dep, C.byref(scenes.orbit_camera(n % views, WIDTH, HEIGHT, frames_per_lap=views)))
+        n += 1
+    elapsed = time.perf_counter() - t0
+    threads = ref.lib.ref_thread_count()
+    ref.free_all()
+    return {"value": n / elapsed, "unit": "frames/s", "cores": max(min(threads - 1, 12), 1), "kind": "reference",
+            "sample": f"{n} orbit views in {elapsed:.1f} s through the unmodified reference (oracle/_ref, g++ -O2 SSE2 build, {threads} hardware threads): image_fill x2 + renderer_begin/giveTask/end per view"}
+
+
+def main():
+    parser = argparse.ArgumentParser()
+    parser.add_argument("--gpus", type=int, default=1)
+    parser.add_argument("--steps", type=int, default=5)
+    parser.add_argument("--warmup", type=int, default=3)
+    parser.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    parser.add_argument("--views", type=int, default=256, help="views per step per GPU")
+    parser.add_argument("--no-cpu-baseline", action="store_true")
+    parser.add_argument("--no-extras", action="store_true")
+    args = parser.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        reference_arm(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from dfpsr_b200 import abi, lib, scenes
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    cuda = lib.load()
+    lib.check(cuda.dfpsr_init(local_rank))
+    distributed = world > 1
+    if distributed:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    sc = scenes.terrain_scene()
+    texture = lib.DeviceTexture(sc["texture"], 5)
+    model = lib.DeviceModel(sc["points"], sc["polygons"], abi.FILTER_SOLID, texture)
+    views = args.views
+    # each rank renders its own arc of the orbit: view v of rank r is orbit frame r * views + v of a (world * views)-frame lap
+    cameras = (abi.Camera * views)()
+    for v in range(views):
+        cameras[v] = lib.camera(scenes.orbit_camera(rank * views + v, WIDTH, HEIGHT, frames_per_lap=world * views))
+    color = torch.empty((views, HEIGHT, WIDTH), dtype=torch.int32, device="cuda")
+    depth = torch.empty((views, HEIGHT, WIDTH), dtype=torch.float32, device="cuda")
+    colors = (abi.Image * views)(*[lib.image(color[v]) for v in range(views)])
+    depths = (abi.Image * views)(*[lib.image(depth[v]) for v in range(views)])
+    ident = abi.Transform3D.identity()
+    stream = torch.cuda.current_stream()
+    sp = lib.stream_ptr(stream)
+
+    def step():
+        lib.check(cuda.dfpsr_model_render_views(C.byref(model.desc), C.byref(ident), colors, depths, cameras, views, 1, sp))
+
+    def barrier():
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    cuda.dfpsr_reset_launch_count()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record(stream)
+    for _ in range(args.steps):
+        step()
+    stop.record(stream)
+    barrier()
+    elapsed_ms = torch.tensor([start.elapsed_time(stop)], dtype=torch.float64, device="cuda")
+    launches = int(cuda.dfpsr_launch_count())
+    clocks = sampler.stop() if rank == 0 else None
+    if distributed:
+        dist.all_reduce(elapsed_ms, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(elapsed_ms.item())
+    total_frames = world * views * args.steps
+    fps = total_frames / (elapsed_ms / 1000.0)
+
+    # ---- roofline of the dominant kernel (raster_kernel), per-launch device time from CUDA events on the launching stream
+    lib.check(cuda.dfpsr_profile_reset())
+    lib.check(cuda.dfpsr_profile_enable(1))
+    step()
+    torch.cuda.synchronize()
+    lib.check(cuda.dfpsr_profile_enable(0))
+    profile = lib.profile_snapshot()
+    total_kernel_ms = sum(ms for ms, _ in profile.values())
+    raster_ms, raster_launches = profile.get("raster_kernel", (0.0, 0))
+    peak, peak_source = load_peaks()
+    achieved = (ALGORITHMIC_BYTES_PER_FRAME / 1e9) / (raster_ms / 1000.0 / max(raster_launches, 1)) if raster_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "kernel": "raster_kernel", "avg_launch_us": 1000.0 * raster_ms / max(raster_launches, 1),
+                "algorithmic_bytes_per_launch": ALGORITHMIC_BYTES_PER_FRAME, "peak_source": peak_source,
+                "kernel_share_of_device_time": raster_ms / total_kernel_ms if total_kernel_ms > 0 else None,
+                "per_kernel_us_per_frame": {k: 1000.0 * ms / views for k, (ms, n) in sorted(profile.items())}}
+
+    # ---- end to end through the host-buffer entry point: pinned host geometry in, finished colour image out, every frame
+    session = C.c_void_p()
+    lib.check(cuda.dfpsr_session_create(C.byref(session)))
+    pts_host = torch.from_numpy(np.ascontiguousarray(sc["points"], np.float32)).pin_memory()
+    poly_host = torch.from_numpy(np.ascontiguousarray(sc["polygons"]).view(np.uint8)).pin_memory()
+    tex_host = texture.pixels.cpu()
+    hm = abi.HostModel()
+    hm.points, hm.pointCount = pts_host.data_ptr(), len(sc["points"])
+    hm.polygons, hm.polygonCount = poly_host.data_ptr(), len(sc["polygons"])
+    hm.filter = abi.FILTER_SOLID
+    hm.diffusePixels, hm.diffuseLayout = tex_host.data_ptr(), texture.desc
+    hm.minBound[:], hm.maxBound[:] = model.desc.minBound[:], model.desc.maxBound[:]
+    slot = C.c_int32()
+    lib.check(cuda.dfpsr_session_upload_model(session, C.byref(hm), C.byref(slot)))
+    color_host = torch.empty((HEIGHT, WIDTH), dtype=torch.int32).pin_memory()
+    e2e_views = min(views, 64)
+
+    def e2e_step():
+        for v in range(e2e_views):
+            lib.check(cuda.dfpsr_session_render_frame_host(session, slot.value, C.byref(ident), C.byref(cameras[v]), color_host.data_ptr(), WIDTH * 4, None, 0, WIDTH, HEIGHT, abi.PACK_RGBA, 1, sp))
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(args.steps // 2, 1)
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_elapsed = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if distributed:
+        dist.all_reduce(e2e_elapsed, op=dist.ReduceOp.MAX)
+    e2e_fps = world * e2e_views * e2e_steps / float(e2e_elapsed.item())
+    lib.check(cuda.dfpsr_session_destroy(session))
+    h2d_per_frame = len(sc["points"]) * 12 + len(sc["polygons"]) * 144 + C.sizeof(abi.Camera) + C.sizeof(abi.Transform3D)
+    e2e = {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d_per_frame * e2e_views, "d2h_bytes_per_step": WIDTH * HEIGHT * 4 * e2e_views,
+           "views_per_step": e2e_views, "note": "per frame: geometry upload from pinned host memory, fused clear+render, colour image download to pinned host memory, stream sync"}
+
+    extras = None
+    if rank == 0 and not args.no_extras:
+        try:
+            import bench_extras
+            extras = bench_extras.run(cuda, lib)
+        except Exception as exc:  # secondary numbers must never break the headline line
+            extras = {"error": repr(exc)}
+
+    baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        baseline = cpu_baseline(views)
+
+    if distributed:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps({
+            "metric": "frames/s at 1920x1080, terrain view batch", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "terrain_1080p_views", "views_per_step_per_gpu": views, "width": WIDTH, "height": HEIGHT, "triangles": int(2 * len(sc["polygons"])),
+                       "texture": "1024x1024 RGBA8, 5 mip levels", "l2": "each step writes views x 16.6 MB of colour+depth (4.25 GB at 256 views) — far larger than the 126 MB L2, no flush needed"},
+            "mpix_per_s": fps * WIDTH * HEIGHT / 1e6,
+            "roofline": roofline, "cpu_baseline": baseline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "extras": extras,
+        }))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,95 @@
+"""Secondary measurements printed under "extras" in bench.py's JSON line: the other BASELINE.json configs on one GPU
+(inputs resident in HBM, CUDA events, after warm-up). Each entry carries its own algorithmic-byte roofline figure
+(SURVEY.md §8d). These are informational; the headline metric is bench.py's terrain view batch."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+
+
+def _time(torch, fn, warmup=3, iters=10):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for _ in range(iters):
+        fn()
+    stop.record()
+    torch.cuda.synchronize()
+    return start.elapsed_time(stop) / iters
+
+
+def run(cuda, lib):
+    import torch
+    import sandbox_scene
+    from dfpsr_b200 import abi, scenes
+    peaks = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak = float(json.load(open(peaks))["hbm_gbs"]) if os.path.exists(peaks) else 6650.0
+    out = {}
+    IM = lib.image
+    s = lib.stream_ptr()
+    ident = abi.Transform3D.identity()
+
+    # ---- config 1: one 1080p terrain frame (latency of a single frame, clear fused)
+    sc = scenes.terrain_scene()
+    tex = lib.DeviceTexture(sc["texture"], 5)
+    model = lib.DeviceModel(sc["points"], sc["polygons"], abi.FILTER_SOLID, tex)
+    color = torch.empty((1080, 1920), dtype=torch.int32, device="cuda")
+    depth = torch.empty((1080, 1920), dtype=torch.float32, device="cuda")
+    cams = (abi.Camera * 1)(lib.camera(scenes.orbit_camera(7, 1920, 1080)))
+    ci, di = (abi.Image * 1)(IM(color)), (abi.Image * 1)(IM(depth))
+    ms = _time(torch, lambda: lib.check(cuda.dfpsr_model_render_views(C.byref(model.desc), C.byref(ident), ci, di, cams, 1, 1, s)), iters=50)
+    out["terrain_1080p_single_frame"] = {"ms": ms, "fps": 1000.0 / ms, "mpix_per_s": 1920 * 1080 / ms / 1e3}
+
+    # ---- config 3: 2 M tiny vertex-coloured triangles at 3840x2160
+    nx, nz = 1000, 999
+    tiny = scenes.tiny_triangle_scene(nx, nz)
+    tmodel = lib.DeviceModel(tiny["points"], tiny["polygons"])
+    color4k = torch.empty((2160, 3840), dtype=torch.int32, device="cuda")
+    depth4k = torch.empty((2160, 3840), dtype=torch.float32, device="cuda")
+    cams4k = (abi.Camera * 1)(lib.camera(scenes.top_down_camera(nx, nz, 3840, 2160)))
+    c4, d4 = (abi.Image * 1)(IM(color4k)), (abi.Image * 1)(IM(depth4k))
+    ms = _time(torch, lambda: lib.check(cuda.dfpsr_model_render_views(C.byref(tmodel.desc), C.byref(ident), c4, d4, cams4k, 1, 1, s)), iters=10)
+    submitted = 2 * nx * nz
+    algorithmic = 12 * len(tiny["points"]) + 24 * submitted + 16 * submitted + 8 * 3840 * 2160  # SURVEY §8d config 3 ≈ 158 MB
+    out["tiny_triangles_4k"] = {"ms": ms, "fps": 1000.0 / ms, "mtri_per_s": submitted / ms / 1e3, "submitted_triangles": submitted,
+                                "algorithmic_gb_s": algorithmic / ms / 1e6, "frac_of_hbm_peak": algorithmic / ms / 1e6 / peak}
+
+    # ---- config 2: Sandbox 800x600, 1 directed + 16 shadow-casting point lights
+    sb = sandbox_scene.build(800, 600, lights=16, seed=5)
+    gpu = sandbox_scene.CudaSandbox(cuda, sb)
+    gpu.composite()
+    ms_light = _time(torch, lambda: gpu.light(), iters=5)
+    ms_comp = _time(torch, lambda: gpu.composite(), iters=5)
+    px = 800 * 600
+    algorithmic = 20 * px + 16 * 2 * 256 * 1536 * 4  # SURVEY §8d config 2 ≈ 60 MB
+    out["sandbox_800x600_16_lights"] = {"ms_light_passes": ms_light, "ms_compositing_40_sprites": ms_comp, "fps_light_passes": 1000.0 / ms_light,
+                                        "algorithmic_gb_s": algorithmic / ms_light / 1e6, "frac_of_hbm_peak": algorithmic / ms_light / 1e6 / peak}
+    blend_ms = _time(torch, lambda: lib.check(cuda.dfpsr_light_blend(C.byref(IM(gpu.C)), C.byref(IM(gpu.D)), C.byref(IM(gpu.L)), s)), iters=50)
+    out["sandbox_800x600_16_lights"]["blend_us"] = 1000.0 * blend_ms
+
+    # ---- config 5: 8192x8192 filter chain (map + bilinear resize), pure streaming
+    size = 8192
+    src = torch.empty((size, size), dtype=torch.int32, device="cuda")
+    mapped = torch.empty_like(src)
+    half = torch.empty((size // 2, size // 2), dtype=torch.int32, device="cuda")
+    up = torch.empty((size, size), dtype=torch.int32, device="cuda")
+    scratch = torch.empty(size * (size // 2), dtype=torch.int32, device="cuda")
+    lib.check(cuda.dfpsr_filter_map(C.byref(IM(src)), abi.MAP_XOR_PATTERN, None, 0, None, 0, 0, s))
+    prm = np.array(sandbox_scene.CHAIN_AFFINE, np.int32)
+    ms_map = _time(torch, lambda: lib.check(cuda.dfpsr_filter_map(C.byref(IM(mapped)), abi.MAP_AFFINE, prm.ctypes.data, 8, C.byref(IM(src)), 0, 0, s)))
+    ms_down = _time(torch, lambda: lib.check(cuda.dfpsr_filter_resize(C.byref(IM(half)), C.byref(IM(mapped)), abi.SAMPLER_LINEAR, 0, None, s)))
+    ms_up = _time(torch, lambda: lib.check(cuda.dfpsr_filter_resize(C.byref(IM(up)), C.byref(IM(half)), abi.SAMPLER_LINEAR, 0, scratch.data_ptr(), s)))
+    map_bytes, down_bytes = 8 * size * size, 4 * (size * size + (size // 2) ** 2)
+    out["filter_chain_8192"] = {
+        "map_ms": ms_map, "map_gb_s": map_bytes / ms_map / 1e6, "map_frac_of_hbm_peak": map_bytes / ms_map / 1e6 / peak,
+        "resize_down_ms": ms_down, "resize_down_gb_s": down_bytes / ms_down / 1e6, "resize_down_frac_of_hbm_peak": down_bytes / ms_down / 1e6 / peak,
+        "resize_up_ms": ms_up, "resize_up_gb_s": down_bytes / ms_up / 1e6,
+        "chain_ms": ms_map + ms_down, "chain_gb_s": (map_bytes + down_bytes) / (ms_map + ms_down) / 1e6,
+        "chain_frac_of_hbm_peak": (map_bytes + down_bytes) / (ms_map + ms_down) / 1e6 / peak,
+    }
+    return out

@@ -37,9 +37,16 @@ extern thread_local char g_error[512];
 extern unsigned long long g_launches;
 int check_launch(const char *name);
 
+// Optional per-kernel device timing (dfpsr_profile_enable): CUDA events on the launching stream around each launch.
+extern bool g_profile;
+void profile_begin(const char *name, cudaStream_t stream);
+void profile_end(cudaStream_t stream);
+
 #define DFPSR_LAUNCH(kernel, grid, block, smem, stream, ...)                      \
 	do {                                                                          \
+		if (dfpsr::g_profile) { dfpsr::profile_begin(#kernel, (stream)); }        \
 		kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);               \
+		if (dfpsr::g_profile) { dfpsr::profile_end((stream)); }                   \
 		dfpsr::g_launches++;                                                      \
 		if (dfpsr::check_launch(#kernel)) { return 1; }                           \
 	} while (0)

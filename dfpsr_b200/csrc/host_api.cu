@@ -5,6 +5,8 @@
 #include <math.h>
 #include <float.h>
 #include <stdarg.h>
+#include <vector>
+#include <utility>
 
 namespace dfpsr {
 
@@ -25,6 +27,41 @@ int check_launch(const char *name) {
 		return 1;
 	}
 	return 0;
+}
+
+// ---- per-kernel profiling
+bool g_profile = false;
+namespace {
+struct ProfileEntry { const char *name; std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events; double ms = 0.0; long long launches = 0; };
+std::vector<ProfileEntry> g_profileEntries;
+ProfileEntry *g_profileCurrent = nullptr;
+cudaEvent_t g_profileStart;
+void profile_collect() {
+	for (ProfileEntry &e : g_profileEntries) {
+		for (auto &pair : e.events) {
+			cudaEventSynchronize(pair.second);
+			float ms = 0.0f;
+			if (cudaEventElapsedTime(&ms, pair.first, pair.second) == cudaSuccess) { e.ms += ms; e.launches++; }
+			cudaEventDestroy(pair.first); cudaEventDestroy(pair.second);
+		}
+		e.events.clear();
+	}
+}
+}
+void profile_begin(const char *name, cudaStream_t stream) {
+	g_profileCurrent = nullptr;
+	for (ProfileEntry &e : g_profileEntries) { if (strcmp(e.name, name) == 0) { g_profileCurrent = &e; break; } }
+	if (!g_profileCurrent) { g_profileEntries.push_back(ProfileEntry{name, {}, 0.0, 0}); g_profileCurrent = &g_profileEntries.back(); }
+	cudaEventCreate(&g_profileStart);
+	cudaEventRecord(g_profileStart, stream);
+}
+void profile_end(cudaStream_t stream) {
+	if (!g_profileCurrent) { return; }
+	cudaEvent_t stop;
+	cudaEventCreate(&stop);
+	cudaEventRecord(stop, stream);
+	g_profileCurrent->events.push_back({g_profileStart, stop});
+	if (g_profileCurrent->events.size() >= 4096) { profile_collect(); }
 }
 
 int sm_count() {
@@ -120,6 +157,26 @@ int dfpsr_init(int device) {
 	DFPSR_REQUIRE(device >= 0 && device < n, "device %d out of range (found %d)", device, n);
 	DFPSR_CHECK_CUDA(cudaSetDevice(device));
 	DFPSR_CHECK_CUDA(cudaFree(0));
+	return 0;
+}
+
+int dfpsr_profile_enable(int enabled) {
+	if (!enabled) { profile_collect(); }
+	g_profile = enabled != 0;
+	return 0;
+}
+int dfpsr_profile_reset(void) {
+	profile_collect();
+	g_profileEntries.clear();
+	return 0;
+}
+int dfpsr_profile_count(void) { profile_collect(); return (int)g_profileEntries.size(); }
+int dfpsr_profile_read(int index, const char **name, double *milliseconds, int64_t *launches) {
+	profile_collect();
+	DFPSR_REQUIRE(index >= 0 && index < (int)g_profileEntries.size(), "profile_read: index out of range");
+	*name = g_profileEntries[index].name;
+	*milliseconds = g_profileEntries[index].ms;
+	*launches = g_profileEntries[index].launches;
 	return 0;
 }
 

@@ -22,6 +22,10 @@ SIGNATURES = {
     "dfpsr_device_count": (i32, []),
     "dfpsr_launch_count": (u64, []),
     "dfpsr_reset_launch_count": (None, []),
+    "dfpsr_profile_enable": (i32, [i32]),
+    "dfpsr_profile_reset": (i32, []),
+    "dfpsr_profile_count": (i32, []),
+    "dfpsr_profile_read": (i32, [i32, P(C.c_char_p), P(C.c_double), P(i64)]),
     "dfpsr_malloc": (i32, [P(vp), sz]),
     "dfpsr_free": (i32, [vp]),
     "dfpsr_malloc_host": (i32, [P(vp), sz]),
@@ -91,6 +95,17 @@ def load():
 def check(status):
     if status != 0:
         raise DfpsrError(load().dfpsr_last_error().decode("utf-8", "replace"))
+
+
+def profile_snapshot():
+    """{kernel name: (milliseconds, launches)} accumulated since dfpsr_profile_reset."""
+    handle = load()
+    out = {}
+    for i in range(handle.dfpsr_profile_count()):
+        name, ms, n = C.c_char_p(), C.c_double(), C.c_int64()
+        check(handle.dfpsr_profile_read(i, C.byref(name), C.byref(ms), C.byref(n)))
+        out[name.value.decode()] = (ms.value, n.value)
+    return out
 
 
 def stream_ptr(stream=None):

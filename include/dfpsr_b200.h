@@ -143,6 +143,13 @@ int dfpsr_device_count(void);
 uint64_t dfpsr_launch_count(void);
 void dfpsr_reset_launch_count(void);
 
+/* Per-kernel device timing for bench.py's roofline: while enabled, every launch is bracketed by CUDA events on its
+ * stream; dfpsr_profile_read returns the accumulated time and launch count per kernel name. */
+int dfpsr_profile_enable(int enabled);
+int dfpsr_profile_reset(void);
+int dfpsr_profile_count(void);
+int dfpsr_profile_read(int index, const char **name, double *milliseconds, int64_t *launches);
+
 /* Device memory helpers for hosts that do not bring their own allocator. */
 int dfpsr_malloc(void **devicePtr, size_t bytes);
 int dfpsr_free(void *devicePtr);

@@ -261,6 +261,18 @@ static uint32_t tex_sample_bilinear(const dfpsr_texture *t, float u, float v, ui
 	return weight_colors(upper, 256u - wy, lower, wy);
 }
 
+/* ---- test hooks (known-answer tests of the reference: test/tests/TextureTest.cpp:13-19, :22-372) */
+uint32_t orc_texture_layer_offset(const dfpsr_texture *t, uint32_t mip) { return tex_layer_offset(t, mip); }
+/* api/textureAPI.h:111-177 texture_getPixelOffset with tiling: coordinates wrap inside the level */
+uint32_t orc_texture_pixel_offset(const dfpsr_texture *t, uint32_t x, uint32_t y, uint32_t mip) {
+	if (mip > t->maxMipLevel) { mip = t->maxMipLevel; }
+	uint32_t maskX = ((1u << t->log2width) - 1u) >> mip, maskY = ((1u << t->log2height) - 1u) >> mip;
+	return tex_layer_offset(t, mip) + (((y & maskY) << (t->log2width - mip)) | (x & maskX));
+}
+/* api/textureAPI.h:265-275 texture_interpolate_color_linear: weight 0..256 of colorB */
+uint32_t orc_interpolate_color_linear(uint32_t colorA, uint32_t colorB, uint32_t weight) { return weight_colors(colorA, 256u - weight, colorB, weight); }
+uint32_t orc_texture_sample_bilinear(const dfpsr_texture *t, float u, float v, uint32_t mip) { return tex_sample_bilinear(t, u, v, mip); }
+
 /* api/textureAPI.h:472-495: one level per quad from lanes 0, 1, 2 */
 static uint32_t tex_mip_level(const dfpsr_texture *t, const float *u, const float *v) {
 	float offsetUX = fabsf(u[0] - u[1]), offsetUY = fabsf(u[0] - u[2]);
@@ -357,6 +369,20 @@ static void rasterize_triangle(const ppoint *p, row_interval *rows, irect bound)
 			cut_convex_edge(p[i].fx, p[i].fy, p[j].fx, p[j].fy, rows, bound);
 		}
 	}
+}
+
+/* test hook: row intervals [left, right) of one triangle given by its 1/256-pixel corners, inside bound (l, t, w, h) */
+void orc_rasterize_rows(const int64_t *fx, const int64_t *fy, int32_t l, int32_t t, int32_t w, int32_t h, int32_t *rowsOut) {
+	ppoint p[3];
+	memset(p, 0, sizeof(p));
+	for (int i = 0; i < 3; i++) { p[i].fx = fx[i]; p[i].fy = fy[i]; }
+	rasterize_triangle(p, (row_interval*)rowsOut, irect_make(l, t, w, h));
+}
+int orc_is_frontfacing(const int64_t *fx, const int64_t *fy) {
+	ppoint p[3];
+	memset(p, 0, sizeof(p));
+	for (int i = 0; i < 3; i++) { p[i].fx = fx[i]; p[i].fy = fy[i]; }
+	return is_frontfacing(p);
 }
 
 typedef struct { int affine; float start[3], dx[3], dy[3]; } projection;

@@ -27,6 +27,13 @@ void orc_project_points(const float *points, int32_t count, const dfpsr_transfor
 
 void orc_texture_layout(dfpsr_texture *out, int32_t width, int32_t height, int32_t resolutions);
 void orc_texture_generate_pyramid(uint32_t *pixels, const dfpsr_texture *layout);
+/* test hooks for the reference's own known-answer tests (test/tests/TextureTest.cpp) and for the coverage property test */
+uint32_t orc_texture_layer_offset(const dfpsr_texture *t, uint32_t mip);
+uint32_t orc_texture_pixel_offset(const dfpsr_texture *t, uint32_t x, uint32_t y, uint32_t mip);
+uint32_t orc_interpolate_color_linear(uint32_t colorA, uint32_t colorB, uint32_t weight);
+uint32_t orc_texture_sample_bilinear(const dfpsr_texture *t, float u, float v, uint32_t mip);
+void orc_rasterize_rows(const int64_t *fx, const int64_t *fy, int32_t l, int32_t t, int32_t w, int32_t h, int32_t *rowsOut);
+int orc_is_frontfacing(const int64_t *fx, const int64_t *fy);
 
 /* model_render / renderer_begin+giveTask+end (identical pixels). color and/or depth may have data == NULL.
  * Returns the number of draw commands (triangles after culling/clipping/back-face removal). */

@@ -63,11 +63,12 @@ def run(cuda, lib):
     sb = sandbox_scene.build(800, 600, lights=16, seed=5)
     gpu = sandbox_scene.CudaSandbox(cuda, sb)
     gpu.composite()
-    ms_light = _time(torch, lambda: gpu.light(), iters=5)
+    ms_light_unbatched = _time(torch, lambda: gpu.light(), iters=3)
+    ms_light = _time(torch, lambda: gpu.light_batched(), iters=10)
     ms_comp = _time(torch, lambda: gpu.composite(), iters=5)
     px = 800 * 600
     algorithmic = 20 * px + 16 * 2 * 256 * 1536 * 4  # SURVEY §8d config 2 ≈ 60 MB
-    out["sandbox_800x600_16_lights"] = {"ms_light_passes": ms_light, "ms_compositing_40_sprites": ms_comp, "fps_light_passes": 1000.0 / ms_light,
+    out["sandbox_800x600_16_lights"] = {"ms_light_passes": ms_light, "ms_light_passes_one_cube_map_per_light_call": ms_light_unbatched, "ms_compositing_40_sprites": ms_comp, "fps_light_passes": 1000.0 / ms_light,
                                         "algorithmic_gb_s": algorithmic / ms_light / 1e6, "frac_of_hbm_peak": algorithmic / ms_light / 1e6 / peak}
     blend_ms = _time(torch, lambda: lib.check(cuda.dfpsr_light_blend(C.byref(IM(gpu.C)), C.byref(IM(gpu.D)), C.byref(IM(gpu.L)), s)), iters=50)
     out["sandbox_800x600_16_lights"]["blend_us"] = 1000.0 * blend_ms

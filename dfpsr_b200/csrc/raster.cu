@@ -1,19 +1,23 @@
-// raster.cu — the triangle pipeline on sm_100a.
+// raster.cu — the triangle pipeline on sm_100a (v2: warp-owned 32x4 tiles, batched views).
 //
-//   project_kernel      ref: api/modelAPI.cpp:238-242 + implementation/render/Camera.h:157-190
-//   setup_kernel<false> ref: implementation/render/renderCore.cpp:172-341 (cull, clip, back-face) — counting pass
-//   scan_kernel         prefix sums that replace List<TriangleDrawCommand>::push (renderCore.cpp:445) and
-//                       CommandQueue::execute's 12 strips (renderCore.cpp:449-480) with per-tile lists
-//   setup_kernel<true>  emits compact draw commands in submission order + their row intervals
-//                       (implementation/render/ITriangle2D.cpp:31-176) + interpolation planes (:182-300)
-//   big_rows_kernel     row intervals of tall triangles, one warp per triangle
-//   raster_kernel       ref: shader/fillerTemplates.h:108-441 + shader/RgbaMultiply.h:37-175 + api/textureAPI.h:253-495
-//                       one CTA per 32x32 screen tile, one thread per aligned 2x2 quad, colour and depth of the
-//                       tile held in registers for the whole triangle list, triangles applied in submission order.
+//   project_kernel       ref: api/modelAPI.cpp:238-242 + implementation/render/Camera.h:157-190 — all tasks of a batch in one launch
+//   setup_kernel<false>  ref: implementation/render/renderCore.cpp:172-341 (cull, clip, back-face) — counting pass: commands and rows per
+//                        slot, an upper bound of the entries of every screen tile (bounding box)
+//   scan_blocks_kernel   ordered prefix sums that replace List<TriangleDrawCommand>::push (renderCore.cpp:445): commands keep submission order
+//   tile_alloc_kernel    hands every tile a segment of the entry pool (warp-aggregated atomics; replaces CommandQueue::execute's 12 strips,
+//                        renderCore.cpp:449-480, with per-tile lists)
+//   setup_kernel<true>   emits compact draw commands + their row intervals (implementation/render/ITriangle2D.cpp:31-176) + interpolation
+//                        planes (:182-300) and bins each command to exactly the tiles its row intervals touch. Tall or wide triangles are
+//                        handed to whole warps through a shared-memory queue (one lane per tile row).
+//   sort_lists_kernel    only when a tile holds more than 32 entries: restores submission order inside long tile lists
+//   raster_kernel        ref: shader/fillerTemplates.h:108-441 + shader/RgbaMultiply.h:37-175 + api/textureAPI.h:253-495
+//                        one WARP per 32x4 pixel tile, one lane per aligned 2x2 quad, colour and depth of the tile in registers for the whole
+//                        list, commands applied in submission order, no block-wide barrier anywhere. Commands are taken 16 at a time: lane
+//                        (command, row pair) replays the reference's running float sums from the triangle's left edge up to the tile ONCE
+//                        and leaves a checkpoint in shared memory; the quad lanes continue from it with at most 15 additions.
 //
-// Exactness: coverage is the reference's int64 row-interval arithmetic; interpolated (1/W, U/W, V/W) replay the
-// reference's chain of float additions from each row pair's outer block start, so colour and depth are
-// bit-identical to the reference's scalar build (exact 1/x) — not merely within tolerance.
+// Exactness: coverage is the reference's int64 row-interval arithmetic; interpolated (1/W, U/W, V/W) replay the reference's chain of float
+// additions from each row pair's outer block start, so colour and depth are bit-identical to the reference's scalar build (exact 1/x).
 #include "common.cuh"
 
 #include <vector>
@@ -21,10 +25,15 @@
 
 namespace dfpsr {
 
-static const int TILE = 32;              // screen tile edge in pixels
-static const int CHUNK = 16;             // commands staged in shared memory per round
-static const int SMALL_ROWS = 16;        // triangles up to this many rows are scan-converted by their set-up thread
+static const int TILE_W = 32, TILE_H = 4;  // one warp: 16 x 2 quads
+static const int BATCH = 16;               // commands whose checkpoints are prepared together (BATCH x 2 row pairs = 32 lanes)
+static const int SMALL_ROWS = 16;          // triangles up to this many rows and SMALL_WIDTH columns are scan-converted by their set-up thread
+static const int SMALL_WIDTH = 128;
+static const int SMALL_TILES = 8;          // counting pass: bounding boxes up to this many tiles are counted by the set-up thread
 static const int SETUP_THREADS = 256;
+static const int RASTER_WARPS = 4;
+static const int SORT_THREADS = 256;
+static const int SORT_SMEM = 4096;         // entries of one tile list sorted in shared memory; longer lists use the rank sort
 
 struct PPoint { // == dfpsr_projected_point
 	float csx, csy, csz, isx, isy;
@@ -36,14 +45,14 @@ static_assert(sizeof(dfpsr_projected_point) == 40, "dfpsr_projected_point layout
 
 // One draw command = one front-facing triangle after culling and clipping (ref: renderCore.h:52-70 carries 456 bytes).
 struct Cmd {
-	float start[3], dx[3], dy[3]; // Projection (ref: ITriangle2D.h:63-76)
-	int32_t bx0, bx1;             // clipped pixel bound, columns
-	int32_t rowStart, rowCount;   // even-aligned rows (ref: ITriangle2D.cpp:70-75)
-	uint32_t rowOffset;           // first entry in the row-interval table
-	uint32_t flags;               // CMD_* | diffuse index << 8 | light index << 20
-	float red[3], green[3], blue[3], alpha[3]; // scaled vertex colours (ref: RgbaMultiply.h:45-60)
-	float u1[3], v1[3], u2[3], v2[3];
+	float start[3], dx[3], dy[3]; // Projection (ref: ITriangle2D.h:63-76)                        bytes   0..35
+	uint32_t flags;               // CMD_* | diffuse index << 8 | light index << 20                     36..39
+	int32_t bx0, bx1;             // clipped pixel bound, columns                                        40..47
+	int32_t rowStart, rowCount;   // even-aligned rows (ref: ITriangle2D.cpp:70-75)                      48..55
+	uint32_t rowOffset;           // first entry in the row-interval table (always even)                 56..59
 	uint32_t pad_;
+	float red[3], green[3], blue[3], alpha[3]; // scaled vertex colours (ref: RgbaMultiply.h:45-60)      64..111
+	float u1[3], v1[3], u2[3], v2[3];          //                                                       112..159
 };
 static_assert(sizeof(Cmd) == 160, "Cmd layout");
 
@@ -51,34 +60,47 @@ enum : uint32_t {
 	CMD_AFFINE = 1u, CMD_ALPHA = 2u, CMD_HAS_DIFFUSE = 4u, CMD_HAS_LIGHT = 8u, CMD_HAS_FADE = 16u, CMD_COLORLESS = 32u
 };
 
-struct BigCmd {
-	uint32_t cmdIndex, pad_;
-	long long fx[3], fy[3];
-};
-
+// One submission (model or triangle batch) for one view. Lives in device memory; every set-up block copies its task to shared memory.
 struct TaskParams {
 	const float *points;
 	const dfpsr_polygon *polygons;
 	const dfpsr_triangle *triangles; // alternative source: pre-projected triangles
 	PPoint *projected;
-	int32_t pointCount, polygonCount, triangleCount;
-	int32_t slotBase, slotCount, blockBase;
+	int32_t pointCount, slotCount;
+	int32_t slotBase, blockBase, blockCount;
+	int32_t view;
+	int32_t filter, diffuseIndex, lightIndex; // texture table indices or -1
+	int32_t depthOnly;
 	dfpsr_transform3d modelToWorld;
 	dfpsr_camera camera;
-	int32_t filter, diffuseIndex, lightIndex; // texture table indices or -1
-	int32_t width, height, depthOnly;
+};
+
+// One render target pair of the batch.
+struct ViewDev {
+	dfpsr_image color, depth; // data == nullptr when absent
+	int32_t width, height;
+	int32_t clipTop, clipBottom; // rows this process draws (strip mode; multiples of TILE_H or the image height)
+	int32_t clear;               // targets are defined to be (clearColor, clearDepth) before this frame: no loads, every pixel stored
+	uint32_t clearColor;
+	float clearDepth;
+	uint32_t tileBase;           // index of this view's first tile in the batch
+	int32_t tilesX, tilesY;
 };
 
 struct FrameDev {
-	uint32_t *slotCounts;  // per slot: command count | rows << 3
-	uint32_t *blockCmds, *blockRows; // per set-up block: totals, then exclusive offsets after scan_kernel
+	const TaskParams *tasks;
+	const ViewDev *views;
+	int32_t taskCount, viewCount, blockCount;
+	uint32_t tileTotal;
+	uint32_t *slotCounts;            // per slot: command count | rows << 3
+	uint32_t *blockCmds, *blockRows; // per set-up block: totals, then exclusive offsets after scan_blocks_kernel
 	uint32_t *tileCount, *tileOffset, *tileCursor;
-	uint32_t *totals;      // [0] commands, [1] rows, [2] tile entries, [3] max entries in one tile, [4] big commands
+	uint32_t *totals;                // [0] commands, [1] rows, [2] tile entries (upper bound), [3] max entries in one tile (upper bound)
 	Cmd *cmds;
 	int2 *rows;
 	uint32_t *tileList;
-	BigCmd *big;
-	int32_t tilesX, tilesY, blockCount;
+	uint32_t *sortTmp;               // rank-sort scratch: gridDim.x * sortTmpStride entries
+	uint32_t sortTmpStride;
 };
 
 // ------------------------------------------------------------------------------------------------ projection
@@ -122,7 +144,19 @@ __device__ __forceinline__ PPoint world_to_screen(const dfpsr_camera &c, const d
 	return camera_to_screen(c, cx, cy, cz);
 }
 
-__global__ void __launch_bounds__(256) project_kernel(const float *__restrict__ points, int32_t count, dfpsr_transform3d m2w, dfpsr_camera camera, PPoint *__restrict__ out) {
+// One launch for every task of the batch: blockIdx.y = task.
+__global__ void __launch_bounds__(256) project_kernel(const TaskParams *__restrict__ tasks) {
+	__shared__ TaskParams task;
+	for (uint32_t w = threadIdx.x; w < sizeof(TaskParams) / 4; w += blockDim.x) { ((uint32_t *)&task)[w] = ((const uint32_t *)&tasks[blockIdx.y])[w]; }
+	__syncthreads();
+	if (task.triangles != nullptr) { return; }
+	for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < task.pointCount; i += gridDim.x * blockDim.x) {
+		task.projected[i] = world_to_screen(task.camera, task.modelToWorld, task.points[3 * i], task.points[3 * i + 1], task.points[3 * i + 2]);
+	}
+}
+
+// dfpsr_project_points: the projection loop alone.
+__global__ void __launch_bounds__(256) project_points_kernel(const float *__restrict__ points, int32_t count, dfpsr_transform3d m2w, dfpsr_camera camera, PPoint *__restrict__ out) {
 	for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
 		out[i] = world_to_screen(camera, m2w, points[3 * i], points[3 * i + 1], points[3 * i + 2]);
 	}
@@ -155,18 +189,19 @@ __device__ __forceinline__ bool is_frontfacing(const PPoint *p) {
 
 struct Bound { int32_t l, t, r, b; bool any; };
 
-// ref: implementation/render/ITriangle2D.cpp:31-43, :62-75 — pixel bound, cut to the target, rows aligned to 2.
-__device__ Bound raster_bound(const PPoint *p, int32_t width, int32_t height) {
+// ref: implementation/render/ITriangle2D.cpp:31-43, :62-75 — pixel bound, cut to the clip rectangle (0, clipTop, width, clipBottom - clipTop)
+// exactly like executeTriangleDrawing's clipBound (renderCore.cpp:203-217), rows aligned to 2.
+__device__ Bound raster_bound(const PPoint *p, int32_t width, int32_t clipTop, int32_t clipBottom) {
 	int32_t rx0 = (int32_t)((p[0].fx + 128) / 256), ry0 = (int32_t)((p[0].fy + 128) / 256);
 	int32_t rx1 = (int32_t)((p[1].fx + 128) / 256), ry1 = (int32_t)((p[1].fy + 128) / 256);
 	int32_t rx2 = (int32_t)((p[2].fx + 128) / 256), ry2 = (int32_t)((p[2].fy + 128) / 256);
 	int32_t l = min(rx0, min(rx1, rx2)) - 1, t = min(ry0, min(ry1, ry2)) - 1;
 	int32_t r = max(rx0, max(rx1, rx2)) + 1, b = max(ry0, max(ry1, ry2)) + 1;
 	Bound out;
-	out.any = l < width && r > 0 && t < height && b > 0; // IRect::overlaps (math/IRect.h:77)
+	out.any = l < width && r > 0 && t < clipBottom && b > clipTop; // IRect::overlaps (math/IRect.h:77)
 	if (!out.any) { out.l = out.t = out.r = out.b = 0; return out; }
 	out.l = max(l, 0); out.r = min(r, width);
-	int32_t top = max(t, 0), bottom = min(b, height);
+	int32_t top = max(t, clipTop), bottom = min(b, clipBottom);
 	out.t = (top / 2) * 2;
 	out.b = ((bottom + 1) / 2) * 2;
 	return out;
@@ -408,20 +443,63 @@ __device__ bool load_triangle(const TaskParams &task, int32_t local, PPoint *p, 
 	return true;
 }
 
+
 // ------------------------------------------------------------------------------------------------ set-up kernel
 
+// A command whose tile counting (counting pass) or rows + tile entries (emit pass) are produced cooperatively by one warp.
+struct BigItem {
+	uint32_t cmdIndex, rowOffset, tileBase;
+	int32_t tilesX, l, t, r, rowCount;
+	int32_t tx0, tx1, ty0, ty1;
+	long long fx[3], fy[3];
+};
+
+// Finds the task a set-up block belongs to (tasks own contiguous block ranges).
+__device__ __forceinline__ int32_t task_of_block(const TaskParams *tasks, int32_t taskCount, int32_t block) {
+	int32_t lo = 0, hi = taskCount - 1;
+	while (lo < hi) {
+		int32_t mid = (lo + hi + 1) >> 1;
+		if (tasks[mid].blockBase <= block) { lo = mid; } else { hi = mid - 1; }
+	}
+	return lo;
+}
+
+// Appends `index` to the lists of the tiles of one tile row that pixels [minL, maxR) touch.
+__device__ __forceinline__ void emit_tile_row(const FrameDev &frame, uint32_t tileBase, int32_t tilesX, int32_t ty, int32_t minL, int32_t maxR, uint32_t index) {
+	if (maxR <= minL) { return; }
+	for (int32_t tx = minL / TILE_W; tx <= (maxR - 1) / TILE_W; tx++) {
+		uint32_t tile = tileBase + (uint32_t)(ty * tilesX + tx);
+		uint32_t pos = atomicAdd(&frame.tileCursor[tile], 1u);
+		frame.tileList[frame.tileOffset[tile] + pos] = index;
+	}
+}
+
 template <bool EMIT>
-__global__ void __launch_bounds__(SETUP_THREADS) setup_kernel(TaskParams task, FrameDev frame) {
+__global__ void __launch_bounds__(SETUP_THREADS) setup_kernel(FrameDev frame) {
+	__shared__ TaskParams task;
 	__shared__ uint32_t warpCmds[SETUP_THREADS / 32], warpRows[SETUP_THREADS / 32];
-	int32_t local = blockIdx.x * SETUP_THREADS + threadIdx.x;
-	bool active = local < task.slotCount;
-	int32_t slot = task.slotBase + local;
-	int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	__shared__ BigItem sBig[SETUP_THREADS];
+	__shared__ uint32_t sBigCount;
+	{
+		int32_t t = task_of_block(frame.tasks, frame.taskCount, (int32_t)blockIdx.x);
+		for (uint32_t w = threadIdx.x; w < sizeof(TaskParams) / 4; w += blockDim.x) { ((uint32_t *)&task)[w] = ((const uint32_t *)&frame.tasks[t])[w]; }
+		if (threadIdx.x == 0) { sBigCount = 0; }
+	}
+	__syncthreads();
+	const ViewDev &view = frame.views[task.view];
+	const int32_t width = view.width, height = view.height, clipTop = view.clipTop, clipBottom = view.clipBottom;
+	const int32_t tilesX = view.tilesX;
+	const uint32_t tileBase = view.tileBase;
+
+	const int32_t localBlock = (int32_t)blockIdx.x - task.blockBase;
+	const int32_t local = localBlock * SETUP_THREADS + threadIdx.x;
+	const bool active = local < task.slotCount;
+	const int32_t slot = task.slotBase + local;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
 	PPoint p[3];
 	float colors[3][4], tex[3][4];
-	bool loaded = active && load_triangle(task, local, p, colors, tex);
-	const int32_t tilesX = frame.tilesX;
+	const bool loaded = active && load_triangle(task, local, p, colors, tex);
 
 	uint32_t cmdBase = 0, rowBase = 0;
 	if (EMIT) {
@@ -438,27 +516,39 @@ __global__ void __launch_bounds__(SETUP_THREADS) setup_kernel(TaskParams task, F
 		__syncthreads();
 		uint32_t preCmd = 0, preRows = 0;
 		for (int w = 0; w < warp; w++) { preCmd += warpCmds[w]; preRows += warpRows[w]; }
-		cmdBase = frame.blockCmds[task.blockBase + blockIdx.x] + preCmd + incCmd - nCmd;
-		rowBase = frame.blockRows[task.blockBase + blockIdx.x] + preRows + incRows - nRows;
+		cmdBase = frame.blockCmds[blockIdx.x] + preCmd + incCmd - nCmd;
+		rowBase = frame.blockRows[blockIdx.x] + preRows + incRows - nRows;
 	}
 
 	uint32_t countCmd = 0, countRows = 0;
 	if (loaded) {
 		float alpha[3] = {colors[0][3], colors[1][3], colors[2][3]};
 		for_each_command(task, p, alpha, [&](const PPoint *q, const float *subB, const float *subC) {
-			Bound bound = raster_bound(q, task.width, task.height);
-			int32_t rowCount = bound.any ? bound.b - bound.t : 0;
-			int32_t tx0 = bound.l / TILE, tx1 = (bound.r - 1) / TILE, ty0 = bound.t / TILE, ty1 = (min(bound.b, task.height) - 1) / TILE;
+			Bound bound = raster_bound(q, width, clipTop, clipBottom);
+			const int32_t rowCount = bound.any ? bound.b - bound.t : 0;
+			const int32_t tx0 = bound.l / TILE_W, tx1 = (bound.r - 1) / TILE_W, ty0 = bound.t / TILE_H, ty1 = (min(bound.b, height) - 1) / TILE_H;
+			const bool small = rowCount <= SMALL_ROWS && (bound.r - bound.l) <= SMALL_WIDTH;
 			if (!EMIT) {
 				if (rowCount > 0) {
-					for (int32_t ty = ty0; ty <= ty1; ty++) {
-						for (int32_t tx = tx0; tx <= tx1; tx++) { atomicAdd(&frame.tileCount[ty * tilesX + tx], 1u); }
+					int32_t tiles = (tx1 - tx0 + 1) * (ty1 - ty0 + 1);
+					uint32_t queued = 0xFFFFFFFFu;
+					if (tiles > SMALL_TILES) {
+						queued = atomicAdd(&sBigCount, 1u);
+						if (queued < (uint32_t)SETUP_THREADS) {
+							BigItem &it = sBig[queued];
+							it.tileBase = tileBase; it.tilesX = tilesX; it.tx0 = tx0; it.tx1 = tx1; it.ty0 = ty0; it.ty1 = ty1;
+						}
+					}
+					if (queued >= (uint32_t)SETUP_THREADS) {
+						for (int32_t ty = ty0; ty <= ty1; ty++) {
+							for (int32_t tx = tx0; tx <= tx1; tx++) { atomicAdd(&frame.tileCount[tileBase + (uint32_t)(ty * tilesX + tx)], 1u); }
+						}
 					}
 				}
 			} else {
-				uint32_t index = cmdBase + countCmd;
+				const uint32_t index = cmdBase + countCmd;
 				Cmd cmd;
-				bool perspective = task.camera.perspective != 0;
+				const bool perspective = task.camera.perspective != 0;
 				get_projection(cmd, q, subB, subC, perspective);
 				cmd.bx0 = bound.l; cmd.bx1 = bound.r;
 				cmd.rowStart = bound.t; cmd.rowCount = rowCount;
@@ -479,25 +569,38 @@ __global__ void __launch_bounds__(SETUP_THREADS) setup_kernel(TaskParams task, F
 				if (almost_one3(cmd.red) && almost_one3(cmd.green) && almost_one3(cmd.blue) && almost_one3(cmd.alpha)) { flags |= CMD_COLORLESS; }
 				cmd.flags = flags;
 				cmd.pad_ = 0;
-				frame.cmds[index] = cmd;
+				{
+					uint4 *dst = (uint4 *)&frame.cmds[index];
+					const uint4 *src = (const uint4 *)&cmd;
+#pragma unroll
+					for (int w = 0; w < (int)(sizeof(Cmd) / 16); w++) { dst[w] = src[w]; }
+				}
 				if (rowCount > 0) {
-					long long fx[3] = {q[0].fx, q[1].fx, q[2].fx}, fy[3] = {q[0].fy, q[1].fy, q[2].fy};
-					if (rowCount <= SMALL_ROWS) {
+					uint32_t queued = 0xFFFFFFFFu;
+					if (!small) {
+						queued = atomicAdd(&sBigCount, 1u);
+						if (queued < (uint32_t)SETUP_THREADS) {
+							BigItem &it = sBig[queued];
+							it.cmdIndex = index; it.rowOffset = cmd.rowOffset; it.tileBase = tileBase; it.tilesX = tilesX;
+							it.l = bound.l; it.t = bound.t; it.r = bound.r; it.rowCount = rowCount;
+							for (int k = 0; k < 3; k++) { it.fx[k] = q[k].fx; it.fy[k] = q[k].fy; }
+						}
+					}
+					if (queued >= (uint32_t)SETUP_THREADS) {
+						// scan conversion by this thread; a tile row (TILE_H rows) is binned when its last row is done
+						long long fx[3] = {q[0].fx, q[1].fx, q[2].fx}, fy[3] = {q[0].fy, q[1].fy, q[2].fy};
 						EdgeSet edges;
 						edges_setup(edges, fx, fy, bound.l, bound.t, bound.r);
-						for (int32_t r = 0; r < rowCount; r++) { frame.rows[cmd.rowOffset + r] = edges_row(edges, bound.t + r); }
-					} else {
-						uint32_t b = atomicAdd(&frame.totals[4], 1u);
-						BigCmd big;
-						big.cmdIndex = index; big.pad_ = 0;
-						for (int k = 0; k < 3; k++) { big.fx[k] = fx[k]; big.fy[k] = fy[k]; }
-						frame.big[b] = big;
-					}
-					for (int32_t ty = ty0; ty <= ty1; ty++) {
-						for (int32_t tx = tx0; tx <= tx1; tx++) {
-							int32_t tile = ty * tilesX + tx;
-							uint32_t pos = atomicAdd(&frame.tileCursor[tile], 1u);
-							frame.tileList[frame.tileOffset[tile] + pos] = index;
+						int32_t minL = 0x7FFFFFFF, maxR = -1;
+						for (int32_t r = 0; r < rowCount; r++) {
+							int32_t y = bound.t + r;
+							int2 row = edges_row(edges, y);
+							frame.rows[cmd.rowOffset + r] = row;
+							if (row.y > row.x && y < height) { minL = min(minL, row.x); maxR = max(maxR, row.y); }
+							if ((y & (TILE_H - 1)) == TILE_H - 1 || r == rowCount - 1) {
+								if (y - (y & (TILE_H - 1)) < height) { emit_tile_row(frame, tileBase, tilesX, y / TILE_H, minL, maxR, index); }
+								minL = 0x7FFFFFFF; maxR = -1;
+							}
 						}
 					}
 				}
@@ -507,9 +610,39 @@ __global__ void __launch_bounds__(SETUP_THREADS) setup_kernel(TaskParams task, F
 		});
 	}
 
+	// ---- commands handed to whole warps
+	__syncthreads();
+	{
+		const uint32_t bigCount = min(sBigCount, (uint32_t)SETUP_THREADS);
+		for (uint32_t b = warp; b < bigCount; b += SETUP_THREADS / 32) {
+			const BigItem &it = sBig[b];
+			if (!EMIT) {
+				int32_t w = it.tx1 - it.tx0 + 1, tiles = w * (it.ty1 - it.ty0 + 1);
+				for (int32_t i = lane; i < tiles; i += 32) {
+					atomicAdd(&frame.tileCount[it.tileBase + (uint32_t)((it.ty0 + i / w) * it.tilesX + it.tx0 + i % w)], 1u);
+				}
+			} else {
+				EdgeSet edges;
+				long long fx[3] = {it.fx[0], it.fx[1], it.fx[2]}, fy[3] = {it.fy[0], it.fy[1], it.fy[2]};
+				edges_setup(edges, fx, fy, it.l, it.t, it.r);
+				const int32_t tyFirst = it.t / TILE_H, tyLast = (it.t + it.rowCount - 1) / TILE_H;
+				for (int32_t ty = tyFirst + lane; ty <= tyLast; ty += 32) {
+					int32_t yBegin = max(it.t, ty * TILE_H), yEnd = min(it.t + it.rowCount, ty * TILE_H + TILE_H);
+					int32_t minL = 0x7FFFFFFF, maxR = -1;
+					for (int32_t y = yBegin; y < yEnd; y++) {
+						int2 row = edges_row(edges, y);
+						frame.rows[it.rowOffset + (uint32_t)(y - it.t)] = row;
+						if (row.y > row.x && y < height) { minL = min(minL, row.x); maxR = max(maxR, row.y); }
+					}
+					if (ty * TILE_H < height) { emit_tile_row(frame, it.tileBase, it.tilesX, ty, minL, maxR, it.cmdIndex); }
+				}
+			}
+		}
+	}
+
 	if (!EMIT) {
 		if (active) { frame.slotCounts[slot] = countCmd | (countRows << 3); }
-		// block totals for scan_kernel
+		// block totals for scan_blocks_kernel
 		uint32_t sumCmd = countCmd, sumRows = countRows;
 #pragma unroll
 		for (int d = 16; d > 0; d >>= 1) {
@@ -521,82 +654,114 @@ __global__ void __launch_bounds__(SETUP_THREADS) setup_kernel(TaskParams task, F
 		if (threadIdx.x == 0) {
 			uint32_t a = 0, b = 0;
 			for (int w = 0; w < SETUP_THREADS / 32; w++) { a += warpCmds[w]; b += warpRows[w]; }
-			frame.blockCmds[task.blockBase + blockIdx.x] = a;
-			frame.blockRows[task.blockBase + blockIdx.x] = b;
+			frame.blockCmds[blockIdx.x] = a;
+			frame.blockRows[blockIdx.x] = b;
 		}
 	}
 }
 
-// One CTA: exclusive scans of the per-block command/row totals and of the per-tile entry counts.
-__global__ void __launch_bounds__(1024) scan_kernel(FrameDev frame) {
-	__shared__ uint32_t warpSum[3][32];
-	__shared__ uint32_t carry[3];
+// One CTA: exclusive scans of the per-block command and row totals (submission order is preserved).
+__global__ void __launch_bounds__(1024) scan_blocks_kernel(FrameDev frame) {
+	__shared__ uint32_t warpSum[2][32];
+	__shared__ uint32_t carry[2];
 	int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	if (threadIdx.x < 3) { carry[threadIdx.x] = 0; }
+	if (threadIdx.x < 2) { carry[threadIdx.x] = 0; }
 	__syncthreads();
-	uint32_t maxTile = 0;
-	int32_t tileTotal = frame.tilesX * frame.tilesY;
-	int32_t longest = max(frame.blockCount, tileTotal);
-	for (int32_t base = 0; base < longest; base += 1024) {
+	for (int32_t base = 0; base < frame.blockCount; base += 1024) {
 		int32_t i = base + threadIdx.x;
-		uint32_t v[3];
+		uint32_t v[2];
 		v[0] = i < frame.blockCount ? frame.blockCmds[i] : 0u;
 		v[1] = i < frame.blockCount ? frame.blockRows[i] : 0u;
-		v[2] = i < tileTotal ? frame.tileCount[i] : 0u;
-		maxTile = max(maxTile, v[2]);
-		uint32_t inc[3] = {v[0], v[1], v[2]};
+		uint32_t inc[2] = {v[0], v[1]};
 #pragma unroll
 		for (int d = 1; d < 32; d <<= 1) {
 #pragma unroll
-			for (int k = 0; k < 3; k++) {
+			for (int k = 0; k < 2; k++) {
 				uint32_t a = __shfl_up_sync(0xffffffffu, inc[k], d);
 				if (lane >= d) { inc[k] += a; }
 			}
 		}
-		if (lane == 31) { for (int k = 0; k < 3; k++) { warpSum[k][warp] = inc[k]; } }
+		if (lane == 31) { for (int k = 0; k < 2; k++) { warpSum[k][warp] = inc[k]; } }
 		__syncthreads();
-		uint32_t pre[3] = {carry[0], carry[1], carry[2]};
-		for (int w = 0; w < warp; w++) { for (int k = 0; k < 3; k++) { pre[k] += warpSum[k][w]; } }
+		uint32_t pre[2] = {carry[0], carry[1]};
+		for (int w = 0; w < warp; w++) { for (int k = 0; k < 2; k++) { pre[k] += warpSum[k][w]; } }
 		if (i < frame.blockCount) {
 			frame.blockCmds[i] = pre[0] + inc[0] - v[0];
 			frame.blockRows[i] = pre[1] + inc[1] - v[1];
 		}
-		if (i < tileTotal) {
-			frame.tileOffset[i] = pre[2] + inc[2] - v[2];
-			frame.tileCursor[i] = 0;
-		}
 		__syncthreads();
-		if (threadIdx.x == 1023) { for (int k = 0; k < 3; k++) { carry[k] = pre[k] + inc[k]; } }
+		if (threadIdx.x == 1023) { for (int k = 0; k < 2; k++) { carry[k] = pre[k] + inc[k]; } }
 		__syncthreads();
 	}
-	// block-wide max of tile counts
-#pragma unroll
-	for (int d = 16; d > 0; d >>= 1) { maxTile = max(maxTile, __shfl_xor_sync(0xffffffffu, maxTile, d)); }
-	if (lane == 0) { warpSum[0][warp] = maxTile; }
-	__syncthreads();
 	if (threadIdx.x == 0) {
-		uint32_t m = 0;
-		for (int w = 0; w < 32; w++) { m = max(m, warpSum[0][w]); }
 		frame.totals[0] = carry[0];
 		frame.totals[1] = carry[1];
-		frame.totals[2] = carry[2];
-		frame.totals[3] = m;
-		frame.totals[4] = 0;
-		frame.tileOffset[tileTotal] = carry[2];
 	}
 }
 
-// Row intervals of the triangles taller than SMALL_ROWS: one warp per triangle, lanes stride over rows.
-__global__ void __launch_bounds__(256) big_rows_kernel(FrameDev frame) {
-	uint32_t count = frame.totals[4];
+// Every tile takes a segment of the entry pool sized by its counted upper bound. Order between tiles is irrelevant, so no scan:
+// one atomicAdd per warp.
+__global__ void __launch_bounds__(256) tile_alloc_kernel(FrameDev frame) {
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	int lane = threadIdx.x & 31;
-	for (uint32_t b = blockIdx.x * 8 + (threadIdx.x >> 5); b < count; b += gridDim.x * 8) {
-		const BigCmd &big = frame.big[b];
-		const Cmd &cmd = frame.cmds[big.cmdIndex];
-		EdgeSet edges;
-		long long fx[3] = {big.fx[0], big.fx[1], big.fx[2]}, fy[3] = {big.fy[0], big.fy[1], big.fy[2]};
-		edges_setup(edges, fx, fy, cmd.bx0, cmd.rowStart, cmd.bx1);
-		for (int32_t r = lane; r < cmd.rowCount; r += 32) { frame.rows[cmd.rowOffset + r] = edges_row(edges, cmd.rowStart + r); }
+	uint32_t c = i < frame.tileTotal ? frame.tileCount[i] : 0u;
+	uint32_t inc = c, mx = c;
+#pragma unroll
+	for (int d = 1; d < 32; d <<= 1) {
+		uint32_t a = __shfl_up_sync(0xffffffffu, inc, d);
+		if (lane >= d) { inc += a; }
+	}
+#pragma unroll
+	for (int d = 16; d > 0; d >>= 1) { mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d)); }
+	uint32_t base = 0;
+	if (lane == 31 && inc > 0) { base = atomicAdd(&frame.totals[2], inc); }
+	base = __shfl_sync(0xffffffffu, base, 31);
+	if (lane == 0 && mx > 0) { atomicMax(&frame.totals[3], mx); }
+	if (i < frame.tileTotal) {
+		frame.tileOffset[i] = base + inc - c;
+		frame.tileCursor[i] = 0;
+	}
+}
+
+// Restores ascending command order in the lists that hold more than 32 entries (shorter ones are sorted in registers by raster_kernel).
+__global__ void __launch_bounds__(SORT_THREADS) sort_lists_kernel(FrameDev frame) {
+	__shared__ uint32_t s[SORT_SMEM];
+	for (uint32_t tile = blockIdx.x; tile < frame.tileTotal; tile += gridDim.x) {
+		const uint32_t n = frame.tileCursor[tile];
+		if (n <= 32u) { continue; }
+		uint32_t *list = frame.tileList + frame.tileOffset[tile];
+		if (n <= (uint32_t)SORT_SMEM) {
+			uint32_t size = 64;
+			while (size < n) { size <<= 1; }
+			for (uint32_t i = threadIdx.x; i < size; i += SORT_THREADS) { s[i] = i < n ? list[i] : 0xFFFFFFFFu; }
+			__syncthreads();
+			for (uint32_t k = 2; k <= size; k <<= 1) {
+				for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+					for (uint32_t i = threadIdx.x; i < size; i += SORT_THREADS) {
+						uint32_t l = i ^ j;
+						if (l > i) {
+							uint32_t a = s[i], b = s[l];
+							bool ascending = (i & k) == 0;
+							if ((a > b) == ascending) { s[i] = b; s[l] = a; }
+						}
+					}
+					__syncthreads();
+				}
+			}
+			for (uint32_t i = threadIdx.x; i < n; i += SORT_THREADS) { list[i] = s[i]; }
+			__syncthreads();
+		} else {
+			// rank sort (keys are distinct): O(n^2 / threads), only for pathological pile-ups of thousands of triangles on one tile
+			uint32_t *tmp = frame.sortTmp + (size_t)blockIdx.x * frame.sortTmpStride;
+			for (uint32_t i = threadIdx.x; i < n; i += SORT_THREADS) {
+				uint32_t key = list[i], rank = 0;
+				for (uint32_t j = 0; j < n; j++) { rank += list[j] < key ? 1u : 0u; }
+				tmp[rank] = key;
+			}
+			__syncthreads();
+			for (uint32_t i = threadIdx.x; i < n; i += SORT_THREADS) { list[i] = tmp[i]; }
+			__syncthreads();
+		}
 	}
 }
 
@@ -669,196 +834,293 @@ __device__ __forceinline__ void sample_quad(const TexDev &t, bool highestResolut
 	}
 }
 
+
 // ------------------------------------------------------------------------------------------------ tile kernel
 
-struct RasterParams {
-	dfpsr_image color, depth; // data == nullptr when absent
-	int32_t width, height;
-	int32_t depthOnly;        // model_renderDepth semantics (1x1 aligned, per-pixel chain)
-	int32_t clear;            // targets are defined to be (clearColor, clearDepth) before this frame: no loads, every pixel stored
-	uint32_t clearColor;
-	float clearDepth;
-	uint32_t sortCapacity;    // entries of shared memory available for sorting a tile's list (power of two)
+// Checkpoint of one (command, row pair) at the left edge of the tile, written by lane (command, row pair) of the warp.
+//   mode 0: v[0..5] = running sums (upper, lower) at position `at`, still left of (or at) the inner block start
+//   mode 1: v[0..11] = the four lanes' sums inside the inner run at `at`, v[12..17] = sums after the run's closing multiplication
+//   mode 2: v[0..5] = running sums at `at`, right of the inner run
+//   mode 3: depth-only path: v[0], v[1] = depth at columns atU / atL of the upper / lower row
+//   mode -1: nothing of this command in this row pair of this tile
+struct Rec {
+	int32_t ul, ur, ll, lr; // row intervals of the pair, as stored
+	int32_t mode, at;
+	float v[18];
 };
+static_assert(sizeof(Rec) == 96, "Rec layout");
 
-// Bitonic sort of s[0..capacity) ascending, capacity a power of two, 256 threads.
-__device__ void sort_shared(uint32_t *s, uint32_t capacity) {
-	for (uint32_t k = 2; k <= capacity; k <<= 1) {
-		for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-			for (uint32_t i = threadIdx.x; i < capacity; i += blockDim.x) {
-				uint32_t l = i ^ j;
-				if (l > i) {
-					uint32_t a = s[i], b = s[l];
-					bool ascending = (i & k) == 0;
-					if ((a > b) == ascending) { s[i] = b; s[l] = a; }
-				}
-			}
-			__syncthreads();
-		}
+__device__ __forceinline__ uint32_t find_view(const ViewDev *views, int32_t viewCount, uint32_t tile) {
+	int32_t lo = 0, hi = viewCount - 1;
+	while (lo < hi) {
+		int32_t mid = (lo + hi + 1) >> 1;
+		if (views[mid].tileBase <= tile) { lo = mid; } else { hi = mid - 1; }
 	}
+	return (uint32_t)lo;
 }
 
-__global__ void __launch_bounds__(256, 2) raster_kernel(FrameDev frame, RasterParams rp, TexTable textures) {
-	extern __shared__ __align__(16) unsigned char smemRaw[];
-	Cmd *sCmd = (Cmd *)smemRaw;                                   // CHUNK commands
-	int2 *sRows = (int2 *)(smemRaw + sizeof(Cmd) * CHUNK);        // CHUNK x TILE row intervals
-	uint32_t *sList = (uint32_t *)(smemRaw + sizeof(Cmd) * CHUNK + sizeof(int2) * CHUNK * TILE);
-	__shared__ uint32_t sCount;
+// Ascending bitonic sort of one key per lane.
+__device__ __forceinline__ uint32_t warp_sort(uint32_t key, int lane) {
+#pragma unroll
+	for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+		for (int j = k >> 1; j > 0; j >>= 1) {
+			uint32_t other = __shfl_xor_sync(0xffffffffu, key, j);
+			bool ascending = (lane & k) == 0, lower = (lane & j) == 0;
+			bool takeMin = ascending == lower;
+			key = takeMin ? min(key, other) : max(key, other);
+		}
+	}
+	return key;
+}
 
-	const int32_t tile = blockIdx.x;
-	const int32_t tileX = tile % frame.tilesX, tileY = tile / frame.tilesX;
-	const uint32_t n = frame.tileCount[tile];
-	if (n == 0 && !rp.clear) { return; }
+template <bool DEPTH_ONLY>
+__global__ void __launch_bounds__(RASTER_WARPS * 32) raster_kernel(FrameDev frame, TexTable textures) {
+	__shared__ __align__(16) Rec sRecAll[RASTER_WARPS][32];
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const uint32_t tile = blockIdx.x * RASTER_WARPS + warp;
+	if (tile >= frame.tileTotal) { return; }
+	Rec *sRec = sRecAll[warp];
+
+	const ViewDev &vw = frame.views[frame.viewCount > 1 ? find_view(frame.views, frame.viewCount, tile) : 0u];
+	const int32_t tilesX = vw.tilesX;
+	const int32_t localTile = (int32_t)(tile - vw.tileBase);
+	const int32_t tileX = localTile % tilesX, tileY = localTile / tilesX;
+	if (tileY * TILE_H >= vw.clipBottom || tileY * TILE_H + TILE_H <= vw.clipTop) { return; }
+	const uint32_t n = frame.tileCursor[tile];
+	const bool clear = vw.clear != 0;
+	if (n == 0 && !clear) { return; }
 	const uint32_t *list = frame.tileList + frame.tileOffset[tile];
 
-	const int32_t qx = threadIdx.x & 15, qy = threadIdx.x >> 4;
-	const int32_t x0 = tileX * TILE + 2 * qx, y1 = tileY * TILE + 2 * qy, y2 = y1 + 1;
-	const bool hasColor = rp.color.data != nullptr, hasDepth = rp.depth.data != nullptr;
-	const bool in[4] = {x0 < rp.width && y1 < rp.height, x0 + 1 < rp.width && y1 < rp.height, x0 < rp.width && y2 < rp.height, x0 + 1 < rp.width && y2 < rp.height};
-	const uint32_t shifts = pack_shifts(rp.color.packOrder);
+	const int32_t width = vw.width, height = vw.height;
+	const int32_t tileLeft = tileX * TILE_W;
+	const int32_t qx = lane & 15, qy = lane >> 4;
+	const int32_t x0 = tileLeft + 2 * qx, y1 = tileY * TILE_H + 2 * qy, y2 = y1 + 1;
+	const dfpsr_image color = vw.color, depth = vw.depth;
+	const bool hasColor = !DEPTH_ONLY && color.data != nullptr, hasDepth = depth.data != nullptr;
+	const bool in[4] = {x0 < width && y1 < height, x0 + 1 < width && y1 < height, x0 < width && y2 < height, x0 + 1 < width && y2 < height};
+	const uint32_t shifts = pack_shifts(color.packOrder);
+	// ref: shader/fillerTemplates.h:286-331 — the last row pair of an odd-height target has no lower row and the reference lets its
+	// lower-row pointers repeat the upper row: unclipped quads then read and overwrite lanes 0/1 through lanes 2/3.
+	const bool aliasLower = y2 >= height;
 
 	uint32_t col[4];
 	float dep[4];
 #pragma unroll
 	for (int l = 0; l < 4; l++) {
 		int32_t px = x0 + (l & 1), py = y1 + (l >> 1);
-		col[l] = rp.clearColor; dep[l] = rp.clearDepth;
-		if (!rp.clear && in[l]) {
-			if (hasColor) { col[l] = row_ptr<uint32_t>(rp.color.data, rp.color.stride, py)[px]; }
-			if (hasDepth) { dep[l] = row_ptr<float>(rp.depth.data, rp.depth.stride, py)[px]; }
+		col[l] = vw.clearColor; dep[l] = vw.clearDepth;
+		if (!clear && in[l]) {
+			if (hasColor) { col[l] = row_ptr<uint32_t>(color.data, color.stride, py)[px]; }
+			if (hasDepth) { dep[l] = row_ptr<float>(depth.data, depth.stride, py)[px]; }
 		}
 	}
-	bool dirty = rp.clear != 0;
+	bool dirty = clear;
 
-	// The tile's list is consumed in ascending command order in windows of at most sortCapacity entries.
-	uint32_t processedBelow = 0; // every entry < processedBelow has been applied
-	uint32_t remaining = n;
-	while (remaining > 0) {
-		uint32_t windowEnd = 0xFFFFFFFFu; // exclusive upper key of this window
-		uint32_t windowCount = remaining;
-		if (remaining > rp.sortCapacity) {
-			// Binary search the largest key bound whose window still fits in shared memory.
-			uint32_t lo = processedBelow, hi = 0xFFFFFFFFu; // count(lo) fits, count(hi) does not
-			// invariant: entries in [processedBelow, lo) <= capacity; [processedBelow, hi) > capacity
-			while (hi - lo > 1) {
-				uint32_t mid = lo + (hi - lo) / 2;
-				if (threadIdx.x == 0) { sCount = 0; }
-				__syncthreads();
-				uint32_t mine = 0;
-				for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) { uint32_t e = list[i]; mine += (e >= processedBelow && e < mid) ? 1u : 0u; }
-				atomicAdd(&sCount, mine);
-				__syncthreads();
-				uint32_t c = sCount;
-				__syncthreads();
-				if (c <= rp.sortCapacity) { lo = mid; } else { hi = mid; }
-			}
-			windowEnd = lo;
-			if (threadIdx.x == 0) { sCount = 0; }
-			__syncthreads();
-			for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-				uint32_t e = list[i];
-				if (e >= processedBelow && e < windowEnd) { sList[atomicAdd(&sCount, 1u)] = e; }
-			}
-			__syncthreads();
-			windowCount = sCount;
-			__syncthreads();
-		} else {
-			if (threadIdx.x == 0) { sCount = 0; }
-			__syncthreads();
-			for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-				uint32_t e = list[i];
-				if (e >= processedBelow) { sList[atomicAdd(&sCount, 1u)] = e; }
-			}
-			__syncthreads();
-			windowCount = sCount;
-			__syncthreads();
-		}
-		// pad to a power of two and sort
-		uint32_t sortSize = 1;
-		while (sortSize < windowCount) { sortSize <<= 1; }
-		for (uint32_t i = windowCount + threadIdx.x; i < sortSize; i += blockDim.x) { sList[i] = 0xFFFFFFFFu; }
-		__syncthreads();
-		if (windowCount > 1) { sort_shared(sList, sortSize); }
+	// lists of up to 32 entries are sorted here; longer ones were sorted by sort_lists_kernel
+	uint32_t sortedKey = 0xFFFFFFFFu;
+	if (n <= 32u) {
+		sortedKey = (uint32_t)lane < n ? __ldg(list + lane) : 0xFFFFFFFFu;
+		if (n > 1u) { sortedKey = warp_sort(sortedKey, lane); }
+	}
 
-		for (uint32_t chunkStart = 0; chunkStart < windowCount; chunkStart += CHUNK) {
-			const uint32_t chunkCount = min((uint32_t)CHUNK, windowCount - chunkStart);
-			// stage CHUNK command records and their row intervals for this tile's 32 rows
-			for (uint32_t w = threadIdx.x; w < chunkCount * (sizeof(Cmd) / 16); w += blockDim.x) {
-				uint32_t c = w / (sizeof(Cmd) / 16), part = w % (sizeof(Cmd) / 16);
-				((uint4 *)&sCmd[c])[part] = __ldg(((const uint4 *)&frame.cmds[sList[chunkStart + c]]) + part);
-			}
-			__syncthreads();
-			for (uint32_t w = threadIdx.x; w < chunkCount * TILE; w += blockDim.x) {
-				uint32_t c = w / TILE, r = w % TILE;
-				int32_t idx = tileY * TILE + (int32_t)r - sCmd[c].rowStart;
-				int2 row = make_int2(0, 0);
-				if (idx >= 0 && idx < sCmd[c].rowCount) { row = frame.rows[sCmd[c].rowOffset + idx]; }
-				sRows[c * TILE + r] = row;
-			}
-			__syncthreads();
-
-			for (uint32_t c = 0; c < chunkCount; c++) {
-				const Cmd &cmd = sCmd[c];
-				int2 upperRow = sRows[c * TILE + 2 * qy], lowerRow = sRows[c * TILE + 2 * qy + 1];
-				const uint32_t flags = cmd.flags;
-				const bool affine = (flags & CMD_AFFINE) != 0;
-
-				if (rp.depthOnly) {
-					// ref: implementation/render/renderCore.cpp:343-387 — per row: value at row.left, then += dx per pixel
+	for (uint32_t batchStart = 0; batchStart < n; batchStart += BATCH) {
+		const uint32_t batchCount = min((uint32_t)BATCH, n - batchStart);
+		// ---- lane (c, r): checkpoint of command c for row pair r of this tile
+		const uint32_t c = (uint32_t)lane & 15u, r = (uint32_t)lane >> 4;
+		uint32_t key;
+		if (n <= 32u) { key = __shfl_sync(0xffffffffu, sortedKey, (int)(batchStart + c) & 31); }
+		else { key = c < batchCount ? __ldg(list + batchStart + c) : 0u; }
+		{
+			Rec rec;
+			rec.mode = -1; rec.at = 0; rec.ul = rec.ur = rec.ll = rec.lr = 0;
+			if (c < batchCount) {
+				const Cmd *cmd = frame.cmds + key;
+				const int4 head = __ldg((const int4 *)cmd + 3); // rowStart, rowCount, rowOffset, pad
+				const int32_t rowStart = head.x, rowCount = head.y;
+				const uint32_t rowOffset = (uint32_t)head.z;
+				const int32_t yTop = tileY * TILE_H + 2 * (int32_t)r;
+				const int32_t idx = yTop - rowStart;
+				if (idx >= 0 && idx < rowCount) {
+					const int4 rr = __ldg((const int4 *)(frame.rows + rowOffset + (uint32_t)idx)); // rows idx and idx + 1 (both even-aligned)
+					rec.ul = rr.x; rec.ur = rr.y; rec.ll = rr.z; rec.lr = rr.w;
+					float start[3], dx[3], dy[3];
+					{
+						const float4 a = __ldg((const float4 *)cmd), b = __ldg((const float4 *)cmd + 1);
+						const float last = __ldg(&cmd->dy[2]);
+						start[0] = a.x; start[1] = a.y; start[2] = a.z; dx[0] = a.w; dx[1] = b.x; dx[2] = b.y; dy[0] = b.z; dy[1] = b.w; dy[2] = last;
+					}
+					if (DEPTH_ONLY) {
+						// ref: implementation/render/renderCore.cpp:343-387 — per row: value at row.left, then += dx per pixel
+						const bool hasU = rec.ur > rec.ul && rec.ur > tileLeft && rec.ul < tileLeft + TILE_W;
+						const bool hasL = rec.lr > rec.ll && rec.lr > tileLeft && rec.ll < tileLeft + TILE_W && yTop + 1 < height;
+						if (hasU || hasL) {
+							rec.mode = 3;
+							float vu = (start[0] + (dx[0] * ((float)rec.ul + 0.5f))) + (dy[0] * ((float)yTop + 0.5f));
+							float vl = (start[0] + (dx[0] * ((float)rec.ll + 0.5f))) + (dy[0] * ((float)(yTop + 1) + 0.5f));
+							if (hasU) { for (int32_t s = rec.ul; s < tileLeft; s++) { vu += dx[0]; } }
+							if (hasL) { for (int32_t s = rec.ll; s < tileLeft; s++) { vl += dx[0]; } }
+							rec.v[0] = vu; rec.v[1] = vl;
+						}
+					} else {
+						// ref: shader/fillerTemplates.h:275-300
+						const int32_t outerStart = min(rec.ul, rec.ll), outerEnd = max(rec.ur, rec.lr);
+						const int32_t innerStart = max(rec.ul, rec.ll), innerEnd = min(rec.ur, rec.lr);
+						const int32_t obs = outerStart & ~1, obe = (outerEnd + 1) & ~1, ibs = (innerStart + 1) & ~1, ibe = innerEnd & ~1;
+						const bool hasTop = rec.ur > rec.ul, hasBottom = (yTop + 1 < height) && rec.lr > rec.ll;
+						if ((hasTop || hasBottom) && obe > tileLeft && obs < tileLeft + TILE_W) {
+							// Replay of the reference's running sums (fillerTemplates.h:329-372) from the outer block start to the tile.
+							float up[3], lo[3], dx2[3];
+							const float fx = (float)obs + 0.5f, fy = (float)yTop + 0.5f;
 #pragma unroll
-					for (int l = 0; l < 4; l++) {
-						int2 row = (l < 2) ? upperRow : lowerRow;
-						int32_t px = x0 + (l & 1), py = y1 + (l >> 1);
-						if (px >= row.x && px < row.y && py < rp.height) {
-							float value = (cmd.start[0] + (cmd.dx[0] * ((float)row.x + 0.5f))) + (cmd.dy[0] * ((float)py + 0.5f));
-							for (int32_t s = row.x; s < px; s++) { value += cmd.dx[0]; }
-							if (affine ? (value < dep[l]) : (value > dep[l])) { dep[l] = value; dirty = true; }
+							for (int k = 0; k < 3; k++) {
+								up[k] = (start[k] + (dx[k] * fx)) + (dy[k] * fy);
+								lo[k] = up[k] + dy[k];
+								dx2[k] = dx[k] * 2.0f;
+							}
+							const int32_t at = max(obs, tileLeft);
+							const bool noInner = ibe <= ibs;
+							rec.at = at;
+							if (noInner || at <= ibs) {
+								for (int32_t s = obs; s < at; s += 2) {
+#pragma unroll
+									for (int k = 0; k < 3; k++) { up[k] += dx2[k]; lo[k] += dx2[k]; }
+								}
+								rec.mode = 0;
+#pragma unroll
+								for (int k = 0; k < 3; k++) { rec.v[k] = up[k]; rec.v[3 + k] = lo[k]; }
+							} else {
+								for (int32_t s = obs; s < ibs; s += 2) {
+#pragma unroll
+									for (int k = 0; k < 3; k++) { up[k] += dx2[k]; lo[k] += dx2[k]; }
+								}
+								const float quadCount = (float)((ibe - ibs) / 2);
+								if (at < ibe) {
+									float lanes[3][4];
+#pragma unroll
+									for (int k = 0; k < 3; k++) { lanes[k][0] = up[k]; lanes[k][1] = up[k] + dx[k]; lanes[k][2] = lo[k]; lanes[k][3] = lo[k] + dx[k]; }
+									for (int32_t s = ibs; s < at; s += 2) {
+#pragma unroll
+										for (int k = 0; k < 3; k++) {
+#pragma unroll
+											for (int l = 0; l < 4; l++) { lanes[k][l] += dx2[k]; }
+										}
+									}
+									rec.mode = 1;
+#pragma unroll
+									for (int k = 0; k < 3; k++) {
+#pragma unroll
+										for (int l = 0; l < 4; l++) { rec.v[k * 4 + l] = lanes[k][l]; }
+										rec.v[12 + k] = up[k] + (dx2[k] * quadCount);
+										rec.v[15 + k] = lo[k] + (dx2[k] * quadCount);
+									}
+								} else {
+#pragma unroll
+									for (int k = 0; k < 3; k++) { up[k] = up[k] + (dx2[k] * quadCount); lo[k] = lo[k] + (dx2[k] * quadCount); }
+									for (int32_t s = ibe; s < at; s += 2) {
+#pragma unroll
+										for (int k = 0; k < 3; k++) { up[k] += dx2[k]; lo[k] += dx2[k]; }
+									}
+									rec.mode = 2;
+#pragma unroll
+									for (int k = 0; k < 3; k++) { rec.v[k] = up[k]; rec.v[3 + k] = lo[k]; }
+								}
+							}
 						}
 					}
-					continue;
 				}
+			}
+			// 96-byte record as six 16-byte stores
+			uint4 *dst = (uint4 *)&sRec[r * BATCH + c];
+			const uint4 *src = (const uint4 *)&rec;
+#pragma unroll
+			for (int w = 0; w < 6; w++) { dst[w] = src[w]; }
+		}
+		__syncwarp();
+		// which commands of the batch touch this tile at all (either row pair)
+		const bool mine = sRec[r * BATCH + c].mode >= 0;
+		const uint32_t touched = __ballot_sync(0xffffffffu, mine);
+		uint32_t pending = (touched | (touched >> 16)) & 0xFFFFu & ((1u << batchCount) - 1u);
 
-				// ref: shader/fillerTemplates.h:275-300
-				int32_t outerStart = min(upperRow.x, lowerRow.x), outerEnd = max(upperRow.y, lowerRow.y);
-				int32_t innerStart = max(upperRow.x, lowerRow.x), innerEnd = min(upperRow.y, lowerRow.y);
-				int32_t obs = outerStart & ~1, obe = (outerEnd + 1) & ~1, ibs = (innerStart + 1) & ~1, ibe = innerEnd & ~1;
-				if (y2 >= rp.height) { lowerRow.y = lowerRow.x; }
-				bool hasTop = upperRow.y > upperRow.x, hasBottom = lowerRow.y > lowerRow.x;
-				if (!(hasTop || hasBottom)) { continue; }
-				if (x0 < obs || x0 >= obe) { continue; }
+		while (pending != 0u) {
+			const uint32_t ci = (uint32_t)__ffs((int)pending) - 1u;
+			pending &= pending - 1u;
+			const uint32_t cmdKey = __shfl_sync(0xffffffffu, key, (int)ci);
+			const Rec &rec = sRec[(uint32_t)qy * BATCH + ci];
+			const int32_t mode = rec.mode;
+			if (mode < 0) { continue; }
+			const Cmd &cmd = frame.cmds[cmdKey];
+			int2 upperRow = make_int2(rec.ul, rec.ur), lowerRow = make_int2(rec.ll, rec.lr);
+			const uint32_t flags = __ldg(&cmd.flags);
+			const bool affine = (flags & CMD_AFFINE) != 0;
 
-				// Replay of the reference's running sums (fillerTemplates.h:329-372): start at the outer block start,
-				// add 2*dx per quad; inner (unclipped) runs advance all four lanes separately; after an inner run the
-				// base jumps by one multiplication.
-				float up[3], lo[3], dx2[3];
-				{
-					float fx = (float)obs + 0.5f, fy = (float)y1 + 0.5f;
+			if (DEPTH_ONLY) {
+				const float dx0 = __ldg(&cmd.dx[0]);
+#pragma unroll
+				for (int l = 0; l < 4; l++) {
+					const int2 row = (l < 2) ? upperRow : lowerRow;
+					const int32_t px = x0 + (l & 1), py = y1 + (l >> 1);
+					if (px >= row.x && px < row.y && py < height) {
+						float value = rec.v[l >> 1];
+						for (int32_t s = max(row.x, tileLeft); s < px; s++) { value += dx0; }
+						if (affine ? (value < dep[l]) : (value > dep[l])) { dep[l] = value; dirty = true; }
+					}
+				}
+				continue;
+			}
+
+			const int32_t outerStart = min(upperRow.x, lowerRow.x), outerEnd = max(upperRow.y, lowerRow.y);
+			const int32_t innerStart = max(upperRow.x, lowerRow.x), innerEnd = min(upperRow.y, lowerRow.y);
+			const int32_t obs = outerStart & ~1, obe = (outerEnd + 1) & ~1, ibs = (innerStart + 1) & ~1, ibe = innerEnd & ~1;
+			if (y2 >= height) { lowerRow.y = lowerRow.x; }
+			if (x0 < obs || x0 >= obe) { continue; }
+			float dx[3];
+			{
+				const float4 a = __ldg((const float4 *)&cmd), b = __ldg((const float4 *)&cmd + 1);
+				dx[0] = a.w; dx[1] = b.x; dx[2] = b.y;
+			}
+			const float dx2[3] = {dx[0] * 2.0f, dx[1] * 2.0f, dx[2] * 2.0f};
+			const int32_t at = rec.at;
+			const bool noInner = ibe <= ibs;
+			float lanes[3][4];
+			bool clipSides = true;
+			if (mode == 1 && x0 < ibe) {
+				clipSides = false;
+#pragma unroll
+				for (int k = 0; k < 3; k++) {
+#pragma unroll
+					for (int l = 0; l < 4; l++) { lanes[k][l] = rec.v[k * 4 + l]; }
+				}
+				for (int32_t s = at; s < x0; s += 2) {
 #pragma unroll
 					for (int k = 0; k < 3; k++) {
-						up[k] = (cmd.start[k] + (cmd.dx[k] * fx)) + (cmd.dy[k] * fy);
-						lo[k] = up[k] + cmd.dy[k];
-						dx2[k] = cmd.dx[k] * 2.0f;
+#pragma unroll
+						for (int l = 0; l < 4; l++) { lanes[k][l] += dx2[k]; }
 					}
 				}
-				float lanes[3][4];
-				bool clipSides = true;
-				const bool noInner = ibe <= ibs;
-				if (noInner || x0 < ibs) {
-					for (int32_t s = obs; s < x0; s += 2) {
+			} else {
+				float up[3], lo[3];
+				int32_t from = at;
+				if (mode == 1) {
 #pragma unroll
-						for (int k = 0; k < 3; k++) { up[k] += dx2[k]; lo[k] += dx2[k]; }
-					}
-#pragma unroll
-					for (int k = 0; k < 3; k++) { lanes[k][0] = up[k]; lanes[k][1] = up[k] + cmd.dx[k]; lanes[k][2] = lo[k]; lanes[k][3] = lo[k] + cmd.dx[k]; }
+					for (int k = 0; k < 3; k++) { up[k] = rec.v[12 + k]; lo[k] = rec.v[15 + k]; }
+					from = ibe;
 				} else {
-					for (int32_t s = obs; s < ibs; s += 2) {
+#pragma unroll
+					for (int k = 0; k < 3; k++) { up[k] = rec.v[k]; lo[k] = rec.v[3 + k]; }
+				}
+				bool inner = false;
+				if (mode == 0 && !noInner && x0 >= ibs) {
+					// the inner run starts inside this tile: finish the left edge, then either enter the run or jump over it
+					for (int32_t s = from; s < ibs; s += 2) {
 #pragma unroll
 						for (int k = 0; k < 3; k++) { up[k] += dx2[k]; lo[k] += dx2[k]; }
 					}
 					if (x0 < ibe) {
+						inner = true;
 						clipSides = false;
 #pragma unroll
-						for (int k = 0; k < 3; k++) { lanes[k][0] = up[k]; lanes[k][1] = up[k] + cmd.dx[k]; lanes[k][2] = lo[k]; lanes[k][3] = lo[k] + cmd.dx[k]; }
+						for (int k = 0; k < 3; k++) { lanes[k][0] = up[k]; lanes[k][1] = up[k] + dx[k]; lanes[k][2] = lo[k]; lanes[k][3] = lo[k] + dx[k]; }
 						for (int32_t s = ibs; s < x0; s += 2) {
 #pragma unroll
 							for (int k = 0; k < 3; k++) {
@@ -867,118 +1129,130 @@ __global__ void __launch_bounds__(256, 2) raster_kernel(FrameDev frame, RasterPa
 							}
 						}
 					} else {
-						float quadCount = (float)((ibe - ibs) / 2);
+						const float quadCount = (float)((ibe - ibs) / 2);
 #pragma unroll
 						for (int k = 0; k < 3; k++) { up[k] = up[k] + (dx2[k] * quadCount); lo[k] = lo[k] + (dx2[k] * quadCount); }
-						for (int32_t s = ibe; s < x0; s += 2) {
-#pragma unroll
-							for (int k = 0; k < 3; k++) { up[k] += dx2[k]; lo[k] += dx2[k]; }
-						}
-#pragma unroll
-						for (int k = 0; k < 3; k++) { lanes[k][0] = up[k]; lanes[k][1] = up[k] + cmd.dx[k]; lanes[k][2] = lo[k]; lanes[k][3] = lo[k] + cmd.dx[k]; }
+						from = ibe;
 					}
 				}
-
-				// ref: shader/fillerTemplates.h:196-243 — weights; :93-138 — visibility
-				float wa[4], wb[4], wc[4];
-				bool vis[4];
-				bool anyVisible = false;
+				if (!inner) {
+					for (int32_t s = from; s < x0; s += 2) {
 #pragma unroll
-				for (int l = 0; l < 4; l++) {
-					if (affine) { wb[l] = lanes[1][l]; wc[l] = lanes[2][l]; }
-					else { float linearDepth = 1.0f / lanes[0][l]; wb[l] = lanes[1][l] * linearDepth; wc[l] = lanes[2][l] * linearDepth; }
-					wa[l] = 1.0f - (wb[l] + wc[l]);
-					bool visible = true;
-					if (clipSides) {
-						int2 row = (l < 2) ? upperRow : lowerRow;
-						int32_t px = x0 + (l & 1);
-						visible = px >= row.x && px < row.y;
+						for (int k = 0; k < 3; k++) { up[k] += dx2[k]; lo[k] += dx2[k]; }
 					}
-					if (visible && hasDepth) { visible = affine ? (lanes[0][l] < dep[l]) : (lanes[0][l] > dep[l]); }
-					vis[l] = visible;
-					anyVisible = anyVisible || visible;
-				}
-				if (!anyVisible) { continue; }
-
-				if (hasColor) {
-					// ref: shader/RgbaMultiply.h:75-106
-					float rgba[4][4];
-					const bool hasDiffuse = (flags & CMD_HAS_DIFFUSE) != 0, hasLight = (flags & CMD_HAS_LIGHT) != 0;
-					const bool fade = (flags & CMD_HAS_FADE) != 0, colorless = (flags & CMD_COLORLESS) != 0 && !fade;
-					if (hasDiffuse && !hasLight && colorless) {
-						sample_quad<false>(textures.t[(flags >> 8) & 0xFFFu], false, cmd.u1, cmd.v1, wa, wb, wc, rgba);
-					} else if (hasLight && !hasDiffuse && colorless) {
-						sample_quad<false>(textures.t[flags >> 20], true, cmd.u2, cmd.v2, wa, wb, wc, rgba);
-					} else {
 #pragma unroll
-						for (int l = 0; l < 4; l++) {
-							if (fade) {
-								rgba[l][0] = interpolate3(cmd.red, wa[l], wb[l], wc[l]);
-								rgba[l][1] = interpolate3(cmd.green, wa[l], wb[l], wc[l]);
-								rgba[l][2] = interpolate3(cmd.blue, wa[l], wb[l], wc[l]);
-								rgba[l][3] = interpolate3(cmd.alpha, wa[l], wb[l], wc[l]);
-							} else {
-								rgba[l][0] = cmd.red[0]; rgba[l][1] = cmd.green[0]; rgba[l][2] = cmd.blue[0]; rgba[l][3] = cmd.alpha[0];
-							}
-						}
-						if (hasDiffuse) { sample_quad<true>(textures.t[(flags >> 8) & 0xFFFu], false, cmd.u1, cmd.v1, wa, wb, wc, rgba); }
-						if (hasLight) { sample_quad<true>(textures.t[flags >> 20], true, cmd.u2, cmd.v2, wa, wb, wc, rgba); }
-					}
-					const bool alphaFilter = (flags & CMD_ALPHA) != 0;
-#pragma unroll
-					for (int l = 0; l < 4; l++) {
-						if (alphaFilter) {
-							// ref: shader/fillerTemplates.h:155-176; lanes that are not visible read as 0 when clipping sides
-							float opacity = rgba[l][3] * (1.0f / 255.0f);
-							uint32_t target = (vis[l] || !clipSides) ? col[l] : 0u;
-							float inv = 1.0f - opacity;
-							float tr = (float)((target >> (shifts & 31u)) & 255u), tg = (float)((target >> ((shifts >> 8) & 31u)) & 255u);
-							float tb = (float)((target >> ((shifts >> 16) & 31u)) & 255u), ta = (float)((target >> ((shifts >> 24) & 31u)) & 255u);
-							rgba[l][0] = (rgba[l][0] * opacity) + (tr * inv);
-							rgba[l][1] = (rgba[l][1] * opacity) + (tg * inv);
-							rgba[l][2] = (rgba[l][2] * opacity) + (tb * inv);
-							rgba[l][3] = (rgba[l][3] * opacity) + (ta * inv);
-						}
-						if (vis[l]) {
-							col[l] = pack_rgba_ordered(saturated_byte(rgba[l][0]), saturated_byte(rgba[l][1]), saturated_byte(rgba[l][2]), saturated_byte(rgba[l][3]), shifts);
-							dirty = true;
-						}
-					}
-					// ref: shader/fillerTemplates.h:387-441 — alpha filtering leaves depth untouched when both buffers exist
-					if (hasDepth && !alphaFilter) {
-#pragma unroll
-						for (int l = 0; l < 4; l++) { if (vis[l]) { dep[l] = lanes[0][l]; } }
-					}
-				} else if (hasDepth) {
-#pragma unroll
-					for (int l = 0; l < 4; l++) { if (vis[l]) { dep[l] = lanes[0][l]; dirty = true; } }
+					for (int k = 0; k < 3; k++) { lanes[k][0] = up[k]; lanes[k][1] = up[k] + dx[k]; lanes[k][2] = lo[k]; lanes[k][3] = lo[k] + dx[k]; }
 				}
 			}
-			__syncthreads();
+
+			// ref: shader/fillerTemplates.h:196-243 — weights; :93-138 — visibility
+			float wa[4], wb[4], wc[4];
+			bool vis[4];
+			bool anyVisible = false;
+			const bool repeatUpper = aliasLower && !clipSides; // lanes 2/3 act on the pixels of lanes 0/1
+#pragma unroll
+			for (int l = 0; l < 4; l++) {
+				if (affine) { wb[l] = lanes[1][l]; wc[l] = lanes[2][l]; }
+				else { float linearDepth = 1.0f / lanes[0][l]; wb[l] = lanes[1][l] * linearDepth; wc[l] = lanes[2][l] * linearDepth; }
+				wa[l] = 1.0f - (wb[l] + wc[l]);
+				bool visible = true;
+				if (clipSides) {
+					int2 row = (l < 2) ? upperRow : lowerRow;
+					int32_t px = x0 + (l & 1);
+					visible = px >= row.x && px < row.y;
+				}
+				if (visible && hasDepth) {
+					const float old = (l >= 2 && repeatUpper) ? dep[l - 2] : dep[l];
+					visible = affine ? (lanes[0][l] < old) : (lanes[0][l] > old);
+				}
+				vis[l] = visible;
+				anyVisible = anyVisible || visible;
+			}
+			if (!anyVisible) { continue; }
+
+			if (hasColor) {
+				// ref: shader/RgbaMultiply.h:75-106
+				float rgba[4][4];
+				const bool hasDiffuse = (flags & CMD_HAS_DIFFUSE) != 0, hasLight = (flags & CMD_HAS_LIGHT) != 0;
+				const bool fade = (flags & CMD_HAS_FADE) != 0, colorless = (flags & CMD_COLORLESS) != 0 && !fade;
+				if (hasDiffuse && !hasLight && colorless) {
+					sample_quad<false>(textures.t[(flags >> 8) & 0xFFFu], false, cmd.u1, cmd.v1, wa, wb, wc, rgba);
+				} else if (hasLight && !hasDiffuse && colorless) {
+					sample_quad<false>(textures.t[flags >> 20], true, cmd.u2, cmd.v2, wa, wb, wc, rgba);
+				} else {
+#pragma unroll
+					for (int l = 0; l < 4; l++) {
+						if (fade) {
+							rgba[l][0] = interpolate3(cmd.red, wa[l], wb[l], wc[l]);
+							rgba[l][1] = interpolate3(cmd.green, wa[l], wb[l], wc[l]);
+							rgba[l][2] = interpolate3(cmd.blue, wa[l], wb[l], wc[l]);
+							rgba[l][3] = interpolate3(cmd.alpha, wa[l], wb[l], wc[l]);
+						} else {
+							rgba[l][0] = cmd.red[0]; rgba[l][1] = cmd.green[0]; rgba[l][2] = cmd.blue[0]; rgba[l][3] = cmd.alpha[0];
+						}
+					}
+					if (hasDiffuse) { sample_quad<true>(textures.t[(flags >> 8) & 0xFFFu], false, cmd.u1, cmd.v1, wa, wb, wc, rgba); }
+					if (hasLight) { sample_quad<true>(textures.t[flags >> 20], true, cmd.u2, cmd.v2, wa, wb, wc, rgba); }
+				}
+				const bool alphaFilter = (flags & CMD_ALPHA) != 0;
+				uint32_t packed[4];
+#pragma unroll
+				for (int l = 0; l < 4; l++) {
+					if (alphaFilter) {
+						// ref: shader/fillerTemplates.h:155-176; all four reads precede the writes; lanes that are not visible read 0 when clipping sides
+						float opacity = rgba[l][3] * (1.0f / 255.0f);
+						uint32_t target = (vis[l] || !clipSides) ? ((l >= 2 && repeatUpper) ? col[l - 2] : col[l]) : 0u;
+						float inv = 1.0f - opacity;
+						float tr = (float)((target >> (shifts & 31u)) & 255u), tg = (float)((target >> ((shifts >> 8) & 31u)) & 255u);
+						float tb = (float)((target >> ((shifts >> 16) & 31u)) & 255u), ta = (float)((target >> ((shifts >> 24) & 31u)) & 255u);
+						rgba[l][0] = (rgba[l][0] * opacity) + (tr * inv);
+						rgba[l][1] = (rgba[l][1] * opacity) + (tg * inv);
+						rgba[l][2] = (rgba[l][2] * opacity) + (tb * inv);
+						rgba[l][3] = (rgba[l][3] * opacity) + (ta * inv);
+					}
+					packed[l] = pack_rgba_ordered(saturated_byte(rgba[l][0]), saturated_byte(rgba[l][1]), saturated_byte(rgba[l][2]), saturated_byte(rgba[l][3]), shifts);
+				}
+				// writes in lane order (clippedWrite); with a repeated upper row lanes 2/3 land on lanes 0/1
+				if (vis[0]) { col[0] = packed[0]; }
+				if (vis[1]) { col[1] = packed[1]; }
+				if (vis[2]) { if (repeatUpper) { col[0] = packed[2]; } else { col[2] = packed[2]; } }
+				if (vis[3]) { if (repeatUpper) { col[1] = packed[3]; } else { col[3] = packed[3]; } }
+				dirty = true;
+				// ref: shader/fillerTemplates.h:387-441 — alpha filtering leaves depth untouched when both buffers exist
+				if (hasDepth && !alphaFilter) {
+					if (vis[0]) { dep[0] = lanes[0][0]; }
+					if (vis[1]) { dep[1] = lanes[0][1]; }
+					if (vis[2]) { if (repeatUpper) { dep[0] = lanes[0][2]; } else { dep[2] = lanes[0][2]; } }
+					if (vis[3]) { if (repeatUpper) { dep[1] = lanes[0][3]; } else { dep[3] = lanes[0][3]; } }
+				}
+			} else if (hasDepth) {
+				if (vis[0]) { dep[0] = lanes[0][0]; }
+				if (vis[1]) { dep[1] = lanes[0][1]; }
+				if (vis[2]) { if (repeatUpper) { dep[0] = lanes[0][2]; } else { dep[2] = lanes[0][2]; } }
+				if (vis[3]) { if (repeatUpper) { dep[1] = lanes[0][3]; } else { dep[3] = lanes[0][3]; } }
+				dirty = true;
+			}
 		}
-		processedBelow = windowEnd;
-		remaining -= windowCount;
+		__syncwarp();
 	}
 
 	if (dirty) {
-		// each thread owns 2 adjacent pixels in two rows: 8-byte stores, 128 contiguous bytes per row per half-warp
+		// each lane owns 2 adjacent pixels in two rows: 8-byte stores (when the row is 8-byte aligned), 128 contiguous bytes per row per half-warp
 		if (hasColor) {
-			if (in[0] && in[1]) { *(uint2 *)(row_ptr<uint32_t>(rp.color.data, rp.color.stride, y1) + x0) = make_uint2(col[0], col[1]); }
-			else if (in[0]) { row_ptr<uint32_t>(rp.color.data, rp.color.stride, y1)[x0] = col[0]; }
-			if (in[2] && in[3]) { *(uint2 *)(row_ptr<uint32_t>(rp.color.data, rp.color.stride, y2) + x0) = make_uint2(col[2], col[3]); }
-			else if (in[2]) { row_ptr<uint32_t>(rp.color.data, rp.color.stride, y2)[x0] = col[2]; }
+			uint32_t *upper = row_ptr<uint32_t>(color.data, color.stride, y1) + x0, *lower = row_ptr<uint32_t>(color.data, color.stride, y2) + x0;
+			if (in[0] && in[1] && (((uintptr_t)upper) & 7u) == 0) { *(uint2 *)upper = make_uint2(col[0], col[1]); }
+			else { if (in[0]) { upper[0] = col[0]; } if (in[1]) { upper[1] = col[1]; } }
+			if (in[2] && in[3] && (((uintptr_t)lower) & 7u) == 0) { *(uint2 *)lower = make_uint2(col[2], col[3]); }
+			else { if (in[2]) { lower[0] = col[2]; } if (in[3]) { lower[1] = col[3]; } }
 		}
 		if (hasDepth) {
-			if (in[0] && in[1]) { *(float2 *)(row_ptr<float>(rp.depth.data, rp.depth.stride, y1) + x0) = make_float2(dep[0], dep[1]); }
-			else if (in[0]) { row_ptr<float>(rp.depth.data, rp.depth.stride, y1)[x0] = dep[0]; }
-			if (in[2] && in[3]) { *(float2 *)(row_ptr<float>(rp.depth.data, rp.depth.stride, y2) + x0) = make_float2(dep[2], dep[3]); }
-			else if (in[2]) { row_ptr<float>(rp.depth.data, rp.depth.stride, y2)[x0] = dep[2]; }
+			float *upper = row_ptr<float>(depth.data, depth.stride, y1) + x0, *lower = row_ptr<float>(depth.data, depth.stride, y2) + x0;
+			if (in[0] && in[1] && (((uintptr_t)upper) & 7u) == 0) { *(float2 *)upper = make_float2(dep[0], dep[1]); }
+			else { if (in[0]) { upper[0] = dep[0]; } if (in[1]) { upper[1] = dep[1]; } }
+			if (in[2] && in[3] && (((uintptr_t)lower) & 7u) == 0) { *(float2 *)lower = make_float2(dep[2], dep[3]); }
+			else { if (in[2]) { lower[0] = dep[2]; } if (in[3]) { lower[1] = dep[3]; } }
 		}
 	}
-}
-
-__global__ void __launch_bounds__(256) zero_kernel(uint32_t *data, int32_t count) {
-	for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) { data[i] = 0u; }
 }
 
 } // namespace dfpsr
@@ -987,34 +1261,22 @@ __global__ void __launch_bounds__(256) zero_kernel(uint32_t *data, int32_t count
 
 using namespace dfpsr;
 
-struct FrameTask {
-	TaskParams params;
-};
-
 struct dfpsr_renderer {
 	bool receiving = false;
-	dfpsr_image color{}, depth{};
-	int32_t width = 0, height = 0;
 	bool depthOnly = false;
-	bool clear = false;
-	uint32_t clearColor = 0;
-	float clearDepth = 0.0f;
-	std::vector<FrameTask> tasks;
-	std::vector<DeviceBuffer> projected; // one per task, reused across frames
-	std::vector<DeviceBuffer> uploads;   // host triangle batches
+	std::vector<ViewDev> views;
+	std::vector<TaskParams> tasks;
+	std::vector<DeviceBuffer> uploads;   // host triangle batches of this frame
+	size_t uploadCount = 0;
 	TexTable textures{};
 	int textureCount = 0;
-	int32_t slotTotal = 0, blockTotal = 0;
 	int64_t lastCommands = -1;
-	DeviceBuffer slotCounts, blockCmds, blockRows, tileCount, tileOffset, tileCursor, totals, cmds, rows, tileList, big;
+	DeviceBuffer dTasks, dViews, projected, slotCounts, blockCmds, blockRows, tileCount, tileOffset, tileCursor, cmds, rows, tileList, sortTmp;
 	uint32_t *hostTotals = nullptr; // pinned
-	FrameDev frame{};
-	bool countsZeroed = false;
 
 	~dfpsr_renderer() {
-		for (auto &b : projected) { b.release(); }
 		for (auto &b : uploads) { b.release(); }
-		DeviceBuffer *all[] = {&slotCounts, &blockCmds, &blockRows, &tileCount, &tileOffset, &tileCursor, &totals, &cmds, &rows, &tileList, &big};
+		DeviceBuffer *all[] = {&dTasks, &dViews, &projected, &slotCounts, &blockCmds, &blockRows, &tileCount, &tileOffset, &tileCursor, &cmds, &rows, &tileList, &sortTmp};
 		for (auto *b : all) { b->release(); }
 		if (hostTotals) { cudaFreeHost(hostTotals); }
 	}
@@ -1034,88 +1296,57 @@ static int register_texture(dfpsr_renderer *r, const dfpsr_texture *t) {
 	return r->textureCount++;
 }
 
-static int renderer_begin_internal(dfpsr_renderer *r, const dfpsr_image *color, const dfpsr_image *depth, bool depthOnly, bool clear, uint32_t clearColor, float clearDepth, cudaStream_t stream) {
-	// ref: api/rendererAPI.cpp:151-168
-	DFPSR_REQUIRE(!r->receiving, "Called renderer_begin on the same renderer twice without ending the previous batch!");
-	r->color = image_exists(color) ? *color : dfpsr_image{};
-	r->depth = image_exists(depth) ? *depth : dfpsr_image{};
+// ref: api/rendererAPI.cpp:151-168 — one view
+static int make_view(ViewDev &v, const dfpsr_image *color, const dfpsr_image *depth, bool clear, uint32_t clearColor, float clearDepth) {
+	memset(&v, 0, sizeof(v));
+	if (image_exists(color)) { v.color = *color; }
+	if (image_exists(depth)) { v.depth = *depth; }
 	if (image_exists(color) && image_exists(depth)) {
 		DFPSR_REQUIRE(color->width == depth->width && color->height == depth->height, "renderer_begin: colour buffer %dx%d and depth buffer %dx%d differ", color->width, color->height, depth->width, depth->height);
 	}
-	if (image_exists(color)) { r->width = color->width; r->height = color->height; }
-	else if (image_exists(depth)) { r->width = depth->width; r->height = depth->height; }
-	else { r->width = 0; r->height = 0; }
+	if (image_exists(color)) { v.width = color->width; v.height = color->height; }
+	else if (image_exists(depth)) { v.width = depth->width; v.height = depth->height; }
+	DFPSR_REQUIRE(v.width >= 0 && v.height >= 0, "renderer_begin: negative image dimensions");
+	v.clipTop = 0; v.clipBottom = v.height;
+	v.clear = clear ? 1 : 0; v.clearColor = clearColor; v.clearDepth = clearDepth;
+	v.tilesX = (v.width + TILE_W - 1) / TILE_W;
+	v.tilesY = (v.height + TILE_H - 1) / TILE_H;
+	return 0;
+}
+
+static int renderer_begin_internal(dfpsr_renderer *r, bool depthOnly) {
+	DFPSR_REQUIRE(!r->receiving, "Called renderer_begin on the same renderer twice without ending the previous batch!");
 	r->receiving = true;
 	r->depthOnly = depthOnly;
-	r->clear = clear; r->clearColor = clearColor; r->clearDepth = clearDepth;
+	r->views.clear();
 	r->tasks.clear();
+	r->uploadCount = 0;
 	r->textureCount = 0;
-	r->slotTotal = 0; r->blockTotal = 0;
-	r->countsZeroed = false;
-	r->frame.tilesX = (r->width + TILE - 1) / TILE;
-	r->frame.tilesY = (r->height + TILE - 1) / TILE;
 	if (!r->hostTotals) { DFPSR_CHECK_CUDA(cudaMallocHost((void **)&r->hostTotals, 8 * sizeof(uint32_t))); }
-	(void)stream;
 	return 0;
 }
 
-static int ensure_tile_counts(dfpsr_renderer *r, cudaStream_t stream) {
-	if (r->countsZeroed) { return 0; }
-	int32_t tiles = r->frame.tilesX * r->frame.tilesY;
-	if (r->tileCount.reserve((size_t)(tiles + 1) * 4)) { return 1; }
-	if (r->tileOffset.reserve((size_t)(tiles + 1) * 4)) { return 1; }
-	if (r->tileCursor.reserve((size_t)(tiles + 1) * 4)) { return 1; }
-	if (r->totals.reserve(8 * 4)) { return 1; }
-	DFPSR_CHECK_CUDA(cudaMemsetAsync(r->tileCount.ptr, 0, (size_t)(tiles + 1) * 4, stream));
-	r->countsZeroed = true;
-	return 0;
-}
-
-// Appends a task: uploads nothing, launches projection + counting set-up.
-static int add_task(dfpsr_renderer *r, TaskParams &task, cudaStream_t stream) {
-	if (r->width <= 0 || r->height <= 0) { return 0; } // ref: renderCore.cpp:307-309 — no target, nothing to draw
-	if (ensure_tile_counts(r, stream)) { return 1; }
-	size_t index = r->tasks.size();
-	task.slotBase = r->slotTotal;
-	task.blockBase = r->blockTotal;
-	task.width = r->width; task.height = r->height;
+static int add_model_task(dfpsr_renderer *r, int32_t view, const dfpsr_model *model, const dfpsr_transform3d *modelToWorld, const dfpsr_camera *camera) {
+	const ViewDev &v = r->views[(size_t)view];
+	if (v.width <= 0 || v.height <= 0) { return 0; } // ref: renderCore.cpp:307-309 — no target, nothing to draw
+	// ref: api/modelAPI.cpp:228 — whole-model culling against the cull frustum on the host
+	if (!dfpsr_camera_is_box_seen(camera, model->minBound, model->maxBound, modelToWorld)) { return 0; }
+	if (model->polygonCount <= 0) { return 0; }
+	TaskParams task;
+	memset(&task, 0, sizeof(task));
+	task.points = model->points;
+	task.polygons = model->polygons;
+	task.pointCount = model->pointCount;
+	task.slotCount = model->polygonCount * 2;
+	task.view = view;
+	task.modelToWorld = *modelToWorld;
+	task.camera = *camera;
+	task.filter = model->filter;
 	task.depthOnly = r->depthOnly ? 1 : 0;
-	int32_t blocks = (task.slotCount + SETUP_THREADS - 1) / SETUP_THREADS;
-	if (blocks == 0) { return 0; }
-	if (task.triangles == nullptr) {
-		if (r->projected.size() <= index) { r->projected.resize(index + 1); }
-		if (r->projected[index].reserve((size_t)task.pointCount * sizeof(PPoint) + 16)) { return 1; }
-		task.projected = (PPoint *)r->projected[index].ptr;
-		int grid = (task.pointCount + 255) / 256;
-		if (grid > sm_count() * 8) { grid = sm_count() * 8; }
-		if (grid > 0) { DFPSR_LAUNCH(project_kernel, grid, 256, 0, stream, task.points, task.pointCount, task.modelToWorld, task.camera, task.projected); }
-	}
-	// per-slot and per-block counters grow with the frame; growing must not lose earlier tasks' counts
-	size_t slotsNeeded = (size_t)(r->slotTotal + task.slotCount) * 4, blocksNeeded = (size_t)(r->blockTotal + blocks) * 4;
-	if (slotsNeeded > r->slotCounts.capacity || blocksNeeded > r->blockCmds.capacity) {
-		// preserve contents when growing mid-frame
-		DeviceBuffer *bufs[3] = {&r->slotCounts, &r->blockCmds, &r->blockRows};
-		size_t needs[3] = {slotsNeeded, blocksNeeded, blocksNeeded};
-		for (int i = 0; i < 3; i++) {
-			if (needs[i] <= bufs[i]->capacity) { continue; }
-			DeviceBuffer fresh;
-			if (fresh.reserve(needs[i] * 2)) { return 1; }
-			if (bufs[i]->ptr && !r->tasks.empty()) { DFPSR_CHECK_CUDA(cudaMemcpyAsync(fresh.ptr, bufs[i]->ptr, bufs[i]->capacity, cudaMemcpyDeviceToDevice, stream)); DFPSR_CHECK_CUDA(cudaStreamSynchronize(stream)); }
-			bufs[i]->release();
-			*bufs[i] = fresh;
-		}
-	}
-	r->frame.slotCounts = (uint32_t *)r->slotCounts.ptr;
-	r->frame.blockCmds = (uint32_t *)r->blockCmds.ptr;
-	r->frame.blockRows = (uint32_t *)r->blockRows.ptr;
-	r->frame.tileCount = (uint32_t *)r->tileCount.ptr;
-	r->frame.tileOffset = (uint32_t *)r->tileOffset.ptr;
-	r->frame.tileCursor = (uint32_t *)r->tileCursor.ptr;
-	r->frame.totals = (uint32_t *)r->totals.ptr;
-	DFPSR_LAUNCH(setup_kernel<false>, blocks, SETUP_THREADS, 0, stream, task, r->frame);
-	r->slotTotal += task.slotCount;
-	r->blockTotal += blocks;
-	r->tasks.push_back(FrameTask{task});
+	task.diffuseIndex = r->depthOnly ? -1 : register_texture(r, &model->diffuse);
+	task.lightIndex = r->depthOnly ? -1 : register_texture(r, &model->light);
+	DFPSR_REQUIRE(task.diffuseIndex != -2 && task.lightIndex != -2, "more than %d distinct textures in one frame", MAX_TEXTURES);
+	r->tasks.push_back(task);
 	return 0;
 }
 
@@ -1124,68 +1355,90 @@ static int renderer_end_internal(dfpsr_renderer *r, cudaStream_t stream) {
 	DFPSR_REQUIRE(r->receiving, "Called renderer_end without renderer_begin!");
 	r->receiving = false;
 	r->lastCommands = 0;
-	if (r->width <= 0 || r->height <= 0) { return 0; }
-	int32_t tiles = r->frame.tilesX * r->frame.tilesY;
-	uint32_t maxTile = 0;
-	if (!r->tasks.empty()) {
-		r->frame.blockCount = r->blockTotal;
-		DFPSR_LAUNCH(scan_kernel, 1, 1024, 0, stream, r->frame);
-		DFPSR_CHECK_CUDA(cudaMemcpyAsync(r->hostTotals, r->totals.ptr, 5 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+	// ---- lay out the batch
+	uint32_t tileTotal = 0;
+	bool anyClear = false;
+	for (ViewDev &v : r->views) {
+		v.tileBase = tileTotal;
+		tileTotal += (uint32_t)(v.tilesX * v.tilesY);
+		anyClear = anyClear || (v.clear != 0 && v.width > 0 && v.height > 0);
+	}
+	if (tileTotal == 0 || (r->tasks.empty() && !anyClear)) { return 0; }
+	int32_t slotTotal = 0, blockTotal = 0;
+	size_t pointTotal = 0;
+	for (TaskParams &t : r->tasks) {
+		t.slotBase = slotTotal; t.blockBase = blockTotal;
+		t.blockCount = (t.slotCount + SETUP_THREADS - 1) / SETUP_THREADS;
+		slotTotal += t.slotCount; blockTotal += t.blockCount;
+		if (t.triangles == nullptr) { pointTotal += (size_t)t.pointCount; }
+	}
+	if (r->projected.reserve(pointTotal * sizeof(PPoint) + 16)) { return 1; }
+	{
+		size_t at = 0;
+		for (TaskParams &t : r->tasks) {
+			if (t.triangles == nullptr) { t.projected = (PPoint *)r->projected.ptr + at; at += (size_t)t.pointCount; }
+		}
+	}
+	const size_t taskCount = r->tasks.size(), viewCount = r->views.size();
+	if (r->dTasks.reserve(taskCount * sizeof(TaskParams) + 16) || r->dViews.reserve(viewCount * sizeof(ViewDev))) { return 1; }
+	if (r->tileCount.reserve(((size_t)tileTotal + 8) * 4) || r->tileOffset.reserve(((size_t)tileTotal + 1) * 4) || r->tileCursor.reserve(((size_t)tileTotal + 1) * 4)) { return 1; }
+	if (r->slotCounts.reserve((size_t)slotTotal * 4 + 16) || r->blockCmds.reserve((size_t)blockTotal * 4 + 16) || r->blockRows.reserve((size_t)blockTotal * 4 + 16)) { return 1; }
+	// pageable sources: cudaMemcpyAsync stages them before returning, so the vectors may change afterwards
+	if (taskCount > 0) { DFPSR_CHECK_CUDA(cudaMemcpyAsync(r->dTasks.ptr, r->tasks.data(), taskCount * sizeof(TaskParams), cudaMemcpyHostToDevice, stream)); }
+	DFPSR_CHECK_CUDA(cudaMemcpyAsync(r->dViews.ptr, r->views.data(), viewCount * sizeof(ViewDev), cudaMemcpyHostToDevice, stream));
+	DFPSR_CHECK_CUDA(cudaMemsetAsync(r->tileCount.ptr, 0, ((size_t)tileTotal + 8) * 4, stream)); // tile counts, cursors of empty frames, totals
+	if (taskCount == 0) { DFPSR_CHECK_CUDA(cudaMemsetAsync(r->tileCursor.ptr, 0, (size_t)tileTotal * 4, stream)); }
+
+	FrameDev frame;
+	memset(&frame, 0, sizeof(frame));
+	frame.tasks = (const TaskParams *)r->dTasks.ptr;
+	frame.views = (const ViewDev *)r->dViews.ptr;
+	frame.taskCount = (int32_t)taskCount; frame.viewCount = (int32_t)viewCount; frame.blockCount = blockTotal;
+	frame.tileTotal = tileTotal;
+	frame.slotCounts = (uint32_t *)r->slotCounts.ptr;
+	frame.blockCmds = (uint32_t *)r->blockCmds.ptr; frame.blockRows = (uint32_t *)r->blockRows.ptr;
+	frame.tileCount = (uint32_t *)r->tileCount.ptr; frame.tileOffset = (uint32_t *)r->tileOffset.ptr; frame.tileCursor = (uint32_t *)r->tileCursor.ptr;
+	frame.totals = frame.tileCount + tileTotal;
+
+	if (taskCount > 0) {
+		int32_t maxPoints = 0;
+		for (const TaskParams &t : r->tasks) { if (t.triangles == nullptr && t.pointCount > maxPoints) { maxPoints = t.pointCount; } }
+		if (maxPoints > 0) {
+			dim3 grid((unsigned)((maxPoints + 255) / 256), (unsigned)taskCount);
+			if (grid.x > 1024u) { grid.x = 1024u; }
+			DFPSR_REQUIRE(taskCount <= 65535, "more than 65535 tasks in one frame");
+			DFPSR_LAUNCH(project_kernel, grid, 256, 0, stream, frame.tasks);
+		}
+		DFPSR_LAUNCH(setup_kernel<false>, blockTotal, SETUP_THREADS, 0, stream, frame);
+		DFPSR_LAUNCH(scan_blocks_kernel, 1, 1024, 0, stream, frame);
+		DFPSR_LAUNCH(tile_alloc_kernel, (tileTotal + 255) / 256, 256, 0, stream, frame);
+		DFPSR_CHECK_CUDA(cudaMemcpyAsync(r->hostTotals, frame.totals, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
 		DFPSR_CHECK_CUDA(cudaStreamSynchronize(stream));
-		uint32_t commandTotal = r->hostTotals[0], rowTotal = r->hostTotals[1], entryTotal = r->hostTotals[2];
-		maxTile = r->hostTotals[3];
+		const uint32_t commandTotal = r->hostTotals[0], rowTotal = r->hostTotals[1], entryTotal = r->hostTotals[2], maxTile = r->hostTotals[3];
 		r->lastCommands = commandTotal;
 		if (commandTotal > 0) {
 			if (r->cmds.reserve((size_t)commandTotal * sizeof(Cmd))) { return 1; }
 			if (r->rows.reserve((size_t)rowTotal * sizeof(int2) + 16)) { return 1; }
 			if (r->tileList.reserve((size_t)entryTotal * 4 + 16)) { return 1; }
-			if (r->big.reserve((size_t)commandTotal * sizeof(BigCmd))) { return 1; }
-			r->frame.cmds = (Cmd *)r->cmds.ptr;
-			r->frame.rows = (int2 *)r->rows.ptr;
-			r->frame.tileList = (uint32_t *)r->tileList.ptr;
-			r->frame.big = (BigCmd *)r->big.ptr;
-			for (FrameTask &t : r->tasks) {
-				int32_t blocks = (t.params.slotCount + SETUP_THREADS - 1) / SETUP_THREADS;
-				DFPSR_LAUNCH(setup_kernel<true>, blocks, SETUP_THREADS, 0, stream, t.params, r->frame);
+			frame.cmds = (Cmd *)r->cmds.ptr;
+			frame.rows = (int2 *)r->rows.ptr;
+			frame.tileList = (uint32_t *)r->tileList.ptr;
+			DFPSR_LAUNCH(setup_kernel<true>, blockTotal, SETUP_THREADS, 0, stream, frame);
+			if (maxTile > 32u) {
+				uint32_t grid = (uint32_t)sm_count() * 8u;
+				if (grid > tileTotal) { grid = tileTotal; }
+				if (maxTile > (uint32_t)SORT_SMEM) {
+					if (r->sortTmp.reserve((size_t)grid * maxTile * 4)) { return 1; }
+					frame.sortTmp = (uint32_t *)r->sortTmp.ptr;
+					frame.sortTmpStride = maxTile;
+				}
+				DFPSR_LAUNCH(sort_lists_kernel, grid, SORT_THREADS, 0, stream, frame);
 			}
-			DFPSR_LAUNCH(big_rows_kernel, sm_count() * 4, 256, 0, stream, r->frame);
 		}
-	} else if (r->clear) {
-		if (ensure_tile_counts(r, stream)) { return 1; }
-		r->frame.tileCount = (uint32_t *)r->tileCount.ptr;
-		r->frame.tileOffset = (uint32_t *)r->tileOffset.ptr;
 	}
-	if (r->tasks.empty() && !r->clear) { return 0; }
-	RasterParams rp;
-	rp.color = r->color; rp.depth = r->depth;
-	rp.width = r->width; rp.height = r->height;
-	rp.depthOnly = r->depthOnly ? 1 : 0;
-	rp.clear = r->clear ? 1 : 0;
-	rp.clearColor = r->clearColor; rp.clearDepth = r->clearDepth;
-	uint32_t capacity = 64;
-	while (capacity < maxTile && capacity < 16384u) { capacity <<= 1; }
-	rp.sortCapacity = capacity;
-	size_t smem = sizeof(Cmd) * CHUNK + sizeof(int2) * CHUNK * TILE + (size_t)capacity * 4;
-	if (smem > 48 * 1024) {
-		DFPSR_CHECK_CUDA(cudaFuncSetAttribute(raster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	}
-	DFPSR_LAUNCH(raster_kernel, tiles, 256, smem, stream, r->frame, rp, r->textures);
-	return 0;
-}
-
-static int fill_model_task(dfpsr_renderer *r, TaskParams &task, const dfpsr_model *model, const dfpsr_transform3d *modelToWorld, const dfpsr_camera *camera) {
-	memset(&task, 0, sizeof(task));
-	task.points = model->points;
-	task.polygons = model->polygons;
-	task.pointCount = model->pointCount;
-	task.polygonCount = model->polygonCount;
-	task.slotCount = model->polygonCount * 2;
-	task.modelToWorld = *modelToWorld;
-	task.camera = *camera;
-	task.filter = model->filter;
-	task.diffuseIndex = r->depthOnly ? -1 : register_texture(r, &model->diffuse);
-	task.lightIndex = r->depthOnly ? -1 : register_texture(r, &model->light);
-	DFPSR_REQUIRE(task.diffuseIndex != -2 && task.lightIndex != -2, "more than %d distinct textures in one frame", MAX_TEXTURES);
+	const uint32_t grid = (tileTotal + RASTER_WARPS - 1) / RASTER_WARPS;
+	if (r->depthOnly) { DFPSR_LAUNCH(raster_kernel<true>, grid, RASTER_WARPS * 32, 0, stream, frame, r->textures); }
+	else { DFPSR_LAUNCH(raster_kernel<false>, grid, RASTER_WARPS * 32, 0, stream, frame, r->textures); }
 	return 0;
 }
 
@@ -1205,25 +1458,38 @@ int dfpsr_renderer_destroy(dfpsr_renderer *renderer) {
 	return 0;
 }
 
+static int begin_one_view(dfpsr_renderer *r, const dfpsr_image *color, const dfpsr_image *depth, bool depthOnly, bool clear, uint32_t clearColor, float clearDepth) {
+	ViewDev v;
+	if (make_view(v, color, depth, clear, clearColor, clearDepth)) { return 1; }
+	if (renderer_begin_internal(r, depthOnly)) { return 1; }
+	r->views.push_back(v);
+	return 0;
+}
+
 int dfpsr_renderer_begin(dfpsr_renderer *renderer, const dfpsr_image *color, const dfpsr_image *depth) {
 	DFPSR_REQUIRE(renderer != nullptr, "renderer_begin: renderer does not exist");
-	return renderer_begin_internal(renderer, color, depth, false, false, 0u, 0.0f, nullptr);
+	return begin_one_view(renderer, color, depth, false, false, 0u, 0.0f);
 }
 
 int dfpsr_renderer_begin_cleared(dfpsr_renderer *renderer, const dfpsr_image *color, const dfpsr_image *depth, uint32_t packedClearColor, float clearDepth) {
 	DFPSR_REQUIRE(renderer != nullptr, "renderer_begin: renderer does not exist");
-	return renderer_begin_internal(renderer, color, depth, false, true, packedClearColor, clearDepth, nullptr);
+	return begin_one_view(renderer, color, depth, false, true, packedClearColor, clearDepth);
+}
+
+int dfpsr_renderer_set_clip_rows(dfpsr_renderer *renderer, int32_t top, int32_t bottom) {
+	DFPSR_REQUIRE(renderer != nullptr && renderer->receiving && renderer->views.size() == 1, "renderer_set_clip_rows: call between renderer_begin and renderer_end");
+	ViewDev &v = renderer->views[0];
+	DFPSR_REQUIRE(top >= 0 && top <= bottom && bottom <= v.height, "renderer_set_clip_rows: rows [%d, %d) outside the %d-row target", top, bottom, v.height);
+	DFPSR_REQUIRE(top % TILE_H == 0 && (bottom % TILE_H == 0 || bottom == v.height), "renderer_set_clip_rows: strip boundaries must be multiples of %d rows", TILE_H);
+	v.clipTop = top; v.clipBottom = bottom;
+	return 0;
 }
 
 int dfpsr_renderer_give_task(dfpsr_renderer *renderer, const dfpsr_model *model, const dfpsr_transform3d *modelToWorld, const dfpsr_camera *camera, void *stream) {
 	DFPSR_REQUIRE(renderer != nullptr && model != nullptr && modelToWorld != nullptr && camera != nullptr, "renderer_giveTask: null argument");
 	DFPSR_REQUIRE(renderer->receiving, "Cannot call renderer_giveTask before renderer_begin!");
-	// ref: api/modelAPI.cpp:228 — whole-model culling against the cull frustum on the host
-	if (!dfpsr_camera_is_box_seen(camera, model->minBound, model->maxBound, modelToWorld)) { return 0; }
-	if (model->polygonCount <= 0) { return 0; }
-	TaskParams task;
-	if (fill_model_task(renderer, task, model, modelToWorld, camera)) { return 1; }
-	return add_task(renderer, task, as_stream(stream));
+	(void)stream;
+	return add_model_task(renderer, 0, model, modelToWorld, camera);
 }
 
 int dfpsr_renderer_give_task_triangles(dfpsr_renderer *renderer, const dfpsr_triangle *triangles, int32_t count, const dfpsr_texture *diffuse, const dfpsr_texture *light, int32_t filter, const dfpsr_camera *camera, void *stream) {
@@ -1231,21 +1497,26 @@ int dfpsr_renderer_give_task_triangles(dfpsr_renderer *renderer, const dfpsr_tri
 	DFPSR_REQUIRE(renderer->receiving, "Cannot call renderer_giveTask_triangle before renderer_begin!");
 	if (count <= 0) { return 0; }
 	DFPSR_REQUIRE(triangles != nullptr, "renderer_giveTask_triangle: null triangles");
-	size_t index = renderer->tasks.size();
+	const ViewDev &v = renderer->views[0];
+	if (v.width <= 0 || v.height <= 0) { return 0; }
+	// vertex data is copied at submission (ref: api/rendererAPI.h:103-107)
+	size_t index = renderer->uploadCount++;
 	if (renderer->uploads.size() <= index) { renderer->uploads.resize(index + 1); }
 	if (renderer->uploads[index].reserve((size_t)count * sizeof(dfpsr_triangle))) { return 1; }
 	DFPSR_CHECK_CUDA(cudaMemcpyAsync(renderer->uploads[index].ptr, triangles, (size_t)count * sizeof(dfpsr_triangle), cudaMemcpyHostToDevice, as_stream(stream)));
 	TaskParams task;
 	memset(&task, 0, sizeof(task));
 	task.triangles = (const dfpsr_triangle *)renderer->uploads[index].ptr;
-	task.triangleCount = count;
 	task.slotCount = count;
+	task.view = 0;
 	task.camera = *camera;
 	task.filter = filter;
+	task.depthOnly = renderer->depthOnly ? 1 : 0;
 	task.diffuseIndex = register_texture(renderer, diffuse);
 	task.lightIndex = register_texture(renderer, light);
 	DFPSR_REQUIRE(task.diffuseIndex != -2 && task.lightIndex != -2, "more than %d distinct textures in one frame", MAX_TEXTURES);
-	return add_task(renderer, task, as_stream(stream));
+	renderer->tasks.push_back(task);
+	return 0;
 }
 
 int dfpsr_renderer_end(dfpsr_renderer *renderer, void *stream) {
@@ -1273,36 +1544,58 @@ static int immediate_renderer(dfpsr_renderer **out) {
 
 int dfpsr_model_render(const dfpsr_model *model, const dfpsr_transform3d *modelToWorld, const dfpsr_image *color, const dfpsr_image *depth, const dfpsr_camera *camera, void *stream) {
 	if (model == nullptr) { return 0; } // ref: api/modelAPI.cpp:198
+	DFPSR_REQUIRE(modelToWorld != nullptr && camera != nullptr, "model_render: null argument");
 	dfpsr_renderer *r;
 	if (immediate_renderer(&r)) { return 1; }
-	if (renderer_begin_internal(r, color, depth, false, false, 0u, 0.0f, as_stream(stream))) { return 1; }
-	int status = dfpsr_renderer_give_task(r, model, modelToWorld, camera, stream);
+	if (begin_one_view(r, color, depth, false, false, 0u, 0.0f)) { return 1; }
+	int status = add_model_task(r, 0, model, modelToWorld, camera);
 	if (status) { r->receiving = false; return status; }
 	return renderer_end_internal(r, as_stream(stream));
 }
 
 int dfpsr_model_render_depth(const dfpsr_model *model, const dfpsr_transform3d *modelToWorld, const dfpsr_image *depth, const dfpsr_camera *camera, void *stream) {
 	if (model == nullptr || !image_exists(depth)) { return 0; } // ref: api/modelAPI.cpp:203, renderCore.cpp:409
+	DFPSR_REQUIRE(modelToWorld != nullptr && camera != nullptr, "model_renderDepth: null argument");
 	dfpsr_renderer *r;
 	if (immediate_renderer(&r)) { return 1; }
-	if (renderer_begin_internal(r, nullptr, depth, true, false, 0u, 0.0f, as_stream(stream))) { return 1; }
-	int status = dfpsr_renderer_give_task(r, model, modelToWorld, camera, stream);
+	if (begin_one_view(r, nullptr, depth, true, false, 0u, 0.0f)) { return 1; }
+	int status = add_model_task(r, 0, model, modelToWorld, camera);
 	if (status) { r->receiving = false; return status; }
 	return renderer_end_internal(r, as_stream(stream));
 }
 
-int dfpsr_model_render_views(const dfpsr_model *model, const dfpsr_transform3d *modelToWorld, const dfpsr_image *colors, const dfpsr_image *depths, const dfpsr_camera *cameras, int32_t count, int32_t clear, void *stream) {
-	DFPSR_REQUIRE(model != nullptr && modelToWorld != nullptr && cameras != nullptr, "model_render_views: null argument");
+// Shared by dfpsr_model_render_views and dfpsr_model_render_depth_views: every (model, transform, camera, target) tuple becomes one task
+// with its own view; the whole batch goes through ONE sequence of launches.
+static int render_batch(const dfpsr_model *const *models, const dfpsr_transform3d *transforms, const dfpsr_image *colors, const dfpsr_image *depths, const dfpsr_camera *cameras, const int32_t *targetOfTask, int32_t taskCount, int32_t viewCount, bool depthOnly, bool clear, uint32_t clearColor, float clearDepth, cudaStream_t stream) {
 	dfpsr_renderer *r;
 	if (immediate_renderer(&r)) { return 1; }
-	for (int32_t i = 0; i < count; i++) {
-		const dfpsr_image *color = colors ? colors + i : nullptr, *depth = depths ? depths + i : nullptr;
-		if (renderer_begin_internal(r, color, depth, false, clear != 0, 0u, 0.0f, as_stream(stream))) { return 1; }
-		int status = dfpsr_renderer_give_task(r, model, modelToWorld, cameras + i, stream);
-		if (status) { r->receiving = false; return status; }
-		if (renderer_end_internal(r, as_stream(stream))) { return 1; }
+	if (renderer_begin_internal(r, depthOnly)) { return 1; }
+	for (int32_t v = 0; v < viewCount; v++) {
+		ViewDev view;
+		if (make_view(view, (colors && !depthOnly) ? colors + v : nullptr, depths ? depths + v : nullptr, clear, clearColor, clearDepth)) { r->receiving = false; return 1; }
+		r->views.push_back(view);
 	}
-	return 0;
+	for (int32_t t = 0; t < taskCount; t++) {
+		int32_t v = targetOfTask ? targetOfTask[t] : t;
+		if (v < 0 || v >= viewCount) { r->receiving = false; set_error("render batch: task %d names target %d of %d", t, v, viewCount); return 1; }
+		if (models[t] == nullptr) { continue; }
+		if (add_model_task(r, v, models[t], transforms + t, cameras + t)) { r->receiving = false; return 1; }
+	}
+	return renderer_end_internal(r, stream);
+}
+
+int dfpsr_model_render_views(const dfpsr_model *model, const dfpsr_transform3d *modelToWorld, const dfpsr_image *colors, const dfpsr_image *depths, const dfpsr_camera *cameras, int32_t count, int32_t clear, void *stream) {
+	DFPSR_REQUIRE(model != nullptr && modelToWorld != nullptr && cameras != nullptr, "model_render_views: null argument");
+	if (count <= 0) { return 0; }
+	std::vector<const dfpsr_model *> models((size_t)count, model);
+	std::vector<dfpsr_transform3d> transforms((size_t)count, *modelToWorld);
+	return render_batch(models.data(), transforms.data(), colors, depths, cameras, nullptr, count, count, false, clear != 0, 0u, 0.0f, as_stream(stream));
+}
+
+int dfpsr_model_render_depth_batch(const dfpsr_model *const *models, const dfpsr_transform3d *modelToWorld, const dfpsr_camera *cameras, const int32_t *targetOfTask, int32_t taskCount, const dfpsr_image *depths, int32_t targetCount, int32_t clear, float clearDepth, void *stream) {
+	DFPSR_REQUIRE(models != nullptr && modelToWorld != nullptr && cameras != nullptr && depths != nullptr, "model_render_depth_batch: null argument");
+	if (targetCount <= 0) { return 0; }
+	return render_batch(models, modelToWorld, nullptr, depths, cameras, targetOfTask, taskCount, targetCount, true, clear != 0, 0u, clearDepth, as_stream(stream));
 }
 
 int dfpsr_project_points(const float *points, int32_t count, const dfpsr_transform3d *modelToWorld, const dfpsr_camera *camera, dfpsr_projected_point *outDevice, void *stream) {
@@ -1310,7 +1603,7 @@ int dfpsr_project_points(const float *points, int32_t count, const dfpsr_transfo
 	if (count <= 0) { return 0; }
 	int grid = (count + 255) / 256;
 	if (grid > sm_count() * 8) { grid = sm_count() * 8; }
-	DFPSR_LAUNCH(project_kernel, grid, 256, 0, as_stream(stream), points, count, *modelToWorld, *camera, (PPoint *)outDevice);
+	DFPSR_LAUNCH(project_points_kernel, grid, 256, 0, as_stream(stream), points, count, *modelToWorld, *camera, (PPoint *)outDevice);
 	return 0;
 }
 

@@ -45,6 +45,8 @@ SIGNATURES = {
     "dfpsr_renderer_destroy": (i32, [vp]),
     "dfpsr_renderer_begin": (i32, [vp, P(abi.Image), P(abi.Image)]),
     "dfpsr_renderer_begin_cleared": (i32, [vp, P(abi.Image), P(abi.Image), u32, f32]),
+    "dfpsr_renderer_set_clip_rows": (i32, [vp, i32, i32]),
+    "dfpsr_model_render_depth_batch": (i32, [vp, vp, vp, vp, i32, vp, i32, i32, f32, vp]),
     "dfpsr_renderer_give_task": (i32, [vp, P(abi.Model), P(abi.Transform3D), P(abi.Camera), vp]),
     "dfpsr_renderer_give_task_triangles": (i32, [vp, vp, i32, P(abi.Texture), P(abi.Texture), i32, P(abi.Camera), vp]),
     "dfpsr_renderer_end": (i32, [vp, vp]),

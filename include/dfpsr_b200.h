@@ -195,6 +195,10 @@ int dfpsr_renderer_begin(dfpsr_renderer *renderer, const dfpsr_image *color, con
 /* image_fill(color, packedClearColor) + image_fill(depth, clearDepth) + renderer_begin fused (ref: SDK/terrain/main.cpp:397-416):
  * the tile kernel starts every tile from the clear values instead of loading it, so the two clears cost no memory pass. */
 int dfpsr_renderer_begin_cleared(dfpsr_renderer *renderer, const dfpsr_image *color, const dfpsr_image *depth, uint32_t packedClearColor, float clearDepth);
+/* Strip mode for multi-GPU frames: only target rows [top, bottom) are drawn by this renderer, exactly like one worker's clipBound in
+ * CommandQueue::execute (ref: implementation/render/renderCore.cpp:459-478). Call between begin and end. top and bottom must be multiples
+ * of 4 (the tile height; bottom may also be the image height). Pixels do not depend on the split. */
+int dfpsr_renderer_set_clip_rows(dfpsr_renderer *renderer, int32_t top, int32_t bottom);
 /* ref: api/modelAPI.cpp:214-281 model_render_threaded / renderer_giveTask. Bound culling
  * (Camera::isBoxSeen) is applied on the host exactly like the reference. Enqueues the projection and
  * triangle set-up kernels on `stream`; nothing is drawn before dfpsr_renderer_end. */
@@ -216,6 +220,11 @@ int dfpsr_model_render_depth(const dfpsr_model *model, const dfpsr_transform3d *
  * `clear` is non-zero every target is first cleared to colour 0 / depth 0.0f as the SDK terrain loop does
  * (ref: SDK/terrain/main.cpp:397-402). Arrays are HOST arrays of descriptors. */
 int dfpsr_model_render_views(const dfpsr_model *model, const dfpsr_transform3d *modelToWorld, const dfpsr_image *colors, const dfpsr_image *depths, const dfpsr_camera *cameras, int32_t count, int32_t clear, void *stream);
+/* Many model_renderDepth calls in one submission (the Sandbox shadow pass: 6 cube faces x shadow casters x lights, ref:
+ * SDK/SpriteEngine/spriteAPI.cpp:389-401, :793-804): task i renders models[i] with modelToWorld[i] and cameras[i] into depths[targetOfTask[i]],
+ * tasks that share a target are applied in array order. When `clear` is non-zero every target is first filled with clearDepth
+ * (CubeMapF32::clear, spriteAPI.cpp:360-362) inside the same kernels. All arrays are HOST arrays. */
+int dfpsr_model_render_depth_batch(const dfpsr_model *const *models, const dfpsr_transform3d *modelToWorld, const dfpsr_camera *cameras, const int32_t *targetOfTask, int32_t taskCount, const dfpsr_image *depths, int32_t targetCount, int32_t clear, float clearDepth, void *stream);
 /* ref: api/modelAPI.cpp:238-242 — the projection loop alone (exposed for parity tests): out[i] = worldToScreen(M * p[i]). */
 int dfpsr_project_points(const float *points, int32_t count, const dfpsr_transform3d *modelToWorld, const dfpsr_camera *camera, dfpsr_projected_point *outDevice, void *stream);
 

@@ -558,10 +558,13 @@ static float *depth_px(const dfpsr_image *im, int32_t x, int32_t y) { return (fl
 
 /* shader/fillerTemplates.h:139-187 fillQuadSuper + :190-244 fillRowSuper body for ONE quad.
  * upper/lower: the running (depth, B, C) plane values for lane 0 and lane 2; lanes 1 and 3 are +dx. */
-static void fill_quad(const fill_mode *m, const shader_data *s, int clipSides, int32_t x, int32_t y1, const float *lanes /* [3][4] */, row_interval upperRow, row_interval lowerRow) {
+static void fill_quad(const fill_mode *m, const shader_data *s, int clipSides, int32_t x, int32_t y1, const float *lanes /* [3][4] */, row_interval upperRow, row_interval lowerRow, int hasTop, int hasBottom) {
 	int32_t y2 = y1 + 1;
 	int32_t px[4] = {x, x + 1, x, x + 1};
-	int32_t py[4] = {y1, y1, y2, y2};
+	/* fillerTemplates.h:302-331: a row pair with an empty row points both row pointers at the non-empty row ("repeat the
+	 * lower/upper row to avoid reading outside"). Only the unclipped inner quads of the last row pair of an odd-height
+	 * target ever touch the repeated row: there lanes 2 and 3 read and overwrite the pixels of lanes 0 and 1. */
+	int32_t py[4] = {hasTop ? y1 : y2, hasTop ? y1 : y2, hasBottom ? y2 : y1, hasBottom ? y2 : y1};
 	float depth[4], wa[4], wb[4], wc[4];
 	for (int l = 0; l < 4; l++) {
 		depth[l] = lanes[0 * 4 + l];
@@ -598,11 +601,15 @@ static void fill_quad(const fill_mode *m, const shader_data *s, int clipSides, i
 		float colors[4][4];
 		shade_quad(s, wa, wb, wc, colors);
 		int order = m->color->packOrder;
+		uint32_t targets[4] = {0u, 0u, 0u, 0u};
+		if (m->alphaFilter) {
+			/* clippedRead: all four reads happen before any write; lanes that are not visible read 0 when clipping sides */
+			for (int l = 0; l < 4; l++) { targets[l] = (vis[l] || !clipSides) ? *color_px(m->color, px[l], py[l]) : 0u; }
+		}
 		for (int l = 0; l < 4; l++) {
 			if (m->alphaFilter) {
 				float opacity = colors[l][3] * (1.0f / 255.0f);
-				/* clippedRead: lanes that are not visible read 0 when clipping sides; inner quads read all four */
-				uint32_t target = (vis[l] || !clipSides) ? *color_px(m->color, px[l], py[l]) : 0u;
+				uint32_t target = targets[l];
 				float dst[4];
 				unpack_ordered(target, order, dst);
 				float inv = 1.0f - opacity;
@@ -639,26 +646,26 @@ static void fill_shape(const fill_mode *m, const shader_data *s, const projectio
 		if (innerBlockEnd <= innerBlockStart) {
 			for (int32_t x = outerBlockStart; x < outerBlockEnd; x += 2) {
 				for (int k = 0; k < 3; k++) { lanes[k * 4 + 0] = upper[k]; lanes[k * 4 + 1] = upper[k] + proj->dx[k]; lanes[k * 4 + 2] = lower[k]; lanes[k * 4 + 3] = lower[k] + proj->dx[k]; }
-				fill_quad(m, s, 1, x, y1, lanes, upperRow, lowerRow);
+				fill_quad(m, s, 1, x, y1, lanes, upperRow, lowerRow, hasTop, hasBottom);
 				for (int k = 0; k < 3; k++) { upper[k] = upper[k] + dx2[k]; lower[k] = lower[k] + dx2[k]; }
 			}
 		} else {
 			for (int32_t x = outerBlockStart; x < innerBlockStart; x += 2) {
 				for (int k = 0; k < 3; k++) { lanes[k * 4 + 0] = upper[k]; lanes[k * 4 + 1] = upper[k] + proj->dx[k]; lanes[k * 4 + 2] = lower[k]; lanes[k * 4 + 3] = lower[k] + proj->dx[k]; }
-				fill_quad(m, s, 1, x, y1, lanes, upperRow, lowerRow);
+				fill_quad(m, s, 1, x, y1, lanes, upperRow, lowerRow, hasTop, hasBottom);
 				for (int k = 0; k < 3; k++) { upper[k] = upper[k] + dx2[k]; lower[k] = lower[k] + dx2[k]; }
 			}
 			/* full quads: the four lanes advance independently by repeated addition (fillRowSuper) */
 			int32_t quadCount = (innerBlockEnd - innerBlockStart) / 2;
 			for (int k = 0; k < 3; k++) { lanes[k * 4 + 0] = upper[k]; lanes[k * 4 + 1] = upper[k] + proj->dx[k]; lanes[k * 4 + 2] = lower[k]; lanes[k * 4 + 3] = lower[k] + proj->dx[k]; }
 			for (int32_t x = innerBlockStart; x < innerBlockEnd; x += 2) {
-				fill_quad(m, s, 0, x, y1, lanes, upperRow, lowerRow);
+				fill_quad(m, s, 0, x, y1, lanes, upperRow, lowerRow, hasTop, hasBottom);
 				for (int k = 0; k < 3; k++) { for (int l = 0; l < 4; l++) { lanes[k * 4 + l] = lanes[k * 4 + l] + dx2[k]; } }
 			}
 			for (int k = 0; k < 3; k++) { upper[k] = upper[k] + (dx2[k] * (float)quadCount); lower[k] = lower[k] + (dx2[k] * (float)quadCount); }
 			for (int32_t x = innerBlockEnd; x < outerBlockEnd; x += 2) {
 				for (int k = 0; k < 3; k++) { lanes[k * 4 + 0] = upper[k]; lanes[k * 4 + 1] = upper[k] + proj->dx[k]; lanes[k * 4 + 2] = lower[k]; lanes[k * 4 + 3] = lower[k] + proj->dx[k]; }
-				fill_quad(m, s, 1, x, y1, lanes, upperRow, lowerRow);
+				fill_quad(m, s, 1, x, y1, lanes, upperRow, lowerRow, hasTop, hasBottom);
 				for (int k = 0; k < 3; k++) { upper[k] = upper[k] + dx2[k]; lower[k] = lower[k] + dx2[k]; }
 			}
 		}

@@ -222,6 +222,40 @@ class CudaSandbox:
         lib.check(cuda.dfpsr_light_blend(C.byref(IM(self.C)), C.byref(IM(self.D)), C.byref(IM(self.L)), s))
         return cubes
 
+    def prepare_batched(self):
+        """Host arrays for dfpsr_model_render_depth_batch: every (light, caster, face) is one task, every (light, face) one target."""
+        import torch
+        lib, sb = self.lib, self.sb
+        res, nl, nc = sb["cube_res"], len(sb["lights"]), len(sb["casters"])
+        self.cubes = torch.zeros((nl, res * 6, res), dtype=torch.float32, device="cuda")
+        targets = (abi.Image * (nl * 6))(*[lib.image(self.cubes[i][f * res:(f + 1) * res]) for i in range(nl) for f in range(6)])
+        n = nl * nc * 6
+        models, transforms, cams, target_of = (C.c_void_p * n)(), (abi.Transform3D * n)(), (abi.Camera * n)(), (C.c_int32 * n)()
+        k = 0
+        for i, light in enumerate(sb["lights"]):
+            for c, model in zip(sb["casters"], self.models):
+                t = caster_transform(c, light)
+                for f in range(6):
+                    models[k], transforms[k], cams[k], target_of[k] = C.addressof(model.desc), t, self.cams[f], i * 6 + f
+                    k += 1
+        self.batch = (models, transforms, cams, target_of, n, targets, nl * 6)
+
+    def light_batched(self):
+        """The same passes with all shadow maps of the frame rendered by ONE submission (B200-first order: the reference reuses a single
+        cube map and therefore interleaves shadow rendering with the light passes, ref: SDK/SpriteEngine/spriteAPI.cpp:789-810)."""
+        cuda, lib, sb = self.cuda, self.lib, self.sb
+        if not hasattr(self, "batch"):
+            self.prepare_batched()
+        s = lib.stream_ptr()
+        d = sb["directed"]
+        IM = lib.image
+        lib.check(cuda.dfpsr_light_directed(C.byref(self.view), C.byref(IM(self.L)), C.byref(IM(self.N)), d["direction"].ctypes.data, d["intensity"], d["color"].ctypes.data, 0, s))
+        models, transforms, cams, target_of, n, targets, nt = self.batch
+        lib.check(cuda.dfpsr_model_render_depth_batch(models, transforms, cams, target_of, n, targets, nt, 1, 0.0, s))
+        for i, light in enumerate(sb["lights"]):
+            lib.check(cuda.dfpsr_light_point(C.byref(self.view), sb["worldCenter"].ctypes.data, C.byref(IM(self.L)), C.byref(IM(self.N)), C.byref(IM(self.H)), light["position"].ctypes.data, light["radius"], light["intensity"], light["color"].ctypes.data, C.byref(IM(self.cubes[i])), s))
+        lib.check(cuda.dfpsr_light_blend(C.byref(IM(self.C)), C.byref(IM(self.D)), C.byref(IM(self.L)), s))
+
     def results(self):
         u = lambda t: t.cpu().numpy().view(np.uint32)
         return {"height": self.H.cpu().numpy(), "diffuse": u(self.D), "normal": u(self.N), "light": u(self.L), "color": u(self.C)}

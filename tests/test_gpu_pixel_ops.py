@@ -190,6 +190,20 @@ def test_sandbox_frame_matches_oracle(cuda, oracle, batched):
         assert_same_u32(got[key], expected[key], key)
 
 
+def test_sandbox_frame_batched_shadows(cuda, oracle):
+    """All cube maps of the frame in one dfpsr_model_render_depth_batch submission: same light buffer, same colours."""
+    sb = sandbox_scene.build(320, 240, lights=4, seed=8, sprites=25, casters=3)
+    expected = sandbox_scene.run_oracle(oracle, sb)
+    gpu = sandbox_scene.CudaSandbox(cuda, sb)
+    gpu.composite()
+    gpu.light_batched()
+    got = gpu.results()
+    for i, b in enumerate(expected["cubes"]):
+        assert_same_u32(bits(host_f32(gpu.cubes[i])), bits(b), f"cube map of light {i}")
+    for key in ("light", "color"):
+        assert_same_u32(got[key], expected[key], key)
+
+
 def test_sandbox_800x600_golden(cuda):
     """BASELINE config 2 at full size against hashes produced by the compiled reference."""
     golden = json.load(open(os.path.join(GOLDEN_DIR, "sandbox.json")))["sandbox_800x600_16"]
@@ -199,6 +213,12 @@ def test_sandbox_800x600_golden(cuda):
     cubes = gpu.light(keep_cubes=True)
     got = gpu.results()
     assert sha(cubes[0]) == golden["cube0_sha256"]
+    assert sha(got["light"]) == golden["light_sha256"]
+    assert sha(got["color"]) == golden["color_sha256"]
+    gpu.L.zero_()
+    gpu.light_batched()
+    got = gpu.results()
+    assert sha(host_f32(gpu.cubes[0])) == golden["cube0_sha256"]
     assert sha(got["light"]) == golden["light_sha256"]
     assert sha(got["color"]) == golden["color_sha256"]
 

@@ -235,3 +235,117 @@ def test_tiny_triangles_4k_golden(cuda):
     c, d = scene.render_cuda(cuda, cam, np.zeros((2160, 3840), np.uint32), np.zeros((2160, 3840), np.float32))
     assert sha(d) == golden["depth_sha256"]
     assert sha(c) == golden["color_sha256"]
+
+
+@pytest.mark.parametrize("size", [(33, 35), (321, 181), (320, 181), (77, 3), (5, 1), (1, 1), (130, 66)])
+@pytest.mark.parametrize("case", [0, 1, 7, 8, 12])
+def test_odd_target_sizes(cuda, oracle, case, size):
+    """Odd widths (rows that are only 4-byte aligned) and odd heights (the reference's repeated-upper-row quirk in the last row pair,
+    ref: shader/fillerTemplates.h:286-331), targets smaller than one tile."""
+    cfg = CASES[case]
+    scene, cam, color, depth = soup_case(500 + case, w=size[0], h=size[1], **cfg)
+    got_c, got_d = scene.render_cuda(cuda, cam, color, depth, cfg["pack"])
+    exp_c, exp_d, _ = scene.render_oracle(oracle, cam, color, depth, cfg["pack"])
+    if depth is not None:
+        assert_same_u32(bits(got_d), bits(exp_d), "depth")
+    if color is not None:
+        assert_same_u32(got_c, exp_c, "colour")
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_strip_mode_equals_full_frame(cuda, oracle, world):
+    """Screen strips: every 'rank' draws only its rows; the union equals the full frame bit for bit."""
+    from dfpsr_b200 import shard
+    sc = scenes.terrain_scene()
+    scene = CudaScene(sc["points"], sc["polygons"], diffuse_level0=sc["texture"], diffuse_levels=5)
+    w, h = 480, 270
+    cam_params = scenes.orbit_camera(9, w, h)
+    cam = lib.camera(cam_params)
+    exp_c, exp_d, _ = scene.render_oracle(oracle, cam_params, np.zeros((h, w), np.uint32), np.zeros((h, w), np.float32))
+    tc, td = dev(np.full((h, w), 0xDEADBEEF, np.uint32)), dev(np.full((h, w), -1.0, np.float32))
+    ident = abi.Transform3D.identity()
+    r = C.c_void_p()
+    lib.check(cuda.dfpsr_renderer_create(C.byref(r)))
+    bounds = shard.strip_rows(h, world, align=4)
+    for y0, y1 in bounds:
+        lib.check(cuda.dfpsr_renderer_begin_cleared(r, C.byref(lib.image(tc)), C.byref(lib.image(td)), 0, 0.0))
+        lib.check(cuda.dfpsr_renderer_set_clip_rows(r, y0, y1))
+        lib.check(cuda.dfpsr_renderer_give_task(r, C.byref(scene.model.desc), C.byref(ident), C.byref(cam), lib.stream_ptr()))
+        lib.check(cuda.dfpsr_renderer_end(r, lib.stream_ptr()))
+        got_c, got_d = host_u32(tc), host_f32(td)
+        assert_same_u32(got_c[y0:y1], exp_c[y0:y1], f"colour rows {y0}:{y1}")
+        assert_same_u32(bits(got_d[y0:y1]), bits(exp_d[y0:y1]), f"depth rows {y0}:{y1}")
+        if y1 < h:
+            assert np.all(got_c[y1:] == 0xDEADBEEF), "rows below the strip were touched"
+    assert cuda.dfpsr_renderer_begin(r, C.byref(lib.image(tc)), C.byref(lib.image(td))) == 0
+    assert cuda.dfpsr_renderer_set_clip_rows(r, 2, 10) != 0  # not a multiple of the tile height
+    lib.check(cuda.dfpsr_renderer_end(r, lib.stream_ptr()))
+    lib.check(cuda.dfpsr_renderer_destroy(r))
+    assert_same_u32(host_u32(tc), exp_c, "colour")
+    assert_same_u32(bits(host_f32(td)), bits(exp_d), "depth")
+
+
+def test_render_views_batch_equals_single_renders(cuda, oracle):
+    """dfpsr_model_render_views: one submission for many views == one dfpsr_model_render per view (BASELINE config 4)."""
+    import torch
+    sc = scenes.terrain_scene()
+    scene = CudaScene(sc["points"], sc["polygons"], diffuse_level0=sc["texture"], diffuse_levels=5)
+    w, h, views = 200, 114, 7
+    cams = (abi.Camera * views)(*[lib.camera(scenes.orbit_camera(3 * v, w, h)) for v in range(views)])
+    color = torch.full((views, h, w), 7, dtype=torch.int32, device="cuda")
+    depth = torch.full((views, h, w), 3.0, dtype=torch.float32, device="cuda")
+    colors = (abi.Image * views)(*[lib.image(color[v]) for v in range(views)])
+    depths = (abi.Image * views)(*[lib.image(depth[v]) for v in range(views)])
+    ident = abi.Transform3D.identity()
+    lib.check(cuda.dfpsr_model_render_views(C.byref(scene.model.desc), C.byref(ident), colors, depths, cams, views, 1, lib.stream_ptr()))
+    for v in range(views):
+        ec, ed, _ = scene.render_oracle(oracle, scenes.orbit_camera(3 * v, w, h), np.zeros((h, w), np.uint32), np.zeros((h, w), np.float32))
+        assert_same_u32(host_u32(color[v]), ec, f"view {v} colour")
+        assert_same_u32(bits(host_f32(depth[v])), bits(ed), f"view {v} depth")
+
+
+def test_render_depth_batch_matches_oracle(cuda, oracle):
+    """dfpsr_model_render_depth_batch: several casters into several cube-face targets in one submission, fused clear."""
+    import torch
+    res, faces = 64, 6
+    soups = [scenes.random_soup(60, 40 + i, extent=2.0, tri_size=1.0, textured=False) for i in range(3)]
+    cscenes = [CudaScene(s["points"], s["polygons"]) for s in soups]
+    sides = [((1, 0, 0), (0, 1, 0)), ((-1, 0, 0), (0, 1, 0)), ((0, 1, 0), (0, 0, 1)), ((0, -1, 0), (0, 0, 1)), ((0, 0, 1), (0, 1, 0)), ((0, 0, -1), (0, 1, 0))]
+    cam_params = [abi.camera_params(True, abi.Transform3D.make((0, 0, 0), np.stack(scenes.make_axis_system(f, u))), res, res) for f, u in sides]
+    cube = torch.full((faces * res, res), 9.0, dtype=torch.float32, device="cuda")
+    targets = (abi.Image * faces)(*[lib.image(cube[f * res:(f + 1) * res]) for f in range(faces)])
+    n = len(cscenes) * faces
+    models = (C.c_void_p * n)()
+    transforms = (abi.Transform3D * n)()
+    cams = (abi.Camera * n)()
+    target_of = (C.c_int32 * n)()
+    moves = [abi.Transform3D.make((0.3 * i, -0.2 * i, 0.1), ((1, 0, 0), (0, 1, 0), (0, 0, 1))) for i in range(len(cscenes))]
+    k = 0
+    for i, cs in enumerate(cscenes):
+        for f in range(faces):
+            models[k] = C.addressof(cs.model.desc)
+            transforms[k] = moves[i]
+            cams[k] = lib.camera(cam_params[f])
+            target_of[k] = f
+            k += 1
+    lib.check(cuda.dfpsr_model_render_depth_batch(models, transforms, cams, target_of, n, targets, faces, 1, 0.0, lib.stream_ptr()))
+    expected = np.zeros((faces * res, res), np.float32)
+    for i, cs in enumerate(cscenes):
+        for f in range(faces):
+            oracle.orc_model_render_depth(C.byref(cs.o_model), C.byref(moves[i]), C.byref(orcbind.image_of(expected[f * res:(f + 1) * res])), C.byref(orcbind.camera(cam_params[f])))
+    assert (expected != 0).mean() > 0.1
+    assert_same_u32(bits(host_f32(cube)), bits(expected), "cube map")
+
+
+def test_thousands_of_triangles_on_one_tile(cuda, oracle):
+    """More than 4096 entries in one 32x4 tile: the rank-sort path of sort_lists_kernel."""
+    soup = scenes.random_soup(6000, 77, extent=0.4, tri_size=0.8, textured=False)
+    scene = CudaScene(soup["points"], soup["polygons"])
+    w, h = 40, 12
+    cam = abi.camera_params(True, scenes.look_at_transform((0, 0, -3), (0, 0, 0)), w, h, width_slope=0.2)
+    c0, d0 = np.zeros((h, w), np.uint32), np.zeros((h, w), np.float32)
+    got_c, got_d = scene.render_cuda(cuda, cam, c0, d0)
+    exp_c, exp_d, commands = scene.render_oracle(oracle, cam, c0, d0)
+    assert commands > 4500
+    assert_same_u32(bits(got_d), bits(exp_d), "depth")
+    assert_same_u32(got_c, exp_c, "colour")

@@ -102,6 +102,16 @@ def test_random_soup_bit_exact_vs_scalar_reference(ref_scalar, oracle, case, mod
         assert np.array_equal(rc, oc), "colour"
 
 
+@pytest.mark.parametrize("size", [(33, 35), (321, 181), (320, 181), (77, 3), (5, 1), (1, 1)])
+@pytest.mark.parametrize("case", [0, 1, 4, 5])
+def test_odd_target_sizes_bit_exact(ref_scalar, oracle, case, size):
+    """Odd heights: the last row pair has no lower row; the reference then points its lower-row pointers at the upper row, so
+    the unclipped inner quads let lanes 2/3 overwrite lanes 0/1 (ref: shader/fillerTemplates.h:286-331). The oracle restates that."""
+    (rc, rz), (oc, oz), n = render_both(ref_scalar, oracle, 300 + case, w=size[0], h=size[1], **SOUP_CASES[case])
+    assert np.array_equal(bits(rz), bits(oz)), "depth"
+    assert np.array_equal(rc, oc), "colour"
+
+
 @pytest.mark.parametrize("case", [0, 1, 2, 4])
 def test_random_soup_within_tolerance_of_sse_reference(ref_sse, oracle, case):
     """The north star's tolerance: identical coverage/depth ordering, +-1 LSB per channel against the SIMD build."""

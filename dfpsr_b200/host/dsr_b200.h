@@ -1,0 +1,546 @@
+// dsr_b200.h — C++14 host shim: DFPSR's own API names for the rendering hot path, implemented over the C ABI of
+// include/dfpsr_b200.h (hand-written sm_100a kernels). Header-only; link with libdfpsr_b200.so. No CPU fallback: without a
+// CUDA device every rendering call throws (the reference reports errors through throwError -> std::exception as well,
+// ref: DFPSR/api/stringAPI.h:597-629).
+//
+// Each declaration cites the reference declaration it mirrors (paths relative to /root/reference/Source/DFPSR).
+// Scope: what SDK/terrain/main.cpp:383-433, SDK/cube, templates/basic3D and SDK/SpriteEngine/{spriteAPI,lightAPI}.cpp call on
+// the path. Images and textures live in device memory; host access (image_readPixel_*, image_writePixel,
+// image_download) goes through a lazily synchronised host mirror, so a frame that is only rendered and presented costs one
+// device-to-host copy and nothing else.
+#pragma once
+
+#include "../../include/dfpsr_b200.h"
+
+#include <cstdint>
+#include <cstring>
+#include <cmath>
+#include <limits>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace dsr {
+
+// ref: api/stringAPI.h:597 throwError
+inline void throwError(const std::string &message) { throw std::runtime_error(message); }
+inline void b200_check(int status) { if (status != 0) { throwError(dfpsr_last_error()); } }
+
+// ---------------------------------------------------------------- math PODs (ref: math/FVector.h, FMatrix3x3.h, Transform3D.h)
+struct FVector2D { float x = 0.0f, y = 0.0f; FVector2D() {} FVector2D(float x, float y) : x(x), y(y) {} };
+struct FVector3D { float x = 0.0f, y = 0.0f, z = 0.0f; FVector3D() {} FVector3D(float x, float y, float z) : x(x), y(y), z(z) {} };
+struct FVector4D { float x = 0.0f, y = 0.0f, z = 0.0f, w = 0.0f; FVector4D() {} FVector4D(float x, float y, float z, float w) : x(x), y(y), z(z), w(w) {} };
+inline FVector3D operator+(const FVector3D &a, const FVector3D &b) { return FVector3D(a.x + b.x, a.y + b.y, a.z + b.z); }
+inline FVector3D operator-(const FVector3D &a, const FVector3D &b) { return FVector3D(a.x - b.x, a.y - b.y, a.z - b.z); }
+inline FVector3D operator-(const FVector3D &a) { return FVector3D(-a.x, -a.y, -a.z); }
+inline FVector3D operator*(const FVector3D &a, float s) { return FVector3D(a.x * s, a.y * s, a.z * s); }
+inline float dotProduct(const FVector3D &a, const FVector3D &b) { return (a.x * b.x) + (a.y * b.y) + (a.z * b.z); }
+inline FVector3D crossProduct(const FVector3D &a, const FVector3D &b) { return FVector3D(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+inline FVector3D normalize(const FVector3D &v) { // ref: math/FVector.h:113-120
+	float l = std::sqrt(v.x * v.x + v.y * v.y + v.z * v.z);
+	if (l == 0.0f) { return FVector3D(0.0f, 0.0f, 1.0f); }
+	return FVector3D(v.x / l, v.y / l, v.z / l);
+}
+struct FMatrix3x3 { // ref: math/FMatrix3x3.h:33-51
+	FVector3D xAxis = FVector3D(1, 0, 0), yAxis = FVector3D(0, 1, 0), zAxis = FVector3D(0, 0, 1);
+	FMatrix3x3() {}
+	FMatrix3x3(const FVector3D &x, const FVector3D &y, const FVector3D &z) : xAxis(x), yAxis(y), zAxis(z) {}
+	static FMatrix3x3 makeAxisSystem(const FVector3D &forward, const FVector3D &up) {
+		FMatrix3x3 r;
+		r.zAxis = normalize(forward);
+		r.xAxis = normalize(crossProduct(normalize(up), r.zAxis));
+		r.yAxis = normalize(crossProduct(r.zAxis, r.xAxis));
+		return r;
+	}
+};
+struct Transform3D { // ref: math/Transform3D.h:33-36
+	FVector3D position;
+	FMatrix3x3 transform;
+	Transform3D() {}
+	Transform3D(const FVector3D &position, const FMatrix3x3 &transform) : position(position), transform(transform) {}
+};
+inline dfpsr_transform3d b200_pod(const Transform3D &t) {
+	dfpsr_transform3d r;
+	r.position[0] = t.position.x; r.position[1] = t.position.y; r.position[2] = t.position.z;
+	r.xAxis[0] = t.transform.xAxis.x; r.xAxis[1] = t.transform.xAxis.y; r.xAxis[2] = t.transform.xAxis.z;
+	r.yAxis[0] = t.transform.yAxis.x; r.yAxis[1] = t.transform.yAxis.y; r.yAxis[2] = t.transform.yAxis.z;
+	r.zAxis[0] = t.transform.zAxis.x; r.zAxis[1] = t.transform.zAxis.y; r.zAxis[2] = t.transform.zAxis.z;
+	return r;
+}
+
+enum class PackOrderIndex { RGBA = 0, BGRA = 1, ARGB = 2, ABGR = 3 }; // ref: implementation/image/PackOrder.h:37-42
+enum class Filter { Solid = 0, Alpha = 1 };                           // ref: implementation/render/constants.h:34
+enum class Sampler { Nearest = 0, Linear = 1 };                       // ref: api/filterAPI.h:33-36
+struct ColorRgbaI32 { // ref: implementation/image/Color.h
+	int32_t red = 0, green = 0, blue = 0, alpha = 0;
+	ColorRgbaI32() {}
+	ColorRgbaI32(int32_t r, int32_t g, int32_t b, int32_t a) : red(r), green(g), blue(b), alpha(a) {}
+};
+
+// ---------------------------------------------------------------- device context
+inline void *&b200_stream() { static thread_local void *stream = nullptr; return stream; } // cudaStream_t used by this thread's calls
+inline void b200_init(int device = 0) { b200_check(dfpsr_init(device)); }
+
+// ---------------------------------------------------------------- images (ref: api/imageAPI.h:47-525, implementation/image/Image.h:58-183)
+struct B200Buffer { // ref-counted device allocation + lazily synchronised host mirror
+	void *device = nullptr;
+	size_t bytes = 0;
+	std::vector<uint8_t> host;
+	bool hostValid = false, deviceDirty = false; // deviceDirty: kernels wrote since the last download
+	explicit B200Buffer(size_t bytes) : bytes(bytes) { b200_check(dfpsr_malloc(&device, bytes > 0 ? bytes : 1)); }
+	~B200Buffer() { if (device) { dfpsr_free(device); } }
+	B200Buffer(const B200Buffer &) = delete;
+	B200Buffer &operator=(const B200Buffer &) = delete;
+	uint8_t *hostData() {
+		if (!hostValid || deviceDirty) {
+			host.resize(bytes);
+			b200_check(dfpsr_download(host.data(), device, bytes, b200_stream()));
+			b200_check(dfpsr_stream_synchronize(b200_stream()));
+			hostValid = true; deviceDirty = false;
+		}
+		return host.data();
+	}
+	void pushHost() { b200_check(dfpsr_upload(device, host.data(), bytes, b200_stream())); b200_check(dfpsr_stream_synchronize(b200_stream())); }
+};
+
+template <typename PIXEL>
+class B200Image {
+public:
+	std::shared_ptr<B200Buffer> buffer;
+	int32_t width = 0, height = 0, stride = 0, startOffset = 0;
+	PackOrderIndex packOrder = PackOrderIndex::RGBA;
+	bool subImage = false;
+	dfpsr_image pod() const {
+		dfpsr_image r;
+		r.data = buffer ? (void *)((uint8_t *)buffer->device + startOffset) : nullptr;
+		r.width = width; r.height = height; r.stride = stride; r.packOrder = (int32_t)packOrder;
+		return r;
+	}
+	void touchedByDevice() const { if (buffer) { buffer->deviceDirty = true; } }
+};
+using ImageRgbaU8 = B200Image<uint32_t>;
+using ImageF32 = B200Image<float>;
+
+template <typename PIXEL>
+inline B200Image<PIXEL> b200_image_create(int32_t width, int32_t height, PackOrderIndex order) {
+	if (width <= 0 || height <= 0) { throwError("image_create: non-positive dimensions"); } // ref: api/imageAPI.cpp:58-66
+	B200Image<PIXEL> image;
+	image.width = width; image.height = height;
+	image.stride = ((width * (int32_t)sizeof(PIXEL) + 255) / 256) * 256; // rows on 256-byte boundaries (the reference pads to its heap alignment, imageAPI.cpp:50)
+	image.packOrder = order;
+	image.buffer = std::make_shared<B200Buffer>((size_t)image.stride * (size_t)height);
+	return image;
+}
+// ref: api/imageAPI.h:63-70. zeroed = true clears like the reference does.
+inline ImageRgbaU8 image_create_RgbaU8(int32_t width, int32_t height, bool zeroed = true) {
+	ImageRgbaU8 image = b200_image_create<uint32_t>(width, height, PackOrderIndex::RGBA);
+	if (zeroed) { dfpsr_image pod = image.pod(); b200_check(dfpsr_image_fill_rgba(&pod, 0, 0, 0, 0, b200_stream())); image.touchedByDevice(); }
+	return image;
+}
+inline ImageRgbaU8 image_create_RgbaU8_native(int32_t width, int32_t height, PackOrderIndex order, bool zeroed = true) {
+	ImageRgbaU8 image = b200_image_create<uint32_t>(width, height, order);
+	if (zeroed) { dfpsr_image pod = image.pod(); b200_check(dfpsr_image_fill_rgba(&pod, 0, 0, 0, 0, b200_stream())); image.touchedByDevice(); }
+	return image;
+}
+inline ImageF32 image_create_F32(int32_t width, int32_t height, bool zeroed = true) {
+	ImageF32 image = b200_image_create<float>(width, height, PackOrderIndex::RGBA);
+	if (zeroed) { dfpsr_image pod = image.pod(); b200_check(dfpsr_image_fill_f32(&pod, 0.0f, b200_stream())); image.touchedByDevice(); }
+	return image;
+}
+template <typename P> inline bool image_exists(const B200Image<P> &image) { return (bool)image.buffer; }          // ref: api/imageAPI.h:96
+template <typename P> inline int32_t image_getWidth(const B200Image<P> &image) { return image.width; }            // ref: api/imageAPI.h:104-120
+template <typename P> inline int32_t image_getHeight(const B200Image<P> &image) { return image.height; }
+template <typename P> inline int32_t image_getStride(const B200Image<P> &image) { return image.stride; }
+template <typename P> inline bool image_isSubImage(const B200Image<P> &image) { return image.subImage; }
+inline PackOrderIndex image_getPackOrderIndex(const ImageRgbaU8 &image) { return image.packOrder; }
+// ref: api/imageAPI.h:380-400 image_getSubImage — a view on the same buffer
+template <typename P> inline B200Image<P> image_getSubImage(const B200Image<P> &image, int32_t left, int32_t top, int32_t width, int32_t height) {
+	if (!image_exists(image)) { return B200Image<P>(); }
+	if (left < 0 || top < 0 || width <= 0 || height <= 0 || left + width > image.width || top + height > image.height) { return B200Image<P>(); } // ref: Image.h:186-206
+	B200Image<P> r = image;
+	r.startOffset = image.startOffset + top * image.stride + left * (int32_t)sizeof(P);
+	r.width = width; r.height = height; r.subImage = true;
+	return r;
+}
+// ref: api/imageAPI.cpp:167-185
+inline void image_fill(ImageRgbaU8 &image, const ColorRgbaI32 &color) {
+	if (!image_exists(image)) { return; }
+	dfpsr_image pod = image.pod();
+	b200_check(dfpsr_image_fill_rgba(&pod, color.red, color.green, color.blue, color.alpha, b200_stream()));
+	image.touchedByDevice();
+}
+inline void image_fill(ImageF32 &image, float value) {
+	if (!image_exists(image)) { return; }
+	dfpsr_image pod = image.pod();
+	b200_check(dfpsr_image_fill_f32(&pod, value, b200_stream()));
+	image.touchedByDevice();
+}
+// ref: api/imageAPI.h:207-341 — reads go through the host mirror
+inline ColorRgbaI32 b200_unpack(uint32_t c, PackOrderIndex order) {
+	static const int index[4][4] = {{0, 1, 2, 3}, {2, 1, 0, 3}, {1, 2, 3, 0}, {3, 2, 1, 0}}; // byte of r, g, b, a (ref: PackOrder.h:85-96)
+	const int *i = index[(int)order];
+	return ColorRgbaI32((int32_t)((c >> (8 * i[0])) & 255u), (int32_t)((c >> (8 * i[1])) & 255u), (int32_t)((c >> (8 * i[2])) & 255u), (int32_t)((c >> (8 * i[3])) & 255u));
+}
+inline ColorRgbaI32 image_readPixel_clamp(const ImageRgbaU8 &image, int32_t x, int32_t y) {
+	if (!image_exists(image)) { return ColorRgbaI32(); }
+	x = x < 0 ? 0 : (x >= image.width ? image.width - 1 : x); y = y < 0 ? 0 : (y >= image.height ? image.height - 1 : y);
+	uint32_t c;
+	std::memcpy(&c, image.buffer->hostData() + image.startOffset + (size_t)y * image.stride + (size_t)x * 4, 4);
+	return b200_unpack(c, image.packOrder);
+}
+inline float image_readPixel_clamp(const ImageF32 &image, int32_t x, int32_t y) {
+	if (!image_exists(image)) { return 0.0f; }
+	x = x < 0 ? 0 : (x >= image.width ? image.width - 1 : x); y = y < 0 ? 0 : (y >= image.height ? image.height - 1 : y);
+	float v;
+	std::memcpy(&v, image.buffer->hostData() + image.startOffset + (size_t)y * image.stride + (size_t)x * 4, 4);
+	return v;
+}
+// Whole-image transfers for presentation / asset upload (tightly packed rows on the host side).
+template <typename P> inline void image_download(const B200Image<P> &image, P *target, int32_t targetStrideBytes) {
+	if (!image_exists(image)) { return; }
+	b200_check(dfpsr_download_2d(target, (size_t)targetStrideBytes, (uint8_t *)image.buffer->device + image.startOffset, (size_t)image.stride, (size_t)image.width * sizeof(P), (size_t)image.height, b200_stream()));
+	b200_check(dfpsr_stream_synchronize(b200_stream()));
+}
+template <typename P> inline void image_upload(B200Image<P> &image, const P *source, int32_t sourceStrideBytes) {
+	if (!image_exists(image)) { return; }
+	b200_check(dfpsr_upload_2d((uint8_t *)image.buffer->device + image.startOffset, (size_t)image.stride, source, (size_t)sourceStrideBytes, (size_t)image.width * sizeof(P), (size_t)image.height, b200_stream()));
+	b200_check(dfpsr_stream_synchronize(b200_stream()));
+	image.buffer->hostValid = false;
+}
+
+// ---------------------------------------------------------------- textures (ref: api/textureAPI.h:450-465, implementation/image/Texture.h)
+class TextureRgbaU8 {
+public:
+	std::shared_ptr<B200Buffer> buffer;
+	dfpsr_texture layout{};
+	dfpsr_texture pod() const { dfpsr_texture r = layout; r.data = buffer ? (const uint32_t *)buffer->device : nullptr; return r; }
+};
+inline bool texture_exists(const TextureRgbaU8 &texture) { return (bool)texture.buffer; }
+inline int32_t texture_getMaxWidth(const TextureRgbaU8 &texture) { return texture_exists(texture) ? 1 << texture.layout.log2width : 0; }
+inline int32_t texture_getMaxHeight(const TextureRgbaU8 &texture) { return texture_exists(texture) ? 1 << texture.layout.log2height : 0; }
+inline int32_t texture_getSmallestMipLevel(const TextureRgbaU8 &texture) { return (int32_t)texture.layout.maxMipLevel; }
+// ref: api/textureAPI.cpp:65-78 texture_create_RgbaU8(width, height, resolutions)
+inline TextureRgbaU8 texture_create_RgbaU8(int32_t width, int32_t height, int32_t resolutions) {
+	TextureRgbaU8 t;
+	b200_check(dfpsr_texture_layout(&t.layout, width, height, resolutions));
+	t.buffer = std::make_shared<B200Buffer>((size_t)t.layout.totalPixels * 4);
+	return t;
+}
+// ref: api/textureAPI.cpp:80-87 texture_generatePyramid
+inline void texture_generatePyramid(TextureRgbaU8 &texture) {
+	if (!texture_exists(texture)) { return; }
+	dfpsr_texture pod = texture.pod();
+	b200_check(dfpsr_texture_generate_pyramid(&pod, b200_stream()));
+	texture.buffer->deviceDirty = true;
+}
+// ref: api/textureAPI.cpp:89-110 texture_create_RgbaU8(image, resolutions): bilinear resize to powers of two, then the pyramid
+inline TextureRgbaU8 texture_create_RgbaU8(const ImageRgbaU8 &image, int32_t resolutions) {
+	if (!image_exists(image)) { return TextureRgbaU8(); }
+	TextureRgbaU8 t = texture_create_RgbaU8(image.width, image.height, resolutions);
+	dfpsr_texture pod = t.pod();
+	dfpsr_image source = image.pod();
+	b200_check(dfpsr_texture_from_image(&pod, &source, b200_stream()));
+	t.buffer->deviceDirty = true;
+	return t;
+}
+// ref: api/textureAPI.h:460-465 texture_getMipLevelImage — a view on one level (level 0 = full resolution)
+inline ImageRgbaU8 texture_getMipLevelImage(const TextureRgbaU8 &texture, int32_t mipLevel) {
+	if (!texture_exists(texture) || mipLevel < 0 || mipLevel > (int32_t)texture.layout.maxMipLevel) { return ImageRgbaU8(); }
+	ImageRgbaU8 image;
+	image.buffer = texture.buffer;
+	image.width = (1 << texture.layout.log2width) >> mipLevel; image.height = (1 << texture.layout.log2height) >> mipLevel;
+	image.stride = image.width * 4;
+	image.startOffset = (int32_t)(texture.layout.startOffset & (texture.layout.maxLevelMask >> (2 * mipLevel))) * 4;
+	image.subImage = true;
+	return image;
+}
+
+// ---------------------------------------------------------------- camera (ref: implementation/render/Camera.h:128-217)
+class Camera {
+public:
+	dfpsr_camera pod{};
+	static Camera createPerspective(const Transform3D &location, float imageWidth, float imageHeight, float widthSlope = 1.0f, float nearClip = 0.01f, float farClip = 1000.0f) {
+		Camera c; dfpsr_transform3d t = b200_pod(location);
+		b200_check(dfpsr_camera_create_perspective(&c.pod, &t, imageWidth, imageHeight, widthSlope, nearClip, farClip));
+		return c;
+	}
+	static Camera createOrthogonal(const Transform3D &location, float imageWidth, float imageHeight, float halfWidth) {
+		Camera c; dfpsr_transform3d t = b200_pod(location);
+		b200_check(dfpsr_camera_create_orthogonal(&c.pod, &t, imageWidth, imageHeight, halfWidth));
+		return c;
+	}
+	// ref: Camera.h:202-217 — 0 hidden, 1 partial, 2 full
+	int isBoxSeen(const FVector3D &minimum, const FVector3D &maximum, const Transform3D &modelToWorld) const {
+		float mn[3] = {minimum.x, minimum.y, minimum.z}, mx[3] = {maximum.x, maximum.y, maximum.z};
+		dfpsr_transform3d t = b200_pod(modelToWorld);
+		return dfpsr_camera_is_box_seen(&pod, mn, mx, &t);
+	}
+};
+
+// ---------------------------------------------------------------- models (ref: api/modelAPI.h:62-301, implementation/render/model/Model.h:54-84)
+struct B200Part {
+	std::string name;
+	TextureRgbaU8 diffuseMap, lightMap;
+	std::vector<dfpsr_polygon> polygons;
+	std::shared_ptr<B200Buffer> devicePolygons;
+	bool dirty = true;
+};
+struct B200Model {
+	Filter filter = Filter::Solid;
+	std::vector<float> points; // x, y, z
+	std::vector<B200Part> parts;
+	FVector3D minBound, maxBound; // ref: Model.cpp:281-288 — starts at the origin and only grows
+	std::shared_ptr<B200Buffer> devicePoints;
+	bool pointsDirty = true;
+};
+using Model = std::shared_ptr<B200Model>;
+
+inline Model model_create() { return std::make_shared<B200Model>(); }
+inline bool model_exists(const Model &model) { return (bool)model; }
+inline Model model_clone(const Model &model) { // ref: api/modelAPI.h:66 — deep copy of geometry, textures shared
+	if (!model) { return Model(); }
+	Model r = std::make_shared<B200Model>(*model);
+	r->devicePoints.reset(); r->pointsDirty = true;
+	for (B200Part &p : r->parts) { p.devicePolygons.reset(); p.dirty = true; }
+	return r;
+}
+inline void b200_require(const Model &model, const char *method) { if (!model) { throwError(std::string(method) + ": the model does not exist"); } }
+inline void model_setFilter(const Model &model, Filter filter) { b200_require(model, "model_setFilter"); model->filter = filter; }
+inline Filter model_getFilter(const Model &model) { b200_require(model, "model_getFilter"); return model->filter; }
+inline int32_t model_addEmptyPart(Model &model, const std::string &name) {
+	b200_require(model, "model_addEmptyPart");
+	model->parts.emplace_back();
+	model->parts.back().name = name;
+	return (int32_t)model->parts.size() - 1;
+}
+inline int32_t model_getNumberOfParts(const Model &model) { b200_require(model, "model_getNumberOfParts"); return (int32_t)model->parts.size(); }
+inline int32_t model_getNumberOfPoints(const Model &model) { b200_require(model, "model_getNumberOfPoints"); return (int32_t)(model->points.size() / 3); }
+inline int32_t model_addPoint(const Model &model, const FVector3D &position) {
+	b200_require(model, "model_addPoint");
+	model->points.push_back(position.x); model->points.push_back(position.y); model->points.push_back(position.z);
+	// ref: Model.cpp:281-288 expandBound
+	if (position.x < model->minBound.x) { model->minBound.x = position.x; } if (position.y < model->minBound.y) { model->minBound.y = position.y; } if (position.z < model->minBound.z) { model->minBound.z = position.z; }
+	if (position.x > model->maxBound.x) { model->maxBound.x = position.x; } if (position.y > model->maxBound.y) { model->maxBound.y = position.y; } if (position.z > model->maxBound.z) { model->maxBound.z = position.z; }
+	model->pointsDirty = true;
+	return (int32_t)(model->points.size() / 3) - 1;
+}
+inline FVector3D model_getPoint(const Model &model, int32_t pointIndex) {
+	b200_require(model, "model_getPoint");
+	if (pointIndex < 0 || pointIndex >= model_getNumberOfPoints(model)) { return FVector3D(); } // ref: Model.cpp:34-42 prints and returns a default
+	return FVector3D(model->points[3 * pointIndex], model->points[3 * pointIndex + 1], model->points[3 * pointIndex + 2]);
+}
+inline void model_setPoint(Model &model, int32_t pointIndex, const FVector3D &position) {
+	b200_require(model, "model_setPoint");
+	if (pointIndex < 0 || pointIndex >= model_getNumberOfPoints(model)) { return; }
+	model->points[3 * pointIndex] = position.x; model->points[3 * pointIndex + 1] = position.y; model->points[3 * pointIndex + 2] = position.z;
+	if (position.x < model->minBound.x) { model->minBound.x = position.x; } if (position.y < model->minBound.y) { model->minBound.y = position.y; } if (position.z < model->minBound.z) { model->minBound.z = position.z; }
+	if (position.x > model->maxBound.x) { model->maxBound.x = position.x; } if (position.y > model->maxBound.y) { model->maxBound.y = position.y; } if (position.z > model->maxBound.z) { model->maxBound.z = position.z; }
+	model->pointsDirty = true;
+}
+inline void model_getBoundingBox(const Model &model, FVector3D &minimum, FVector3D &maximum) { b200_require(model, "model_getBoundingBox"); minimum = model->minBound; maximum = model->maxBound; }
+inline B200Part *b200_part(const Model &model, int32_t partIndex, const char *method) {
+	b200_require(model, method);
+	if (partIndex < 0 || partIndex >= (int32_t)model->parts.size()) { return nullptr; }
+	return &model->parts[(size_t)partIndex];
+}
+inline int32_t b200_add_polygon(Model &model, int32_t partIndex, int32_t a, int32_t b, int32_t c, int32_t d, const char *method) {
+	B200Part *part = b200_part(model, partIndex, method);
+	if (!part) { return -1; }
+	dfpsr_polygon polygon;
+	std::memset(&polygon, 0, sizeof(polygon));
+	polygon.pointIndices[0] = a; polygon.pointIndices[1] = b; polygon.pointIndices[2] = c; polygon.pointIndices[3] = d;
+	for (int v = 0; v < 4; v++) { for (int ch = 0; ch < 4; ch++) { polygon.colors[v][ch] = 1.0f; } } // ref: Model.h:30-52 default white, texcoords 0
+	part->polygons.push_back(polygon);
+	part->dirty = true;
+	return (int32_t)part->polygons.size() - 1;
+}
+inline int32_t model_addTriangle(Model &model, int32_t partIndex, int32_t pointA, int32_t pointB, int32_t pointC) { return b200_add_polygon(model, partIndex, pointA, pointB, pointC, -1, "model_addTriangle"); }
+inline int32_t model_addQuad(Model &model, int32_t partIndex, int32_t pointA, int32_t pointB, int32_t pointC, int32_t pointD) { return b200_add_polygon(model, partIndex, pointA, pointB, pointC, pointD, "model_addQuad"); }
+inline int32_t model_getNumberOfPolygons(const Model &model, int32_t partIndex) { B200Part *p = b200_part(model, partIndex, "model_getNumberOfPolygons"); return p ? (int32_t)p->polygons.size() : 0; }
+inline dfpsr_polygon *b200_polygon(const Model &model, int32_t partIndex, int32_t polygonIndex, int32_t vertexIndex, const char *method) {
+	B200Part *part = b200_part(model, partIndex, method);
+	if (!part || polygonIndex < 0 || polygonIndex >= (int32_t)part->polygons.size() || vertexIndex < 0 || vertexIndex > 3) { return nullptr; }
+	part->dirty = true;
+	return &part->polygons[(size_t)polygonIndex];
+}
+inline void model_setVertexColor(Model &model, int32_t partIndex, int32_t polygonIndex, int32_t vertexIndex, const FVector4D &color) {
+	if (dfpsr_polygon *p = b200_polygon(model, partIndex, polygonIndex, vertexIndex, "model_setVertexColor")) { p->colors[vertexIndex][0] = color.x; p->colors[vertexIndex][1] = color.y; p->colors[vertexIndex][2] = color.z; p->colors[vertexIndex][3] = color.w; }
+}
+inline void model_setTexCoord(Model &model, int32_t partIndex, int32_t polygonIndex, int32_t vertexIndex, const FVector4D &texCoord) {
+	if (dfpsr_polygon *p = b200_polygon(model, partIndex, polygonIndex, vertexIndex, "model_setTexCoord")) { p->texCoords[vertexIndex][0] = texCoord.x; p->texCoords[vertexIndex][1] = texCoord.y; p->texCoords[vertexIndex][2] = texCoord.z; p->texCoords[vertexIndex][3] = texCoord.w; }
+}
+inline void model_setDiffuseMap(Model &model, int32_t partIndex, const TextureRgbaU8 &diffuseMap) { if (B200Part *p = b200_part(model, partIndex, "model_setDiffuseMap")) { p->diffuseMap = diffuseMap; } }
+inline void model_setLightMap(Model &model, int32_t partIndex, const TextureRgbaU8 &lightMap) { if (B200Part *p = b200_part(model, partIndex, "model_setLightMap")) { p->lightMap = lightMap; } }
+inline TextureRgbaU8 model_getDiffuseMap(const Model &model, int32_t partIndex) { B200Part *p = b200_part(model, partIndex, "model_getDiffuseMap"); return p ? p->diffuseMap : TextureRgbaU8(); }
+inline TextureRgbaU8 model_getLightMap(const Model &model, int32_t partIndex) { B200Part *p = b200_part(model, partIndex, "model_getLightMap"); return p ? p->lightMap : TextureRgbaU8(); }
+
+// Uploads whatever changed since the last draw and returns one dfpsr_model per part (the C ABI's model has one part).
+inline std::vector<dfpsr_model> b200_device_models(const Model &model) {
+	std::vector<dfpsr_model> result;
+	if (!model || model->points.empty()) { return result; }
+	if (model->pointsDirty || !model->devicePoints || model->devicePoints->bytes < model->points.size() * 4) {
+		if (!model->devicePoints || model->devicePoints->bytes < model->points.size() * 4) { model->devicePoints = std::make_shared<B200Buffer>(model->points.size() * 4); }
+		b200_check(dfpsr_upload(model->devicePoints->device, model->points.data(), model->points.size() * 4, b200_stream()));
+		b200_check(dfpsr_stream_synchronize(b200_stream()));
+		model->pointsDirty = false;
+	}
+	for (B200Part &part : model->parts) {
+		if (part.polygons.empty()) { continue; }
+		size_t bytes = part.polygons.size() * sizeof(dfpsr_polygon);
+		if (part.dirty || !part.devicePolygons || part.devicePolygons->bytes < bytes) {
+			if (!part.devicePolygons || part.devicePolygons->bytes < bytes) { part.devicePolygons = std::make_shared<B200Buffer>(bytes); }
+			b200_check(dfpsr_upload(part.devicePolygons->device, part.polygons.data(), bytes, b200_stream()));
+			b200_check(dfpsr_stream_synchronize(b200_stream()));
+			part.dirty = false;
+		}
+		dfpsr_model m;
+		std::memset(&m, 0, sizeof(m));
+		m.points = (const float *)model->devicePoints->device; m.pointCount = (int32_t)(model->points.size() / 3);
+		m.polygons = (const dfpsr_polygon *)part.devicePolygons->device; m.polygonCount = (int32_t)part.polygons.size();
+		m.filter = (int32_t)model->filter;
+		m.diffuse = part.diffuseMap.pod(); m.light = part.lightMap.pod();
+		m.minBound[0] = model->minBound.x; m.minBound[1] = model->minBound.y; m.minBound[2] = model->minBound.z;
+		m.maxBound[0] = model->maxBound.x; m.maxBound[1] = model->maxBound.y; m.maxBound[2] = model->maxBound.z;
+		result.push_back(m);
+	}
+	return result;
+}
+
+// ---------------------------------------------------------------- renderer (ref: api/rendererAPI.h:54-135, api/rendererAPI.cpp:141-168, :352-402)
+struct B200Renderer {
+	dfpsr_renderer *handle = nullptr;
+	ImageRgbaU8 colorBuffer;
+	ImageF32 depthBuffer;
+	bool receiving = false;
+	B200Renderer() { b200_check(dfpsr_renderer_create(&handle)); }
+	~B200Renderer() { if (handle) { dfpsr_renderer_destroy(handle); } }
+	B200Renderer(const B200Renderer &) = delete;
+	B200Renderer &operator=(const B200Renderer &) = delete;
+};
+using Renderer = std::shared_ptr<B200Renderer>;
+
+inline Renderer renderer_create() { return std::make_shared<B200Renderer>(); }
+inline bool renderer_exists(const Renderer &renderer) { return (bool)renderer; }
+inline void renderer_begin(Renderer &renderer, ImageRgbaU8 &colorBuffer, ImageF32 &depthBuffer) {
+	if (!renderer) { throwError("renderer_begin: renderer does not exist"); }
+	dfpsr_image color = colorBuffer.pod(), depth = depthBuffer.pod();
+	b200_check(dfpsr_renderer_begin(renderer->handle, &color, &depth)); // "twice without ending" is reported by the library (rendererAPI.cpp:152-154)
+	renderer->colorBuffer = colorBuffer; renderer->depthBuffer = depthBuffer; renderer->receiving = true;
+}
+inline ImageRgbaU8 renderer_getColorBuffer(const Renderer &renderer) { return renderer ? renderer->colorBuffer : ImageRgbaU8(); }
+inline ImageF32 renderer_getDepthBuffer(const Renderer &renderer) { return renderer ? renderer->depthBuffer : ImageF32(); }
+inline bool renderer_takesTriangles(const Renderer &renderer) { return renderer && renderer->receiving; }
+// ref: api/modelAPI.cpp:214-281 model_render_threaded == renderer_giveTask
+inline void model_render_threaded(const Model &model, const Transform3D &modelToWorldTransform, Renderer &renderer, const Camera &camera) {
+	if (!renderer) { throwError("renderer_giveTask: renderer does not exist"); }
+	if (!model) { return; }
+	dfpsr_transform3d t = b200_pod(modelToWorldTransform);
+	for (const dfpsr_model &m : b200_device_models(model)) { b200_check(dfpsr_renderer_give_task(renderer->handle, &m, &t, &camera.pod, b200_stream())); }
+}
+inline void renderer_giveTask(Renderer &renderer, const Model &model, const Transform3D &modelToWorldTransform, const Camera &camera) { model_render_threaded(model, modelToWorldTransform, renderer, camera); }
+// ref: api/rendererAPI.h:108-129 renderer_giveTask_triangle with points the caller projected (ProjectedPoint, 40 bytes)
+inline void renderer_giveTask_triangle(Renderer &renderer, const dfpsr_projected_point &posA, const dfpsr_projected_point &posB, const dfpsr_projected_point &posC,
+  const FVector4D &colorA, const FVector4D &colorB, const FVector4D &colorC, const FVector4D &texCoordA, const FVector4D &texCoordB, const FVector4D &texCoordC,
+  const TextureRgbaU8 &diffuse, const TextureRgbaU8 &light, Filter filter, const Camera &camera) {
+	if (!renderer) { throwError("renderer_giveTask_triangle: renderer does not exist"); }
+	dfpsr_triangle tri;
+	tri.pos[0] = posA; tri.pos[1] = posB; tri.pos[2] = posC;
+	const FVector4D *colors[3] = {&colorA, &colorB, &colorC}, *tex[3] = {&texCoordA, &texCoordB, &texCoordC};
+	for (int k = 0; k < 3; k++) {
+		tri.colors[k][0] = colors[k]->x; tri.colors[k][1] = colors[k]->y; tri.colors[k][2] = colors[k]->z; tri.colors[k][3] = colors[k]->w;
+		tri.texCoords[k][0] = tex[k]->x; tri.texCoords[k][1] = tex[k]->y; tri.texCoords[k][2] = tex[k]->z; tri.texCoords[k][3] = tex[k]->w;
+	}
+	dfpsr_texture d = diffuse.pod(), l = light.pod();
+	b200_check(dfpsr_renderer_give_task_triangles(renderer->handle, &tri, 1, &d, &l, (int32_t)filter, &camera.pod, b200_stream()));
+}
+inline void renderer_end(Renderer &renderer, bool debugWireframe = false) {
+	(void)debugWireframe; // the wireframe overlay (rendererAPI.cpp:362-399) is a 2D draw call outside the path
+	if (!renderer) { throwError("renderer_end: renderer does not exist"); }
+	b200_check(dfpsr_renderer_end(renderer->handle, b200_stream()));
+	renderer->colorBuffer.touchedByDevice(); renderer->depthBuffer.touchedByDevice();
+	renderer->colorBuffer = ImageRgbaU8(); renderer->depthBuffer = ImageF32(); renderer->receiving = false; // ref: rendererAPI.cpp:480-488
+}
+// ref: api/modelAPI.cpp:197-206
+inline void model_render(const Model &model, const Transform3D &modelToWorldTransform, ImageRgbaU8 &colorBuffer, ImageF32 &depthBuffer, const Camera &camera) {
+	if (!model) { return; }
+	dfpsr_transform3d t = b200_pod(modelToWorldTransform);
+	dfpsr_image color = colorBuffer.pod(), depth = depthBuffer.pod();
+	for (const dfpsr_model &m : b200_device_models(model)) { b200_check(dfpsr_model_render(&m, &t, &color, &depth, &camera.pod, b200_stream())); }
+	colorBuffer.touchedByDevice(); depthBuffer.touchedByDevice();
+}
+inline void model_renderDepth(const Model &model, const Transform3D &modelToWorldTransform, ImageF32 &depthBuffer, const Camera &camera) {
+	if (!model) { return; }
+	dfpsr_transform3d t = b200_pod(modelToWorldTransform);
+	dfpsr_image depth = depthBuffer.pod();
+	for (const dfpsr_model &m : b200_device_models(model)) { b200_check(dfpsr_model_render_depth(&m, &t, &depth, &camera.pod, b200_stream())); }
+	depthBuffer.touchedByDevice();
+}
+
+// ---------------------------------------------------------------- 2D draw calls on the path (ref: api/drawAPI.h)
+inline void draw_copy(ImageRgbaU8 &target, const ImageRgbaU8 &source, int32_t left = 0, int32_t top = 0) {
+	dfpsr_image t = target.pod(), s = source.pod();
+	b200_check(dfpsr_draw_copy_rgba(&t, &s, left, top, b200_stream())); target.touchedByDevice();
+}
+inline void draw_copy(ImageF32 &target, const ImageF32 &source, int32_t left = 0, int32_t top = 0) {
+	dfpsr_image t = target.pod(), s = source.pod();
+	b200_check(dfpsr_draw_copy_f32(&t, &s, left, top, b200_stream())); target.touchedByDevice();
+}
+// ref: api/drawAPI.cpp:962-979 draw_higher(F32 height, + 0 / 1 / 2 RGBA payloads)
+inline void draw_higher(ImageF32 &targetHeight, const ImageF32 &sourceHeight, int32_t left = 0, int32_t top = 0, float sourceHeightOffset = 0.0f) {
+	dfpsr_image th = targetHeight.pod(), sh = sourceHeight.pod();
+	b200_check(dfpsr_draw_higher(&th, &sh, nullptr, nullptr, nullptr, nullptr, left, top, sourceHeightOffset, b200_stream())); targetHeight.touchedByDevice();
+}
+inline void draw_higher(ImageF32 &targetHeight, const ImageF32 &sourceHeight, ImageRgbaU8 &targetA, const ImageRgbaU8 &sourceA, int32_t left = 0, int32_t top = 0, float sourceHeightOffset = 0.0f) {
+	dfpsr_image th = targetHeight.pod(), sh = sourceHeight.pod(), ta = targetA.pod(), sa = sourceA.pod();
+	b200_check(dfpsr_draw_higher(&th, &sh, &ta, &sa, nullptr, nullptr, left, top, sourceHeightOffset, b200_stream())); targetHeight.touchedByDevice(); targetA.touchedByDevice();
+}
+inline void draw_higher(ImageF32 &targetHeight, const ImageF32 &sourceHeight, ImageRgbaU8 &targetA, const ImageRgbaU8 &sourceA, ImageRgbaU8 &targetB, const ImageRgbaU8 &sourceB, int32_t left = 0, int32_t top = 0, float sourceHeightOffset = 0.0f) {
+	dfpsr_image th = targetHeight.pod(), sh = sourceHeight.pod(), ta = targetA.pod(), sa = sourceA.pod(), tb = targetB.pod(), sb = sourceB.pod();
+	b200_check(dfpsr_draw_higher(&th, &sh, &ta, &sa, &tb, &sb, left, top, sourceHeightOffset, b200_stream())); targetHeight.touchedByDevice(); targetA.touchedByDevice(); targetB.touchedByDevice();
+}
+
+// ---------------------------------------------------------------- Sandbox deferred light (ref: SDK/SpriteEngine/lightAPI.h:27-31, orthoAPI.h:52-77)
+struct OrthoView { dfpsr_ortho_view pod{}; };
+inline void b200_light_directed(const OrthoView &view, ImageRgbaU8 &lightBuffer, const ImageRgbaU8 &normalBuffer, const FVector3D &lightDirection, float lightIntensity, const ColorRgbaI32 &lightColor, int add) {
+	dfpsr_image l = lightBuffer.pod(), n = normalBuffer.pod();
+	float d[3] = {lightDirection.x, lightDirection.y, lightDirection.z};
+	int32_t c[3] = {lightColor.red, lightColor.green, lightColor.blue};
+	b200_check(dfpsr_light_directed(&view.pod, &l, &n, d, lightIntensity, c, add, b200_stream())); lightBuffer.touchedByDevice();
+}
+inline void setDirectedLight(const OrthoView &camera, ImageRgbaU8 &lightBuffer, const ImageRgbaU8 &normalBuffer, const FVector3D &lightDirection, float lightIntensity, const ColorRgbaI32 &lightColor) { b200_light_directed(camera, lightBuffer, normalBuffer, lightDirection, lightIntensity, lightColor, 0); }
+inline void addDirectedLight(const OrthoView &camera, ImageRgbaU8 &lightBuffer, const ImageRgbaU8 &normalBuffer, const FVector3D &lightDirection, float lightIntensity, const ColorRgbaI32 &lightColor) { b200_light_directed(camera, lightBuffer, normalBuffer, lightDirection, lightIntensity, lightColor, 1); }
+inline void addPointLight(const OrthoView &camera, int32_t worldCenterX, int32_t worldCenterY, ImageRgbaU8 &lightBuffer, const ImageRgbaU8 &normalBuffer, const ImageF32 &heightBuffer, const FVector3D &lightPosition, float lightRadius, float lightIntensity, const ColorRgbaI32 &lightColor, const ImageF32 &shadowCubeMap = ImageF32()) {
+	dfpsr_image l = lightBuffer.pod(), n = normalBuffer.pod(), h = heightBuffer.pod(), cube = shadowCubeMap.pod();
+	float p[3] = {lightPosition.x, lightPosition.y, lightPosition.z};
+	int32_t c[3] = {lightColor.red, lightColor.green, lightColor.blue}, wc[2] = {worldCenterX, worldCenterY};
+	b200_check(dfpsr_light_point(&camera.pod, wc, &l, &n, &h, p, lightRadius, lightIntensity, c, image_exists(shadowCubeMap) ? &cube : nullptr, b200_stream())); lightBuffer.touchedByDevice();
+}
+inline void blendLight(ImageRgbaU8 &colorBuffer, const ImageRgbaU8 &diffuseBuffer, const ImageRgbaU8 &lightBuffer) {
+	dfpsr_image c = colorBuffer.pod(), d = diffuseBuffer.pod(), l = lightBuffer.pod();
+	b200_check(dfpsr_light_blend(&c, &d, &l, b200_stream())); colorBuffer.touchedByDevice();
+}
+
+// ---------------------------------------------------------------- filters (ref: api/filterAPI.h:41-79)
+inline ImageRgbaU8 filter_resize(const ImageRgbaU8 &source, Sampler interpolation, int32_t newWidth, int32_t newHeight) {
+	if (!image_exists(source)) { return ImageRgbaU8(); } // ref: api/filterAPI.cpp:852-860
+	ImageRgbaU8 result = b200_image_create<uint32_t>(newWidth, newHeight, PackOrderIndex::RGBA);
+	size_t need = dfpsr_filter_resize_scratch_bytes(source.width, source.height, newWidth, newHeight);
+	std::unique_ptr<B200Buffer> scratch(need > 0 ? new B200Buffer(need) : nullptr);
+	dfpsr_image t = result.pod(), s = source.pod();
+	b200_check(dfpsr_filter_resize(&t, &s, (int32_t)interpolation, source.subImage ? 1 : 0, scratch ? scratch->device : nullptr, b200_stream()));
+	if (scratch) { b200_check(dfpsr_stream_synchronize(b200_stream())); }
+	result.touchedByDevice();
+	return result;
+}
+// The reference takes a host lambda per pixel (api/filterAPI.h:54-59), which a device cannot call; the shim exposes the enumerated device ops.
+inline void filter_mapRgbaU8(ImageRgbaU8 &target, int32_t deviceOp, const int32_t *params, int32_t paramCount, const ImageRgbaU8 &source = ImageRgbaU8(), int32_t startX = 0, int32_t startY = 0) {
+	dfpsr_image t = target.pod(), s = source.pod();
+	b200_check(dfpsr_filter_map(&t, deviceOp, params, paramCount, image_exists(source) ? &s : nullptr, startX, startY, b200_stream())); target.touchedByDevice();
+}
+inline void filter_blockMagnify(ImageRgbaU8 &target, const ImageRgbaU8 &source, int32_t pixelWidth, int32_t pixelHeight) {
+	dfpsr_image t = target.pod(), s = source.pod();
+	b200_check(dfpsr_filter_block_magnify(&t, &s, pixelWidth, pixelHeight, b200_stream())); target.touchedByDevice();
+}
+
+} // namespace dsr

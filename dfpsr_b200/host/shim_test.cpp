@@ -1,0 +1,127 @@
+// shim_test.cpp — drives the rendering hot path through DFPSR's own C++ API names (dsr_b200.h), the way
+// SDK/terrain/main.cpp:383-433 and the reference's test programs (test/tests/*Test.cpp) do. Used by tests/test_gpu_shim.py:
+//   shim_test <scene.bin> <out.bin>   renders the scene the Python test wrote, twice (renderer_begin/giveTask/end and model_render),
+//                                     checks the API's state machine and writes colour + depth for comparison with the oracle.
+#include "dsr_b200.h"
+
+#include <cstdio>
+#include <cstdlib>
+
+using namespace dsr;
+
+#define ASSERT(cond) do { if (!(cond)) { std::fprintf(stderr, "ASSERT failed at %s:%d: %s\n", __FILE__, __LINE__, #cond); std::exit(2); } } while (0)
+#define ASSERT_THROWS(stmt, text) do { bool thrown_ = false; try { stmt; } catch (const std::exception &e) { thrown_ = std::string(e.what()).find(text) != std::string::npos; } \
+	if (!thrown_) { std::fprintf(stderr, "expected an error containing \"%s\" at %s:%d\n", text, __FILE__, __LINE__); std::exit(2); } } while (0)
+
+struct SceneHeader { int32_t width, height, pointCount, polygonCount, textureWidth, textureHeight, textureLevels, filter, perspective; float location[12]; float widthSlope; };
+
+template <typename T> static std::vector<T> readArray(FILE *f, size_t count) {
+	std::vector<T> v(count);
+	if (count > 0 && std::fread(v.data(), sizeof(T), count, f) != count) { std::fprintf(stderr, "short scene file\n"); std::exit(2); }
+	return v;
+}
+
+int main(int argc, char **argv) {
+	if (argc < 3) { std::fprintf(stderr, "usage: shim_test scene.bin out.bin\n"); return 2; }
+	FILE *f = std::fopen(argv[1], "rb");
+	ASSERT(f != nullptr);
+	SceneHeader h;
+	ASSERT(std::fread(&h, sizeof(h), 1, f) == 1);
+	std::vector<float> points = readArray<float>(f, (size_t)h.pointCount * 3);
+	std::vector<dfpsr_polygon> polygons = readArray<dfpsr_polygon>(f, (size_t)h.polygonCount);
+	std::vector<uint32_t> texels = readArray<uint32_t>(f, (size_t)h.textureWidth * h.textureHeight);
+	std::fclose(f);
+
+	b200_init(0);
+
+	// texture_create_RgbaU8 + upload of level 0 + texture_generatePyramid (ref: SDK/terrain/main.cpp:370, api/textureAPI.cpp:65-87)
+	TextureRgbaU8 diffuse;
+	if (h.textureWidth > 0) {
+		diffuse = texture_create_RgbaU8(h.textureWidth, h.textureHeight, h.textureLevels);
+		ImageRgbaU8 level0 = texture_getMipLevelImage(diffuse, 0);
+		ASSERT(image_getWidth(level0) == h.textureWidth && image_getHeight(level0) == h.textureHeight);
+		image_upload(level0, texels.data(), h.textureWidth * 4);
+		texture_generatePyramid(diffuse);
+		ASSERT(texture_getMaxWidth(diffuse) == h.textureWidth && texture_getSmallestMipLevel(diffuse) <= h.textureLevels - 1);
+	}
+
+	// the model, through the model_* calls (ref: api/modelAPI.h:62-258)
+	Model model = model_create();
+	ASSERT(model_exists(model));
+	model_setFilter(model, h.filter ? Filter::Alpha : Filter::Solid);
+	int32_t part = model_addEmptyPart(model, "part");
+	ASSERT(part == 0 && model_getNumberOfParts(model) == 1);
+	for (int32_t i = 0; i < h.pointCount; i++) { ASSERT(model_addPoint(model, FVector3D(points[3 * i], points[3 * i + 1], points[3 * i + 2])) == i); }
+	for (int32_t i = 0; i < h.polygonCount; i++) {
+		const dfpsr_polygon &p = polygons[(size_t)i];
+		int32_t index = p.pointIndices[3] < 0 ? model_addTriangle(model, part, p.pointIndices[0], p.pointIndices[1], p.pointIndices[2])
+		                                      : model_addQuad(model, part, p.pointIndices[0], p.pointIndices[1], p.pointIndices[2], p.pointIndices[3]);
+		ASSERT(index == i);
+		for (int v = 0; v < 4; v++) {
+			model_setVertexColor(model, part, index, v, FVector4D(p.colors[v][0], p.colors[v][1], p.colors[v][2], p.colors[v][3]));
+			model_setTexCoord(model, part, index, v, FVector4D(p.texCoords[v][0], p.texCoords[v][1], p.texCoords[v][2], p.texCoords[v][3]));
+		}
+	}
+	ASSERT(model_getNumberOfPolygons(model, part) == h.polygonCount && model_getNumberOfPoints(model) == h.pointCount);
+	model_setDiffuseMap(model, part, diffuse);
+	ASSERT(model_addTriangle(model, 7, 0, 1, 2) == -1); // out-of-range part: reported, nothing added (ref: Model.cpp:34-42)
+
+	Transform3D location(FVector3D(h.location[0], h.location[1], h.location[2]),
+	                     FMatrix3x3(FVector3D(h.location[3], h.location[4], h.location[5]), FVector3D(h.location[6], h.location[7], h.location[8]), FVector3D(h.location[9], h.location[10], h.location[11])));
+	Camera camera = h.perspective ? Camera::createPerspective(location, (float)h.width, (float)h.height, h.widthSlope) : Camera::createOrthogonal(location, (float)h.width, (float)h.height, h.widthSlope);
+
+	// ---- one frame as SDK/terrain/main.cpp:397-421 does it
+	ImageRgbaU8 colorBuffer = image_create_RgbaU8(h.width, h.height);
+	ImageF32 depthBuffer = image_create_F32(h.width, h.height);
+	Renderer worker = renderer_create();
+	ASSERT(renderer_exists(worker) && !renderer_takesTriangles(worker));
+	ASSERT_THROWS(renderer_end(worker), "without renderer_begin");
+	image_fill(colorBuffer, ColorRgbaI32(0, 0, 0, 0));
+	image_fill(depthBuffer, h.perspective ? 0.0f : 1.0e9f);
+	renderer_begin(worker, colorBuffer, depthBuffer);
+	ASSERT(renderer_takesTriangles(worker));
+	ASSERT_THROWS(renderer_begin(worker, colorBuffer, depthBuffer), "twice");
+	renderer_giveTask(worker, model, Transform3D(), camera);
+	renderer_end(worker);
+	ASSERT(!renderer_takesTriangles(worker) && !image_exists(renderer_getColorBuffer(worker)));
+
+	// ---- the same frame through model_render into a second pair of images: identical pixels
+	ImageRgbaU8 color2 = image_create_RgbaU8(h.width, h.height);
+	ImageF32 depth2 = image_create_F32(h.width, h.height);
+	image_fill(depth2, h.perspective ? 0.0f : 1.0e9f);
+	model_render(model, Transform3D(), color2, depth2, camera);
+	std::vector<uint32_t> c1((size_t)h.width * h.height), c2(c1.size());
+	std::vector<float> d1(c1.size()), d2(c1.size());
+	image_download(colorBuffer, c1.data(), h.width * 4); image_download(color2, c2.data(), h.width * 4);
+	image_download(depthBuffer, d1.data(), h.width * 4); image_download(depth2, d2.data(), h.width * 4);
+	ASSERT(std::memcmp(c1.data(), c2.data(), c1.size() * 4) == 0);
+	ASSERT(std::memcmp(d1.data(), d2.data(), d1.size() * 4) == 0);
+
+	// ---- pixel reads and sub-images behave like the reference's handles (ref: api/imageAPI.h:207-341, Image.h:186-206)
+	int32_t mx = h.width / 2, my = h.height / 2;
+	ColorRgbaI32 centre = image_readPixel_clamp(colorBuffer, mx, my);
+	uint32_t packed = c1[(size_t)my * h.width + mx];
+	ASSERT(centre.red == (int32_t)(packed & 255u) && centre.alpha == (int32_t)(packed >> 24));
+	ASSERT(image_readPixel_clamp(depthBuffer, -5, my) == d1[(size_t)my * h.width]);
+	ImageRgbaU8 sub = image_getSubImage(colorBuffer, mx / 2, my / 2, mx, my);
+	ASSERT(image_isSubImage(sub) && image_getWidth(sub) == mx && image_getStride(sub) == image_getStride(colorBuffer));
+	ColorRgbaI32 viaSub = image_readPixel_clamp(sub, mx - mx / 2, my - my / 2);
+	ASSERT(viaSub.red == centre.red && viaSub.green == centre.green && viaSub.blue == centre.blue);
+	ASSERT(!image_exists(image_getSubImage(colorBuffer, 1, 1, h.width, h.height)));
+	// model_renderDepth into a depth-only target equals the depth of a colourless render where nothing is alpha filtered
+	ImageF32 depth3 = image_create_F32(h.width, h.height);
+	image_fill(depth3, h.perspective ? 0.0f : 1.0e9f);
+	ImageRgbaU8 none;
+	model_render(model, Transform3D(), none, depth3, camera);
+	std::vector<float> d3(c1.size());
+	image_download(depth3, d3.data(), h.width * 4);
+	if (!h.filter) { ASSERT(std::memcmp(d1.data(), d3.data(), d1.size() * 4) == 0); }
+
+	FILE *out = std::fopen(argv[2], "wb");
+	ASSERT(out != nullptr);
+	std::fwrite(c1.data(), 4, c1.size(), out);
+	std::fwrite(d1.data(), 4, d1.size(), out);
+	std::fclose(out);
+	std::printf("shim_test ok: %d polygons, %dx%d\n", h.polygonCount, h.width, h.height);
+	return 0;
+}

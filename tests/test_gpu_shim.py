@@ -1,0 +1,73 @@
+"""The C++14 host shim (dfpsr_b200/host/dsr_b200.h): DFPSR's own API names over the C ABI. The C++ test program renders a scene
+through renderer_begin/giveTask/end and model_render exactly like SDK/terrain/main.cpp does; its pixels must equal the oracle's."""
+import ctypes as C
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+import orcbind
+from dfpsr_b200 import abi, scenes
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "dfpsr_b200", "host", "shim_test")
+
+
+def write_scene(path, w, h, points, polygons, texture, levels, filt, cam_params):
+    loc = cam_params.location
+    header = struct.pack("<9i12ff", w, h, len(points), len(polygons), texture.shape[1] if texture is not None else 0, texture.shape[0] if texture is not None else 0,
+                         levels, filt, cam_params.perspective, *loc.position, *loc.xAxis, *loc.yAxis, *loc.zAxis, cam_params.widthSlope)
+    with open(path, "wb") as f:
+        f.write(header)
+        f.write(np.ascontiguousarray(points, np.float32).tobytes())
+        f.write(np.ascontiguousarray(polygons).tobytes())
+        if texture is not None:
+            f.write(np.ascontiguousarray(texture, np.uint32).tobytes())
+
+
+def test_shim_program_is_built():
+    assert os.path.exists(EXE), "run `make -C dfpsr_b200/host` (done by __graft_entry__.build())"
+
+
+def test_shim_fails_loudly_without_a_gpu(tmp_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    sc = scenes.random_soup(4, 1)
+    cam = abi.camera_params(True, scenes.look_at_transform((0, 0, -3), (0, 0, 0)), 32, 32)
+    write_scene(tmp_path / "scene.bin", 32, 32, sc["points"], sc["polygons"], None, 1, 0, cam)
+    out = subprocess.run([EXE, str(tmp_path / "scene.bin"), str(tmp_path / "out.bin")], capture_output=True, text=True)
+    assert out.returncode != 0
+    assert "no CUDA device" in out.stderr or "no CUDA device" in out.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["terrain", "soup_alpha", "soup_ortho"])
+def test_shim_frame_matches_oracle(cuda, oracle, tmp_path, kind):
+    if kind == "terrain":
+        sc = scenes.terrain_scene()
+        w, h, points, polygons, texture, levels, filt = 640, 360, sc["points"], sc["polygons"], sc["texture"], 5, abi.FILTER_SOLID
+        cam = scenes.orbit_camera(12, w, h)
+    else:
+        alpha = kind == "soup_alpha"
+        soup = scenes.random_soup(200, 4, textured=True, alpha=alpha)
+        w, h, points, polygons, texture, levels = 322, 201, soup["points"], soup["polygons"], scenes.checker_texture(64, 2), 4
+        filt = abi.FILTER_ALPHA if alpha else abi.FILTER_SOLID
+        persp = kind != "soup_ortho"
+        cam = abi.camera_params(persp, scenes.look_at_transform((0.4, 0.2, -0.6), (0.1, -0.2, 2.0)), w, h, width_slope=1.0 if persp else 6.0)
+    write_scene(tmp_path / "scene.bin", w, h, points, polygons, texture, levels, filt, cam)
+    out = subprocess.run([EXE, str(tmp_path / "scene.bin"), str(tmp_path / "out.bin")], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr + out.stdout
+    raw = np.fromfile(tmp_path / "out.bin", np.uint32)
+    got_c, got_d = raw[: w * h].reshape(h, w), raw[w * h:].reshape(h, w)
+    buf, tex = orcbind.build_texture(texture, levels)
+    model, keep = orcbind.model_of(points, polygons, filt, tex)
+    ec = np.zeros((h, w), np.uint32)
+    ed = np.zeros((h, w), np.float32) if cam.perspective else np.full((h, w), 1e9, np.float32)
+    ident = abi.Transform3D.identity()
+    n = oracle.orc_model_render(C.byref(model), C.byref(ident), C.byref(orcbind.image_of(ec)), C.byref(orcbind.image_of(ed)), C.byref(orcbind.camera(cam)))
+    assert n > 20
+    assert np.array_equal(got_d, ed.view(np.uint32)), "depth"
+    assert np.array_equal(got_c, ec), "colour"

@@ -249,16 +249,19 @@ def main():
     profile = lib.profile_snapshot()
     total_kernel_ms = sum(ms for ms, _ in profile.values())
     raster_ms, raster_launches = profile.get("raster_kernel<false>", (0.0, 0))
-    raster_launches *= views  # one launch rasterises every view of the batch: per-frame figures
     peak, peak_source = load_peaks()
-    achieved = (ALGORITHMIC_BYTES_PER_FRAME / 1e9) / (raster_ms / 1000.0 / max(raster_launches, 1)) if raster_ms > 0 else 0.0
+    launch_bytes = ALGORITHMIC_BYTES_PER_FRAME * views  # one launch rasterises every view of the step
+    launch_us = 1000.0 * raster_ms / max(raster_launches, 1)
+    achieved = (launch_bytes / 1e9) / (launch_us / 1e6) if raster_ms > 0 else 0.0
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "kernel": "raster_kernel<false> (per 1080p frame of the batched launch)", "avg_launch_us": 1000.0 * raster_ms / max(raster_launches, 1),
-                "algorithmic_bytes_per_launch": ALGORITHMIC_BYTES_PER_FRAME, "peak_source": peak_source,
+                "kernel": "raster_kernel<false>", "avg_launch_us": launch_us, "frames_per_launch": views,
+                "algorithmic_bytes_per_launch": launch_bytes, "algorithmic_bytes_per_frame": ALGORITHMIC_BYTES_PER_FRAME, "peak_source": peak_source,
                 "kernel_share_of_device_time": raster_ms / total_kernel_ms if total_kernel_ms > 0 else None,
-                "per_kernel_us_per_frame": {k: 1000.0 * ms / views for k, (ms, n) in sorted(profile.items())}}
+                "per_kernel_us_per_frame": {k: 1000.0 * ms / views for k, (ms, n) in sorted(profile.items())},
+                "note": "the tile kernel is instruction-issue bound (bit-exact shading), not HBM bound: see DESIGN.md section 6 and profiles/"}
 
-    # ---- end to end through the host-buffer entry point: pinned host geometry in, finished colour image out, every frame
+    # ---- end to end through the host-buffer entry point: every step uploads the geometry and the step's cameras from pinned host
+    # memory and brings every finished colour image back to pinned host memory; rendering of chunk k+1 overlaps the copy of chunk k
     session = C.c_void_p()
     lib.check(cuda.dfpsr_session_create(C.byref(session)))
     pts_host = torch.from_numpy(np.ascontiguousarray(sc["points"], np.float32)).pin_memory()
@@ -272,17 +275,17 @@ def main():
     hm.minBound[:], hm.maxBound[:] = model.desc.minBound[:], model.desc.maxBound[:]
     slot = C.c_int32()
     lib.check(cuda.dfpsr_session_upload_model(session, C.byref(hm), C.byref(slot)))
-    color_host = torch.empty((HEIGHT, WIDTH), dtype=torch.int32).pin_memory()
-    e2e_views = min(views, 64)
+    e2e_views = views
+    color_host = torch.empty((e2e_views, HEIGHT, WIDTH), dtype=torch.int32).pin_memory()
+    host_ptrs = (C.c_void_p * e2e_views)(*[color_host[v].data_ptr() for v in range(e2e_views)])
 
     def e2e_step():
-        for v in range(e2e_views):
-            lib.check(cuda.dfpsr_session_render_frame_host(session, slot.value, C.byref(ident), C.byref(cameras[v]), color_host.data_ptr(), WIDTH * 4, None, 0, WIDTH, HEIGHT, abi.PACK_RGBA, 1, sp))
+        lib.check(cuda.dfpsr_session_render_views_host(session, slot.value, C.byref(ident), cameras, e2e_views, host_ptrs, WIDTH * 4, None, 0, WIDTH, HEIGHT, abi.PACK_RGBA, 1, sp))
 
     e2e_step()
     barrier()
     t0 = time.perf_counter()
-    e2e_steps = max(args.steps // 2, 1)
+    e2e_steps = max(args.steps, 1)
     for _ in range(e2e_steps):
         e2e_step()
     barrier()
@@ -290,10 +293,12 @@ def main():
     if distributed:
         dist.all_reduce(e2e_elapsed, op=dist.ReduceOp.MAX)
     e2e_fps = world * e2e_views * e2e_steps / float(e2e_elapsed.item())
+    e2e_checksum = int(color_host[0].to(torch.int64).sum().item()) & 0xFFFFFFFF
     lib.check(cuda.dfpsr_session_destroy(session))
-    h2d_per_frame = len(sc["points"]) * 12 + len(sc["polygons"]) * 144 + C.sizeof(abi.Camera) + C.sizeof(abi.Transform3D)
-    e2e = {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d_per_frame * e2e_views, "d2h_bytes_per_step": WIDTH * HEIGHT * 4 * e2e_views,
-           "views_per_step": e2e_views, "note": "per frame: geometry upload from pinned host memory, fused clear+render, colour image download to pinned host memory, stream sync"}
+    h2d_per_step = len(sc["points"]) * 12 + len(sc["polygons"]) * 144 + e2e_views * (C.sizeof(abi.Camera) + C.sizeof(abi.Transform3D))
+    e2e = {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d_per_step, "d2h_bytes_per_step": WIDTH * HEIGHT * 4 * e2e_views,
+           "views_per_step": e2e_views, "first_view_checksum": e2e_checksum,
+           "note": "dfpsr_session_render_views_host: per step the geometry and cameras come from pinned host memory and every finished 1080p colour image goes back to pinned host memory (PCIe-bound); 16-view chunks, copy of chunk k overlaps rendering of chunk k+1"}
 
     extras = None
     if rank == 0 and not args.no_extras:

@@ -723,6 +723,14 @@ __global__ void __launch_bounds__(256) tile_alloc_kernel(FrameDev frame) {
 	}
 }
 
+// The frame's counters go to the host through mapped pinned memory written by this kernel, not through a device-to-host copy: a copy
+// would queue on the copy engine behind megabytes of finished frames travelling to the host (dfpsr_session_render_views_host) and
+// stall the next chunk's set-up for milliseconds.
+__global__ void publish_totals_kernel(const uint32_t *__restrict__ totals, volatile uint32_t *hostTotals) {
+	if (threadIdx.x < 4) { hostTotals[threadIdx.x] = totals[threadIdx.x]; }
+	__threadfence_system();
+}
+
 // Restores ascending command order in the lists that hold more than 32 entries (shorter ones are sorted in registers by raster_kernel).
 __global__ void __launch_bounds__(SORT_THREADS) sort_lists_kernel(FrameDev frame) {
 	__shared__ uint32_t s[SORT_SMEM];
@@ -877,10 +885,12 @@ __device__ __forceinline__ uint32_t warp_sort(uint32_t key, int lane) {
 template <bool DEPTH_ONLY>
 __global__ void __launch_bounds__(RASTER_WARPS * 32) raster_kernel(FrameDev frame, TexTable textures) {
 	__shared__ __align__(16) Rec sRecAll[RASTER_WARPS][32];
+	__shared__ __align__(16) uint32_t sMaskAll[RASTER_WARPS][32]; // per (row pair, command): which of the 16 quads of the row pair the command may touch
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const uint32_t tile = blockIdx.x * RASTER_WARPS + warp;
 	if (tile >= frame.tileTotal) { return; }
 	Rec *sRec = sRecAll[warp];
+	uint32_t *sMask = sMaskAll[warp];
 
 	const ViewDev &vw = frame.views[frame.viewCount > 1 ? find_view(frame.views, frame.viewCount, tile) : 0u];
 	const int32_t tilesX = vw.tilesX;
@@ -934,6 +944,7 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32) raster_kernel(FrameDev fram
 		{
 			Rec rec;
 			rec.mode = -1; rec.at = 0; rec.ul = rec.ur = rec.ll = rec.lr = 0;
+			int32_t quadFirst = 0, quadEnd = 0; // quads [quadFirst, quadEnd) of this row pair can be touched
 			if (c < batchCount) {
 				const Cmd *cmd = frame.cmds + key;
 				const int4 head = __ldg((const int4 *)cmd + 3); // rowStart, rowCount, rowOffset, pad
@@ -956,6 +967,8 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32) raster_kernel(FrameDev fram
 						const bool hasL = rec.lr > rec.ll && rec.lr > tileLeft && rec.ll < tileLeft + TILE_W && yTop + 1 < height;
 						if (hasU || hasL) {
 							rec.mode = 3;
+							const int32_t lo = min(hasU ? rec.ul : 0x7FFFFFFF, hasL ? rec.ll : 0x7FFFFFFF), hi = max(hasU ? rec.ur : -1, hasL ? rec.lr : -1);
+							quadFirst = (max(lo, tileLeft) - tileLeft) >> 1; quadEnd = (min(hi, tileLeft + TILE_W) - tileLeft + 1) >> 1;
 							float vu = (start[0] + (dx[0] * ((float)rec.ul + 0.5f))) + (dy[0] * ((float)yTop + 0.5f));
 							float vl = (start[0] + (dx[0] * ((float)rec.ll + 0.5f))) + (dy[0] * ((float)(yTop + 1) + 0.5f));
 							if (hasU) { for (int32_t s = rec.ul; s < tileLeft; s++) { vu += dx[0]; } }
@@ -981,6 +994,7 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32) raster_kernel(FrameDev fram
 							const int32_t at = max(obs, tileLeft);
 							const bool noInner = ibe <= ibs;
 							rec.at = at;
+							quadFirst = (at - tileLeft) >> 1; quadEnd = (min(obe, tileLeft + TILE_W) - tileLeft) >> 1;
 							if (noInner || at <= ibs) {
 								for (int32_t s = obs; s < at; s += 2) {
 #pragma unroll
@@ -1035,20 +1049,30 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32) raster_kernel(FrameDev fram
 			const uint4 *src = (const uint4 *)&rec;
 #pragma unroll
 			for (int w = 0; w < 6; w++) { dst[w] = src[w]; }
+			sMask[r * BATCH + c] = (rec.mode >= 0 && quadEnd > quadFirst) ? ((0xFFFFFFFFu >> (32 - quadEnd)) & ~((1u << quadFirst) - 1u)) : 0u;
 		}
 		__syncwarp();
-		// which commands of the batch touch this tile at all (either row pair)
-		const bool mine = sRec[r * BATCH + c].mode >= 0;
-		const uint32_t touched = __ballot_sync(0xffffffffu, mine);
-		uint32_t pending = (touched | (touched >> 16)) & 0xFFFFu & ((1u << batchCount) - 1u);
+		// Every lane collects the commands of the batch that may touch ITS quad and works through them in submission order. Lanes are
+		// independent (a pixel only depends on the commands that cover it), so lanes covered by different triangles shade at the same
+		// time instead of idling through each other's commands: the warp needs as many rounds as its busiest quad has commands.
+		uint32_t cover = 0;
+		{
+			const uint4 *masks = (const uint4 *)(sMask + qy * BATCH);
+#pragma unroll
+			for (int w = 0; w < BATCH / 4; w++) {
+				const uint4 m = masks[w];
+				cover |= ((m.x >> qx) & 1u) << (4 * w) | ((m.y >> qx) & 1u) << (4 * w + 1) | ((m.z >> qx) & 1u) << (4 * w + 2) | ((m.w >> qx) & 1u) << (4 * w + 3);
+			}
+		}
 
-		while (pending != 0u) {
-			const uint32_t ci = (uint32_t)__ffs((int)pending) - 1u;
-			pending &= pending - 1u;
+		while (__any_sync(0xffffffffu, cover != 0u)) {
+			const bool busy = cover != 0u;
+			const uint32_t ci = busy ? (uint32_t)__ffs((int)cover) - 1u : 0u;
+			cover &= cover - 1u;
 			const uint32_t cmdKey = __shfl_sync(0xffffffffu, key, (int)ci);
+			if (!busy) { continue; }
 			const Rec &rec = sRec[(uint32_t)qy * BATCH + ci];
 			const int32_t mode = rec.mode;
-			if (mode < 0) { continue; }
 			const Cmd &cmd = frame.cmds[cmdKey];
 			int2 upperRow = make_int2(rec.ul, rec.ur), lowerRow = make_int2(rec.ll, rec.lr);
 			const uint32_t flags = __ldg(&cmd.flags);
@@ -1272,7 +1296,7 @@ struct dfpsr_renderer {
 	int textureCount = 0;
 	int64_t lastCommands = -1;
 	DeviceBuffer dTasks, dViews, projected, slotCounts, blockCmds, blockRows, tileCount, tileOffset, tileCursor, cmds, rows, tileList, sortTmp;
-	uint32_t *hostTotals = nullptr; // pinned
+	uint32_t *hostTotals = nullptr, *hostTotalsDevice = nullptr; // mapped pinned memory and its device alias
 
 	~dfpsr_renderer() {
 		for (auto &b : uploads) { b.release(); }
@@ -1322,7 +1346,10 @@ static int renderer_begin_internal(dfpsr_renderer *r, bool depthOnly) {
 	r->tasks.clear();
 	r->uploadCount = 0;
 	r->textureCount = 0;
-	if (!r->hostTotals) { DFPSR_CHECK_CUDA(cudaMallocHost((void **)&r->hostTotals, 8 * sizeof(uint32_t))); }
+	if (!r->hostTotals) {
+		DFPSR_CHECK_CUDA(cudaHostAlloc((void **)&r->hostTotals, 8 * sizeof(uint32_t), cudaHostAllocMapped));
+		DFPSR_CHECK_CUDA(cudaHostGetDevicePointer((void **)&r->hostTotalsDevice, r->hostTotals, 0));
+	}
 	return 0;
 }
 
@@ -1412,7 +1439,7 @@ static int renderer_end_internal(dfpsr_renderer *r, cudaStream_t stream) {
 		DFPSR_LAUNCH(setup_kernel<false>, blockTotal, SETUP_THREADS, 0, stream, frame);
 		DFPSR_LAUNCH(scan_blocks_kernel, 1, 1024, 0, stream, frame);
 		DFPSR_LAUNCH(tile_alloc_kernel, (tileTotal + 255) / 256, 256, 0, stream, frame);
-		DFPSR_CHECK_CUDA(cudaMemcpyAsync(r->hostTotals, frame.totals, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+		DFPSR_LAUNCH(publish_totals_kernel, 1, 32, 0, stream, frame.totals, r->hostTotalsDevice);
 		DFPSR_CHECK_CUDA(cudaStreamSynchronize(stream));
 		const uint32_t commandTotal = r->hostTotals[0], rowTotal = r->hostTotals[1], entryTotal = r->hostTotals[2], maxTile = r->hostTotals[3];
 		r->lastCommands = commandTotal;

@@ -3,6 +3,7 @@
 // the render targets so that a frame only moves what changed (geometry on request, the finished colour/depth out).
 #include "common.cuh"
 
+#include <stdlib.h>
 #include <vector>
 #include <new>
 
@@ -18,11 +19,23 @@ struct ModelSlot {
 
 } // namespace
 
+static const int PIPELINE_CHUNK = 16; // views rendered per submission while the previous chunk is copied to the host
+
 struct dfpsr_session {
 	std::vector<ModelSlot *> models;
 	dfpsr_renderer *renderer = nullptr;
 	DeviceBuffer color, depth;
+	// double-buffered targets of dfpsr_session_render_views_host
+	DeviceBuffer chunkColor[2], chunkDepth[2];
+	cudaStream_t copyStream = nullptr;
+	cudaEvent_t rendered[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr};
 	~dfpsr_session() {
+		for (int b = 0; b < 2; b++) {
+			chunkColor[b].release(); chunkDepth[b].release();
+			if (rendered[b]) { cudaEventDestroy(rendered[b]); }
+			if (copied[b]) { cudaEventDestroy(copied[b]); }
+		}
+		if (copyStream) { cudaStreamDestroy(copyStream); }
 		for (ModelSlot *m : models) {
 			m->points.release(); m->polygons.release(); m->diffuse.release(); m->light.release();
 			delete m;
@@ -99,6 +112,65 @@ int dfpsr_session_render_frame_host(dfpsr_session *session, int32_t slot, const 
 	if (dfpsr_renderer_end(session->renderer, stream)) { return 1; }
 	if (colorHost != nullptr) { DFPSR_CHECK_CUDA(cudaMemcpy2DAsync(colorHost, (size_t)colorStride, color.data, (size_t)pitch, (size_t)width * 4, (size_t)height, cudaMemcpyDeviceToHost, s)); }
 	if (depthHost != nullptr) { DFPSR_CHECK_CUDA(cudaMemcpy2DAsync(depthHost, (size_t)depthStride, depth.data, (size_t)pitch, (size_t)width * 4, (size_t)height, cudaMemcpyDeviceToHost, s)); }
+	DFPSR_CHECK_CUDA(cudaStreamSynchronize(s));
+	return 0;
+}
+
+// Many views of one model with HOST targets (BASELINE config 4 end to end): views are rendered PIPELINE_CHUNK at a time into one of two
+// device buffer sets while the previous chunk travels to the host on a second stream, so the PCIe copy of frame i overlaps the
+// rasterisation of frame i + 1. Host images should be pinned (dfpsr_malloc_host) for the copies to be asynchronous.
+int dfpsr_session_render_views_host(dfpsr_session *session, int32_t slot, const dfpsr_transform3d *modelToWorld, const dfpsr_camera *cameras, int32_t count, uint32_t *const *colorHost, int32_t colorStride, float *const *depthHost, int32_t depthStride, int32_t width, int32_t height, int32_t packOrder, int32_t uploadGeometry, void *stream) {
+	DFPSR_REQUIRE(session != nullptr && modelToWorld != nullptr && cameras != nullptr, "session_render_views_host: null argument");
+	DFPSR_REQUIRE(slot >= 0 && slot < (int32_t)session->models.size(), "session_render_views_host: model slot %d does not exist", slot);
+	DFPSR_REQUIRE(width > 0 && height > 0, "session_render_views_host: empty target");
+	if (count <= 0) { return 0; }
+	cudaStream_t s = as_stream(stream);
+	ModelSlot *m = session->models[slot];
+	if (!session->copyStream) {
+		DFPSR_CHECK_CUDA(cudaStreamCreateWithFlags(&session->copyStream, cudaStreamNonBlocking));
+		for (int b = 0; b < 2; b++) {
+			DFPSR_CHECK_CUDA(cudaEventCreateWithFlags(&session->rendered[b], cudaEventDisableTiming));
+			DFPSR_CHECK_CUDA(cudaEventCreateWithFlags(&session->copied[b], cudaEventDisableTiming));
+		}
+	}
+	if (uploadGeometry) {
+		DFPSR_CHECK_CUDA(cudaMemcpyAsync(m->points.ptr, m->host.points, (size_t)m->host.pointCount * 12, cudaMemcpyHostToDevice, s));
+		DFPSR_CHECK_CUDA(cudaMemcpyAsync(m->polygons.ptr, m->host.polygons, (size_t)m->host.polygonCount * sizeof(dfpsr_polygon), cudaMemcpyHostToDevice, s));
+	}
+	const int32_t pitch = ((width * 4 + 255) / 256) * 256;
+	const size_t frameBytes = (size_t)pitch * (size_t)height;
+	int32_t chunkLimit = PIPELINE_CHUNK;
+	if (const char *env = getenv("DFPSR_PIPELINE_CHUNK")) { int v = atoi(env); if (v > 0 && v <= 1024) { chunkLimit = v; } } // tuning knob
+	const int32_t chunk = count < chunkLimit ? count : chunkLimit;
+	for (int b = 0; b < 2; b++) {
+		if (session->chunkColor[b].reserve(frameBytes * chunk) || session->chunkDepth[b].reserve(frameBytes * chunk)) { return 1; }
+	}
+	std::vector<dfpsr_image> colors((size_t)chunk), depths((size_t)chunk);
+	int32_t chunkIndex = 0;
+	for (int32_t first = 0; first < count; first += chunk, chunkIndex++) {
+		const int b = chunkIndex & 1;
+		const int32_t n = count - first < chunk ? count - first : chunk;
+		if (chunkIndex >= 2) { DFPSR_CHECK_CUDA(cudaStreamWaitEvent(s, session->copied[b], 0)); } // the buffer set is free again
+		for (int32_t v = 0; v < n; v++) {
+			colors[(size_t)v] = dfpsr_image{(uint8_t *)session->chunkColor[b].ptr + frameBytes * v, width, height, pitch, packOrder};
+			depths[(size_t)v] = dfpsr_image{(uint8_t *)session->chunkDepth[b].ptr + frameBytes * v, width, height, pitch, 0};
+		}
+		if (dfpsr_model_render_views(&m->device, modelToWorld, colors.data(), depths.data(), cameras + first, n, 1, stream)) { return 1; }
+		DFPSR_CHECK_CUDA(cudaEventRecord(session->rendered[b], s));
+		DFPSR_CHECK_CUDA(cudaStreamWaitEvent(session->copyStream, session->rendered[b], 0));
+		for (int32_t v = 0; v < n; v++) {
+			if (colorHost != nullptr && colorHost[first + v] != nullptr) {
+				if (colorStride == pitch && pitch == width * 4) { DFPSR_CHECK_CUDA(cudaMemcpyAsync(colorHost[first + v], colors[(size_t)v].data, frameBytes, cudaMemcpyDeviceToHost, session->copyStream)); }
+				else { DFPSR_CHECK_CUDA(cudaMemcpy2DAsync(colorHost[first + v], (size_t)colorStride, colors[(size_t)v].data, (size_t)pitch, (size_t)width * 4, (size_t)height, cudaMemcpyDeviceToHost, session->copyStream)); }
+			}
+			if (depthHost != nullptr && depthHost[first + v] != nullptr) {
+				if (depthStride == pitch && pitch == width * 4) { DFPSR_CHECK_CUDA(cudaMemcpyAsync(depthHost[first + v], depths[(size_t)v].data, frameBytes, cudaMemcpyDeviceToHost, session->copyStream)); }
+				else { DFPSR_CHECK_CUDA(cudaMemcpy2DAsync(depthHost[first + v], (size_t)depthStride, depths[(size_t)v].data, (size_t)pitch, (size_t)width * 4, (size_t)height, cudaMemcpyDeviceToHost, session->copyStream)); }
+			}
+		}
+		DFPSR_CHECK_CUDA(cudaEventRecord(session->copied[b], session->copyStream));
+	}
+	DFPSR_CHECK_CUDA(cudaStreamSynchronize(session->copyStream));
 	DFPSR_CHECK_CUDA(cudaStreamSynchronize(s));
 	return 0;
 }

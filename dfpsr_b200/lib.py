@@ -71,6 +71,7 @@ SIGNATURES = {
     "dfpsr_session_create": (i32, [P(vp)]),
     "dfpsr_session_destroy": (i32, [vp]),
     "dfpsr_session_upload_model": (i32, [vp, P(abi.HostModel), P(i32)]),
+    "dfpsr_session_render_views_host": (i32, [vp, i32, P(abi.Transform3D), vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, vp]),
     "dfpsr_session_render_frame_host": (i32, [vp, i32, P(abi.Transform3D), P(abi.Camera), vp, i32, vp, i32, i32, i32, i32, i32, vp]),
 }
 

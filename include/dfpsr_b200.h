@@ -298,6 +298,11 @@ int dfpsr_session_upload_model(dfpsr_session *session, const dfpsr_host_model *m
  * into HOST buffers — one SDK terrain frame (ref: SDK/terrain/main.cpp:397-421). */
 int dfpsr_session_render_frame_host(dfpsr_session *session, int32_t slot, const dfpsr_transform3d *modelToWorld, const dfpsr_camera *camera, uint32_t *colorHost, int32_t colorStride, float *depthHost, int32_t depthStride, int32_t width, int32_t height, int32_t packOrder, int32_t uploadGeometry, void *stream);
 
+/* The same for `count` views of one model (BASELINE config 4 end to end): colorHost / depthHost are HOST arrays of `count` HOST image
+ * pointers (depthHost or single entries may be NULL). Rendering of the next chunk of views overlaps the device-to-host copy of the
+ * previous one; pinned host images (dfpsr_malloc_host) make the copies asynchronous. Returns after everything has arrived. */
+int dfpsr_session_render_views_host(dfpsr_session *session, int32_t slot, const dfpsr_transform3d *modelToWorld, const dfpsr_camera *cameras, int32_t count, uint32_t *const *colorHost, int32_t colorStride, float *const *depthHost, int32_t depthStride, int32_t width, int32_t height, int32_t packOrder, int32_t uploadGeometry, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -349,3 +349,40 @@ def test_thousands_of_triangles_on_one_tile(cuda, oracle):
     assert commands > 4500
     assert_same_u32(bits(got_d), bits(exp_d), "depth")
     assert_same_u32(got_c, exp_c, "colour")
+
+
+def test_session_render_views_host_pipeline(cuda, oracle):
+    """dfpsr_session_render_views_host: host geometry in, host images out, chunks of 16 views double-buffered (40 views = 3 chunks)."""
+    import torch
+    sc = scenes.terrain_scene()
+    texture = lib.DeviceTexture(sc["texture"], 5)
+    w, h, views = 160, 90, 40
+    pts = np.ascontiguousarray(sc["points"], np.float32)
+    poly = np.ascontiguousarray(sc["polygons"])
+    tex_host = texture.pixels.cpu()
+    hm = abi.HostModel()
+    hm.points, hm.pointCount = pts.ctypes.data, len(pts)
+    hm.polygons, hm.polygonCount = poly.ctypes.data, len(poly)
+    hm.filter = abi.FILTER_SOLID
+    hm.diffusePixels, hm.diffuseLayout = tex_host.data_ptr(), texture.desc
+    mn, mx = lib.model_bounds(pts)
+    hm.minBound[:], hm.maxBound[:] = mn, mx
+    session, slot = C.c_void_p(), C.c_int32()
+    lib.check(cuda.dfpsr_session_create(C.byref(session)))
+    lib.check(cuda.dfpsr_session_upload_model(session, C.byref(hm), C.byref(slot)))
+    cams = (abi.Camera * views)(*[lib.camera(scenes.orbit_camera(v, w, h, frames_per_lap=views)) for v in range(views)])
+    color = torch.zeros((views, h, w), dtype=torch.int32).pin_memory()
+    depth = torch.zeros((views, h, w), dtype=torch.float32).pin_memory()
+    cptr = (C.c_void_p * views)(*[color[v].data_ptr() for v in range(views)])
+    dptr = (C.c_void_p * views)(*[depth[v].data_ptr() for v in range(views)])
+    ident = abi.Transform3D.identity()
+    for _ in range(2):  # second call reuses the buffers and events
+        lib.check(cuda.dfpsr_session_render_views_host(session, slot.value, C.byref(ident), cams, views, cptr, w * 4, dptr, w * 4, w, h, abi.PACK_RGBA, 1, lib.stream_ptr()))
+    lib.check(cuda.dfpsr_session_destroy(session))
+    buf, otex = orcbind.build_texture(sc["texture"], 5)
+    omodel, keep = orcbind.model_of(pts, poly, diffuse=otex)
+    for v in (0, 15, 16, 31, 39):
+        ec, ed = np.zeros((h, w), np.uint32), np.zeros((h, w), np.float32)
+        oracle.orc_model_render(C.byref(omodel), C.byref(ident), C.byref(orcbind.image_of(ec)), C.byref(orcbind.image_of(ed)), C.byref(orcbind.camera(scenes.orbit_camera(v, w, h, frames_per_lap=views))))
+        assert_same_u32(color[v].numpy().view(np.uint32), ec, f"view {v} colour")
+        assert_same_u32(bits(depth[v].numpy()), bits(ed), f"view {v} depth")

@@ -30,7 +30,8 @@ def needs_build():
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources()
+    extra = os.environ.get("DFPSR_NVCC_EXTRA", "").split()  # tuning experiments, e.g. -DRASTER_MIN_BLOCKS=6
+    cmd = [NVCC] + FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources()
     subprocess.check_call(cmd)
     return LIB
 

@@ -32,8 +32,12 @@ static const int SMALL_WIDTH = 128;
 static const int SMALL_TILES = 8;          // counting pass: bounding boxes up to this many tiles are counted by the set-up thread
 static const int SETUP_THREADS = 256;
 static const int RASTER_WARPS = 4;
+#ifndef RASTER_MIN_BLOCKS
+#define RASTER_MIN_BLOCKS 8 // 64 registers: measured 50 us per 1080p terrain frame against 63 us at 128 registers (tools/variant_sweep.py)
+#endif
 static const int SORT_THREADS = 256;
-static const int SORT_SMEM = 4096;         // entries of one tile list sorted in shared memory; longer lists use the rank sort
+static const int SORT_SMEM = 4096;         // entries of one tile list sorted in shared memory by a CTA; longer lists use the rank sort
+static const int SORT_WARP = SORT_SMEM / (SORT_THREADS / 32); // lists up to this long are sorted by single warps
 
 struct PPoint { // == dfpsr_projected_point
 	float csx, csy, csz, isx, isy;
@@ -47,7 +51,8 @@ static_assert(sizeof(dfpsr_projected_point) == 40, "dfpsr_projected_point layout
 struct Cmd {
 	float start[3], dx[3], dy[3]; // Projection (ref: ITriangle2D.h:63-76)                        bytes   0..35
 	uint32_t flags;               // CMD_* | diffuse index << 8 | light index << 20                     36..39
-	int32_t bx0, bx1;             // clipped pixel bound, columns                                        40..47
+	uint32_t chkOffset;           // first stored checkpoint record, CHK_NONE when the tile kernel computes them  40..43
+	uint32_t chkShape;            // first tile column | tile columns << 16 of the checkpoint table           44..47
 	int32_t rowStart, rowCount;   // even-aligned rows (ref: ITriangle2D.cpp:70-75)                      48..55
 	uint32_t rowOffset;           // first entry in the row-interval table (always even)                 56..59
 	uint32_t pad_;
@@ -55,6 +60,16 @@ struct Cmd {
 	float u1[3], v1[3], u2[3], v2[3];          //                                                       112..159
 };
 static_assert(sizeof(Cmd) == 160, "Cmd layout");
+static const uint32_t CHK_NONE = 0xFFFFFFFFu;
+
+// Stored checkpoint of one (command, row pair, tile column): the reference's running sums where the row pair enters the tile.
+// Written by the set-up warp that scan-converts a large triangle, read by the tile kernel (same meaning as Rec::mode / Rec::v there).
+struct ChkRec {
+	int32_t mode;
+	float v[18];
+	int32_t pad_;
+};
+static_assert(sizeof(ChkRec) == 80, "ChkRec layout");
 
 enum : uint32_t {
 	CMD_AFFINE = 1u, CMD_ALPHA = 2u, CMD_HAS_DIFFUSE = 4u, CMD_HAS_LIGHT = 8u, CMD_HAS_FADE = 16u, CMD_COLORLESS = 32u
@@ -95,12 +110,13 @@ struct FrameDev {
 	uint32_t *slotCounts;            // per slot: command count | rows << 3
 	uint32_t *blockCmds, *blockRows; // per set-up block: totals, then exclusive offsets after scan_blocks_kernel
 	uint32_t *tileCount, *tileOffset, *tileCursor;
-	uint32_t *totals;                // [0] commands, [1] rows, [2] tile entries (upper bound), [3] max entries in one tile (upper bound)
+	uint32_t *totals;                // [0] commands, [1] rows, [2] tile entries (upper bound), [3] max entries in one tile (upper bound),
+	                                 // [4] checkpoint records (upper bound), [5] checkpoint cursor, [6] rank-sort scratch cursor
 	Cmd *cmds;
 	int2 *rows;
 	uint32_t *tileList;
-	uint32_t *sortTmp;               // rank-sort scratch: gridDim.x * sortTmpStride entries
-	uint32_t sortTmpStride;
+	ChkRec *chk;                     // checkpoint records of large triangles; totals[4] = records needed (upper bound), totals[5] = cursor
+	uint32_t *sortTmp;               // rank-sort scratch, as large as the entry pool; totals[6] = cursor
 };
 
 // ------------------------------------------------------------------------------------------------ projection
@@ -448,7 +464,7 @@ __device__ bool load_triangle(const TaskParams &task, int32_t local, PPoint *p, 
 
 // A command whose tile counting (counting pass) or rows + tile entries (emit pass) are produced cooperatively by one warp.
 struct BigItem {
-	uint32_t cmdIndex, rowOffset, tileBase;
+	uint32_t cmdIndex, rowOffset, tileBase, chkOffset;
 	int32_t tilesX, l, t, r, rowCount;
 	int32_t tx0, tx1, ty0, ty1;
 	long long fx[3], fy[3];
@@ -474,13 +490,80 @@ __device__ __forceinline__ void emit_tile_row(const FrameDev &frame, uint32_t ti
 	}
 }
 
+__device__ __forceinline__ void chk_store(ChkRec *dst, int32_t mode, const float *v, int count) {
+	ChkRec rec;
+	rec.mode = mode; rec.pad_ = 0;
+#pragma unroll
+	for (int i = 0; i < 18; i++) { rec.v[i] = i < count ? v[i] : 0.0f; }
+	uint4 *d = (uint4 *)dst;
+	const uint4 *src = (const uint4 *)&rec;
+#pragma unroll
+	for (int w = 0; w < 5; w++) { d[w] = src[w]; }
+}
+
+// Walks one row pair of a large triangle like the reference's fillShapeSuper does (shader/fillerTemplates.h:329-372: left-edge quads, the
+// unclipped inner run whose four lanes advance separately, the closing multiplication, right-edge quads) and leaves a checkpoint of the
+// running sums at the row pair's first quad and at every tile column boundary. recs is indexed by tile column - firstColumn.
+__device__ void chk_walk_row_pair(const float *start, const float *dx, const float *dy, int2 upperRow, int2 lowerRow, int32_t y1, ChkRec *recs, int32_t firstColumn) {
+	const int32_t outerStart = min(upperRow.x, lowerRow.x), outerEnd = max(upperRow.y, lowerRow.y);
+	const int32_t innerStart = max(upperRow.x, lowerRow.x), innerEnd = min(upperRow.y, lowerRow.y);
+	const int32_t obs = outerStart & ~1, obe = (outerEnd + 1) & ~1, ibs = (innerStart + 1) & ~1, ibe = innerEnd & ~1;
+	if (obe <= obs) { return; }
+	float v[18], dx2[3];
+	const float fx = (float)obs + 0.5f, fy = (float)y1 + 0.5f;
+#pragma unroll
+	for (int k = 0; k < 3; k++) {
+		v[k] = (start[k] + (dx[k] * fx)) + (dy[k] * fy);
+		v[3 + k] = v[k] + dy[k];
+		dx2[k] = dx[k] * 2.0f;
+	}
+	const bool noInner = ibe <= ibs;
+	const int32_t leftEnd = noInner ? obe : ibs;
+	int32_t x = obs;
+	chk_store(recs + (x / TILE_W - firstColumn), 0, v, 6);
+	while (x < leftEnd) {
+#pragma unroll
+		for (int k = 0; k < 6; k++) { v[k] += dx2[k % 3]; }
+		x += 2;
+		if ((x & (TILE_W - 1)) == 0 && x < obe && (noInner || x <= ibs)) { chk_store(recs + (x / TILE_W - firstColumn), 0, v, 6); }
+	}
+	if (noInner) { return; }
+	// inner run: v[0..11] = lanes[k][l], v[12..17] = the sums after the run
+	{
+		const float quadCount = (float)((ibe - ibs) / 2);
+		float up[3] = {v[0], v[1], v[2]}, lo[3] = {v[3], v[4], v[5]};
+#pragma unroll
+		for (int k = 0; k < 3; k++) {
+			v[k * 4 + 0] = up[k]; v[k * 4 + 1] = up[k] + dx[k]; v[k * 4 + 2] = lo[k]; v[k * 4 + 3] = lo[k] + dx[k];
+			v[12 + k] = up[k] + (dx2[k] * quadCount);
+			v[15 + k] = lo[k] + (dx2[k] * quadCount);
+		}
+	}
+	while (x < ibe) {
+#pragma unroll
+		for (int i = 0; i < 12; i++) { v[i] += dx2[i / 4]; }
+		x += 2;
+		if ((x & (TILE_W - 1)) == 0 && x < ibe) { chk_store(recs + (x / TILE_W - firstColumn), 1, v, 18); }
+	}
+#pragma unroll
+	for (int k = 0; k < 6; k++) { v[k] = v[12 + k]; }
+	if ((x & (TILE_W - 1)) == 0 && x < obe) { chk_store(recs + (x / TILE_W - firstColumn), 2, v, 6); }
+	while (x < obe) {
+#pragma unroll
+		for (int k = 0; k < 6; k++) { v[k] += dx2[k % 3]; }
+		x += 2;
+		if ((x & (TILE_W - 1)) == 0 && x < obe) { chk_store(recs + (x / TILE_W - firstColumn), 2, v, 6); }
+	}
+}
+
 template <bool EMIT>
 __global__ void __launch_bounds__(SETUP_THREADS) setup_kernel(FrameDev frame) {
 	__shared__ TaskParams task;
 	__shared__ uint32_t warpCmds[SETUP_THREADS / 32], warpRows[SETUP_THREADS / 32];
 	__shared__ BigItem sBig[SETUP_THREADS];
-	__shared__ uint32_t sBigCount;
+	__shared__ uint32_t sBigCount, sChkCount;
 	{
+		if (threadIdx.x == 0) { sChkCount = 0; }
 		int32_t t = task_of_block(frame.tasks, frame.taskCount, (int32_t)blockIdx.x);
 		for (uint32_t w = threadIdx.x; w < sizeof(TaskParams) / 4; w += blockDim.x) { ((uint32_t *)&task)[w] = ((const uint32_t *)&frame.tasks[t])[w]; }
 		if (threadIdx.x == 0) { sBigCount = 0; }
@@ -530,6 +613,7 @@ __global__ void __launch_bounds__(SETUP_THREADS) setup_kernel(FrameDev frame) {
 			const bool small = rowCount <= SMALL_ROWS && (bound.r - bound.l) <= SMALL_WIDTH;
 			if (!EMIT) {
 				if (rowCount > 0) {
+					if (!small && !task.depthOnly) { atomicAdd(&sChkCount, (uint32_t)((rowCount / 2) * (tx1 - tx0 + 1))); }
 					int32_t tiles = (tx1 - tx0 + 1) * (ty1 - ty0 + 1);
 					uint32_t queued = 0xFFFFFFFFu;
 					if (tiles > SMALL_TILES) {
@@ -550,7 +634,7 @@ __global__ void __launch_bounds__(SETUP_THREADS) setup_kernel(FrameDev frame) {
 				Cmd cmd;
 				const bool perspective = task.camera.perspective != 0;
 				get_projection(cmd, q, subB, subC, perspective);
-				cmd.bx0 = bound.l; cmd.bx1 = bound.r;
+				cmd.chkOffset = CHK_NONE; cmd.chkShape = 0u;
 				cmd.rowStart = bound.t; cmd.rowCount = rowCount;
 				cmd.rowOffset = rowBase + countRows;
 				uint32_t flags = perspective ? 0u : CMD_AFFINE;
@@ -569,6 +653,26 @@ __global__ void __launch_bounds__(SETUP_THREADS) setup_kernel(FrameDev frame) {
 				if (almost_one3(cmd.red) && almost_one3(cmd.green) && almost_one3(cmd.blue) && almost_one3(cmd.alpha)) { flags |= CMD_COLORLESS; }
 				cmd.flags = flags;
 				cmd.pad_ = 0;
+				// large triangles go to a whole warp: it scan-converts, bins and leaves interpolation checkpoints for the tile kernel
+				uint32_t queued = 0xFFFFFFFFu;
+				if (rowCount > 0 && !small) {
+					queued = atomicAdd(&sBigCount, 1u);
+					if (queued < (uint32_t)SETUP_THREADS) {
+						BigItem &it = sBig[queued];
+						it.cmdIndex = index; it.rowOffset = cmd.rowOffset; it.tileBase = tileBase; it.tilesX = tilesX;
+						it.l = bound.l; it.t = bound.t; it.r = bound.r; it.rowCount = rowCount;
+						it.tx0 = tx0; it.tx1 = tx1;
+						for (int k = 0; k < 3; k++) { it.fx[k] = q[k].fx; it.fy[k] = q[k].fy; }
+						it.chkOffset = CHK_NONE;
+#ifndef DFPSR_NO_CHK
+						if (!task.depthOnly) {
+							it.chkOffset = atomicAdd(&frame.totals[5], (uint32_t)((rowCount / 2) * (tx1 - tx0 + 1)));
+							cmd.chkOffset = it.chkOffset;
+							cmd.chkShape = (uint32_t)tx0 | ((uint32_t)(tx1 - tx0 + 1) << 16);
+						}
+#endif
+					}
+				}
 				{
 					uint4 *dst = (uint4 *)&frame.cmds[index];
 					const uint4 *src = (const uint4 *)&cmd;
@@ -576,16 +680,6 @@ __global__ void __launch_bounds__(SETUP_THREADS) setup_kernel(FrameDev frame) {
 					for (int w = 0; w < (int)(sizeof(Cmd) / 16); w++) { dst[w] = src[w]; }
 				}
 				if (rowCount > 0) {
-					uint32_t queued = 0xFFFFFFFFu;
-					if (!small) {
-						queued = atomicAdd(&sBigCount, 1u);
-						if (queued < (uint32_t)SETUP_THREADS) {
-							BigItem &it = sBig[queued];
-							it.cmdIndex = index; it.rowOffset = cmd.rowOffset; it.tileBase = tileBase; it.tilesX = tilesX;
-							it.l = bound.l; it.t = bound.t; it.r = bound.r; it.rowCount = rowCount;
-							for (int k = 0; k < 3; k++) { it.fx[k] = q[k].fx; it.fy[k] = q[k].fy; }
-						}
-					}
 					if (queued >= (uint32_t)SETUP_THREADS) {
 						// scan conversion by this thread; a tile row (TILE_H rows) is binned when its last row is done
 						long long fx[3] = {q[0].fx, q[1].fx, q[2].fx}, fy[3] = {q[0].fy, q[1].fy, q[2].fy};
@@ -625,14 +719,27 @@ __global__ void __launch_bounds__(SETUP_THREADS) setup_kernel(FrameDev frame) {
 				EdgeSet edges;
 				long long fx[3] = {it.fx[0], it.fx[1], it.fx[2]}, fy[3] = {it.fy[0], it.fy[1], it.fy[2]};
 				edges_setup(edges, fx, fy, it.l, it.t, it.r);
+				float start[3], dx[3], dy[3];
+				const bool checkpoints = it.chkOffset != CHK_NONE;
+				if (checkpoints) {
+					// the command record was written by a thread of this block before the barrier above
+					const float *planes = (const float *)&frame.cmds[it.cmdIndex];
+#pragma unroll
+					for (int k = 0; k < 3; k++) { start[k] = planes[k]; dx[k] = planes[3 + k]; dy[k] = planes[6 + k]; }
+				}
+				const int32_t columns = it.tx1 - it.tx0 + 1;
 				const int32_t tyFirst = it.t / TILE_H, tyLast = (it.t + it.rowCount - 1) / TILE_H;
 				for (int32_t ty = tyFirst + lane; ty <= tyLast; ty += 32) {
 					int32_t yBegin = max(it.t, ty * TILE_H), yEnd = min(it.t + it.rowCount, ty * TILE_H + TILE_H);
 					int32_t minL = 0x7FFFFFFF, maxR = -1;
-					for (int32_t y = yBegin; y < yEnd; y++) {
-						int2 row = edges_row(edges, y);
-						frame.rows[it.rowOffset + (uint32_t)(y - it.t)] = row;
-						if (row.y > row.x && y < height) { minL = min(minL, row.x); maxR = max(maxR, row.y); }
+					for (int32_t y = yBegin; y < yEnd; y += 2) { // rows come in even-aligned pairs
+						int2 upperRow = edges_row(edges, y), lowerRow = edges_row(edges, y + 1);
+						*(int4 *)&frame.rows[it.rowOffset + (uint32_t)(y - it.t)] = make_int4(upperRow.x, upperRow.y, lowerRow.x, lowerRow.y);
+						if (upperRow.y > upperRow.x && y < height) { minL = min(minL, upperRow.x); maxR = max(maxR, upperRow.y); }
+						if (lowerRow.y > lowerRow.x && y + 1 < height) { minL = min(minL, lowerRow.x); maxR = max(maxR, lowerRow.y); }
+						if (checkpoints && y < height) {
+							chk_walk_row_pair(start, dx, dy, upperRow, lowerRow, y, frame.chk + it.chkOffset + (size_t)((y - it.t) / 2) * (size_t)columns, it.tx0);
+						}
 					}
 					if (ty * TILE_H < height) { emit_tile_row(frame, it.tileBase, it.tilesX, ty, minL, maxR, it.cmdIndex); }
 				}
@@ -641,6 +748,7 @@ __global__ void __launch_bounds__(SETUP_THREADS) setup_kernel(FrameDev frame) {
 	}
 
 	if (!EMIT) {
+		if (threadIdx.x == 0 && sChkCount > 0) { atomicAdd(&frame.totals[4], sChkCount); }
 		if (active) { frame.slotCounts[slot] = countCmd | (countRows << 3); }
 		// block totals for scan_blocks_kernel
 		uint32_t sumCmd = countCmd, sumRows = countRows;
@@ -727,16 +835,59 @@ __global__ void __launch_bounds__(256) tile_alloc_kernel(FrameDev frame) {
 // would queue on the copy engine behind megabytes of finished frames travelling to the host (dfpsr_session_render_views_host) and
 // stall the next chunk's set-up for milliseconds.
 __global__ void publish_totals_kernel(const uint32_t *__restrict__ totals, volatile uint32_t *hostTotals) {
-	if (threadIdx.x < 4) { hostTotals[threadIdx.x] = totals[threadIdx.x]; }
+	if (threadIdx.x < 5) { hostTotals[threadIdx.x] = totals[threadIdx.x]; }
 	__threadfence_system();
 }
 
 // Restores ascending command order in the lists that hold more than 32 entries (shorter ones are sorted in registers by raster_kernel).
+// Every thread looks at one tile; the long ones are queued in shared memory and sorted by the whole CTA one after the other.
 __global__ void __launch_bounds__(SORT_THREADS) sort_lists_kernel(FrameDev frame) {
 	__shared__ uint32_t s[SORT_SMEM];
-	for (uint32_t tile = blockIdx.x; tile < frame.tileTotal; tile += gridDim.x) {
+	__shared__ uint32_t sQueue[SORT_THREADS];
+	__shared__ uint32_t sQueued;
+	if (threadIdx.x == 0) { sQueued = 0; }
+	__syncthreads();
+	{
+		const uint32_t tile = blockIdx.x * SORT_THREADS + threadIdx.x;
+		if (tile < frame.tileTotal && frame.tileCursor[tile] > 32u) { sQueue[atomicAdd(&sQueued, 1u)] = tile; }
+	}
+	__syncthreads();
+	const uint32_t queued = sQueued;
+	// lists of up to SORT_WARP entries: one warp each, all warps of the CTA in parallel
+	{
+		const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+		uint32_t *ws = s + warp * SORT_WARP;
+		for (uint32_t q = warp; q < queued; q += SORT_THREADS / 32) {
+			const uint32_t tile = sQueue[q];
+			const uint32_t n = frame.tileCursor[tile];
+			if (n > (uint32_t)SORT_WARP) { continue; }
+			uint32_t *list = frame.tileList + frame.tileOffset[tile];
+			uint32_t size = 64;
+			while (size < n) { size <<= 1; }
+			for (uint32_t i = lane; i < size; i += 32) { ws[i] = i < n ? list[i] : 0xFFFFFFFFu; }
+			__syncwarp();
+			for (uint32_t k = 2; k <= size; k <<= 1) {
+				for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+					for (uint32_t i = lane; i < size; i += 32) {
+						uint32_t l = i ^ j;
+						if (l > i) {
+							uint32_t a = ws[i], b = ws[l];
+							bool ascending = (i & k) == 0;
+							if ((a > b) == ascending) { ws[i] = b; ws[l] = a; }
+						}
+					}
+					__syncwarp();
+				}
+			}
+			for (uint32_t i = lane; i < n; i += 32) { list[i] = ws[i]; }
+			__syncwarp();
+		}
+	}
+	__syncthreads();
+	for (uint32_t q = 0; q < queued; q++) {
+		const uint32_t tile = sQueue[q];
 		const uint32_t n = frame.tileCursor[tile];
-		if (n <= 32u) { continue; }
+		if (n <= (uint32_t)SORT_WARP) { continue; }
 		uint32_t *list = frame.tileList + frame.tileOffset[tile];
 		if (n <= (uint32_t)SORT_SMEM) {
 			uint32_t size = 64;
@@ -759,8 +910,12 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_lists_kernel(FrameDev frame
 			for (uint32_t i = threadIdx.x; i < n; i += SORT_THREADS) { list[i] = s[i]; }
 			__syncthreads();
 		} else {
-			// rank sort (keys are distinct): O(n^2 / threads), only for pathological pile-ups of thousands of triangles on one tile
-			uint32_t *tmp = frame.sortTmp + (size_t)blockIdx.x * frame.sortTmpStride;
+			// rank sort (keys are distinct): O(n^2 / threads), only for pathological pile-ups of thousands of triangles on one tile.
+			// Scratch: every such list claims its own n entries of a pool as large as the whole entry pool (totals[6] is the cursor).
+			__shared__ uint32_t sSegment;
+			if (threadIdx.x == 0) { sSegment = atomicAdd(&frame.totals[6], n); }
+			__syncthreads();
+			uint32_t *tmp = frame.sortTmp + sSegment;
 			for (uint32_t i = threadIdx.x; i < n; i += SORT_THREADS) {
 				uint32_t key = list[i], rank = 0;
 				for (uint32_t j = 0; j < n; j++) { rank += list[j] < key ? 1u : 0u; }
@@ -883,7 +1038,7 @@ __device__ __forceinline__ uint32_t warp_sort(uint32_t key, int lane) {
 }
 
 template <bool DEPTH_ONLY>
-__global__ void __launch_bounds__(RASTER_WARPS * 32) raster_kernel(FrameDev frame, TexTable textures) {
+__global__ void __launch_bounds__(RASTER_WARPS * 32, RASTER_MIN_BLOCKS) raster_kernel(FrameDev frame, TexTable textures) {
 	__shared__ __align__(16) Rec sRecAll[RASTER_WARPS][32];
 	__shared__ __align__(16) uint32_t sMaskAll[RASTER_WARPS][32]; // per (row pair, command): which of the 16 quads of the row pair the command may touch
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -950,6 +1105,7 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32) raster_kernel(FrameDev fram
 				const int4 head = __ldg((const int4 *)cmd + 3); // rowStart, rowCount, rowOffset, pad
 				const int32_t rowStart = head.x, rowCount = head.y;
 				const uint32_t rowOffset = (uint32_t)head.z;
+				const uint4 third = __ldg((const uint4 *)cmd + 2); // dy[2], flags, chkOffset, chkShape
 				const int32_t yTop = tileY * TILE_H + 2 * (int32_t)r;
 				const int32_t idx = yTop - rowStart;
 				if (idx >= 0 && idx < rowCount) {
@@ -995,7 +1151,18 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32) raster_kernel(FrameDev fram
 							const bool noInner = ibe <= ibs;
 							rec.at = at;
 							quadFirst = (at - tileLeft) >> 1; quadEnd = (min(obe, tileLeft + TILE_W) - tileLeft) >> 1;
-							if (noInner || at <= ibs) {
+							if (third.z != CHK_NONE) {
+								// a set-up warp walked this row pair and left the sums at this tile column
+								const uint32_t firstColumn = third.w & 0xFFFFu, columns = third.w >> 16;
+								const uint4 *src = (const uint4 *)(frame.chk + third.z + (size_t)(idx >> 1) * columns + ((uint32_t)tileX - firstColumn));
+								const uint4 w0 = __ldg(src), w1 = __ldg(src + 1), w2 = __ldg(src + 2), w3 = __ldg(src + 3), w4 = __ldg(src + 4);
+								rec.mode = (int32_t)w0.x;
+								rec.v[0] = __uint_as_float(w0.y); rec.v[1] = __uint_as_float(w0.z); rec.v[2] = __uint_as_float(w0.w);
+								rec.v[3] = __uint_as_float(w1.x); rec.v[4] = __uint_as_float(w1.y); rec.v[5] = __uint_as_float(w1.z); rec.v[6] = __uint_as_float(w1.w);
+								rec.v[7] = __uint_as_float(w2.x); rec.v[8] = __uint_as_float(w2.y); rec.v[9] = __uint_as_float(w2.z); rec.v[10] = __uint_as_float(w2.w);
+								rec.v[11] = __uint_as_float(w3.x); rec.v[12] = __uint_as_float(w3.y); rec.v[13] = __uint_as_float(w3.z); rec.v[14] = __uint_as_float(w3.w);
+								rec.v[15] = __uint_as_float(w4.x); rec.v[16] = __uint_as_float(w4.y); rec.v[17] = __uint_as_float(w4.z);
+							} else if (noInner || at <= ibs) {
 								for (int32_t s = obs; s < at; s += 2) {
 #pragma unroll
 									for (int k = 0; k < 3; k++) { up[k] += dx2[k]; lo[k] += dx2[k]; }
@@ -1295,12 +1462,12 @@ struct dfpsr_renderer {
 	TexTable textures{};
 	int textureCount = 0;
 	int64_t lastCommands = -1;
-	DeviceBuffer dTasks, dViews, projected, slotCounts, blockCmds, blockRows, tileCount, tileOffset, tileCursor, cmds, rows, tileList, sortTmp;
+	DeviceBuffer dTasks, dViews, projected, slotCounts, blockCmds, blockRows, tileCount, tileOffset, tileCursor, cmds, rows, tileList, chk, sortTmp;
 	uint32_t *hostTotals = nullptr, *hostTotalsDevice = nullptr; // mapped pinned memory and its device alias
 
 	~dfpsr_renderer() {
 		for (auto &b : uploads) { b.release(); }
-		DeviceBuffer *all[] = {&dTasks, &dViews, &projected, &slotCounts, &blockCmds, &blockRows, &tileCount, &tileOffset, &tileCursor, &cmds, &rows, &tileList, &sortTmp};
+		DeviceBuffer *all[] = {&dTasks, &dViews, &projected, &slotCounts, &blockCmds, &blockRows, &tileCount, &tileOffset, &tileCursor, &cmds, &rows, &tileList, &chk, &sortTmp};
 		for (auto *b : all) { b->release(); }
 		if (hostTotals) { cudaFreeHost(hostTotals); }
 	}
@@ -1447,19 +1614,18 @@ static int renderer_end_internal(dfpsr_renderer *r, cudaStream_t stream) {
 			if (r->cmds.reserve((size_t)commandTotal * sizeof(Cmd))) { return 1; }
 			if (r->rows.reserve((size_t)rowTotal * sizeof(int2) + 16)) { return 1; }
 			if (r->tileList.reserve((size_t)entryTotal * 4 + 16)) { return 1; }
+			if (r->chk.reserve((size_t)r->hostTotals[4] * sizeof(ChkRec) + 16)) { return 1; }
+			frame.chk = (ChkRec *)r->chk.ptr;
 			frame.cmds = (Cmd *)r->cmds.ptr;
 			frame.rows = (int2 *)r->rows.ptr;
 			frame.tileList = (uint32_t *)r->tileList.ptr;
 			DFPSR_LAUNCH(setup_kernel<true>, blockTotal, SETUP_THREADS, 0, stream, frame);
 			if (maxTile > 32u) {
-				uint32_t grid = (uint32_t)sm_count() * 8u;
-				if (grid > tileTotal) { grid = tileTotal; }
 				if (maxTile > (uint32_t)SORT_SMEM) {
-					if (r->sortTmp.reserve((size_t)grid * maxTile * 4)) { return 1; }
+					if (r->sortTmp.reserve((size_t)entryTotal * 4 + 16)) { return 1; }
 					frame.sortTmp = (uint32_t *)r->sortTmp.ptr;
-					frame.sortTmpStride = maxTile;
 				}
-				DFPSR_LAUNCH(sort_lists_kernel, grid, SORT_THREADS, 0, stream, frame);
+				DFPSR_LAUNCH(sort_lists_kernel, (tileTotal + SORT_THREADS - 1) / SORT_THREADS, SORT_THREADS, 0, stream, frame);
 			}
 		}
 	}

@@ -64,14 +64,32 @@ def run(cuda, lib):
     gpu = sandbox_scene.CudaSandbox(cuda, sb)
     gpu.composite()
     ms_light_unbatched = _time(torch, lambda: gpu.light(), iters=3)
-    ms_light = _time(torch, lambda: gpu.light_batched(), iters=10)
+    ms_light_batched = _time(torch, lambda: gpu.light_batched(), iters=10)
+    ms_light = _time(torch, lambda: gpu.light_fused(), iters=20)
     ms_comp = _time(torch, lambda: gpu.composite(), iters=5)
     px = 800 * 600
     algorithmic = 20 * px + 16 * 2 * 256 * 1536 * 4  # SURVEY §8d config 2 ≈ 60 MB
-    out["sandbox_800x600_16_lights"] = {"ms_light_passes": ms_light, "ms_light_passes_one_cube_map_per_light_call": ms_light_unbatched, "ms_compositing_40_sprites": ms_comp, "fps_light_passes": 1000.0 / ms_light,
+    out["sandbox_800x600_16_lights"] = {"ms_light_passes": ms_light, "ms_light_passes_one_cube_map_per_light_call": ms_light_unbatched, "ms_light_passes_batched_shadows_separate_light_kernels": ms_light_batched, "ms_compositing_40_sprites": ms_comp, "fps_light_passes": 1000.0 / ms_light,
                                         "algorithmic_gb_s": algorithmic / ms_light / 1e6, "frac_of_hbm_peak": algorithmic / ms_light / 1e6 / peak}
     blend_ms = _time(torch, lambda: lib.check(cuda.dfpsr_light_blend(C.byref(IM(gpu.C)), C.byref(IM(gpu.D)), C.byref(IM(gpu.L)), s)), iters=50)
     out["sandbox_800x600_16_lights"]["blend_us"] = 1000.0 * blend_ms
+
+    # ---- the same per-pixel light passes at a size where launch latency does not hide their bandwidth (8192 x 8192)
+    big = 8192
+    bigN = torch.randint(0, 2 ** 31 - 1, (big, big), dtype=torch.int32, device="cuda")
+    bigD = torch.randint(0, 2 ** 31 - 1, (big, big), dtype=torch.int32, device="cuda")
+    bigL, bigC = torch.zeros_like(bigN), torch.zeros_like(bigN)
+    d = sb["directed"]
+    ms_dir = _time(torch, lambda: lib.check(cuda.dfpsr_light_directed(C.byref(gpu.view), C.byref(IM(bigL)), C.byref(IM(bigN)), d["direction"].ctypes.data, d["intensity"], d["color"].ctypes.data, 0, s)), iters=20)
+    ms_dir_add = _time(torch, lambda: lib.check(cuda.dfpsr_light_directed(C.byref(gpu.view), C.byref(IM(bigL)), C.byref(IM(bigN)), d["direction"].ctypes.data, d["intensity"], d["color"].ctypes.data, 1, s)), iters=20)
+    ms_blend = _time(torch, lambda: lib.check(cuda.dfpsr_light_blend(C.byref(IM(bigC)), C.byref(IM(bigD)), C.byref(IM(bigL)), s)), iters=20)
+    px4k = big * big
+    out["light_passes_8192x8192"] = {
+        "set_directed_ms": ms_dir, "set_directed_gb_s": 8 * px4k / ms_dir / 1e6, "set_directed_frac_of_hbm_peak": 8 * px4k / ms_dir / 1e6 / peak,
+        "add_directed_ms": ms_dir_add, "add_directed_gb_s": 12 * px4k / ms_dir_add / 1e6, "add_directed_frac_of_hbm_peak": 12 * px4k / ms_dir_add / 1e6 / peak,
+        "blend_ms": ms_blend, "blend_gb_s": 12 * px4k / ms_blend / 1e6, "blend_frac_of_hbm_peak": 12 * px4k / ms_blend / 1e6 / peak,
+        "note": "256 MB per buffer, larger than the 126 MB L2; bytes = algorithmic 8 / 12 / 12 B per pixel"}
+    del bigN, bigD, bigL, bigC
 
     # ---- config 5: 8192x8192 filter chain (map + bilinear resize), pure streaming
     size = 8192

@@ -99,6 +99,14 @@ class SpriteDraw(C.Structure):
     _fields_ = [("sourceHeight", Image), ("sourceA", Image), ("sourceB", Image), ("left", C.c_int32), ("top", C.c_int32), ("heightOffset", C.c_float)]
 
 
+class DirectedLight(C.Structure):
+    _fields_ = [("direction", C.c_float * 3), ("intensity", C.c_float), ("colorRgb", C.c_int32 * 3)]
+
+
+class PointLight(C.Structure):
+    _fields_ = [("position", C.c_float * 3), ("radius", C.c_float), ("intensity", C.c_float), ("colorRgb", C.c_int32 * 3), ("shadowCubeMap", Image)]
+
+
 class HostModel(C.Structure):
     _fields_ = [
         ("points", C.c_void_p), ("pointCount", C.c_int32),

@@ -9,6 +9,7 @@
 #include "common.cuh"
 
 #include <math.h>
+#include <vector>
 
 namespace dfpsr {
 
@@ -17,6 +18,12 @@ static inline dim3 grid_for(int32_t width, int32_t height, dim3 block) {
 	return dim3((unsigned)((width + PX * (int)block.x - 1) / (PX * (int)block.x)), (unsigned)((height + (int)block.y - 1) / (int)block.y));
 }
 static const dim3 BLOCK(64, 4);
+// Streaming kernels: every thread owns 4 pixels (16 bytes) in each of ROWS rows and issues all its loads before the first store, so a
+// CTA of 256 threads keeps 16 KB per input in flight — what HBM3e needs to approach its peak (4 KB per CTA reached 56 % of it).
+static const int ROWS = 4;
+static inline dim3 grid_rows(int32_t width, int32_t height, dim3 block) {
+	return dim3((unsigned)((width + PX * (int)block.x - 1) / (PX * (int)block.x)), (unsigned)((height + ROWS * (int)block.y - 1) / (ROWS * (int)block.y)));
+}
 
 struct Img {
 	uint8_t *data;
@@ -160,41 +167,64 @@ __device__ __forceinline__ uint32_t light_pack(float r, float g, float b) {
 
 // ref: SDK/SpriteEngine/lightAPI.cpp:23-68
 __global__ void __launch_bounds__(256) directed_kernel(Img light, Img normal, float rx, float ry, float rz, float colorR, float colorG, float colorB, int add) {
-	int32_t x = (blockIdx.x * blockDim.x + threadIdx.x) * PX, y = blockIdx.y * blockDim.y + threadIdx.y;
-	if (x >= light.width || y >= light.height) { return; }
-	int n = min(PX, light.width - x);
-	uint32_t nc[4], out[4], old[4] = {0, 0, 0, 0};
-	load4(normal, x, y, n, nc);
-	if (add) { load4(light, x, y, n, old); }
+	const int32_t x = (blockIdx.x * blockDim.x + threadIdx.x) * PX, y0 = blockIdx.y * (blockDim.y * ROWS) + threadIdx.y;
+	if (x >= light.width) { return; }
+	const int n = min(PX, light.width - x);
+	uint32_t nc[ROWS][4], old[ROWS][4];
 #pragma unroll
-	for (int i = 0; i < 4; i++) {
-		float nx = (float)(nc[i] & 255u) - 128.0f, ny = (float)((nc[i] >> 8) & 255u) - 128.0f, nz = (float)((nc[i] >> 16) & 255u) - 128.0f;
-		float dot = (nx * rx) + (ny * ry) + (nz * rz);
-		float in = dot > 0.0f ? dot : 0.0f;
-		uint32_t packed = light_pack(in * colorR, in * colorG, in * colorB);
-		out[i] = add ? sat_add_bytes(old[i], packed) : packed;
+	for (int j = 0; j < ROWS; j++) {
+		const int32_t y = y0 + j * blockDim.y;
+		if (y < light.height) {
+			load4(normal, x, y, n, nc[j]);
+			if (add) { load4(light, x, y, n, old[j]); }
+		}
 	}
-	store4(light, x, y, n, out);
+#pragma unroll
+	for (int j = 0; j < ROWS; j++) {
+		const int32_t y = y0 + j * blockDim.y;
+		if (y < light.height) {
+			uint32_t out[4];
+#pragma unroll
+			for (int i = 0; i < 4; i++) {
+				float nx = (float)(nc[j][i] & 255u) - 128.0f, ny = (float)((nc[j][i] >> 8) & 255u) - 128.0f, nz = (float)((nc[j][i] >> 16) & 255u) - 128.0f;
+				float dot = (nx * rx) + (ny * ry) + (nz * rz);
+				float in = dot > 0.0f ? dot : 0.0f;
+				uint32_t packed = light_pack(in * colorR, in * colorG, in * colorB);
+				out[i] = add ? sat_add_bytes(old[j][i], packed) : packed;
+			}
+			store4(light, x, y, n, out);
+		}
+	}
 }
 
 // ref: SDK/SpriteEngine/lightAPI.cpp:287-323
 __global__ void __launch_bounds__(256) blend_kernel(Img color, Img diffuse, Img light) {
-	int32_t x = (blockIdx.x * blockDim.x + threadIdx.x) * PX, y = blockIdx.y * blockDim.y + threadIdx.y;
-	if (x >= color.width || y >= color.height) { return; }
-	int n = min(PX, color.width - x);
-	uint32_t d[4], l[4], out[4];
-	load4(diffuse, x, y, n, d);
-	load4(light, x, y, n, l);
-	const float scale = 0.0078125f; // 1 / 128
-	uint32_t shifts = pack_shifts(color.packOrder);
+	const int32_t x = (blockIdx.x * blockDim.x + threadIdx.x) * PX, y0 = blockIdx.y * (blockDim.y * ROWS) + threadIdx.y;
+	if (x >= color.width) { return; }
+	const int n = min(PX, color.width - x);
+	uint32_t d[ROWS][4], l[ROWS][4];
 #pragma unroll
-	for (int i = 0; i < 4; i++) {
-		float red = ((float)(d[i] & 255u) * (float)(l[i] & 255u)) * scale;
-		float green = ((float)((d[i] >> 8) & 255u) * (float)((l[i] >> 8) & 255u)) * scale;
-		float blue = ((float)((d[i] >> 16) & 255u) * (float)((l[i] >> 16) & 255u)) * scale;
-		out[i] = pack_rgba_ordered(saturated_byte(red), saturated_byte(green), saturated_byte(blue), 0u, shifts);
+	for (int j = 0; j < ROWS; j++) {
+		const int32_t y = y0 + j * blockDim.y;
+		if (y < color.height) { load4(diffuse, x, y, n, d[j]); load4(light, x, y, n, l[j]); }
 	}
-	store4(color, x, y, n, out);
+	const float scale = 0.0078125f; // 1 / 128
+	const uint32_t shifts = pack_shifts(color.packOrder);
+#pragma unroll
+	for (int j = 0; j < ROWS; j++) {
+		const int32_t y = y0 + j * blockDim.y;
+		if (y < color.height) {
+			uint32_t out[4];
+#pragma unroll
+			for (int i = 0; i < 4; i++) {
+				float red = ((float)(d[j][i] & 255u) * (float)(l[j][i] & 255u)) * scale;
+				float green = ((float)((d[j][i] >> 8) & 255u) * (float)((l[j][i] >> 8) & 255u)) * scale;
+				float blue = ((float)((d[j][i] >> 16) & 255u) * (float)((l[j][i] >> 16) & 255u)) * scale;
+				out[i] = pack_rgba_ordered(saturated_byte(red), saturated_byte(green), saturated_byte(blue), 0u, shifts);
+			}
+			store4(color, x, y, n, out);
+		}
+	}
 }
 
 struct PointLightParams {
@@ -268,6 +298,110 @@ __global__ void __launch_bounds__(256) point_light_kernel(Img light, Img normal,
 		if (p.shadow) { in = in * shadow_transparency(cube, p.cubeCenter, ox, oy, oz); }
 		uint32_t *t = px_u32(light, x, y);
 		*t = sat_add_bytes(*t, light_pack(in * p.colorR, in * p.colorG, in * p.colorB));
+	}
+}
+
+// ---- the whole light part of a Sandbox frame in one pass (ref: SDK/SpriteEngine/spriteAPI.cpp:775-814): directed lights (the first
+// one sets, the others add), every point light, blend. Per pixel: normal, height and diffuse are read once, light and colour written
+// once (20 B instead of 8 + 16 per point light + 12). Saturating byte additions of non-negative contributions commute, so keeping the
+// light accumulator in a register gives the reference's bytes.
+static const int FRAME_MAX_DIRECTED = 8;
+static const int FRAME_LIGHT_GROUP = 16; // at most this many point lights have their row sums staged in shared memory together (12 threads each)
+struct FramePointLight { PointLightParams p; Img cube; };
+struct FrameLightParams {
+	int32_t directedCount, pointCount, chainStride, group;
+	float directed[FRAME_MAX_DIRECTED][6]; // rx, ry, rz, colour r, g, b
+	const FramePointLight *points;
+};
+
+// One CTA per image row. For every group of point lights, 12 threads per light (3 components x 4 lanes) first replay the reference's
+// running sums for this row (lightAPI.cpp:196-268: += dy per row, += laneCount * dx per vector), then all threads shade pixels.
+__global__ void __launch_bounds__(256) light_frame_kernel(Img color, Img diffuse, Img light, Img normal, Img height, FrameLightParams fp) {
+	extern __shared__ float sChains[]; // [light in group][vector][component * 4 + lane], chainStride floats per light
+	const int32_t y = (int32_t)blockIdx.x;
+	const int32_t perThread = (light.width + (int32_t)blockDim.x - 1) / (int32_t)blockDim.x;
+	// pixels x = threadIdx.x + i * blockDim.x, at most 8 per thread are kept in registers per sweep
+	for (int32_t sweep = 0; sweep < perThread; sweep += 8) {
+		uint32_t acc[8], nc[8];
+		float h[8];
+#pragma unroll
+		for (int i = 0; i < 8; i++) {
+			const int32_t x = (int32_t)threadIdx.x + (sweep + i) * (int32_t)blockDim.x;
+			acc[i] = 0u; nc[i] = 0u; h[i] = 0.0f;
+			if (sweep + i < perThread && x < light.width) {
+				nc[i] = *px_u32(normal, x, y);
+				if (height.data) { h[i] = *px_f32(height, x, y); }
+				const float nx = (float)(nc[i] & 255u) - 128.0f, ny = (float)((nc[i] >> 8) & 255u) - 128.0f, nz = (float)((nc[i] >> 16) & 255u) - 128.0f;
+				for (int32_t d = 0; d < fp.directedCount; d++) {
+					const float dot = (nx * fp.directed[d][0]) + (ny * fp.directed[d][1]) + (nz * fp.directed[d][2]);
+					const float in = dot > 0.0f ? dot : 0.0f;
+					const uint32_t packed = light_pack(in * fp.directed[d][3], in * fp.directed[d][4], in * fp.directed[d][5]);
+					acc[i] = d == 0 ? packed : sat_add_bytes(acc[i], packed);
+				}
+			}
+		}
+		for (int32_t groupStart = 0; groupStart < fp.pointCount; groupStart += fp.group) {
+			const int32_t groupCount = min(fp.group, fp.pointCount - groupStart);
+			__syncthreads();
+			if ((int32_t)threadIdx.x < groupCount * 12) {
+				const int32_t g = threadIdx.x / 12, comp = (threadIdx.x % 12) / 4, l = threadIdx.x % 4;
+				const PointLightParams &p = fp.points[groupStart + g].p;
+				if (y >= p.top && y < p.top + p.height) {
+					const float base = comp == 0 ? p.baseX : (comp == 1 ? p.baseY : p.baseZ);
+					const float dx = comp == 0 ? p.dxX : (comp == 1 ? p.dxY : p.dxZ), dy = comp == 0 ? p.dyX : (comp == 1 ? p.dyY : p.dyZ);
+					float v = l == 0 ? base : (l == 1 ? base + dx : base + dx * (float)l); // createGradient (ref: base/simd.h:474)
+					for (int32_t r = p.top; r < y; r++) { v += dy; }
+					const float step = dx * 4.0f;
+					float *dst = sChains + g * fp.chainStride + comp * 4 + l;
+					const int32_t vectors = p.width / 4;
+					for (int32_t k = 0; k < vectors; k++) { dst[k * 12] = v; v += step; }
+				}
+			}
+			__syncthreads();
+			for (int32_t g = 0; g < groupCount; g++) {
+				const FramePointLight &fl = fp.points[groupStart + g];
+				const PointLightParams &p = fl.p;
+				if (y < p.top || y >= p.top + p.height) { continue; }
+				const float *chain = sChains + g * fp.chainStride;
+#pragma unroll
+				for (int i = 0; i < 8; i++) {
+					const int32_t x = (int32_t)threadIdx.x + (sweep + i) * (int32_t)blockDim.x;
+					const int32_t rel = x - p.left;
+					if (sweep + i < perThread && x < light.width && rel >= 0 && rel < p.width) {
+						const int32_t k = rel >> 2, l = rel & 3;
+						const float ox = chain[k * 12 + l] + (p.faceX * h[i]);
+						const float oy = chain[k * 12 + 4 + l] + (p.faceY * h[i]);
+						const float oz = chain[k * 12 + 8 + l] + (p.faceZ * h[i]);
+						const float sq = (ox * ox) + (oy * oy) + (oz * oz);
+						float lightRatio = sqrtf(sq) * p.reciprocalRadius;
+						if (1.0f < lightRatio) { lightRatio = 1.0f; }
+						const float nx = ((float)(nc[i] & 255u) - 128.0f) * (-1.0f / 128.0f), ny = ((float)((nc[i] >> 8) & 255u) - 128.0f) * (-1.0f / 128.0f), nz = ((float)((nc[i] >> 16) & 255u) - 128.0f) * (-1.0f / 128.0f);
+						const float distanceIntensity = 1.0f - 2.0f * lightRatio + lightRatio * lightRatio;
+						const float rs = (float)(1.0 / sqrt((double)sq)); // scalar-build reciprocalSquareRoot (ref: base/simd.h:4104)
+						const float dot = ((ox * rs) * nx) + ((oy * rs) * ny) + ((oz * rs) * nz);
+						float in = (dot > 0.0f ? dot : 0.0f) * distanceIntensity;
+						if (p.shadow) { in = in * shadow_transparency(fl.cube, p.cubeCenter, ox, oy, oz); }
+						acc[i] = sat_add_bytes(acc[i], light_pack(in * p.colorR, in * p.colorG, in * p.colorB));
+					}
+				}
+			}
+		}
+		const uint32_t shifts = pack_shifts(color.packOrder);
+#pragma unroll
+		for (int i = 0; i < 8; i++) {
+			const int32_t x = (int32_t)threadIdx.x + (sweep + i) * (int32_t)blockDim.x;
+			if (sweep + i < perThread && x < light.width) {
+				*px_u32(light, x, y) = acc[i];
+				if (color.data) {
+					const uint32_t d = *px_u32(diffuse, x, y);
+					const float scale = 0.0078125f;
+					const float red = ((float)(d & 255u) * (float)(acc[i] & 255u)) * scale;
+					const float green = ((float)((d >> 8) & 255u) * (float)((acc[i] >> 8) & 255u)) * scale;
+					const float blue = ((float)((d >> 16) & 255u) * (float)((acc[i] >> 16) & 255u)) * scale;
+					*px_u32(color, x, y) = pack_rgba_ordered(saturated_byte(red), saturated_byte(green), saturated_byte(blue), 0u, shifts);
+				}
+			}
+		}
 	}
 }
 
@@ -395,6 +529,68 @@ __global__ void __launch_bounds__(256) map_kernel(Img target, Img source, MapPar
 		out[i] = saturate_and_pack(c, shifts);
 	}
 	store4(target, x0, ty, n, out);
+}
+
+
+__device__ __forceinline__ uint32_t affine_pixel(uint32_t c, uint32_t ss, uint32_t ts, const int32_t *p) {
+	int32_t r = (int32_t)((c >> (ss & 31u)) & 255u) * p[0] + p[4], g = (int32_t)((c >> ((ss >> 8) & 31u)) & 255u) * p[1] + p[5];
+	int32_t b = (int32_t)((c >> ((ss >> 16) & 31u)) & 255u) * p[2] + p[6], a = (int32_t)((c >> ((ss >> 24) & 31u)) & 255u) * p[3] + p[7];
+	return pack_rgba_ordered((uint32_t)min(max(r, 0), 255), (uint32_t)min(max(g, 0), 255), (uint32_t)min(max(b, 0), 255), (uint32_t)min(max(a, 0), 255), ts);
+}
+
+// filter_map, affine op, every read inside the source (ref: api/filterAPI.cpp:759-777 with image_readPixel_clamp never clamping).
+__global__ void __launch_bounds__(256) map_affine_stream_kernel(Img target, Img source, MapParams mp) {
+	const int32_t x = (blockIdx.x * blockDim.x + threadIdx.x) * PX, y0 = blockIdx.y * (blockDim.y * ROWS) + threadIdx.y;
+	if (x >= target.width) { return; }
+	const int n = min(PX, target.width - x);
+	const uint32_t ss = pack_shifts(source.packOrder), ts = pack_shifts(target.packOrder);
+	uint32_t v[ROWS][4];
+#pragma unroll
+	for (int j = 0; j < ROWS; j++) {
+		const int32_t y = y0 + j * blockDim.y;
+		if (y < target.height) { load4(source, x + mp.startX, y + mp.startY, n, v[j]); }
+	}
+#pragma unroll
+	for (int j = 0; j < ROWS; j++) {
+		const int32_t y = y0 + j * blockDim.y;
+		if (y < target.height) {
+#pragma unroll
+			for (int i = 0; i < 4; i++) { v[j][i] = affine_pixel(v[j][i], ss, ts, mp.p); }
+			store4(target, x, y, n, v[j]);
+		}
+	}
+}
+
+// filter_resize, bilinear, exactly half the width and half the height: the 16.16 read position of target pixel i is 2 i + 0.5 on both
+// axes (ref: api/filterAPI.cpp:118-154 with offset = 131072 and start = 65536 - 32768), so every lerp has weight 32768 and
+// (a * 32768 + b * 32768) >> 16 == (a + b) >> 1 per channel: two truncating byte averages horizontally, one vertically.
+__global__ void __launch_bounds__(256) resize_half_kernel(Img target, Img source) {
+	const int32_t x = (blockIdx.x * blockDim.x + threadIdx.x) * PX, y0 = blockIdx.y * (blockDim.y * 2) + threadIdx.y;
+	if (x >= target.width) { return; }
+	const int n = min(PX, target.width - x);
+	const uint32_t ss = pack_shifts(source.packOrder), ts = pack_shifts(target.packOrder);
+	uint32_t up[2][8], lo[2][8];
+#pragma unroll
+	for (int j = 0; j < 2; j++) {
+		const int32_t y = y0 + j * blockDim.y;
+		if (y < target.height) {
+			load4(source, 2 * x, 2 * y, min(4, 2 * n), up[j]); load4(source, 2 * x + 4, 2 * y, max(0, 2 * n - 4), up[j] + 4);
+			load4(source, 2 * x, 2 * y + 1, min(4, 2 * n), lo[j]); load4(source, 2 * x + 4, 2 * y + 1, max(0, 2 * n - 4), lo[j] + 4);
+		}
+	}
+#pragma unroll
+	for (int j = 0; j < 2; j++) {
+		const int32_t y = y0 + j * blockDim.y;
+		if (y < target.height) {
+			uint32_t out[4];
+#pragma unroll
+			for (int i = 0; i < 4; i++) {
+				uint32_t c = __vhaddu4(__vhaddu4(up[j][2 * i], up[j][2 * i + 1]), __vhaddu4(lo[j][2 * i], lo[j][2 * i + 1]));
+				out[i] = ss == ts ? c : repack(c, ss, ts);
+			}
+			store4(target, x, y, n, out);
+		}
+	}
 }
 
 // ref: api/filterAPI.cpp:724-757 + :340-365
@@ -525,29 +721,27 @@ int dfpsr_light_directed(const dfpsr_ortho_view *view, const dfpsr_image *light,
 	float rx = -n.x * intensity * 2.0f, ry = -n.y * intensity * 2.0f, rz = -n.z * intensity * 2.0f;
 	float colorR = fmaxf(0.0f, (float)colorRgb[0] / 255.0f), colorG = fmaxf(0.0f, (float)colorRgb[1] / 255.0f), colorB = fmaxf(0.0f, (float)colorRgb[2] / 255.0f);
 	Img l = img_of(light);
-	DFPSR_LAUNCH(directed_kernel, grid_for(l.width, l.height, BLOCK), BLOCK, 0, as_stream(stream), l, img_of(normal), rx, ry, rz, colorR, colorG, colorB, add);
+	DFPSR_LAUNCH(directed_kernel, grid_rows(l.width, l.height, BLOCK), BLOCK, 0, as_stream(stream), l, img_of(normal), rx, ry, rz, colorR, colorG, colorB, add);
 	return 0;
 }
 
-int dfpsr_light_point(const dfpsr_ortho_view *view, const int32_t worldCenter[2], const dfpsr_image *light, const dfpsr_image *normal, const dfpsr_image *height, const float position[3], float radius, float intensity, const int32_t colorRgb[3], const dfpsr_image *shadowCubeMap, void *stream) {
-	DFPSR_REQUIRE(view && worldCenter && exists(light) && exists(normal) && exists(height) && position && colorRgb, "light_point: null argument");
+// ref: SDK/SpriteEngine/lightAPI.cpp:76-105 calculateBound + :190-206 uniforms of addPointLightSuper. Returns false when the light's
+// rectangle misses the image.
+static bool point_light_params(PointLightParams &p, const dfpsr_ortho_view *view, const int32_t worldCenter[2], int32_t imageWidth, int32_t imageHeight, const float position[3], float radius, float intensity, const int32_t colorRgb[3], const dfpsr_image *shadowCubeMap) {
 	const int32_t laneCount = 4; // laneCountX_32Bit of the reference's SSE2 and scalar builds
-	// ref: SDK/SpriteEngine/lightAPI.cpp:76-105 calculateBound
 	V3 S = mat_transform_transposed(view->normalToWorldSpace, V3{position[0], position[1], position[2]});
 	V3 rotated = mat_transform(view->lightSpaceToScreenDepth, S);
 	int32_t cx = (int32_t)rotated.x + worldCenter[0], cy = (int32_t)rotated.y + worldCenter[1];
 	int32_t pixelRadius = (int32_t)(radius * view->lightSpaceToScreenDepth.xAxis[0]);
-	if (cx < -pixelRadius || cx > light->width + pixelRadius || cy < -pixelRadius || cy > light->height + pixelRadius) { return 0; }
+	if (cx < -pixelRadius || cx > imageWidth + pixelRadius || cy < -pixelRadius || cy > imageHeight + pixelRadius) { return false; }
 	int32_t size = (int32_t)((float)pixelRadius * 2.0f);
 	int32_t l = cx - pixelRadius, t = cy - pixelRadius, r = l + size, b = t + size;
-	if (!(l < light->width && r > 0 && t < light->height && b > 0)) { return 0; }
-	l = l > 0 ? l : 0; t = t > 0 ? t : 0; r = r < light->width ? r : light->width; b = b < light->height ? b : light->height;
-	if (r <= l || b <= t) { return 0; }
+	if (!(l < imageWidth && r > 0 && t < imageHeight && b > 0)) { return false; }
+	l = l > 0 ? l : 0; t = t > 0 ? t : 0; r = r < imageWidth ? r : imageWidth; b = b < imageHeight ? b : imageHeight;
+	if (r <= l || b <= t) { return false; }
 	l = (l / laneCount) * laneCount;
 	r = ((r + laneCount - 1) / laneCount) * laneCount;
-	PointLightParams p;
 	p.left = l; p.top = t; p.width = r - l; p.height = b - t; p.laneCount = laneCount;
-	// ref: lightAPI.cpp:190-206
 	V3 origin = mat_transform(view->screenDepthToLightSpace, V3{0.5f - (float)worldCenter[0] + (float)l, 0.5f - (float)worldCenter[1] + (float)t, 0.0f});
 	p.baseX = origin.x - S.x; p.baseY = origin.y - S.y; p.baseZ = origin.z - S.z;
 	p.dxX = view->screenDepthToLightSpace.xAxis[0]; p.dxY = view->screenDepthToLightSpace.xAxis[1]; p.dxZ = view->screenDepthToLightSpace.xAxis[2];
@@ -557,9 +751,64 @@ int dfpsr_light_point(const dfpsr_ortho_view *view, const int32_t worldCenter[2]
 	p.reciprocalRadius = 1.0f / radius;
 	p.shadow = exists(shadowCubeMap) ? 1 : 0;
 	p.cubeCenter = p.shadow ? (float)shadowCubeMap->width * 0.5f : 0.0f;
-	size_t smem = (size_t)(p.width / laneCount) * 3 * laneCount * sizeof(float);
+	return true;
+}
+
+int dfpsr_light_point(const dfpsr_ortho_view *view, const int32_t worldCenter[2], const dfpsr_image *light, const dfpsr_image *normal, const dfpsr_image *height, const float position[3], float radius, float intensity, const int32_t colorRgb[3], const dfpsr_image *shadowCubeMap, void *stream) {
+	DFPSR_REQUIRE(view && worldCenter && exists(light) && exists(normal) && exists(height) && position && colorRgb, "light_point: null argument");
+	PointLightParams p;
+	if (!point_light_params(p, view, worldCenter, light->width, light->height, position, radius, intensity, colorRgb, shadowCubeMap)) { return 0; }
+	size_t smem = (size_t)(p.width / p.laneCount) * 3 * p.laneCount * sizeof(float);
 	if (smem > 48 * 1024) { DFPSR_CHECK_CUDA(cudaFuncSetAttribute(point_light_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); }
 	DFPSR_LAUNCH(point_light_kernel, p.height, 256, smem, as_stream(stream), img_of(light), img_of(normal), img_of(height), img_of(p.shadow ? shadowCubeMap : nullptr), p);
+	return 0;
+}
+
+// ref: SDK/SpriteEngine/spriteAPI.cpp:775-814 — the light part of SpriteWorldImpl::draw in ONE kernel.
+int dfpsr_light_frame(const dfpsr_ortho_view *view, const int32_t worldCenter[2], const dfpsr_image *color, const dfpsr_image *diffuse, const dfpsr_image *light, const dfpsr_image *normal, const dfpsr_image *height, const dfpsr_directed_light *directed, int32_t directedCount, const dfpsr_point_light *points, int32_t pointCount, void *stream) {
+	DFPSR_REQUIRE(view && worldCenter && exists(light) && exists(normal), "light_frame: null argument");
+	DFPSR_REQUIRE(directedCount >= 0 && pointCount >= 0 && (directedCount == 0 || directed) && (pointCount == 0 || points), "light_frame: bad light arrays");
+	DFPSR_REQUIRE(pointCount == 0 || exists(height), "light_frame: point lights need the height buffer");
+	DFPSR_REQUIRE(light->width == normal->width && light->height == normal->height, "light_frame: light and normal buffers differ in size");
+	DFPSR_REQUIRE(!exists(color) || (exists(diffuse) && color->width == light->width && color->height == light->height && diffuse->width == light->width && diffuse->height == light->height), "light_frame: colour, diffuse and light buffers differ in size");
+	DFPSR_REQUIRE(directedCount <= FRAME_MAX_DIRECTED, "light_frame: at most %d directed lights", FRAME_MAX_DIRECTED);
+	FrameLightParams fp;
+	memset(&fp, 0, sizeof(fp));
+	fp.directedCount = directedCount;
+	for (int32_t i = 0; i < directedCount; i++) {
+		// ref: SDK/SpriteEngine/lightAPI.cpp:26-30 (host-side uniforms)
+		V3 n = normalize3(mat_transform_transposed(view->normalToWorldSpace, V3{directed[i].direction[0], directed[i].direction[1], directed[i].direction[2]}));
+		fp.directed[i][0] = -n.x * directed[i].intensity * 2.0f; fp.directed[i][1] = -n.y * directed[i].intensity * 2.0f; fp.directed[i][2] = -n.z * directed[i].intensity * 2.0f;
+		fp.directed[i][3] = fmaxf(0.0f, (float)directed[i].colorRgb[0] / 255.0f); fp.directed[i][4] = fmaxf(0.0f, (float)directed[i].colorRgb[1] / 255.0f); fp.directed[i][5] = fmaxf(0.0f, (float)directed[i].colorRgb[2] / 255.0f);
+	}
+	static thread_local DeviceBuffer staging;
+	std::vector<FramePointLight> lights;
+	int32_t maxWidth = 0;
+	for (int32_t i = 0; i < pointCount; i++) {
+		FramePointLight fl;
+		if (!point_light_params(fl.p, view, worldCenter, light->width, light->height, points[i].position, points[i].radius, points[i].intensity, points[i].colorRgb, &points[i].shadowCubeMap)) { continue; }
+		fl.cube = img_of(fl.p.shadow ? &points[i].shadowCubeMap : nullptr);
+		if (fl.p.width > maxWidth) { maxWidth = fl.p.width; }
+		lights.push_back(fl);
+	}
+	fp.pointCount = (int32_t)lights.size();
+	if (!lights.empty()) {
+		if (staging.reserve(lights.size() * sizeof(FramePointLight))) { return 1; }
+		DFPSR_CHECK_CUDA(cudaMemcpyAsync(staging.ptr, lights.data(), lights.size() * sizeof(FramePointLight), cudaMemcpyHostToDevice, as_stream(stream)));
+		fp.points = (const FramePointLight *)staging.ptr;
+	}
+	fp.chainStride = maxWidth * 3;
+	// lights per shared-memory group: about 40 KB per CTA keeps five CTAs (40 warps) on an SM; the arithmetic (double-precision rsqrt of
+	// the reference's scalar build, cube-map gathers) needs the occupancy more than it needs fewer barriers
+	size_t perLight = (size_t)fp.chainStride * sizeof(float);
+	fp.group = perLight > 0 ? (int32_t)((40 * 1024) / perLight) : FRAME_LIGHT_GROUP;
+	if (fp.group < 1) { fp.group = 1; }
+	if (fp.group > FRAME_LIGHT_GROUP) { fp.group = FRAME_LIGHT_GROUP; }
+	size_t smem = (size_t)fp.group * perLight;
+	DFPSR_REQUIRE(smem <= 200 * 1024, "light_frame: light rectangles of %d pixels exceed the shared memory budget", maxWidth);
+	if (smem > 48 * 1024) { DFPSR_CHECK_CUDA(cudaFuncSetAttribute(light_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); }
+	Img l = img_of(light);
+	DFPSR_LAUNCH(light_frame_kernel, l.height, 256, smem, as_stream(stream), img_of(exists(color) ? color : nullptr), img_of(exists(color) ? diffuse : nullptr), l, img_of(normal), img_of(exists(height) ? height : nullptr), fp);
 	return 0;
 }
 
@@ -567,7 +816,7 @@ int dfpsr_light_blend(const dfpsr_image *color, const dfpsr_image *diffuse, cons
 	DFPSR_REQUIRE(exists(color) && exists(diffuse) && exists(light), "light_blend: null argument");
 	DFPSR_REQUIRE(color->width == diffuse->width && color->height == diffuse->height && color->width == light->width && color->height == light->height, "light_blend: buffers differ in size");
 	Img c = img_of(color);
-	DFPSR_LAUNCH(blend_kernel, grid_for(c.width, c.height, BLOCK), BLOCK, 0, as_stream(stream), c, img_of(diffuse), img_of(light));
+	DFPSR_LAUNCH(blend_kernel, grid_rows(c.width, c.height, BLOCK), BLOCK, 0, as_stream(stream), c, img_of(diffuse), img_of(light));
 	return 0;
 }
 
@@ -630,6 +879,10 @@ int dfpsr_filter_map(const dfpsr_image *target, int32_t op, const int32_t *param
 	for (int i = 0; i < needed; i++) { mp.p[i] = params[i]; }
 	DFPSR_REQUIRE(op != DFPSR_MAP_AFFINE || exists(source), "filter_map: the affine op needs a source image");
 	Img t = img_of(target);
+	if (op == DFPSR_MAP_AFFINE && startX >= 0 && startY >= 0 && (int64_t)startX + t.width <= source->width && (int64_t)startY + t.height <= source->height) {
+		DFPSR_LAUNCH(map_affine_stream_kernel, grid_rows(t.width, t.height, BLOCK), BLOCK, 0, as_stream(stream), t, img_of(source), mp);
+		return 0;
+	}
 	DFPSR_LAUNCH(map_kernel, grid_for(t.width, t.height, BLOCK), BLOCK, 0, as_stream(stream), t, img_of(exists(source) ? source : nullptr), mp);
 	return 0;
 }
@@ -666,6 +919,11 @@ static int resize_single(const Img &target, const Img &source, bool bilinear, bo
 	if (sameWidth && (samePack || bilinear)) { rp.path = bilinear ? (simdAligned ? RESIZE_VERTICAL_PACKED : RESIZE_VERTICAL) : RESIZE_VERTICAL_NEAREST; }
 	else if (sameHeight) { rp.path = RESIZE_HORIZONTAL; }
 	else { rp.path = RESIZE_GENERAL; }
+	if (rp.path == RESIZE_GENERAL && bilinear && source.width == 2 * target.width && source.height == 2 * target.height) {
+		dim3 grid((unsigned)((target.width + PX * (int)BLOCK.x - 1) / (PX * (int)BLOCK.x)), (unsigned)((target.height + 2 * (int)BLOCK.y - 1) / (2 * (int)BLOCK.y)));
+		DFPSR_LAUNCH(resize_half_kernel, grid, BLOCK, 0, stream, target, source);
+		return 0;
+	}
 	DFPSR_LAUNCH(resize_kernel, grid_for(target.width, target.height, BLOCK), BLOCK, 0, stream, target, source, rp);
 	return 0;
 }

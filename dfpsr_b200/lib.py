@@ -63,6 +63,7 @@ SIGNATURES = {
     "dfpsr_draw_higher_batch": (i32, [P(abi.Image), P(abi.Image), P(abi.Image), vp, i32, vp]),
     "dfpsr_light_directed": (i32, [P(abi.OrthoView), P(abi.Image), P(abi.Image), vp, f32, vp, i32, vp]),
     "dfpsr_light_point": (i32, [P(abi.OrthoView), vp, P(abi.Image), P(abi.Image), P(abi.Image), vp, f32, f32, vp, P(abi.Image), vp]),
+    "dfpsr_light_frame": (i32, [P(abi.OrthoView), vp, P(abi.Image), P(abi.Image), P(abi.Image), P(abi.Image), P(abi.Image), vp, i32, vp, i32, vp]),
     "dfpsr_light_blend": (i32, [P(abi.Image), P(abi.Image), P(abi.Image), vp]),
     "dfpsr_filter_resize_scratch_bytes": (sz, [i32, i32, i32, i32]),
     "dfpsr_filter_resize": (i32, [P(abi.Image), P(abi.Image), i32, i32, vp, vp]),

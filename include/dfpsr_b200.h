@@ -260,6 +260,15 @@ int dfpsr_light_point(const dfpsr_ortho_view *view, const int32_t worldCenter[2]
 /* ref: SDK/SpriteEngine/lightAPI.cpp:287-323 blendLight. */
 int dfpsr_light_blend(const dfpsr_image *color, const dfpsr_image *diffuse, const dfpsr_image *light, void *stream);
 
+/* One Sandbox frame's light passes in a single kernel (ref: SDK/SpriteEngine/spriteAPI.cpp:775-814, the part of SpriteWorldImpl::draw
+ * after drawDeferred): the first directed light overwrites the light buffer (no directed light = black, :783-786), the others and
+ * every point light are added with saturation, then colour = blendLight(diffuse, light) when `color` is given. Same bytes as the
+ * separate calls above; every buffer is read or written once per pixel. Shadow cube maps must already be rendered
+ * (dfpsr_model_render_depth_batch). directed / points are HOST arrays. */
+typedef struct dfpsr_directed_light { float direction[3]; float intensity; int32_t colorRgb[3]; } dfpsr_directed_light;
+typedef struct dfpsr_point_light { float position[3]; float radius, intensity; int32_t colorRgb[3]; dfpsr_image shadowCubeMap; /* data == NULL: no shadows */ } dfpsr_point_light;
+int dfpsr_light_frame(const dfpsr_ortho_view *view, const int32_t worldCenter[2], const dfpsr_image *color, const dfpsr_image *diffuse, const dfpsr_image *light, const dfpsr_image *normal, const dfpsr_image *height, const dfpsr_directed_light *directed, int32_t directedCount, const dfpsr_point_light *points, int32_t pointCount, void *stream);
+
 /* ---------------------------------------------------------------- filters */
 
 /* ref: api/filterAPI.cpp:852-860 filter_resize(ImageRgbaU8): `target` (newWidth x newHeight, RGBA order,

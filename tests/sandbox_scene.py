@@ -256,6 +256,32 @@ class CudaSandbox:
             lib.check(cuda.dfpsr_light_point(C.byref(self.view), sb["worldCenter"].ctypes.data, C.byref(IM(self.L)), C.byref(IM(self.N)), C.byref(IM(self.H)), light["position"].ctypes.data, light["radius"], light["intensity"], light["color"].ctypes.data, C.byref(IM(self.cubes[i])), s))
         lib.check(cuda.dfpsr_light_blend(C.byref(IM(self.C)), C.byref(IM(self.D)), C.byref(IM(self.L)), s))
 
+    def light_fused(self):
+        """Shadow maps in one submission, then directed + all point lights + blend in ONE kernel (dfpsr_light_frame)."""
+        cuda, lib, sb = self.cuda, self.lib, self.sb
+        if not hasattr(self, "batch"):
+            self.prepare_batched()
+        if not hasattr(self, "frame_lights"):
+            d = sb["directed"]
+            directed = (abi.DirectedLight * 1)()
+            directed[0].direction[:] = [float(v) for v in d["direction"]]
+            directed[0].intensity = d["intensity"]
+            directed[0].colorRgb[:] = [int(v) for v in d["color"]]
+            points = (abi.PointLight * len(sb["lights"]))()
+            for i, light in enumerate(sb["lights"]):
+                points[i].position[:] = [float(v) for v in light["position"]]
+                points[i].radius, points[i].intensity = light["radius"], light["intensity"]
+                points[i].colorRgb[:] = [int(v) for v in light["color"]]
+                points[i].shadowCubeMap = lib.image(self.cubes[i])
+            self.frame_lights = (directed, points)
+        s = lib.stream_ptr()
+        IM = lib.image
+        models, transforms, cams, target_of, n, targets, nt = self.batch
+        lib.check(cuda.dfpsr_model_render_depth_batch(models, transforms, cams, target_of, n, targets, nt, 1, 0.0, s))
+        directed, points = self.frame_lights
+        lib.check(cuda.dfpsr_light_frame(C.byref(self.view), sb["worldCenter"].ctypes.data, C.byref(IM(self.C)), C.byref(IM(self.D)), C.byref(IM(self.L)), C.byref(IM(self.N)), C.byref(IM(self.H)),
+                                         directed, len(directed), points, len(points), s))
+
     def results(self):
         u = lambda t: t.cpu().numpy().view(np.uint32)
         return {"height": self.H.cpu().numpy(), "diffuse": u(self.D), "normal": u(self.N), "light": u(self.L), "color": u(self.C)}

@@ -204,6 +204,26 @@ def test_sandbox_frame_batched_shadows(cuda, oracle):
         assert_same_u32(got[key], expected[key], key)
 
 
+@pytest.mark.parametrize("size", [(320, 240), (413, 131), (1100, 90)])
+def test_sandbox_frame_fused_light(cuda, oracle, size):
+    """dfpsr_light_frame: directed + point lights + blend in one kernel == the separate passes, bit for bit. Widths above 1024 exercise
+    more than four pixels per thread, 20 lights exercise two shared-memory groups."""
+    sb = sandbox_scene.build(size[0], size[1], lights=20 if size[0] > 1000 else 5, seed=9, sprites=12, casters=3)
+    expected = sandbox_scene.run_oracle(oracle, sb)
+    gpu = sandbox_scene.CudaSandbox(cuda, sb)
+    gpu.composite()
+    gpu.light_fused()
+    got = gpu.results()
+    assert (expected["light"] != 0).mean() > 0.3
+    for key in ("light", "color"):
+        assert_same_u32(got[key], expected[key], key)
+    # no directed light: the light buffer starts black (ref: SDK/SpriteEngine/spriteAPI.cpp:783-786); no colour target: light only
+    view = sandbox_scene.ortho_view()
+    tl = dev(np.full((size[1], size[0]), 0x12345678, np.uint32))
+    lib.check(cuda.dfpsr_light_frame(C.byref(view), sb["worldCenter"].ctypes.data, None, None, C.byref(IM(tl)), C.byref(IM(gpu.N)), C.byref(IM(gpu.H)), None, 0, None, 0, lib.stream_ptr()))
+    assert np.all(host_u32(tl) == 0)
+
+
 def test_sandbox_800x600_golden(cuda):
     """BASELINE config 2 at full size against hashes produced by the compiled reference."""
     golden = json.load(open(os.path.join(GOLDEN_DIR, "sandbox.json")))["sandbox_800x600_16"]
@@ -217,6 +237,11 @@ def test_sandbox_800x600_golden(cuda):
     assert sha(got["color"]) == golden["color_sha256"]
     gpu.L.zero_()
     gpu.light_batched()
+    got = gpu.results()
+    assert sha(got["light"]) == golden["light_sha256"]
+    gpu.L.zero_()
+    gpu.C.zero_()
+    gpu.light_fused()
     got = gpu.results()
     assert sha(host_f32(gpu.cubes[0])) == golden["cube0_sha256"]
     assert sha(got["light"]) == golden["light_sha256"]
@@ -249,3 +274,33 @@ def test_filter_chain_8192_golden(cuda):
     assert sha(host_u32(resize(mapped, 5000, 3000, abi.SAMPLER_LINEAR))) == golden["odd_5000x3000_sha256"]
     assert sha(host_u32(resize(half, 8192, 8192, abi.SAMPLER_LINEAR))) == golden["up_8192_sha256"]
     assert sha(host_u32(resize(mapped, 3000, 5000, abi.SAMPLER_NEAREST))) == golden["nearest_3000x5000_sha256"]
+
+
+@pytest.mark.parametrize("shape", [(84, 62), (256, 128), (10, 6), (1030, 70)])
+@pytest.mark.parametrize("packs", [(0, 0), (1, 0), (0, 3)])
+def test_filter_resize_exact_half(cuda, oracle, shape, packs):
+    """Bilinear resize to exactly half the size takes the streaming kernel (two byte averages): same bits as the general path."""
+    rng = np.random.default_rng(16)
+    sw, sh = shape
+    src = rand_rgba(rng, sh, sw)
+    ts = dev(src)
+    tt = dev(np.zeros((sh // 2, sw // 2), np.uint32))
+    lib.check(cuda.dfpsr_filter_resize(C.byref(IM(tt, packs[1])), C.byref(IM(ts, packs[0])), abi.SAMPLER_LINEAR, 0, None, lib.stream_ptr()))
+    e = np.zeros((sh // 2, sw // 2), np.uint32)
+    oracle.orc_filter_resize(C.byref(OI(e, packs[1])), C.byref(OI(src, packs[0])), abi.SAMPLER_LINEAR, 0, None)
+    assert_same_u32(host_u32(tt), e, f"half resize {shape} packs={packs}")
+
+
+@pytest.mark.parametrize("packs", [(0, 0), (2, 1)])
+def test_filter_map_affine_streaming(cuda, oracle, packs):
+    """Affine map whose reads all fall inside the source (the streaming kernel), incl. a window of a larger source and ragged widths."""
+    rng = np.random.default_rng(17)
+    src = rand_rgba(rng, 70, 131)
+    ts = dev(src)
+    prm = np.array([3, -2, 1, 0, -100, 400, 7, 128], np.int32)
+    for (tw, th, sx, sy) in [(131, 70, 0, 0), (64, 33, 5, 7), (1, 1, 130, 69), (127, 19, 4, 51)]:
+        tt = dev(np.zeros((th, tw), np.uint32))
+        lib.check(cuda.dfpsr_filter_map(C.byref(IM(tt, packs[1])), abi.MAP_AFFINE, prm.ctypes.data, 8, C.byref(IM(ts, packs[0])), sx, sy, lib.stream_ptr()))
+        e = np.zeros((th, tw), np.uint32)
+        oracle.orc_filter_map(C.byref(OI(e, packs[1])), abi.MAP_AFFINE, orcbind.ptr(prm), C.byref(OI(src, packs[0])), sx, sy)
+        assert_same_u32(host_u32(tt), e, f"affine map {tw}x{th} at ({sx},{sy})")

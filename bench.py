@@ -192,6 +192,7 @@ def main():
     lib.check(cuda.dfpsr_init(local_rank))
     distributed = world > 1
     if distributed:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     sc = scenes.terrain_scene()

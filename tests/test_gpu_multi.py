@@ -1,0 +1,46 @@
+"""Multi-GPU paths on real devices (skipped with fewer than two GPUs): independent views under torchrun with NCCL, and a
+strip-sharded frame gathered with one NCCL all_gather. The CPU-side logic is covered by tests/test_shard_gloo.py."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.gpu
+
+
+def gpu_count():
+    import torch
+    return torch.cuda.device_count()
+
+
+def torchrun(script_args, port):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", str(port)] + script_args
+    return subprocess.run(cmd, capture_output=True, text=True, cwd=ROOT, timeout=600)
+
+
+def last_json(stdout):
+    for line in reversed(stdout.strip().splitlines()):
+        if line.startswith("{"):
+            return json.loads(line)
+    raise AssertionError("no JSON line in: " + stdout[-2000:])
+
+
+def test_strip_sharded_frame_two_gpus():
+    if gpu_count() < 2:
+        pytest.skip("needs two GPUs")
+    out = torchrun(["tools/strip_bench.py", "--scene", "terrain", "--iters", "3"], 29631)
+    assert out.returncode == 0, out.stderr[-3000:]
+    line = last_json(out.stdout)
+    assert line["n_gpus"] == 2 and line["gathered_equals_full_frame"] is True
+
+
+def test_view_sharded_bench_two_gpus():
+    if gpu_count() < 2:
+        pytest.skip("needs two GPUs")
+    out = torchrun(["bench.py", "--gpus", "2", "--steps", "1", "--warmup", "3", "--views", "16", "--no-extras", "--no-cpu-baseline"], 29632)
+    assert out.returncode == 0, out.stderr[-3000:]
+    line = last_json(out.stdout)
+    assert line["n_gpus"] == 2 and line["scaling"] == "weak" and line["value"] > 0 and line["gpu_launches"] > 0

@@ -117,18 +117,24 @@ struct FrameDev {
 	uint32_t *tileList;
 	ChkRec *chk;                     // checkpoint records of large triangles; totals[4] = records needed (upper bound), totals[5] = cursor
 	uint32_t *sortTmp;               // rank-sort scratch, as large as the entry pool; totals[6] = cursor
+	const float *occlusionGrid;      // 16-pixel cells of the farthest depth at which something can still be visible; null = no occluders
+	int32_t gridWidth, gridHeight, gridStride;
 };
 
 // ------------------------------------------------------------------------------------------------ projection
 
 // The reference's int64_t(float) is x86 cvttss2si: out-of-range and NaN give INT64_MIN.
-__device__ __forceinline__ long long float_to_i64(float v) {
+__host__ __device__ __forceinline__ long long float_to_i64(float v) {
 	if (!(fabsf(v) < 9.2233720368547758e18f)) { return (long long)0x8000000000000000ull; }
+#ifdef __CUDA_ARCH__
 	return __float2ll_rz(v);
+#else
+	return (long long)v; // host copy for the occlusion grid (compiled with -ffp-contract=off)
+#endif
 }
 
 // ref: implementation/render/Camera.h:160-187
-__device__ __forceinline__ PPoint camera_to_screen(const dfpsr_camera &c, float x, float y, float z) {
+__host__ __device__ __forceinline__ PPoint camera_to_screen(const dfpsr_camera &c, float x, float y, float z) {
 	PPoint r;
 	r.csx = x; r.csy = y; r.csz = z; r.pad = 0;
 	if (c.perspective) {
@@ -203,7 +209,7 @@ __device__ __forceinline__ bool is_frontfacing(const PPoint *p) {
 	return ((p[2].fx - p[0].fx) * (p[1].fy - p[0].fy)) + ((p[2].fy - p[0].fy) * (p[0].fx - p[1].fx)) < 0;
 }
 
-struct Bound { int32_t l, t, r, b; bool any; };
+struct Bound { int32_t l, t, r, b; bool any; int32_t wl, wt, wr, wb; /* whole (unclipped) bound, ref: ITriangle2D.h wholeBound */ };
 
 // ref: implementation/render/ITriangle2D.cpp:31-43, :62-75 — pixel bound, cut to the clip rectangle (0, clipTop, width, clipBottom - clipTop)
 // exactly like executeTriangleDrawing's clipBound (renderCore.cpp:203-217), rows aligned to 2.
@@ -214,6 +220,7 @@ __device__ Bound raster_bound(const PPoint *p, int32_t width, int32_t clipTop, i
 	int32_t l = min(rx0, min(rx1, rx2)) - 1, t = min(ry0, min(ry1, ry2)) - 1;
 	int32_t r = max(rx0, max(rx1, rx2)) + 1, b = max(ry0, max(ry1, ry2)) + 1;
 	Bound out;
+	out.wl = l; out.wt = t; out.wr = r; out.wb = b;
 	out.any = l < width && r > 0 && t < clipBottom && b > clipTop; // IRect::overlaps (math/IRect.h:77)
 	if (!out.any) { out.l = out.t = out.r = out.b = 0; return out; }
 	out.l = max(l, 0); out.r = min(r, width);
@@ -460,6 +467,64 @@ __device__ bool load_triangle(const TaskParams &task, int32_t local, PPoint *p, 
 }
 
 
+// ------------------------------------------------------------------------------------------------ occlusion grid (ref: api/rendererAPI.cpp:36-351, :403-477)
+
+static const int CELL_SIZE = 16; // ref: api/rendererAPI.cpp:36
+
+struct CellBound { int32_t x0, y0, x1, y1; };
+// ref: api/rendererAPI.cpp:169-180 getOuterCellBound (C++ division truncates toward zero, also for negative pixel coordinates)
+__host__ __device__ __forceinline__ CellBound outer_cell_bound(int32_t left, int32_t top, int32_t right, int32_t bottom, int32_t gridWidth, int32_t gridHeight) {
+	CellBound c;
+	c.x0 = left / CELL_SIZE; c.x1 = right / CELL_SIZE + 1; c.y0 = top / CELL_SIZE; c.y1 = bottom / CELL_SIZE + 1;
+	if (c.x0 < 0) { c.x0 = 0; } if (c.y0 < 0) { c.y0 = 0; }
+	if (c.x1 > gridWidth) { c.x1 = gridWidth; } if (c.y1 > gridHeight) { c.y1 = gridHeight; }
+	return c;
+}
+// ref: api/rendererAPI.cpp:99-135 pointInsideOfHull on the four corners of a cell, in 1/256 pixel units
+__host__ __device__ __forceinline__ bool point_inside_of_hull(const PPoint *hull, int count, long long x, long long y) {
+	for (int c = 0; c < count; c++) {
+		int nc = c + 1 == count ? 0 : c + 1;
+		long long dirX = hull[nc].fy - hull[c].fy, dirY = hull[c].fx - hull[nc].fx;
+		if (!((dirX * (x - hull[c].fx)) + (dirY * (y - hull[c].fy)) <= 0)) { return false; }
+	}
+	return true;
+}
+__host__ __device__ __forceinline__ bool cell_inside_of_hull(const PPoint *hull, int count, int32_t cellX, int32_t cellY) {
+	long long l = (long long)cellX * CELL_SIZE * 256, t = (long long)cellY * CELL_SIZE * 256, r = l + CELL_SIZE * 256, b = t + CELL_SIZE * 256;
+	return point_inside_of_hull(hull, count, l, t) && point_inside_of_hull(hull, count, r, t) && point_inside_of_hull(hull, count, l, b) && point_inside_of_hull(hull, count, r, b);
+}
+
+// ref: api/rendererAPI.cpp:193-217 completeOcclusion for one command: nothing of it can be visible in any cell its whole bound touches
+__device__ __forceinline__ bool command_occluded(const FrameDev &frame, const Bound &bound, const PPoint *q) {
+	if (frame.occlusionGrid == nullptr) { return false; }
+	const CellBound cells = outer_cell_bound(bound.wl, bound.wt, bound.wr, bound.wb, frame.gridWidth, frame.gridHeight);
+	const float triangleDepth = fminf(q[0].csz, fminf(q[1].csz, q[2].csz));
+	for (int32_t cy = cells.y0; cy < cells.y1; cy++) {
+		for (int32_t cx = cells.x0; cx < cells.x1; cx++) {
+			if ((double)triangleDepth < (double)frame.occlusionGrid[cy * frame.gridStride + cx] + 0.001) { return false; }
+		}
+	}
+	return true;
+}
+
+// ref: api/rendererAPI.cpp:403-477 occludeFromTopRows: per cell the extreme of the FIRST pixel row of its cell row (the reference scans
+// columns [16 k - 1, 16 k + 15) for cell k > 0 and [0, 15) for cell 0). out[cell] = the distance the host merges into the grid.
+__global__ void __launch_bounds__(256) top_rows_kernel(dfpsr_image depth, int32_t width, int32_t gridWidth, int32_t gridHeight, int32_t perspective, float *__restrict__ out) {
+	int32_t cell = blockIdx.x * blockDim.x + threadIdx.x;
+	if (cell >= gridWidth * gridHeight) { return; }
+	int32_t gx = cell % gridWidth, gy = cell / gridWidth;
+	int32_t x0 = gx == 0 ? 0 : gx * CELL_SIZE - 1, x1 = gx * CELL_SIZE + CELL_SIZE - 1;
+	if (x1 >= width) { x1 = width; }
+	if (x0 > x1) { x0 = x1; } // cells after the first capped one see an empty range
+	const float *row = row_ptr<float>(depth.data, depth.stride, gy * CELL_SIZE);
+	float extreme = perspective ? INFINITY : 0.0f;
+	for (int32_t x = x0; x < x1; x++) {
+		float v = row[x];
+		if (perspective) { if (v < extreme) { extreme = v; } } else { if (v > extreme) { extreme = v; } }
+	}
+	out[cell] = perspective ? 1.0f / extreme : extreme;
+}
+
 // ------------------------------------------------------------------------------------------------ set-up kernel
 
 // A command whose tile counting (counting pass) or rows + tile entries (emit pass) are produced cooperatively by one warp.
@@ -608,7 +673,8 @@ __global__ void __launch_bounds__(SETUP_THREADS) setup_kernel(FrameDev frame) {
 		float alpha[3] = {colors[0][3], colors[1][3], colors[2][3]};
 		for_each_command(task, p, alpha, [&](const PPoint *q, const float *subB, const float *subC) {
 			Bound bound = raster_bound(q, width, clipTop, clipBottom);
-			const int32_t rowCount = bound.any ? bound.b - bound.t : 0;
+			// ref: api/rendererAPI.cpp:193-217 — a command that the occlusion grid hides stays in the queue (it keeps its index) but draws nothing
+			const int32_t rowCount = (bound.any && !command_occluded(frame, bound, q)) ? bound.b - bound.t : 0;
 			const int32_t tx0 = bound.l / TILE_W, tx1 = (bound.r - 1) / TILE_W, ty0 = bound.t / TILE_H, ty1 = (min(bound.b, height) - 1) / TILE_H;
 			const bool small = rowCount <= SMALL_ROWS && (bound.r - bound.l) <= SMALL_WIDTH;
 			if (!EMIT) {
@@ -766,6 +832,37 @@ __global__ void __launch_bounds__(SETUP_THREADS) setup_kernel(FrameDev frame) {
 			frame.blockRows[blockIdx.x] = b;
 		}
 	}
+}
+
+// ref: api/rendererAPI.cpp:242-258 occludeFromExistingTriangles: every solid command queued so far is an occluder for the cells that lie
+// completely inside it (occludeFromSortedHull, :218-241). The grid keeps the minimum, so the order of the atomics does not matter.
+__global__ void __launch_bounds__(SETUP_THREADS) occlude_existing_kernel(FrameDev frame, float *grid) {
+	__shared__ TaskParams task;
+	{
+		int32_t t = task_of_block(frame.tasks, frame.taskCount, (int32_t)blockIdx.x);
+		for (uint32_t w = threadIdx.x; w < sizeof(TaskParams) / 4; w += blockDim.x) { ((uint32_t *)&task)[w] = ((const uint32_t *)&frame.tasks[t])[w]; }
+	}
+	__syncthreads();
+	if (task.filter != DFPSR_FILTER_SOLID) { return; }
+	const ViewDev &view = frame.views[task.view];
+	const int32_t local = ((int32_t)blockIdx.x - task.blockBase) * SETUP_THREADS + threadIdx.x;
+	if (local >= task.slotCount) { return; }
+	PPoint p[3];
+	float colors[3][4], tex[3][4];
+	if (!load_triangle(task, local, p, colors, tex)) { return; }
+	float alpha[3] = {colors[0][3], colors[1][3], colors[2][3]};
+	const int32_t width = view.width, clipTop = view.clipTop, clipBottom = view.clipBottom;
+	for_each_command(task, p, alpha, [&](const PPoint *q, const float *, const float *) {
+		Bound bound = raster_bound(q, width, clipTop, clipBottom);
+		if (!(bound.wr - bound.wl > CELL_SIZE && bound.wb - bound.wt > CELL_SIZE)) { return; }
+		float distance = fmaxf(0.0f, fmaxf(q[0].csz, fmaxf(q[1].csz, q[2].csz)));
+		const CellBound cells = outer_cell_bound(bound.wl, bound.wt, bound.wr, bound.wb, frame.gridWidth, frame.gridHeight);
+		for (int32_t cy = cells.y0; cy < cells.y1; cy++) {
+			for (int32_t cx = cells.x0; cx < cells.x1; cx++) {
+				if (cell_inside_of_hull(q, 3, cx, cy)) { atomicMin((int *)&grid[cy * frame.gridStride + cx], __float_as_int(distance)); }
+			}
+		}
+	});
 }
 
 // One CTA: exclusive scans of the per-block command and row totals (submission order is preserved).
@@ -1464,10 +1561,15 @@ struct dfpsr_renderer {
 	int64_t lastCommands = -1;
 	DeviceBuffer dTasks, dViews, projected, slotCounts, blockCmds, blockRows, tileCount, tileOffset, tileCursor, cmds, rows, tileList, chk, sortTmp;
 	uint32_t *hostTotals = nullptr, *hostTotalsDevice = nullptr; // mapped pinned memory and its device alias
+	// occlusion grid (ref: api/rendererAPI.cpp:145, :181-192): lives on the host, where occluder boxes and visibility queries are evaluated
+	std::vector<float> grid;
+	int32_t gridWidth = 0, gridHeight = 0, gridAllocW = 0, gridAllocH = 0;
+	bool occluded = false;
+	DeviceBuffer dGrid;
 
 	~dfpsr_renderer() {
 		for (auto &b : uploads) { b.release(); }
-		DeviceBuffer *all[] = {&dTasks, &dViews, &projected, &slotCounts, &blockCmds, &blockRows, &tileCount, &tileOffset, &tileCursor, &cmds, &rows, &tileList, &chk, &sortTmp};
+		DeviceBuffer *all[] = {&dTasks, &dViews, &projected, &slotCounts, &blockCmds, &blockRows, &tileCount, &tileOffset, &tileCursor, &cmds, &rows, &tileList, &chk, &sortTmp, &dGrid};
 		for (auto *b : all) { b->release(); }
 		if (hostTotals) { cudaFreeHost(hostTotals); }
 	}
@@ -1509,6 +1611,7 @@ static int renderer_begin_internal(dfpsr_renderer *r, bool depthOnly) {
 	DFPSR_REQUIRE(!r->receiving, "Called renderer_begin on the same renderer twice without ending the previous batch!");
 	r->receiving = true;
 	r->depthOnly = depthOnly;
+	r->occluded = false;
 	r->views.clear();
 	r->tasks.clear();
 	r->uploadCount = 0;
@@ -1544,6 +1647,36 @@ static int add_model_task(dfpsr_renderer *r, int32_t view, const dfpsr_model *mo
 	return 0;
 }
 
+// Gives every task its slot, block and projected-point ranges (tasks own contiguous ranges in submission order).
+static int layout_tasks(dfpsr_renderer *r, int32_t &slotTotal, int32_t &blockTotal) {
+	slotTotal = 0; blockTotal = 0;
+	size_t pointTotal = 0;
+	for (TaskParams &t : r->tasks) {
+		t.slotBase = slotTotal; t.blockBase = blockTotal;
+		t.blockCount = (t.slotCount + SETUP_THREADS - 1) / SETUP_THREADS;
+		slotTotal += t.slotCount; blockTotal += t.blockCount;
+		if (t.triangles == nullptr) { pointTotal += (size_t)t.pointCount; }
+	}
+	if (r->projected.reserve(pointTotal * sizeof(PPoint) + 16)) { return 1; }
+	size_t at = 0;
+	for (TaskParams &t : r->tasks) {
+		if (t.triangles == nullptr) { t.projected = (PPoint *)r->projected.ptr + at; at += (size_t)t.pointCount; }
+	}
+	return 0;
+}
+
+static int launch_projection(dfpsr_renderer *r, const FrameDev &frame, cudaStream_t stream) {
+	int32_t maxPoints = 0;
+	for (const TaskParams &t : r->tasks) { if (t.triangles == nullptr && t.pointCount > maxPoints) { maxPoints = t.pointCount; } }
+	if (maxPoints > 0) {
+		dim3 grid((unsigned)((maxPoints + 255) / 256), (unsigned)r->tasks.size());
+		if (grid.x > 1024u) { grid.x = 1024u; }
+		DFPSR_REQUIRE(r->tasks.size() <= 65535, "more than 65535 tasks in one frame");
+		DFPSR_LAUNCH(project_kernel, grid, 256, 0, stream, frame.tasks);
+	}
+	return 0;
+}
+
 static int renderer_end_internal(dfpsr_renderer *r, cudaStream_t stream) {
 	// ref: api/rendererAPI.cpp:352-402
 	DFPSR_REQUIRE(r->receiving, "Called renderer_end without renderer_begin!");
@@ -1559,20 +1692,7 @@ static int renderer_end_internal(dfpsr_renderer *r, cudaStream_t stream) {
 	}
 	if (tileTotal == 0 || (r->tasks.empty() && !anyClear)) { return 0; }
 	int32_t slotTotal = 0, blockTotal = 0;
-	size_t pointTotal = 0;
-	for (TaskParams &t : r->tasks) {
-		t.slotBase = slotTotal; t.blockBase = blockTotal;
-		t.blockCount = (t.slotCount + SETUP_THREADS - 1) / SETUP_THREADS;
-		slotTotal += t.slotCount; blockTotal += t.blockCount;
-		if (t.triangles == nullptr) { pointTotal += (size_t)t.pointCount; }
-	}
-	if (r->projected.reserve(pointTotal * sizeof(PPoint) + 16)) { return 1; }
-	{
-		size_t at = 0;
-		for (TaskParams &t : r->tasks) {
-			if (t.triangles == nullptr) { t.projected = (PPoint *)r->projected.ptr + at; at += (size_t)t.pointCount; }
-		}
-	}
+	if (layout_tasks(r, slotTotal, blockTotal)) { return 1; }
 	const size_t taskCount = r->tasks.size(), viewCount = r->views.size();
 	if (r->dTasks.reserve(taskCount * sizeof(TaskParams) + 16) || r->dViews.reserve(viewCount * sizeof(ViewDev))) { return 1; }
 	if (r->tileCount.reserve(((size_t)tileTotal + 8) * 4) || r->tileOffset.reserve(((size_t)tileTotal + 1) * 4) || r->tileCursor.reserve(((size_t)tileTotal + 1) * 4)) { return 1; }
@@ -1595,13 +1715,13 @@ static int renderer_end_internal(dfpsr_renderer *r, cudaStream_t stream) {
 	frame.totals = frame.tileCount + tileTotal;
 
 	if (taskCount > 0) {
-		int32_t maxPoints = 0;
-		for (const TaskParams &t : r->tasks) { if (t.triangles == nullptr && t.pointCount > maxPoints) { maxPoints = t.pointCount; } }
-		if (maxPoints > 0) {
-			dim3 grid((unsigned)((maxPoints + 255) / 256), (unsigned)taskCount);
-			if (grid.x > 1024u) { grid.x = 1024u; }
-			DFPSR_REQUIRE(taskCount <= 65535, "more than 65535 tasks in one frame");
-			DFPSR_LAUNCH(project_kernel, grid, 256, 0, stream, frame.tasks);
+		if (launch_projection(r, frame, stream)) { return 1; }
+		if (r->occluded) {
+			// completeOcclusion (ref: api/rendererAPI.cpp:193-217) happens inside the set-up kernels, against the grid as it is now
+			if (r->dGrid.reserve(r->grid.size() * sizeof(float) + 16)) { return 1; }
+			DFPSR_CHECK_CUDA(cudaMemcpyAsync(r->dGrid.ptr, r->grid.data(), r->grid.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
+			frame.occlusionGrid = (const float *)r->dGrid.ptr;
+			frame.gridWidth = r->gridWidth; frame.gridHeight = r->gridHeight; frame.gridStride = r->gridAllocW;
 		}
 		DFPSR_LAUNCH(setup_kernel<false>, blockTotal, SETUP_THREADS, 0, stream, frame);
 		DFPSR_LAUNCH(scan_blocks_kernel, 1, 1024, 0, stream, frame);
@@ -1669,6 +1789,8 @@ int dfpsr_renderer_begin_cleared(dfpsr_renderer *renderer, const dfpsr_image *co
 	return begin_one_view(renderer, color, depth, false, true, packedClearColor, clearDepth);
 }
 
+static bool box_visible(const dfpsr_renderer *r, const float *mn, const float *mx, const dfpsr_transform3d *m2w, const dfpsr_camera *camera);
+
 int dfpsr_renderer_set_clip_rows(dfpsr_renderer *renderer, int32_t top, int32_t bottom) {
 	DFPSR_REQUIRE(renderer != nullptr && renderer->receiving && renderer->views.size() == 1, "renderer_set_clip_rows: call between renderer_begin and renderer_end");
 	ViewDev &v = renderer->views[0];
@@ -1682,6 +1804,8 @@ int dfpsr_renderer_give_task(dfpsr_renderer *renderer, const dfpsr_model *model,
 	DFPSR_REQUIRE(renderer != nullptr && model != nullptr && modelToWorld != nullptr && camera != nullptr, "renderer_giveTask: null argument");
 	DFPSR_REQUIRE(renderer->receiving, "Cannot call renderer_giveTask before renderer_begin!");
 	(void)stream;
+	// ref: api/modelAPI.cpp:229-234 — whole models hidden by the occluders given so far are skipped
+	if (renderer->occluded && dfpsr_camera_is_box_seen(camera, model->minBound, model->maxBound, modelToWorld) && !box_visible(renderer, model->minBound, model->maxBound, modelToWorld, camera)) { return 0; }
 	return add_model_task(renderer, 0, model, modelToWorld, camera);
 }
 
@@ -1709,6 +1833,179 @@ int dfpsr_renderer_give_task_triangles(dfpsr_renderer *renderer, const dfpsr_tri
 	task.lightIndex = register_texture(renderer, light);
 	DFPSR_REQUIRE(task.diffuseIndex != -2 && task.lightIndex != -2, "more than %d distinct textures in one frame", MAX_TEXTURES);
 	renderer->tasks.push_back(task);
+	return 0;
+}
+
+// ---- occlusion (ref: api/rendererAPI.cpp:181-351, :403-477, :521-562)
+
+// ref: api/rendererAPI.cpp:181-192 prepareForOcclusion
+static void prepare_for_occlusion(dfpsr_renderer *r) {
+	const ViewDev &v = r->views[0];
+	r->gridWidth = (v.width + (CELL_SIZE - 1)) / CELL_SIZE;
+	r->gridHeight = (v.height + (CELL_SIZE - 1)) / CELL_SIZE;
+	if (!r->occluded) {
+		if (!(!r->grid.empty() && r->gridAllocW >= r->gridWidth && r->gridAllocH >= r->gridHeight)) {
+			r->gridAllocW = r->gridWidth; r->gridAllocH = r->gridHeight;
+			r->grid.assign((size_t)(r->gridAllocW * r->gridAllocH > 0 ? r->gridAllocW * r->gridAllocH : 1), INFINITY);
+		}
+		for (float &cell : r->grid) { cell = INFINITY; }
+	}
+	r->occluded = true;
+}
+static float grid_read(const dfpsr_renderer *r, int32_t x, int32_t y) { // image_readPixel_clamp; a grid that does not exist reads 0
+	if (r->grid.empty() || r->gridAllocW <= 0 || r->gridAllocH <= 0) { return 0.0f; }
+	x = x < 0 ? 0 : (x >= r->gridAllocW ? r->gridAllocW - 1 : x); y = y < 0 ? 0 : (y >= r->gridAllocH ? r->gridAllocH - 1 : y);
+	return r->grid[(size_t)y * r->gridAllocW + x];
+}
+static PPoint host_camera_point(const dfpsr_camera *c, const dfpsr_transform3d *m, const float *p, float *cameraSpace) {
+	float wx = (p[0] * m->xAxis[0] + p[1] * m->yAxis[0] + p[2] * m->zAxis[0]) + m->position[0];
+	float wy = (p[0] * m->xAxis[1] + p[1] * m->yAxis[1] + p[2] * m->zAxis[1]) + m->position[1];
+	float wz = (p[0] * m->xAxis[2] + p[1] * m->yAxis[2] + p[2] * m->zAxis[2]) + m->position[2];
+	const dfpsr_transform3d &l = c->location;
+	float dx = wx - l.position[0], dy = wy - l.position[1], dz = wz - l.position[2];
+	cameraSpace[0] = dx * l.xAxis[0] + dy * l.xAxis[1] + dz * l.xAxis[2];
+	cameraSpace[1] = dx * l.yAxis[0] + dy * l.yAxis[1] + dz * l.yAxis[2];
+	cameraSpace[2] = dx * l.zAxis[0] + dy * l.zAxis[1] + dz * l.zAxis[2];
+	return camera_to_screen(*c, cameraSpace[0], cameraSpace[1], cameraSpace[2]);
+}
+static bool host_plane_inside(const float *pl, float x, float y, float z) { return (((pl[0] * x) + (pl[1] * y) + (pl[2] * z)) - pl[3]) <= 0.0f; }
+static void box_corner(float *out, const float *mn, const float *mx, int i) { out[0] = (i & 4) ? mx[0] : mn[0]; out[1] = (i & 2) ? mx[1] : mn[1]; out[2] = (i & 1) ? mx[2] : mn[2]; }
+// ref: api/rendererAPI.cpp:89-95 getPixelBoundFromProjection (left, top, right, bottom)
+static void pixel_bound_from_projection(const PPoint *hull, int count, int32_t *bound) {
+	bound[0] = (int32_t)(hull[0].fx / 256); bound[1] = (int32_t)(hull[0].fy / 256); bound[2] = bound[0] + 1; bound[3] = bound[1] + 1;
+	for (int p = 1; p < count; p++) {
+		int32_t x = (int32_t)(hull[p].fx / 256), y = (int32_t)(hull[p].fy / 256);
+		if (x < bound[0]) { bound[0] = x; } if (y < bound[1]) { bound[1] = y; }
+		if (x + 1 > bound[2]) { bound[2] = x + 1; } if (y + 1 > bound[3]) { bound[3] = y + 1; }
+	}
+}
+
+// ref: api/rendererAPI.cpp:268-299 occludeFromBox (host: a handful of occluders per frame, the grid is a few thousand cells)
+int dfpsr_renderer_occlude_from_box(dfpsr_renderer *renderer, const float minBound[3], const float maxBound[3], const dfpsr_transform3d *modelToWorld, const dfpsr_camera *camera) {
+	DFPSR_REQUIRE(renderer != nullptr && minBound && maxBound && modelToWorld && camera, "renderer_occludeFromBox: null argument");
+	DFPSR_REQUIRE(renderer->receiving && renderer->views.size() == 1, "Cannot call renderer_occludeFromBox without first calling renderer_begin!");
+	prepare_for_occlusion(renderer);
+	PPoint projected[8], hull[8];
+	for (int p = 0; p < 8; p++) { // projectHull (:76-88)
+		float local[3], cs[3];
+		box_corner(local, minBound, maxBound, p);
+		projected[p] = host_camera_point(camera, modelToWorld, local, cs);
+		for (int s = 0; s < camera->cullPlaneCount; s++) {
+			if (!host_plane_inside(camera->cullPlanes[s], cs[0] * 0.5f, cs[1] * 0.5f, cs[2] * 1.0f)) { return 0; }
+		}
+	}
+	// jarvisConvexHullAlgorithm (:38-74)
+	int count = 0, l = 0;
+	for (int i = 1; i < 8; i++) { if (projected[i].fx < projected[l].fx) { l = i; } }
+	int p = l;
+	do {
+		if (count >= 8) { break; }
+		hull[count++] = projected[p];
+		int q = (p + 1) % 8;
+		for (int i = 0; i < 8; i++) {
+			const PPoint &a = projected[p], &b = projected[i], &c = projected[q];
+			if ((b.fy - a.fy) * (c.fx - b.fx) - (b.fx - a.fx) * (c.fy - b.fy) < 0) { q = i; }
+		}
+		p = q;
+	} while (p != l);
+	// occludeFromSortedHull (:218-241)
+	int32_t bound[4];
+	pixel_bound_from_projection(hull, count, bound);
+	if (!(bound[2] - bound[0] > CELL_SIZE && bound[3] - bound[1] > CELL_SIZE)) { return 0; }
+	float distance = 0.0f;
+	for (int c = 0; c < count; c++) { if (hull[c].csz > distance) { distance = hull[c].csz; } }
+	CellBound cells = outer_cell_bound(bound[0], bound[1], bound[2], bound[3], renderer->gridWidth, renderer->gridHeight);
+	for (int32_t cy = cells.y0; cy < cells.y1; cy++) {
+		for (int32_t cx = cells.x0; cx < cells.x1; cx++) {
+			if (cell_inside_of_hull(hull, count, cx, cy) && distance < grid_read(renderer, cx, cy)) { renderer->grid[(size_t)cy * renderer->gridAllocW + cx] = distance; }
+		}
+	}
+	return 0;
+}
+
+int dfpsr_renderer_has_occluders(const dfpsr_renderer *renderer) { return renderer != nullptr && renderer->occluded ? 1 : 0; } // ref: :557-562
+
+// ref: api/rendererAPI.cpp:302-351 isHullOccluded / isBoxOccluded, negated as in renderer_isBoxVisible (:538-543)
+static bool box_visible(const dfpsr_renderer *r, const float *mn, const float *mx, const dfpsr_transform3d *m2w, const dfpsr_camera *camera) {
+	PPoint projected[8];
+	float cs[8][3];
+	for (int p = 0; p < 8; p++) {
+		float local[3];
+		box_corner(local, mn, mx, p);
+		projected[p] = host_camera_point(camera, m2w, local, cs[p]);
+	}
+	for (int s = 0; s < camera->cullPlaneCount; s++) {
+		bool allOutside = true;
+		for (int p = 0; p < 8; p++) { if (host_plane_inside(camera->cullPlanes[s], cs[p][0], cs[p][1], cs[p][2])) { allOutside = false; break; } }
+		if (allOutside) { return false; }
+	}
+	int32_t bound[4];
+	pixel_bound_from_projection(projected, 8, bound);
+	float closest = INFINITY;
+	for (int c = 0; c < 8; c++) { if (projected[c].csz < closest) { closest = projected[c].csz; } }
+	int32_t gridWidth = (r->views[0].width + (CELL_SIZE - 1)) / CELL_SIZE, gridHeight = (r->views[0].height + (CELL_SIZE - 1)) / CELL_SIZE;
+	CellBound cells = outer_cell_bound(bound[0], bound[1], bound[2], bound[3], gridWidth, gridHeight);
+	for (int32_t cy = cells.y0; cy < cells.y1; cy++) {
+		for (int32_t cx = cells.x0; cx < cells.x1; cx++) { if (closest < grid_read(r, cx, cy)) { return true; } }
+	}
+	return false;
+}
+int dfpsr_renderer_is_box_visible(const dfpsr_renderer *renderer, const float minBound[3], const float maxBound[3], const dfpsr_transform3d *modelToWorld, const dfpsr_camera *camera, int32_t *visible) {
+	DFPSR_REQUIRE(renderer != nullptr && minBound && maxBound && modelToWorld && camera && visible, "renderer_isBoxVisible: null argument");
+	DFPSR_REQUIRE(renderer->receiving && renderer->views.size() == 1, "Cannot call renderer_isBoxVisible without first calling renderer_begin and giving occluder shapes to the pass!");
+	*visible = box_visible(renderer, minBound, maxBound, modelToWorld, camera) ? 1 : 0;
+	return 0;
+}
+
+// ref: api/rendererAPI.cpp:403-477 occludeFromTopRows: the depth buffer is on the device, so one small kernel reduces the scanned row of
+// every cell and the host merges the result into its grid (one synchronisation, like the reference's read of the depth buffer).
+int dfpsr_renderer_occlude_from_top_rows(dfpsr_renderer *renderer, const dfpsr_camera *camera, void *stream) {
+	DFPSR_REQUIRE(renderer != nullptr && camera != nullptr, "renderer_occludeFromTopRows: null argument");
+	DFPSR_REQUIRE(renderer->receiving && renderer->views.size() == 1, "Cannot call renderer_occludeFromTopRows without first calling renderer_begin!");
+	const ViewDev &v = renderer->views[0];
+	DFPSR_REQUIRE(v.depth.data != nullptr, "Cannot call renderer_occludeFromTopRows without having given a depth buffer in renderer_begin!");
+	prepare_for_occlusion(renderer);
+	const int32_t cells = renderer->gridWidth * renderer->gridHeight;
+	if (cells <= 0) { return 0; }
+	if (renderer->dGrid.reserve((size_t)cells * sizeof(float) + renderer->grid.size() * sizeof(float) + 16)) { return 1; }
+	std::vector<float> rowExtremes((size_t)cells);
+	DFPSR_LAUNCH(top_rows_kernel, (cells + 255) / 256, 256, 0, as_stream(stream), v.depth, v.width, renderer->gridWidth, renderer->gridHeight, camera->perspective, (float *)renderer->dGrid.ptr);
+	DFPSR_CHECK_CUDA(cudaMemcpyAsync(rowExtremes.data(), renderer->dGrid.ptr, (size_t)cells * sizeof(float), cudaMemcpyDeviceToHost, as_stream(stream)));
+	DFPSR_CHECK_CUDA(cudaStreamSynchronize(as_stream(stream)));
+	for (int32_t gy = 0; gy < renderer->gridHeight; gy++) {
+		for (int32_t gx = 0; gx < renderer->gridWidth; gx++) {
+			float maxDistance = rowExtremes[(size_t)gy * renderer->gridWidth + gx];
+			float &cell = renderer->grid[(size_t)gy * renderer->gridAllocW + gx];
+			if (maxDistance < cell) { cell = maxDistance; }
+		}
+	}
+	return 0;
+}
+
+// ref: api/rendererAPI.cpp:242-258 occludeFromExistingTriangles: the triangles queued so far are projected, culled and clipped on the
+// device and rasterised into the grid as occluders; the grid then returns to the host for the following visibility queries.
+int dfpsr_renderer_occlude_from_existing_triangles(dfpsr_renderer *renderer, void *stream) {
+	DFPSR_REQUIRE(renderer != nullptr, "renderer_occludeFromExistingTriangles: renderer does not exist");
+	DFPSR_REQUIRE(renderer->receiving && renderer->views.size() == 1, "Cannot call renderer_occludeFromExistingTriangles without first calling renderer_begin!");
+	prepare_for_occlusion(renderer);
+	dfpsr_renderer *r = renderer;
+	if (r->tasks.empty()) { return 0; }
+	cudaStream_t s = as_stream(stream);
+	int32_t slotTotal = 0, blockTotal = 0;
+	if (layout_tasks(r, slotTotal, blockTotal)) { return 1; }
+	if (r->dTasks.reserve(r->tasks.size() * sizeof(TaskParams) + 16) || r->dViews.reserve(sizeof(ViewDev)) || r->dGrid.reserve(r->grid.size() * sizeof(float) + 16)) { return 1; }
+	DFPSR_CHECK_CUDA(cudaMemcpyAsync(r->dTasks.ptr, r->tasks.data(), r->tasks.size() * sizeof(TaskParams), cudaMemcpyHostToDevice, s));
+	DFPSR_CHECK_CUDA(cudaMemcpyAsync(r->dViews.ptr, r->views.data(), sizeof(ViewDev), cudaMemcpyHostToDevice, s));
+	DFPSR_CHECK_CUDA(cudaMemcpyAsync(r->dGrid.ptr, r->grid.data(), r->grid.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+	FrameDev frame;
+	memset(&frame, 0, sizeof(frame));
+	frame.tasks = (const TaskParams *)r->dTasks.ptr; frame.views = (const ViewDev *)r->dViews.ptr;
+	frame.taskCount = (int32_t)r->tasks.size(); frame.viewCount = 1; frame.blockCount = blockTotal;
+	frame.gridWidth = r->gridWidth; frame.gridHeight = r->gridHeight; frame.gridStride = r->gridAllocW;
+	if (launch_projection(r, frame, s)) { return 1; }
+	DFPSR_LAUNCH(occlude_existing_kernel, blockTotal, SETUP_THREADS, 0, s, frame, (float *)r->dGrid.ptr);
+	DFPSR_CHECK_CUDA(cudaMemcpyAsync(r->grid.data(), r->dGrid.ptr, r->grid.size() * sizeof(float), cudaMemcpyDeviceToHost, s));
+	DFPSR_CHECK_CUDA(cudaStreamSynchronize(s));
 	return 0;
 }
 

@@ -454,6 +454,31 @@ inline void renderer_giveTask_triangle(Renderer &renderer, const dfpsr_projected
 	dfpsr_texture d = diffuse.pod(), l = light.pod();
 	b200_check(dfpsr_renderer_give_task_triangles(renderer->handle, &tri, 1, &d, &l, (int32_t)filter, &camera.pod, b200_stream()));
 }
+// ref: api/rendererAPI.h:73-97, :131 — the occlusion grid
+inline void renderer_occludeFromBox(Renderer &renderer, const FVector3D &minimum, const FVector3D &maximum, const Transform3D &modelToWorldTransform, const Camera &camera, bool debugSilhouette = false) {
+	(void)debugSilhouette;
+	if (!renderer) { throwError("renderer_occludeFromBox: renderer does not exist"); }
+	float mn[3] = {minimum.x, minimum.y, minimum.z}, mx[3] = {maximum.x, maximum.y, maximum.z};
+	dfpsr_transform3d t = b200_pod(modelToWorldTransform);
+	b200_check(dfpsr_renderer_occlude_from_box(renderer->handle, mn, mx, &t, &camera.pod));
+}
+inline void renderer_occludeFromTopRows(Renderer &renderer, const Camera &camera) {
+	if (!renderer) { throwError("renderer_occludeFromTopRows: renderer does not exist"); }
+	b200_check(dfpsr_renderer_occlude_from_top_rows(renderer->handle, &camera.pod, b200_stream()));
+}
+inline void renderer_occludeFromExistingTriangles(Renderer &renderer) {
+	if (!renderer) { throwError("renderer_occludeFromExistingTriangles: renderer does not exist"); }
+	b200_check(dfpsr_renderer_occlude_from_existing_triangles(renderer->handle, b200_stream()));
+}
+inline bool renderer_hasOccluders(const Renderer &renderer) { return renderer && dfpsr_renderer_has_occluders(renderer->handle) != 0; }
+inline bool renderer_isBoxVisible(const Renderer &renderer, const FVector3D &minimum, const FVector3D &maximum, const Transform3D &modelToWorldTransform, const Camera &camera) {
+	if (!renderer) { throwError("renderer_isBoxVisible: renderer does not exist"); }
+	float mn[3] = {minimum.x, minimum.y, minimum.z}, mx[3] = {maximum.x, maximum.y, maximum.z};
+	dfpsr_transform3d t = b200_pod(modelToWorldTransform);
+	int32_t visible = 0;
+	b200_check(dfpsr_renderer_is_box_visible(renderer->handle, mn, mx, &t, &camera.pod, &visible));
+	return visible != 0;
+}
 inline void renderer_end(Renderer &renderer, bool debugWireframe = false) {
 	(void)debugWireframe; // the wireframe overlay (rendererAPI.cpp:362-399) is a 2D draw call outside the path
 	if (!renderer) { throwError("renderer_end: renderer does not exist"); }

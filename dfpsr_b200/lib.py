@@ -45,6 +45,11 @@ SIGNATURES = {
     "dfpsr_renderer_destroy": (i32, [vp]),
     "dfpsr_renderer_begin": (i32, [vp, P(abi.Image), P(abi.Image)]),
     "dfpsr_renderer_begin_cleared": (i32, [vp, P(abi.Image), P(abi.Image), u32, f32]),
+    "dfpsr_renderer_occlude_from_box": (i32, [vp, vp, vp, P(abi.Transform3D), P(abi.Camera)]),
+    "dfpsr_renderer_occlude_from_top_rows": (i32, [vp, P(abi.Camera), vp]),
+    "dfpsr_renderer_occlude_from_existing_triangles": (i32, [vp, vp]),
+    "dfpsr_renderer_has_occluders": (i32, [vp]),
+    "dfpsr_renderer_is_box_visible": (i32, [vp, vp, vp, P(abi.Transform3D), P(abi.Camera), P(i32)]),
     "dfpsr_renderer_set_clip_rows": (i32, [vp, i32, i32]),
     "dfpsr_model_render_depth_batch": (i32, [vp, vp, vp, vp, i32, vp, i32, i32, f32, vp]),
     "dfpsr_renderer_give_task": (i32, [vp, P(abi.Model), P(abi.Transform3D), P(abi.Camera), vp]),

@@ -199,6 +199,17 @@ int dfpsr_renderer_begin_cleared(dfpsr_renderer *renderer, const dfpsr_image *co
  * CommandQueue::execute (ref: implementation/render/renderCore.cpp:459-478). Call between begin and end. top and bottom must be multiples
  * of 4 (the tile height; bottom may also be the image height). Pixels do not depend on the split. */
 int dfpsr_renderer_set_clip_rows(dfpsr_renderer *renderer, int32_t top, int32_t bottom);
+/* Occlusion grid (ref: api/rendererAPI.h:73-97, :131; api/rendererAPI.cpp:181-351, :403-477): 16x16-pixel cells holding the farthest
+ * depth at which something may still be visible. Occluder boxes and visibility queries are evaluated on the host (the grid is a few
+ * thousand floats); triangles and the depth buffer live on the device, so occlude_from_existing_triangles and occlude_from_top_rows
+ * run a kernel and synchronise `stream` once. Commands hidden by the grid are skipped at renderer_end exactly like completeOcclusion
+ * does (api/rendererAPI.cpp:193-217), and renderer_give_task skips whole models like model_render_threaded (api/modelAPI.cpp:229-234).
+ * All of them must be called between renderer_begin and renderer_end with the frame's camera. */
+int dfpsr_renderer_occlude_from_box(dfpsr_renderer *renderer, const float minBound[3], const float maxBound[3], const dfpsr_transform3d *modelToWorld, const dfpsr_camera *camera);
+int dfpsr_renderer_occlude_from_top_rows(dfpsr_renderer *renderer, const dfpsr_camera *camera, void *stream);
+int dfpsr_renderer_occlude_from_existing_triangles(dfpsr_renderer *renderer, void *stream);
+int dfpsr_renderer_has_occluders(const dfpsr_renderer *renderer);
+int dfpsr_renderer_is_box_visible(const dfpsr_renderer *renderer, const float minBound[3], const float maxBound[3], const dfpsr_transform3d *modelToWorld, const dfpsr_camera *camera, int32_t *visible);
 /* ref: api/modelAPI.cpp:214-281 model_render_threaded / renderer_giveTask. Bound culling
  * (Camera::isBoxSeen) is applied on the host exactly like the reference. Enqueues the projection and
  * triangle set-up kernels on `stream`; nothing is drawn before dfpsr_renderer_end. */

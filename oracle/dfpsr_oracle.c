@@ -296,6 +296,7 @@ static irect irect_make(int32_t l, int32_t t, int32_t w, int32_t h) { irect r = 
 static int irect_overlaps(irect a, irect b) { /* math/IRect.h:77 */
 	return a.l < b.l + b.w && a.l + a.w > b.l && a.t < b.t + b.h && a.t + a.h > b.t;
 }
+static int32_t clamp_i32(int32_t lo, int32_t v, int32_t hi) { return v < lo ? lo : (v > hi ? hi : v); }
 static int32_t imin(int32_t a, int32_t b) { return a < b ? a : b; }
 static int32_t imax(int32_t a, int32_t b) { return a > b ? a : b; }
 static irect irect_cut(irect a, irect b) { /* math/IRect.h:56-66 */
@@ -672,6 +673,7 @@ static void fill_shape(const fill_mode *m, const shader_data *s, const projectio
 	}
 }
 
+struct orc_renderer;
 typedef struct {
 	const dfpsr_image *color, *depth;
 	int32_t width, height;
@@ -679,11 +681,14 @@ typedef struct {
 	int filter;
 	shader_data shader;
 	int64_t commands;
+	struct orc_renderer *queue; /* when set, triangles are queued like CommandQueue::add instead of being drawn at once */
 } draw_context;
+static void queue_push(struct orc_renderer *r, const draw_context *ctx, const ppoint *p, const float *subB, const float *subC);
 
 /* implementation/render/renderCore.cpp:203-217 executeTriangleDrawing + shader/fillerTemplates.h:387-441 fillShape */
 static void execute_triangle(draw_context *ctx, const ppoint *p, const float *subB, const float *subC) {
 	ctx->commands++;
+	if (ctx->queue != NULL) { queue_push(ctx->queue, ctx, p, subB, subC); return; }
 	irect clip = irect_make(0, 0, ctx->width, ctx->height);
 	irect whole = triangle_bound(p);
 	if (!irect_overlaps(whole, clip)) { return; }
@@ -841,10 +846,17 @@ static int context_init(draw_context *ctx, const dfpsr_image *color, const dfpsr
 }
 
 /* api/modelAPI.cpp:214-281 (== implementation/render/model/Model.cpp:135-197) */
+static void submit_model(draw_context *ctx, const dfpsr_model *model, const dfpsr_transform3d *m2w, const dfpsr_camera *camera);
+
 int64_t orc_model_render(const dfpsr_model *model, const dfpsr_transform3d *m2w, const dfpsr_image *color, const dfpsr_image *depth, const dfpsr_camera *camera) {
 	draw_context ctx;
 	if (!context_init(&ctx, color, depth, camera, model->filter)) { return 0; }
 	if (!orc_camera_is_box_seen(camera, model->minBound, model->maxBound, m2w)) { return 0; }
+	submit_model(&ctx, model, m2w, camera);
+	return ctx.commands;
+}
+
+static void submit_model(draw_context *ctxp, const dfpsr_model *model, const dfpsr_transform3d *m2w, const dfpsr_camera *camera) {
 	ppoint *projected = (ppoint*)malloc(sizeof(ppoint) * (size_t)(model->pointCount > 0 ? model->pointCount : 1));
 	for (int32_t i = 0; i < model->pointCount; i++) {
 		projected[i] = world_to_screen(camera, transform_point(m2w, v3_from(model->points + 3 * i)));
@@ -858,11 +870,10 @@ int64_t orc_model_render(const dfpsr_model *model, const dfpsr_transform3d *m2w,
 			float colors[3][4], tex[3][4];
 			memcpy(colors[0], poly->colors[ia], 16); memcpy(colors[1], poly->colors[ib], 16); memcpy(colors[2], poly->colors[ic], 16);
 			memcpy(tex[0], poly->texCoords[ia], 16); memcpy(tex[1], poly->texCoords[ib], 16); memcpy(tex[2], poly->texCoords[ic], 16);
-			render_triangle(&ctx, p, colors, tex, &model->diffuse, &model->light);
+			render_triangle(ctxp, p, colors, tex, &model->diffuse, &model->light);
 		}
 	}
 	free(projected);
-	return ctx.commands;
 }
 
 /* api/rendererAPI.cpp:503-519 */
@@ -874,6 +885,247 @@ int64_t orc_render_triangles(const dfpsr_triangle *triangles, int32_t count, con
 		render_triangle(&ctx, p, triangles[i].colors, triangles[i].texCoords, diffuse, light);
 	}
 	return ctx.commands;
+}
+
+/* ------------------------------------------------------------------------------------------- renderer with occlusion grid */
+
+/* api/rendererAPI.cpp:141-150 RendererImpl: deferred queue + 16-pixel-cell occlusion grid */
+typedef struct {
+	ppoint p[3];
+	float subB[3], subC[3];
+	shader_data shader;
+	int filter;
+	const dfpsr_camera *camera;
+	dfpsr_camera cameraCopy;
+	int occluded;
+} queued_command;
+
+struct orc_renderer {
+	int receiving;
+	dfpsr_image color, depth;
+	int32_t width, height, gridWidth, gridHeight;
+	float *grid; int32_t gridAllocW, gridAllocH; /* depthGrid keeps its old size when large enough (rendererAPI.cpp:186-189) */
+	int occluded;
+	queued_command *commands; int64_t count, capacity;
+	int64_t lastOccluded;
+};
+#define CELL_SIZE 16 /* api/rendererAPI.cpp:36 */
+
+static void queue_push(struct orc_renderer *r, const draw_context *ctx, const ppoint *p, const float *subB, const float *subC) {
+	if (r->count == r->capacity) {
+		r->capacity = r->capacity ? r->capacity * 2 : 1024;
+		r->commands = (queued_command*)realloc(r->commands, sizeof(queued_command) * (size_t)r->capacity);
+	}
+	queued_command *c = &r->commands[r->count++];
+	memcpy(c->p, p, sizeof(c->p)); memcpy(c->subB, subB, 12); memcpy(c->subC, subC, 12);
+	c->shader = ctx->shader; c->filter = ctx->filter; c->cameraCopy = *ctx->camera; c->camera = NULL; c->occluded = 0;
+}
+
+orc_renderer *orc_renderer_create(void) { return (orc_renderer*)calloc(1, sizeof(orc_renderer)); }
+void orc_renderer_destroy(orc_renderer *r) { if (r) { free(r->grid); free(r->commands); free(r); } }
+
+/* api/rendererAPI.cpp:151-168 */
+void orc_renderer_begin(orc_renderer *r, const dfpsr_image *color, const dfpsr_image *depth) {
+	r->receiving = 1;
+	memset(&r->color, 0, sizeof(r->color)); memset(&r->depth, 0, sizeof(r->depth));
+	if (color != NULL && color->data != NULL) { r->color = *color; }
+	if (depth != NULL && depth->data != NULL) { r->depth = *depth; }
+	if (r->color.data != NULL) { r->width = r->color.width; r->height = r->color.height; }
+	else if (r->depth.data != NULL) { r->width = r->depth.width; r->height = r->depth.height; }
+	r->gridWidth = (r->width + (CELL_SIZE - 1)) / CELL_SIZE;
+	r->gridHeight = (r->height + (CELL_SIZE - 1)) / CELL_SIZE;
+	r->occluded = 0;
+	r->count = 0;
+}
+int orc_renderer_has_occluders(const orc_renderer *r) { return r->occluded; }
+
+/* image_readPixel_clamp on the grid image (a missing image reads 0) */
+static float grid_read(const orc_renderer *r, int32_t x, int32_t y) {
+	if (r->grid == NULL) { return 0.0f; }
+	x = clamp_i32(0, x, r->gridAllocW - 1); y = clamp_i32(0, y, r->gridAllocH - 1);
+	return r->grid[y * r->gridAllocW + x];
+}
+/* api/rendererAPI.cpp:181-192 */
+static void prepare_for_occlusion(orc_renderer *r) {
+	if (!r->occluded) {
+		if (!(r->grid != NULL && r->gridAllocW >= r->gridWidth && r->gridAllocH >= r->gridHeight)) {
+			free(r->grid);
+			r->gridAllocW = r->gridWidth; r->gridAllocH = r->gridHeight;
+			r->grid = (float*)malloc(sizeof(float) * (size_t)(r->gridAllocW * r->gridAllocH > 0 ? r->gridAllocW * r->gridAllocH : 1));
+		}
+		for (int32_t i = 0; i < r->gridAllocW * r->gridAllocH; i++) { r->grid[i] = INFINITY; }
+	}
+	r->occluded = 1;
+}
+/* api/rendererAPI.cpp:169-180 (IRect(l, t, w, h): right = l + w) */
+static irect outer_cell_bound(const orc_renderer *r, irect pixelBound) {
+	int32_t minX = pixelBound.l / CELL_SIZE, maxX = (pixelBound.l + pixelBound.w) / CELL_SIZE + 1;
+	int32_t minY = pixelBound.t / CELL_SIZE, maxY = (pixelBound.t + pixelBound.h) / CELL_SIZE + 1;
+	if (minX < 0) { minX = 0; } if (minY < 0) { minY = 0; }
+	if (maxX > r->gridWidth) { maxX = r->gridWidth; } if (maxY > r->gridHeight) { maxY = r->gridHeight; }
+	return irect_make(minX, minY, maxX - minX, maxY - minY);
+}
+/* api/rendererAPI.cpp:99-126 */
+static int point_inside_of_hull(const ppoint *hull, int count, int64_t x, int64_t y) {
+	for (int c = 0; c < count; c++) {
+		int nc = c + 1 == count ? 0 : c + 1;
+		int64_t dirX = hull[nc].fy - hull[c].fy, dirY = hull[c].fx - hull[nc].fx;
+		if (!((dirX * (x - hull[c].fx)) + (dirY * (y - hull[c].fy)) <= 0)) { return 0; }
+	}
+	return 1;
+}
+/* api/rendererAPI.cpp:218-241 occludeFromSortedHull */
+static void occlude_from_sorted_hull(orc_renderer *r, const ppoint *hull, int count, irect pixelBound) {
+	if (!(pixelBound.w > CELL_SIZE && pixelBound.h > CELL_SIZE)) { return; }
+	float distance = 0.0f;
+	for (int c = 0; c < count; c++) { if (hull[c].cs.z > distance) { distance = hull[c].cs.z; } }
+	irect outer = outer_cell_bound(r, pixelBound);
+	for (int32_t cy = outer.t; cy < outer.t + outer.h; cy++) {
+		for (int32_t cx = outer.l; cx < outer.l + outer.w; cx++) {
+			int64_t l = (int64_t)cx * CELL_SIZE * 256, t = (int64_t)cy * CELL_SIZE * 256, rr = l + CELL_SIZE * 256, b = t + CELL_SIZE * 256; /* IRect * unitsPerPixel */
+			if (point_inside_of_hull(hull, count, l, t) && point_inside_of_hull(hull, count, rr, t) && point_inside_of_hull(hull, count, l, b) && point_inside_of_hull(hull, count, rr, b)) {
+				if (distance < grid_read(r, cx, cy)) { r->grid[cy * r->gridAllocW + cx] = distance; }
+			}
+		}
+	}
+}
+/* api/rendererAPI.cpp:89-95 getPixelBoundFromProjection: merge of 1x1 rectangles at flat / 256 (truncating division) */
+static irect pixel_bound_from_projection(const ppoint *hull, int count) {
+	int32_t l = (int32_t)(hull[0].fx / 256), t = (int32_t)(hull[0].fy / 256), rr = l + 1, b = t + 1;
+	for (int p = 1; p < count; p++) {
+		int32_t x = (int32_t)(hull[p].fx / 256), y = (int32_t)(hull[p].fy / 256);
+		l = imin(l, x); t = imin(t, y); rr = imax(rr, x + 1); b = imax(b, y + 1);
+	}
+	return irect_make(l, t, rr - l, b - t);
+}
+static void box_corners(v3 *out, const float *mn, const float *mx) { /* api/rendererAPI.cpp:259-267 */
+	for (int i = 0; i < 8; i++) { out[i] = v3_make((i & 4) ? mx[0] : mn[0], (i & 2) ? mx[1] : mn[1], (i & 1) ? mx[2] : mn[2]); }
+}
+/* api/rendererAPI.cpp:38-74 jarvisConvexHullAlgorithm */
+static int counter_clockwise(const ppoint *p, const ppoint *q, const ppoint *rr) {
+	return (q->fy - p->fy) * (rr->fx - q->fx) - (q->fx - p->fx) * (rr->fy - q->fy) < 0;
+}
+static void jarvis(ppoint *out, int *outCount, const ppoint *in, int n) {
+	if (n < 3) { *outCount = n; for (int p = 0; p < n; p++) { out[p] = in[p]; } return; }
+	int l = 0;
+	*outCount = 0;
+	for (int i = 1; i < n; i++) { if (in[i].fx < in[l].fx) { l = i; } }
+	int p = l;
+	do {
+		if (*outCount >= n) { return; }
+		out[(*outCount)++] = in[p];
+		int q = (p + 1) % n;
+		for (int i = 0; i < n; i++) { if (counter_clockwise(&in[p], &in[i], &in[q])) { q = i; } }
+		p = q;
+	} while (p != l);
+}
+/* api/rendererAPI.cpp:268-299 occludeFromBox (+ :76-88 projectHull) */
+void orc_renderer_occlude_from_box(orc_renderer *r, const float *mn, const float *mx, const dfpsr_transform3d *m2w, const dfpsr_camera *camera) {
+	prepare_for_occlusion(r);
+	v3 local[8]; ppoint projected[8], hull[8];
+	box_corners(local, mn, mx);
+	for (int p = 0; p < 8; p++) {
+		v3 cameraPoint = transform_point_transposed_inverse(&camera->location, transform_point(m2w, local[p]));
+		v3 narrow = v3_make(cameraPoint.x * 0.5f, cameraPoint.y * 0.5f, cameraPoint.z * 1.0f);
+		for (int s = 0; s < camera->cullPlaneCount; s++) { if (!plane_inside(camera->cullPlanes[s], narrow)) { return; } }
+		projected[p] = camera_to_screen(camera, cameraPoint);
+	}
+	int count = 0;
+	jarvis(hull, &count, projected, 8);
+	occlude_from_sorted_hull(r, hull, count, pixel_bound_from_projection(hull, count));
+}
+/* api/rendererAPI.cpp:242-258 occludeFromExistingTriangles */
+void orc_renderer_occlude_from_existing_triangles(orc_renderer *r) {
+	prepare_for_occlusion(r);
+	for (int64_t t = 0; t < r->count; t++) {
+		if (r->commands[t].filter == DFPSR_FILTER_SOLID) { occlude_from_sorted_hull(r, r->commands[t].p, 3, triangle_bound(r->commands[t].p)); }
+	}
+}
+/* api/rendererAPI.cpp:403-477 occludeFromTopRows: scans the first pixel row of every cell row of the depth buffer */
+void orc_renderer_occlude_from_top_rows(orc_renderer *r, const dfpsr_camera *camera) {
+	prepare_for_occlusion(r);
+	if (r->depth.data == NULL) { return; }
+	for (int32_t y = 0, gy = 0; y < r->height; y += CELL_SIZE, gy++) {
+		const float *depthPixel = depth_px(&r->depth, 0, y);
+		int32_t x = 0, right = CELL_SIZE - 1;
+		for (int32_t gx = 0; gx < r->gridWidth; gx++) {
+			float extreme = camera->perspective ? INFINITY : 0.0f;
+			if (right >= r->width) { right = r->width; }
+			while (x < right) {
+				float v = *depthPixel;
+				if (camera->perspective) { if (v < extreme) { extreme = v; } } else { if (v > extreme) { extreme = v; } }
+				depthPixel += 1; x += 1;
+			}
+			float maxDistance = camera->perspective ? 1.0f / extreme : extreme;
+			if (maxDistance < r->grid[gy * r->gridAllocW + gx]) { r->grid[gy * r->gridAllocW + gx] = maxDistance; }
+			right += CELL_SIZE;
+		}
+	}
+}
+/* api/rendererAPI.cpp:302-351 isHullOccluded / isBoxOccluded, negated like renderer_isBoxVisible (:538-543) */
+int orc_renderer_is_box_visible(const orc_renderer *r, const float *mn, const float *mx, const dfpsr_transform3d *m2w, const dfpsr_camera *camera) {
+	v3 local[8], cameraPoints[8]; ppoint projected[8];
+	box_corners(local, mn, mx);
+	for (int p = 0; p < 8; p++) {
+		cameraPoints[p] = transform_point_transposed_inverse(&camera->location, transform_point(m2w, local[p]));
+		projected[p] = camera_to_screen(camera, cameraPoints[p]);
+	}
+	for (int s = 0; s < camera->cullPlaneCount; s++) {
+		int allOutside = 1;
+		for (int p = 0; p < 8; p++) { if (plane_inside(camera->cullPlanes[s], cameraPoints[p])) { allOutside = 0; break; } }
+		if (allOutside) { return 0; }
+	}
+	irect pixelBound = pixel_bound_from_projection(projected, 8);
+	float closest = INFINITY;
+	for (int c = 0; c < 8; c++) { if (projected[c].cs.z < closest) { closest = projected[c].cs.z; } }
+	irect outer = outer_cell_bound(r, pixelBound);
+	for (int32_t cy = outer.t; cy < outer.t + outer.h; cy++) {
+		for (int32_t cx = outer.l; cx < outer.l + outer.w; cx++) { if (closest < grid_read(r, cx, cy)) { return 1; } }
+	}
+	return 0;
+}
+/* api/modelAPI.cpp:214-281 model_render_threaded */
+void orc_renderer_give_task(orc_renderer *r, const dfpsr_model *model, const dfpsr_transform3d *m2w, const dfpsr_camera *camera) {
+	draw_context ctx;
+	if (!context_init(&ctx, &r->color, &r->depth, camera, model->filter)) { return; }
+	if (!orc_camera_is_box_seen(camera, model->minBound, model->maxBound, m2w)) { return; }
+	if (r->occluded && !orc_renderer_is_box_visible(r, model->minBound, model->maxBound, m2w, camera)) { return; }
+	ctx.queue = r;
+	submit_model(&ctx, model, m2w, camera);
+}
+/* api/rendererAPI.cpp:193-217 completeOcclusion + :352-402 endFrame. Returns the queue length; *occludedOut = commands skipped. */
+int64_t orc_renderer_end(orc_renderer *r, int64_t *occludedOut) {
+	r->receiving = 0;
+	int64_t skipped = 0;
+	if (r->occluded) {
+		for (int64_t t = r->count - 1; t >= 0; t--) {
+			queued_command *c = &r->commands[t];
+			int anyVisible = 0;
+			irect outer = outer_cell_bound(r, triangle_bound(c->p));
+			float triangleDepth = c->p[0].cs.z;
+			if (c->p[1].cs.z < triangleDepth) { triangleDepth = c->p[1].cs.z; }
+			if (c->p[2].cs.z < triangleDepth) { triangleDepth = c->p[2].cs.z; }
+			for (int32_t cy = outer.t; cy < outer.t + outer.h; cy++) {
+				for (int32_t cx = outer.l; cx < outer.l + outer.w; cx++) {
+					if ((double)triangleDepth < (double)grid_read(r, cx, cy) + 0.001) { anyVisible = 1; }
+				}
+			}
+			if (!anyVisible) { c->occluded = 1; skipped++; }
+		}
+	}
+	for (int64_t t = 0; t < r->count; t++) {
+		queued_command *c = &r->commands[t];
+		if (c->occluded) { continue; }
+		draw_context ctx;
+		if (!context_init(&ctx, &r->color, &r->depth, &c->cameraCopy, c->filter)) { continue; }
+		ctx.shader = c->shader;
+		execute_triangle(&ctx, c->p, c->subB, c->subC);
+	}
+	if (occludedOut != NULL) { *occludedOut = skipped; }
+	r->lastOccluded = skipped;
+	int64_t n = r->count;
+	r->count = 0;
+	return n;
 }
 
 /* ------------------------------------------------------------------------------------------- depth-only path */
@@ -941,7 +1193,6 @@ static uint32_t pack_bytes_ordered(uint32_t r, uint32_t g, uint32_t b, uint32_t 
 	const int *ix = packIndex[order];
 	return (r << (8 * ix[0])) | (g << (8 * ix[1])) | (b << (8 * ix[2])) | (a << (8 * ix[3]));
 }
-static int32_t clamp_i32(int32_t lo, int32_t v, int32_t hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 /* api/imageAPI.cpp:167-185 + api/drawAPI.cpp:72-174 (whole-image rectangle) */
 void orc_image_fill_rgba(const dfpsr_image *image, int32_t r, int32_t g, int32_t b, int32_t a) {

@@ -40,6 +40,18 @@ int orc_is_frontfacing(const int64_t *fx, const int64_t *fy);
 int64_t orc_model_render(const dfpsr_model *model, const dfpsr_transform3d *modelToWorld, const dfpsr_image *color, const dfpsr_image *depth, const dfpsr_camera *camera);
 /* renderer_giveTask_triangle for pre-projected triangles. */
 int64_t orc_render_triangles(const dfpsr_triangle *triangles, int32_t count, const dfpsr_texture *diffuse, const dfpsr_texture *light, int32_t filter, const dfpsr_image *color, const dfpsr_image *depth, const dfpsr_camera *camera);
+/* Renderer object with the deferred queue and the 16-pixel-cell occlusion grid (ref: api/rendererAPI.cpp:141-477). */
+typedef struct orc_renderer orc_renderer;
+orc_renderer *orc_renderer_create(void);
+void orc_renderer_destroy(orc_renderer *r);
+void orc_renderer_begin(orc_renderer *r, const dfpsr_image *color, const dfpsr_image *depth);
+int orc_renderer_has_occluders(const orc_renderer *r);
+void orc_renderer_occlude_from_box(orc_renderer *r, const float *minBound, const float *maxBound, const dfpsr_transform3d *modelToWorld, const dfpsr_camera *camera);
+void orc_renderer_occlude_from_existing_triangles(orc_renderer *r);
+void orc_renderer_occlude_from_top_rows(orc_renderer *r, const dfpsr_camera *camera);
+int orc_renderer_is_box_visible(const orc_renderer *r, const float *minBound, const float *maxBound, const dfpsr_transform3d *modelToWorld, const dfpsr_camera *camera);
+void orc_renderer_give_task(orc_renderer *r, const dfpsr_model *model, const dfpsr_transform3d *modelToWorld, const dfpsr_camera *camera);
+int64_t orc_renderer_end(orc_renderer *r, int64_t *occludedOut);
 /* model_renderDepth */
 void orc_model_render_depth(const dfpsr_model *model, const dfpsr_transform3d *modelToWorld, const dfpsr_image *depth, const dfpsr_camera *camera);
 

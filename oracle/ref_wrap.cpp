@@ -280,6 +280,27 @@ void ref_models_render_frame(const int *models, const dfpsr_transform3d *modelTo
 	renderer_end(worker);
 }
 
+// ---- the renderer API step by step, for the occlusion grid (api/rendererAPI.h:56-135)
+static Renderer &stepRenderer() { static Renderer worker = renderer_create(); return worker; }
+void ref_renderer_begin(int colorId, int depthId) {
+	ImageRgbaU8 color = rgbaOrNull(colorId);
+	ImageF32 depth = f32OrNull(depthId);
+	renderer_begin(stepRenderer(), color, depth);
+}
+void ref_renderer_give_task(int model, const dfpsr_transform3d *modelToWorld, const dfpsr_camera *camera) {
+	renderer_giveTask(stepRenderer(), g_models[model], toTransform(modelToWorld), toCamera(camera));
+}
+void ref_renderer_occlude_from_box(const float *mn, const float *mx, const dfpsr_transform3d *modelToWorld, const dfpsr_camera *camera) {
+	renderer_occludeFromBox(stepRenderer(), v3(mn), v3(mx), toTransform(modelToWorld), toCamera(camera));
+}
+void ref_renderer_occlude_from_top_rows(const dfpsr_camera *camera) { renderer_occludeFromTopRows(stepRenderer(), toCamera(camera)); }
+void ref_renderer_occlude_from_existing_triangles() { renderer_occludeFromExistingTriangles(stepRenderer()); }
+int ref_renderer_is_box_visible(const float *mn, const float *mx, const dfpsr_transform3d *modelToWorld, const dfpsr_camera *camera) {
+	return renderer_isBoxVisible(stepRenderer(), v3(mn), v3(mx), toTransform(modelToWorld), toCamera(camera)) ? 1 : 0;
+}
+int ref_renderer_has_occluders() { return renderer_hasOccluders(stepRenderer()) ? 1 : 0; }
+void ref_renderer_end() { renderer_end(stepRenderer()); }
+
 void ref_model_render_depth(int model, const dfpsr_transform3d *modelToWorld, int depthId, const dfpsr_camera *camera) {
 	ImageF32 depth = f32OrNull(depthId);
 	model_renderDepth(g_models[model], toTransform(modelToWorld), depth, toCamera(camera));

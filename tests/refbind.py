@@ -38,6 +38,10 @@ def load(flavour="scalar"):
         "ref_model_render": (None, [i, T, i, i, Cam, i]),
         "ref_models_render_frame": (None, [p, p, i, i, i, Cam]),
         "ref_model_render_depth": (None, [i, T, i, Cam]),
+        "ref_renderer_begin": (None, [i, i]), "ref_renderer_give_task": (None, [i, T, Cam]),
+        "ref_renderer_occlude_from_box": (None, [p, p, T, Cam]), "ref_renderer_occlude_from_top_rows": (None, [Cam]),
+        "ref_renderer_occlude_from_existing_triangles": (None, []), "ref_renderer_is_box_visible": (i, [p, p, T, Cam]),
+        "ref_renderer_has_occluders": (i, []), "ref_renderer_end": (None, []),
         "ref_terrain_frame": (d, [i, T, i, i, Cam]),
         "ref_project_points": (None, [p, i, T, Cam, p]),
         "ref_camera_fill": (None, [Cam]), "ref_camera_is_box_seen": (i, [Cam, p, p, T]),

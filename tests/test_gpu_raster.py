@@ -386,3 +386,17 @@ def test_session_render_views_host_pipeline(cuda, oracle):
         oracle.orc_model_render(C.byref(omodel), C.byref(ident), C.byref(orcbind.image_of(ec)), C.byref(orcbind.image_of(ed)), C.byref(orcbind.camera(scenes.orbit_camera(v, w, h, frames_per_lap=views))))
         assert_same_u32(color[v].numpy().view(np.uint32), ec, f"view {v} colour")
         assert_same_u32(bits(depth[v].numpy()), bits(ed), f"view {v} depth")
+
+
+@pytest.mark.parametrize("variant", [dict(), dict(top_rows=True), dict(perspective=False), dict(seed=11, width=333, height=201, top_rows=True)])
+def test_occlusion_grid_matches_oracle(cuda, oracle, variant):
+    """renderer_occludeFromBox / occludeFromExistingTriangles / occludeFromTopRows / isBoxVisible (ref: api/rendererAPI.cpp:181-477):
+    same visibility answers as the oracle, same command count, same pixels."""
+    import occlusion_scene
+    sc = occlusion_scene.build(**variant)
+    expected = occlusion_scene.run_oracle(oracle, sc)
+    got = occlusion_scene.run_cuda(cuda, sc)
+    assert got["visible"] == expected["visible"]
+    assert got["commands"] == expected["commands"]
+    assert_same_u32(bits(got["depth"]), bits(expected["depth"]), "depth")
+    assert_same_u32(got["color"], expected["color"], "colour")

@@ -308,3 +308,20 @@ def test_coverage_equals_pixel_centre_edge_predicate(oracle):
         assert np.array_equal(covered_rows[:, first:], inside[:, first:]), (fx, fy)
         checked += 1
     assert checked > 1500
+
+
+@pytest.mark.parametrize("variant", [dict(), dict(top_rows=True), dict(perspective=False), dict(seed=11, width=333, height=201, top_rows=True)])
+def test_occlusion_grid_bit_exact(ref_scalar, oracle, variant):
+    """renderer_occludeFromBox / occludeFromExistingTriangles / occludeFromTopRows / isBoxVisible (ref: api/rendererAPI.cpp:181-477):
+    same visibility answers, same pixels — occluded triangles really are skipped (the wall's declared box is trusted)."""
+    import occlusion_scene
+    sc = occlusion_scene.build(**variant)
+    expected = occlusion_scene.run_reference(ref_scalar, sc)
+    ref_scalar.free_all()
+    got = occlusion_scene.run_oracle(oracle, sc)
+    assert got["visible"] == expected["visible"]
+    assert 0 < sum(expected["visible"]) < len(expected["visible"])
+    if variant.get("perspective", True):
+        assert got["occluded"] > 0  # triangles of models that passed the box test are still culled one by one at renderer_end
+    assert np.array_equal(bits(expected["depth"]), bits(got["depth"]))
+    assert np.array_equal(expected["color"], got["color"])

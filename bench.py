@@ -254,7 +254,13 @@ def main():
     launch_bytes = ALGORITHMIC_BYTES_PER_FRAME * views  # one launch rasterises every view of the step
     launch_us = 1000.0 * raster_ms / max(raster_launches, 1)
     achieved = (launch_bytes / 1e9) / (launch_us / 1e6) if raster_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    traffic, traffic_source = None, None
+    traffic_path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(traffic_path):  # dram bytes of this kernel from one `ncu --set full` capture of this very command (never measured under the timer)
+        t = json.load(open(traffic_path)).get("raster_kernel<false>")
+        if t:
+            traffic, traffic_source = t["dram_bytes_per_launch"] * views / t["views_per_launch"], t["source"]
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_source,
                 "kernel": "raster_kernel<false>", "avg_launch_us": launch_us, "frames_per_launch": views,
                 "algorithmic_bytes_per_launch": launch_bytes, "algorithmic_bytes_per_frame": ALGORITHMIC_BYTES_PER_FRAME, "peak_source": peak_source,
                 "kernel_share_of_device_time": raster_ms / total_kernel_ms if total_kernel_ms > 0 else None,

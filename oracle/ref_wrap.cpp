@@ -19,8 +19,28 @@
 #include <vector>
 #include <cstring>
 #include <chrono>
+#include <cstdlib>
+#include <new>
 
 using namespace dsr;
+
+// The reference's heap (DFPSR/base/heap.cpp:671-684) writes a new allocation's header through an AllocationHeader
+// pointer, which slices off HeapHeader's own fields (destructor, useCount, flags, binIndex): it relies on every
+// 16 MiB arena from operator new being fresh zero pages from mmap. Inside a long-lived Python process glibc raises
+// its dynamic mmap threshold after large numpy arrays are freed, arenas then come from recycled (dirty) memory and
+// heap_free calls a garbage destructor pointer. The replaceable global allocation functions below (a standard C++
+// customisation point, resolved inside this shared object first) hand the reference zeroed memory, which restores
+// the condition it assumes without touching its sources.
+void *operator new(std::size_t size) {
+	void *p = calloc(size ? size : 1, 1);
+	if (p == nullptr) throw std::bad_alloc();
+	return p;
+}
+void *operator new[](std::size_t size) { return operator new(size); }
+void operator delete(void *p) noexcept { free(p); }
+void operator delete[](void *p) noexcept { free(p); }
+void operator delete(void *p, std::size_t) noexcept { free(p); }
+void operator delete[](void *p, std::size_t) noexcept { free(p); }
 
 namespace {
 

@@ -20,6 +20,7 @@
 // additions from each row pair's outer block start, so colour and depth are bit-identical to the reference's scalar build (exact 1/x).
 #include "common.cuh"
 
+#include <algorithm>
 #include <vector>
 #include <new>
 
@@ -1119,10 +1120,11 @@ __device__ __forceinline__ uint32_t find_view(const ViewDev *views, int32_t view
 	return (uint32_t)lo;
 }
 
-// Ascending bitonic sort of one key per lane.
+// Ascending bitonic sort of one key per lane inside aligned groups of K lanes.
+template <int K>
 __device__ __forceinline__ uint32_t warp_sort(uint32_t key, int lane) {
 #pragma unroll
-	for (int k = 2; k <= 32; k <<= 1) {
+	for (int k = 2; k <= K; k <<= 1) {
 #pragma unroll
 		for (int j = k >> 1; j > 0; j >>= 1) {
 			uint32_t other = __shfl_xor_sync(0xffffffffu, key, j);
@@ -1139,12 +1141,23 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32, RASTER_MIN_BLOCKS) raster_k
 	__shared__ __align__(16) Rec sRecAll[RASTER_WARPS][32];
 	__shared__ __align__(16) uint32_t sMaskAll[RASTER_WARPS][32]; // per (row pair, command): which of the 16 quads of the row pair the command may touch
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const uint32_t tile = blockIdx.x * RASTER_WARPS + warp;
-	if (tile >= frame.tileTotal) { return; }
 	Rec *sRec = sRecAll[warp];
 	uint32_t *sMask = sMaskAll[warp];
 
-	const ViewDev &vw = frame.views[frame.viewCount > 1 ? find_view(frame.views, frame.viewCount, tile) : 0u];
+	// grid = (tiles of the largest view / RASTER_WARPS, views); batches of more than 65535 views fall back to a flat grid and a search
+	uint32_t tile, viewIndex;
+	if (gridDim.y > 1u || frame.viewCount == 1) {
+		viewIndex = blockIdx.y;
+		const ViewDev &v = frame.views[viewIndex];
+		const uint32_t local = blockIdx.x * RASTER_WARPS + warp;
+		if (local >= (uint32_t)(v.tilesX * v.tilesY)) { return; }
+		tile = v.tileBase + local;
+	} else {
+		tile = blockIdx.x * RASTER_WARPS + warp;
+		if (tile >= frame.tileTotal) { return; }
+		viewIndex = find_view(frame.views, frame.viewCount, tile);
+	}
+	const ViewDev &vw = frame.views[viewIndex];
 	const int32_t tilesX = vw.tilesX;
 	const int32_t localTile = (int32_t)(tile - vw.tileBase);
 	const int32_t tileX = localTile % tilesX, tileY = localTile / tilesX;
@@ -1183,7 +1196,15 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32, RASTER_MIN_BLOCKS) raster_k
 	uint32_t sortedKey = 0xFFFFFFFFu;
 	if (n <= 32u) {
 		sortedKey = (uint32_t)lane < n ? __ldg(list + lane) : 0xFFFFFFFFu;
-		if (n > 1u) { sortedKey = warp_sort(sortedKey, lane); }
+		if (n > 1u) {
+			// the set-up pass fills lists roughly in command order: most short lists arrive sorted
+			const uint32_t previous = __shfl_up_sync(0xffffffffu, sortedKey, 1);
+			if (__any_sync(0xffffffffu, lane > 0 && previous > sortedKey)) {
+				if (n <= 8u) { sortedKey = warp_sort<8>(sortedKey, lane); }
+				else if (n <= 16u) { sortedKey = warp_sort<16>(sortedKey, lane); }
+				else { sortedKey = warp_sort<32>(sortedKey, lane); }
+			}
+		}
 	}
 
 	for (uint32_t batchStart = 0; batchStart < n; batchStart += BATCH) {
@@ -1749,7 +1770,12 @@ static int renderer_end_internal(dfpsr_renderer *r, cudaStream_t stream) {
 			}
 		}
 	}
-	const uint32_t grid = (tileTotal + RASTER_WARPS - 1) / RASTER_WARPS;
+	dim3 grid((tileTotal + RASTER_WARPS - 1) / RASTER_WARPS, 1, 1);
+	if (viewCount > 1 && viewCount <= 65535) {
+		uint32_t largest = 0;
+		for (const ViewDev &v : r->views) { largest = std::max(largest, (uint32_t)(v.tilesX * v.tilesY)); }
+		grid = dim3((largest + RASTER_WARPS - 1) / RASTER_WARPS, (unsigned)viewCount, 1);
+	}
 	if (r->depthOnly) { DFPSR_LAUNCH(raster_kernel<true>, grid, RASTER_WARPS * 32, 0, stream, frame, r->textures); }
 	else { DFPSR_LAUNCH(raster_kernel<false>, grid, RASTER_WARPS * 32, 0, stream, frame, r->textures); }
 	return 0;

@@ -118,6 +118,60 @@ class HostModel(C.Structure):
     ]
 
 
+class OrthoCamera(C.Structure):
+    _fields_ = [
+        ("id", C.c_int32), ("worldDirection", C.c_int32),
+        ("normalToWorldSpace", Matrix3x3),
+        ("pixelOffsetPerTileX", C.c_int32 * 2), ("pixelOffsetPerTileZ", C.c_int32 * 2), ("yPixelsPerTile", C.c_int32),
+        ("screenDepthToWorldSpace", Matrix3x3), ("worldSpaceToScreenDepth", Matrix3x3),
+        ("screenDepthToLightSpace", Matrix3x3), ("lightSpaceToScreenDepth", Matrix3x3),
+        ("roundedScreenPixelsToWorldTiles", C.c_float * 4),
+    ]
+
+    def light_view(self):
+        return OrthoView(self.normalToWorldSpace, self.screenDepthToLightSpace, self.lightSpaceToScreenDepth)
+
+
+class OrthoSystem(C.Structure):
+    _fields_ = [("cameraTilt", C.c_float), ("pixelsPerTile", C.c_int32), ("view", OrthoCamera * 8)]
+
+
+DENSE_TRIANGLE_DTYPE = np.dtype([(name, np.float32, (3,)) for name in ("colorA", "colorB", "colorC", "posA", "posB", "posC", "normalA", "normalB", "normalC")])
+assert DENSE_TRIANGLE_DTYPE.itemsize == 108
+
+
+class SpriteConfig(C.Structure):
+    _fields_ = [
+        ("centerX", C.c_int32), ("centerY", C.c_int32), ("frameRows", C.c_int32), ("propertyColumns", C.c_int32),
+        ("minBound", C.c_float * 3), ("maxBound", C.c_float * 3),
+        ("points", C.c_void_p), ("pointCount", C.c_int32),
+        ("triangleIndices", C.c_void_p), ("triangleIndexCount", C.c_int32),
+    ]
+
+
+class SpriteInstance(C.Structure):
+    _fields_ = [("typeIndex", C.c_int32), ("direction", C.c_int32), ("location", C.c_int32 * 3), ("shadowCasting", C.c_int32), ("userData", C.c_uint64)]
+
+
+class ModelInstance(C.Structure):
+    _fields_ = [("typeIndex", C.c_int32), ("location", Transform3D), ("userData", C.c_uint64)]
+
+
+(SW_BLOCK_CLEAR, SW_BLOCK_SPRITE, SW_BLOCK_MODEL, SW_COPY_BLOCK, SW_SPRITE, SW_MODEL, SW_LIGHT_CLEAR, SW_LIGHT_DIRECTED,
+ SW_SHADOW_CLEAR, SW_SHADOW_SPRITE, SW_SHADOW_MODEL, SW_LIGHT_POINT, SW_BLEND) = range(1, 14)
+
+
+class SpriteWorldOp(C.Structure):
+    _fields_ = [
+        ("op", C.c_int32), ("block", C.c_int32), ("typeIndex", C.c_int32), ("frame", C.c_int32),
+        ("left", C.c_int32), ("top", C.c_int32), ("width", C.c_int32), ("height", C.c_int32),
+        ("sourceLeft", C.c_int32), ("sourceTop", C.c_int32),
+        ("heightOffset", C.c_float), ("worldOrigin", C.c_float * 2),
+        ("transform", Transform3D),
+        ("light", C.c_int32), ("flag", C.c_int32),
+    ]
+
+
 def camera_params(perspective, location, width, height, width_slope=1.0, near=0.01, far=1000.0):
     """A camera POD holding only the constructor arguments; derived fields are filled by
     dfpsr_camera_create_* (product), orc_camera_create (oracle) or ref_camera_fill (reference)."""

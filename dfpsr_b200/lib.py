@@ -74,6 +74,36 @@ SIGNATURES = {
     "dfpsr_filter_resize": (i32, [P(abi.Image), P(abi.Image), i32, i32, vp, vp]),
     "dfpsr_filter_map": (i32, [P(abi.Image), i32, vp, i32, P(abi.Image), i32, i32, vp]),
     "dfpsr_filter_block_magnify": (i32, [P(abi.Image), P(abi.Image), i32, i32, vp]),
+    "dfpsr_ortho_system_create": (i32, [P(abi.OrthoSystem), f32, i32]),
+    "dfpsr_ortho_camera_light_view": (i32, [P(abi.OrthoCamera), P(abi.OrthoView)]),
+    "dfpsr_dense_model_triangle_count": (i32, [vp, i32]),
+    "dfpsr_dense_model_build": (i32, [vp, i32, vp, i32, vp, vp, vp]),
+    "dfpsr_dense_model_render": (i32, [vp, i32, vp, vp, P(abi.OrthoCamera), P(abi.Image), P(abi.Image), P(abi.Image), vp, P(abi.Transform3D), i32, vp, vp]),
+    "dfpsr_sprite_type_create": (i32, [vp, i32, i32, i32, P(abi.SpriteConfig), P(i32)]),
+    "dfpsr_sprite_type_count": (i32, []),
+    "dfpsr_model_type_create": (i32, [vp, i32, vp, vp, P(abi.HostModel), P(i32)]),
+    "dfpsr_model_type_count": (i32, []),
+    "dfpsr_sprite_world_create": (i32, [P(vp), P(abi.OrthoSystem), i32]),
+    "dfpsr_sprite_world_destroy": (i32, [vp]),
+    "dfpsr_sprite_world_add_background_sprite": (i32, [vp, P(abi.SpriteInstance)]),
+    "dfpsr_sprite_world_add_background_model": (i32, [vp, P(abi.ModelInstance)]),
+    "dfpsr_sprite_world_add_temporary_sprite": (i32, [vp, P(abi.SpriteInstance)]),
+    "dfpsr_sprite_world_add_temporary_model": (i32, [vp, P(abi.ModelInstance)]),
+    "dfpsr_sprite_world_remove_background_sprites": (i32, [vp, vp, vp, vp, vp]),
+    "dfpsr_sprite_world_remove_background_models": (i32, [vp, vp, vp, vp, vp]),
+    "dfpsr_sprite_world_create_temporary_point_light": (i32, [vp, vp, f32, f32, vp, i32]),
+    "dfpsr_sprite_world_create_temporary_directed_light": (i32, [vp, vp, f32, vp]),
+    "dfpsr_sprite_world_clear_temporary": (i32, [vp]),
+    "dfpsr_sprite_world_get_camera_location": (i32, [vp, vp]),
+    "dfpsr_sprite_world_set_camera_location": (i32, [vp, vp]),
+    "dfpsr_sprite_world_move_camera_in_pixels": (i32, [vp, i32, i32]),
+    "dfpsr_sprite_world_get_camera_direction_index": (i32, [vp, P(i32)]),
+    "dfpsr_sprite_world_set_camera_direction_index": (i32, [vp, i32]),
+    "dfpsr_sprite_world_find_ground_at_pixel": (i32, [vp, i32, i32, i32, i32, vp]),
+    "dfpsr_sprite_world_plan_frame": (i32, [vp, i32, i32, P(P(abi.SpriteWorldOp)), P(i32)]),
+    "dfpsr_sprite_world_draw": (i32, [vp, P(abi.Image), vp]),
+    "dfpsr_sprite_world_draw_host": (i32, [vp, vp, i32, i32, i32, i32, vp]),
+    "dfpsr_sprite_world_get_buffers": (i32, [vp, P(abi.Image), P(abi.Image), P(abi.Image), P(abi.Image)]),
     "dfpsr_session_create": (i32, [P(vp)]),
     "dfpsr_session_destroy": (i32, [vp]),
     "dfpsr_session_upload_model": (i32, [vp, P(abi.HostModel), P(i32)]),

@@ -280,6 +280,141 @@ typedef struct dfpsr_directed_light { float direction[3]; float intensity; int32
 typedef struct dfpsr_point_light { float position[3]; float radius, intensity; int32_t colorRgb[3]; dfpsr_image shadowCubeMap; /* data == NULL: no shadows */ } dfpsr_point_light;
 int dfpsr_light_frame(const dfpsr_ortho_view *view, const int32_t worldCenter[2], const dfpsr_image *color, const dfpsr_image *diffuse, const dfpsr_image *light, const dfpsr_image *normal, const dfpsr_image *height, const dfpsr_directed_light *directed, int32_t directedCount, const dfpsr_point_light *points, int32_t pointCount, void *stream);
 
+/* ---------------------------------------------------------------- Sandbox sprite engine: views, dense models, sprite world */
+
+/* ref: SDK/SpriteEngine/orthoAPI.h:40-83 OrthoView, all derived members. */
+typedef struct dfpsr_ortho_camera {
+	int32_t id, worldDirection;
+	dfpsr_matrix3x3 normalToWorldSpace;
+	int32_t pixelOffsetPerTileX[2], pixelOffsetPerTileZ[2], yPixelsPerTile;
+	dfpsr_matrix3x3 screenDepthToWorldSpace, worldSpaceToScreenDepth, screenDepthToLightSpace, lightSpaceToScreenDepth;
+	float roundedScreenPixelsToWorldTiles[4]; /* FMatrix2x2: xAxis.x, xAxis.y, yAxis.x, yAxis.y */
+} dfpsr_ortho_camera;
+/* ref: SDK/SpriteEngine/orthoAPI.h:92-134 OrthoSystem (8 fixed camera angles). */
+typedef struct dfpsr_ortho_system {
+	float cameraTilt;
+	int32_t pixelsPerTile;
+	dfpsr_ortho_camera view[8];
+} dfpsr_ortho_system;
+/* ref: SDK/SpriteEngine/orthoAPI.cpp:5-32, :82-119 OrthoSystem(cameraTilt, pixelsPerTile) -> update(). Host arithmetic, no GPU needed. */
+int dfpsr_ortho_system_create(dfpsr_ortho_system *out, float cameraTilt, int32_t pixelsPerTile);
+/* The three matrices the light passes read (dfpsr_ortho_view) taken from a full view. */
+int dfpsr_ortho_camera_light_view(const dfpsr_ortho_camera *camera, dfpsr_ortho_view *out);
+
+/* ref: SDK/SpriteEngine/spriteAPI.cpp:236-249 DenseTriangle (108 bytes): colours 0..255, object-space positions, smooth normals. */
+typedef struct dfpsr_dense_triangle {
+	float colorA[3], colorB[3], colorC[3];
+	float posA[3], posB[3], posC[3];
+	float normalA[3], normalB[3], normalC[3];
+} dfpsr_dense_triangle;
+/* ref: SDK/SpriteEngine/spriteAPI.cpp:1176-1233 DenseModel_create: smooth per-point normals, polygons fanned into triangles (0, b, b + 1),
+ * vertex colours scaled by 255. Host arithmetic (set-up time). `out` holds dfpsr_dense_model_triangle_count() HOST triangles; the bounds
+ * are the model's bounding box (ref: implementation/render/model/Model.cpp:281-288, always contains the origin). */
+int32_t dfpsr_dense_model_triangle_count(const dfpsr_polygon *polygons, int32_t polygonCount);
+int dfpsr_dense_model_build(const float *points, int32_t pointCount, const dfpsr_polygon *polygons, int32_t polygonCount, dfpsr_dense_triangle *out, float minBound[3], float maxBound[3]);
+/* ref: SDK/SpriteEngine/spriteAPI.cpp:1243-1327 renderDenseModel<HIGH_QUALITY>: orthogonal vertex-colour triangles with float barycentric
+ * weights (tolerance -0.00001), height test `>`, writing height + diffuse + normal (RGBA order). `triangles` is a DEVICE array.
+ * dirtyRect receives {left, top, width, height} of the pessimistic bound the reference returns (all zero when culled); may be NULL. */
+int dfpsr_dense_model_render(const dfpsr_dense_triangle *triangles, int32_t triangleCount, const float minBound[3], const float maxBound[3], const dfpsr_ortho_camera *view, const dfpsr_image *height, const dfpsr_image *diffuse, const dfpsr_image *normal, const float worldOrigin[2], const dfpsr_transform3d *modelToWorld, int32_t highQuality, int32_t dirtyRect[4], void *stream);
+
+/* Sprite types are process-global like the reference's (ref: SDK/SpriteEngine/spriteAPI.cpp:279-289). The reference loads
+ * <name>.png + <name>.ini; here the decoded atlas (RGBA order, HOST memory) and the parsed configuration are passed in
+ * (ref: spriteAPI.cpp:47-133 SpriteConfig, :190-232 SpriteType): the atlas holds frameRows rows of [colour | height | normal ...]
+ * columns; heights become (red * (maxBound.y - minBound.y) / 255 + minBound.y) where the colour's alpha > 127, -inf elsewhere
+ * (:157-174 scaleHeightImage, evaluated on the device). points / triangleIndices describe the optional shadow model. */
+typedef struct dfpsr_sprite_config {
+	int32_t centerX, centerY, frameRows, propertyColumns;
+	float minBound[3], maxBound[3];
+	const float *points; int32_t pointCount;                   /* 3 floats per point */
+	const int32_t *triangleIndices; int32_t triangleIndexCount; /* multiples of three */
+} dfpsr_sprite_config;
+int dfpsr_sprite_type_create(const uint32_t *atlasHost, int32_t width, int32_t height, int32_t strideBytes, const dfpsr_sprite_config *config, int32_t *typeIndex);
+int32_t dfpsr_sprite_type_count(void);
+/* ref: SDK/SpriteEngine/spriteAPI.cpp:262-277, :291-299 ModelType(visibleModel, shadowModel): dense triangles (HOST, from
+ * dfpsr_dense_model_build) + an optional shadow model (HOST geometry; only points and polygons are read). */
+struct dfpsr_host_model; /* declared with the host-buffer entry points below */
+int dfpsr_model_type_create(const dfpsr_dense_triangle *triangles, int32_t triangleCount, const float minBound[3], const float maxBound[3], const struct dfpsr_host_model *shadowModel, int32_t *typeIndex);
+int32_t dfpsr_model_type_count(void);
+
+/* ref: SDK/SpriteEngine/spriteAPI.h:24-53 */
+typedef struct dfpsr_sprite_instance {
+	int32_t typeIndex, direction;
+	int32_t location[3]; /* mini-tile units (1024 per tile) */
+	int32_t shadowCasting;
+	uint64_t userData;
+} dfpsr_sprite_instance;
+typedef struct dfpsr_model_instance {
+	int32_t typeIndex;
+	dfpsr_transform3d location; /* tile units */
+	uint64_t userData;
+} dfpsr_model_instance;
+
+/* The host side of SpriteWorldImpl (ref: SDK/SpriteEngine/spriteAPI.cpp:572-816): octrees of passive sprites and models, 512x512
+ * background blocks, dirty rectangles, temporary sprites / models / lights and the pass order of a frame. A frame is first PLANNED on
+ * the host into a list of operations (this is where the reference's control flow lives) and then EXECUTED on the device with the
+ * kernels above: block (re)generation and temporary sprites through dfpsr_draw_higher_batch / dfpsr_dense_model_render, all
+ * background copies of the frame in one kernel, every shadow cube map of the frame in one dfpsr_model_render_depth_batch and all
+ * lights plus blendLight in one dfpsr_light_frame. */
+typedef struct dfpsr_sprite_world dfpsr_sprite_world;
+enum {
+	DFPSR_SW_BLOCK_CLEAR = 1,   /* block: diffuse = 0, normal = (128,128,128,128), height = -1000000 (spriteAPI.cpp:521-523, :545-551) */
+	DFPSR_SW_BLOCK_SPRITE = 2,  /* draw_higher of sprite frame (typeIndex, frame) into block at (left, top) with heightOffset */
+	DFPSR_SW_BLOCK_MODEL = 3,   /* renderDenseModel<false> of model typeIndex into block with worldOrigin / transform */
+	DFPSR_SW_COPY_BLOCK = 4,    /* draw_copy x3: block pixels from (sourceLeft, sourceTop), size (width, height), to frame buffers at (left, top) */
+	DFPSR_SW_SPRITE = 5,        /* temporary sprite into the frame buffers */
+	DFPSR_SW_MODEL = 6,         /* temporary model into the frame buffers */
+	DFPSR_SW_LIGHT_CLEAR = 7,   /* no directed light: light buffer = 0 */
+	DFPSR_SW_LIGHT_DIRECTED = 8,/* light = index into the directed lights; flag = 1 overwrite, 0 add */
+	DFPSR_SW_SHADOW_CLEAR = 9,  /* cube map of point light `light` = 0 */
+	DFPSR_SW_SHADOW_SPRITE = 10,/* 6 x model_renderDepth of sprite type typeIndex's shadow model with `transform` (relative to the light) */
+	DFPSR_SW_SHADOW_MODEL = 11, /* the same for model type typeIndex */
+	DFPSR_SW_LIGHT_POINT = 12,  /* addPointLight of light `light`; flag = 1 with its shadow cube map */
+	DFPSR_SW_BLEND = 13         /* blendLight into the colour target */
+};
+typedef struct dfpsr_sprite_world_op {
+	int32_t op;
+	int32_t block;                 /* background block slot */
+	int32_t typeIndex, frame;
+	int32_t left, top, width, height;
+	int32_t sourceLeft, sourceTop;
+	float heightOffset;
+	float worldOrigin[2];
+	dfpsr_transform3d transform;
+	int32_t light, flag;
+} dfpsr_sprite_world_op;
+
+int dfpsr_sprite_world_create(dfpsr_sprite_world **out, const dfpsr_ortho_system *ortho, int32_t shadowResolution); /* ref: spriteAPI.cpp:818 */
+int dfpsr_sprite_world_destroy(dfpsr_sprite_world *world);
+int dfpsr_sprite_world_add_background_sprite(dfpsr_sprite_world *world, const dfpsr_sprite_instance *sprite); /* ref: spriteAPI.cpp:900-916 */
+int dfpsr_sprite_world_add_background_model(dfpsr_sprite_world *world, const dfpsr_model_instance *model);    /* ref: spriteAPI.cpp:918-937 */
+int dfpsr_sprite_world_add_temporary_sprite(dfpsr_sprite_world *world, const dfpsr_sprite_instance *sprite);  /* ref: spriteAPI.cpp:975-980 */
+int dfpsr_sprite_world_add_temporary_model(dfpsr_sprite_world *world, const dfpsr_model_instance *model);     /* ref: spriteAPI.cpp:982-986 */
+/* ref: spriteAPI.cpp:939-973. filter == NULL erases everything touching the search box; otherwise it returns non-zero to erase. */
+typedef int (*dfpsr_sprite_selection)(dfpsr_sprite_instance *sprite, const int32_t origin[3], const int32_t minBound[3], const int32_t maxBound[3], void *user);
+typedef int (*dfpsr_model_selection)(dfpsr_model_instance *model, const int32_t origin[3], const int32_t minBound[3], const int32_t maxBound[3], void *user);
+int dfpsr_sprite_world_remove_background_sprites(dfpsr_sprite_world *world, const int32_t searchMin[3], const int32_t searchMax[3], dfpsr_sprite_selection filter, void *user);
+int dfpsr_sprite_world_remove_background_models(dfpsr_sprite_world *world, const int32_t searchMin[3], const int32_t searchMax[3], dfpsr_model_selection filter, void *user);
+int dfpsr_sprite_world_create_temporary_point_light(dfpsr_sprite_world *world, const float position[3], float radius, float intensity, const int32_t colorRgb[3], int32_t shadowCasting); /* ref: spriteAPI.cpp:988-991 */
+int dfpsr_sprite_world_create_temporary_directed_light(dfpsr_sprite_world *world, const float direction[3], float intensity, const int32_t colorRgb[3]); /* ref: spriteAPI.cpp:993-996 */
+int dfpsr_sprite_world_clear_temporary(dfpsr_sprite_world *world); /* ref: spriteAPI.cpp:998-1004 */
+/* Camera (ref: spriteAPI.cpp:1050-1112). */
+int dfpsr_sprite_world_get_camera_location(const dfpsr_sprite_world *world, int32_t location[3]);
+int dfpsr_sprite_world_set_camera_location(dfpsr_sprite_world *world, const int32_t location[3]);
+int dfpsr_sprite_world_move_camera_in_pixels(dfpsr_sprite_world *world, int32_t offsetX, int32_t offsetY);
+int dfpsr_sprite_world_get_camera_direction_index(const dfpsr_sprite_world *world, int32_t *index);
+int dfpsr_sprite_world_set_camera_direction_index(dfpsr_sprite_world *world, int32_t index);
+int dfpsr_sprite_world_find_ground_at_pixel(const dfpsr_sprite_world *world, int32_t targetWidth, int32_t targetHeight, int32_t pixelX, int32_t pixelY, int32_t location[3]);
+/* Plans one frame for a width x height colour target exactly like SpriteWorldImpl::draw (ref: spriteAPI.cpp:754-816) and advances the
+ * world's state (block cache, dirty rectangles) WITHOUT touching the GPU. *ops stays valid until the next call on this world.
+ * Used by dfpsr_sprite_world_draw and by the host-logic parity tests, which replay the operations with the CPU oracle. */
+int dfpsr_sprite_world_plan_frame(dfpsr_sprite_world *world, int32_t width, int32_t height, const dfpsr_sprite_world_op **ops, int32_t *opCount);
+/* spriteWorld_draw (ref: spriteAPI.cpp:1006-1009): plans the frame and executes it on the device into `colorTarget` (DEVICE image). */
+int dfpsr_sprite_world_draw(dfpsr_sprite_world *world, const dfpsr_image *colorTarget, void *stream);
+/* The same with a HOST colour image: the blended frame is copied back and the stream synchronised. */
+int dfpsr_sprite_world_draw_host(dfpsr_sprite_world *world, uint32_t *colorHost, int32_t strideBytes, int32_t width, int32_t height, int32_t packOrder, void *stream);
+/* ref: spriteAPI.cpp:1078-1096 spriteWorld_get{Diffuse,Normal,Light,Height}Buffer — DEVICE images of the last frame (data == NULL before the first draw). */
+int dfpsr_sprite_world_get_buffers(const dfpsr_sprite_world *world, dfpsr_image *diffuse, dfpsr_image *normal, dfpsr_image *light, dfpsr_image *height);
+
 /* ---------------------------------------------------------------- filters */
 
 /* ref: api/filterAPI.cpp:852-860 filter_resize(ImageRgbaU8): `target` (newWidth x newHeight, RGBA order,

@@ -1262,10 +1262,105 @@ void orc_draw_higher(const dfpsr_image *targetHeight, const dfpsr_image *sourceH
 	}
 }
 
-/* ------------------------------------------------------------------------------------------- Sandbox light */
-
 static v3 mat3_transform(const dfpsr_matrix3x3 *m, v3 p) { return mat_transform(m->xAxis, m->yAxis, m->zAxis, p); }
 static v3 mat3_transform_transposed(const dfpsr_matrix3x3 *m, v3 p) { return mat_transform_transposed(m->xAxis, m->yAxis, m->zAxis, p); }
+
+/* ------------------------------------------------------------------------------------------- Sandbox dense models and sprite heights */
+
+/* The reference converts with cvttss2si; (uint32_t)float goes through the 64-bit conversion on x86-64. */
+static int32_t trunc_i32(float v) { return (v > -2147483904.0f && v < 2147483648.0f) ? (int32_t)v : INT32_MIN; }
+static uint32_t trunc_u32(float v) { return (v > -9223373136366403584.0f && v < 9223372036854775808.0f) ? (uint32_t)(int64_t)v : 0u; }
+
+/* SDK/SpriteEngine/spriteAPI.cpp:1243-1327 renderDenseModel<HIGH_QUALITY>, one triangle after the other like the reference. */
+void orc_dense_model_render(const dfpsr_dense_triangle *triangles, int32_t triangleCount, const float *minBound, const float *maxBound, const dfpsr_ortho_camera *view,
+                            const dfpsr_image *height, const dfpsr_image *diffuse, const dfpsr_image *normal, const float *worldOrigin, const dfpsr_transform3d *modelToWorld,
+                            int32_t highQuality, int32_t *dirtyRect) {
+	/* combineModelToScreenTransform (:27-33): modelToWorld * Transform3D((ox, oy, 0), worldSpaceToScreenDepth), math/Transform3D.h:56-58 */
+	const dfpsr_matrix3x3 *w2s = &view->worldSpaceToScreenDepth;
+	dfpsr_transform3d o2s;
+	{
+		v3 p = mat3_transform(w2s, v3_from(modelToWorld->position));
+		o2s.position[0] = p.x + worldOrigin[0]; o2s.position[1] = p.y + worldOrigin[1]; o2s.position[2] = p.z + 0.0f;
+		v3 ax = mat3_transform(w2s, v3_from(modelToWorld->xAxis)), ay = mat3_transform(w2s, v3_from(modelToWorld->yAxis)), az = mat3_transform(w2s, v3_from(modelToWorld->zAxis));
+		o2s.xAxis[0] = ax.x; o2s.xAxis[1] = ax.y; o2s.xAxis[2] = ax.z; o2s.yAxis[0] = ay.x; o2s.yAxis[1] = ay.y; o2s.yAxis[2] = ay.z; o2s.zAxis[0] = az.x; o2s.zAxis[1] = az.y; o2s.zAxis[2] = az.z;
+	}
+	/* boundingBoxToRectangle (:1132-1141) */
+	int32_t bl = 0, bt = 0, br = 0, bb = 0;
+	for (int c = 0; c < 8; c++) {
+		v3 p = transform_point(&o2s, v3_make((c & 1) ? maxBound[0] : minBound[0], (c & 2) ? maxBound[1] : minBound[1], (c & 4) ? maxBound[2] : minBound[2]));
+		int32_t x = trunc_i32(p.x), y = trunc_i32(p.y);
+		if (c == 0) { bl = x; bt = y; br = x + 1; bb = y + 1; }
+		else { if (x < bl) { bl = x; } if (y < bt) { bt = y; } if (x + 1 > br) { br = x + 1; } if (y + 1 > bb) { bb = y + 1; } }
+	}
+	const int32_t cw = height->width, ch = height->height;
+	if (dirtyRect) { dirtyRect[0] = dirtyRect[1] = dirtyRect[2] = dirtyRect[3] = 0; }
+	if (!(bl < cw && br > 0 && bt < ch && bb > 0)) { return; }
+	if (dirtyRect) { dirtyRect[0] = bl; dirtyRect[1] = bt; dirtyRect[2] = br - bl; dirtyRect[3] = bb - bt; }
+	/* modelToNormalSpace = modelToWorld.transform * transpose(normalToWorldSpace) (:1262, math/FMatrix3x3.h:78-80) */
+	const dfpsr_matrix3x3 *n2w = &view->normalToWorldSpace;
+	dfpsr_matrix3x3 nt, m2n;
+	nt.xAxis[0] = n2w->xAxis[0]; nt.xAxis[1] = n2w->yAxis[0]; nt.xAxis[2] = n2w->zAxis[0];
+	nt.yAxis[0] = n2w->xAxis[1]; nt.yAxis[1] = n2w->yAxis[1]; nt.yAxis[2] = n2w->zAxis[1];
+	nt.zAxis[0] = n2w->xAxis[2]; nt.zAxis[1] = n2w->yAxis[2]; nt.zAxis[2] = n2w->zAxis[2];
+	{
+		v3 ax = mat3_transform(&nt, v3_from(modelToWorld->xAxis)), ay = mat3_transform(&nt, v3_from(modelToWorld->yAxis)), az = mat3_transform(&nt, v3_from(modelToWorld->zAxis));
+		m2n.xAxis[0] = ax.x; m2n.xAxis[1] = ax.y; m2n.xAxis[2] = ax.z; m2n.yAxis[0] = ay.x; m2n.yAxis[1] = ay.y; m2n.yAxis[2] = ay.z; m2n.zAxis[0] = az.x; m2n.zAxis[1] = az.y; m2n.zAxis[2] = az.z;
+	}
+	for (int32_t i = 0; i < triangleCount; i++) {
+		const dfpsr_dense_triangle *tri = triangles + i;
+		v3 a = transform_point(&o2s, v3_from(tri->posA)), b = transform_point(&o2s, v3_from(tri->posB)), c = transform_point(&o2s, v3_from(tri->posC));
+		/* getBackCulledTriangleBound (:1143-1156) */
+		if (((c.x - a.x) * (b.y - a.y)) + ((c.y - a.y) * (a.x - b.x)) >= 0.0f) { continue; }
+		float minX = a.x < b.x ? a.x : b.x; minX = minX < c.x ? minX : c.x;
+		float minY = a.y < b.y ? a.y : b.y; minY = minY < c.y ? minY : c.y;
+		float maxX = a.x > b.x ? a.x : b.x; maxX = maxX > c.x ? maxX : c.x;
+		float maxY = a.y > b.y ? a.y : b.y; maxY = maxY > c.y ? maxY : c.y;
+		int32_t l = trunc_i32(minX), t = trunc_i32(minY), r = trunc_i32(maxX) + 1, bo = trunc_i32(maxY) + 1;
+		if (!(l < cw && r > 0 && t < ch && bo > 0)) { continue; } /* IRect::cut, math/IRect.h:56-66 */
+		if (l < 0) { l = 0; } if (t < 0) { t = 0; } if (r > cw) { r = cw; } if (bo > ch) { bo = ch; }
+		if (!(r > l && bo > t)) { continue; }
+		/* inverse(FMatrix2x2(B - A, C - A)), math/FMatrix2x2.h:69-76 */
+		const float xx = b.x - a.x, xy = b.y - a.y, yx = c.x - a.x, yy = c.y - a.y;
+		const float inv = 1.0f / (xx * yy - xy * yx);
+		const float m0 = yy * inv, m1 = -xy * inv, m2 = -yx * inv, m3 = xx * inv;
+		v3 na = mat3_transform(&m2n, v3_from(tri->normalA)), nb = mat3_transform(&m2n, v3_from(tri->normalB)), nc = mat3_transform(&m2n, v3_from(tri->normalC));
+		for (int32_t y = t; y < bo; y++) {
+			for (int32_t x = l; x < r; x++) {
+				const float ox = ((float)x + 0.5f) - a.x, oy = ((float)y + 0.5f) - a.y;
+				const float wb = ox * m0 + oy * m2, wc = ox * m1 + oy * m3;
+				const float wa = 1.0f - (wb + wc);
+				if (wa >= -0.00001f && wb >= -0.00001f && wc >= -0.00001f) {
+					const float h = a.z * wa + b.z * wb + c.z * wc;
+					float *hp = depth_px(height, x, y);
+					if (h > *hp) {
+						*hp = h;
+						const float cr = tri->colorA[0] * wa + tri->colorB[0] * wb + tri->colorC[0] * wc;
+						const float cg = tri->colorA[1] * wa + tri->colorB[1] * wb + tri->colorC[1] * wc;
+						const float cb = tri->colorA[2] * wa + tri->colorB[2] * wb + tri->colorC[2] * wc;
+						*color_px(diffuse, x, y) = trunc_u32(cr) | (trunc_u32(cg) << 8) | (trunc_u32(cb) << 16) | (255u << 24);
+						v3 n = v3_make(na.x * wa + nb.x * wb + nc.x * wc, na.y * wa + nb.y * wb + nc.y * wc, na.z * wa + nb.z * wb + nc.z * wc);
+						if (highQuality) { n = v3_normalize(n); }
+						*color_px(normal, x, y) = trunc_u32((n.x + 1.0f) * 127.5f) | (trunc_u32((n.y + 1.0f) * 127.5f) << 8) | (trunc_u32((n.z + 1.0f) * 127.5f) << 16) | (255u << 24);
+					}
+				}
+			}
+		}
+	}
+}
+
+/* SDK/SpriteEngine/spriteAPI.cpp:157-174 scaleHeightImage: heights of one sprite frame from the atlas' height column (RGBA order). */
+void orc_sprite_scale_height(const dfpsr_image *heightColumn, const dfpsr_image *colorColumn, float minHeight, float maxHeight, const dfpsr_image *out) {
+	const float scale = (maxHeight - minHeight) / 255.0f, offset = minHeight;
+	for (int32_t y = 0; y < out->height; y++) {
+		for (int32_t x = 0; x < out->width; x++) {
+			const float value = (float)(*color_px(heightColumn, x, y) & 255u);
+			*depth_px(out, x, y) = ((*color_px(colorColumn, x, y) >> 24) > 127u) ? (value * scale) + offset : -INFINITY;
+		}
+	}
+}
+
+/* ------------------------------------------------------------------------------------------- Sandbox light */
+
 
 static uint8_t sat_add_u8(uint8_t a, uint8_t b) { uint32_t s = (uint32_t)a + (uint32_t)b; return (uint8_t)(s > 255u ? 255u : s); } /* base/simd.h:2670 */
 

@@ -61,6 +61,13 @@ void orc_draw_copy_rgba(const dfpsr_image *target, const dfpsr_image *source, in
 void orc_draw_copy_f32(const dfpsr_image *target, const dfpsr_image *source, int32_t left, int32_t top);
 void orc_draw_higher(const dfpsr_image *targetHeight, const dfpsr_image *sourceHeight, const dfpsr_image *targetA, const dfpsr_image *sourceA, const dfpsr_image *targetB, const dfpsr_image *sourceB, int32_t left, int32_t top, float offset);
 
+/* renderDenseModel<HIGH_QUALITY> (SDK/SpriteEngine/spriteAPI.cpp:1243-1327); dirtyRect = {left, top, width, height} or zeros when culled. */
+void orc_dense_model_render(const dfpsr_dense_triangle *triangles, int32_t triangleCount, const float *minBound, const float *maxBound, const dfpsr_ortho_camera *view,
+                            const dfpsr_image *height, const dfpsr_image *diffuse, const dfpsr_image *normal, const float *worldOrigin, const dfpsr_transform3d *modelToWorld,
+                            int32_t highQuality, int32_t *dirtyRect);
+/* scaleHeightImage (SDK/SpriteEngine/spriteAPI.cpp:157-174) for one sprite frame. */
+void orc_sprite_scale_height(const dfpsr_image *heightColumn, const dfpsr_image *colorColumn, float minHeight, float maxHeight, const dfpsr_image *out);
+
 /* laneCount: the reference's laneCountX_32Bit (4 for the SSE2/scalar builds, 8 for AVX2); it decides the
  * alignment of the point light's rectangle and the grouping of its incremental position adds.
  * rowsPerJob: 0 = one job for the whole rectangle (DISABLE_MULTI_THREADING build). */

@@ -15,6 +15,9 @@
 #include "DFPSR/api/rendererAPI.h"
 #include "SDK/SpriteEngine/lightAPI.h"
 #include "SDK/SpriteEngine/orthoAPI.h"
+// The sprite engine keeps renderDenseModel, SpriteType, ModelType and SpriteWorldImpl local to its translation unit. Including that
+// unit here (it is compiled from where it lies and is NOT built a second time, see oracle/Makefile) lets the wrappers below call them.
+#include "SDK/SpriteEngine/spriteAPI.cpp"
 
 #include <vector>
 #include <cstring>
@@ -474,6 +477,119 @@ void ref_filter_map(int target, int op, const int32_t *params, int source, int s
 
 void ref_filter_block_magnify(int target, int source, int pixelWidth, int pixelHeight) {
 	filter_blockMagnify(g_images[target].rgba, g_images[source].rgba, pixelWidth, pixelHeight);
+}
+
+// ---- Sandbox sprite engine (SDK/SpriteEngine/spriteAPI.cpp, orthoAPI.cpp)
+
+static void fillOrthoCamera(dfpsr_ortho_camera &out, const OrthoView &v) {
+	memset(&out, 0, sizeof(out));
+	out.id = v.id; out.worldDirection = v.worldDirection;
+	fromMatrix(out.normalToWorldSpace, v.normalToWorldSpace);
+	out.pixelOffsetPerTileX[0] = v.pixelOffsetPerTileX.x; out.pixelOffsetPerTileX[1] = v.pixelOffsetPerTileX.y;
+	out.pixelOffsetPerTileZ[0] = v.pixelOffsetPerTileZ.x; out.pixelOffsetPerTileZ[1] = v.pixelOffsetPerTileZ.y;
+	out.yPixelsPerTile = v.yPixelsPerTile;
+	fromMatrix(out.screenDepthToWorldSpace, v.screenDepthToWorldSpace);
+	fromMatrix(out.worldSpaceToScreenDepth, v.worldSpaceToScreenDepth);
+	fromMatrix(out.screenDepthToLightSpace, v.screenDepthToLightSpace);
+	fromMatrix(out.lightSpaceToScreenDepth, v.lightSpaceToScreenDepth);
+	out.roundedScreenPixelsToWorldTiles[0] = v.roundedScreenPixelsToWorldTiles.xAxis.x; out.roundedScreenPixelsToWorldTiles[1] = v.roundedScreenPixelsToWorldTiles.xAxis.y;
+	out.roundedScreenPixelsToWorldTiles[2] = v.roundedScreenPixelsToWorldTiles.yAxis.x; out.roundedScreenPixelsToWorldTiles[3] = v.roundedScreenPixelsToWorldTiles.yAxis.y;
+}
+
+void ref_ortho_system(float cameraTilt, int pixelsPerTile, dfpsr_ortho_system *out) {
+	ensureStarted();
+	OrthoSystem system(cameraTilt, pixelsPerTile);
+	out->cameraTilt = system.cameraTilt; out->pixelsPerTile = system.pixelsPerTile;
+	for (int a = 0; a < 8; a++) { fillOrthoCamera(out->view[a], system.view[a]); }
+}
+
+static std::vector<DenseModel> g_dense;
+static std::vector<SpriteWorld> g_worlds;
+
+int ref_dense_model_create(int model) {
+	g_dense.push_back(DenseModel_create(g_models[model]));
+	return (int)g_dense.size() - 1;
+}
+
+int ref_dense_model_triangles(int dense, dfpsr_dense_triangle *out, float *minOut, float *maxOut) {
+	const DenseModel &m = g_dense[dense];
+	static_assert(sizeof(DenseTriangle) == sizeof(dfpsr_dense_triangle), "DenseTriangle layout");
+	if (out) { for (int i = 0; i < m->triangles.length(); i++) { memcpy(out + i, &m->triangles[i], sizeof(DenseTriangle)); } }
+	if (minOut) { minOut[0] = m->minBound.x; minOut[1] = m->minBound.y; minOut[2] = m->minBound.z; }
+	if (maxOut) { maxOut[0] = m->maxBound.x; maxOut[1] = m->maxBound.y; maxOut[2] = m->maxBound.z; }
+	return (int)m->triangles.length();
+}
+
+void ref_dense_model_render(int dense, float cameraTilt, int pixelsPerTile, int viewIndex, int height, int diffuse, int normal, float originX, float originY, const dfpsr_transform3d *modelToWorld, int highQuality, int32_t *rect) {
+	OrthoSystem system(cameraTilt, pixelsPerTile);
+	IRect r;
+	if (highQuality) { r = renderDenseModel<true>(g_dense[dense], system.view[viewIndex], g_images[height].f32, g_images[diffuse].rgba, g_images[normal].rgba, FVector2D(originX, originY), toTransform(modelToWorld)); }
+	else { r = renderDenseModel<false>(g_dense[dense], system.view[viewIndex], g_images[height].f32, g_images[diffuse].rgba, g_images[normal].rgba, FVector2D(originX, originY), toTransform(modelToWorld)); }
+	if (rect) { rect[0] = r.left(); rect[1] = r.top(); rect[2] = r.width(); rect[3] = r.height(); }
+}
+
+// The reference only loads sprite types from <name>.png + <name>.ini: the atlas image and the configuration text are written to
+// `folder` with the reference's own PNG encoder (lossless) and loaded back through spriteWorld_loadSpriteTypeFromFile.
+int ref_sprite_type_create(int atlas, const char *iniText, const char *folder, const char *name) {
+	ensureStarted();
+	String folderPath = string_combine(folder), spriteName = string_combine(name);
+	String base = file_combinePaths(folderPath, spriteName);
+	image_save(g_images[atlas].rgba, string_combine(base, U".png"));
+	string_save(string_combine(base, U".ini"), string_combine(iniText));
+	return spriteWorld_loadSpriteTypeFromFile(folderPath, spriteName);
+}
+
+int ref_sprite_type_count() { return spriteWorld_getSpriteTypeCount(); }
+
+int ref_model_type_create(int dense, int shadowModel) {
+	ensureStarted();
+	return (int)modelTypes.pushConstructGetIndex(g_dense[dense], shadowModel >= 0 ? g_models[shadowModel] : Model());
+}
+
+int ref_world_create(float cameraTilt, int pixelsPerTile, int shadowResolution) {
+	ensureStarted();
+	g_worlds.push_back(spriteWorld_create(OrthoSystem(cameraTilt, pixelsPerTile), shadowResolution));
+	return (int)g_worlds.size() - 1;
+}
+
+static SpriteInstance toSprite(const dfpsr_sprite_instance *s) {
+	return SpriteInstance(s->typeIndex, s->direction, IVector3D(s->location[0], s->location[1], s->location[2]), s->shadowCasting != 0, s->userData);
+}
+static ModelInstance toModelInstance(const dfpsr_model_instance *m) { return ModelInstance(m->typeIndex, toTransform(&m->location), m->userData); }
+
+void ref_world_add_background_sprite(int world, const dfpsr_sprite_instance *s) { spriteWorld_addBackgroundSprite(g_worlds[world], toSprite(s)); }
+void ref_world_add_background_model(int world, const dfpsr_model_instance *m) { spriteWorld_addBackgroundModel(g_worlds[world], toModelInstance(m)); }
+void ref_world_add_temporary_sprite(int world, const dfpsr_sprite_instance *s) { spriteWorld_addTemporarySprite(g_worlds[world], toSprite(s)); }
+void ref_world_add_temporary_model(int world, const dfpsr_model_instance *m) { spriteWorld_addTemporaryModel(g_worlds[world], toModelInstance(m)); }
+void ref_world_remove_background_sprites(int world, const int32_t *mn, const int32_t *mx) { spriteWorld_removeBackgroundSprites(g_worlds[world], IVector3D(mn[0], mn[1], mn[2]), IVector3D(mx[0], mx[1], mx[2])); }
+void ref_world_remove_background_models(int world, const int32_t *mn, const int32_t *mx) { spriteWorld_removeBackgroundModels(g_worlds[world], IVector3D(mn[0], mn[1], mn[2]), IVector3D(mx[0], mx[1], mx[2])); }
+void ref_world_point_light(int world, const float *position, float radius, float intensity, const int32_t *color, int shadowCasting) {
+	spriteWorld_createTemporary_pointLight(g_worlds[world], v3(position), radius, intensity, ColorRgbI32(color[0], color[1], color[2]), shadowCasting != 0);
+}
+void ref_world_directed_light(int world, const float *direction, float intensity, const int32_t *color) {
+	spriteWorld_createTemporary_directedLight(g_worlds[world], v3(direction), intensity, ColorRgbI32(color[0], color[1], color[2]));
+}
+void ref_world_clear_temporary(int world) { spriteWorld_clearTemporary(g_worlds[world]); }
+void ref_world_set_camera_location(int world, const int32_t *p) { spriteWorld_setCameraLocation(g_worlds[world], IVector3D(p[0], p[1], p[2])); }
+void ref_world_get_camera_location(int world, int32_t *p) { IVector3D l = spriteWorld_getCameraLocation(g_worlds[world]); p[0] = l.x; p[1] = l.y; p[2] = l.z; }
+void ref_world_move_camera_in_pixels(int world, int x, int y) { spriteWorld_moveCameraInPixels(g_worlds[world], IVector2D(x, y)); }
+void ref_world_set_camera_direction_index(int world, int index) { spriteWorld_setCameraDirectionIndex(g_worlds[world], index); }
+void ref_world_find_ground_at_pixel(int world, int color, int x, int y, int32_t *out) {
+	IVector3D l = spriteWorld_findGroundAtPixel(g_worlds[world], g_images[color].rgbaAligned, IVector2D(x, y));
+	out[0] = l.x; out[1] = l.y; out[2] = l.z;
+}
+// colour must be a whole image (not a sub-image)
+void ref_world_draw(int world, int color) { spriteWorld_draw(g_worlds[world], g_images[color].rgbaAligned); }
+// Copies of the four deferred buffers after a draw: tight rows, 4 bytes per pixel.
+void ref_world_read_buffers(int world, uint32_t *diffuse, uint32_t *normal, uint32_t *light, float *height) {
+	SpriteWorld &w = g_worlds[world];
+	int width = image_getWidth(w->diffuseBuffer), h = image_getHeight(w->diffuseBuffer);
+	for (int y = 0; y < h; y++) {
+		if (diffuse) { memcpy(diffuse + (size_t)y * width, image_getSafePointer<uint32_t>(w->diffuseBuffer, y).getUnsafe(), (size_t)width * 4); }
+		if (normal) { memcpy(normal + (size_t)y * width, image_getSafePointer<uint32_t>(w->normalBuffer, y).getUnsafe(), (size_t)width * 4); }
+		if (light) { memcpy(light + (size_t)y * width, image_getSafePointer<uint32_t>(w->lightBuffer, y).getUnsafe(), (size_t)width * 4); }
+		if (height) { memcpy(height + (size_t)y * width, image_getSafePointer<float>(w->heightBuffer, y).getUnsafe(), (size_t)width * 4); }
+	}
 }
 
 } // extern "C"

@@ -24,6 +24,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import refbind  # noqa: E402
 from dfpsr_b200 import abi, scenes  # noqa: E402
 import sandbox_scene  # noqa: E402
+import sprite_world_scene  # noqa: E402
 
 
 def sha(a):
@@ -88,11 +89,23 @@ def sandbox(ref):
     return {"sandbox_800x600_16": out}
 
 
+def sprite_world(ref):
+    """The scripted Sandbox session of tests/sprite_world_scene.py through the reference's spriteWorld_* API, plus renderDenseModel alone."""
+    import tempfile
+    assets, script = sprite_world_scene.build_assets(), sprite_world_scene.build_script()
+    frames = sprite_world_scene.run_reference(ref, assets, script, tempfile.mkdtemp(prefix="dfpsr_golden_"))
+    out = {"script_frames": [dict(sprite_world_scene.frame_hashes(f), camera=[int(v) for v in f["camera"]], ground=[int(v) for v in f["ground"]],
+                                  covered=float((f["height"] > -1e5).mean())) for f in frames]}
+    out["dense"] = [dict(case=case, **sprite_world_scene.frame_hashes_dense(sprite_world_scene.dense_reference(ref, assets, case))) for case in range(len(sprite_world_scene.DENSE_CASES))]
+    ref.free_all()
+    return out
+
+
 if __name__ == "__main__":
     ref = refbind.Ref("scalar")
-    which = sys.argv[1:] or ["raster", "filters", "sandbox"]
+    which = sys.argv[1:] or ["raster", "filters", "sandbox", "sprite_world"]
     for name in which:
-        data = {"raster": raster, "filters": filters, "sandbox": sandbox}[name](ref)
+        data = {"raster": raster, "filters": filters, "sandbox": sandbox, "sprite_world": sprite_world}[name](ref)
         path = os.path.join(HERE, name + ".json")
         json.dump(data, open(path, "w"), indent=1, sort_keys=True)
         print("wrote", path)

@@ -52,6 +52,21 @@ def load(flavour="scalar"):
         "ref_light_blend": (None, [i, i, i]),
         "ref_filter_resize": (i, [i, i, i, i]), "ref_filter_map": (None, [i, i, p, i, i, i]),
         "ref_filter_block_magnify": (None, [i, i, i, i]),
+        "ref_ortho_system": (None, [f, i, C.POINTER(abi.OrthoSystem)]),
+        "ref_dense_model_create": (i, [i]), "ref_dense_model_triangles": (i, [i, p, p, p]),
+        "ref_dense_model_render": (None, [i, f, i, i, i, i, i, f, f, T, i, p]),
+        "ref_sprite_type_create": (i, [i, C.c_char_p, C.c_char_p, C.c_char_p]), "ref_sprite_type_count": (i, []),
+        "ref_model_type_create": (i, [i, i]),
+        "ref_world_create": (i, [f, i, i]),
+        "ref_world_add_background_sprite": (None, [i, C.POINTER(abi.SpriteInstance)]), "ref_world_add_background_model": (None, [i, C.POINTER(abi.ModelInstance)]),
+        "ref_world_add_temporary_sprite": (None, [i, C.POINTER(abi.SpriteInstance)]), "ref_world_add_temporary_model": (None, [i, C.POINTER(abi.ModelInstance)]),
+        "ref_world_remove_background_sprites": (None, [i, p, p]), "ref_world_remove_background_models": (None, [i, p, p]),
+        "ref_world_point_light": (None, [i, p, f, f, p, i]), "ref_world_directed_light": (None, [i, p, f, p]),
+        "ref_world_clear_temporary": (None, [i]),
+        "ref_world_set_camera_location": (None, [i, p]), "ref_world_get_camera_location": (None, [i, p]),
+        "ref_world_move_camera_in_pixels": (None, [i, i, i]), "ref_world_set_camera_direction_index": (None, [i, i]),
+        "ref_world_find_ground_at_pixel": (None, [i, i, i, i, p]),
+        "ref_world_draw": (None, [i, i]), "ref_world_read_buffers": (None, [i, p, p, p, p]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

@@ -88,8 +88,10 @@ struct B200Buffer { // ref-counted device allocation + lazily synchronised host 
 	size_t bytes = 0;
 	std::vector<uint8_t> host;
 	bool hostValid = false, deviceDirty = false; // deviceDirty: kernels wrote since the last download
+	bool owned = true;
 	explicit B200Buffer(size_t bytes) : bytes(bytes) { b200_check(dfpsr_malloc(&device, bytes > 0 ? bytes : 1)); }
-	~B200Buffer() { if (device) { dfpsr_free(device); } }
+	B200Buffer(void *borrowedDevice, size_t bytes) : device(borrowedDevice), bytes(bytes), deviceDirty(true), owned(false) {} // a view of memory owned elsewhere
+	~B200Buffer() { if (device && owned) { dfpsr_free(device); } }
 	B200Buffer(const B200Buffer &) = delete;
 	B200Buffer &operator=(const B200Buffer &) = delete;
 	uint8_t *hostData() {
@@ -545,6 +547,134 @@ inline void blendLight(ImageRgbaU8 &colorBuffer, const ImageRgbaU8 &diffuseBuffe
 	dfpsr_image c = colorBuffer.pod(), d = diffuseBuffer.pod(), l = lightBuffer.pod();
 	b200_check(dfpsr_light_blend(&c, &d, &l, b200_stream())); colorBuffer.touchedByDevice();
 }
+
+// ---------------------------------------------------------------- Sandbox sprite world (ref: SDK/SpriteEngine/spriteAPI.h:24-145, orthoAPI.h:92-134)
+struct IVector2D { int32_t x = 0, y = 0; IVector2D() {} IVector2D(int32_t x, int32_t y) : x(x), y(y) {} };
+struct IVector3D { int32_t x = 0, y = 0, z = 0; IVector3D() {} IVector3D(int32_t x, int32_t y, int32_t z) : x(x), y(y), z(z) {} };
+using Direction = int32_t;
+static const int32_t ortho_miniUnitsPerTile = 1024; // ref: orthoAPI.h:28
+struct OrthoSystem { // ref: orthoAPI.h:92-134 — the eight views are derived exactly like OrthoSystem::update (orthoAPI.cpp:82-119)
+	dfpsr_ortho_system pod{};
+	OrthoSystem() {}
+	OrthoSystem(float cameraTilt, int32_t pixelsPerTile) { b200_check(dfpsr_ortho_system_create(&pod, cameraTilt, pixelsPerTile)); }
+	OrthoView lightView(int32_t cameraIndex) const { OrthoView v; b200_check(dfpsr_ortho_camera_light_view(&pod.view[cameraIndex], &v.pod)); return v; }
+};
+struct SpriteInstance { // ref: spriteAPI.h:24-36
+	int32_t typeIndex; Direction direction; IVector3D location; bool shadowCasting; uint64_t userData;
+	SpriteInstance(int32_t typeIndex, Direction direction, const IVector3D &location, bool shadowCasting, uint64_t userData = 0)
+	: typeIndex(typeIndex), direction(direction), location(location), shadowCasting(shadowCasting), userData(userData) {}
+};
+struct ModelInstance { // ref: spriteAPI.h:44-52
+	int32_t typeIndex; Transform3D location; uint64_t userData;
+	ModelInstance(int32_t typeIndex, const Transform3D &location, uint64_t userData = 0) : typeIndex(typeIndex), location(location), userData(userData) {}
+};
+inline dfpsr_sprite_instance b200_pod(const SpriteInstance &s) {
+	dfpsr_sprite_instance r; r.typeIndex = s.typeIndex; r.direction = s.direction; r.location[0] = s.location.x; r.location[1] = s.location.y; r.location[2] = s.location.z;
+	r.shadowCasting = s.shadowCasting ? 1 : 0; r.userData = s.userData; return r;
+}
+inline dfpsr_model_instance b200_pod(const ModelInstance &m) { dfpsr_model_instance r; r.typeIndex = m.typeIndex; r.location = b200_pod(m.location); r.userData = m.userData; return r; }
+
+// Sprite types. The reference loads <name>.png + <name>.ini (spriteAPI.cpp:190-232); image codecs are outside of the hot path, so the
+// decoded atlas (RGBA order, host pixels) and the parsed settings are handed over instead.
+struct SpriteConfig { // ref: spriteAPI.cpp:47-55
+	int32_t centerX = 0, centerY = 0, frameRows = 1, propertyColumns = 3;
+	FVector3D minBound, maxBound;
+	std::vector<FVector3D> points; std::vector<int32_t> triangleIndices;
+};
+inline int32_t spriteWorld_createSpriteType(const uint32_t *atlasPixels, int32_t width, int32_t height, int32_t strideBytes, const SpriteConfig &config) {
+	dfpsr_sprite_config c{};
+	c.centerX = config.centerX; c.centerY = config.centerY; c.frameRows = config.frameRows; c.propertyColumns = config.propertyColumns;
+	c.minBound[0] = config.minBound.x; c.minBound[1] = config.minBound.y; c.minBound[2] = config.minBound.z;
+	c.maxBound[0] = config.maxBound.x; c.maxBound[1] = config.maxBound.y; c.maxBound[2] = config.maxBound.z;
+	std::vector<float> flat;
+	for (const FVector3D &p : config.points) { flat.push_back(p.x); flat.push_back(p.y); flat.push_back(p.z); }
+	c.points = flat.data(); c.pointCount = (int32_t)config.points.size();
+	c.triangleIndices = config.triangleIndices.data(); c.triangleIndexCount = (int32_t)config.triangleIndices.size();
+	int32_t index = -1;
+	b200_check(dfpsr_sprite_type_create(atlasPixels, width, height, strideBytes, &c, &index));
+	return index;
+}
+inline int32_t spriteWorld_getSpriteTypeCount() { return dfpsr_sprite_type_count(); } // ref: spriteAPI.h:60
+inline int32_t spriteWorld_getModelTypeCount() { return dfpsr_model_type_count(); }   // ref: spriteAPI.h:65
+// ref: spriteAPI.cpp:262-277 ModelType(visibleModel, shadowModel): DenseModel_create(visible) + the shadow model's geometry (all parts)
+inline int32_t spriteWorld_createModelType(const Model &visibleModel, const Model &shadowModel) {
+	b200_require(visibleModel, "spriteWorld_createModelType");
+	auto flatten = [](const Model &m, std::vector<dfpsr_polygon> &polygons) { for (const B200Part &part : m->parts) { polygons.insert(polygons.end(), part.polygons.begin(), part.polygons.end()); } };
+	std::vector<dfpsr_polygon> visible, shadow;
+	flatten(visibleModel, visible);
+	std::vector<dfpsr_dense_triangle> triangles((size_t)dfpsr_dense_model_triangle_count(visible.data(), (int32_t)visible.size()));
+	float mn[3], mx[3];
+	b200_check(dfpsr_dense_model_build(visibleModel->points.data(), (int32_t)(visibleModel->points.size() / 3), visible.data(), (int32_t)visible.size(), triangles.data(), mn, mx));
+	dfpsr_host_model host{};
+	if (shadowModel) {
+		flatten(shadowModel, shadow);
+		host.points = shadowModel->points.data(); host.pointCount = (int32_t)(shadowModel->points.size() / 3);
+		host.polygons = shadow.data(); host.polygonCount = (int32_t)shadow.size();
+	}
+	int32_t index = -1;
+	b200_check(dfpsr_model_type_create(triangles.data(), (int32_t)triangles.size(), mn, mx, shadowModel ? &host : nullptr, &index));
+	return index;
+}
+
+struct B200SpriteWorld {
+	dfpsr_sprite_world *handle = nullptr;
+	OrthoSystem ortho;
+	B200SpriteWorld(const OrthoSystem &ortho, int32_t shadowResolution) : ortho(ortho) { b200_check(dfpsr_sprite_world_create(&handle, &ortho.pod, shadowResolution)); }
+	~B200SpriteWorld() { dfpsr_sprite_world_destroy(handle); }
+	B200SpriteWorld(const B200SpriteWorld &) = delete;
+	B200SpriteWorld &operator=(const B200SpriteWorld &) = delete;
+};
+using SpriteWorld = std::shared_ptr<B200SpriteWorld>;
+inline dfpsr_sprite_world *b200_world(const SpriteWorld &world, const char *method) { if (!world) { throwError(std::string("The world handle was null in ") + method); } return world->handle; }
+inline SpriteWorld spriteWorld_create(OrthoSystem ortho, int32_t shadowResolution) { return std::make_shared<B200SpriteWorld>(ortho, shadowResolution); } // ref: spriteAPI.h:68
+inline void spriteWorld_addBackgroundSprite(SpriteWorld &world, const SpriteInstance &sprite) { dfpsr_sprite_instance s = b200_pod(sprite); b200_check(dfpsr_sprite_world_add_background_sprite(b200_world(world, "spriteWorld_addBackgroundSprite"), &s)); }
+inline void spriteWorld_addBackgroundModel(SpriteWorld &world, const ModelInstance &instance) { dfpsr_model_instance m = b200_pod(instance); b200_check(dfpsr_sprite_world_add_background_model(b200_world(world, "spriteWorld_addBackgroundModel"), &m)); }
+inline void spriteWorld_addTemporarySprite(SpriteWorld &world, const SpriteInstance &sprite) { dfpsr_sprite_instance s = b200_pod(sprite); b200_check(dfpsr_sprite_world_add_temporary_sprite(b200_world(world, "spriteWorld_addTemporarySprite"), &s)); }
+inline void spriteWorld_addTemporaryModel(SpriteWorld &world, const ModelInstance &instance) { dfpsr_model_instance m = b200_pod(instance); b200_check(dfpsr_sprite_world_add_temporary_model(b200_world(world, "spriteWorld_addTemporaryModel"), &m)); }
+// ref: spriteAPI.h:76-92 — erase everything touching the box (the selection-callback overloads are available on the C ABI)
+inline void spriteWorld_removeBackgroundSprites(SpriteWorld &world, const IVector3D &searchMinBound, const IVector3D &searchMaxBound) {
+	const int32_t mn[3] = {searchMinBound.x, searchMinBound.y, searchMinBound.z}, mx[3] = {searchMaxBound.x, searchMaxBound.y, searchMaxBound.z};
+	b200_check(dfpsr_sprite_world_remove_background_sprites(b200_world(world, "spriteWorld_removeBackgroundSprites"), mn, mx, nullptr, nullptr));
+}
+inline void spriteWorld_removeBackgroundModels(SpriteWorld &world, const IVector3D &searchMinBound, const IVector3D &searchMaxBound) {
+	const int32_t mn[3] = {searchMinBound.x, searchMinBound.y, searchMinBound.z}, mx[3] = {searchMaxBound.x, searchMaxBound.y, searchMaxBound.z};
+	b200_check(dfpsr_sprite_world_remove_background_models(b200_world(world, "spriteWorld_removeBackgroundModels"), mn, mx, nullptr, nullptr));
+}
+inline void spriteWorld_createTemporary_pointLight(SpriteWorld &world, const FVector3D position, float radius, float intensity, const ColorRgbaI32 &color, bool shadowCasting) { // ref: spriteAPI.h:96
+	const float p[3] = {position.x, position.y, position.z}; const int32_t c[3] = {color.red, color.green, color.blue};
+	b200_check(dfpsr_sprite_world_create_temporary_point_light(b200_world(world, "spriteWorld_createTemporary_pointLight"), p, radius, intensity, c, shadowCasting ? 1 : 0));
+}
+inline void spriteWorld_createTemporary_directedLight(SpriteWorld &world, const FVector3D direction, float intensity, const ColorRgbaI32 &color) { // ref: spriteAPI.h:97
+	const float d[3] = {direction.x, direction.y, direction.z}; const int32_t c[3] = {color.red, color.green, color.blue};
+	b200_check(dfpsr_sprite_world_create_temporary_directed_light(b200_world(world, "spriteWorld_createTemporary_directedLight"), d, intensity, c));
+}
+inline void spriteWorld_clearTemporary(SpriteWorld &world) { b200_check(dfpsr_sprite_world_clear_temporary(b200_world(world, "spriteWorld_clearTemporary"))); } // ref: spriteAPI.h:99
+inline void spriteWorld_draw(SpriteWorld &world, ImageRgbaU8 &colorTarget) { // ref: spriteAPI.h:102
+	dfpsr_image c = colorTarget.pod();
+	b200_check(dfpsr_sprite_world_draw(b200_world(world, "spriteWorld_draw"), &c, b200_stream())); colorTarget.touchedByDevice();
+}
+inline IVector3D spriteWorld_findGroundAtPixel(SpriteWorld &world, const ImageRgbaU8 &colorBuffer, const IVector2D &pixelLocation) { // ref: spriteAPI.h:109
+	int32_t r[3]; b200_check(dfpsr_sprite_world_find_ground_at_pixel(b200_world(world, "spriteWorld_findGroundAtPixel"), colorBuffer.width, colorBuffer.height, pixelLocation.x, pixelLocation.y, r));
+	return IVector3D(r[0], r[1], r[2]);
+}
+inline void spriteWorld_moveCameraInPixels(SpriteWorld &world, const IVector2D &pixelOffset) { b200_check(dfpsr_sprite_world_move_camera_in_pixels(b200_world(world, "spriteWorld_moveCameraInPixels"), pixelOffset.x, pixelOffset.y)); } // ref: spriteAPI.h:113
+inline IVector3D spriteWorld_getCameraLocation(const SpriteWorld &world) { int32_t r[3]; b200_check(dfpsr_sprite_world_get_camera_location(b200_world(world, "spriteWorld_getCameraLocation"), r)); return IVector3D(r[0], r[1], r[2]); } // ref: spriteAPI.h:126
+inline void spriteWorld_setCameraLocation(SpriteWorld &world, const IVector3D miniTileLocation) { const int32_t p[3] = {miniTileLocation.x, miniTileLocation.y, miniTileLocation.z}; b200_check(dfpsr_sprite_world_set_camera_location(b200_world(world, "spriteWorld_setCameraLocation"), p)); }
+inline int32_t spriteWorld_getCameraDirectionIndex(const SpriteWorld &world) { int32_t i = 0; b200_check(dfpsr_sprite_world_get_camera_direction_index(b200_world(world, "spriteWorld_getCameraDirectionIndex"), &i)); return i; } // ref: spriteAPI.h:132
+inline void spriteWorld_setCameraDirectionIndex(SpriteWorld &world, int32_t index) { b200_check(dfpsr_sprite_world_set_camera_direction_index(b200_world(world, "spriteWorld_setCameraDirectionIndex"), index)); }
+inline OrthoSystem &spriteWorld_getOrthoSystem(SpriteWorld &world) { b200_world(world, "spriteWorld_getOrthoSystem"); return world->ortho; } // ref: spriteAPI.h:139
+// ref: spriteAPI.h:120-123 — views over the world's device buffers of the last frame (not owned: valid until the world is resized or destroyed)
+template <typename P> inline B200Image<P> b200_borrowed_image(const dfpsr_image &im) {
+	B200Image<P> r;
+	if (im.data == nullptr) { return r; }
+	r.buffer = std::make_shared<B200Buffer>(im.data, (size_t)im.stride * (size_t)im.height);
+	r.width = im.width; r.height = im.height; r.stride = im.stride; r.packOrder = (PackOrderIndex)im.packOrder;
+	return r;
+}
+inline ImageRgbaU8 spriteWorld_getDiffuseBuffer(SpriteWorld &world) { dfpsr_image im{}; b200_check(dfpsr_sprite_world_get_buffers(b200_world(world, "spriteWorld_getDiffuseBuffer"), &im, nullptr, nullptr, nullptr)); return b200_borrowed_image<uint32_t>(im); }
+inline ImageRgbaU8 spriteWorld_getNormalBuffer(SpriteWorld &world) { dfpsr_image im{}; b200_check(dfpsr_sprite_world_get_buffers(b200_world(world, "spriteWorld_getNormalBuffer"), nullptr, &im, nullptr, nullptr)); return b200_borrowed_image<uint32_t>(im); }
+inline ImageRgbaU8 spriteWorld_getLightBuffer(SpriteWorld &world) { dfpsr_image im{}; b200_check(dfpsr_sprite_world_get_buffers(b200_world(world, "spriteWorld_getLightBuffer"), nullptr, nullptr, &im, nullptr)); return b200_borrowed_image<uint32_t>(im); }
+inline ImageF32 spriteWorld_getHeightBuffer(SpriteWorld &world) { dfpsr_image im{}; b200_check(dfpsr_sprite_world_get_buffers(b200_world(world, "spriteWorld_getHeightBuffer"), nullptr, nullptr, nullptr, &im)); return b200_borrowed_image<float>(im); }
 
 // ---------------------------------------------------------------- filters (ref: api/filterAPI.h:41-79)
 inline ImageRgbaU8 filter_resize(const ImageRgbaU8 &source, Sampler interpolation, int32_t newWidth, int32_t newHeight) {

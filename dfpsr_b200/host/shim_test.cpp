@@ -21,7 +21,66 @@ template <typename T> static std::vector<T> readArray(FILE *f, size_t count) {
 	return v;
 }
 
+// shim_test --sprites <assets.bin> <out.bin>: a small Sandbox session through spriteWorld_* (ref: SDK/sandbox/sandbox.cpp:336-353, :366-493):
+// one sprite type and one model type from the file, a grid of passive sprites, two lights, a temporary sprite, two frames.
+struct SpriteHeader { int32_t atlasWidth, atlasHeight, frameRows, centerX, centerY, pointCount, polygonCount, width, height; float minBound[3], maxBound[3]; };
+static int spriteSession(const char *inPath, const char *outPath) {
+	FILE *f = std::fopen(inPath, "rb");
+	ASSERT(f != nullptr);
+	SpriteHeader h;
+	ASSERT(std::fread(&h, sizeof(h), 1, f) == 1);
+	std::vector<uint32_t> atlas = readArray<uint32_t>(f, (size_t)h.atlasWidth * h.atlasHeight);
+	std::vector<float> points = readArray<float>(f, (size_t)h.pointCount * 3);
+	std::vector<dfpsr_polygon> polygons = readArray<dfpsr_polygon>(f, (size_t)h.polygonCount);
+	std::fclose(f);
+	b200_init(0);
+	SpriteConfig config;
+	config.centerX = h.centerX; config.centerY = h.centerY; config.frameRows = h.frameRows; config.propertyColumns = 3;
+	config.minBound = FVector3D(h.minBound[0], h.minBound[1], h.minBound[2]); config.maxBound = FVector3D(h.maxBound[0], h.maxBound[1], h.maxBound[2]);
+	const int32_t spriteType = spriteWorld_createSpriteType(atlas.data(), h.atlasWidth, h.atlasHeight, h.atlasWidth * 4, config);
+	ASSERT(spriteType == spriteWorld_getSpriteTypeCount() - 1);
+	Model visible = model_create();
+	const int32_t part = model_addEmptyPart(visible, "part");
+	for (int32_t i = 0; i < h.pointCount; i++) { model_addPoint(visible, FVector3D(points[3 * i], points[3 * i + 1], points[3 * i + 2])); }
+	for (int32_t i = 0; i < h.polygonCount; i++) {
+		const dfpsr_polygon &p = polygons[(size_t)i];
+		const int32_t index = p.pointIndices[3] < 0 ? model_addTriangle(visible, part, p.pointIndices[0], p.pointIndices[1], p.pointIndices[2]) : model_addQuad(visible, part, p.pointIndices[0], p.pointIndices[1], p.pointIndices[2], p.pointIndices[3]);
+		for (int v = 0; v < 4; v++) { model_setVertexColor(visible, part, index, v, FVector4D(p.colors[v][0], p.colors[v][1], p.colors[v][2], p.colors[v][3])); }
+	}
+	const int32_t modelType = spriteWorld_createModelType(visible, visible);
+	SpriteWorld world = spriteWorld_create(OrthoSystem(-0.6f, 64), 64);
+	SpriteWorld none;
+	ASSERT_THROWS(spriteWorld_clearTemporary(none), "null");
+	ASSERT_THROWS(spriteWorld_addBackgroundSprite(world, SpriteInstance(1000000, 0, IVector3D(), false)), "out of bound");
+	for (int32_t x = -3; x <= 3; x++) {
+		for (int32_t z = -3; z <= 3; z++) { spriteWorld_addBackgroundSprite(world, SpriteInstance(spriteType, (x + z + 16) % 8, IVector3D(x * ortho_miniUnitsPerTile, 0, z * ortho_miniUnitsPerTile), true)); }
+	}
+	spriteWorld_addBackgroundModel(world, ModelInstance(modelType, Transform3D(FVector3D(0.5f, 0.0f, -0.5f), FMatrix3x3())));
+	ImageRgbaU8 color = image_create_RgbaU8(h.width, h.height);
+	std::vector<uint32_t> frames((size_t)h.width * h.height * 2);
+	for (int frame = 0; frame < 2; frame++) {
+		spriteWorld_clearTemporary(world);
+		spriteWorld_createTemporary_directedLight(world, FVector3D(1.0f, -1.0f, 0.0f), 0.1f, ColorRgbaI32(255, 255, 255, 255));
+		spriteWorld_createTemporary_pointLight(world, FVector3D(0.5f, 1.5f, 0.5f), 4.0f, 1.0f, ColorRgbaI32(255, 200, 150, 255), true);
+		spriteWorld_addTemporarySprite(world, SpriteInstance(spriteType, frame, IVector3D(300 + 200 * frame, 256, -100), true));
+		if (frame == 1) { spriteWorld_moveCameraInPixels(world, IVector2D(12, -7)); }
+		spriteWorld_draw(world, color);
+		image_download(color, frames.data() + (size_t)frame * h.width * h.height, h.width * 4);
+	}
+	ASSERT(image_getWidth(spriteWorld_getHeightBuffer(world)) == h.width && image_exists(spriteWorld_getDiffuseBuffer(world)));
+	const IVector3D ground = spriteWorld_findGroundAtPixel(world, color, IVector2D(10, 20)), camera = spriteWorld_getCameraLocation(world);
+	FILE *out = std::fopen(outPath, "wb");
+	ASSERT(out != nullptr);
+	const int32_t tail[8] = {ground.x, ground.y, ground.z, camera.x, camera.y, camera.z, spriteType, modelType};
+	std::fwrite(frames.data(), 4, frames.size(), out);
+	std::fwrite(tail, 4, 8, out);
+	std::fclose(out);
+	std::printf("shim_test sprites ok: %dx%d\n", h.width, h.height);
+	return 0;
+}
+
 int main(int argc, char **argv) {
+	if (argc == 4 && std::string(argv[1]) == "--sprites") { return spriteSession(argv[2], argv[3]); }
 	if (argc < 3) { std::fprintf(stderr, "usage: shim_test scene.bin out.bin\n"); return 2; }
 	FILE *f = std::fopen(argv[1], "rb");
 	ASSERT(f != nullptr);

@@ -71,3 +71,46 @@ def test_shim_frame_matches_oracle(cuda, oracle, tmp_path, kind):
     assert n > 20
     assert np.array_equal(got_d, ed.view(np.uint32)), "depth"
     assert np.array_equal(got_c, ec), "colour"
+
+
+@pytest.mark.gpu
+def test_shim_sprite_world_session(tmp_path, oracle):
+    """spriteWorld_* through the C++ shim == the host planner replayed with the oracle (same calls through ctypes)."""
+    import sprite_world_scene as sws
+    from dfpsr_b200 import lib
+    assets = sws.build_assets()
+    sprite, model = assets["sprites"][1], assets["models"][0]
+    w, h = 300, 220
+    atlas = np.ascontiguousarray(sprite["atlas"])
+    header = struct.pack("<9i6f", atlas.shape[1], atlas.shape[0], sprite["frames"], sprite["center"][0], sprite["center"][1], len(model["points"]), len(model["polygons"]), w, h,
+                         *[float(v) for v in sprite["min"]], *[float(v) for v in sprite["max"]])
+    with open(tmp_path / "assets.bin", "wb") as f:
+        f.write(header + atlas.tobytes() + np.ascontiguousarray(model["points"], np.float32).tobytes() + np.ascontiguousarray(model["polygons"]).tobytes())
+    result = subprocess.run([EXE, "--sprites", str(tmp_path / "assets.bin"), str(tmp_path / "out.bin")], capture_output=True, text=True)
+    assert result.returncode == 0, result.stdout + result.stderr
+    raw = np.fromfile(tmp_path / "out.bin", np.uint32)
+    frames, tail = raw[:2 * w * h].reshape(2, h, w), raw[2 * w * h:].view(np.int32)
+    # the same session through the C ABI's host planner + the oracle
+    handle = lib.load()
+    local = {"sprites": [dict(sprite, points=None, indices=None)], "models": [dict(model, shadow_points=model["points"], shadow_polygons=model["polygons"])]}
+    pw = sws.ProductWorld(handle, lib.check, local)  # OrthoSystem(-0.6, 64), shadow resolution 64: what the C++ program uses
+    for x in range(-3, 4):
+        for z in range(-3, 4):
+            pw.apply(("bg_sprite", 0, (x + z + 16) % 8, (x * 1024, 0, z * 1024), 1))
+    pw.apply(("bg_model", 0, (0.5, 0.0, -0.5), ((1, 0, 0), (0, 1, 0), (0, 0, 1))))
+    ex = sws.OracleExecutor(oracle, pw)
+    for frame in range(2):
+        pw.apply(("clear_temporary",))
+        pw.apply(("directed", (1.0, -1.0, 0.0), 0.1, (255, 255, 255)))
+        pw.apply(("point", (0.5, 1.5, 0.5), 4.0, 1.0, (255, 200, 150), 1))
+        pw.apply(("tmp_sprite", 0, frame, (300 + 200 * frame, 256, -100), 1))
+        if frame == 1:
+            pw.apply(("move_camera", 12, -7))
+        ops, count = C.POINTER(abi.SpriteWorldOp)(), C.c_int32()
+        lib.check(handle.dfpsr_sprite_world_plan_frame(pw.world, w, h, C.byref(ops), C.byref(count)))
+        expected = ex.frame(ops, count.value, w, h, 0)
+        assert np.array_equal(frames[frame], expected["color"]), frame
+        assert (frames[frame] != 0).mean() > 0.5
+    location, _ground, _index = pw.camera_state(w, h)
+    assert list(tail[3:6]) == [int(v) for v in location]
+    pw.close()

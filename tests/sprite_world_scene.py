@@ -183,7 +183,7 @@ def _i3(values):
 
 # ------------------------------------------------------------------------------------------------ reference back end
 
-def run_reference(ref, assets, script, folder):
+def run_reference(ref, assets, script, folder, shadow_res=SHADOW_RES, keep_frames=True, timing=None):
     """Returns one dict of buffers per draw."""
     lib = ref.lib
     sprite_ids, model_ids = [], []
@@ -193,7 +193,7 @@ def run_reference(ref, assets, script, folder):
     for m in assets["models"]:
         dense = lib.ref_dense_model_create(ref.model(m["points"], m["polygons"]))
         model_ids.append(lib.ref_model_type_create(dense, ref.model(m["shadow_points"], m["shadow_polygons"])))
-    world = lib.ref_world_create(TILT, PIXELS_PER_TILE, SHADOW_RES)
+    world = lib.ref_world_create(TILT, PIXELS_PER_TILE, shadow_res)
     frames = []
     for action in script:
         kind = action[0]
@@ -224,7 +224,12 @@ def run_reference(ref, assets, script, folder):
         elif kind == "draw":
             w, h = action[1], action[2]
             colour = ref.rgba(shape=(h, w))
+            t0 = lib.ref_time_seconds()
             lib.ref_world_draw(world, colour)
+            if timing is not None:
+                timing.append(lib.ref_time_seconds() - t0)
+            if not keep_frames:
+                continue
             d, n, l, hgt = np.zeros((h, w), np.uint32), np.zeros((h, w), np.uint32), np.zeros((h, w), np.uint32), np.zeros((h, w), F)
             lib.ref_world_read_buffers(world, _ptr(d), _ptr(n), _ptr(l), _ptr(hgt))
             location = np.zeros(3, np.int32)
@@ -240,7 +245,7 @@ def run_reference(ref, assets, script, folder):
 class ProductWorld:
     """Creates the types and the world through the C ABI (host only) and applies the non-draw actions of the script."""
 
-    def __init__(self, lib_handle, check, assets):
+    def __init__(self, lib_handle, check, assets, shadow_res=SHADOW_RES):
         self.h, self.check = lib_handle, check
         self.assets = assets
         self.sprite_ids, self.model_ids, self.dense = [], [], []
@@ -269,7 +274,7 @@ class ProductWorld:
         self.ortho = abi.OrthoSystem()
         check(h.dfpsr_ortho_system_create(C.byref(self.ortho), TILT, PIXELS_PER_TILE))
         self.world = C.c_void_p()
-        check(h.dfpsr_sprite_world_create(C.byref(self.world), C.byref(self.ortho), SHADOW_RES))
+        check(h.dfpsr_sprite_world_create(C.byref(self.world), C.byref(self.ortho), shadow_res))
         self.directed, self.points = [], []
 
     def close(self):
@@ -563,3 +568,36 @@ def dense_cuda(lib_handle, lib, assets, case):
 def frame_hashes_dense(result):
     return {"height": sha(result["height"]), "diffuse": sha(result["diffuse"]), "normal": sha(result["normal"]), "rect": [int(v) for v in result["rect"]],
             "touched": float((result["diffuse"] != 0).mean())}
+
+
+# ------------------------------------------------------------------------------------------------ BASELINE config 2 through the sprite world
+
+def sandbox_script(width=800, height=600, lights=16, frames=6, seed=31):
+    """An 800x600 Sandbox session in the spirit of SDK/sandbox/sandbox.cpp:336-353, :366-493: a tiled floor with objects, one directed light,
+    `lights` shadow-casting point lights on a grid and two moving temporary sprites; the camera pans every other frame."""
+    rng = np.random.default_rng(seed)
+    s = []
+    for gx in range(-12, 13):
+        for gz in range(-12, 13):
+            s.append(("bg_sprite", 0, 0, (gx * MINI, 0, gz * MINI), 0))
+            r = rng.random()
+            if r < 0.2:
+                s.append(("bg_sprite", 1, int(rng.integers(0, 8)), (gx * MINI + int(rng.integers(-300, 300)), 0, gz * MINI + int(rng.integers(-300, 300))), 1))
+            elif r < 0.35:
+                s.append(("bg_sprite", 2, int(rng.integers(0, 8)), (gx * MINI + int(rng.integers(-400, 400)), 0, gz * MINI + int(rng.integers(-400, 400))), 1))
+    for k in range(6):
+        s.append(("bg_model", k % 2, (F(rng.random() * 10 - 5), F(0.0), F(rng.random() * 10 - 5)), rotation_y(rng.random() * 6.28)))
+    grid = int(np.ceil(np.sqrt(lights)))
+    for frame in range(frames):
+        s.append(("clear_temporary",))
+        s.append(("directed", (1.0, -1.0, 0.0), 0.1, (255, 255, 255)))
+        for i in range(lights):
+            gx, gz = i % grid, i // grid
+            colour = (int(90 + 40 * (i % 4)), int(255 - 30 * (i % 5)), int(120 + 25 * (i % 6)))
+            s.append(("point", (F(-4.5 + 9.0 * (gx + 0.5) / grid), F(1.0 + 0.1 * (i % 3)), F(-4.5 + 9.0 * (gz + 0.5) / grid)), 4.0, 1.0, colour, 1))
+        s.append(("tmp_sprite", 2, frame % 8, (500 + 150 * frame, 200, -300), 1))
+        s.append(("tmp_sprite", 1, (frame + 3) % 8, (-1200, 0, 900 - 100 * frame), 1))
+        if frame % 2 == 1:
+            s.append(("move_camera", 8, -5))
+        s.append(("draw", width, height))
+    return s

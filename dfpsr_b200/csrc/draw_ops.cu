@@ -1,0 +1,215 @@
+// draw_ops.cu — the 2D draw calls that touch the same device images around the hot path, on sm_100a:
+//   draw_rectangle (RgbaU8 / F32)                   ref: api/drawAPI.cpp:72-174
+//   draw_line (RgbaU8 / F32)                        ref: api/drawAPI.cpp:176-310
+//   draw_alphaFilter / draw_maxAlpha / draw_alphaClip / draw_silhouette   ref: api/drawAPI.cpp:636-744, :926-960
+// They exist so that GUI overlays, debug wireframes (api/rendererAPI.cpp:374-399) and sprite tools can draw into device images
+// without a device -> host -> device round trip. All integer arithmetic, bit-exact; one thread per pixel (per line step).
+#include "common.cuh"
+
+#include <algorithm>
+#include <utility>
+
+namespace dfpsr {
+namespace {
+
+struct Img { uint8_t *data; int32_t width, height, stride, packOrder; };
+inline Img img_of(const dfpsr_image *im) {
+	Img r;
+	if (im == nullptr) { r.data = nullptr; r.width = r.height = r.stride = r.packOrder = 0; return r; }
+	r.data = (uint8_t *)im->data; r.width = im->width; r.height = im->height; r.stride = im->stride; r.packOrder = im->packOrder;
+	return r;
+}
+inline bool exists(const dfpsr_image *im) { return im != nullptr && im->data != nullptr; }
+__device__ __forceinline__ uint32_t *px_u32(const Img &im, int32_t x, int32_t y) { return (uint32_t *)(im.data + (size_t)y * (size_t)im.stride) + x; }
+__device__ __forceinline__ uint8_t *px_u8(const Img &im, int32_t x, int32_t y) { return im.data + (size_t)y * (size_t)im.stride + x; }
+
+struct Intersection { int32_t tx, ty, sx, sy, w, h; };
+// ref: api/drawAPI.cpp:330-385 ImageIntersection
+bool intersect(const Img &target, const Img &source, int32_t left, int32_t top, Intersection &out) {
+	const int32_t x0 = left > 0 ? left : 0, y0 = top > 0 ? top : 0;
+	const int64_t r = (int64_t)left + source.width, b = (int64_t)top + source.height;
+	const int32_t x1 = r < target.width ? (int32_t)r : target.width, y1 = b < target.height ? (int32_t)b : target.height;
+	if (x1 <= x0 || y1 <= y0) { return false; }
+	out.tx = x0; out.ty = y0; out.sx = x0 - left; out.sy = y0 - top; out.w = x1 - x0; out.h = y1 - y0;
+	return true;
+}
+
+// ref: api/drawAPI.cpp:46-54
+__device__ __forceinline__ uint32_t byte_mul(uint32_t a, uint32_t b) { return (a * b * 65793u + 8388608u) >> 24; }
+
+__device__ __forceinline__ void unpack(uint32_t c, uint32_t shifts, uint32_t *v) {
+	v[0] = (c >> (shifts & 31u)) & 255u; v[1] = (c >> ((shifts >> 8) & 31u)) & 255u; v[2] = (c >> ((shifts >> 16) & 31u)) & 255u; v[3] = (c >> ((shifts >> 24) & 31u)) & 255u;
+}
+
+__global__ void __launch_bounds__(256) rectangle_kernel(Img target, int32_t left, int32_t top, int32_t width, int32_t height, uint32_t value) {
+	const int32_t x = (int32_t)(blockIdx.x * 32u + (threadIdx.x & 31u)), y = (int32_t)(blockIdx.y * 8u + (threadIdx.x >> 5));
+	if (x < width && y < height) { *px_u32(target, left + x, top + y) = value; }
+}
+
+// ref: api/drawAPI.cpp:176-283 drawLineSuper. Step j along the major axis writes (major0 + j, minor0 + sign * k(j)) where the reference's
+// running error (error += tilt; if error >= maxError { minor += sign; error -= 2 * maxError }) has the closed form
+// k(j) = floor((j * tilt + maxError) / (2 * maxError)).
+struct LineParams { int32_t major0, minor0, sign, steps, firstStep; int32_t majorIsY; long long tilt, maxError; };
+__global__ void __launch_bounds__(256) line_kernel(Img target, LineParams p, uint32_t value) {
+	const int32_t i = (int32_t)(blockIdx.x * blockDim.x + threadIdx.x);
+	if (i >= p.steps) { return; }
+	const long long j = (long long)p.firstStep + i;
+	const long long k = p.maxError > 0 ? (j * p.tilt + p.maxError) / (2 * p.maxError) : 0;
+	const long long major = (long long)p.major0 + j, minor = (long long)p.minor0 + p.sign * k;
+	const long long x = p.majorIsY ? minor : major, y = p.majorIsY ? major : minor;
+	if (x >= 0 && x < target.width && y >= 0 && y < target.height) { *px_u32(target, (int32_t)x, (int32_t)y) = value; }
+}
+
+enum { OP_ALPHA_FILTER = 0, OP_MAX_ALPHA = 1, OP_MAX_ALPHA_OFFSET = 2, OP_ALPHA_CLIP = 3 };
+template <int OP>
+__global__ void __launch_bounds__(256) image_over_kernel(Img target, Img source, Intersection is, int32_t parameter) {
+	const int32_t x = (int32_t)(blockIdx.x * 32u + (threadIdx.x & 31u)), y = (int32_t)(blockIdx.y * 8u + (threadIdx.x >> 5));
+	if (x >= is.w || y >= is.h) { return; }
+	const uint32_t ts = pack_shifts(target.packOrder), ss = pack_shifts(source.packOrder);
+	uint32_t *tp = px_u32(target, is.tx + x, is.ty + y);
+	uint32_t s[4], t[4];
+	unpack(*px_u32(source, is.sx + x, is.sy + y), ss, s);
+	if (OP == OP_ALPHA_FILTER) { // ref: api/drawAPI.cpp:636-661
+		const uint32_t sourceRatio = s[3];
+		if (sourceRatio == 0u) { return; }
+		if (sourceRatio == 255u) { *tp = pack_rgba_ordered(s[0], s[1], s[2], 255u, ts); return; }
+		unpack(*tp, ts, t);
+		const uint32_t targetRatio = 255u - sourceRatio;
+		// the sums are stored into bytes by the reference: keep the low 8 bits
+		*tp = pack_rgba_ordered((byte_mul(t[0], targetRatio) + byte_mul(s[0], sourceRatio)) & 255u, (byte_mul(t[1], targetRatio) + byte_mul(s[1], sourceRatio)) & 255u,
+		                        (byte_mul(t[2], targetRatio) + byte_mul(s[2], sourceRatio)) & 255u, (byte_mul(t[3], targetRatio) + sourceRatio) & 255u, ts);
+	} else if (OP == OP_MAX_ALPHA) { // ref: api/drawAPI.cpp:663-679
+		unpack(*tp, ts, t);
+		if ((int32_t)s[3] > (int32_t)t[3]) { *tp = pack_rgba_ordered(s[0], s[1], s[2], s[3], ts); }
+	} else if (OP == OP_MAX_ALPHA_OFFSET) { // ref: api/drawAPI.cpp:680-697
+		int32_t sourceAlpha = (int32_t)s[3];
+		if (sourceAlpha > 0) {
+			sourceAlpha += parameter;
+			unpack(*tp, ts, t);
+			if (sourceAlpha > (int32_t)t[3]) {
+				if (sourceAlpha < 0) { sourceAlpha = 0; }
+				if (sourceAlpha > 255) { sourceAlpha = 255; }
+				*tp = pack_rgba_ordered(s[0], s[1], s[2], (uint32_t)sourceAlpha, ts);
+			}
+		}
+	} else { // OP_ALPHA_CLIP, ref: api/drawAPI.cpp:700-715
+		if ((int32_t)s[3] > parameter) { *tp = pack_rgba_ordered(s[0], s[1], s[2], 255u, ts); }
+	}
+}
+
+// ref: api/drawAPI.cpp:717-757 drawSilhouette_template / imageImpl_drawSilhouette
+__global__ void __launch_bounds__(256) silhouette_kernel(Img target, Img source, Intersection is, uint32_t red, uint32_t green, uint32_t blue, uint32_t alpha, int fullAlpha) {
+	const int32_t x = (int32_t)(blockIdx.x * 32u + (threadIdx.x & 31u)), y = (int32_t)(blockIdx.y * 8u + (threadIdx.x >> 5));
+	if (x >= is.w || y >= is.h) { return; }
+	const uint32_t ts = pack_shifts(target.packOrder);
+	uint32_t sourceRatio = *px_u8(source, is.sx + x, is.sy + y);
+	if (!fullAlpha) { sourceRatio = byte_mul(sourceRatio, alpha); }
+	if (sourceRatio == 0u) { return; }
+	uint32_t *tp = px_u32(target, is.tx + x, is.ty + y);
+	if (sourceRatio == 255u) { *tp = pack_rgba_ordered(red, green, blue, 255u, ts); return; }
+	uint32_t t[4];
+	unpack(*tp, ts, t);
+	const uint32_t targetRatio = 255u - sourceRatio;
+	*tp = pack_rgba_ordered((byte_mul(t[0], targetRatio) + byte_mul(red, sourceRatio)) & 255u, (byte_mul(t[1], targetRatio) + byte_mul(green, sourceRatio)) & 255u,
+	                        (byte_mul(t[2], targetRatio) + byte_mul(blue, sourceRatio)) & 255u, (byte_mul(t[3], targetRatio) + sourceRatio) & 255u, ts);
+}
+
+inline dim3 grid2d(int32_t w, int32_t h) { return dim3((unsigned)((w + 31) / 32), (unsigned)((h + 7) / 8)); }
+inline uint32_t clamp255(int32_t v) { return (uint32_t)(v < 0 ? 0 : (v > 255 ? 255 : v)); }
+
+int rectangle(const dfpsr_image *image, int32_t left, int32_t top, int32_t width, int32_t height, uint32_t value, cudaStream_t stream) {
+	if (!exists(image)) { return 0; }
+	const Img t = img_of(image);
+	// ref: api/drawAPI.cpp:73-77 — the rectangle is clipped to the image
+	const int64_t right = (int64_t)left + width, bottom = (int64_t)top + height;
+	const int32_t l = left > 0 ? left : 0, tp = top > 0 ? top : 0;
+	const int32_t r = right < t.width ? (int32_t)right : t.width, b = bottom < t.height ? (int32_t)bottom : t.height;
+	if (r <= l || b <= tp) { return 0; }
+	DFPSR_LAUNCH(rectangle_kernel, grid2d(r - l, b - tp), 256, 0, stream, t, l, tp, r - l, b - tp, value);
+	return 0;
+}
+
+int line(const dfpsr_image *image, int32_t x1, int32_t y1, int32_t x2, int32_t y2, uint32_t value, cudaStream_t stream) {
+	if (!exists(image)) { return 0; }
+	const Img t = img_of(image);
+	if ((x1 < 0 && x2 < 0) || (y1 < 0 && y2 < 0) || (x1 >= t.width && x2 >= t.width) || (y1 >= t.height && y2 >= t.height)) { return 0; }
+	LineParams p;
+	const int64_t dx = (int64_t)x2 - x1, dy = (int64_t)y2 - y1;
+	const int64_t adx = dx < 0 ? -dx : dx, ady = dy < 0 ? -dy : dy;
+	int64_t length;
+	if (ady >= adx) { // vertical, or closer to vertical: walk down (ref: :203-236); a horizontal line has ady == 0 == adx only when both are 0
+		if (y2 < y1) { std::swap(x1, x2); std::swap(y1, y2); }
+		p.majorIsY = 1; p.major0 = y1; p.minor0 = x1; p.sign = x2 > x1 ? 1 : -1; p.tilt = 2 * adx; p.maxError = ady; length = ady;
+	} else { // closer to horizontal: walk right (ref: :237-276)
+		if (x2 < x1) { std::swap(x1, x2); std::swap(y1, y2); }
+		p.majorIsY = 0; p.major0 = x1; p.minor0 = y1; p.sign = y2 > y1 ? 1 : -1; p.tilt = 2 * ady; p.maxError = adx; length = adx;
+	}
+	// only the steps whose major coordinate lies inside the image can write
+	const int64_t limit = p.majorIsY ? t.height : t.width;
+	const int64_t first = p.major0 < 0 ? -(int64_t)p.major0 : 0, last = std::min<int64_t>(length, limit - 1 - p.major0);
+	if (last < first) { return 0; }
+	p.firstStep = (int32_t)first; p.steps = (int32_t)(last - first + 1);
+	DFPSR_LAUNCH(line_kernel, (p.steps + 255) / 256, 256, 0, stream, t, p, value);
+	return 0;
+}
+
+uint32_t saturate_and_pack(const dfpsr_image *image, const int32_t rgba[4]) { // ref: api/imageAPI.cpp image_saturateAndPack
+	const uint32_t shifts = pack_shifts(image->packOrder);
+	return (clamp255(rgba[0]) << (shifts & 31u)) | (clamp255(rgba[1]) << ((shifts >> 8) & 31u)) | (clamp255(rgba[2]) << ((shifts >> 16) & 31u)) | (clamp255(rgba[3]) << ((shifts >> 24) & 31u));
+}
+
+} // namespace
+} // namespace dfpsr
+
+using namespace dfpsr;
+
+extern "C" {
+
+int dfpsr_draw_rectangle_rgba(const dfpsr_image *image, int32_t left, int32_t top, int32_t width, int32_t height, const int32_t colorRgba[4], void *stream) {
+	if (!exists(image)) { return 0; }
+	DFPSR_REQUIRE(colorRgba != nullptr, "draw_rectangle: null colour");
+	return rectangle(image, left, top, width, height, saturate_and_pack(image, colorRgba), as_stream(stream));
+}
+int dfpsr_draw_rectangle_f32(const dfpsr_image *image, int32_t left, int32_t top, int32_t width, int32_t height, float value, void *stream) {
+	uint32_t bits;
+	memcpy(&bits, &value, 4);
+	return rectangle(image, left, top, width, height, bits, as_stream(stream));
+}
+int dfpsr_draw_line_rgba(const dfpsr_image *image, int32_t x1, int32_t y1, int32_t x2, int32_t y2, const int32_t colorRgba[4], void *stream) {
+	if (!exists(image)) { return 0; }
+	DFPSR_REQUIRE(colorRgba != nullptr, "draw_line: null colour");
+	return line(image, x1, y1, x2, y2, saturate_and_pack(image, colorRgba), as_stream(stream));
+}
+int dfpsr_draw_line_f32(const dfpsr_image *image, int32_t x1, int32_t y1, int32_t x2, int32_t y2, float value, void *stream) {
+	uint32_t bits;
+	memcpy(&bits, &value, 4);
+	return line(image, x1, y1, x2, y2, bits, as_stream(stream));
+}
+
+#define IMAGE_OVER(OP, parameter)                                                                                         \
+	if (!exists(target) || !exists(source)) { return 0; }                                                                 \
+	const Img t = img_of(target), s = img_of(source);                                                                     \
+	Intersection is;                                                                                                      \
+	if (!intersect(t, s, left, top, is)) { return 0; }                                                                    \
+	DFPSR_LAUNCH(image_over_kernel<OP>, grid2d(is.w, is.h), 256, 0, as_stream(stream), t, s, is, (parameter));            \
+	return 0;
+
+int dfpsr_draw_alpha_filter(const dfpsr_image *target, const dfpsr_image *source, int32_t left, int32_t top, void *stream) { IMAGE_OVER(OP_ALPHA_FILTER, 0) }
+int dfpsr_draw_max_alpha(const dfpsr_image *target, const dfpsr_image *source, int32_t left, int32_t top, int32_t sourceAlphaOffset, void *stream) {
+	if (sourceAlphaOffset == 0) { IMAGE_OVER(OP_MAX_ALPHA, 0) }
+	IMAGE_OVER(OP_MAX_ALPHA_OFFSET, sourceAlphaOffset)
+}
+int dfpsr_draw_alpha_clip(const dfpsr_image *target, const dfpsr_image *source, int32_t left, int32_t top, int32_t threshold, void *stream) { IMAGE_OVER(OP_ALPHA_CLIP, threshold) }
+
+int dfpsr_draw_silhouette(const dfpsr_image *target, const dfpsr_image *silhouetteU8, const int32_t colorRgba[4], int32_t left, int32_t top, void *stream) {
+	if (!exists(target) || !exists(silhouetteU8)) { return 0; }
+	DFPSR_REQUIRE(colorRgba != nullptr, "draw_silhouette: null colour");
+	if (colorRgba[3] <= 0) { return 0; } // ref: api/drawAPI.cpp:748
+	const Img t = img_of(target), s = img_of(silhouetteU8);
+	Intersection is;
+	if (!intersect(t, s, left, top, is)) { return 0; }
+	DFPSR_LAUNCH(silhouette_kernel, grid2d(is.w, is.h), 256, 0, as_stream(stream), t, s, is, clamp255(colorRgba[0]), clamp255(colorRgba[1]), clamp255(colorRgba[2]), clamp255(colorRgba[3]), colorRgba[3] >= 255 ? 1 : 0);
+	return 0;
+}
+
+} // extern "C"

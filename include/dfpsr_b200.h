@@ -251,6 +251,19 @@ int dfpsr_draw_copy_f32(const dfpsr_image *target, const dfpsr_image *source, in
  * (targetA/sourceA and targetB/sourceB may be NULL together). */
 int dfpsr_draw_higher(const dfpsr_image *targetHeight, const dfpsr_image *sourceHeight, const dfpsr_image *targetA, const dfpsr_image *sourceA, const dfpsr_image *targetB, const dfpsr_image *sourceB, int32_t left, int32_t top, float sourceHeightOffset, void *stream);
 
+/* The remaining draw calls on RGBA8 / F32 device images, so that overlays and debug drawing stay on the device.
+ * ref: api/drawAPI.cpp:72-174 draw_rectangle (clipped; colour saturated and packed in the image's pack order), :176-310 draw_line
+ * (the reference's error-accumulating line, every step evaluated in closed form), :636-661 draw_alphaFilter, :663-698 draw_maxAlpha,
+ * :700-715 draw_alphaClip, :717-757 draw_silhouette (source = 8-bit image: 1 byte per pixel, stride in bytes). */
+int dfpsr_draw_rectangle_rgba(const dfpsr_image *image, int32_t left, int32_t top, int32_t width, int32_t height, const int32_t colorRgba[4], void *stream);
+int dfpsr_draw_rectangle_f32(const dfpsr_image *image, int32_t left, int32_t top, int32_t width, int32_t height, float value, void *stream);
+int dfpsr_draw_line_rgba(const dfpsr_image *image, int32_t x1, int32_t y1, int32_t x2, int32_t y2, const int32_t colorRgba[4], void *stream);
+int dfpsr_draw_line_f32(const dfpsr_image *image, int32_t x1, int32_t y1, int32_t x2, int32_t y2, float value, void *stream);
+int dfpsr_draw_alpha_filter(const dfpsr_image *target, const dfpsr_image *source, int32_t left, int32_t top, void *stream);
+int dfpsr_draw_max_alpha(const dfpsr_image *target, const dfpsr_image *source, int32_t left, int32_t top, int32_t sourceAlphaOffset, void *stream);
+int dfpsr_draw_alpha_clip(const dfpsr_image *target, const dfpsr_image *source, int32_t left, int32_t top, int32_t threshold, void *stream);
+int dfpsr_draw_silhouette(const dfpsr_image *target, const dfpsr_image *silhouetteU8, const int32_t colorRgba[4], int32_t left, int32_t top, void *stream);
+
 /* One sprite placement for the batched compositor: sources live in an atlas on the device. */
 typedef struct dfpsr_sprite_draw {
 	dfpsr_image sourceHeight, sourceA, sourceB;

@@ -1265,6 +1265,138 @@ void orc_draw_higher(const dfpsr_image *targetHeight, const dfpsr_image *sourceH
 static v3 mat3_transform(const dfpsr_matrix3x3 *m, v3 p) { return mat_transform(m->xAxis, m->yAxis, m->zAxis, p); }
 static v3 mat3_transform_transposed(const dfpsr_matrix3x3 *m, v3 p) { return mat_transform_transposed(m->xAxis, m->yAxis, m->zAxis, p); }
 
+/* ------------------------------------------------------------------------------------------- remaining 2D draw calls (api/drawAPI.cpp) */
+
+static uint32_t clamp_byte(int32_t v) { return (uint32_t)(v < 0 ? 0 : (v > 255 ? 255 : v)); }
+static uint32_t draw_color(const dfpsr_image *image, const int32_t *c) {
+	return pack_bytes_ordered(clamp_byte(c[0]), clamp_byte(c[1]), clamp_byte(c[2]), clamp_byte(c[3]), image->packOrder);
+}
+static void write_pixel_u32(const dfpsr_image *im, int64_t x, int64_t y, uint32_t value) { /* image_writePixel: out-of-bound writes are ignored */
+	if (x >= 0 && x < im->width && y >= 0 && y < im->height) { *color_px(im, (int32_t)x, (int32_t)y) = value; }
+}
+/* api/drawAPI.cpp:72-88, :152-174 */
+static void rectangle_u32(const dfpsr_image *im, int32_t left, int32_t top, int32_t width, int32_t height, uint32_t value) {
+	if (im == NULL || im->data == NULL) { return; }
+	int64_t right = (int64_t)left + width, bottom = (int64_t)top + height;
+	int32_t l = left > 0 ? left : 0, t = top > 0 ? top : 0;
+	int32_t r = right < im->width ? (int32_t)right : im->width, b = bottom < im->height ? (int32_t)bottom : im->height;
+	for (int32_t y = t; y < b; y++) { for (int32_t x = l; x < r; x++) { *color_px(im, x, y) = value; } }
+}
+void orc_draw_rectangle_rgba(const dfpsr_image *image, int32_t left, int32_t top, int32_t width, int32_t height, const int32_t *colorRgba) {
+	if (image == NULL || image->data == NULL) { return; }
+	rectangle_u32(image, left, top, width, height, draw_color(image, colorRgba));
+}
+void orc_draw_rectangle_f32(const dfpsr_image *image, int32_t left, int32_t top, int32_t width, int32_t height, float value) {
+	uint32_t bits; memcpy(&bits, &value, 4);
+	rectangle_u32(image, left, top, width, height, bits);
+}
+/* api/drawAPI.cpp:176-283 drawLineSuper, with the reference's running error term */
+static void line_u32(const dfpsr_image *im, int32_t x1, int32_t y1, int32_t x2, int32_t y2, uint32_t value) {
+	if (im == NULL || im->data == NULL) { return; }
+	int32_t width = im->width, height = im->height;
+	if ((x1 < 0 && x2 < 0) || (y1 < 0 && y2 < 0) || (x1 >= width && x2 >= width) || (y1 >= height && y2 >= height)) { return; }
+	if (y1 == y2) {
+		int32_t l = x1 < x2 ? x1 : x2, r = x1 > x2 ? x1 : x2;
+		for (int64_t x = l; x <= r; x++) { write_pixel_u32(im, x, y1, value); }
+	} else if (x1 == x2) {
+		int32_t t = y1 < y2 ? y1 : y2, b = y1 > y2 ? y1 : y2;
+		for (int64_t y = t; y <= b; y++) { write_pixel_u32(im, x1, y, value); }
+	} else {
+		int64_t adx = (int64_t)x2 - x1, ady = (int64_t)y2 - y1;
+		if (adx < 0) { adx = -adx; } if (ady < 0) { ady = -ady; }
+		if (ady >= adx) {
+			if (y2 < y1) { int32_t tx = x1, ty = y1; x1 = x2; y1 = y2; x2 = tx; y2 = ty; }
+			int64_t x = x1, y = y1, tilt = adx * 2, maxError = (int64_t)y2 - y1, error = 0, step = x2 > x1 ? 1 : -1;
+			while (y <= y2) {
+				write_pixel_u32(im, x, y, value);
+				error += tilt;
+				if (error >= maxError) { x += step; error -= maxError * 2; }
+				y++;
+			}
+		} else {
+			if (x2 < x1) { int32_t tx = x1, ty = y1; x1 = x2; y1 = y2; x2 = tx; y2 = ty; }
+			int64_t x = x1, y = y1, tilt = ady * 2, maxError = (int64_t)x2 - x1, error = 0, step = y2 > y1 ? 1 : -1;
+			while (x <= x2) {
+				write_pixel_u32(im, x, y, value);
+				error += tilt;
+				if (error >= maxError) { y += step; error -= maxError * 2; }
+				x++;
+			}
+		}
+	}
+}
+void orc_draw_line_rgba(const dfpsr_image *image, int32_t x1, int32_t y1, int32_t x2, int32_t y2, const int32_t *colorRgba) {
+	if (image == NULL || image->data == NULL) { return; }
+	line_u32(image, x1, y1, x2, y2, draw_color(image, colorRgba));
+}
+void orc_draw_line_f32(const dfpsr_image *image, int32_t x1, int32_t y1, int32_t x2, int32_t y2, float value) {
+	uint32_t bits; memcpy(&bits, &value, 4);
+	line_u32(image, x1, y1, x2, y2, bits);
+}
+static uint32_t byte_mul(uint32_t a, uint32_t b) { return (a * b * 65793u + 8388608u) >> 24; } /* api/drawAPI.cpp:46-54 */
+static void unpack_color(uint32_t c, int order, uint32_t *v) { const int *s = packIndex[order]; for (int k = 0; k < 4; k++) { v[k] = (c >> (8 * s[k])) & 255u; } }
+/* api/drawAPI.cpp:636-715: op 0 alphaFilter, 1 maxAlpha (parameter = sourceAlphaOffset), 2 alphaClip (parameter = threshold) */
+static void image_over(const dfpsr_image *target, const dfpsr_image *source, int32_t left, int32_t top, int op, int32_t parameter) {
+	intersection is;
+	if (target == NULL || source == NULL || target->data == NULL || source->data == NULL) { return; }
+	if (!intersect(target, source, left, top, &is)) { return; }
+	for (int32_t y = 0; y < is.h; y++) {
+		for (int32_t x = 0; x < is.w; x++) {
+			uint32_t s[4], t[4];
+			uint32_t *tp = color_px(target, is.tx + x, is.ty + y);
+			unpack_color(*color_px(source, is.sx + x, is.sy + y), source->packOrder, s);
+			unpack_color(*tp, target->packOrder, t);
+			if (op == 0) {
+				uint32_t sr = s[3];
+				if (sr > 0) {
+					if (sr == 255) { *tp = pack_bytes_ordered(s[0], s[1], s[2], 255, target->packOrder); }
+					else {
+						uint32_t tr = 255 - sr;
+						*tp = pack_bytes_ordered((uint8_t)(byte_mul(t[0], tr) + byte_mul(s[0], sr)), (uint8_t)(byte_mul(t[1], tr) + byte_mul(s[1], sr)), (uint8_t)(byte_mul(t[2], tr) + byte_mul(s[2], sr)), (uint8_t)(byte_mul(t[3], tr) + sr), target->packOrder);
+					}
+				}
+			} else if (op == 1) {
+				int32_t sa = (int32_t)s[3];
+				if (parameter == 0) {
+					if (sa > (int32_t)t[3]) { *tp = pack_bytes_ordered(s[0], s[1], s[2], (uint32_t)sa, target->packOrder); }
+				} else if (sa > 0) {
+					sa += parameter;
+					if (sa > (int32_t)t[3]) {
+						if (sa < 0) { sa = 0; } if (sa > 255) { sa = 255; }
+						*tp = pack_bytes_ordered(s[0], s[1], s[2], (uint32_t)sa, target->packOrder);
+					}
+				}
+			} else {
+				if ((int32_t)s[3] > parameter) { *tp = pack_bytes_ordered(s[0], s[1], s[2], 255, target->packOrder); }
+			}
+		}
+	}
+}
+void orc_draw_alpha_filter(const dfpsr_image *target, const dfpsr_image *source, int32_t left, int32_t top) { image_over(target, source, left, top, 0, 0); }
+void orc_draw_max_alpha(const dfpsr_image *target, const dfpsr_image *source, int32_t left, int32_t top, int32_t sourceAlphaOffset) { image_over(target, source, left, top, 1, sourceAlphaOffset); }
+void orc_draw_alpha_clip(const dfpsr_image *target, const dfpsr_image *source, int32_t left, int32_t top, int32_t threshold) { image_over(target, source, left, top, 2, threshold); }
+/* api/drawAPI.cpp:717-757; the silhouette is an 8-bit image (1 byte per pixel) */
+void orc_draw_silhouette(const dfpsr_image *target, const dfpsr_image *silhouetteU8, const int32_t *colorRgba, int32_t left, int32_t top) {
+	intersection is;
+	if (target == NULL || silhouetteU8 == NULL || target->data == NULL || silhouetteU8->data == NULL) { return; }
+	if (colorRgba[3] <= 0) { return; }
+	uint32_t red = clamp_byte(colorRgba[0]), green = clamp_byte(colorRgba[1]), blue = clamp_byte(colorRgba[2]), alpha = clamp_byte(colorRgba[3]);
+	int fullAlpha = colorRgba[3] >= 255;
+	if (!intersect(target, silhouetteU8, left, top, &is)) { return; }
+	for (int32_t y = 0; y < is.h; y++) {
+		for (int32_t x = 0; x < is.w; x++) {
+			uint32_t sr = *((const uint8_t*)silhouetteU8->data + (size_t)(is.sy + y) * silhouetteU8->stride + (is.sx + x));
+			if (!fullAlpha) { sr = byte_mul(sr, alpha); }
+			if (sr == 0) { continue; }
+			uint32_t *tp = color_px(target, is.tx + x, is.ty + y);
+			if (sr == 255) { *tp = pack_bytes_ordered(red, green, blue, 255, target->packOrder); continue; }
+			uint32_t t[4], tr = 255 - sr;
+			unpack_color(*tp, target->packOrder, t);
+			*tp = pack_bytes_ordered((uint8_t)(byte_mul(t[0], tr) + byte_mul(red, sr)), (uint8_t)(byte_mul(t[1], tr) + byte_mul(green, sr)), (uint8_t)(byte_mul(t[2], tr) + byte_mul(blue, sr)), (uint8_t)(byte_mul(t[3], tr) + sr), target->packOrder);
+		}
+	}
+}
+
 /* ------------------------------------------------------------------------------------------- Sandbox dense models and sprite heights */
 
 /* The reference converts with cvttss2si; (uint32_t)float goes through the 64-bit conversion on x86-64. */

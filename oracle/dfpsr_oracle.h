@@ -61,6 +61,16 @@ void orc_draw_copy_rgba(const dfpsr_image *target, const dfpsr_image *source, in
 void orc_draw_copy_f32(const dfpsr_image *target, const dfpsr_image *source, int32_t left, int32_t top);
 void orc_draw_higher(const dfpsr_image *targetHeight, const dfpsr_image *sourceHeight, const dfpsr_image *targetA, const dfpsr_image *sourceA, const dfpsr_image *targetB, const dfpsr_image *sourceB, int32_t left, int32_t top, float offset);
 
+/* The remaining draw calls on RGBA8 / F32 images (api/drawAPI.cpp:72-310, :636-757). */
+void orc_draw_rectangle_rgba(const dfpsr_image *image, int32_t left, int32_t top, int32_t width, int32_t height, const int32_t *colorRgba);
+void orc_draw_rectangle_f32(const dfpsr_image *image, int32_t left, int32_t top, int32_t width, int32_t height, float value);
+void orc_draw_line_rgba(const dfpsr_image *image, int32_t x1, int32_t y1, int32_t x2, int32_t y2, const int32_t *colorRgba);
+void orc_draw_line_f32(const dfpsr_image *image, int32_t x1, int32_t y1, int32_t x2, int32_t y2, float value);
+void orc_draw_alpha_filter(const dfpsr_image *target, const dfpsr_image *source, int32_t left, int32_t top);
+void orc_draw_max_alpha(const dfpsr_image *target, const dfpsr_image *source, int32_t left, int32_t top, int32_t sourceAlphaOffset);
+void orc_draw_alpha_clip(const dfpsr_image *target, const dfpsr_image *source, int32_t left, int32_t top, int32_t threshold);
+void orc_draw_silhouette(const dfpsr_image *target, const dfpsr_image *silhouetteU8, const int32_t *colorRgba, int32_t left, int32_t top);
+
 /* renderDenseModel<HIGH_QUALITY> (SDK/SpriteEngine/spriteAPI.cpp:1243-1327); dirtyRect = {left, top, width, height} or zeros when culled. */
 void orc_dense_model_render(const dfpsr_dense_triangle *triangles, int32_t triangleCount, const float *minBound, const float *maxBound, const dfpsr_ortho_camera *view,
                             const dfpsr_image *height, const dfpsr_image *diffuse, const dfpsr_image *normal, const float *worldOrigin, const dfpsr_transform3d *modelToWorld,

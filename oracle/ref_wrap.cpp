@@ -54,6 +54,7 @@ struct AnyImage {
 	OrderedImageRgbaU8 rgbaOrdered; // only for whole RGBA-order images
 	ImageF32 f32;
 	AlignedImageF32 f32Aligned; // only for whole images
+	ImageU8 u8;                 // kind 3
 };
 
 std::vector<AnyImage> g_images;
@@ -478,6 +479,26 @@ void ref_filter_map(int target, int op, const int32_t *params, int source, int s
 void ref_filter_block_magnify(int target, int source, int pixelWidth, int pixelHeight) {
 	filter_blockMagnify(g_images[target].rgba, g_images[source].rgba, pixelWidth, pixelHeight);
 }
+
+// ---- the remaining draw calls (api/drawAPI.h:68-161)
+
+int ref_image_create_u8(int w, int h, const uint8_t *pixels) { // tight rows in
+	ensureStarted();
+	AnyImage img;
+	img.kind = 3;
+	img.u8 = image_create_U8(w, h);
+	for (int y = 0; y < h; y++) { memcpy(image_getSafePointer<uint8_t>(img.u8, y).getUnsafe(), pixels + (size_t)y * w, (size_t)w); }
+	g_images.push_back(img);
+	return (int)g_images.size() - 1;
+}
+void ref_draw_rectangle_rgba(int image, int left, int top, int width, int height, const int32_t *c) { draw_rectangle(g_images[image].rgba, IRect(left, top, width, height), ColorRgbaI32(c[0], c[1], c[2], c[3])); }
+void ref_draw_rectangle_f32(int image, int left, int top, int width, int height, float value) { draw_rectangle(g_images[image].f32, IRect(left, top, width, height), value); }
+void ref_draw_line_rgba(int image, int x1, int y1, int x2, int y2, const int32_t *c) { draw_line(g_images[image].rgba, x1, y1, x2, y2, ColorRgbaI32(c[0], c[1], c[2], c[3])); }
+void ref_draw_line_f32(int image, int x1, int y1, int x2, int y2, float value) { draw_line(g_images[image].f32, x1, y1, x2, y2, value); }
+void ref_draw_alpha_filter(int target, int source, int left, int top) { draw_alphaFilter(g_images[target].rgba, g_images[source].rgba, left, top); }
+void ref_draw_max_alpha(int target, int source, int left, int top, int offset) { draw_maxAlpha(g_images[target].rgba, g_images[source].rgba, left, top, offset); }
+void ref_draw_alpha_clip(int target, int source, int left, int top, int threshold) { draw_alphaClip(g_images[target].rgba, g_images[source].rgba, left, top, threshold); }
+void ref_draw_silhouette(int target, int source, const int32_t *c, int left, int top) { draw_silhouette(g_images[target].rgba, g_images[source].u8, ColorRgbaI32(c[0], c[1], c[2], c[3]), left, top); }
 
 // ---- Sandbox sprite engine (SDK/SpriteEngine/spriteAPI.cpp, orthoAPI.cpp)
 

@@ -25,6 +25,7 @@ import refbind  # noqa: E402
 from dfpsr_b200 import abi, scenes  # noqa: E402
 import sandbox_scene  # noqa: E402
 import sprite_world_scene  # noqa: E402
+import draw_scene  # noqa: E402
 
 
 def sha(a):
@@ -89,6 +90,16 @@ def sandbox(ref):
     return {"sandbox_800x600_16": out}
 
 
+def draw(ref):
+    """The 2D draw call sequences of tests/draw_scene.py through the reference's drawAPI."""
+    cases = []
+    for case in draw_scene.CASES:
+        color, depth = draw_scene.run_reference(ref, draw_scene.build(*case))
+        cases.append({"color_sha256": sha(color), "depth_sha256": sha(depth)})
+        ref.free_all()
+    return {"cases": cases}
+
+
 def sprite_world(ref):
     """The scripted Sandbox session of tests/sprite_world_scene.py through the reference's spriteWorld_* API, plus renderDenseModel alone."""
     import tempfile
@@ -103,9 +114,9 @@ def sprite_world(ref):
 
 if __name__ == "__main__":
     ref = refbind.Ref("scalar")
-    which = sys.argv[1:] or ["raster", "filters", "sandbox", "sprite_world"]
+    which = sys.argv[1:] or ["raster", "filters", "sandbox", "sprite_world", "draw"]
     for name in which:
-        data = {"raster": raster, "filters": filters, "sandbox": sandbox, "sprite_world": sprite_world}[name](ref)
+        data = {"raster": raster, "filters": filters, "sandbox": sandbox, "sprite_world": sprite_world, "draw": draw}[name](ref)
         path = os.path.join(HERE, name + ".json")
         json.dump(data, open(path, "w"), indent=1, sort_keys=True)
         print("wrote", path)

@@ -52,6 +52,11 @@ def load(flavour="scalar"):
         "ref_light_blend": (None, [i, i, i]),
         "ref_filter_resize": (i, [i, i, i, i]), "ref_filter_map": (None, [i, i, p, i, i, i]),
         "ref_filter_block_magnify": (None, [i, i, i, i]),
+        "ref_image_create_u8": (i, [i, i, p]),
+        "ref_draw_rectangle_rgba": (None, [i, i, i, i, i, p]), "ref_draw_rectangle_f32": (None, [i, i, i, i, i, f]),
+        "ref_draw_line_rgba": (None, [i, i, i, i, i, p]), "ref_draw_line_f32": (None, [i, i, i, i, i, f]),
+        "ref_draw_alpha_filter": (None, [i, i, i, i]), "ref_draw_max_alpha": (None, [i, i, i, i, i]), "ref_draw_alpha_clip": (None, [i, i, i, i, i]),
+        "ref_draw_silhouette": (None, [i, i, p, i, i]),
         "ref_ortho_system": (None, [f, i, C.POINTER(abi.OrthoSystem)]),
         "ref_dense_model_create": (i, [i]), "ref_dense_model_triangles": (i, [i, p, p, p]),
         "ref_dense_model_render": (None, [i, f, i, i, i, i, i, f, f, T, i, p]),

@@ -527,6 +527,33 @@ inline void draw_higher(ImageF32 &targetHeight, const ImageF32 &sourceHeight, Im
 	b200_check(dfpsr_draw_higher(&th, &sh, &ta, &sa, &tb, &sb, left, top, sourceHeightOffset, b200_stream())); targetHeight.touchedByDevice(); targetA.touchedByDevice(); targetB.touchedByDevice();
 }
 
+// ---------------------------------------------------------------- remaining 2D draw calls (ref: api/drawAPI.h:68-161)
+struct IRect { int32_t l = 0, t = 0, w = 0, h = 0; IRect() {} IRect(int32_t left, int32_t top, int32_t width, int32_t height) : l(left), t(top), w(width), h(height) {}
+	int32_t left() const { return l; } int32_t top() const { return t; } int32_t width() const { return w; } int32_t height() const { return h; } int32_t right() const { return l + w; } int32_t bottom() const { return t + h; } };
+using ImageU8 = B200Image<uint8_t>;
+inline ImageU8 image_create_U8(int32_t width, int32_t height, bool zeroed = true) { // ref: api/imageAPI.h:47
+	ImageU8 image = b200_image_create<uint8_t>(width, height, PackOrderIndex::RGBA);
+	if (zeroed) { image.buffer->host.assign(image.buffer->bytes, 0); image.buffer->hostValid = true; image.buffer->pushHost(); }
+	return image;
+}
+inline void draw_rectangle(ImageRgbaU8 &image, const IRect &bound, const ColorRgbaI32 &color) {
+	dfpsr_image im = image.pod(); const int32_t c[4] = {color.red, color.green, color.blue, color.alpha};
+	b200_check(dfpsr_draw_rectangle_rgba(&im, bound.l, bound.t, bound.w, bound.h, c, b200_stream())); image.touchedByDevice();
+}
+inline void draw_rectangle(ImageF32 &image, const IRect &bound, float color) { dfpsr_image im = image.pod(); b200_check(dfpsr_draw_rectangle_f32(&im, bound.l, bound.t, bound.w, bound.h, color, b200_stream())); image.touchedByDevice(); }
+inline void draw_line(ImageRgbaU8 &image, int32_t x1, int32_t y1, int32_t x2, int32_t y2, const ColorRgbaI32 &color) {
+	dfpsr_image im = image.pod(); const int32_t c[4] = {color.red, color.green, color.blue, color.alpha};
+	b200_check(dfpsr_draw_line_rgba(&im, x1, y1, x2, y2, c, b200_stream())); image.touchedByDevice();
+}
+inline void draw_line(ImageF32 &image, int32_t x1, int32_t y1, int32_t x2, int32_t y2, float color) { dfpsr_image im = image.pod(); b200_check(dfpsr_draw_line_f32(&im, x1, y1, x2, y2, color, b200_stream())); image.touchedByDevice(); }
+inline void draw_alphaFilter(ImageRgbaU8 &target, const ImageRgbaU8 &source, int32_t left = 0, int32_t top = 0) { dfpsr_image t = target.pod(), s = source.pod(); b200_check(dfpsr_draw_alpha_filter(&t, &s, left, top, b200_stream())); target.touchedByDevice(); }
+inline void draw_maxAlpha(ImageRgbaU8 &target, const ImageRgbaU8 &source, int32_t left = 0, int32_t top = 0, int32_t sourceAlphaOffset = 0) { dfpsr_image t = target.pod(), s = source.pod(); b200_check(dfpsr_draw_max_alpha(&t, &s, left, top, sourceAlphaOffset, b200_stream())); target.touchedByDevice(); }
+inline void draw_alphaClip(ImageRgbaU8 &target, const ImageRgbaU8 &source, int32_t left = 0, int32_t top = 0, int32_t threshold = 127) { dfpsr_image t = target.pod(), s = source.pod(); b200_check(dfpsr_draw_alpha_clip(&t, &s, left, top, threshold, b200_stream())); target.touchedByDevice(); }
+inline void draw_silhouette(ImageRgbaU8 &target, const ImageU8 &silhouette, const ColorRgbaI32 &color, int32_t left = 0, int32_t top = 0) {
+	dfpsr_image t = target.pod(), s = silhouette.pod(); const int32_t c[4] = {color.red, color.green, color.blue, color.alpha};
+	b200_check(dfpsr_draw_silhouette(&t, &s, c, left, top, b200_stream())); target.touchedByDevice();
+}
+
 // ---------------------------------------------------------------- Sandbox deferred light (ref: SDK/SpriteEngine/lightAPI.h:27-31, orthoAPI.h:52-77)
 struct OrthoView { dfpsr_ortho_view pod{}; };
 inline void b200_light_directed(const OrthoView &view, ImageRgbaU8 &lightBuffer, const ImageRgbaU8 &normalBuffer, const FVector3D &lightDirection, float lightIntensity, const ColorRgbaI32 &lightColor, int add) {

@@ -497,6 +497,63 @@ __global__ void __launch_bounds__(256) resize_kernel(Img target, Img source, Res
 	store4(target, x0, y, n, out);
 }
 
+// filter_resize, bilinear, when the reference runs two passes (api/filterAPI.cpp:298-314: the width changes and the height grows): pass 1
+// stretches every source row horizontally with 16-bit weights into a temporary image in the target's pack order (:118-154, lerp16 +
+// saturate and pack), pass 2 mixes two rows of the temporary with 8-bit weights (mixColorsUniform, :49-63, :200-230). This kernel produces
+// the same integers in ONE pass: a thread owns 4 columns x FUSED_ROWS target rows, forms each needed row of the temporary in registers
+// (a row is reused by about targetHeight / sourceHeight consecutive target rows) and never writes it to memory:
+// 4 B x (source + target) of traffic instead of 4 B x (source + 3 x temporary + target).
+static const int FUSED_ROWS = 8;
+__global__ void __launch_bounds__(256) resize_up_fused_kernel(Img target, Img source, ResizeParams rp) {
+	const int32_t x0 = (int32_t)(blockIdx.x * blockDim.x + threadIdx.x) * PX, yFirst = (int32_t)(blockIdx.y * blockDim.y + threadIdx.y) * FUSED_ROWS;
+	if (x0 >= target.width || yFirst >= target.height) { return; }
+	const int n = min(PX, target.width - x0);
+	const uint32_t shifts = pack_shifts(target.packOrder);
+	int32_t leftX[4];
+	uint32_t rightRatio[4];
+#pragma unroll
+	for (int i = 0; i < 4; i++) {
+		const int32_t readX = rp.startX + (x0 + i) * rp.offsetX;
+		const uint32_t sampleX = (uint32_t)(readX < 0 ? 0 : readX);
+		leftX[i] = (int32_t)(sampleX >> 16); rightRatio[i] = sampleX & 65535u;
+	}
+	int32_t heldRow[2] = {-1, -1};
+	uint32_t held[2][4];
+	int next = 0;
+	const int32_t yEnd = min(yFirst + FUSED_ROWS, target.height);
+	for (int32_t y = yFirst; y < yEnd; y++) {
+		const int32_t readY = rp.startY + y * rp.offsetY;
+		const uint32_t sampleY = (uint32_t)(readY < 0 ? 0 : readY);
+		uint32_t upperY = sampleY >> 16, lowerY = upperY + 1;
+		const uint32_t lowerRatio = sampleY & 65535u;
+		if (upperY >= (uint32_t)source.height) { upperY = (uint32_t)source.height - 1; }
+		if (lowerY >= (uint32_t)source.height) { lowerY = (uint32_t)source.height - 1; }
+		int slot[2];
+#pragma unroll
+		for (int r = 0; r < 2; r++) {
+			const int32_t row = (int32_t)(r == 0 ? upperY : lowerY);
+			if (heldRow[0] == row) { slot[r] = 0; }
+			else if (heldRow[1] == row) { slot[r] = 1; }
+			else {
+				// replace the row that is not needed by this target row (rows only move downwards)
+				int victim = next;
+				if (r == 1 && victim == slot[0]) { victim ^= 1; }
+#pragma unroll
+				for (int i = 0; i < 4; i++) {
+					if (i < n) { held[victim][i] = saturate_and_pack(lerp16(read_clamp(source, leftX[i], row), read_clamp(source, leftX[i] + 1, row), rightRatio[i]), shifts); }
+				}
+				heldRow[victim] = row;
+				slot[r] = victim;
+				next = victim ^ 1;
+			}
+		}
+		uint32_t out[4];
+#pragma unroll
+		for (int i = 0; i < 4; i++) { out[i] = mix_uniform(held[slot[0]][i], held[slot[1]][i], lowerRatio); }
+		store4(target, x0, y, n, out);
+	}
+}
+
 struct MapParams { int32_t op, startX, startY; int32_t p[8]; };
 
 // ref: api/filterAPI.cpp:759-777 with the enumerated device ops of dfpsr_b200.h
@@ -843,6 +900,17 @@ int dfpsr_filter_resize(const dfpsr_image *target, const dfpsr_image *source, in
 	Img t = img_of(target), s = img_of(source);
 	bool bilinear = sampler == DFPSR_SAMPLER_LINEAR;
 	// ref: api/filterAPI.cpp:298-314 resizeToTarget
+	if (t.width != s.width && t.height > s.height && bilinear) {
+		// both passes of the reference in one kernel (the scratch buffer is not needed)
+		ResizeParams rp;
+		rp.offsetX = (int32_t)(65536u * (uint32_t)s.width / (uint32_t)t.width);
+		rp.offsetY = (int32_t)(65536u * (uint32_t)s.height / (uint32_t)t.height);
+		rp.startX = rp.offsetX / 2 - 32768; rp.startY = rp.offsetY / 2 - 32768;
+		rp.bilinear = 1; rp.path = RESIZE_GENERAL;
+		dim3 grid((unsigned)((t.width + PX * (int)BLOCK.x - 1) / (PX * (int)BLOCK.x)), (unsigned)((t.height + FUSED_ROWS * (int)BLOCK.y - 1) / (FUSED_ROWS * (int)BLOCK.y)));
+		DFPSR_LAUNCH(resize_up_fused_kernel, grid, BLOCK, 0, as_stream(stream), t, s, rp);
+		return 0;
+	}
 	if (t.width != s.width && t.height > s.height) {
 		DFPSR_REQUIRE(scratch != nullptr, "filter_resize: up-scaling both dimensions needs the scratch buffer (dfpsr_filter_resize_scratch_bytes)");
 		Img temp;

@@ -149,6 +149,11 @@ class SpriteConfig(C.Structure):
     ]
 
 
+class BakedSprite(C.Structure):
+    _fields_ = [("atlas", Image), ("centerX", C.c_int32), ("centerY", C.c_int32), ("frameRows", C.c_int32), ("propertyColumns", C.c_int32),
+                ("minBound", C.c_float * 3), ("maxBound", C.c_float * 3)]
+
+
 class SpriteInstance(C.Structure):
     _fields_ = [("typeIndex", C.c_int32), ("direction", C.c_int32), ("location", C.c_int32 * 3), ("shadowCasting", C.c_int32), ("userData", C.c_uint64)]
 

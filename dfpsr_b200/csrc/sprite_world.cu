@@ -235,6 +235,25 @@ __global__ void __launch_bounds__(256) background_copy_kernel(const CopyDev *__r
 	row_ptr<float>(height.data, height.stride, c.top + y)[c.left + x] = c.height[src];
 }
 
+// ---- sprite baking (ref: spriteAPI.cpp:1329-1432 sprite_generateFromModel)
+// height image of one camera angle: red = (height - minY) * 255 / (maxY - minY) saturated to a byte, alpha = the colour's alpha (:1375-1381)
+__global__ void __launch_bounds__(256) bake_height_kernel(const float *__restrict__ depth, const uint32_t *__restrict__ color, uint32_t *__restrict__ heightImage, int32_t pixels, float minY, float heightScale) {
+	const int32_t i = (int32_t)(blockIdx.x * blockDim.x + threadIdx.x);
+	if (i >= pixels) { return; }
+	int32_t h = f2i((depth[i] - minY) * heightScale);
+	h = h < 0 ? 0 : (h > 255 ? 255 : h);
+	heightImage[i] = (uint32_t)h | (color[i] & 0xFF000000u);
+}
+// bound of the pixels with a non-zero alpha over all angles (:1385-1401): crop = {minX, minY, maxX, maxY}
+__global__ void __launch_bounds__(256) bake_crop_kernel(const uint32_t *__restrict__ color, int32_t width, int32_t height, int32_t angles, int32_t *crop) {
+	const int32_t x = (int32_t)(blockIdx.x * 32u + (threadIdx.x & 31u)), y = (int32_t)(blockIdx.y * 8u + (threadIdx.x >> 5));
+	bool any = false;
+	if (x < width && y < height) {
+		for (int32_t a = 0; a < angles; a++) { any = any || (color[((size_t)a * height + y) * width + x] >> 24) != 0u; }
+	}
+	if (any) { atomicMin(crop + 0, x); atomicMin(crop + 1, y); atomicMax(crop + 2, x); atomicMax(crop + 3, y); }
+}
+
 // ------------------------------------------------------------------------------------------------ types (process global, like the reference)
 
 struct DeviceModel { // shadow model resident on the device (lazily)
@@ -1060,6 +1079,65 @@ int dfpsr_dense_model_render(const dfpsr_dense_triangle *triangles, int32_t tria
 	DFPSR_REQUIRE(height->width == diffuse->width && height->height == diffuse->height && height->width == normal->width && height->height == normal->height, "dense_model_render: targets differ in size");
 	DFPSR_REQUIRE(triangles || triangleCount == 0, "dense_model_render: null triangles");
 	return dense_render(triangles, triangleCount, minBound, maxBound, *view, *height, *diffuse, *normal, worldOrigin, *modelToWorld, highQuality != 0, dirtyRect, as_stream(stream));
+}
+
+int dfpsr_sprite_generate_from_model(const dfpsr_dense_triangle *triangles, int32_t triangleCount, const float minBound[3], const float maxBound[3], const dfpsr_ortho_system *ortho, int32_t cameraAngles, dfpsr_baked_sprite *out, void *stream) {
+	int devices = 0;
+	DFPSR_REQUIRE(cudaGetDeviceCount(&devices) == cudaSuccess && devices > 0, "no CUDA device available; dfpsr_b200 has no CPU fallback");
+	DFPSR_REQUIRE((triangles || triangleCount == 0) && minBound && maxBound && ortho && out, "sprite_generate_from_model: null argument");
+	DFPSR_REQUIRE(cameraAngles >= 1 && cameraAngles <= 8, "Need at least one camera angle to generate a sprite!");
+	memset(out, 0, sizeof(*out));
+	if (minBound[0] > maxBound[0]) { return 0; } // nothing visible (:1345-1348)
+	cudaStream_t s = as_stream(stream);
+	// ref: :1352-1358 — worst-case square image
+	const float worstCaseDiameter = (std::max(maxBound[0], -minBound[0]) + std::max(maxBound[1], -minBound[1]) + std::max(maxBound[2], -minBound[2])) * 2;
+	const int32_t size = f2i(worstCaseDiameter) * ortho->pixelsPerTile;
+	const int32_t maxRes = (int32_t)(size + 1 - signed_modulo(size - 1, 2)) + 4; // roundUp(size, 2) + 4
+	DFPSR_REQUIRE(maxRes > 0 && maxRes <= 16384, "sprite_generate_from_model: the model needs a %d pixel wide image", maxRes);
+	const int32_t width = maxRes, height = maxRes;
+	const size_t pixels = (size_t)width * height;
+	DeviceBuffer depth, planes, dTriangles, dCrop;
+	struct Release { DeviceBuffer *b[4]; ~Release() { for (DeviceBuffer *x : b) { x->release(); } } } release{{&depth, &planes, &dTriangles, &dCrop}};
+	if (depth.reserve(pixels * 4) || planes.reserve(pixels * 4 * 3 * (size_t)cameraAngles) || dTriangles.reserve(std::max<size_t>((size_t)triangleCount * sizeof(dfpsr_dense_triangle), 16)) || dCrop.reserve(16)) { return 1; }
+	uint32_t *color = (uint32_t *)planes.ptr, *heights = color + pixels * cameraAngles, *normals = heights + pixels * cameraAngles;
+	DFPSR_CHECK_CUDA(cudaMemcpyAsync(dTriangles.ptr, triangles, (size_t)triangleCount * sizeof(dfpsr_dense_triangle), cudaMemcpyHostToDevice, s));
+	DFPSR_CHECK_CUDA(cudaMemsetAsync(planes.ptr, 0, pixels * 4 * 3 * (size_t)cameraAngles, s)); // new images are black and transparent
+	const float heightScale = 255.0f / (maxBound[1] - minBound[1]);
+	const float origin[2] = {(float)width * 0.5f, (float)height * 0.5f};
+	dfpsr_transform3d identity;
+	memset(&identity, 0, sizeof(identity));
+	identity.xAxis[0] = identity.yAxis[1] = identity.zAxis[2] = 1.0f;
+	for (int32_t a = 0; a < cameraAngles; a++) {
+		dfpsr_image d, c, n;
+		d.data = depth.ptr; c.data = color + pixels * a; n.data = normals + pixels * a;
+		d.width = c.width = n.width = width; d.height = c.height = n.height = height; d.stride = c.stride = n.stride = width * 4; d.packOrder = c.packOrder = n.packOrder = DFPSR_PACK_RGBA;
+		if (dfpsr_image_fill_f32(&d, -1000000000.0f, stream)) { return 1; }
+		if (dense_render((const dfpsr_dense_triangle *)dTriangles.ptr, triangleCount, minBound, maxBound, ortho->view[a], d, c, n, origin, identity, true, nullptr, s)) { return 1; }
+		DFPSR_LAUNCH(bake_height_kernel, (unsigned)((pixels + 255) / 256), 256, 0, s, (const float *)depth.ptr, (const uint32_t *)c.data, heights + pixels * a, (int32_t)pixels, minBound[1], heightScale);
+	}
+	const int32_t cropInit[4] = {width, height, 0, 0};
+	DFPSR_CHECK_CUDA(cudaMemcpyAsync(dCrop.ptr, cropInit, sizeof(cropInit), cudaMemcpyHostToDevice, s));
+	DFPSR_LAUNCH(bake_crop_kernel, dim3((unsigned)((width + 31) / 32), (unsigned)((height + 7) / 8)), 256, 0, s, (const uint32_t *)color, width, height, cameraAngles, (int32_t *)dCrop.ptr);
+	int32_t crop[4];
+	DFPSR_CHECK_CUDA(cudaMemcpyAsync(crop, dCrop.ptr, sizeof(crop), cudaMemcpyDeviceToHost, s));
+	DFPSR_CHECK_CUDA(cudaStreamSynchronize(s));
+	if (crop[0] > crop[2]) { return 0; } // nothing drawn (:1402-1405)
+	const int32_t croppedWidth = crop[2] + 1 - crop[0], croppedHeight = crop[3] + 1 - crop[1];
+	void *atlas = nullptr;
+	const size_t atlasStride = (size_t)croppedWidth * 3 * 4;
+	DFPSR_CHECK_CUDA(cudaMalloc(&atlas, atlasStride * croppedHeight * cameraAngles));
+	for (int32_t a = 0; a < cameraAngles; a++) { // ref: :1420-1425 — [colour | height | normal] per row of the atlas
+		const uint32_t *sources[3] = {color + pixels * a, heights + pixels * a, normals + pixels * a};
+		for (int column = 0; column < 3; column++) {
+			DFPSR_CHECK_CUDA(cudaMemcpy2DAsync((uint8_t *)atlas + (size_t)a * croppedHeight * atlasStride + (size_t)column * croppedWidth * 4, atlasStride,
+			                                   sources[column] + (size_t)crop[1] * width + crop[0], (size_t)width * 4, (size_t)croppedWidth * 4, (size_t)croppedHeight, cudaMemcpyDeviceToDevice, s));
+		}
+	}
+	DFPSR_CHECK_CUDA(cudaStreamSynchronize(s)); // the working images are released on return
+	out->atlas.data = atlas; out->atlas.width = croppedWidth * 3; out->atlas.height = croppedHeight * cameraAngles; out->atlas.stride = (int32_t)atlasStride; out->atlas.packOrder = DFPSR_PACK_RGBA;
+	out->centerX = width / 2 - crop[0]; out->centerY = height / 2 - crop[1]; out->frameRows = cameraAngles; out->propertyColumns = 3;
+	for (int k = 0; k < 3; k++) { out->minBound[k] = minBound[k]; out->maxBound[k] = maxBound[k]; }
+	return 0;
 }
 
 int dfpsr_sprite_type_create(const uint32_t *atlasHost, int32_t width, int32_t height, int32_t strideBytes, const dfpsr_sprite_config *config, int32_t *typeIndex) {

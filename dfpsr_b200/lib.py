@@ -87,6 +87,7 @@ SIGNATURES = {
     "dfpsr_dense_model_triangle_count": (i32, [vp, i32]),
     "dfpsr_dense_model_build": (i32, [vp, i32, vp, i32, vp, vp, vp]),
     "dfpsr_dense_model_render": (i32, [vp, i32, vp, vp, P(abi.OrthoCamera), P(abi.Image), P(abi.Image), P(abi.Image), vp, P(abi.Transform3D), i32, vp, vp]),
+    "dfpsr_sprite_generate_from_model": (i32, [vp, i32, vp, vp, P(abi.OrthoSystem), i32, P(abi.BakedSprite), vp]),
     "dfpsr_sprite_type_create": (i32, [vp, i32, i32, i32, P(abi.SpriteConfig), P(i32)]),
     "dfpsr_sprite_type_count": (i32, []),
     "dfpsr_model_type_create": (i32, [vp, i32, vp, vp, P(abi.HostModel), P(i32)]),

@@ -330,6 +330,18 @@ int dfpsr_dense_model_build(const float *points, int32_t pointCount, const dfpsr
  * dirtyRect receives {left, top, width, height} of the pessimistic bound the reference returns (all zero when culled); may be NULL. */
 int dfpsr_dense_model_render(const dfpsr_dense_triangle *triangles, int32_t triangleCount, const float minBound[3], const float maxBound[3], const dfpsr_ortho_camera *view, const dfpsr_image *height, const dfpsr_image *diffuse, const dfpsr_image *normal, const float worldOrigin[2], const dfpsr_transform3d *modelToWorld, int32_t highQuality, int32_t dirtyRect[4], void *stream);
 
+/* ref: SDK/SpriteEngine/spriteAPI.cpp:1329-1432 sprite_generateFromModel: renders a dense model (HOST triangles from dfpsr_dense_model_build) with
+ * renderDenseModel<true> from `cameraAngles` of the system's views into a worst-case square image, converts heights to 8 bits, crops all angles
+ * uniformly to the drawn pixels and packs [colour | height | normal] x angles into an atlas. The atlas is a DEVICE image allocated by the call
+ * (release atlas.data with dfpsr_free); atlas.data stays NULL when nothing is visible. The remaining fields are the SpriteConfig the reference
+ * writes to the .ini (the caller appends its shadow model). Synchronises `stream`. */
+typedef struct dfpsr_baked_sprite {
+	dfpsr_image atlas;
+	int32_t centerX, centerY, frameRows, propertyColumns;
+	float minBound[3], maxBound[3];
+} dfpsr_baked_sprite;
+int dfpsr_sprite_generate_from_model(const dfpsr_dense_triangle *triangles, int32_t triangleCount, const float minBound[3], const float maxBound[3], const dfpsr_ortho_system *ortho, int32_t cameraAngles, dfpsr_baked_sprite *out, void *stream);
+
 /* Sprite types are process-global like the reference's (ref: SDK/SpriteEngine/spriteAPI.cpp:279-289). The reference loads
  * <name>.png + <name>.ini; here the decoded atlas (RGBA order, HOST memory) and the parsed configuration are passed in
  * (ref: spriteAPI.cpp:47-133 SpriteConfig, :190-232 SpriteType): the atlas holds frameRows rows of [colour | height | normal ...]

@@ -567,6 +567,23 @@ int ref_model_type_create(int dense, int shadowModel) {
 	return (int)modelTypes.pushConstructGetIndex(g_dense[dense], shadowModel >= 0 ? g_models[shadowModel] : Model());
 }
 
+// sprite_generateFromModel (SDK/SpriteEngine/spriteAPI.cpp:1329-1432): returns the atlas as a new image id (-1 when nothing was generated) and the
+// numbers of the configuration text: out = {centerX, centerY, frameRows, propertyColumns}.
+int ref_sprite_generate_from_model(int visibleModel, int shadowModel, float cameraTilt, int pixelsPerTile, int cameraAngles, int32_t *out) {
+	ensureStarted();
+	ImageRgbaU8 atlas;
+	String configText;
+	sprite_generateFromModel(atlas, configText, g_models[visibleModel], shadowModel >= 0 ? g_models[shadowModel] : Model(), OrthoSystem(cameraTilt, pixelsPerTile), U"", cameraAngles);
+	if (!image_exists(atlas)) { return -1; }
+	SpriteConfig config(configText);
+	out[0] = config.centerX; out[1] = config.centerY; out[2] = config.frameRows; out[3] = config.propertyColumns;
+	AnyImage img;
+	img.kind = 1;
+	img.rgba = atlas;
+	g_images.push_back(img);
+	return (int)g_images.size() - 1;
+}
+
 int ref_world_create(float cameraTilt, int pixelsPerTile, int shadowResolution) {
 	ensureStarted();
 	g_worlds.push_back(spriteWorld_create(OrthoSystem(cameraTilt, pixelsPerTile), shadowResolution));

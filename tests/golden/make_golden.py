@@ -108,6 +108,10 @@ def sprite_world(ref):
     out = {"script_frames": [dict(sprite_world_scene.frame_hashes(f), camera=[int(v) for v in f["camera"]], ground=[int(v) for v in f["ground"]],
                                   covered=float((f["height"] > -1e5).mean())) for f in frames]}
     out["dense"] = [dict(case=case, **sprite_world_scene.frame_hashes_dense(sprite_world_scene.dense_reference(ref, assets, case))) for case in range(len(sprite_world_scene.DENSE_CASES))]
+    out["bake"] = []
+    for case in range(len(sprite_world_scene.BAKE_CASES)):
+        baked = sprite_world_scene.bake_reference(ref, assets, case)
+        out["bake"].append({"atlas_sha256": sha(baked["atlas"]), "shape": list(baked["atlas"].shape), "config": baked["config"], "opaque": float((baked["atlas"] >> 24 != 0).mean())})
     ref.free_all()
     return out
 

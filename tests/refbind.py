@@ -62,6 +62,7 @@ def load(flavour="scalar"):
         "ref_dense_model_render": (None, [i, f, i, i, i, i, i, f, f, T, i, p]),
         "ref_sprite_type_create": (i, [i, C.c_char_p, C.c_char_p, C.c_char_p]), "ref_sprite_type_count": (i, []),
         "ref_model_type_create": (i, [i, i]),
+        "ref_sprite_generate_from_model": (i, [i, i, f, i, i, p]),
         "ref_world_create": (i, [f, i, i]),
         "ref_world_add_background_sprite": (None, [i, C.POINTER(abi.SpriteInstance)]), "ref_world_add_background_model": (None, [i, C.POINTER(abi.ModelInstance)]),
         "ref_world_add_temporary_sprite": (None, [i, C.POINTER(abi.SpriteInstance)]), "ref_world_add_temporary_model": (None, [i, C.POINTER(abi.ModelInstance)]),

@@ -601,3 +601,35 @@ def sandbox_script(width=800, height=600, lights=16, frames=6, seed=31):
             s.append(("move_camera", 8, -5))
         s.append(("draw", width, height))
     return s
+
+
+# ------------------------------------------------------------------------------------------------ sprite baking (sprite_generateFromModel)
+
+BAKE_CASES = [(0, 8), (1, 3), (0, 1)]  # (model, camera angles)
+
+
+def bake_reference(ref, assets, case):
+    model, angles = BAKE_CASES[case]
+    m = assets["models"][model]
+    info = np.zeros(4, np.int32)
+    atlas = ref.lib.ref_sprite_generate_from_model(ref.model(m["points"], m["polygons"]), -1, TILT, PIXELS_PER_TILE, angles, _ptr(info))
+    assert atlas >= 0
+    return {"atlas": ref.read_rgba(atlas), "config": [int(v) for v in info]}
+
+
+def bake_cuda(lib_handle, lib, assets, case):
+    import torch
+    model, angles = BAKE_CASES[case]
+    m = assets["models"][model]
+    tris, mn, mx = dense_build(lib_handle, lib.check, m["points"], m["polygons"])
+    ortho = abi.OrthoSystem()
+    lib.check(lib_handle.dfpsr_ortho_system_create(C.byref(ortho), TILT, PIXELS_PER_TILE))
+    baked = abi.BakedSprite()
+    lib.check(lib_handle.dfpsr_sprite_generate_from_model(_ptr(tris), len(tris), _ptr(mn), _ptr(mx), C.byref(ortho), angles, C.byref(baked), lib.stream_ptr()))
+    assert baked.atlas.data
+    host = np.zeros((baked.atlas.height, baked.atlas.stride // 4), np.uint32)
+    lib.check(lib_handle.dfpsr_download(_ptr(host), baked.atlas.data, host.nbytes, lib.stream_ptr()))
+    torch.cuda.synchronize()
+    lib.check(lib_handle.dfpsr_free(baked.atlas.data))
+    assert list(baked.minBound) == [float(v) for v in mn] and list(baked.maxBound) == [float(v) for v in mx]
+    return {"atlas": host[:, :baked.atlas.width].copy(), "config": [baked.centerX, baked.centerY, baked.frameRows, baked.propertyColumns]}

@@ -31,7 +31,10 @@ static const int BATCH = 16;               // commands whose checkpoints are pre
 static const int SMALL_ROWS = 16;          // triangles up to this many rows and SMALL_WIDTH columns are scan-converted by their set-up thread
 static const int SMALL_WIDTH = 128;
 static const int SMALL_TILES = 8;          // counting pass: bounding boxes up to this many tiles are counted by the set-up thread
-static const int SETUP_THREADS = 256;
+#ifndef SETUP_THREADS_N
+#define SETUP_THREADS_N 64
+#endif
+static const int SETUP_THREADS = SETUP_THREADS_N; // slots (quads / pre-projected triangles) per set-up CTA
 static const int RASTER_WARPS = 4;
 #ifndef RASTER_MIN_BLOCKS
 #define RASTER_MIN_BLOCKS 8 // 64 registers: measured 50 us per 1080p terrain frame against 63 us at 128 registers (tools/variant_sweep.py)
@@ -112,12 +115,15 @@ struct FrameDev {
 	uint32_t *blockCmds, *blockRows; // per set-up block: totals, then exclusive offsets after scan_blocks_kernel
 	uint32_t *tileCount, *tileOffset, *tileCursor;
 	uint32_t *totals;                // [0] commands, [1] rows, [2] tile entries (upper bound), [3] max entries in one tile (upper bound),
-	                                 // [4] checkpoint records (upper bound), [5] checkpoint cursor, [6] rank-sort scratch cursor
+	                                 // [4] checkpoint records (upper bound), [5] checkpoint cursor, [6] rank-sort scratch cursor,
+	                                 // [7] (command, tile row) units of large commands, [8] large command cursor, [9] unit cursor
 	Cmd *cmds;
 	int2 *rows;
 	uint32_t *tileList;
 	ChkRec *chk;                     // checkpoint records of large triangles; totals[4] = records needed (upper bound), totals[5] = cursor
 	uint32_t *sortTmp;               // rank-sort scratch, as large as the entry pool; totals[6] = cursor
+	struct BigItem *bigItems;        // large commands of the frame (totals[8] = cursor) and, per (command, tile row) unit, the index of its
+	uint32_t *bigUnits;              // command in bigItems (totals[7] = units needed, counted by the first pass; totals[9] = cursor)
 	const float *occlusionGrid;      // 16-pixel cells of the farthest depth at which something can still be visible; null = no occluders
 	int32_t gridWidth, gridHeight, gridStride;
 };
@@ -531,6 +537,7 @@ __global__ void __launch_bounds__(256) top_rows_kernel(dfpsr_image depth, int32_
 // A command whose tile counting (counting pass) or rows + tile entries (emit pass) are produced cooperatively by one warp.
 struct BigItem {
 	uint32_t cmdIndex, rowOffset, tileBase, chkOffset;
+	uint32_t unitStart; // first (command, tile row) unit of this command in FrameDev::bigUnits
 	int32_t tilesX, l, t, r, rowCount;
 	int32_t tx0, tx1, ty0, ty1;
 	long long fx[3], fy[3];
@@ -627,9 +634,10 @@ __global__ void __launch_bounds__(SETUP_THREADS) setup_kernel(FrameDev frame) {
 	__shared__ TaskParams task;
 	__shared__ uint32_t warpCmds[SETUP_THREADS / 32], warpRows[SETUP_THREADS / 32];
 	__shared__ BigItem sBig[SETUP_THREADS];
-	__shared__ uint32_t sBigCount, sChkCount;
+	__shared__ uint32_t sBigCount, sChkCount, sUnitCount, sItemBase, sUnitBase;
+	__shared__ uint32_t sUnitEnd[SETUP_THREADS]; // emit pass: inclusive prefix of tile rows over the queued commands
 	{
-		if (threadIdx.x == 0) { sChkCount = 0; }
+		if (threadIdx.x == 0) { sChkCount = 0; sUnitCount = 0; }
 		int32_t t = task_of_block(frame.tasks, frame.taskCount, (int32_t)blockIdx.x);
 		for (uint32_t w = threadIdx.x; w < sizeof(TaskParams) / 4; w += blockDim.x) { ((uint32_t *)&task)[w] = ((const uint32_t *)&frame.tasks[t])[w]; }
 		if (threadIdx.x == 0) { sBigCount = 0; }
@@ -681,6 +689,7 @@ __global__ void __launch_bounds__(SETUP_THREADS) setup_kernel(FrameDev frame) {
 			if (!EMIT) {
 				if (rowCount > 0) {
 					if (!small && !task.depthOnly) { atomicAdd(&sChkCount, (uint32_t)((rowCount / 2) * (tx1 - tx0 + 1))); }
+					if (!small) { atomicAdd(&sUnitCount, (uint32_t)((bound.t + rowCount - 1) / TILE_H - bound.t / TILE_H + 1)); }
 					int32_t tiles = (tx1 - tx0 + 1) * (ty1 - ty0 + 1);
 					uint32_t queued = 0xFFFFFFFFu;
 					if (tiles > SMALL_TILES) {
@@ -728,7 +737,7 @@ __global__ void __launch_bounds__(SETUP_THREADS) setup_kernel(FrameDev frame) {
 						BigItem &it = sBig[queued];
 						it.cmdIndex = index; it.rowOffset = cmd.rowOffset; it.tileBase = tileBase; it.tilesX = tilesX;
 						it.l = bound.l; it.t = bound.t; it.r = bound.r; it.rowCount = rowCount;
-						it.tx0 = tx0; it.tx1 = tx1;
+						it.tx0 = tx0; it.tx1 = tx1; it.ty0 = 0; it.ty1 = height;
 						for (int k = 0; k < 3; k++) { it.fx[k] = q[k].fx; it.fy[k] = q[k].fy; }
 						it.chkOffset = CHK_NONE;
 #ifndef DFPSR_NO_CHK
@@ -771,51 +780,52 @@ __global__ void __launch_bounds__(SETUP_THREADS) setup_kernel(FrameDev frame) {
 		});
 	}
 
-	// ---- commands handed to whole warps
+	// ---- large commands: the count pass walks bounding boxes warp by warp; the emit pass flattens them into (command, tile row) units and
+	// gives every thread of the block the same number of units, so a block full of tall triangles is not eight warps working through 32
+	// commands each with a third of their lanes busy (that serial tail was 200 us of a single 1080p frame)
 	__syncthreads();
-	{
+	if (!EMIT) {
 		const uint32_t bigCount = min(sBigCount, (uint32_t)SETUP_THREADS);
 		for (uint32_t b = warp; b < bigCount; b += SETUP_THREADS / 32) {
 			const BigItem &it = sBig[b];
-			if (!EMIT) {
-				int32_t w = it.tx1 - it.tx0 + 1, tiles = w * (it.ty1 - it.ty0 + 1);
-				for (int32_t i = lane; i < tiles; i += 32) {
-					atomicAdd(&frame.tileCount[it.tileBase + (uint32_t)((it.ty0 + i / w) * it.tilesX + it.tx0 + i % w)], 1u);
-				}
-			} else {
-				EdgeSet edges;
-				long long fx[3] = {it.fx[0], it.fx[1], it.fx[2]}, fy[3] = {it.fy[0], it.fy[1], it.fy[2]};
-				edges_setup(edges, fx, fy, it.l, it.t, it.r);
-				float start[3], dx[3], dy[3];
-				const bool checkpoints = it.chkOffset != CHK_NONE;
-				if (checkpoints) {
-					// the command record was written by a thread of this block before the barrier above
-					const float *planes = (const float *)&frame.cmds[it.cmdIndex];
-#pragma unroll
-					for (int k = 0; k < 3; k++) { start[k] = planes[k]; dx[k] = planes[3 + k]; dy[k] = planes[6 + k]; }
-				}
-				const int32_t columns = it.tx1 - it.tx0 + 1;
-				const int32_t tyFirst = it.t / TILE_H, tyLast = (it.t + it.rowCount - 1) / TILE_H;
-				for (int32_t ty = tyFirst + lane; ty <= tyLast; ty += 32) {
-					int32_t yBegin = max(it.t, ty * TILE_H), yEnd = min(it.t + it.rowCount, ty * TILE_H + TILE_H);
-					int32_t minL = 0x7FFFFFFF, maxR = -1;
-					for (int32_t y = yBegin; y < yEnd; y += 2) { // rows come in even-aligned pairs
-						int2 upperRow = edges_row(edges, y), lowerRow = edges_row(edges, y + 1);
-						*(int4 *)&frame.rows[it.rowOffset + (uint32_t)(y - it.t)] = make_int4(upperRow.x, upperRow.y, lowerRow.x, lowerRow.y);
-						if (upperRow.y > upperRow.x && y < height) { minL = min(minL, upperRow.x); maxR = max(maxR, upperRow.y); }
-						if (lowerRow.y > lowerRow.x && y + 1 < height) { minL = min(minL, lowerRow.x); maxR = max(maxR, lowerRow.y); }
-						if (checkpoints && y < height) {
-							chk_walk_row_pair(start, dx, dy, upperRow, lowerRow, y, frame.chk + it.chkOffset + (size_t)((y - it.t) / 2) * (size_t)columns, it.tx0);
-						}
-					}
-					if (ty * TILE_H < height) { emit_tile_row(frame, it.tileBase, it.tilesX, ty, minL, maxR, it.cmdIndex); }
-				}
+			int32_t w = it.tx1 - it.tx0 + 1, tiles = w * (it.ty1 - it.ty0 + 1);
+			for (int32_t i = lane; i < tiles; i += 32) {
+				atomicAdd(&frame.tileCount[it.tileBase + (uint32_t)((it.ty0 + i / w) * it.tilesX + it.tx0 + i % w)], 1u);
 			}
+		}
+	} else {
+		const uint32_t bigCount = min(sBigCount, (uint32_t)SETUP_THREADS);
+		// inclusive prefix of tile rows per queued command (bigCount <= SETUP_THREADS: one command per thread)
+		uint32_t mine = 0;
+		if (threadIdx.x < bigCount) { const BigItem &it = sBig[threadIdx.x]; mine = (uint32_t)((it.t + it.rowCount - 1) / TILE_H - it.t / TILE_H + 1); }
+		uint32_t inclusive = mine;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) { const uint32_t a = __shfl_up_sync(0xffffffffu, inclusive, d); if (lane >= d) { inclusive += a; } }
+		if (lane == 31) { warpCmds[warp] = inclusive; }
+		__syncthreads();
+		uint32_t before = 0;
+		for (int w = 0; w < warp; w++) { before += warpCmds[w]; }
+		sUnitEnd[threadIdx.x] = before + inclusive;
+		__syncthreads();
+		const uint32_t unitTotal = bigCount > 0 ? sUnitEnd[bigCount - 1] : 0u;
+		// the block reserves its share of the frame-wide queues with one atomic each; big_units_kernel then gives every unit its own thread
+		if (threadIdx.x == 0 && bigCount > 0) { sItemBase = atomicAdd(&frame.totals[8], bigCount); sUnitBase = atomicAdd(&frame.totals[9], unitTotal); }
+		__syncthreads();
+		if (threadIdx.x < bigCount) {
+			BigItem it = sBig[threadIdx.x];
+			it.unitStart = sUnitBase + (threadIdx.x > 0 ? sUnitEnd[threadIdx.x - 1] : 0u);
+			frame.bigItems[sItemBase + threadIdx.x] = it;
+		}
+		for (uint32_t u = threadIdx.x; u < unitTotal; u += SETUP_THREADS) {
+			uint32_t lo = 0, hi = bigCount - 1; // first command whose inclusive end exceeds u
+			while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (sUnitEnd[mid] > u) { hi = mid; } else { lo = mid + 1; } }
+			frame.bigUnits[sUnitBase + u] = sItemBase + lo;
 		}
 	}
 
 	if (!EMIT) {
 		if (threadIdx.x == 0 && sChkCount > 0) { atomicAdd(&frame.totals[4], sChkCount); }
+		if (threadIdx.x == 0 && sUnitCount > 0) { atomicAdd(&frame.totals[7], sUnitCount); }
 		if (active) { frame.slotCounts[slot] = countCmd | (countRows << 3); }
 		// block totals for scan_blocks_kernel
 		uint32_t sumCmd = countCmd, sumRows = countRows;
@@ -833,6 +843,42 @@ __global__ void __launch_bounds__(SETUP_THREADS) setup_kernel(FrameDev frame) {
 			frame.blockRows[blockIdx.x] = b;
 		}
 	}
+}
+
+// One thread per (large command, tile row): scan-converts the row pairs of that tile row (ref: ITriangle2D.cpp:86-176), bins the command to
+// the tiles they touch and walks the interpolation chains across the tile columns, leaving the checkpoints the tile kernel continues from.
+// The units of the whole batch are spread over the whole grid, so one 1080p frame (about 60 k units) already fills the machine.
+__global__ void __launch_bounds__(256) big_units_kernel(FrameDev frame, uint32_t unitTotal) {
+	const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+	// unitTotal is the first pass's count (the launch size); commands that overflowed a block's queue were finished by their own thread,
+	// so the cursor holds the number of units that were really queued
+	if (u >= unitTotal || u >= frame.totals[9]) { return; }
+	const BigItem &it = frame.bigItems[frame.bigUnits[u]];
+	const int32_t ty = it.t / TILE_H + (int32_t)(u - it.unitStart);
+	const int32_t height = it.ty1; // the view's height travels in ty1 (unused by the emit pass)
+	EdgeSet edges;
+	long long fx[3] = {it.fx[0], it.fx[1], it.fx[2]}, fy[3] = {it.fy[0], it.fy[1], it.fy[2]};
+	edges_setup(edges, fx, fy, it.l, it.t, it.r);
+	float start[3], dx[3], dy[3];
+	const bool checkpoints = it.chkOffset != CHK_NONE;
+	if (checkpoints) {
+		const float *planes = (const float *)&frame.cmds[it.cmdIndex];
+#pragma unroll
+		for (int k = 0; k < 3; k++) { start[k] = planes[k]; dx[k] = planes[3 + k]; dy[k] = planes[6 + k]; }
+	}
+	const int32_t columns = it.tx1 - it.tx0 + 1;
+	const int32_t yBegin = max(it.t, ty * TILE_H), yEnd = min(it.t + it.rowCount, ty * TILE_H + TILE_H);
+	int32_t minL = 0x7FFFFFFF, maxR = -1;
+	for (int32_t y = yBegin; y < yEnd; y += 2) { // rows come in even-aligned pairs
+		int2 upperRow = edges_row(edges, y), lowerRow = edges_row(edges, y + 1);
+		*(int4 *)&frame.rows[it.rowOffset + (uint32_t)(y - it.t)] = make_int4(upperRow.x, upperRow.y, lowerRow.x, lowerRow.y);
+		if (upperRow.y > upperRow.x && y < height) { minL = min(minL, upperRow.x); maxR = max(maxR, upperRow.y); }
+		if (lowerRow.y > lowerRow.x && y + 1 < height) { minL = min(minL, lowerRow.x); maxR = max(maxR, lowerRow.y); }
+		if (checkpoints && y < height) {
+			chk_walk_row_pair(start, dx, dy, upperRow, lowerRow, y, frame.chk + it.chkOffset + (size_t)((y - it.t) / 2) * (size_t)columns, it.tx0);
+		}
+	}
+	if (ty * TILE_H < height) { emit_tile_row(frame, it.tileBase, it.tilesX, ty, minL, maxR, it.cmdIndex); }
 }
 
 // ref: api/rendererAPI.cpp:242-258 occludeFromExistingTriangles: every solid command queued so far is an occluder for the cells that lie
@@ -933,7 +979,7 @@ __global__ void __launch_bounds__(256) tile_alloc_kernel(FrameDev frame) {
 // would queue on the copy engine behind megabytes of finished frames travelling to the host (dfpsr_session_render_views_host) and
 // stall the next chunk's set-up for milliseconds.
 __global__ void publish_totals_kernel(const uint32_t *__restrict__ totals, volatile uint32_t *hostTotals) {
-	if (threadIdx.x < 5) { hostTotals[threadIdx.x] = totals[threadIdx.x]; }
+	if (threadIdx.x < 8) { hostTotals[threadIdx.x] = totals[threadIdx.x]; }
 	__threadfence_system();
 }
 
@@ -1580,7 +1626,7 @@ struct dfpsr_renderer {
 	TexTable textures{};
 	int textureCount = 0;
 	int64_t lastCommands = -1;
-	DeviceBuffer dTasks, dViews, projected, slotCounts, blockCmds, blockRows, tileCount, tileOffset, tileCursor, cmds, rows, tileList, chk, sortTmp;
+	DeviceBuffer dTasks, dViews, projected, slotCounts, blockCmds, blockRows, tileCount, tileOffset, tileCursor, cmds, rows, tileList, chk, sortTmp, bigItems, bigUnits;
 	uint32_t *hostTotals = nullptr, *hostTotalsDevice = nullptr; // mapped pinned memory and its device alias
 	// occlusion grid (ref: api/rendererAPI.cpp:145, :181-192): lives on the host, where occluder boxes and visibility queries are evaluated
 	std::vector<float> grid;
@@ -1590,7 +1636,7 @@ struct dfpsr_renderer {
 
 	~dfpsr_renderer() {
 		for (auto &b : uploads) { b.release(); }
-		DeviceBuffer *all[] = {&dTasks, &dViews, &projected, &slotCounts, &blockCmds, &blockRows, &tileCount, &tileOffset, &tileCursor, &cmds, &rows, &tileList, &chk, &sortTmp, &dGrid};
+		DeviceBuffer *all[] = {&dTasks, &dViews, &projected, &slotCounts, &blockCmds, &blockRows, &tileCount, &tileOffset, &tileCursor, &cmds, &rows, &tileList, &chk, &sortTmp, &bigItems, &bigUnits, &dGrid};
 		for (auto *b : all) { b->release(); }
 		if (hostTotals) { cudaFreeHost(hostTotals); }
 	}
@@ -1638,7 +1684,7 @@ static int renderer_begin_internal(dfpsr_renderer *r, bool depthOnly) {
 	r->uploadCount = 0;
 	r->textureCount = 0;
 	if (!r->hostTotals) {
-		DFPSR_CHECK_CUDA(cudaHostAlloc((void **)&r->hostTotals, 8 * sizeof(uint32_t), cudaHostAllocMapped));
+		DFPSR_CHECK_CUDA(cudaHostAlloc((void **)&r->hostTotals, 16 * sizeof(uint32_t), cudaHostAllocMapped));
 		DFPSR_CHECK_CUDA(cudaHostGetDevicePointer((void **)&r->hostTotalsDevice, r->hostTotals, 0));
 	}
 	return 0;
@@ -1716,12 +1762,12 @@ static int renderer_end_internal(dfpsr_renderer *r, cudaStream_t stream) {
 	if (layout_tasks(r, slotTotal, blockTotal)) { return 1; }
 	const size_t taskCount = r->tasks.size(), viewCount = r->views.size();
 	if (r->dTasks.reserve(taskCount * sizeof(TaskParams) + 16) || r->dViews.reserve(viewCount * sizeof(ViewDev))) { return 1; }
-	if (r->tileCount.reserve(((size_t)tileTotal + 8) * 4) || r->tileOffset.reserve(((size_t)tileTotal + 1) * 4) || r->tileCursor.reserve(((size_t)tileTotal + 1) * 4)) { return 1; }
+	if (r->tileCount.reserve(((size_t)tileTotal + 12) * 4) || r->tileOffset.reserve(((size_t)tileTotal + 1) * 4) || r->tileCursor.reserve(((size_t)tileTotal + 1) * 4)) { return 1; }
 	if (r->slotCounts.reserve((size_t)slotTotal * 4 + 16) || r->blockCmds.reserve((size_t)blockTotal * 4 + 16) || r->blockRows.reserve((size_t)blockTotal * 4 + 16)) { return 1; }
 	// pageable sources: cudaMemcpyAsync stages them before returning, so the vectors may change afterwards
 	if (taskCount > 0) { DFPSR_CHECK_CUDA(cudaMemcpyAsync(r->dTasks.ptr, r->tasks.data(), taskCount * sizeof(TaskParams), cudaMemcpyHostToDevice, stream)); }
 	DFPSR_CHECK_CUDA(cudaMemcpyAsync(r->dViews.ptr, r->views.data(), viewCount * sizeof(ViewDev), cudaMemcpyHostToDevice, stream));
-	DFPSR_CHECK_CUDA(cudaMemsetAsync(r->tileCount.ptr, 0, ((size_t)tileTotal + 8) * 4, stream)); // tile counts, cursors of empty frames, totals
+	DFPSR_CHECK_CUDA(cudaMemsetAsync(r->tileCount.ptr, 0, ((size_t)tileTotal + 12) * 4, stream)); // tile counts, cursors of empty frames, totals
 	if (taskCount == 0) { DFPSR_CHECK_CUDA(cudaMemsetAsync(r->tileCursor.ptr, 0, (size_t)tileTotal * 4, stream)); }
 
 	FrameDev frame;
@@ -1760,7 +1806,13 @@ static int renderer_end_internal(dfpsr_renderer *r, cudaStream_t stream) {
 			frame.cmds = (Cmd *)r->cmds.ptr;
 			frame.rows = (int2 *)r->rows.ptr;
 			frame.tileList = (uint32_t *)r->tileList.ptr;
+			const uint32_t unitTotal = r->hostTotals[7];
+			if (unitTotal > 0) {
+				if (r->bigItems.reserve((size_t)commandTotal * sizeof(BigItem)) || r->bigUnits.reserve((size_t)unitTotal * 4)) { return 1; }
+				frame.bigItems = (BigItem *)r->bigItems.ptr; frame.bigUnits = (uint32_t *)r->bigUnits.ptr;
+			}
 			DFPSR_LAUNCH(setup_kernel<true>, blockTotal, SETUP_THREADS, 0, stream, frame);
+			if (unitTotal > 0) { DFPSR_LAUNCH(big_units_kernel, (unitTotal + 255) / 256, 256, 0, stream, frame, unitTotal); }
 			if (maxTile > 32u) {
 				if (maxTile > (uint32_t)SORT_SMEM) {
 					if (r->sortTmp.reserve((size_t)entryTotal * 4 + 16)) { return 1; }

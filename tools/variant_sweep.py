@@ -8,6 +8,7 @@ for flags in sys.argv[1:]:
     try:
         line = json.loads(out.stdout.strip().splitlines()[-1])
         k = line["roofline"]["per_kernel_us_per_frame"]
-        print(flags, "| fps", round(line["value"]), "| raster us", round(k.get("raster_kernel<false>", 0), 1), "| setup us", round(k.get("setup_kernel<true>", 0), 1), flush=True)
+        single = subprocess.run([sys.executable, "tools/single_frame_profile.py"], capture_output=True, text=True).stdout.strip().splitlines()
+        print(flags, "| fps", round(line["value"]), "| raster us", round(k.get("raster_kernel<false>", 0), 1), "| setup us", round(k.get("setup_kernel<true>", 0), 1), "|", single[0] if single else "", flush=True)
     except Exception as exc:
         print(flags, "failed", exc, out.stderr[-800:], flush=True)

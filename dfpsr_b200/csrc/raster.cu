@@ -39,6 +39,7 @@ static const int RASTER_WARPS = 4;
 #ifndef RASTER_MIN_BLOCKS
 #define RASTER_MIN_BLOCKS 8 // 64 registers: measured 50 us per 1080p terrain frame against 63 us at 128 registers (tools/variant_sweep.py)
 #endif
+static const int LOCAL_SORT = 64;           // tile lists up to this long are sorted by the tile kernel's own warp (two keys per lane)
 static const int SORT_THREADS = 256;
 static const int SORT_SMEM = 4096;         // entries of one tile list sorted in shared memory by a CTA; longer lists use the rank sort
 static const int SORT_WARP = SORT_SMEM / (SORT_THREADS / 32); // lists up to this long are sorted by single warps
@@ -912,37 +913,58 @@ __global__ void __launch_bounds__(SETUP_THREADS) occlude_existing_kernel(FrameDe
 	});
 }
 
-// One CTA: exclusive scans of the per-block command and row totals (submission order is preserved).
+// One CTA: exclusive scans of the per-block command and row totals (submission order is preserved). Every thread owns SCAN_ITEMS
+// consecutive blocks per round, so 2 M tiny triangles (16 k set-up blocks) need two rounds instead of sixteen.
+static const int SCAN_ITEMS = 8;
 __global__ void __launch_bounds__(1024) scan_blocks_kernel(FrameDev frame) {
 	__shared__ uint32_t warpSum[2][32];
 	__shared__ uint32_t carry[2];
-	int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	if (threadIdx.x < 2) { carry[threadIdx.x] = 0; }
 	__syncthreads();
-	for (int32_t base = 0; base < frame.blockCount; base += 1024) {
-		int32_t i = base + threadIdx.x;
-		uint32_t v[2];
-		v[0] = i < frame.blockCount ? frame.blockCmds[i] : 0u;
-		v[1] = i < frame.blockCount ? frame.blockRows[i] : 0u;
-		uint32_t inc[2] = {v[0], v[1]};
+	for (int32_t base = 0; base < frame.blockCount; base += 1024 * SCAN_ITEMS) {
+		const int32_t first = base + (int32_t)threadIdx.x * SCAN_ITEMS;
+		uint32_t v[2][SCAN_ITEMS], total[2] = {0u, 0u};
+#pragma unroll
+		for (int e = 0; e < SCAN_ITEMS; e++) {
+			const bool valid = first + e < frame.blockCount;
+			v[0][e] = valid ? frame.blockCmds[first + e] : 0u; v[1][e] = valid ? frame.blockRows[first + e] : 0u;
+			total[0] += v[0][e]; total[1] += v[1][e];
+		}
+		uint32_t inc[2] = {total[0], total[1]};
 #pragma unroll
 		for (int d = 1; d < 32; d <<= 1) {
 #pragma unroll
 			for (int k = 0; k < 2; k++) {
-				uint32_t a = __shfl_up_sync(0xffffffffu, inc[k], d);
+				const uint32_t a = __shfl_up_sync(0xffffffffu, inc[k], d);
 				if (lane >= d) { inc[k] += a; }
 			}
 		}
 		if (lane == 31) { for (int k = 0; k < 2; k++) { warpSum[k][warp] = inc[k]; } }
 		__syncthreads();
-		uint32_t pre[2] = {carry[0], carry[1]};
-		for (int w = 0; w < warp; w++) { for (int k = 0; k < 2; k++) { pre[k] += warpSum[k][w]; } }
-		if (i < frame.blockCount) {
-			frame.blockCmds[i] = pre[0] + inc[0] - v[0];
-			frame.blockRows[i] = pre[1] + inc[1] - v[1];
+		if (warp == 0) { // inclusive scan of the 32 warp totals
+			uint32_t w[2] = {warpSum[0][lane], warpSum[1][lane]};
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) {
+#pragma unroll
+				for (int k = 0; k < 2; k++) {
+					const uint32_t a = __shfl_up_sync(0xffffffffu, w[k], d);
+					if (lane >= d) { w[k] += a; }
+				}
+			}
+			warpSum[0][lane] = w[0]; warpSum[1][lane] = w[1];
 		}
 		__syncthreads();
-		if (threadIdx.x == 1023) { for (int k = 0; k < 2; k++) { carry[k] = pre[k] + inc[k]; } }
+		uint32_t running[2];
+#pragma unroll
+		for (int k = 0; k < 2; k++) { running[k] = carry[k] + (warp > 0 ? warpSum[k][warp - 1] : 0u) + inc[k] - total[k]; }
+#pragma unroll
+		for (int e = 0; e < SCAN_ITEMS; e++) {
+			if (first + e < frame.blockCount) { frame.blockCmds[first + e] = running[0]; frame.blockRows[first + e] = running[1]; }
+			running[0] += v[0][e]; running[1] += v[1][e];
+		}
+		__syncthreads();
+		if (threadIdx.x == 0) { for (int k = 0; k < 2; k++) { carry[k] += warpSum[k][31]; } }
 		__syncthreads();
 	}
 	if (threadIdx.x == 0) {
@@ -983,7 +1005,7 @@ __global__ void publish_totals_kernel(const uint32_t *__restrict__ totals, volat
 	__threadfence_system();
 }
 
-// Restores ascending command order in the lists that hold more than 32 entries (shorter ones are sorted in registers by raster_kernel).
+// Restores ascending command order in the lists that hold more than LOCAL_SORT entries (shorter ones are sorted in registers by raster_kernel).
 // Every thread looks at one tile; the long ones are queued in shared memory and sorted by the whole CTA one after the other.
 __global__ void __launch_bounds__(SORT_THREADS) sort_lists_kernel(FrameDev frame) {
 	__shared__ uint32_t s[SORT_SMEM];
@@ -993,7 +1015,7 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_lists_kernel(FrameDev frame
 	__syncthreads();
 	{
 		const uint32_t tile = blockIdx.x * SORT_THREADS + threadIdx.x;
-		if (tile < frame.tileTotal && frame.tileCursor[tile] > 32u) { sQueue[atomicAdd(&sQueued, 1u)] = tile; }
+		if (tile < frame.tileTotal && frame.tileCursor[tile] > (uint32_t)LOCAL_SORT) { sQueue[atomicAdd(&sQueued, 1u)] = tile; }
 	}
 	__syncthreads();
 	const uint32_t queued = sQueued;
@@ -1182,9 +1204,31 @@ __device__ __forceinline__ uint32_t warp_sort(uint32_t key, int lane) {
 	return key;
 }
 
+// Ascending bitonic sort of 64 keys held two per lane: element i lives in lane (i & 31), register (i >> 5).
+__device__ __forceinline__ void warp_sort64(uint32_t &k0, uint32_t &k1, int lane) {
+#pragma unroll
+	for (int k = 2; k <= 64; k <<= 1) {
+#pragma unroll
+		for (int j = k >> 1; j > 0; j >>= 1) {
+			if (j == 32) {
+				// partners are the two registers of a lane; k == 64 here, every pair ascends
+				const uint32_t lo = min(k0, k1), hi = max(k0, k1);
+				k0 = lo; k1 = hi;
+			} else {
+				const uint32_t o0 = __shfl_xor_sync(0xffffffffu, k0, j), o1 = __shfl_xor_sync(0xffffffffu, k1, j);
+				const bool lower = (lane & j) == 0;
+				const bool up0 = (lane & k) == 0 || k == 64, up1 = ((lane + 32) & k) == 0; // direction of the block each element belongs to
+				k0 = (up0 == lower) ? min(k0, o0) : max(k0, o0);
+				k1 = (up1 == lower) ? min(k1, o1) : max(k1, o1);
+			}
+		}
+	}
+}
+
 template <bool DEPTH_ONLY>
 __global__ void __launch_bounds__(RASTER_WARPS * 32, RASTER_MIN_BLOCKS) raster_kernel(FrameDev frame, TexTable textures) {
 	__shared__ __align__(16) Rec sRecAll[RASTER_WARPS][32];
+	__shared__ uint32_t sKeysAll[RASTER_WARPS][LOCAL_SORT]; // the tile's command list in submission order (lists up to LOCAL_SORT entries)
 	__shared__ __align__(16) uint32_t sMaskAll[RASTER_WARPS][32]; // per (row pair, command): which of the 16 quads of the row pair the command may touch
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	Rec *sRec = sRecAll[warp];
@@ -1238,19 +1282,26 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32, RASTER_MIN_BLOCKS) raster_k
 	}
 	bool dirty = clear;
 
-	// lists of up to 32 entries are sorted here; longer ones were sorted by sort_lists_kernel
-	uint32_t sortedKey = 0xFFFFFFFFu;
-	if (n <= 32u) {
-		sortedKey = (uint32_t)lane < n ? __ldg(list + lane) : 0xFFFFFFFFu;
+	// lists of up to LOCAL_SORT entries are sorted here and kept in shared memory; longer ones were sorted by sort_lists_kernel
+	uint32_t *sKeys = sKeysAll[warp];
+	const bool localSort = n <= (uint32_t)LOCAL_SORT;
+	if (localSort) {
+		uint32_t k0 = (uint32_t)lane < n ? __ldg(list + lane) : 0xFFFFFFFFu;
+		uint32_t k1 = (uint32_t)lane + 32u < n ? __ldg(list + 32 + lane) : 0xFFFFFFFFu;
 		if (n > 1u) {
 			// the set-up pass fills lists roughly in command order: most short lists arrive sorted
-			const uint32_t previous = __shfl_up_sync(0xffffffffu, sortedKey, 1);
-			if (__any_sync(0xffffffffu, lane > 0 && previous > sortedKey)) {
-				if (n <= 8u) { sortedKey = warp_sort<8>(sortedKey, lane); }
-				else if (n <= 16u) { sortedKey = warp_sort<16>(sortedKey, lane); }
-				else { sortedKey = warp_sort<32>(sortedKey, lane); }
+			const uint32_t previous0 = __shfl_up_sync(0xffffffffu, k0, 1), last0 = __shfl_sync(0xffffffffu, k0, 31);
+			uint32_t previous1 = __shfl_up_sync(0xffffffffu, k1, 1);
+			if (lane == 0) { previous1 = last0; }
+			if (__any_sync(0xffffffffu, (lane > 0 && previous0 > k0) || previous1 > k1)) {
+				if (n <= 8u) { k0 = warp_sort<8>(k0, lane); }
+				else if (n <= 16u) { k0 = warp_sort<16>(k0, lane); }
+				else if (n <= 32u) { k0 = warp_sort<32>(k0, lane); }
+				else { warp_sort64(k0, k1, lane); }
 			}
 		}
+		sKeys[lane] = k0; sKeys[lane + 32] = k1;
+		__syncwarp();
 	}
 
 	for (uint32_t batchStart = 0; batchStart < n; batchStart += BATCH) {
@@ -1258,7 +1309,7 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32, RASTER_MIN_BLOCKS) raster_k
 		// ---- lane (c, r): checkpoint of command c for row pair r of this tile
 		const uint32_t c = (uint32_t)lane & 15u, r = (uint32_t)lane >> 4;
 		uint32_t key;
-		if (n <= 32u) { key = __shfl_sync(0xffffffffu, sortedKey, (int)(batchStart + c) & 31); }
+		if (localSort) { key = sKeys[(batchStart + c) & (uint32_t)(LOCAL_SORT - 1)]; }
 		else { key = c < batchCount ? __ldg(list + batchStart + c) : 0u; }
 		{
 			Rec rec;
@@ -1813,7 +1864,7 @@ static int renderer_end_internal(dfpsr_renderer *r, cudaStream_t stream) {
 			}
 			DFPSR_LAUNCH(setup_kernel<true>, blockTotal, SETUP_THREADS, 0, stream, frame);
 			if (unitTotal > 0) { DFPSR_LAUNCH(big_units_kernel, (unitTotal + 255) / 256, 256, 0, stream, frame, unitTotal); }
-			if (maxTile > 32u) {
+			if (maxTile > (uint32_t)LOCAL_SORT) {
 				if (maxTile > (uint32_t)SORT_SMEM) {
 					if (r->sortTmp.reserve((size_t)entryTotal * 4 + 16)) { return 1; }
 					frame.sortTmp = (uint32_t *)r->sortTmp.ptr;

@@ -192,7 +192,7 @@ def cpu_baseline(views, seconds=12.0):
 def main():
     parser = argparse.ArgumentParser()
     parser.add_argument("--gpus", type=int, default=1)
-    parser.add_argument("--steps", type=int, default=5)
+    parser.add_argument("--steps", type=int, default=20)
     parser.add_argument("--warmup", type=int, default=3)
     parser.add_argument("--impl", default="ours", choices=["ours", "reference"])
     parser.add_argument("--views", type=int, default=256, help="views per step per GPU")

@@ -400,3 +400,37 @@ def test_occlusion_grid_matches_oracle(cuda, oracle, variant):
     assert got["commands"] == expected["commands"]
     assert_same_u32(bits(got["depth"]), bits(expected["depth"]), "depth")
     assert_same_u32(got["color"], expected["color"], "colour")
+
+
+def edge_scenes():
+    """Degenerate inputs: (name, points, polygons). Shared with the CPU test that pins the oracle to the reference on the same cases."""
+    F = np.float32
+    poly = lambda rows: np.array([(r, np.zeros((4, 4), F), np.ones((4, 4), F)) for r in rows], abi.POLYGON_DTYPE)
+    rng = np.random.default_rng(77)
+    out = []
+    out.append(("no polygons", np.zeros((3, 3), F), poly([])))
+    out.append(("everything behind the camera", np.array([[0, 0, -5], [1, 0, -5], [0, 1, -6]], F), poly([(0, 1, 2, -1)])))
+    out.append(("zero-area triangles", np.array([[0, 0, 3], [1, 1, 3], [2, 2, 3], [0.5, 0.5, 3]], F), poly([(0, 1, 2, -1), (0, 0, 0, -1), (3, 3, 1, -1)])))
+    out.append(("one triangle covering the whole target and far beyond", np.array([[-900, -900, 2], [900, -900, 2], [0, 1500, 2]], F), poly([(0, 2, 1, -1), (0, 1, 2, -1)])))
+    out.append(("huge and non-finite coordinates", np.array([[1e30, 0, 5], [0, 1e30, 5], [-1e30, -1e30, 5], [0, 0, 1e-30], [np.inf, 1, 2], [np.nan, 0, 3], [0, 0, 2], [1, 0, 2], [0, 1, 2]], F),
+                poly([(0, 1, 2, -1), (3, 6, 7, -1), (4, 7, 8, -1), (5, 6, 8, -1), (6, 8, 7, -1)])))
+    pts = (rng.random((40, 3)) * 2 - 1).astype(F) * np.array([0.02, 0.02, 0.0], F) + np.array([0, 0, 1.5], F)
+    out.append(("sub-pixel triangles", pts, poly([(i, i + 1, i + 2, -1) for i in range(0, 36, 3)] + [(i + 2, i + 1, i, -1) for i in range(0, 36, 3)])))
+    quad_pts = np.array([[-1, -1, 2], [1, -1, 2], [1, 1, 2.5], [-1, 1, 2.5], [-1, -1, 2], [1, -1, 2], [1, 1, 2.5], [-1, 1, 2.5]], F)
+    out.append(("coincident quads: equal depth everywhere, the first one drawn wins", quad_pts, poly([(0, 3, 2, 1), (4, 7, 6, 5)])))
+    out[-1][2]["colors"][1, :, :3] = 0.25
+    return out
+
+
+@pytest.mark.parametrize("size", [(1, 1), (2, 2), (3, 5), (31, 4), (33, 9), (640, 3)])
+def test_degenerate_inputs_and_tiny_targets(cuda, oracle, size):
+    """Empty models, culled and degenerate triangles, non-finite coordinates, coincident surfaces, on targets smaller than one tile."""
+    w, h = size
+    cam = abi.camera_params(True, scenes.look_at_transform((0, 0, 0), (0, 0, 1)), w, h)
+    for name, points, polygons in edge_scenes():
+        scene = CudaScene(points, polygons)
+        c0, d0 = np.full((h, w), 0x11223344, np.uint32), np.zeros((h, w), np.float32)
+        got_c, got_d = scene.render_cuda(cuda, cam, c0, d0)
+        exp_c, exp_d, _ = scene.render_oracle(oracle, cam, c0, d0)
+        assert_same_u32(bits(got_d), bits(exp_d), f"depth ({name}, {w}x{h})")
+        assert_same_u32(got_c, exp_c, f"colour ({name}, {w}x{h})")

@@ -325,3 +325,25 @@ def test_occlusion_grid_bit_exact(ref_scalar, oracle, variant):
         assert got["occluded"] > 0  # triangles of models that passed the box test are still culled one by one at renderer_end
     assert np.array_equal(bits(expected["depth"]), bits(got["depth"]))
     assert np.array_equal(expected["color"], got["color"])
+
+
+@pytest.mark.parametrize("size", [(1, 1), (3, 5), (33, 9), (640, 3)])
+def test_degenerate_inputs_match_reference(oracle, ref_scalar, size):
+    """The edge cases of tests/test_gpu_raster.py::test_degenerate_inputs_and_tiny_targets, oracle against the compiled reference."""
+    import ctypes as C
+    from test_gpu_raster import edge_scenes
+    w, h = size
+    params = abi.camera_params(True, scenes.look_at_transform((0, 0, 0), (0, 0, 1)), w, h)
+    for name, points, polygons in edge_scenes():
+        c0, d0 = np.full((h, w), 0x11223344, np.uint32), np.zeros((h, w), np.float32)
+        model, _keep = orcbind.model_of(points, polygons)
+        c, d = c0.copy(), d0.copy()
+        ident = abi.Transform3D.identity()
+        oracle.orc_model_render(C.byref(model), C.byref(ident), C.byref(orcbind.image_of(c)), C.byref(orcbind.image_of(d)), C.byref(orcbind.camera(params)))
+        rc, rd = ref_scalar.rgba(c0), ref_scalar.f32(d0)
+        cam = abi.Camera.from_buffer_copy(params)
+        ref_scalar.lib.ref_camera_fill(C.byref(cam))
+        ref_scalar.render(ref_scalar.model(points, polygons), cam, rc, rd, mode=0)
+        assert np.array_equal(ref_scalar.read_f32(rd).view(np.uint32), d.view(np.uint32)), (name, size)
+        assert np.array_equal(ref_scalar.read_rgba(rc), c), (name, size)
+        ref_scalar.free_all()

@@ -635,7 +635,7 @@ __global__ void __launch_bounds__(SETUP_THREADS) setup_kernel(FrameDev frame) {
 	__shared__ TaskParams task;
 	__shared__ uint32_t warpCmds[SETUP_THREADS / 32], warpRows[SETUP_THREADS / 32];
 	__shared__ BigItem sBig[SETUP_THREADS];
-	__shared__ uint32_t sBigCount, sChkCount, sUnitCount, sItemBase, sUnitBase;
+	__shared__ uint32_t sBigCount, sChkCount, sUnitCount, sItemBase, sUnitBase, sChkBase;
 	__shared__ uint32_t sUnitEnd[SETUP_THREADS]; // emit pass: inclusive prefix of tile rows over the queued commands
 	{
 		if (threadIdx.x == 0) { sChkCount = 0; sUnitCount = 0; }
@@ -743,7 +743,10 @@ __global__ void __launch_bounds__(SETUP_THREADS) setup_kernel(FrameDev frame) {
 						it.chkOffset = CHK_NONE;
 #ifndef DFPSR_NO_CHK
 						if (!task.depthOnly) {
-							it.chkOffset = atomicAdd(&frame.totals[5], (uint32_t)((rowCount / 2) * (tx1 - tx0 + 1)));
+							// position inside the block's share of the checkpoint pool; the block reserves its share with ONE global atomic
+							// after the barrier below and patches the command records (one cursor bumped by every large command of a
+							// frame is a serial chain of same-address atomics)
+							it.chkOffset = atomicAdd(&sChkCount, (uint32_t)((rowCount / 2) * (tx1 - tx0 + 1)));
 							cmd.chkOffset = it.chkOffset;
 							cmd.chkShape = (uint32_t)tx0 | ((uint32_t)(tx1 - tx0 + 1) << 16);
 						}
@@ -810,11 +813,15 @@ __global__ void __launch_bounds__(SETUP_THREADS) setup_kernel(FrameDev frame) {
 		__syncthreads();
 		const uint32_t unitTotal = bigCount > 0 ? sUnitEnd[bigCount - 1] : 0u;
 		// the block reserves its share of the frame-wide queues with one atomic each; big_units_kernel then gives every unit its own thread
-		if (threadIdx.x == 0 && bigCount > 0) { sItemBase = atomicAdd(&frame.totals[8], bigCount); sUnitBase = atomicAdd(&frame.totals[9], unitTotal); }
+		if (threadIdx.x == 0 && bigCount > 0) {
+			sItemBase = atomicAdd(&frame.totals[8], bigCount); sUnitBase = atomicAdd(&frame.totals[9], unitTotal);
+			sChkBase = sChkCount > 0 ? atomicAdd(&frame.totals[5], sChkCount) : 0u;
+		}
 		__syncthreads();
 		if (threadIdx.x < bigCount) {
 			BigItem it = sBig[threadIdx.x];
 			it.unitStart = sUnitBase + (threadIdx.x > 0 ? sUnitEnd[threadIdx.x - 1] : 0u);
+			if (it.chkOffset != CHK_NONE) { it.chkOffset += sChkBase; frame.cmds[it.cmdIndex].chkOffset = it.chkOffset; }
 			frame.bigItems[sItemBase + threadIdx.x] = it;
 		}
 		for (uint32_t u = threadIdx.x; u < unitTotal; u += SETUP_THREADS) {
@@ -925,12 +932,20 @@ __global__ void __launch_bounds__(1024) scan_blocks_kernel(FrameDev frame) {
 	for (int32_t base = 0; base < frame.blockCount; base += 1024 * SCAN_ITEMS) {
 		const int32_t first = base + (int32_t)threadIdx.x * SCAN_ITEMS;
 		uint32_t v[2][SCAN_ITEMS], total[2] = {0u, 0u};
+		if (first + SCAN_ITEMS <= frame.blockCount) { // 32 consecutive bytes per thread and array: two 16-byte loads, a warp reads 1 KB contiguously
+			const uint4 a0 = *(const uint4 *)(frame.blockCmds + first), a1 = *(const uint4 *)(frame.blockCmds + first + 4);
+			const uint4 b0 = *(const uint4 *)(frame.blockRows + first), b1 = *(const uint4 *)(frame.blockRows + first + 4);
+			v[0][0] = a0.x; v[0][1] = a0.y; v[0][2] = a0.z; v[0][3] = a0.w; v[0][4] = a1.x; v[0][5] = a1.y; v[0][6] = a1.z; v[0][7] = a1.w;
+			v[1][0] = b0.x; v[1][1] = b0.y; v[1][2] = b0.z; v[1][3] = b0.w; v[1][4] = b1.x; v[1][5] = b1.y; v[1][6] = b1.z; v[1][7] = b1.w;
+		} else {
 #pragma unroll
-		for (int e = 0; e < SCAN_ITEMS; e++) {
-			const bool valid = first + e < frame.blockCount;
-			v[0][e] = valid ? frame.blockCmds[first + e] : 0u; v[1][e] = valid ? frame.blockRows[first + e] : 0u;
-			total[0] += v[0][e]; total[1] += v[1][e];
+			for (int e = 0; e < SCAN_ITEMS; e++) {
+				const bool valid = first + e < frame.blockCount;
+				v[0][e] = valid ? frame.blockCmds[first + e] : 0u; v[1][e] = valid ? frame.blockRows[first + e] : 0u;
+			}
 		}
+#pragma unroll
+		for (int e = 0; e < SCAN_ITEMS; e++) { total[0] += v[0][e]; total[1] += v[1][e]; }
 		uint32_t inc[2] = {total[0], total[1]};
 #pragma unroll
 		for (int d = 1; d < 32; d <<= 1) {
@@ -958,10 +973,15 @@ __global__ void __launch_bounds__(1024) scan_blocks_kernel(FrameDev frame) {
 		uint32_t running[2];
 #pragma unroll
 		for (int k = 0; k < 2; k++) { running[k] = carry[k] + (warp > 0 ? warpSum[k][warp - 1] : 0u) + inc[k] - total[k]; }
+		uint32_t out[2][SCAN_ITEMS];
 #pragma unroll
-		for (int e = 0; e < SCAN_ITEMS; e++) {
-			if (first + e < frame.blockCount) { frame.blockCmds[first + e] = running[0]; frame.blockRows[first + e] = running[1]; }
-			running[0] += v[0][e]; running[1] += v[1][e];
+		for (int e = 0; e < SCAN_ITEMS; e++) { out[0][e] = running[0]; out[1][e] = running[1]; running[0] += v[0][e]; running[1] += v[1][e]; }
+		if (first + SCAN_ITEMS <= frame.blockCount) {
+			*(uint4 *)(frame.blockCmds + first) = make_uint4(out[0][0], out[0][1], out[0][2], out[0][3]); *(uint4 *)(frame.blockCmds + first + 4) = make_uint4(out[0][4], out[0][5], out[0][6], out[0][7]);
+			*(uint4 *)(frame.blockRows + first) = make_uint4(out[1][0], out[1][1], out[1][2], out[1][3]); *(uint4 *)(frame.blockRows + first + 4) = make_uint4(out[1][4], out[1][5], out[1][6], out[1][7]);
+		} else {
+#pragma unroll
+			for (int e = 0; e < SCAN_ITEMS; e++) { if (first + e < frame.blockCount) { frame.blockCmds[first + e] = out[0][e]; frame.blockRows[first + e] = out[1][e]; } }
 		}
 		__syncthreads();
 		if (threadIdx.x == 0) { for (int k = 0; k < 2; k++) { carry[k] += warpSum[k][31]; } }

@@ -11,6 +11,7 @@ PACK_RGBA, PACK_BGRA, PACK_ARGB, PACK_ABGR = 0, 1, 2, 3
 FILTER_SOLID, FILTER_ALPHA = 0, 1
 SAMPLER_NEAREST, SAMPLER_LINEAR = 0, 1
 MAP_XOR_PATTERN, MAP_AFFINE, MAP_CONSTANT = 0, 1, 2
+FORMAT_U8, FORMAT_U16, FORMAT_F32, FORMAT_RGBA_U8 = 1, 2, 3, 4
 
 
 class Transform3D(C.Structure):

@@ -74,6 +74,10 @@ SIGNATURES = {
     "dfpsr_draw_max_alpha": (i32, [P(abi.Image), P(abi.Image), i32, i32, i32, vp]),
     "dfpsr_draw_alpha_clip": (i32, [P(abi.Image), P(abi.Image), i32, i32, i32, vp]),
     "dfpsr_draw_silhouette": (i32, [P(abi.Image), P(abi.Image), vp, i32, i32, vp]),
+    "dfpsr_draw_rectangle_mono": (i32, [P(abi.Image), i32, i32, i32, i32, i32, i32, vp]),
+    "dfpsr_draw_line_mono": (i32, [P(abi.Image), i32, i32, i32, i32, i32, i32, vp]),
+    "dfpsr_draw_copy_formats": (i32, [P(abi.Image), i32, P(abi.Image), i32, i32, i32, vp]),
+    "dfpsr_draw_higher_u16": (i32, [P(abi.Image)] * 6 + [i32, i32, i32, vp]),
     "dfpsr_light_directed": (i32, [P(abi.OrthoView), P(abi.Image), P(abi.Image), vp, f32, vp, i32, vp]),
     "dfpsr_light_point": (i32, [P(abi.OrthoView), vp, P(abi.Image), P(abi.Image), P(abi.Image), vp, f32, f32, vp, P(abi.Image), vp]),
     "dfpsr_light_frame": (i32, [P(abi.OrthoView), vp, P(abi.Image), P(abi.Image), P(abi.Image), P(abi.Image), P(abi.Image), vp, i32, vp, i32, vp]),

@@ -264,6 +264,17 @@ int dfpsr_draw_max_alpha(const dfpsr_image *target, const dfpsr_image *source, i
 int dfpsr_draw_alpha_clip(const dfpsr_image *target, const dfpsr_image *source, int32_t left, int32_t top, int32_t threshold, void *stream);
 int dfpsr_draw_silhouette(const dfpsr_image *target, const dfpsr_image *silhouetteU8, const int32_t colorRgba[4], int32_t left, int32_t top, void *stream);
 
+/* 8-bit and 16-bit monochrome images and the conversions between formats (ref: api/drawAPI.h:68-103, :128-135): the descriptor is the
+ * same dfpsr_image (stride in bytes, packOrder ignored for monochrome); the pixel format is passed next to it. */
+enum { DFPSR_FORMAT_U8 = 1, DFPSR_FORMAT_U16 = 2, DFPSR_FORMAT_F32 = 3, DFPSR_FORMAT_RGBA_U8 = 4 };
+int dfpsr_draw_rectangle_mono(const dfpsr_image *image, int32_t format, int32_t left, int32_t top, int32_t width, int32_t height, int32_t color, void *stream);
+int dfpsr_draw_line_mono(const dfpsr_image *image, int32_t format, int32_t x1, int32_t y1, int32_t x2, int32_t y2, int32_t color, void *stream);
+/* All thirteen draw_copy overloads (ref: api/drawAPI.cpp:497-634), including their conversions as the reference performs them: luma
+ * replicated with alpha 255 into RGBA, saturateFloat rounding for F32 -> 8 bits, U16 clamped to 255 on its way to U8 / F32 / RGBA. */
+int dfpsr_draw_copy_formats(const dfpsr_image *target, int32_t targetFormat, const dfpsr_image *source, int32_t sourceFormat, int32_t left, int32_t top, void *stream);
+/* ref: api/drawAPI.cpp:759-832 draw_higher on 16-bit heights (0 = empty) with 0, 1 or 2 RGBA payload images. */
+int dfpsr_draw_higher_u16(const dfpsr_image *targetHeight, const dfpsr_image *sourceHeight, const dfpsr_image *targetA, const dfpsr_image *sourceA, const dfpsr_image *targetB, const dfpsr_image *sourceB, int32_t left, int32_t top, int32_t sourceHeightOffset, void *stream);
+
 /* One sprite placement for the batched compositor: sources live in an atlas on the device. */
 typedef struct dfpsr_sprite_draw {
 	dfpsr_image sourceHeight, sourceA, sourceB;

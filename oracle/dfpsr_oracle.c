@@ -1397,6 +1397,94 @@ void orc_draw_silhouette(const dfpsr_image *target, const dfpsr_image *silhouett
 	}
 }
 
+/* ---- 8-bit / 16-bit monochrome images and conversions between formats (api/drawAPI.cpp:130-150, :284-297, :476-486, :519-634, :759-832) */
+
+static uint8_t *u8_px(const dfpsr_image *im, int32_t x, int32_t y) { return (uint8_t*)im->data + (size_t)y * im->stride + x; }
+static uint16_t *u16_px(const dfpsr_image *im, int32_t x, int32_t y) { return (uint16_t*)((uint8_t*)im->data + (size_t)y * im->stride) + x; }
+static void mono_write(const dfpsr_image *im, int32_t format, int64_t x, int64_t y, uint32_t value) {
+	if (x < 0 || x >= im->width || y < 0 || y >= im->height) { return; }
+	if (format == DFPSR_FORMAT_U8) { *u8_px(im, (int32_t)x, (int32_t)y) = (uint8_t)value; } else { *u16_px(im, (int32_t)x, (int32_t)y) = (uint16_t)value; }
+}
+static uint32_t mono_color(int32_t format, int32_t color) { int32_t top = format == DFPSR_FORMAT_U8 ? 255 : 65535; return (uint32_t)(color < 0 ? 0 : (color > top ? top : color)); }
+void orc_draw_rectangle_mono(const dfpsr_image *image, int32_t format, int32_t left, int32_t top, int32_t width, int32_t height, int32_t color) {
+	if (image == NULL || image->data == NULL) { return; }
+	int64_t right = (int64_t)left + width, bottom = (int64_t)top + height;
+	int32_t l = left > 0 ? left : 0, t = top > 0 ? top : 0;
+	int32_t r = right < image->width ? (int32_t)right : image->width, b = bottom < image->height ? (int32_t)bottom : image->height;
+	uint32_t value = mono_color(format, color);
+	/* api/drawAPI.cpp:136-146: a 16-bit colour whose two bytes are equal takes the memset path, which is handed 0 instead of the byte */
+	if (format == DFPSR_FORMAT_U16 && (value & 0xFFu) == (value >> 8)) { value = 0u; }
+	for (int32_t y = t; y < b; y++) { for (int32_t x = l; x < r; x++) { mono_write(image, format, x, y, value); } }
+}
+void orc_draw_line_mono(const dfpsr_image *image, int32_t format, int32_t x1, int32_t y1, int32_t x2, int32_t y2, int32_t color) {
+	/* the same walk as line_u32 with a narrower store: drawn into a 32-bit scratch image of the same size, then copied where it was touched */
+	if (image == NULL || image->data == NULL) { return; }
+	dfpsr_image scratch = *image;
+	uint32_t *mask = (uint32_t*)calloc((size_t)image->width * image->height, 4);
+	scratch.data = mask; scratch.stride = image->width * 4;
+	line_u32(&scratch, x1, y1, x2, y2, 0xFFFFFFFFu);
+	for (int32_t y = 0; y < image->height; y++) { for (int32_t x = 0; x < image->width; x++) { if (mask[(size_t)y * image->width + x]) { mono_write(image, format, x, y, mono_color(format, color)); } } }
+	free(mask);
+}
+static int32_t saturate_float(float value) { /* api/drawAPI.cpp:476-486 */
+	if (!(value >= 0.5f)) { return 0; }
+	if (value > 254.5f) { return 255; }
+	return (uint8_t)(value + 0.5f);
+}
+static size_t format_size(int32_t format) { return format == DFPSR_FORMAT_U8 ? 1 : (format == DFPSR_FORMAT_U16 ? 2 : 4); }
+void orc_draw_copy_formats(const dfpsr_image *target, int32_t targetFormat, const dfpsr_image *source, int32_t sourceFormat, int32_t left, int32_t top) {
+	intersection is;
+	if (target == NULL || source == NULL || target->data == NULL || source->data == NULL) { return; }
+	if (targetFormat == DFPSR_FORMAT_RGBA_U8 && sourceFormat == DFPSR_FORMAT_RGBA_U8) { orc_draw_copy_rgba(target, source, left, top); return; }
+	if (!intersect(target, source, left, top, &is)) { return; }
+	for (int32_t y = 0; y < is.h; y++) {
+		for (int32_t x = 0; x < is.w; x++) {
+			const uint8_t *sp = (const uint8_t*)source->data + (size_t)(is.sy + y) * source->stride + (size_t)(is.sx + x) * format_size(sourceFormat);
+			uint8_t *tp = (uint8_t*)target->data + (size_t)(is.ty + y) * target->stride + (size_t)(is.tx + x) * format_size(targetFormat);
+			if (targetFormat == sourceFormat) { memcpy(tp, sp, format_size(targetFormat)); continue; }
+			if (targetFormat == DFPSR_FORMAT_RGBA_U8) {
+				int32_t luma;
+				if (sourceFormat == DFPSR_FORMAT_U8) { luma = *sp; }
+				else if (sourceFormat == DFPSR_FORMAT_U16) { luma = *(const uint16_t*)sp; if (luma > 255) { luma = 255; } }
+				else { luma = saturate_float(*(const float*)sp); }
+				*(uint32_t*)tp = pack_bytes_ordered((uint32_t)luma, (uint32_t)luma, (uint32_t)luma, 255u, target->packOrder);
+			} else if (targetFormat == DFPSR_FORMAT_U8) {
+				if (sourceFormat == DFPSR_FORMAT_F32) { *tp = (uint8_t)saturate_float(*(const float*)sp); }
+				else { int32_t luma = *(const uint16_t*)sp; if (luma > 255) { luma = 255; } *tp = (uint8_t)luma; }
+			} else if (targetFormat == DFPSR_FORMAT_U16) {
+				/* from F32 the reference stores *sourcePixel, the first byte of the float (:603-614) */
+				*(uint16_t*)tp = *sp;
+			} else {
+				if (sourceFormat == DFPSR_FORMAT_U8) { *(float*)tp = (float)*sp; }
+				else { int32_t luma = *(const uint16_t*)sp; if (luma > 255) { luma = 255; } *(float*)tp = (float)luma; }
+			}
+		}
+	}
+}
+void orc_draw_higher_u16(const dfpsr_image *targetHeight, const dfpsr_image *sourceHeight, const dfpsr_image *targetA, const dfpsr_image *sourceA, const dfpsr_image *targetB, const dfpsr_image *sourceB, int32_t left, int32_t top, int32_t offset) {
+	intersection is;
+	if (targetHeight == NULL || sourceHeight == NULL || targetHeight->data == NULL || sourceHeight->data == NULL) { return; }
+	if (!intersect(targetHeight, sourceHeight, left, top, &is)) { return; }
+	int hasA = targetA != NULL && targetA->data != NULL && sourceA != NULL && sourceA->data != NULL;
+	int hasB = targetB != NULL && targetB->data != NULL && sourceB != NULL && sourceB->data != NULL;
+	for (int32_t y = 0; y < is.h; y++) {
+		for (int32_t x = 0; x < is.w; x++) {
+			int32_t newHeight = *u16_px(sourceHeight, is.sx + x, is.sy + y);
+			if (newHeight > 0) {
+				newHeight += offset;
+				if (newHeight < 0) { newHeight = 0; }
+				if (newHeight > 65535) { newHeight = 65535; }
+				uint16_t *t = u16_px(targetHeight, is.tx + x, is.ty + y);
+				if (newHeight > 0 && newHeight > *t) {
+					*t = (uint16_t)newHeight;
+					if (hasA) { *color_px(targetA, is.tx + x, is.ty + y) = repack(*color_px(sourceA, is.sx + x, is.sy + y), sourceA->packOrder, targetA->packOrder); }
+					if (hasB) { *color_px(targetB, is.tx + x, is.ty + y) = repack(*color_px(sourceB, is.sx + x, is.sy + y), sourceB->packOrder, targetB->packOrder); }
+				}
+			}
+		}
+	}
+}
+
 /* ------------------------------------------------------------------------------------------- Sandbox dense models and sprite heights */
 
 /* The reference converts with cvttss2si; (uint32_t)float goes through the 64-bit conversion on x86-64. */

@@ -71,6 +71,12 @@ void orc_draw_max_alpha(const dfpsr_image *target, const dfpsr_image *source, in
 void orc_draw_alpha_clip(const dfpsr_image *target, const dfpsr_image *source, int32_t left, int32_t top, int32_t threshold);
 void orc_draw_silhouette(const dfpsr_image *target, const dfpsr_image *silhouetteU8, const int32_t *colorRgba, int32_t left, int32_t top);
 
+/* 8-bit / 16-bit monochrome images, the mixed-format draw_copy overloads and draw_higher on 16-bit heights (api/drawAPI.cpp:130-150, :284-297, :519-634, :759-832). */
+void orc_draw_rectangle_mono(const dfpsr_image *image, int32_t format, int32_t left, int32_t top, int32_t width, int32_t height, int32_t color);
+void orc_draw_line_mono(const dfpsr_image *image, int32_t format, int32_t x1, int32_t y1, int32_t x2, int32_t y2, int32_t color);
+void orc_draw_copy_formats(const dfpsr_image *target, int32_t targetFormat, const dfpsr_image *source, int32_t sourceFormat, int32_t left, int32_t top);
+void orc_draw_higher_u16(const dfpsr_image *targetHeight, const dfpsr_image *sourceHeight, const dfpsr_image *targetA, const dfpsr_image *sourceA, const dfpsr_image *targetB, const dfpsr_image *sourceB, int32_t left, int32_t top, int32_t offset);
+
 /* renderDenseModel<HIGH_QUALITY> (SDK/SpriteEngine/spriteAPI.cpp:1243-1327); dirtyRect = {left, top, width, height} or zeros when culled. */
 void orc_dense_model_render(const dfpsr_dense_triangle *triangles, int32_t triangleCount, const float *minBound, const float *maxBound, const dfpsr_ortho_camera *view,
                             const dfpsr_image *height, const dfpsr_image *diffuse, const dfpsr_image *normal, const float *worldOrigin, const dfpsr_transform3d *modelToWorld,

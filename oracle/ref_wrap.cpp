@@ -55,6 +55,7 @@ struct AnyImage {
 	ImageF32 f32;
 	AlignedImageF32 f32Aligned; // only for whole images
 	ImageU8 u8;                 // kind 3
+	ImageU16 u16;               // kind 4
 };
 
 std::vector<AnyImage> g_images;
@@ -490,6 +491,50 @@ int ref_image_create_u8(int w, int h, const uint8_t *pixels) { // tight rows in
 	for (int y = 0; y < h; y++) { memcpy(image_getSafePointer<uint8_t>(img.u8, y).getUnsafe(), pixels + (size_t)y * w, (size_t)w); }
 	g_images.push_back(img);
 	return (int)g_images.size() - 1;
+}
+int ref_image_create_u16(int w, int h, const uint16_t *pixels) { // tight rows in
+	ensureStarted();
+	AnyImage img;
+	img.kind = 4;
+	img.u16 = image_create_U16(w, h);
+	for (int y = 0; y < h; y++) { memcpy(image_getSafePointer<uint16_t>(img.u16, y).getUnsafe(), pixels + (size_t)y * w, (size_t)w * 2); }
+	g_images.push_back(img);
+	return (int)g_images.size() - 1;
+}
+void ref_image_read_mono(int id, void *dst) { // tight rows out, 1 or 2 bytes per pixel
+	const AnyImage &img = g_images[id];
+	if (img.kind == 3) { int w = image_getWidth(img.u8); for (int y = 0; y < image_getHeight(img.u8); y++) { memcpy((uint8_t*)dst + (size_t)y * w, image_getSafePointer<uint8_t>(img.u8, y).getUnsafe(), (size_t)w); } }
+	else { int w = image_getWidth(img.u16); for (int y = 0; y < image_getHeight(img.u16); y++) { memcpy((uint16_t*)dst + (size_t)y * w, image_getSafePointer<uint16_t>(img.u16, y).getUnsafe(), (size_t)w * 2); } }
+}
+void ref_draw_rectangle_mono(int image, int left, int top, int width, int height, int color) {
+	if (g_images[image].kind == 3) { draw_rectangle(g_images[image].u8, IRect(left, top, width, height), color); } else { draw_rectangle(g_images[image].u16, IRect(left, top, width, height), color); }
+}
+void ref_draw_line_mono(int image, int x1, int y1, int x2, int y2, int color) {
+	if (g_images[image].kind == 3) { draw_line(g_images[image].u8, x1, y1, x2, y2, color); } else { draw_line(g_images[image].u16, x1, y1, x2, y2, color); }
+}
+// every draw_copy overload of api/drawAPI.h:91-103, selected by the kinds of the two images (1 RGBA, 2 F32, 3 U8, 4 U16)
+void ref_draw_copy_formats(int target, int source, int left, int top) {
+	const AnyImage &t = g_images[target], &s = g_images[source];
+	switch (t.kind * 10 + s.kind) {
+		case 11: draw_copy(t.rgba, s.rgba, left, top); break; case 13: draw_copy(t.rgba, s.u8, left, top); break;
+		case 14: draw_copy(t.rgba, s.u16, left, top); break;  case 12: draw_copy(t.rgba, s.f32, left, top); break;
+		case 33: draw_copy(t.u8, s.u8, left, top); break;     case 32: draw_copy(t.u8, s.f32, left, top); break;
+		case 34: draw_copy(t.u8, s.u16, left, top); break;    case 44: draw_copy(t.u16, s.u16, left, top); break;
+		case 43: draw_copy(t.u16, s.u8, left, top); break;    case 42: draw_copy(t.u16, s.f32, left, top); break;
+		case 22: draw_copy(t.f32, s.f32, left, top); break;   case 23: draw_copy(t.f32, s.u8, left, top); break;
+		case 24: draw_copy(t.f32, s.u16, left, top); break;
+	}
+}
+void ref_draw_higher_u16(int targetH, int sourceH, int targetA, int sourceA, int targetB, int sourceB, int left, int top, int offset) {
+	if (targetA < 0) {
+		// like the F32 case above: the height-only overload is declared (drawAPI.h:124) with a signature its definition (drawAPI.cpp:946) does
+		// not match; throw-away payload images give the same heights (a clamped height of 0 can never exceed an unsigned target)
+		ImageRgbaU8 dummyTarget = image_create_RgbaU8(image_getWidth(g_images[targetH].u16), image_getHeight(g_images[targetH].u16));
+		ImageRgbaU8 dummySource = image_create_RgbaU8(image_getWidth(g_images[sourceH].u16), image_getHeight(g_images[sourceH].u16));
+		draw_higher(g_images[targetH].u16, g_images[sourceH].u16, dummyTarget, dummySource, left, top, offset);
+	}
+	else if (targetB < 0) { draw_higher(g_images[targetH].u16, g_images[sourceH].u16, g_images[targetA].rgba, g_images[sourceA].rgba, left, top, offset); }
+	else { draw_higher(g_images[targetH].u16, g_images[sourceH].u16, g_images[targetA].rgba, g_images[sourceA].rgba, g_images[targetB].rgba, g_images[sourceB].rgba, left, top, offset); }
 }
 void ref_draw_rectangle_rgba(int image, int left, int top, int width, int height, const int32_t *c) { draw_rectangle(g_images[image].rgba, IRect(left, top, width, height), ColorRgbaI32(c[0], c[1], c[2], c[3])); }
 void ref_draw_rectangle_f32(int image, int left, int top, int width, int height, float value) { draw_rectangle(g_images[image].f32, IRect(left, top, width, height), value); }

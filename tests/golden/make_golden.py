@@ -26,6 +26,7 @@ from dfpsr_b200 import abi, scenes  # noqa: E402
 import sandbox_scene  # noqa: E402
 import sprite_world_scene  # noqa: E402
 import draw_scene  # noqa: E402
+import mono_scene  # noqa: E402
 
 
 def sha(a):
@@ -97,7 +98,11 @@ def draw(ref):
         color, depth = draw_scene.run_reference(ref, draw_scene.build(*case))
         cases.append({"color_sha256": sha(color), "depth_sha256": sha(depth)})
         ref.free_all()
-    return {"cases": cases}
+    mono = []
+    for seed in mono_scene.SEEDS:
+        mono.append({"seed": seed, "sha256": mono_scene.sha(mono_scene.run_reference(ref, mono_scene.build(seed)))})
+        ref.free_all()
+    return {"cases": cases, "mono": mono}
 
 
 def sprite_world(ref):

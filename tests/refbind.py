@@ -53,6 +53,9 @@ def load(flavour="scalar"):
         "ref_filter_resize": (i, [i, i, i, i]), "ref_filter_map": (None, [i, i, p, i, i, i]),
         "ref_filter_block_magnify": (None, [i, i, i, i]),
         "ref_image_create_u8": (i, [i, i, p]),
+        "ref_image_create_u16": (i, [i, i, p]), "ref_image_read_mono": (None, [i, p]),
+        "ref_draw_rectangle_mono": (None, [i, i, i, i, i, i]), "ref_draw_line_mono": (None, [i, i, i, i, i, i]),
+        "ref_draw_copy_formats": (None, [i, i, i, i]), "ref_draw_higher_u16": (None, [i, i, i, i, i, i, i, i, i]),
         "ref_draw_rectangle_rgba": (None, [i, i, i, i, i, p]), "ref_draw_rectangle_f32": (None, [i, i, i, i, i, f]),
         "ref_draw_line_rgba": (None, [i, i, i, i, i, p]), "ref_draw_line_f32": (None, [i, i, i, i, i, f]),
         "ref_draw_alpha_filter": (None, [i, i, i, i]), "ref_draw_max_alpha": (None, [i, i, i, i, i]), "ref_draw_alpha_clip": (None, [i, i, i, i, i]),

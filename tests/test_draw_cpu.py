@@ -8,6 +8,7 @@ import numpy as np
 import pytest
 
 import draw_scene
+import mono_scene
 import orcbind
 from dfpsr_b200 import abi
 
@@ -84,3 +85,19 @@ def test_clipped_rectangle_and_lines_small_case(oracle):
     colour = np.zeros((2, 3), np.uint32)
     oracle.orc_draw_rectangle_rgba(C.byref(IM(colour)), 1, 0, 5, 1, np.array([300, -4, 16, 255], np.int32).ctypes.data)  # saturated like image_saturateAndPack
     assert colour.tolist() == [[0, 0xFF1000FF, 0xFF1000FF], [0, 0, 0]]
+
+
+@pytest.mark.parametrize("seed", mono_scene.SEEDS)
+def test_oracle_monochrome_and_mixed_format_draws_match_reference(oracle, ref_scalar, seed):
+    """draw_rectangle / draw_line on U8 and U16 images, all thirteen draw_copy overloads (with the reference's conversions, including its
+    U16 <- F32 overload that stores the float's first byte) and draw_higher on 16-bit heights with 0, 1 and 2 payloads."""
+    sc = mono_scene.build(seed)
+    expected, got = mono_scene.run_reference(ref_scalar, sc), mono_scene.run_oracle(oracle, sc)
+    assert mono_scene.same(got, expected)
+    assert not mono_scene.same(got, mono_scene.results_list(sc["targets"], sc["higher_target"]))  # something was drawn
+
+
+@pytest.mark.parametrize("seed", mono_scene.SEEDS)
+def test_oracle_monochrome_and_mixed_format_draws_match_golden(oracle, seed):
+    entry = json.load(open(GOLDEN))["mono"][mono_scene.SEEDS.index(seed)]
+    assert mono_scene.sha(mono_scene.run_oracle(oracle, mono_scene.build(seed))) == entry["sha256"]

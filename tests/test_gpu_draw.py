@@ -6,6 +6,7 @@ import numpy as np
 import pytest
 
 import draw_scene
+import mono_scene
 from dfpsr_b200 import lib
 
 pytestmark = pytest.mark.gpu
@@ -40,3 +41,12 @@ def test_long_lines_cross_a_large_image(cuda, oracle):
     torch.cuda.synchronize()
     assert np.array_equal(dev.cpu().numpy().view(np.uint32), host)
     assert (host != 0).sum() > 20000
+
+
+@pytest.mark.parametrize("seed", mono_scene.SEEDS)
+def test_monochrome_and_mixed_format_draws_bit_exact(cuda, oracle, seed):
+    sc = mono_scene.build(seed)
+    got = mono_scene.run_cuda(cuda, lib, sc)
+    assert mono_scene.same(got, mono_scene.run_oracle(oracle, sc))
+    entry = json.load(open(GOLDEN))["mono"][mono_scene.SEEDS.index(seed)]
+    assert mono_scene.sha(got) == entry["sha256"]

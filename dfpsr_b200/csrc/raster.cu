@@ -1140,10 +1140,12 @@ static const int MAX_TEXTURES = 64;
 struct TexTable { TexDev t[MAX_TEXTURES]; };
 
 // ref: api/textureAPI.h:253-263 weightColors on 16-bit lane pairs (sums never exceed 255 * 256, so lanes cannot carry)
+// Bytes 1 and 3 are moved into the 16-bit lanes, and the high bytes of the four lane sums are gathered, with one byte permute each
+// instead of shift + mask pairs: the integer ALU pipe is the busiest pipe of the tile kernel (ncu: 50 %), the multiplies run on the FMA pipe.
 __device__ __forceinline__ uint32_t weight_colors(uint32_t colorA, uint32_t weightA, uint32_t colorB, uint32_t weightB) {
 	uint32_t low = (colorA & 0x00FF00FFu) * weightA + (colorB & 0x00FF00FFu) * weightB;
-	uint32_t high = ((colorA >> 8) & 0x00FF00FFu) * weightA + ((colorB >> 8) & 0x00FF00FFu) * weightB;
-	return ((low >> 8) & 0x00FF00FFu) | (high & 0xFF00FF00u);
+	uint32_t high = __byte_perm(colorA, 0u, 0x4341) * weightA + __byte_perm(colorB, 0u, 0x4341) * weightB;
+	return __byte_perm(low, high, 0x7351); // ((low >> 8) & 0x00FF00FF) | (high & 0xFF00FF00)
 }
 
 // ref: api/textureAPI.h:342-438 texture_sample_bilinear<SQUARE=false, *, MIP_INSIDE=true, *>
@@ -1193,7 +1195,9 @@ __device__ __forceinline__ void sample_quad(const TexDev &t, bool highestResolut
 #pragma unroll
 	for (int l = 0; l < 4; l++) {
 		uint32_t c = sample_bilinear(t, u[l], v[l], mip);
-		float r = (float)(c & 255u), g = (float)((c >> 8) & 255u), b = (float)((c >> 16) & 255u), a = (float)(c >> 24);
+		// byte -> float without the conversion pipe: the byte becomes the low mantissa bits of 2^23, then 2^23 is subtracted (exact)
+		const float r = __uint_as_float(__byte_perm(c, 0x4B000000u, 0x7440)) - 8388608.0f, g = __uint_as_float(__byte_perm(c, 0x4B000000u, 0x7441)) - 8388608.0f;
+		const float b = __uint_as_float(__byte_perm(c, 0x4B000000u, 0x7442)) - 8388608.0f, a = __uint_as_float(__byte_perm(c, 0x4B000000u, 0x7443)) - 8388608.0f;
 		if (MULTIPLY) { rgba[l][0] = rgba[l][0] * r; rgba[l][1] = rgba[l][1] * g; rgba[l][2] = rgba[l][2] * b; rgba[l][3] = rgba[l][3] * a; }
 		else { rgba[l][0] = r; rgba[l][1] = g; rgba[l][2] = b; rgba[l][3] = a; }
 	}
@@ -1348,8 +1352,10 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32, RASTER_MIN_BLOCKS) raster_k
 		if (localSort) { key = sKeys[(batchStart + c) & (uint32_t)(LOCAL_SORT - 1)]; }
 		else { key = c < batchCount ? __ldg(list + batchStart + c) : 0u; }
 		{
-			Rec rec;
-			rec.mode = -1; rec.at = 0; rec.ul = rec.ur = rec.ll = rec.lr = 0;
+			// the record is written straight into shared memory (a local copy that is stored through a uint4 view lives on the stack)
+			Rec &rec = sRec[r * BATCH + c];
+			int32_t recMode = -1;
+			rec.at = 0; rec.ul = rec.ur = rec.ll = rec.lr = 0;
 			int32_t quadFirst = 0, quadEnd = 0; // quads [quadFirst, quadEnd) of this row pair can be touched
 			if (c < batchCount) {
 				const Cmd *cmd = frame.cmds + key;
@@ -1373,7 +1379,7 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32, RASTER_MIN_BLOCKS) raster_k
 						const bool hasU = rec.ur > rec.ul && rec.ur > tileLeft && rec.ul < tileLeft + TILE_W;
 						const bool hasL = rec.lr > rec.ll && rec.lr > tileLeft && rec.ll < tileLeft + TILE_W && yTop + 1 < height;
 						if (hasU || hasL) {
-							rec.mode = 3;
+							recMode = 3;
 							const int32_t lo = min(hasU ? rec.ul : 0x7FFFFFFF, hasL ? rec.ll : 0x7FFFFFFF), hi = max(hasU ? rec.ur : -1, hasL ? rec.lr : -1);
 							quadFirst = (max(lo, tileLeft) - tileLeft) >> 1; quadEnd = (min(hi, tileLeft + TILE_W) - tileLeft + 1) >> 1;
 							float vu = (start[0] + (dx[0] * ((float)rec.ul + 0.5f))) + (dy[0] * ((float)yTop + 0.5f));
@@ -1407,7 +1413,7 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32, RASTER_MIN_BLOCKS) raster_k
 								const uint32_t firstColumn = third.w & 0xFFFFu, columns = third.w >> 16;
 								const uint4 *src = (const uint4 *)(frame.chk + third.z + (size_t)(idx >> 1) * columns + ((uint32_t)tileX - firstColumn));
 								const uint4 w0 = __ldg(src), w1 = __ldg(src + 1), w2 = __ldg(src + 2), w3 = __ldg(src + 3), w4 = __ldg(src + 4);
-								rec.mode = (int32_t)w0.x;
+								recMode = (int32_t)w0.x;
 								rec.v[0] = __uint_as_float(w0.y); rec.v[1] = __uint_as_float(w0.z); rec.v[2] = __uint_as_float(w0.w);
 								rec.v[3] = __uint_as_float(w1.x); rec.v[4] = __uint_as_float(w1.y); rec.v[5] = __uint_as_float(w1.z); rec.v[6] = __uint_as_float(w1.w);
 								rec.v[7] = __uint_as_float(w2.x); rec.v[8] = __uint_as_float(w2.y); rec.v[9] = __uint_as_float(w2.z); rec.v[10] = __uint_as_float(w2.w);
@@ -1418,7 +1424,7 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32, RASTER_MIN_BLOCKS) raster_k
 #pragma unroll
 									for (int k = 0; k < 3; k++) { up[k] += dx2[k]; lo[k] += dx2[k]; }
 								}
-								rec.mode = 0;
+								recMode = 0;
 #pragma unroll
 								for (int k = 0; k < 3; k++) { rec.v[k] = up[k]; rec.v[3 + k] = lo[k]; }
 							} else {
@@ -1438,7 +1444,7 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32, RASTER_MIN_BLOCKS) raster_k
 											for (int l = 0; l < 4; l++) { lanes[k][l] += dx2[k]; }
 										}
 									}
-									rec.mode = 1;
+									recMode = 1;
 #pragma unroll
 									for (int k = 0; k < 3; k++) {
 #pragma unroll
@@ -1453,7 +1459,7 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32, RASTER_MIN_BLOCKS) raster_k
 #pragma unroll
 										for (int k = 0; k < 3; k++) { up[k] += dx2[k]; lo[k] += dx2[k]; }
 									}
-									rec.mode = 2;
+									recMode = 2;
 #pragma unroll
 									for (int k = 0; k < 3; k++) { rec.v[k] = up[k]; rec.v[3 + k] = lo[k]; }
 								}
@@ -1462,12 +1468,8 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32, RASTER_MIN_BLOCKS) raster_k
 					}
 				}
 			}
-			// 96-byte record as six 16-byte stores
-			uint4 *dst = (uint4 *)&sRec[r * BATCH + c];
-			const uint4 *src = (const uint4 *)&rec;
-#pragma unroll
-			for (int w = 0; w < 6; w++) { dst[w] = src[w]; }
-			sMask[r * BATCH + c] = (rec.mode >= 0 && quadEnd > quadFirst) ? ((0xFFFFFFFFu >> (32 - quadEnd)) & ~((1u << quadFirst) - 1u)) : 0u;
+			rec.mode = recMode;
+			sMask[r * BATCH + c] = (recMode >= 0 && quadEnd > quadFirst) ? ((0xFFFFFFFFu >> (32 - quadEnd)) & ~((1u << quadFirst) - 1u)) : 0u;
 		}
 		__syncwarp();
 		// Every lane collects the commands of the batch that may touch ITS quad and works through them in submission order. Lanes are

@@ -581,14 +581,14 @@ __device__ __forceinline__ void emit_tile_row(const FrameDev &frame, uint32_t ti
 }
 
 __device__ __forceinline__ void chk_store(ChkRec *dst, int32_t mode, const float *v, int count) {
-	ChkRec rec;
-	rec.mode = mode; rec.pad_ = 0;
+	// word 0 = mode, words 1..18 = v, word 19 = padding; assembled from registers (no local copy of the record)
+	uint32_t w[20];
+	w[0] = (uint32_t)mode; w[19] = 0u;
 #pragma unroll
-	for (int i = 0; i < 18; i++) { rec.v[i] = i < count ? v[i] : 0.0f; }
+	for (int i = 0; i < 18; i++) { w[1 + i] = i < count ? __float_as_uint(v[i]) : 0u; }
 	uint4 *d = (uint4 *)dst;
-	const uint4 *src = (const uint4 *)&rec;
 #pragma unroll
-	for (int w = 0; w < 5; w++) { d[w] = src[w]; }
+	for (int q = 0; q < 5; q++) { d[q] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]); }
 }
 
 // Walks one row pair of a large triangle like the reference's fillShapeSuper does (shader/fillerTemplates.h:329-372: left-edge quads, the
@@ -770,10 +770,20 @@ __global__ void __launch_bounds__(SETUP_THREADS) setup_kernel(FrameDev frame) {
 					}
 				}
 				{
+					// assembled field by field: copying the record through a uint4 view of its address would put it on the stack
 					uint4 *dst = (uint4 *)&frame.cmds[index];
-					const uint4 *src = (const uint4 *)&cmd;
-#pragma unroll
-					for (int w = 0; w < (int)(sizeof(Cmd) / 16); w++) { dst[w] = src[w]; }
+#define FU(x) __float_as_uint(x)
+					dst[0] = make_uint4(FU(cmd.start[0]), FU(cmd.start[1]), FU(cmd.start[2]), FU(cmd.dx[0]));
+					dst[1] = make_uint4(FU(cmd.dx[1]), FU(cmd.dx[2]), FU(cmd.dy[0]), FU(cmd.dy[1]));
+					dst[2] = make_uint4(FU(cmd.dy[2]), cmd.flags, cmd.chkOffset, cmd.chkShape);
+					dst[3] = make_uint4((uint32_t)cmd.rowStart, (uint32_t)cmd.rowCount, cmd.rowOffset, 0u);
+					dst[4] = make_uint4(FU(cmd.red[0]), FU(cmd.red[1]), FU(cmd.red[2]), FU(cmd.green[0]));
+					dst[5] = make_uint4(FU(cmd.green[1]), FU(cmd.green[2]), FU(cmd.blue[0]), FU(cmd.blue[1]));
+					dst[6] = make_uint4(FU(cmd.blue[2]), FU(cmd.alpha[0]), FU(cmd.alpha[1]), FU(cmd.alpha[2]));
+					dst[7] = make_uint4(FU(cmd.u1[0]), FU(cmd.u1[1]), FU(cmd.u1[2]), FU(cmd.v1[0]));
+					dst[8] = make_uint4(FU(cmd.v1[1]), FU(cmd.v1[2]), FU(cmd.u2[0]), FU(cmd.u2[1]));
+					dst[9] = make_uint4(FU(cmd.u2[2]), FU(cmd.v2[0]), FU(cmd.v2[1]), FU(cmd.v2[2]));
+#undef FU
 				}
 				if (rowCount > 0) {
 					if (queued >= (uint32_t)SETUP_THREADS) {

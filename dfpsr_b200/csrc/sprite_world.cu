@@ -10,6 +10,8 @@
 #include "sprite_math.cuh"
 
 #include <algorithm>
+#include <ctime>
+#include <cstdlib>
 #include <memory>
 #include <new>
 #include <vector>
@@ -978,7 +980,11 @@ static int execute_frame(dfpsr_sprite_world *w, const dfpsr_image *colorTarget, 
 		default: break;
 		}
 	}
+	const bool timing = getenv("DFPSR_SW_TIMING") != nullptr; // developer aid: host-side phase times of one frame on stderr
+	auto now = []() { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec * 1e6 + t.tv_nsec * 1e-3; };
+	const double t0 = timing ? now() : 0.0;
 	if (flush() || flush_copies()) { return 1; }
+	const double t1 = timing ? now() : 0.0;
 	if (!cubeFaces.empty()) {
 		// every cube map of the frame: cleared to 0 and rendered by one submission (also when a light has no casters)
 		if (dfpsr_model_render_depth_batch(shadowModels.data(), shadowTransforms.data(), shadowCameras.data(), shadowTargets.data(), (int32_t)shadowModels.size(),
@@ -987,7 +993,10 @@ static int execute_frame(dfpsr_sprite_world *w, const dfpsr_image *colorTarget, 
 	const int32_t worldCenter[2] = {find_world_center(w, width, height).x, find_world_center(w, width, height).y};
 	dfpsr_ortho_view lightView;
 	dfpsr_ortho_camera_light_view(&view, &lightView);
-	return dfpsr_light_frame(&lightView, worldCenter, blend ? colorTarget : nullptr, &fDiffuse, &fLight, &fNormal, &fHeight, directed.data(), (int32_t)directed.size(), points.data(), (int32_t)points.size(), stream);
+	const double t2 = timing ? now() : 0.0;
+	const int status = dfpsr_light_frame(&lightView, worldCenter, blend ? colorTarget : nullptr, &fDiffuse, &fLight, &fNormal, &fHeight, directed.data(), (int32_t)directed.size(), points.data(), (int32_t)points.size(), stream);
+	if (timing) { fprintf(stderr, "sprite world frame: sprites+copies %.0f us, shadow batch (%zu tasks) %.0f us, light frame launch %.0f us\n", t1 - t0, shadowModels.size(), t2 - t1, now() - t2); }
+	return status;
 }
 
 // ------------------------------------------------------------------------------------------------ C ABI

@@ -122,6 +122,12 @@ SIGNATURES = {
     "dfpsr_session_upload_model": (i32, [vp, P(abi.HostModel), P(i32)]),
     "dfpsr_session_render_views_host": (i32, [vp, i32, P(abi.Transform3D), vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, vp]),
     "dfpsr_session_render_frame_host": (i32, [vp, i32, P(abi.Transform3D), P(abi.Camera), vp, i32, vp, i32, i32, i32, i32, i32, vp]),
+    "dfpsr_peer_alloc": (i32, [P(vp), sz, vp]),
+    "dfpsr_peer_free": (i32, [vp]),
+    "dfpsr_peer_open": (i32, [P(vp), vp]),
+    "dfpsr_peer_close": (i32, [vp]),
+    "dfpsr_peer_signal": (i32, [P(vp), i32, u32, vp]),
+    "dfpsr_peer_wait": (i32, [vp, i32, u32, u32, vp, vp]),
 }
 
 
@@ -172,6 +178,22 @@ def image(tensor, pack=abi.PACK_RGBA):
         return abi.Image.null()
     assert tensor.is_cuda and tensor.dim() == 2 and tensor.element_size() == 4 and tensor.stride(1) == 1
     return abi.Image(tensor.data_ptr(), tensor.shape[1], tensor.shape[0], tensor.stride(0) * 4, pack)
+
+
+def image_from_ptr(ptr, width, height, stride_bytes=None, pack=abi.PACK_RGBA):
+    """dfpsr_image over raw device memory (e.g. a peer-mapped frame of another rank, dfpsr_peer_open)."""
+    return abi.Image(ptr, width, height, stride_bytes if stride_bytes is not None else width * 4, pack)
+
+
+class _RawCudaArray:
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+def tensor_from_ptr(ptr, shape, typestr="<i4", device="cuda"):
+    """A torch view (no copy, no ownership) of raw device memory through __cuda_array_interface__."""
+    import torch
+    return torch.as_tensor(_RawCudaArray(ptr, shape, typestr), device=device)
 
 
 def to_device(array, device="cuda"):

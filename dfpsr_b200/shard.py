@@ -49,3 +49,129 @@ def gather_strips(frame, bounds, group=None):
     for (a, b), part in zip(bounds, parts):
         frame[a:b] = part[: b - a]
     return frame
+
+
+# ---------------------------------------------------------------------------------------------- strips over NVLink peer memory
+
+class CudaPeerTransport:
+    """dfpsr_peer_* of the CUDA library (include/dfpsr_b200.h): IPC-exported device memory, flag stores and flag waits as kernels on
+    the current stream. tests/test_shard_gloo.py drives PeerStripFrame with a host-memory stand-in of the same six calls."""
+
+    def __init__(self, cuda, timeout_ms=2000):
+        import ctypes as C
+        from . import lib
+        self.C, self.lib, self.cuda, self.timeout_ms = C, lib, cuda, timeout_ms
+        self.status_ptr = None
+
+    def alloc(self, nbytes):
+        C = self.C
+        ptr, handle = C.c_void_p(), (C.c_uint8 * 64)()
+        self.lib.check(self.cuda.dfpsr_peer_alloc(C.byref(ptr), nbytes, handle))
+        return ptr.value, bytes(handle)
+
+    def free(self, ptr):
+        self.lib.check(self.cuda.dfpsr_peer_free(self.C.c_void_p(ptr)))
+
+    def open(self, handle):
+        C = self.C
+        ptr = C.c_void_p()
+        self.lib.check(self.cuda.dfpsr_peer_open(C.byref(ptr), (C.c_uint8 * 64).from_buffer_copy(handle)))
+        return ptr.value
+
+    def close(self, ptr):
+        self.lib.check(self.cuda.dfpsr_peer_close(self.C.c_void_p(ptr)))
+
+    def signal(self, flag_ptrs, value):
+        C = self.C
+        array = (C.c_void_p * len(flag_ptrs))(*flag_ptrs)
+        self.lib.check(self.cuda.dfpsr_peer_signal(array, len(flag_ptrs), value, self.lib.stream_ptr()))
+
+    def wait(self, flags_ptr, count, value, status_ptr):
+        self.lib.check(self.cuda.dfpsr_peer_wait(self.C.c_void_p(flags_ptr), count, value, self.timeout_ms, self.C.c_void_p(status_ptr), self.lib.stream_ptr()))
+
+    def read_u32(self, ptr):
+        C = self.C
+        out = C.c_uint32()
+        self.lib.check(self.cuda.dfpsr_download(C.byref(out), C.c_void_p(ptr), 4, self.lib.stream_ptr()))
+        self.lib.check(self.cuda.dfpsr_stream_synchronize(self.lib.stream_ptr()))
+        return out.value
+
+
+class PeerStripFrame:
+    """One frame whose row strips are rendered by different ranks straight into the presenting rank's memory (SURVEY.md §8e, screen strips;
+    the reference's workers share one target the same way, ref: implementation/render/renderCore.cpp:449-480).
+
+    The presenter exports frame + `done` flags (one u32 per rank); every rank exports a `consumed` flag of its own. Per frame k = 1, 2, ...:
+        rank r:     begin_frame(k)   waits (on its stream) until the presenter has consumed frame k - 1
+                    ... renders rows bounds[r] into `color_ptr` (dfpsr_renderer_begin_cleared + set_clip_rows + give_task + end) ...
+                    end_frame(k)     signals done[r] = k in the presenter's memory; the presenter then waits for all done[*] >= k
+        presenter:  ... consumes the frame on its stream ...
+                    release_frame(k) signals consumed = k on every other rank
+    Nothing in the loop touches the host or launches a collective; the data path is the tile kernel's own stores."""
+
+    FLAG_BYTES = 256
+
+    def __init__(self, transport, height, width, rank, world, presenter=0, align=4, bytes_per_pixel=4, group=None):
+        assert 0 <= presenter < world and world <= 16
+        self.t, self.rank, self.world, self.presenter, self.group = transport, rank, world, presenter, group
+        self.height, self.width, self.stride = height, width, width * bytes_per_pixel
+        self.bounds = strip_rows(height, world, align)
+        self.is_presenter = rank == presenter
+        self.mapped, self.owned = [], []
+        mine = {}
+        # own block: [0] consumed flag, [64] wait status
+        self.local_ptr, mine["consumed"] = transport.alloc(self.FLAG_BYTES)
+        self.owned.append(self.local_ptr)
+        if self.is_presenter:
+            self.color_ptr, mine["frame"] = transport.alloc(max(height * self.stride, 4))
+            self.done_ptr, mine["done"] = transport.alloc(self.FLAG_BYTES)
+            self.owned += [self.color_ptr, self.done_ptr]
+        everyone = [None] * world
+        if world > 1:
+            dist.all_gather_object(everyone, mine, group=group)
+        else:
+            everyone[0] = mine
+        self.consumed_ptrs = []
+        if self.is_presenter:
+            for r in range(world):
+                if r != rank:
+                    p = transport.open(everyone[r]["consumed"])
+                    self.mapped.append(p)
+                    self.consumed_ptrs.append(p)
+        else:
+            self.color_ptr = transport.open(everyone[presenter]["frame"])
+            self.done_ptr = transport.open(everyone[presenter]["done"])
+            self.mapped += [self.color_ptr, self.done_ptr]
+        self.status_ptr = self.local_ptr + 64
+
+    @property
+    def rows(self):
+        return self.bounds[self.rank]
+
+    def begin_frame(self, k):
+        if not self.is_presenter and k > 1:
+            self.t.wait(self.local_ptr, 1, k - 1, self.status_ptr)
+
+    def end_frame(self, k):
+        self.t.signal([self.done_ptr + 4 * self.rank], k)
+        if self.is_presenter:
+            self.t.wait(self.done_ptr, self.world, k, self.status_ptr)
+
+    def release_frame(self, k):
+        if self.is_presenter and self.consumed_ptrs:
+            self.t.signal(self.consumed_ptrs, k)
+
+    def timed_out(self):
+        """True when one of this rank's waits gave up (a peer never signalled). Synchronises the stream."""
+        return self.t.read_u32(self.status_ptr) != 0
+
+    def close(self):
+        if self.world > 1:
+            dist.barrier(group=self.group)
+        for p in self.mapped:
+            self.t.close(p)
+        if self.world > 1:
+            dist.barrier(group=self.group)
+        for p in self.owned:
+            self.t.free(p)
+        self.mapped, self.owned = [], []

@@ -494,6 +494,29 @@ int dfpsr_session_render_frame_host(dfpsr_session *session, int32_t slot, const 
  * previous one; pinned host images (dfpsr_malloc_host) make the copies asynchronous. Returns after everything has arrived. */
 int dfpsr_session_render_views_host(dfpsr_session *session, int32_t slot, const dfpsr_transform3d *modelToWorld, const dfpsr_camera *cameras, int32_t count, uint32_t *const *colorHost, int32_t colorStride, float *const *depthHost, int32_t depthStride, int32_t width, int32_t height, int32_t packOrder, int32_t uploadGeometry, void *stream);
 
+/* ---------------------------------------------------------------- strip-sharded frames over NVLink peer memory */
+
+/* One frame split into row strips across GPUs (one process per GPU): the reference's workers all write their strip into the same target
+ * (ref: implementation/render/renderCore.cpp:449-480); here the presenting rank owns the frame, exports it with dfpsr_peer_alloc, every
+ * other rank maps it with dfpsr_peer_open and uses the mapped pointer as the colour target of dfpsr_renderer_begin[_cleared] +
+ * dfpsr_renderer_set_clip_rows, so the tile kernel's own stores deliver the strip through NVLink/NVSwitch — no staging copy, no collective.
+ * Hand-shake, all stream-ordered and without the host: a rank ends its frame with dfpsr_peer_signal(flag in the presenter's memory, frame
+ * number); the presenter's stream runs dfpsr_peer_wait on those flags before it consumes the frame, then signals "consumed" flags in the
+ * ranks' own memory, on which they wait before they overwrite the frame with the next one. */
+#define DFPSR_PEER_HANDLE_BYTES 64
+#define DFPSR_PEER_MAX_RANKS 16
+/* cudaMalloc (zero-filled) + IPC export; handle receives DFPSR_PEER_HANDLE_BYTES bytes to send to the other processes. */
+int dfpsr_peer_alloc(void **devicePtr, size_t bytes, uint8_t *handle);
+int dfpsr_peer_free(void *devicePtr);
+/* Maps an exported allocation of another process (same or other GPU of the box) into this one; close before the owner frees it. */
+int dfpsr_peer_open(void **devicePtr, const uint8_t *handle);
+int dfpsr_peer_close(void *devicePtr);
+/* After everything queued on `stream` so far (peer stores included) is visible system-wide, stores `value` to each of the `count` flags. */
+int dfpsr_peer_signal(uint32_t *const *flags, int32_t count, uint32_t value, void *stream);
+/* Blocks `stream` (not the host) until flags[0..count) have all reached `value` (wrap-safe >=). Gives up after timeoutMs (1..10000) and
+ * stores 1 to *status (device memory, caller-zeroed) instead of hanging the device. */
+int dfpsr_peer_wait(const uint32_t *flags, int32_t count, uint32_t value, uint32_t timeoutMs, uint32_t *status, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -96,6 +96,11 @@ def test_compute_entry_points_fail_loudly_without_a_gpu():
     assert handle.dfpsr_init(0) != 0
     with pytest.raises(lib.DfpsrError):
         lib.check(handle.dfpsr_init(0))
+    ptr, ipc = C.c_void_p(), (C.c_uint8 * 64)()
+    assert handle.dfpsr_peer_alloc(C.byref(ptr), 1024, ipc) != 0 and ptr.value is None
+    assert handle.dfpsr_peer_open(C.byref(ptr), ipc) != 0
+    # a flag wait must carry a time limit: a peer that never signals may not hang the device
+    assert handle.dfpsr_peer_wait(C.c_void_p(256), 1, 1, 0, C.c_void_p(512), None) != 0 and b"time limit" in handle.dfpsr_last_error()
 
 
 @pytest.mark.parametrize("perspective", [True, False])

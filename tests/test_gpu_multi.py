@@ -35,6 +35,8 @@ def test_strip_sharded_frame_two_gpus():
     assert out.returncode == 0, out.stderr[-3000:]
     line = last_json(out.stdout)
     assert line["n_gpus"] == 2 and line["gathered_equals_full_frame"] is True
+    # the same strips stored by the tile kernels straight into rank 0's frame over NVLink peer memory (dfpsr_peer_*, shard.PeerStripFrame)
+    assert line["peer_equals_full_frame"] is True and line["peer_wait_timed_out"] is False
 
 
 def test_view_sharded_bench_two_gpus():

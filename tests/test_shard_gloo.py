@@ -108,3 +108,91 @@ def test_strip_gather_and_view_sharding_world_size_2(tmp_path):
     world = 2
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     assert all(os.path.exists(tmp_path / f"ok{r}") for r in range(world))
+
+
+class HostPeerTransport:
+    """Stand-in for shard.CudaPeerTransport on a machine without GPUs: 'device memory' is a file under a shared directory mapped by
+    every process, a 'pointer' is (region << 32 | offset), signal / wait are synchronous stores and polls. It exercises the handle
+    exchange and the frame hand-shake of shard.PeerStripFrame with real processes; the CUDA transport is covered on two GPUs by
+    tests/test_gpu_multi.py."""
+
+    def __init__(self, directory, rank):
+        self.directory, self.rank, self.regions, self.count = directory, rank, {}, 0
+
+    def _map(self, path, nbytes=None):
+        self.count += 1
+        mode = "r+" if os.path.exists(path) else "w+"
+        self.regions[self.count] = np.memmap(path, dtype=np.uint8, mode=mode, shape=(nbytes,) if nbytes else None)
+        return self.count << 32
+
+    def alloc(self, nbytes):
+        path = os.path.join(self.directory, f"r{self.rank}_{self.count}")
+        ptr = self._map(path, nbytes)
+        return ptr, path.encode().ljust(64, b"\0")[:64] if len(path) <= 64 else path.encode()
+
+    def open(self, handle):
+        return self._map(handle.rstrip(b"\0").decode())
+
+    def close(self, ptr):
+        self.regions.pop(ptr >> 32).flush()
+
+    free = close
+
+    def u32(self, ptr):
+        region, offset = self.regions[ptr >> 32], ptr & 0xFFFFFFFF
+        return region[offset:offset + 4].view(np.uint32)
+
+    def signal(self, flag_ptrs, value):
+        for p in flag_ptrs:
+            self.u32(p)[0] = value
+            self.regions[p >> 32].flush()
+
+    def wait(self, flags_ptr, count, value, status_ptr):
+        import time
+        deadline = time.time() + 20.0
+        while any(int(self.u32(flags_ptr + 4 * i)[0]) < value for i in range(count)):
+            if time.time() > deadline:
+                self.u32(status_ptr)[0] = 1
+                return
+            time.sleep(0.0005)
+
+    def read_u32(self, ptr):
+        return int(self.u32(ptr)[0])
+
+    def rows(self, ptr, stride, y0, y1):
+        region = self.regions[ptr >> 32]
+        return region[y0 * stride:y1 * stride]
+
+
+def _peer_worker(rank, world, port, result_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        h, w = 22, 8
+        t = HostPeerTransport(result_dir, rank)
+        frame = shard.PeerStripFrame(t, h, w, rank, world, presenter=0, align=4)
+        assert frame.bounds == shard.strip_rows(h, world, align=4) and frame.rows == frame.bounds[rank]
+        y0, y1 = frame.rows
+        for k in range(1, 6):
+            frame.begin_frame(k)                                   # a rank may not overwrite frame k - 1 before the presenter has consumed it
+            t.rows(frame.color_ptr, frame.stride, y0, y1)[:] = (10 * k + rank) & 255
+            frame.end_frame(k)                                     # presenter returns from here only when every strip of frame k has arrived
+            if frame.is_presenter:
+                for r, (a, b) in enumerate(frame.bounds):
+                    got = np.unique(t.rows(frame.color_ptr, frame.stride, a, b))
+                    assert got.tolist() == [(10 * k + r) & 255], (k, r, got)
+            frame.release_frame(k)
+        assert not frame.timed_out()
+        frame.close()
+        open(os.path.join(result_dir, f"peer_ok{rank}"), "w").write("ok")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_peer_strip_frame_handshake_world_size_2(tmp_path):
+    """Handle exchange + done/consumed hand-shake of shard.PeerStripFrame with two processes (host-memory stand-in for NVLink peer memory)."""
+    world = 2
+    mp.spawn(_peer_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(tmp_path / f"peer_ok{r}") for r in range(world))

@@ -1,5 +1,8 @@
 """Screen-strip mode across GPUs: every rank rasterises rows strip_rows(height, world)[rank] of ONE frame from a
-replicated scene (dfpsr_renderer_set_clip_rows), then a single NCCL all_gather over NVLink assembles the frame on every rank.
+replicated scene (dfpsr_renderer_set_clip_rows). Two ways to assemble the frame are timed:
+  gather  a single NCCL all_gather over NVLink puts the whole frame on every rank (the library baseline)
+  peer    the presenting rank (0) owns the frame, the others map it (dfpsr_peer_open) and their tile kernels store their strips straight
+          into it over NVLink; flags in peer memory order the frames (shard.PeerStripFrame) — no collective, no staging copy
 Run: torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tools/strip_bench.py [--scene terrain|tiny]
 Rank 0 checks the gathered frame against a full-frame render on its own GPU and prints one JSON line."""
 import argparse, ctypes as C, json, os, sys
@@ -50,7 +53,21 @@ def main():
         if strip and world > 1:
             shard.gather_strips(color, bounds)
 
-    def timed(strip):
+    psf = shard.PeerStripFrame(shard.CudaPeerTransport(cuda), h, w, rank, world) if world > 1 else None
+    counter = [0]
+
+    def peer_frame(_strip):
+        counter[0] += 1
+        k = counter[0]
+        psf.begin_frame(k)
+        lib.check(cuda.dfpsr_renderer_begin_cleared(r, C.byref(lib.image_from_ptr(psf.color_ptr, w, h)), C.byref(lib.image(depth)), 0, 0.0))
+        lib.check(cuda.dfpsr_renderer_set_clip_rows(r, psf.rows[0], psf.rows[1]))
+        lib.check(cuda.dfpsr_renderer_give_task(r, C.byref(model.desc), C.byref(ident), C.byref(cam), sp))
+        lib.check(cuda.dfpsr_renderer_end(r, sp))
+        psf.end_frame(k)      # presenter: its stream now waits for every strip
+        psf.release_frame(k)  # presenter: the frame is consumed at this point of its stream (a display hand-off would sit before this)
+
+    def timed(strip, frame=frame):
         for _ in range(3):
             frame(strip)
         if world > 1:
@@ -69,12 +86,24 @@ def main():
 
     ms_strip = timed(True)
     gathered = color.clone()
+    ms_peer, peer_frame_copy, peer_timed_out = None, None, False
+    if psf is not None:
+        ms_peer = timed(True, peer_frame)
+        peer_timed_out = psf.timed_out()
+        if rank == 0:
+            peer_frame_copy = lib.tensor_from_ptr(psf.color_ptr, (h, w)).clone()
     ms_full = timed(False)
     same = bool(torch.equal(gathered, color))
+    peer_same = bool(torch.equal(peer_frame_copy, color)) if peer_frame_copy is not None else None
     if rank == 0:
         print(json.dumps({"scene": args.scene, "n_gpus": world, "width": w, "height": h, "strip_frame_ms": ms_strip, "single_gpu_frame_ms": ms_full,
-                          "speedup": ms_full / ms_strip, "gathered_equals_full_frame": same, "gather_bytes_per_rank": (bounds[rank][1] - bounds[rank][0]) * w * 4}))
+                          "speedup": ms_full / ms_strip, "gathered_equals_full_frame": same, "gather_bytes_per_rank": (bounds[rank][1] - bounds[rank][0]) * w * 4,
+                          "peer_strip_frame_ms": ms_peer, "peer_speedup": (ms_full / ms_peer) if ms_peer else None, "peer_equals_full_frame": peer_same,
+                          "peer_wait_timed_out": peer_timed_out}))
+    if psf is not None:
+        psf.close()
     assert same, "strip-sharded frame differs from the full-frame render"
+    assert peer_same is not False and not peer_timed_out, "peer-store strip frame differs from the full-frame render (or a wait timed out)"
     if world > 1:
         dist.destroy_process_group()
 

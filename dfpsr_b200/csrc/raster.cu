@@ -885,37 +885,56 @@ __global__ void __launch_bounds__(SETUP_THREADS, SETUP_MIN_BLOCKS) setup_kernel(
 // One thread per (large command, tile row): scan-converts the row pairs of that tile row (ref: ITriangle2D.cpp:86-176), bins the command to
 // the tiles they touch and walks the interpolation chains across the tile columns, leaving the checkpoints the tile kernel continues from.
 // The units of the whole batch are spread over the whole grid, so one 1080p frame (about 60 k units) already fills the machine.
+// SPLIT: two threads per unit (adjacent lanes), one per row pair of the tile row — twice the threads and half the serial chain per thread for
+// frames whose units do not fill the machine anyway (one 1080p terrain frame has 15 k units); the bins of the two row pairs meet in a shuffle.
+template <bool SPLIT>
 __global__ void __launch_bounds__(256) big_units_kernel(FrameDev frame, uint32_t unitTotal) {
-	const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t thread = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t u = SPLIT ? thread >> 1 : thread;
+	const int32_t half = SPLIT ? (int32_t)(thread & 1u) : 0;
 	// unitTotal is the first pass's count (the launch size); commands that overflowed a block's queue were finished by their own thread,
 	// so the cursor holds the number of units that were really queued
-	if (u >= unitTotal || u >= frame.totals[9]) { return; }
-	const BigItem &it = frame.bigItems[frame.bigUnits[u]];
-	const int32_t ty = it.t / TILE_H + (int32_t)(u - it.unitStart);
-	const int32_t height = it.ty1; // the view's height travels in ty1 (unused by the emit pass)
-	EdgeSet edges;
-	long long fx[3] = {it.fx[0], it.fx[1], it.fx[2]}, fy[3] = {it.fy[0], it.fy[1], it.fy[2]};
-	edges_setup(edges, fx, fy, it.l, it.t, it.r);
-	float start[3], dx[3], dy[3];
-	const bool checkpoints = it.chkOffset != CHK_NONE;
-	if (checkpoints) {
-		const float *planes = (const float *)&frame.cmds[it.cmdIndex];
-#pragma unroll
-		for (int k = 0; k < 3; k++) { start[k] = planes[k]; dx[k] = planes[3 + k]; dy[k] = planes[6 + k]; }
-	}
-	const int32_t columns = it.tx1 - it.tx0 + 1;
-	const int32_t yBegin = max(it.t, ty * TILE_H), yEnd = min(it.t + it.rowCount, ty * TILE_H + TILE_H);
+	const bool valid = u < unitTotal && u < frame.totals[9];
+	if (!SPLIT && !valid) { return; }
 	int32_t minL = 0x7FFFFFFF, maxR = -1;
-	for (int32_t y = yBegin; y < yEnd; y += 2) { // rows come in even-aligned pairs
-		int2 upperRow = edges_row(edges, y), lowerRow = edges_row(edges, y + 1);
-		*(int4 *)&frame.rows[it.rowOffset + (uint32_t)(y - it.t)] = make_int4(upperRow.x, upperRow.y, lowerRow.x, lowerRow.y);
-		if (upperRow.y > upperRow.x && y < height) { minL = min(minL, upperRow.x); maxR = max(maxR, upperRow.y); }
-		if (lowerRow.y > lowerRow.x && y + 1 < height) { minL = min(minL, lowerRow.x); maxR = max(maxR, lowerRow.y); }
-		if (checkpoints && y < height) {
-			chk_walk_row_pair(start, dx, dy, upperRow, lowerRow, y, frame.chk + it.chkOffset + (size_t)((y - it.t) / 2) * (size_t)columns, it.tx0);
+	int32_t ty = 0, height = 0;
+	const BigItem *item = nullptr;
+	if (valid) {
+		const BigItem &it = frame.bigItems[frame.bigUnits[u]];
+		item = &it;
+		ty = it.t / TILE_H + (int32_t)(u - it.unitStart);
+		height = it.ty1; // the view's height travels in ty1 (unused by the emit pass)
+		const int32_t yBegin = max(it.t, ty * TILE_H), yEnd = min(it.t + it.rowCount, ty * TILE_H + TILE_H);
+		const int32_t yFirst = SPLIT ? yBegin + 2 * half : yBegin, yLast = SPLIT ? min(yEnd, yFirst + 2) : yEnd;
+		if (yFirst < yLast) {
+			EdgeSet edges;
+			long long fx[3] = {it.fx[0], it.fx[1], it.fx[2]}, fy[3] = {it.fy[0], it.fy[1], it.fy[2]};
+			edges_setup(edges, fx, fy, it.l, it.t, it.r);
+			float start[3], dx[3], dy[3];
+			const bool checkpoints = it.chkOffset != CHK_NONE;
+			if (checkpoints) {
+				const float *planes = (const float *)&frame.cmds[it.cmdIndex];
+#pragma unroll
+				for (int k = 0; k < 3; k++) { start[k] = planes[k]; dx[k] = planes[3 + k]; dy[k] = planes[6 + k]; }
+			}
+			const int32_t columns = it.tx1 - it.tx0 + 1;
+			for (int32_t y = yFirst; y < yLast; y += 2) { // rows come in even-aligned pairs
+				int2 upperRow = edges_row(edges, y), lowerRow = edges_row(edges, y + 1);
+				*(int4 *)&frame.rows[it.rowOffset + (uint32_t)(y - it.t)] = make_int4(upperRow.x, upperRow.y, lowerRow.x, lowerRow.y);
+				if (upperRow.y > upperRow.x && y < height) { minL = min(minL, upperRow.x); maxR = max(maxR, upperRow.y); }
+				if (lowerRow.y > lowerRow.x && y + 1 < height) { minL = min(minL, lowerRow.x); maxR = max(maxR, lowerRow.y); }
+				if (checkpoints && y < height) {
+					chk_walk_row_pair(start, dx, dy, upperRow, lowerRow, y, frame.chk + it.chkOffset + (size_t)((y - it.t) / 2) * (size_t)columns, it.tx0);
+				}
+			}
 		}
 	}
-	if (ty * TILE_H < height) { emit_tile_row(frame, it.tileBase, it.tilesX, ty, minL, maxR, it.cmdIndex); }
+	if (SPLIT) {
+		minL = min(minL, __shfl_xor_sync(0xffffffffu, minL, 1));
+		maxR = max(maxR, __shfl_xor_sync(0xffffffffu, maxR, 1));
+		if (!valid || half != 0) { return; }
+	}
+	if (ty * TILE_H < height) { emit_tile_row(frame, item->tileBase, item->tilesX, ty, minL, maxR, item->cmdIndex); }
 }
 
 // ref: api/rendererAPI.cpp:242-258 occludeFromExistingTriangles: every solid command queued so far is an occluder for the cells that lie
@@ -1846,9 +1865,14 @@ static int launch_projection(dfpsr_renderer *r, const FrameDev &frame, cudaStrea
 	return 0;
 }
 
+static double host_now_us() { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec * 1e6 + t.tv_nsec * 1e-3; }
+
 static int renderer_end_internal(dfpsr_renderer *r, cudaStream_t stream) {
 	// ref: api/rendererAPI.cpp:352-402
 	DFPSR_REQUIRE(r->receiving, "Called renderer_end without renderer_begin!");
+	static const bool timing = getenv("DFPSR_END_TIMING") != nullptr; // developer aid: host-side phase times of one renderer_end on stderr
+	const double tStart = timing ? host_now_us() : 0.0;
+	double tUploaded = 0.0, tLaunched = 0.0, tSynced = 0.0;
 	r->receiving = false;
 	r->lastCommands = 0;
 	// ---- lay out the batch
@@ -1871,6 +1895,7 @@ static int renderer_end_internal(dfpsr_renderer *r, cudaStream_t stream) {
 	DFPSR_CHECK_CUDA(cudaMemcpyAsync(r->dViews.ptr, r->views.data(), viewCount * sizeof(ViewDev), cudaMemcpyHostToDevice, stream));
 	DFPSR_CHECK_CUDA(cudaMemsetAsync(r->tileCount.ptr, 0, ((size_t)tileTotal + 12) * 4, stream)); // tile counts, cursors of empty frames, totals
 	if (taskCount == 0) { DFPSR_CHECK_CUDA(cudaMemsetAsync(r->tileCursor.ptr, 0, (size_t)tileTotal * 4, stream)); }
+	if (timing) { tUploaded = host_now_us(); }
 
 	FrameDev frame;
 	memset(&frame, 0, sizeof(frame));
@@ -1896,7 +1921,9 @@ static int renderer_end_internal(dfpsr_renderer *r, cudaStream_t stream) {
 		DFPSR_LAUNCH(scan_blocks_kernel, 1, 1024, 0, stream, frame);
 		DFPSR_LAUNCH(tile_alloc_kernel, (tileTotal + 255) / 256, 256, 0, stream, frame);
 		DFPSR_LAUNCH(publish_totals_kernel, 1, 32, 0, stream, frame.totals, r->hostTotalsDevice);
+		if (timing) { tLaunched = host_now_us(); }
 		DFPSR_CHECK_CUDA(cudaStreamSynchronize(stream));
+		if (timing) { tSynced = host_now_us(); }
 		const uint32_t commandTotal = r->hostTotals[0], rowTotal = r->hostTotals[1], entryTotal = r->hostTotals[2], maxTile = r->hostTotals[3];
 		r->lastCommands = commandTotal;
 		if (commandTotal > 0) {
@@ -1914,7 +1941,11 @@ static int renderer_end_internal(dfpsr_renderer *r, cudaStream_t stream) {
 				frame.bigItems = (BigItem *)r->bigItems.ptr; frame.bigUnits = (uint32_t *)r->bigUnits.ptr;
 			}
 			DFPSR_LAUNCH(setup_kernel<true>, blockTotal, SETUP_THREADS, 0, stream, frame);
-			if (unitTotal > 0) { DFPSR_LAUNCH(big_units_kernel, (unitTotal + 255) / 256, 256, 0, stream, frame, unitTotal); }
+			if (unitTotal > 0) {
+				// frames with few units (a single 1080p frame: 15 k) are latency-bound: two threads per unit; large batches keep one
+				if (unitTotal <= (uint32_t)sm_count() * 2048u) { DFPSR_LAUNCH(big_units_kernel<true>, (2u * unitTotal + 255u) / 256u, 256, 0, stream, frame, unitTotal); }
+				else { DFPSR_LAUNCH(big_units_kernel<false>, (unitTotal + 255) / 256, 256, 0, stream, frame, unitTotal); }
+			}
 			if (maxTile > (uint32_t)LOCAL_SORT) {
 				if (maxTile > (uint32_t)SORT_SMEM) {
 					if (r->sortTmp.reserve((size_t)entryTotal * 4 + 16)) { return 1; }
@@ -1932,6 +1963,10 @@ static int renderer_end_internal(dfpsr_renderer *r, cudaStream_t stream) {
 	}
 	if (r->depthOnly) { DFPSR_LAUNCH(raster_kernel<true>, grid, RASTER_WARPS * 32, 0, stream, frame, r->textures); }
 	else { DFPSR_LAUNCH(raster_kernel<false>, grid, RASTER_WARPS * 32, 0, stream, frame, r->textures); }
+	if (timing) {
+		fprintf(stderr, "renderer_end: %zu tasks, %zu views | layout+upload %.0f us, first launches %.0f us, wait for totals %.0f us, second launches %.0f us\n",
+		        taskCount, viewCount, tUploaded - tStart, tLaunched - tUploaded, tSynced - tLaunched, host_now_us() - tSynced);
+	}
 	return 0;
 }
 
@@ -2240,6 +2275,8 @@ static int render_batch(const dfpsr_model *const *models, const dfpsr_transform3
 	dfpsr_renderer *r;
 	if (immediate_renderer(&r)) { return 1; }
 	if (renderer_begin_internal(r, depthOnly)) { return 1; }
+	static const bool timing = getenv("DFPSR_END_TIMING") != nullptr;
+	const double tStart = timing ? host_now_us() : 0.0;
 	for (int32_t v = 0; v < viewCount; v++) {
 		ViewDev view;
 		if (make_view(view, (colors && !depthOnly) ? colors + v : nullptr, depths ? depths + v : nullptr, clear, clearColor, clearDepth)) { r->receiving = false; return 1; }
@@ -2251,6 +2288,7 @@ static int render_batch(const dfpsr_model *const *models, const dfpsr_transform3
 		if (models[t] == nullptr) { continue; }
 		if (add_model_task(r, v, models[t], transforms + t, cameras + t)) { r->receiving = false; return 1; }
 	}
+	if (timing) { fprintf(stderr, "render_batch: %d submissions -> %zu tasks in %.0f us\n", taskCount, r->tasks.size(), host_now_us() - tStart); }
 	return renderer_end_internal(r, stream);
 }
 

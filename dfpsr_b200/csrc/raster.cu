@@ -125,6 +125,7 @@ struct FrameDev {
 	uint32_t *sortTmp;               // rank-sort scratch, as large as the entry pool; totals[6] = cursor
 	struct BigItem *bigItems;        // large commands of the frame (totals[8] = cursor) and, per (command, tile row) unit, the index of its
 	uint32_t *bigUnits;              // command in bigItems (totals[7] = units needed, counted by the first pass; totals[9] = cursor)
+	int32_t smallRows;               // triangles up to this many rows (and SMALL_WIDTH columns) are scan-converted by their set-up thread
 	const float *occlusionGrid;      // 16-pixel cells of the farthest depth at which something can still be visible; null = no occluders
 	int32_t gridWidth, gridHeight, gridStride;
 };
@@ -705,7 +706,7 @@ __global__ void __launch_bounds__(SETUP_THREADS, SETUP_MIN_BLOCKS) setup_kernel(
 			// ref: api/rendererAPI.cpp:193-217 — a command that the occlusion grid hides stays in the queue (it keeps its index) but draws nothing
 			const int32_t rowCount = (bound.any && !command_occluded(frame, bound, q)) ? bound.b - bound.t : 0;
 			const int32_t tx0 = bound.l / TILE_W, tx1 = (bound.r - 1) / TILE_W, ty0 = bound.t / TILE_H, ty1 = (min(bound.b, height) - 1) / TILE_H;
-			const bool small = rowCount <= SMALL_ROWS && (bound.r - bound.l) <= SMALL_WIDTH;
+			const bool small = rowCount <= frame.smallRows && (bound.r - bound.l) <= SMALL_WIDTH;
 			if (!EMIT) {
 				if (rowCount > 0) {
 					if (!small && !task.depthOnly) { atomicAdd(&sChkCount, (uint32_t)((rowCount / 2) * (tx1 - tx0 + 1))); }
@@ -1907,6 +1908,12 @@ static int renderer_end_internal(dfpsr_renderer *r, cudaStream_t stream) {
 	frame.blockCmds = (uint32_t *)r->blockCmds.ptr; frame.blockRows = (uint32_t *)r->blockRows.ptr;
 	frame.tileCount = (uint32_t *)r->tileCount.ptr; frame.tileOffset = (uint32_t *)r->tileOffset.ptr; frame.tileCursor = (uint32_t *)r->tileCursor.ptr;
 	frame.totals = frame.tileCount + tileTotal;
+	// A frame that does not fill the machine (one 1080p terrain frame: 7.6 k slots) is bound by its longest thread: only triangles within one
+	// tile row stay with their set-up thread, everything taller goes to the unit queue (one thread per row pair). Large batches keep the
+	// serial scan conversion of small triangles (less queue and checkpoint traffic per triangle).
+	static const int smallRowsOverride = getenv("DFPSR_SMALL_ROWS") ? atoi(getenv("DFPSR_SMALL_ROWS")) : -1;
+	frame.smallRows = slotTotal <= sm_count() * 1024 ? TILE_H : SMALL_ROWS;
+	if (smallRowsOverride >= 0) { frame.smallRows = smallRowsOverride; }
 
 	if (taskCount > 0) {
 		if (launch_projection(r, frame, stream)) { return 1; }

@@ -1328,6 +1328,26 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32, RASTER_MIN_BLOCKS) raster_k
 	const uint32_t n = frame.tileCursor[tile];
 	const bool clear = vw.clear != 0;
 	if (n == 0 && !clear) { return; }
+	if (n == 0) {
+		// An empty tile of a cleared target (sky; most tiles of a shadow cube map): nothing to load, sort or shade. Lane = four pixels of
+		// one row, one 16-byte store per buffer when the row allows it.
+		const int32_t x = tileX * TILE_W + 4 * (lane & 7), y = tileY * TILE_H + (lane >> 3);
+		if (y >= vw.height || x >= vw.width) { return; }
+		const int32_t count = min(4, vw.width - x);
+		if (!DEPTH_ONLY && vw.color.data != nullptr) {
+			uint32_t *dst = row_ptr<uint32_t>(vw.color.data, vw.color.stride, y) + x;
+			const uint32_t c = vw.clearColor;
+			if (count == 4 && (((uintptr_t)dst) & 15u) == 0) { *(uint4 *)dst = make_uint4(c, c, c, c); }
+			else { for (int32_t i = 0; i < count; i++) { dst[i] = c; } }
+		}
+		if (vw.depth.data != nullptr) {
+			float *dst = row_ptr<float>(vw.depth.data, vw.depth.stride, y) + x;
+			const float d = vw.clearDepth;
+			if (count == 4 && (((uintptr_t)dst) & 15u) == 0) { *(float4 *)dst = make_float4(d, d, d, d); }
+			else { for (int32_t i = 0; i < count; i++) { dst[i] = d; } }
+		}
+		return;
+	}
 	const uint32_t *list = frame.tileList + frame.tileOffset[tile];
 
 	const int32_t width = vw.width, height = vw.height;
@@ -1532,15 +1552,24 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32, RASTER_MIN_BLOCKS) raster_k
 			const bool affine = (flags & CMD_AFFINE) != 0;
 
 			if (DEPTH_ONLY) {
+				// The reference adds dx once per pixel from the row's left end (renderCore.cpp:343-387). Both rows walk to this quad's first
+				// column in ONE loop (the checkpoint holds the sums at max(row.left, tileLeft)); the second column is one more addition.
 				const float dx0 = __ldg(&cmd.dx[0]);
+				const int32_t startU = max(upperRow.x, tileLeft), startL = max(lowerRow.x, tileLeft);
+				const bool touchU = x0 + 1 >= upperRow.x && x0 < upperRow.y, touchL = x0 + 1 >= lowerRow.x && x0 < lowerRow.y && y2 < height;
+				const int32_t stepsU = touchU ? x0 - startU : -1, stepsL = touchL ? x0 - startL : -1; // negative: the row starts right of the first column (or misses the quad)
+				float vu = rec.v[0], vl = rec.v[1];
+				for (int32_t i = 0, steps = max(stepsU, stepsL); i < steps; i++) {
+					if (i < stepsU) { vu += dx0; }
+					if (i < stepsL) { vl += dx0; }
+				}
+				const float value[4] = {vu, stepsU >= 0 ? vu + dx0 : vu, vl, stepsL >= 0 ? vl + dx0 : vl};
 #pragma unroll
 				for (int l = 0; l < 4; l++) {
 					const int2 row = (l < 2) ? upperRow : lowerRow;
 					const int32_t px = x0 + (l & 1), py = y1 + (l >> 1);
 					if (px >= row.x && px < row.y && py < height) {
-						float value = rec.v[l >> 1];
-						for (int32_t s = max(row.x, tileLeft); s < px; s++) { value += dx0; }
-						if (affine ? (value < dep[l]) : (value > dep[l])) { dep[l] = value; dirty = true; }
+						if (affine ? (value[l] < dep[l]) : (value[l] > dep[l])) { dep[l] = value[l]; dirty = true; }
 					}
 				}
 				continue;

@@ -16,7 +16,8 @@ FLAGS = [
 
 
 def sources():
-    return sorted(glob.glob(os.path.join(HERE, "csrc", "*.cu")))
+    # *.cpp: host-only arithmetic (SSE vector extensions the CUDA front end does not parse), handed to the host compiler as is
+    return sorted(glob.glob(os.path.join(HERE, "csrc", "*.cu")) + glob.glob(os.path.join(HERE, "csrc", "*.cpp")))
 
 
 def needs_build():

@@ -253,34 +253,7 @@ int dfpsr_camera_create_orthogonal(dfpsr_camera *out, const dfpsr_transform3d *l
 }
 
 // ref: implementation/render/Camera.h:73-95, :202-217
-int dfpsr_camera_is_box_seen(const dfpsr_camera *c, const float mn[3], const float mx[3], const dfpsr_transform3d *m2w) {
-	bool anyOutside = false;
-	V3 corners[8];
-	for (int i = 0; i < 8; i++) {
-		float px = (i & 1) ? mx[0] : mn[0], py = (i & 2) ? mx[1] : mn[1], pz = (i & 4) ? mx[2] : mn[2];
-		// modelToWorld.transformPoint (math/Transform3D.h:41-43)
-		float wx = (px * m2w->xAxis[0] + py * m2w->yAxis[0] + pz * m2w->zAxis[0]) + m2w->position[0];
-		float wy = (px * m2w->xAxis[1] + py * m2w->yAxis[1] + pz * m2w->zAxis[1]) + m2w->position[1];
-		float wz = (px * m2w->xAxis[2] + py * m2w->yAxis[2] + pz * m2w->zAxis[2]) + m2w->position[2];
-		// worldToCamera (math/Transform3D.h:50-52)
-		const dfpsr_transform3d &l = c->location;
-		float dx = wx - l.position[0], dy = wy - l.position[1], dz = wz - l.position[2];
-		corners[i] = V3{
-		  dx * l.xAxis[0] + dy * l.xAxis[1] + dz * l.xAxis[2],
-		  dx * l.yAxis[0] + dy * l.yAxis[1] + dz * l.yAxis[2],
-		  dx * l.zAxis[0] + dy * l.zAxis[1] + dz * l.zAxis[2]};
-	}
-	for (int s = 0; s < c->cullPlaneCount; s++) {
-		const float *pl = c->cullPlanes[s];
-		bool anyInside = false;
-		for (int p = 0; p < 8; p++) {
-			float d = ((pl[0] * corners[p].x) + (pl[1] * corners[p].y) + (pl[2] * corners[p].z)) - pl[3];
-			if (d <= 0.0f) { anyInside = true; } else { anyOutside = true; }
-		}
-		if (!anyInside) { return 0; }
-	}
-	return anyOutside ? 1 : 2;
-}
+// dfpsr_camera_is_box_seen lives in host_math.cpp (four corners per SSE vector, same IEEE operations in the same order).
 
 // ref: api/textureAPI.cpp:30-41, :65-78; implementation/image/Texture.h:63-102
 int dfpsr_texture_layout(dfpsr_texture *out, int32_t width, int32_t height, int32_t resolutions) {

@@ -227,6 +227,36 @@ __global__ void __launch_bounds__(256) blend_kernel(Img color, Img diffuse, Img 
 	}
 }
 
+// (float)(1.0 / sqrt((double)x)) — reciprocalSquareRoot of the reference's scalar build (ref: base/simd.h:4104) — without the FP64 square
+// root and division (about 70 double-precision instructions per pixel and light; the point light was bound by them). A 22-bit seed and two
+// Newton steps in double land within 2^-50 of the true value; the reference's own result lies within 2^-52 of it. Unless the estimate is
+// closer than 2^-47 (relative) to a boundary between two floats, both round to the same float; the few values that are (3.6e-7 of all
+// inputs) take the literal expression. Checked on the host over 4e8 inputs with perturbed seeds and on the device by
+// dfpsr_selftest_rsqrt (tests/test_gpu_pixel_ops.py).
+__device__ __forceinline__ float reference_rsqrt(float x) {
+	if (!(x >= 1.17549435e-38f && x <= 3.0e38f)) { return (float)(1.0 / sqrt((double)x)); } // zero, denormal, negative, inf, nan
+	const double d = (double)x, halfD = 0.5 * d;
+	double y = (double)rsqrtf(x);
+	y = y * (1.5 - (halfD * (y * y)));
+	y = y * (1.5 - (halfD * (y * y)));
+	const float f = (float)y;
+	const double ulp = (double)__uint_as_float(__float_as_uint(f) + 1u) - (double)f;
+	const double below = (__float_as_uint(f) & 0x7FFFFFu) == 0u ? 0.25 * ulp : 0.5 * ulp; // the spacing halves below a power of two
+	const double diff = y - (double)f, slack = y * 7.105427357601002e-15; // 2^-47
+	if (diff > 0.5 * ulp - slack || -diff > below - slack) { return (float)(1.0 / sqrt((double)x)); }
+	return f;
+}
+
+__global__ void __launch_bounds__(256) selftest_rsqrt_kernel(uint32_t firstBits, uint32_t count, unsigned long long *mismatches) {
+	unsigned long long bad = 0;
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+		const float x = __uint_as_float(firstBits + i);
+		const float fast = reference_rsqrt(x), literal = (float)(1.0 / sqrt((double)x));
+		if (__float_as_uint(fast) != __float_as_uint(literal) && !(fast != fast && literal != literal)) { bad++; }
+	}
+	if (bad) { atomicAdd(mismatches, bad); }
+}
+
 struct PointLightParams {
 	int32_t left, top, width, height; // lane-aligned rectangle (ref: lightAPI.cpp:76-105)
 	int32_t laneCount;
@@ -292,7 +322,7 @@ __global__ void __launch_bounds__(256) point_light_kernel(Img light, Img normal,
 		float nx = ((float)(nc & 255u) - 128.0f) * (-1.0f / 128.0f), ny = ((float)((nc >> 8) & 255u) - 128.0f) * (-1.0f / 128.0f), nz = ((float)((nc >> 16) & 255u) - 128.0f) * (-1.0f / 128.0f);
 		float distanceIntensity = 1.0f - 2.0f * lightRatio + lightRatio * lightRatio;
 		// scalar-build reciprocalSquareRoot: the quotient is formed in double (ref: base/simd.h:4104, see oracle/dfpsr_oracle.c)
-		float rs = (float)(1.0 / sqrt((double)sq));
+		float rs = reference_rsqrt(sq);
 		float dot = ((ox * rs) * nx) + ((oy * rs) * ny) + ((oz * rs) * nz);
 		float in = (dot > 0.0f ? dot : 0.0f) * distanceIntensity;
 		if (p.shadow) { in = in * shadow_transparency(cube, p.cubeCenter, ox, oy, oz); }
@@ -377,7 +407,7 @@ __global__ void __launch_bounds__(256) light_frame_kernel(Img color, Img diffuse
 						if (1.0f < lightRatio) { lightRatio = 1.0f; }
 						const float nx = ((float)(nc[i] & 255u) - 128.0f) * (-1.0f / 128.0f), ny = ((float)((nc[i] >> 8) & 255u) - 128.0f) * (-1.0f / 128.0f), nz = ((float)((nc[i] >> 16) & 255u) - 128.0f) * (-1.0f / 128.0f);
 						const float distanceIntensity = 1.0f - 2.0f * lightRatio + lightRatio * lightRatio;
-						const float rs = (float)(1.0 / sqrt((double)sq)); // scalar-build reciprocalSquareRoot (ref: base/simd.h:4104)
+						const float rs = reference_rsqrt(sq); // scalar-build reciprocalSquareRoot (ref: base/simd.h:4104)
 						const float dot = ((ox * rs) * nx) + ((oy * rs) * ny) + ((oz * rs) * nz);
 						float in = (dot > 0.0f ? dot : 0.0f) * distanceIntensity;
 						if (p.shadow) { in = in * shadow_transparency(fl.cube, p.cubeCenter, ox, oy, oz); }
@@ -1007,3 +1037,22 @@ static int resize_single(const Img &target, const Img &source, bool bilinear, bo
 }
 
 } // namespace dfpsr
+
+extern "C" int dfpsr_selftest_rsqrt(uint32_t firstBits, uint32_t count, uint64_t *mismatchesHost, void *stream) {
+	DFPSR_REQUIRE(mismatchesHost != nullptr, "selftest_rsqrt: null output");
+	unsigned long long *counter = nullptr;
+	DFPSR_CHECK_CUDA(cudaMalloc((void **)&counter, sizeof(unsigned long long)));
+	cudaError_t err = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), dfpsr::as_stream(stream));
+	if (err == cudaSuccess && count > 0) {
+		dfpsr::selftest_rsqrt_kernel<<<dfpsr::sm_count() * 8, 256, 0, dfpsr::as_stream(stream)>>>(firstBits, count, counter);
+		dfpsr::g_launches++;
+		err = cudaGetLastError();
+	}
+	unsigned long long result = 0;
+	if (err == cudaSuccess) { err = cudaMemcpyAsync(&result, counter, sizeof(result), cudaMemcpyDeviceToHost, dfpsr::as_stream(stream)); }
+	if (err == cudaSuccess) { err = cudaStreamSynchronize(dfpsr::as_stream(stream)); }
+	cudaFree(counter);
+	if (err != cudaSuccess) { dfpsr::set_error("selftest_rsqrt: %s", cudaGetErrorString(err)); return 1; }
+	*mismatchesHost = (uint64_t)result;
+	return 0;
+}

@@ -1847,7 +1847,11 @@ static int add_model_task(dfpsr_renderer *r, int32_t view, const dfpsr_model *mo
 	// ref: api/modelAPI.cpp:228 — whole-model culling against the cull frustum on the host
 	if (!dfpsr_camera_is_box_seen(camera, model->minBound, model->maxBound, modelToWorld)) { return 0; }
 	if (model->polygonCount <= 0) { return 0; }
-	TaskParams task;
+	const int32_t diffuseIndex = r->depthOnly ? -1 : register_texture(r, &model->diffuse);
+	const int32_t lightIndex = r->depthOnly ? -1 : register_texture(r, &model->light);
+	DFPSR_REQUIRE(diffuseIndex != -2 && lightIndex != -2, "more than %d distinct textures in one frame", MAX_TEXTURES);
+	r->tasks.emplace_back(); // filled in place: a Sandbox frame queues hundreds of 400-byte tasks
+	TaskParams &task = r->tasks.back();
 	memset(&task, 0, sizeof(task));
 	task.points = model->points;
 	task.polygons = model->polygons;
@@ -1858,10 +1862,8 @@ static int add_model_task(dfpsr_renderer *r, int32_t view, const dfpsr_model *mo
 	task.camera = *camera;
 	task.filter = model->filter;
 	task.depthOnly = r->depthOnly ? 1 : 0;
-	task.diffuseIndex = r->depthOnly ? -1 : register_texture(r, &model->diffuse);
-	task.lightIndex = r->depthOnly ? -1 : register_texture(r, &model->light);
-	DFPSR_REQUIRE(task.diffuseIndex != -2 && task.lightIndex != -2, "more than %d distinct textures in one frame", MAX_TEXTURES);
-	r->tasks.push_back(task);
+	task.diffuseIndex = diffuseIndex;
+	task.lightIndex = lightIndex;
 	return 0;
 }
 

@@ -122,6 +122,7 @@ SIGNATURES = {
     "dfpsr_session_upload_model": (i32, [vp, P(abi.HostModel), P(i32)]),
     "dfpsr_session_render_views_host": (i32, [vp, i32, P(abi.Transform3D), vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, vp]),
     "dfpsr_session_render_frame_host": (i32, [vp, i32, P(abi.Transform3D), P(abi.Camera), vp, i32, vp, i32, i32, i32, i32, i32, vp]),
+    "dfpsr_selftest_rsqrt": (i32, [u32, u32, P(u64), vp]),
     "dfpsr_peer_alloc": (i32, [P(vp), sz, vp]),
     "dfpsr_peer_free": (i32, [vp]),
     "dfpsr_peer_open": (i32, [P(vp), vp]),

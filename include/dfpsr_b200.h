@@ -494,6 +494,11 @@ int dfpsr_session_render_frame_host(dfpsr_session *session, int32_t slot, const 
  * previous one; pinned host images (dfpsr_malloc_host) make the copies asynchronous. Returns after everything has arrived. */
 int dfpsr_session_render_views_host(dfpsr_session *session, int32_t slot, const dfpsr_transform3d *modelToWorld, const dfpsr_camera *cameras, int32_t count, uint32_t *const *colorHost, int32_t colorStride, float *const *depthHost, int32_t depthStride, int32_t width, int32_t height, int32_t packOrder, int32_t uploadGeometry, void *stream);
 
+/* Diagnostic: the point light's reciprocal square root (ref: base/simd.h:4104, (float)(1.0 / sqrt((double)x)) in the scalar build) is evaluated
+ * on the device without FP64 sqrt / division plus an exact fallback; this compares it with the literal expression for the `count` floats whose
+ * bit patterns start at firstBits and returns the number of differing results (must be 0). */
+int dfpsr_selftest_rsqrt(uint32_t firstBits, uint32_t count, uint64_t *mismatchesHost, void *stream);
+
 /* ---------------------------------------------------------------- strip-sharded frames over NVLink peer memory */
 
 /* One frame split into row strips across GPUs (one process per GPU): the reference's workers all write their strip into the same target

@@ -304,3 +304,17 @@ def test_filter_map_affine_streaming(cuda, oracle, packs):
         e = np.zeros((th, tw), np.uint32)
         oracle.orc_filter_map(C.byref(OI(e, packs[1])), abi.MAP_AFFINE, orcbind.ptr(prm), C.byref(OI(src, packs[0])), sx, sy)
         assert_same_u32(host_u32(tt), e, f"affine map {tw}x{th} at ({sx},{sy})")
+
+
+def test_reference_rsqrt_fast_path_equals_the_literal_expression():
+    """The point light's reciprocal square root is (float)(1.0 / sqrt((double)x)) in the reference's scalar build (base/simd.h:4104). The
+    kernels evaluate it with a 22-bit seed + two Newton steps in double and fall back to the literal expression near float rounding
+    boundaries; dfpsr_selftest_rsqrt compares both on the device. Every float of 44 binades (squared light distances live in a few of
+    them) plus zeros, denormals, infinities, NaNs and negative inputs."""
+    cuda = lib.load()
+    bad = C.c_uint64(1)
+    lib.check(cuda.dfpsr_selftest_rsqrt(0x3A000000, 0x50000000 - 0x3A000000, C.byref(bad), lib.stream_ptr()))
+    assert bad.value == 0
+    for first, count in ((0, 1 << 20), (0x7F000000, 1 << 24), (0x80000000, 1 << 20), (0xBF000000, 1 << 20), (0x00700000, 1 << 21)):
+        lib.check(cuda.dfpsr_selftest_rsqrt(first, count, C.byref(bad), lib.stream_ptr()))
+        assert bad.value == 0, hex(first)

@@ -337,7 +337,7 @@ def main():
     if rank == 0 and not args.no_extras:
         try:
             import bench_extras
-            extras = bench_extras.run(cuda, lib)
+            extras = bench_extras.run(cuda, lib, cpu=not args.no_cpu_baseline)
         except Exception as exc:  # secondary numbers must never break the headline line
             extras = {"error": repr(exc)}
 

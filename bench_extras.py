@@ -24,7 +24,54 @@ def _time(torch, fn, warmup=3, iters=10):
     return start.elapsed_time(stop) / iters
 
 
-def run(cuda, lib):
+def cpu_reference(out):
+    """The unmodified reference (oracle/_ref SSE2 build, its own worker threads) on the host cores for configs 3 and 5, written next to the
+    device numbers (reported baseline only; oracle/_ref is test infrastructure). The reference renders tiny triangles through
+    renderer_begin / giveTask / end and runs its filters single-threaded; filter_mapRgbaU8 is timed with the wrapper's C++ lambda."""
+    import refbind
+    import sandbox_scene
+    from dfpsr_b200 import abi, scenes
+    if not refbind.available("sse"):
+        return
+    ref = refbind.Ref("sse")
+    threads = int(ref.lib.ref_thread_count())
+    if "tiny_triangles_4k" in out:
+        nx, nz = 1000, 999
+        sc = scenes.tiny_triangle_scene(nx, nz)
+        model = ref.model(sc["points"], sc["polygons"])
+        col, dep = ref.rgba(shape=(2160, 3840)), ref.f32(shape=(2160, 3840))
+        cam = scenes.top_down_camera(nx, nz, 3840, 2160)
+        times = []
+        for _ in range(3):
+            ref.lib.ref_image_fill_rgba(col, 0, 0, 0, 0)
+            ref.lib.ref_image_fill_f32(dep, 0.0)
+            t0 = time.perf_counter()
+            ref.render(model, cam, col, dep, mode=1)
+            times.append(1000.0 * (time.perf_counter() - t0))
+        ref.free_all()
+        e = out["tiny_triangles_4k"]
+        e["cpu_reference_ms"] = min(times[1:])
+        e["cpu_reference_threads"] = threads
+        e["speedup_vs_cpu_reference"] = e["cpu_reference_ms"] / e["ms"]
+    if "filter_chain_8192" in out:
+        size = 8192
+        src = ref.lib.ref_image_create_rgba(size, size, abi.PACK_RGBA)
+        ref.lib.ref_filter_map(src, abi.MAP_XOR_PATTERN, None, -1, 0, 0)
+        mapped = ref.lib.ref_image_create_rgba(size, size, abi.PACK_RGBA)
+        params = np.array(sandbox_scene.CHAIN_AFFINE, np.int32)
+        t0 = time.perf_counter()
+        ref.lib.ref_filter_map(mapped, abi.MAP_AFFINE, refbind.ptr(params), src, 0, 0)
+        t1 = time.perf_counter()
+        ref.lib.ref_filter_resize(mapped, abi.SAMPLER_LINEAR, size // 2, size // 2)
+        t2 = time.perf_counter()
+        ref.free_all()
+        e = out["filter_chain_8192"]
+        e["cpu_reference_map_ms"], e["cpu_reference_resize_down_ms"] = 1000.0 * (t1 - t0), 1000.0 * (t2 - t1)
+        e["cpu_reference_threads"] = 1
+        e["speedup_vs_cpu_reference"] = (e["cpu_reference_map_ms"] + e["cpu_reference_resize_down_ms"]) / e["chain_ms"]
+
+
+def run(cuda, lib, cpu=True):
     import torch
     import sandbox_scene
     from dfpsr_b200 import abi, scenes
@@ -152,4 +199,10 @@ def run(cuda, lib):
         "chain_ms": ms_map + ms_down, "chain_gb_s": (map_bytes + down_bytes) / (ms_map + ms_down) / 1e6,
         "chain_frac_of_hbm_peak": (map_bytes + down_bytes) / (ms_map + ms_down) / 1e6 / peak,
     }
+    del src, mapped, half, up, scratch
+    if cpu:
+        try:
+            cpu_reference(out)
+        except Exception as exc:
+            out["cpu_reference_error"] = repr(exc)
     return out

@@ -317,7 +317,7 @@ __global__ void __launch_bounds__(256) point_light_kernel(Img light, Img normal,
 		float oz = sChain[k * 3 * lanes + 2 * lanes + l] + (p.faceZ * h);
 		float sq = (ox * ox) + (oy * oy) + (oz * oz);
 		float lightRatio = sqrtf(sq) * p.reciprocalRadius;
-		if (1.0f < lightRatio) { lightRatio = 1.0f; }
+		if (lightRatio >= 1.0f) { continue; } // the distance term is (1 - 2) + 1 = 0 exactly: this light adds zero bytes here
 		uint32_t nc = *px_u32(normal, x, y);
 		float nx = ((float)(nc & 255u) - 128.0f) * (-1.0f / 128.0f), ny = ((float)((nc >> 8) & 255u) - 128.0f) * (-1.0f / 128.0f), nz = ((float)((nc >> 16) & 255u) - 128.0f) * (-1.0f / 128.0f);
 		float distanceIntensity = 1.0f - 2.0f * lightRatio + lightRatio * lightRatio;
@@ -325,6 +325,7 @@ __global__ void __launch_bounds__(256) point_light_kernel(Img light, Img normal,
 		float rs = reference_rsqrt(sq);
 		float dot = ((ox * rs) * nx) + ((oy * rs) * ny) + ((oz * rs) * nz);
 		float in = (dot > 0.0f ? dot : 0.0f) * distanceIntensity;
+		if (in == 0.0f) { continue; } // zero times the shadow term (0 or 1) stays zero
 		if (p.shadow) { in = in * shadow_transparency(cube, p.cubeCenter, ox, oy, oz); }
 		uint32_t *t = px_u32(light, x, y);
 		*t = sat_add_bytes(*t, light_pack(in * p.colorR, in * p.colorG, in * p.colorB));
@@ -404,12 +405,15 @@ __global__ void __launch_bounds__(256) light_frame_kernel(Img color, Img diffuse
 						const float oz = chain[k * 12 + 8 + l] + (p.faceZ * h[i]);
 						const float sq = (ox * ox) + (oy * oy) + (oz * oz);
 						float lightRatio = sqrtf(sq) * p.reciprocalRadius;
-						if (1.0f < lightRatio) { lightRatio = 1.0f; }
+						// At or beyond the radius the ratio clamps to 1 and the distance term is (1 - 2) + 1 = 0 exactly: the pixel receives
+						// max(dot, 0) * 0 = 0 from this light (the corners of the light's square, a fifth of it), and adding zero bytes changes nothing.
+						if (lightRatio >= 1.0f) { continue; }
 						const float nx = ((float)(nc[i] & 255u) - 128.0f) * (-1.0f / 128.0f), ny = ((float)((nc[i] >> 8) & 255u) - 128.0f) * (-1.0f / 128.0f), nz = ((float)((nc[i] >> 16) & 255u) - 128.0f) * (-1.0f / 128.0f);
 						const float distanceIntensity = 1.0f - 2.0f * lightRatio + lightRatio * lightRatio;
 						const float rs = reference_rsqrt(sq); // scalar-build reciprocalSquareRoot (ref: base/simd.h:4104)
 						const float dot = ((ox * rs) * nx) + ((oy * rs) * ny) + ((oz * rs) * nz);
 						float in = (dot > 0.0f ? dot : 0.0f) * distanceIntensity;
+						if (in == 0.0f) { continue; } // faces away from the light: zero times the shadow term (0 or 1) stays zero
 						if (p.shadow) { in = in * shadow_transparency(fl.cube, p.cubeCenter, ox, oy, oz); }
 						acc[i] = sat_add_bytes(acc[i], light_pack(in * p.colorR, in * p.colorG, in * p.colorB));
 					}

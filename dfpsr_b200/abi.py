@@ -190,3 +190,12 @@ def camera_params(perspective, location, width, height, width_slope=1.0, near=0.
     c.nearClip = float(np.float32(near))
     c.farClip = float(np.float32(far))
     return c
+
+
+class ImportedPart(C.Structure):
+    _fields_ = [("name", C.c_char * 64), ("diffuseName", C.c_char * 64), ("lightName", C.c_char * 64), ("firstPolygon", C.c_int32), ("polygonCount", C.c_int32)]
+
+
+class ImportedModel(C.Structure):
+    _fields_ = [("points", C.POINTER(C.c_float)), ("pointCount", C.c_int32), ("polygons", C.c_void_p), ("polygonCount", C.c_int32),
+                ("parts", C.POINTER(ImportedPart)), ("partCount", C.c_int32), ("filter", C.c_int32), ("minBound", C.c_float * 3), ("maxBound", C.c_float * 3)]

@@ -14,6 +14,8 @@
 
 #include <cstdint>
 #include <cstring>
+#include <cstdio>
+#include <utility>
 #include <cmath>
 #include <limits>
 #include <memory>
@@ -352,7 +354,9 @@ inline int32_t b200_add_polygon(Model &model, int32_t partIndex, int32_t a, int3
 	dfpsr_polygon polygon;
 	std::memset(&polygon, 0, sizeof(polygon));
 	polygon.pointIndices[0] = a; polygon.pointIndices[1] = b; polygon.pointIndices[2] = c; polygon.pointIndices[3] = d;
-	for (int v = 0; v < 4; v++) { for (int ch = 0; ch < 4; ch++) { polygon.colors[v][ch] = 1.0f; } } // ref: Model.h:30-52 default white, texcoords 0
+	// ref: Model.cpp:74-103 Polygon(indexA, indexB, indexC[, indexD]): white corners, texture coordinates spanning the whole texture
+	static const float cornerTexCoords[4][4] = {{0.0f, 0.0f, 0.0f, 0.0f}, {1.0f, 0.0f, 1.0f, 0.0f}, {1.0f, 1.0f, 1.0f, 1.0f}, {0.0f, 1.0f, 0.0f, 1.0f}};
+	for (int v = 0; v < 4; v++) { for (int ch = 0; ch < 4; ch++) { polygon.colors[v][ch] = 1.0f; polygon.texCoords[v][ch] = cornerTexCoords[v][ch]; } }
 	part->polygons.push_back(polygon);
 	part->dirty = true;
 	return (int32_t)part->polygons.size() - 1;
@@ -378,6 +382,55 @@ inline TextureRgbaU8 model_getDiffuseMap(const Model &model, int32_t partIndex) 
 inline TextureRgbaU8 model_getLightMap(const Model &model, int32_t partIndex) { B200Part *p = b200_part(model, partIndex, "model_getLightMap"); return p ? p->lightMap : TextureRgbaU8(); }
 
 // Uploads whatever changed since the last draw and returns one dfpsr_model per part (the C ABI's model has one part).
+// ---------------------------------------------------------------- importers (ref: SDK/SpriteEngine/importer.h, api/modelAPI.h:303-319)
+// Textures are resolved by the caller: `textureNames`, when given, receives per part {diffuse name, light name} ("" when the shader has none);
+// the reference's ResourcePool decodes image files, which is outside the path.
+inline Model b200_model_from_import(dfpsr_imported_model &imported, std::vector<std::pair<std::string, std::string>> *textureNames) {
+	Model model = model_create();
+	model->filter = imported.filter == DFPSR_FILTER_ALPHA ? Filter::Alpha : Filter::Solid;
+	model->points.assign(imported.points, imported.points + 3 * (size_t)imported.pointCount);
+	model->minBound = FVector3D(imported.minBound[0], imported.minBound[1], imported.minBound[2]);
+	model->maxBound = FVector3D(imported.maxBound[0], imported.maxBound[1], imported.maxBound[2]);
+	for (int32_t p = 0; p < imported.partCount; p++) {
+		const dfpsr_imported_part &part = imported.parts[p];
+		model->parts.emplace_back();
+		model->parts.back().name = part.name;
+		model->parts.back().polygons.assign(imported.polygons + part.firstPolygon, imported.polygons + part.firstPolygon + part.polygonCount);
+		if (textureNames) { textureNames->push_back({part.diffuseName, part.lightName}); }
+	}
+	dfpsr_import_free(&imported);
+	return model;
+}
+// ref: SDK/SpriteEngine/importer.cpp:52-262 loadPlyModel on file content
+inline Model importer_loadModelFromContent(const std::string &plyContent, bool flipX, const Transform3D &axisConversion) {
+	dfpsr_imported_model imported;
+	const dfpsr_transform3d axis = b200_pod(axisConversion);
+	b200_check(dfpsr_import_ply(plyContent.data(), plyContent.size(), flipX ? 1 : 0, &axis, &imported));
+	return b200_model_from_import(imported, nullptr);
+}
+// ref: SDK/SpriteEngine/importer.cpp:280-290 importer_loadModel(filename, flipX, axisConversion); only PLY, like the reference
+inline Model importer_loadModel(const std::string &filename, bool flipX, const Transform3D &axisConversion) {
+	const size_t dot = filename.find_last_of('.');
+	if (dot == std::string::npos) { throwError("The model's filename " + filename + " does not have an extension!"); }
+	std::string extension = filename.substr(dot + 1);
+	for (char &c : extension) { if (c >= 'a' && c <= 'z') { c = (char)(c - 'a' + 'A'); } }
+	if (extension != "PLY") { throwError("The extension " + extension + " in " + filename + " is not yet supported!"); }
+	FILE *file = std::fopen(filename.c_str(), "rb");
+	if (!file) { throwError("Failed to load " + filename); }
+	std::string content;
+	char block[65536];
+	size_t got;
+	while ((got = std::fread(block, 1, sizeof(block), file)) > 0) { content.append(block, got); }
+	std::fclose(file);
+	return importer_loadModelFromContent(content, flipX, axisConversion);
+}
+// ref: api/modelAPI.h:319 importFromContent_DMF1(fileContent, pool, detailLevel = 2)
+inline Model importFromContent_DMF1(const std::string &fileContent, int32_t detailLevel = 2, std::vector<std::pair<std::string, std::string>> *textureNames = nullptr) {
+	dfpsr_imported_model imported;
+	b200_check(dfpsr_import_dmf1(fileContent.data(), fileContent.size(), detailLevel, &imported));
+	return b200_model_from_import(imported, textureNames);
+}
+
 inline std::vector<dfpsr_model> b200_device_models(const Model &model) {
 	std::vector<dfpsr_model> result;
 	if (!model || model->points.empty()) { return result; }

@@ -123,6 +123,9 @@ SIGNATURES = {
     "dfpsr_session_render_views_host": (i32, [vp, i32, P(abi.Transform3D), vp, i32, vp, i32, vp, i32, i32, i32, i32, i32, vp]),
     "dfpsr_session_render_frame_host": (i32, [vp, i32, P(abi.Transform3D), P(abi.Camera), vp, i32, vp, i32, i32, i32, i32, i32, vp]),
     "dfpsr_selftest_rsqrt": (i32, [u32, u32, P(u64), vp]),
+    "dfpsr_import_ply": (i32, [C.c_char_p, sz, i32, P(abi.Transform3D), P(abi.ImportedModel)]),
+    "dfpsr_import_dmf1": (i32, [C.c_char_p, sz, i32, P(abi.ImportedModel)]),
+    "dfpsr_import_free": (None, [P(abi.ImportedModel)]),
     "dfpsr_peer_alloc": (i32, [P(vp), sz, vp]),
     "dfpsr_peer_free": (i32, [vp]),
     "dfpsr_peer_open": (i32, [P(vp), vp]),
@@ -165,6 +168,34 @@ def profile_snapshot():
         check(handle.dfpsr_profile_read(i, C.byref(name), C.byref(ms), C.byref(n)))
         out[name.value.decode()] = (ms.value, n.value)
     return out
+
+
+def imported_arrays(model):
+    """(points (n, 3) float32, polygons (POLYGON_DTYPE), parts [(name, diffuse, light, first, count)]) copied out of a dfpsr_imported_model."""
+    pts = np.ctypeslib.as_array(model.points, shape=(model.pointCount * 3,)).reshape(-1, 3).copy() if model.pointCount else np.zeros((0, 3), np.float32)
+    if model.polygonCount:
+        raw = C.string_at(model.polygons, model.polygonCount * abi.POLYGON_DTYPE.itemsize)
+        polys = np.frombuffer(raw, dtype=abi.POLYGON_DTYPE).copy()
+    else:
+        polys = np.zeros(0, abi.POLYGON_DTYPE)
+    parts = [(model.parts[i].name.decode(), model.parts[i].diffuseName.decode(), model.parts[i].lightName.decode(), model.parts[i].firstPolygon, model.parts[i].polygonCount) for i in range(model.partCount)]
+    return pts, polys, parts
+
+
+def import_model(kind, text, flip_x=False, axis=None, detail_level=2):
+    """dfpsr_import_ply / dfpsr_import_dmf1 on a str or bytes; returns (points, polygons, parts, filter, (min, max))."""
+    handle = load()
+    data = text.encode("utf-8") if isinstance(text, str) else bytes(text)
+    out = abi.ImportedModel()
+    if kind == "ply":
+        check(handle.dfpsr_import_ply(data, len(data), 1 if flip_x else 0, C.byref(axis) if axis is not None else None, C.byref(out)))
+    else:
+        check(handle.dfpsr_import_dmf1(data, len(data), detail_level, C.byref(out)))
+    try:
+        pts, polys, parts = imported_arrays(out)
+        return pts, polys, parts, out.filter, (list(out.minBound), list(out.maxBound))
+    finally:
+        handle.dfpsr_import_free(C.byref(out))
 
 
 def stream_ptr(stream=None):

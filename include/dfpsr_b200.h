@@ -494,6 +494,31 @@ int dfpsr_session_render_frame_host(dfpsr_session *session, int32_t slot, const 
  * previous one; pinned host images (dfpsr_malloc_host) make the copies asynchronous. Returns after everything has arrived. */
 int dfpsr_session_render_views_host(dfpsr_session *session, int32_t slot, const dfpsr_transform3d *modelToWorld, const dfpsr_camera *cameras, int32_t count, uint32_t *const *colorHost, int32_t colorStride, float *const *depthHost, int32_t depthStride, int32_t width, int32_t height, int32_t packOrder, int32_t uploadGeometry, void *stream);
 
+/* ---------------------------------------------------------------- scene formats feeding the path (host side, no GPU needed) */
+
+/* One part of an imported model: polygons [firstPolygon, firstPolygon + polygonCount) and the texture names its shader asks for
+ * (DMF1: M_Diffuse_1Tex / M_Diffuse_2Tex -> Texture[0] / Texture[1]; empty when absent, ref: dmf1.cpp:336-347). */
+typedef struct dfpsr_imported_part {
+	char name[64], diffuseName[64], lightName[64];
+	int32_t firstPolygon, polygonCount;
+} dfpsr_imported_part;
+/* Host arrays in the layout dfpsr_host_model / dfpsr_model take; released with dfpsr_import_free. */
+typedef struct dfpsr_imported_model {
+	float *points; int32_t pointCount;
+	dfpsr_polygon *polygons; int32_t polygonCount;
+	dfpsr_imported_part *parts; int32_t partCount;
+	int32_t filter;
+	float minBound[3], maxBound[3];
+} dfpsr_imported_model;
+/* ref: SDK/SpriteEngine/importer.cpp:52-290 importer_loadModel for ASCII PLY 1.0 (vertex x/y/z/red/green/blue/alpha as float or uchar,
+ * face vertex_indices lists: quads kept, other polygons fanned; flipX mirrors and reverses the winding; axisConversion may be NULL). */
+int dfpsr_import_ply(const char *content, size_t length, int32_t flipX, const dfpsr_transform3d *axisConversion, dfpsr_imported_model *out);
+/* ref: DFPSR/implementation/render/model/format/dmf1.cpp importFromContent_DMF1(content, pool, detailLevel): parts within the detail
+ * level, points merged within 0.00001, per-vertex colours and two texture coordinate sets. Textures are returned by NAME (the
+ * reference resolves them through a ResourcePool; decoding image files is outside the path). */
+int dfpsr_import_dmf1(const char *content, size_t length, int32_t detailLevel, dfpsr_imported_model *out);
+void dfpsr_import_free(dfpsr_imported_model *model);
+
 /* Diagnostic: the point light's reciprocal square root (ref: base/simd.h:4104, (float)(1.0 / sqrt((double)x)) in the scalar build) is evaluated
  * on the device without FP64 sqrt / division plus an exact fallback; this compares it with the literal expression for the `count` floats whose
  * bit patterns start at firstBits and returns the number of differing results (must be 0). */

@@ -23,6 +23,8 @@
 #include <cstring>
 #include <chrono>
 #include <cstdlib>
+#include <cstdio>
+#include <string>
 #include <new>
 
 using namespace dsr;
@@ -673,6 +675,76 @@ void ref_world_read_buffers(int world, uint32_t *diffuse, uint32_t *normal, uint
 		if (light) { memcpy(light + (size_t)y * width, image_getSafePointer<uint32_t>(w->lightBuffer, y).getUnsafe(), (size_t)width * 4); }
 		if (height) { memcpy(height + (size_t)y * width, image_getSafePointer<float>(w->heightBuffer, y).getUnsafe(), (size_t)width * 4); }
 	}
+}
+
+} // extern "C"
+
+// ---- model importers (SDK/SpriteEngine/importer.cpp, DFPSR/implementation/render/model/format/dmf1.cpp)
+
+// A resource pool that loads nothing and remembers which texture names the importer asked for, in order.
+struct NameOnlyPool : public ResourcePool {
+	std::vector<std::string> requested;
+	static std::string narrow(const ReadableString &text) { std::string r; for (intptr_t i = 0; i < string_length(text); i++) { r.push_back((char)text[i]); } return r; }
+	const ImageRgbaU8 fetchImageRgba(const ReadableString &name) override { requested.push_back(narrow(name)); return ImageRgbaU8(); }
+	const TextureRgbaU8 fetchTextureRgba(const ReadableString &name, int32_t resolutions) override { (void)resolutions; requested.push_back(narrow(name)); return TextureRgbaU8(); }
+};
+static std::vector<std::vector<std::string>> g_importNames; // per imported model: texture names in request order
+
+extern "C" {
+
+// importer_loadModel(filename, flipX, axisConversion) on a PLY file; returns a model id (read it back with ref_model_dump*)
+int ref_import_ply(const char *filename, int flipX, const dfpsr_transform3d *axisConversion) {
+	ensureStarted();
+	Model model = importer_loadModel(String(filename), flipX != 0, toTransform(axisConversion));
+	g_models.push_back(model);
+	g_importNames.resize(g_models.size());
+	return (int)g_models.size() - 1;
+}
+
+int ref_import_dmf1(const char *content, int detailLevel) {
+	ensureStarted();
+	NameOnlyPool pool;
+	Model model = importFromContent_DMF1(String(content), pool, detailLevel);
+	g_models.push_back(model);
+	g_importNames.resize(g_models.size());
+	g_importNames.back() = pool.requested;
+	return (int)g_models.size() - 1;
+}
+
+// counts[0] = points, counts[1] = parts, counts[2] = polygons over all parts, counts[3] = filter, counts[4] = requested texture names
+void ref_model_dump_counts(int model, int *counts) {
+	const Model &m = g_models[model];
+	counts[0] = model_getNumberOfPoints(m); counts[1] = model_getNumberOfParts(m); counts[2] = 0;
+	for (int p = 0; p < counts[1]; p++) { counts[2] += model_getNumberOfPolygons(m, p); }
+	counts[3] = model_getFilter(m) == Filter::Alpha ? DFPSR_FILTER_ALPHA : DFPSR_FILTER_SOLID;
+	counts[4] = (size_t)model < g_importNames.size() ? (int)g_importNames[model].size() : 0;
+}
+
+// points: 3 floats each; polygons in part order (dfpsr_polygon = the reference's Polygon layout); polygonsPerPart: one count per part
+void ref_model_dump(int model, float *points, dfpsr_polygon *polygons, int *polygonsPerPart) {
+	const Model &m = g_models[model];
+	for (int i = 0; i < model_getNumberOfPoints(m); i++) { FVector3D p = model_getPoint(m, i); points[3 * i] = p.x; points[3 * i + 1] = p.y; points[3 * i + 2] = p.z; }
+	int at = 0;
+	for (int p = 0; p < model_getNumberOfParts(m); p++) {
+		const List<Polygon> &source = m->partBuffer[p].polygonBuffer;
+		polygonsPerPart[p] = (int)source.length();
+		for (int i = 0; i < (int)source.length(); i++, at++) {
+			dfpsr_polygon &dst = polygons[at];
+			for (int c = 0; c < 4; c++) {
+				dst.pointIndices[c] = source[i].pointIndices[c];
+				dst.texCoords[c][0] = source[i].texCoords[c].x; dst.texCoords[c][1] = source[i].texCoords[c].y; dst.texCoords[c][2] = source[i].texCoords[c].z; dst.texCoords[c][3] = source[i].texCoords[c].w;
+				dst.colors[c][0] = source[i].colors[c].x; dst.colors[c][1] = source[i].colors[c].y; dst.colors[c][2] = source[i].colors[c].z; dst.colors[c][3] = source[i].colors[c].w;
+			}
+		}
+	}
+}
+
+// name of part `part` (index >= 0) or requested texture name number -1 - part; truncated to size - 1 characters
+void ref_model_dump_name(int model, int part, char *out, int size) {
+	std::string text;
+	if (part >= 0) { text = NameOnlyPool::narrow(model_getPartName(g_models[model], part)); }
+	else { text = g_importNames[model][(size_t)(-1 - part)]; }
+	snprintf(out, (size_t)size, "%s", text.c_str());
 }
 
 } // extern "C"

@@ -75,6 +75,8 @@ def load(flavour="scalar"):
         "ref_world_set_camera_location": (None, [i, p]), "ref_world_get_camera_location": (None, [i, p]),
         "ref_world_move_camera_in_pixels": (None, [i, i, i]), "ref_world_set_camera_direction_index": (None, [i, i]),
         "ref_world_find_ground_at_pixel": (None, [i, i, i, i, p]),
+        "ref_import_ply": (i, [C.c_char_p, i, T]), "ref_import_dmf1": (i, [C.c_char_p, i]),
+        "ref_model_dump_counts": (None, [i, p]), "ref_model_dump": (None, [i, p, p, p]), "ref_model_dump_name": (None, [i, i, C.c_char_p, i]),
         "ref_world_draw": (None, [i, i]), "ref_world_read_buffers": (None, [i, p, p, p, p]),
     }
     for name, (res, args) in sig.items():
@@ -162,6 +164,29 @@ class Ref:
         out = np.zeros(len(pts), abi.PROJECTED_DTYPE)
         self.lib.ref_project_points(ptr(pts), len(pts), C.byref(m2w), C.byref(camera), ptr(out))
         return out
+
+    # ---- importers
+    def dump_model(self, model):
+        """(points, polygons, parts [(name, polygon count)], filter, requested texture names) of a reference model."""
+        counts = np.zeros(5, np.int32)
+        self.lib.ref_model_dump_counts(model, ptr(counts))
+        points = np.zeros((int(counts[0]), 3), np.float32)
+        polygons = np.zeros(int(counts[2]), abi.POLYGON_DTYPE)
+        per_part = np.zeros(max(int(counts[1]), 1), np.int32)
+        self.lib.ref_model_dump(model, ptr(points), ptr(polygons), ptr(per_part))
+
+        def name(index):
+            buf = C.create_string_buffer(256)
+            self.lib.ref_model_dump_name(model, index, buf, 256)
+            return buf.value.decode()
+        parts = [(name(k), int(per_part[k])) for k in range(int(counts[1]))]
+        return points, polygons, parts, int(counts[3]), [name(-1 - k) for k in range(int(counts[4]))]
+
+    def import_ply(self, path, flip_x=False, axis=None):
+        return self.dump_model(self.lib.ref_import_ply(path.encode(), 1 if flip_x else 0, C.byref(axis or abi.Transform3D.identity())))
+
+    def import_dmf1(self, text, detail_level=2):
+        return self.dump_model(self.lib.ref_import_dmf1(text.encode("utf-8"), detail_level))
 
     def free_all(self):
         self.lib.ref_free_all()

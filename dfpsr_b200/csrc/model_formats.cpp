@@ -1,4 +1,4 @@
-// importers.cpp — the scene formats that feed the path: ASCII PLY (ref: SDK/SpriteEngine/importer.cpp) and the
+// model_formats.cpp — the scene formats that feed the path: ASCII PLY (ref: SDK/SpriteEngine/importer.cpp) and the
 // reference's own DMF1 text format (ref: DFPSR/implementation/render/model/format/dmf1.cpp), parsed on the host into the point /
 // polygon arrays the C ABI takes (dfpsr_model, dfpsr_host_model). Host-only code: no kernel, no CUDA call. Numbers are read with the
 // reference's own digit-by-digit conversion (ref: api/stringAPI.cpp:1563-1620), not strtod, so every float equals the reference's.

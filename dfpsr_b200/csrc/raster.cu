@@ -1779,6 +1779,8 @@ struct dfpsr_renderer {
 	int64_t lastCommands = -1;
 	DeviceBuffer dTasks, dViews, projected, slotCounts, blockCmds, blockRows, tileCount, tileOffset, tileCursor, cmds, rows, tileList, chk, sortTmp, bigItems, bigUnits;
 	uint32_t *hostTotals = nullptr, *hostTotalsDevice = nullptr; // mapped pinned memory and its device alias
+	void *pinnedTasks = nullptr;                                 // page-locked staging for the task records (a pageable source of a few hundred
+	size_t pinnedTasksCapacity = 0;                              // KB makes cudaMemcpyAsync wait for everything queued on the stream before it)
 	// occlusion grid (ref: api/rendererAPI.cpp:145, :181-192): lives on the host, where occluder boxes and visibility queries are evaluated
 	std::vector<float> grid;
 	int32_t gridWidth = 0, gridHeight = 0, gridAllocW = 0, gridAllocH = 0;
@@ -1790,6 +1792,7 @@ struct dfpsr_renderer {
 		DeviceBuffer *all[] = {&dTasks, &dViews, &projected, &slotCounts, &blockCmds, &blockRows, &tileCount, &tileOffset, &tileCursor, &cmds, &rows, &tileList, &chk, &sortTmp, &bigItems, &bigUnits, &dGrid};
 		for (auto *b : all) { b->release(); }
 		if (hostTotals) { cudaFreeHost(hostTotals); }
+		if (pinnedTasks) { cudaFreeHost(pinnedTasks); }
 	}
 };
 
@@ -1923,7 +1926,19 @@ static int renderer_end_internal(dfpsr_renderer *r, cudaStream_t stream) {
 	if (r->tileCount.reserve(((size_t)tileTotal + 12) * 4) || r->tileOffset.reserve(((size_t)tileTotal + 1) * 4) || r->tileCursor.reserve(((size_t)tileTotal + 1) * 4)) { return 1; }
 	if (r->slotCounts.reserve((size_t)slotTotal * 4 + 16) || r->blockCmds.reserve((size_t)blockTotal * 4 + 16) || r->blockRows.reserve((size_t)blockTotal * 4 + 16)) { return 1; }
 	// pageable sources: cudaMemcpyAsync stages them before returning, so the vectors may change afterwards
-	if (taskCount > 0) { DFPSR_CHECK_CUDA(cudaMemcpyAsync(r->dTasks.ptr, r->tasks.data(), taskCount * sizeof(TaskParams), cudaMemcpyHostToDevice, stream)); }
+	if (taskCount > 0) {
+		// The records go through page-locked staging: the copy is then a plain DMA in stream order. The staging buffer is free again when this
+		// function returns (the wait for the set-up totals below comes after the copy on the same stream).
+		const size_t bytes = taskCount * sizeof(TaskParams);
+		if (bytes > r->pinnedTasksCapacity) {
+			if (r->pinnedTasks) { cudaFreeHost(r->pinnedTasks); r->pinnedTasks = nullptr; r->pinnedTasksCapacity = 0; }
+			const size_t grown = bytes + bytes / 2 + 4096;
+			DFPSR_CHECK_CUDA(cudaHostAlloc(&r->pinnedTasks, grown, cudaHostAllocDefault));
+			r->pinnedTasksCapacity = grown;
+		}
+		memcpy(r->pinnedTasks, r->tasks.data(), bytes);
+		DFPSR_CHECK_CUDA(cudaMemcpyAsync(r->dTasks.ptr, r->pinnedTasks, bytes, cudaMemcpyHostToDevice, stream));
+	}
 	DFPSR_CHECK_CUDA(cudaMemcpyAsync(r->dViews.ptr, r->views.data(), viewCount * sizeof(ViewDev), cudaMemcpyHostToDevice, stream));
 	DFPSR_CHECK_CUDA(cudaMemsetAsync(r->tileCount.ptr, 0, ((size_t)tileTotal + 12) * 4, stream)); // tile counts, cursors of empty frames, totals
 	if (taskCount == 0) { DFPSR_CHECK_CUDA(cudaMemsetAsync(r->tileCursor.ptr, 0, (size_t)tileTotal * 4, stream)); }

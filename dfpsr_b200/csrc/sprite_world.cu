@@ -871,7 +871,8 @@ static int execute_frame(dfpsr_sprite_world *w, const dfpsr_image *colorTarget, 
 			dim3 grid((unsigned)((maxW + 31) / 32), (unsigned)((maxH + 7) / 8), (unsigned)n);
 			DFPSR_LAUNCH(background_copy_kernel, grid, 256, 0, stream, (const CopyDev *)w->copyStaging.ptr + first, fDiffuse, fNormal, fHeight);
 		}
-		DFPSR_CHECK_CUDA(cudaStreamSynchronize(stream)); // `copies` is pageable host memory
+		// `copies` is pageable host memory: cudaMemcpyAsync has staged it before returning, so it may be reused at once. (Waiting for the
+		// stream here made every frame start by draining the previous frame's light pass: no overlap between frames.)
 		copies.clear();
 		return 0;
 	};

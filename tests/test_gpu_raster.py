@@ -456,3 +456,35 @@ def test_imported_models_render_bit_exact(cuda, oracle):
             exp_c, exp_d, commands = scene.render_oracle(oracle, cam, c0, d0)
             assert_same_u32(bits(got_d), bits(exp_d), f"{name} depth")
             assert_same_u32(got_c, exp_c, f"{name} colour")
+
+
+def test_large_batches_take_the_in_thread_small_triangle_path(cuda, oracle):
+    """Frames with up to 148 x 1024 slots send every triangle taller than one tile row to the unit queue; larger batches keep triangles of up
+    to 16 rows with their set-up thread (less queue traffic per triangle). Both must give the oracle's pixels: batches of 24 terrain views
+    (182 k slots, mip-mapped texture) and of 200 views of an alpha-filtered, partly clipped triangle soup (160 k slots)."""
+    import torch
+    ident = abi.Transform3D.identity()
+
+    def batch(scene, cam_params, w, h, check):
+        views = len(cam_params)
+        cams = (abi.Camera * views)(*[lib.camera(p) for p in cam_params])
+        color = torch.zeros((views, h, w), dtype=torch.int32, device="cuda")
+        depth = torch.zeros((views, h, w), dtype=torch.float32, device="cuda")
+        colors = (abi.Image * views)(*[lib.image(color[v]) for v in range(views)])
+        depths = (abi.Image * views)(*[lib.image(depth[v]) for v in range(views)])
+        lib.check(cuda.dfpsr_model_render_views(C.byref(scene.model.desc), C.byref(ident), colors, depths, cams, views, 1, lib.stream_ptr()))
+        for v in check:
+            ec, ed, _ = scene.render_oracle(oracle, cam_params[v], np.zeros((h, w), np.uint32), np.zeros((h, w), np.float32))
+            assert_same_u32(bits(host_f32(depth[v])), bits(ed), f"view {v} depth")
+            assert_same_u32(host_u32(color[v]), ec, f"view {v} colour")
+
+    sc = scenes.terrain_scene()
+    terrain = CudaScene(sc["points"], sc["polygons"], diffuse_level0=sc["texture"], diffuse_levels=5)
+    assert 24 * 2 * len(sc["polygons"]) > 148 * 1024
+    batch(terrain, [scenes.orbit_camera(5 * v, 320, 182) for v in range(24)], 320, 182, check=(0, 7, 23))
+
+    soup = scenes.random_soup(400, 77, extent=2.5, tri_size=0.6, textured=False)
+    assert 200 * 2 * len(soup["polygons"]) > 148 * 1024
+    alpha = CudaScene(soup["points"], soup["polygons"], abi.FILTER_ALPHA)
+    cams = [abi.camera_params(True, scenes.look_at_transform((3.0 * np.cos(0.1 * v), 0.5 + 0.01 * v, 3.0 * np.sin(0.1 * v)), (0, 0, 0)), 96, 64, near=0.5) for v in range(200)]
+    batch(alpha, cams, 96, 64, check=(0, 63, 199))

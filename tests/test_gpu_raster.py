@@ -488,3 +488,28 @@ def test_large_batches_take_the_in_thread_small_triangle_path(cuda, oracle):
     alpha = CudaScene(soup["points"], soup["polygons"], abi.FILTER_ALPHA)
     cams = [abi.camera_params(True, scenes.look_at_transform((3.0 * np.cos(0.1 * v), 0.5 + 0.01 * v, 3.0 * np.sin(0.1 * v)), (0, 0, 0)), 96, 64, near=0.5) for v in range(200)]
     batch(alpha, cams, 96, 64, check=(0, 63, 199))
+
+
+def test_terrain_1080p_view_batch_golden(cuda):
+    """BASELINE config 4 at full size: 48 orbit views of the terrain at 1920x1080 in ONE submission (the bench's path: more than 148 x 2048
+    units, so one thread per unit, and more than 148 x 1024 slots, so small triangles stay with their set-up thread). The views the
+    compiled reference was hashed on (tests/golden/make_golden.py) must come out with exactly those hashes."""
+    import torch
+    golden = {e["frame"]: e for e in json.load(open(GOLDEN))["terrain_1080p"]}
+    sc = scenes.terrain_scene()
+    scene = CudaScene(sc["points"], sc["polygons"], diffuse_level0=sc["texture"], diffuse_levels=5)
+    views, w, h = 48, 1920, 1080
+    cams = (abi.Camera * views)(*[lib.camera(scenes.orbit_camera(v, w, h)) for v in range(views)])
+    color = torch.empty((views, h, w), dtype=torch.int32, device="cuda")
+    depth = torch.empty((views, h, w), dtype=torch.float32, device="cuda")
+    colors = (abi.Image * views)(*[lib.image(color[v]) for v in range(views)])
+    depths = (abi.Image * views)(*[lib.image(depth[v]) for v in range(views)])
+    ident = abi.Transform3D.identity()
+    lib.check(cuda.dfpsr_model_render_views(C.byref(scene.model.desc), C.byref(ident), colors, depths, cams, views, 1, lib.stream_ptr()))
+    checked = 0
+    for frame, entry in golden.items():
+        if frame < views:
+            assert sha(host_f32(depth[frame])) == entry["depth_sha256"], f"frame {frame} depth"
+            assert sha(host_u32(color[frame])) == entry["color_sha256"], f"frame {frame} colour"
+            checked += 1
+    assert checked >= 3

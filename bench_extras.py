@@ -207,15 +207,21 @@ def run(cuda, lib, cpu=True):
     ms_map = _time(torch, lambda: lib.check(cuda.dfpsr_filter_map(C.byref(IM(mapped)), abi.MAP_AFFINE, prm.ctypes.data, 8, C.byref(IM(src)), 0, 0, s)))
     ms_down = _time(torch, lambda: lib.check(cuda.dfpsr_filter_resize(C.byref(IM(half)), C.byref(IM(mapped)), abi.SAMPLER_LINEAR, 0, None, s)))
     ms_up = _time(torch, lambda: lib.check(cuda.dfpsr_filter_resize(C.byref(IM(up)), C.byref(IM(half)), abi.SAMPLER_LINEAR, 0, scratch.data_ptr(), s)))
+    odd = torch.empty((3000, 5000), dtype=torch.int32, device="cuda")  # the reference's generic (16-bit weight) path: neither dimension is kept or halved
+    odd_scratch_bytes = int(cuda.dfpsr_filter_resize_scratch_bytes(size, size, 5000, 3000))
+    odd_scratch = torch.empty(max(odd_scratch_bytes // 4, 1), dtype=torch.int32, device="cuda")
+    ms_odd = _time(torch, lambda: lib.check(cuda.dfpsr_filter_resize(C.byref(IM(odd)), C.byref(IM(mapped)), abi.SAMPLER_LINEAR, 0, odd_scratch.data_ptr() if odd_scratch_bytes else None, s)))
+    odd_bytes = 4 * (size * size + 5000 * 3000)
     map_bytes, down_bytes = 8 * size * size, 4 * (size * size + (size // 2) ** 2)
     out["filter_chain_8192"] = {
         "map_ms": ms_map, "map_gb_s": map_bytes / ms_map / 1e6, "map_frac_of_hbm_peak": map_bytes / ms_map / 1e6 / peak,
         "resize_down_ms": ms_down, "resize_down_gb_s": down_bytes / ms_down / 1e6, "resize_down_frac_of_hbm_peak": down_bytes / ms_down / 1e6 / peak,
         "resize_up_ms": ms_up, "resize_up_gb_s": down_bytes / ms_up / 1e6,
+        "resize_5000x3000_ms": ms_odd, "resize_5000x3000_gb_s": odd_bytes / ms_odd / 1e6, "resize_5000x3000_frac_of_hbm_peak": odd_bytes / ms_odd / 1e6 / peak,
         "chain_ms": ms_map + ms_down, "chain_gb_s": (map_bytes + down_bytes) / (ms_map + ms_down) / 1e6,
         "chain_frac_of_hbm_peak": (map_bytes + down_bytes) / (ms_map + ms_down) / 1e6 / peak,
     }
-    del src, mapped, half, up, scratch
+    del src, mapped, half, up, scratch, odd, odd_scratch
     if cpu:
         try:
             cpu_reference(out)

@@ -551,8 +551,11 @@ __device__ __forceinline__ uint32_t lerp16_lanes(uint32_t a, uint32_t b, uint32_
 	return __byte_perm(__byte_perm(s0, s1, 0x4462), __byte_perm(s2, s3, 0x4462), 0x5410);
 }
 
+#ifndef RESIZE_UP_MIN_BLOCKS
+#define RESIZE_UP_MIN_BLOCKS 6 // 42 registers, 48 warps per SM: 115 us for 4096^2 -> 8192^2 against 121 us unbounded and 128 us at 8 (tools/resize_sweep.py)
+#endif
 template <bool SAME_ORDER>
-__global__ void __launch_bounds__(256) resize_up_fused_kernel(Img target, Img source, ResizeParams rp) {
+__global__ void __launch_bounds__(256, RESIZE_UP_MIN_BLOCKS) resize_up_fused_kernel(Img target, Img source, ResizeParams rp) {
 	const int32_t x0 = (int32_t)(blockIdx.x * blockDim.x + threadIdx.x) * PX, yFirst = (int32_t)(blockIdx.y * blockDim.y + threadIdx.y) * FUSED_ROWS;
 	if (x0 >= target.width || yFirst >= target.height) { return; }
 	const int n = min(PX, target.width - x0);

@@ -481,6 +481,18 @@ __device__ __forceinline__ uint32_t mix_uniform(uint32_t a, uint32_t b, uint32_t
 	return ((low >> 8) & 0x00FF00FFu) | (high & 0xFF00FF00u);
 }
 
+// lerp16 + saturate-and-pack on whole pixels when source and target share a pack order: every byte lane is interpolated on its own
+// (ref: api/filterAPI.cpp:86-88, the weights add up to 65536, so a lane's sum stays below 2^24 and its result is byte 2 of the sum;
+// interpolated bytes never leave 0..255, so the saturation is the identity). 19 instructions per pixel instead of about 50.
+__device__ __forceinline__ uint32_t lerp16_lanes(uint32_t a, uint32_t b, uint32_t ratioB) {
+	const uint32_t ratioA = 65536u - ratioB;
+	const uint32_t s0 = __byte_perm(a, 0u, 0x4440) * ratioA + __byte_perm(b, 0u, 0x4440) * ratioB;
+	const uint32_t s1 = __byte_perm(a, 0u, 0x4441) * ratioA + __byte_perm(b, 0u, 0x4441) * ratioB;
+	const uint32_t s2 = __byte_perm(a, 0u, 0x4442) * ratioA + __byte_perm(b, 0u, 0x4442) * ratioB;
+	const uint32_t s3 = __byte_perm(a, 0u, 0x4443) * ratioA + __byte_perm(b, 0u, 0x4443) * ratioB;
+	return __byte_perm(__byte_perm(s0, s1, 0x4462), __byte_perm(s2, s3, 0x4462), 0x5410);
+}
+
 enum { RESIZE_VERTICAL_PACKED = 0, RESIZE_VERTICAL = 1, RESIZE_VERTICAL_NEAREST = 2, RESIZE_HORIZONTAL = 3, RESIZE_GENERAL = 4 };
 
 struct ResizeParams { int32_t offsetX, offsetY, startX, startY, bilinear, path; };
@@ -508,6 +520,20 @@ __global__ void __launch_bounds__(256) resize_kernel(Img target, Img source, Res
 			for (int i = 0; i < n; i++) { out[i] = saturate_and_pack(lerp16(read_clamp(source, x0 + i, (int32_t)upperY), read_clamp(source, x0 + i, (int32_t)lowerY), lowerRatio), shifts); }
 		} else {
 			load4(source, x0, (int32_t)upperY, n, out);
+		}
+	} else if (rp.bilinear && target.packOrder == source.packOrder) {
+		// the same integers on whole pixels, byte lane by byte lane (lerp16_lanes): four clamped reads and three interpolations per pixel
+		const int32_t lastX = source.width - 1, lastY = source.height - 1;
+		const int32_t rowA = rp.path == RESIZE_HORIZONTAL ? min(y, lastY) : min((int32_t)upperY, lastY), rowB = min((int32_t)upperY + 1, lastY);
+		const uint32_t *lineA = row_ptr<uint32_t>(source.data, source.stride, rowA), *lineB = row_ptr<uint32_t>(source.data, source.stride, rowB);
+		for (int i = 0; i < n; i++) {
+			const int32_t readX = rp.startX + (x0 + i) * rp.offsetX;
+			const uint32_t sampleX = (uint32_t)(readX < 0 ? 0 : readX);
+			const int32_t leftX = min((int32_t)(sampleX >> 16), lastX), rightX = min((int32_t)(sampleX >> 16) + 1, lastX);
+			const uint32_t rightRatio = sampleX & 65535u;
+			const uint32_t upper = lerp16_lanes(__ldg(lineA + leftX), __ldg(lineA + rightX), rightRatio);
+			if (rp.path == RESIZE_HORIZONTAL) { out[i] = upper; }
+			else { out[i] = lerp16_lanes(upper, lerp16_lanes(__ldg(lineB + leftX), __ldg(lineB + rightX), rightRatio), lowerRatio); }
 		}
 	} else {
 		for (int i = 0; i < n; i++) {
@@ -538,18 +564,6 @@ __global__ void __launch_bounds__(256) resize_kernel(Img target, Img source, Res
 // (a row is reused by about targetHeight / sourceHeight consecutive target rows) and never writes it to memory:
 // 4 B x (source + target) of traffic instead of 4 B x (source + 3 x temporary + target).
 static const int FUSED_ROWS = 16;
-
-// lerp16 + saturate-and-pack on whole pixels when source and target share a pack order: every byte lane is interpolated on its own
-// (ref: api/filterAPI.cpp:86-88, the weights add up to 65536, so a lane's sum stays below 2^24 and its result is byte 2 of the sum;
-// interpolated bytes never leave 0..255, so the saturation is the identity). 19 instructions per pixel instead of about 50.
-__device__ __forceinline__ uint32_t lerp16_lanes(uint32_t a, uint32_t b, uint32_t ratioB) {
-	const uint32_t ratioA = 65536u - ratioB;
-	const uint32_t s0 = __byte_perm(a, 0u, 0x4440) * ratioA + __byte_perm(b, 0u, 0x4440) * ratioB;
-	const uint32_t s1 = __byte_perm(a, 0u, 0x4441) * ratioA + __byte_perm(b, 0u, 0x4441) * ratioB;
-	const uint32_t s2 = __byte_perm(a, 0u, 0x4442) * ratioA + __byte_perm(b, 0u, 0x4442) * ratioB;
-	const uint32_t s3 = __byte_perm(a, 0u, 0x4443) * ratioA + __byte_perm(b, 0u, 0x4443) * ratioB;
-	return __byte_perm(__byte_perm(s0, s1, 0x4462), __byte_perm(s2, s3, 0x4462), 0x5410);
-}
 
 #ifndef RESIZE_UP_MIN_BLOCKS
 #define RESIZE_UP_MIN_BLOCKS 6 // 42 registers, 48 warps per SM: 115 us for 4096^2 -> 8192^2 against 121 us unbounded and 128 us at 8 (tools/resize_sweep.py)

@@ -318,3 +318,21 @@ def test_reference_rsqrt_fast_path_equals_the_literal_expression():
     for first, count in ((0, 1 << 20), (0x7F000000, 1 << 24), (0x80000000, 1 << 20), (0xBF000000, 1 << 20), (0x00700000, 1 << 21)):
         lib.check(cuda.dfpsr_selftest_rsqrt(first, count, C.byref(bad), lib.stream_ptr()))
         assert bad.value == 0, hex(first)
+
+
+@pytest.mark.parametrize("packs", [(2, 0), (1, 0), (3, 3), (2, 1)])
+def test_filter_resize_pack_orders(cuda, oracle, packs):
+    """Bilinear resize with source and target in different pack orders (the channel-by-channel path; when the orders agree the kernels
+    interpolate whole pixels byte lane by byte lane) and in an equal non-RGBA order, over every reference code path."""
+    import torch
+    rng = np.random.default_rng(23)
+    src = rand_rgba(rng, 61, 83)
+    ts = dev(src)
+    for nw, nh in RESIZE_SHAPES:
+        tt = dev(np.zeros((nh, nw), np.uint32))
+        need = cuda.dfpsr_filter_resize_scratch_bytes(83, 61, nw, nh)
+        scratch = torch.zeros(max(need // 4, 1), dtype=torch.int32, device="cuda")
+        lib.check(cuda.dfpsr_filter_resize(C.byref(IM(tt, packs[1])), C.byref(IM(ts, packs[0])), abi.SAMPLER_LINEAR, 0, scratch.data_ptr(), lib.stream_ptr()))
+        e, es = np.zeros((nh, nw), np.uint32), np.zeros(nw * 61 + 4, np.uint32)
+        oracle.orc_filter_resize(C.byref(OI(e, packs[1])), C.byref(OI(src, packs[0])), abi.SAMPLER_LINEAR, 0, orcbind.ptr(es))
+        assert_same_u32(host_u32(tt), e, f"resize to {nw}x{nh} packs={packs}")

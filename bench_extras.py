@@ -195,6 +195,23 @@ def run(cuda, lib, cpu=True):
         "note": "256 MB per buffer, larger than the 126 MB L2; bytes = algorithmic 8 / 12 / 12 B per pixel"}
     del bigN, bigD, bigL, bigC
 
+    # ---- image_fill / draw_copy / draw_higher at a size where their bandwidth shows (rows a18-a20): 8192 x 8192 buffers of 268 MB
+    big = 8192
+    fa = torch.randint(0, 2 ** 31 - 1, (big, big), dtype=torch.int32, device="cuda")
+    fb = torch.empty_like(fa)
+    ha = torch.rand((big, big), dtype=torch.float32, device="cuda")
+    hb = torch.rand((big, big), dtype=torch.float32, device="cuda")
+    ms_fill = _time(torch, lambda: lib.check(cuda.dfpsr_image_fill_rgba(C.byref(IM(fb)), 10, 20, 30, 40, s)), iters=20)
+    ms_copy = _time(torch, lambda: lib.check(cuda.dfpsr_draw_copy_rgba(C.byref(IM(fb)), C.byref(IM(fa)), 0, 0, s)), iters=20)
+    ms_higher = _time(torch, lambda: lib.check(cuda.dfpsr_draw_higher(C.byref(IM(hb)), C.byref(IM(ha)), C.byref(IM(fb)), C.byref(IM(fa)), None, None, 0, 0, 0.0, s)), iters=10)
+    pxb = big * big
+    out["fill_copy_higher_8192x8192"] = {
+        "fill_ms": ms_fill, "fill_gb_s": 4 * pxb / ms_fill / 1e6, "fill_frac_of_hbm_peak": 4 * pxb / ms_fill / 1e6 / peak,
+        "copy_ms": ms_copy, "copy_gb_s": 8 * pxb / ms_copy / 1e6, "copy_frac_of_hbm_peak": 8 * pxb / ms_copy / 1e6 / peak,
+        "higher_ms": ms_higher, "higher_note": "height + one colour image; steady state of repeated calls: the target already holds the higher value everywhere, so both height fields are read (8 B per pixel) and nothing is written",
+        "higher_gb_s": 8 * pxb / ms_higher / 1e6, "higher_frac_of_hbm_peak": 8 * pxb / ms_higher / 1e6 / peak}
+    del fa, fb, ha, hb
+
     # ---- config 5: 8192x8192 filter chain (map + bilinear resize), pure streaming
     size = 8192
     src = torch.empty((size, size), dtype=torch.int32, device="cuda")

@@ -99,18 +99,28 @@ __global__ void __launch_bounds__(256) higher_kernel(Img targetH, Img sourceH, I
 	int32_t x = (blockIdx.x * blockDim.x + threadIdx.x) * PX, y = blockIdx.y * blockDim.y + threadIdx.y;
 	if (x >= is.w || y >= is.h) { return; }
 	int n = min(PX, is.w - x);
-	for (int i = 0; i < n; i++) {
-		float newHeight = *px_f32(sourceH, is.sx + x + i, is.sy + y);
+	// both height fields come in as 16-byte loads when the rows allow it (large images: the pass is a stream of heights); colours are only
+	// touched where the source is higher
+	Img sourceBits = sourceH, targetBits = targetH;
+	uint32_t sourceWords[4], targetWords[4];
+	load4(sourceBits, is.sx + x, is.sy + y, n, sourceWords);
+	load4(targetBits, is.tx + x, is.ty + y, n, targetWords);
+	bool changed = false;
+#pragma unroll
+	for (int i = 0; i < 4; i++) {
+		if (i >= n) { break; }
+		float newHeight = __uint_as_float(sourceWords[i]);
 		if (newHeight > -INFINITY) {
 			newHeight += offset;
-			float *t = px_f32(targetH, is.tx + x + i, is.ty + y);
-			if (newHeight > *t) {
-				*t = newHeight;
+			if (newHeight > __uint_as_float(targetWords[i])) {
+				targetWords[i] = __float_as_uint(newHeight);
+				changed = true;
 				if (targetA.data) { *px_u32(targetA, is.tx + x + i, is.ty + y) = repack(*px_u32(sourceA, is.sx + x + i, is.sy + y), pack_shifts(sourceA.packOrder), pack_shifts(targetA.packOrder)); }
 				if (targetB.data) { *px_u32(targetB, is.tx + x + i, is.ty + y) = repack(*px_u32(sourceB, is.sx + x + i, is.sy + y), pack_shifts(sourceB.packOrder), pack_shifts(targetB.packOrder)); }
 			}
 		}
 	}
+	if (changed) { store4(targetBits, is.tx + x, is.ty + y, n, targetWords); }
 }
 
 struct SpriteDev { Img sourceH, sourceA, sourceB; int32_t left, top; float offset; };

@@ -125,6 +125,7 @@ struct FrameDev {
 	uint32_t *sortTmp;               // rank-sort scratch, as large as the entry pool; totals[6] = cursor
 	struct BigItem *bigItems;        // large commands of the frame (totals[8] = cursor) and, per (command, tile row) unit, the index of its
 	uint32_t *bigUnits;              // command in bigItems (totals[7] = units needed, counted by the first pass; totals[9] = cursor)
+	const int32_t *blockTask;        // task of every set-up block (null: binary search over the tasks' block ranges)
 	int32_t smallRows;               // triangles up to this many rows (and SMALL_WIDTH columns) are scan-converted by their set-up thread
 	const float *occlusionGrid;      // 16-pixel cells of the farthest depth at which something can still be visible; null = no occluders
 	int32_t gridWidth, gridHeight, gridStride;
@@ -659,7 +660,7 @@ __global__ void __launch_bounds__(SETUP_THREADS, SETUP_MIN_BLOCKS) setup_kernel(
 	__shared__ uint32_t sUnitEnd[SETUP_THREADS]; // emit pass: inclusive prefix of tile rows over the queued commands
 	{
 		if (threadIdx.x == 0) { sChkCount = 0; sUnitCount = 0; }
-		int32_t t = task_of_block(frame.tasks, frame.taskCount, (int32_t)blockIdx.x);
+		int32_t t = frame.blockTask ? frame.blockTask[blockIdx.x] : task_of_block(frame.tasks, frame.taskCount, (int32_t)blockIdx.x);
 		for (uint32_t w = threadIdx.x; w < sizeof(TaskParams) / 4; w += blockDim.x) { ((uint32_t *)&task)[w] = ((const uint32_t *)&frame.tasks[t])[w]; }
 		if (threadIdx.x == 0) { sBigCount = 0; }
 	}
@@ -943,7 +944,7 @@ __global__ void __launch_bounds__(256) big_units_kernel(FrameDev frame, uint32_t
 __global__ void __launch_bounds__(SETUP_THREADS) occlude_existing_kernel(FrameDev frame, float *grid) {
 	__shared__ TaskParams task;
 	{
-		int32_t t = task_of_block(frame.tasks, frame.taskCount, (int32_t)blockIdx.x);
+		int32_t t = frame.blockTask ? frame.blockTask[blockIdx.x] : task_of_block(frame.tasks, frame.taskCount, (int32_t)blockIdx.x);
 		for (uint32_t w = threadIdx.x; w < sizeof(TaskParams) / 4; w += blockDim.x) { ((uint32_t *)&task)[w] = ((const uint32_t *)&frame.tasks[t])[w]; }
 	}
 	__syncthreads();
@@ -1926,18 +1927,29 @@ static int renderer_end_internal(dfpsr_renderer *r, cudaStream_t stream) {
 	if (r->tileCount.reserve(((size_t)tileTotal + 12) * 4) || r->tileOffset.reserve(((size_t)tileTotal + 1) * 4) || r->tileCursor.reserve(((size_t)tileTotal + 1) * 4)) { return 1; }
 	if (r->slotCounts.reserve((size_t)slotTotal * 4 + 16) || r->blockCmds.reserve((size_t)blockTotal * 4 + 16) || r->blockRows.reserve((size_t)blockTotal * 4 + 16)) { return 1; }
 	// pageable sources: cudaMemcpyAsync stages them before returning, so the vectors may change afterwards
+	const int32_t *blockTaskDevice = nullptr;
 	if (taskCount > 0) {
 		// The records go through page-locked staging: the copy is then a plain DMA in stream order. The staging buffer is free again when this
 		// function returns (the wait for the set-up totals below comes after the copy on the same stream).
-		const size_t bytes = taskCount * sizeof(TaskParams);
+		// behind the records: the task of every set-up block, so that a block of a frame with hundreds of tasks (the shadow pass of a Sandbox
+		// frame) starts with one load instead of a ten-step binary search of dependent loads
+		const size_t taskBytes = taskCount * sizeof(TaskParams), tableBytes = taskCount > 1 ? (size_t)blockTotal * sizeof(int32_t) : 0;
+		const size_t bytes = taskBytes + tableBytes;
+		if (r->dTasks.reserve(bytes + 16)) { return 1; }
 		if (bytes > r->pinnedTasksCapacity) {
 			if (r->pinnedTasks) { cudaFreeHost(r->pinnedTasks); r->pinnedTasks = nullptr; r->pinnedTasksCapacity = 0; }
 			const size_t grown = bytes + bytes / 2 + 4096;
 			DFPSR_CHECK_CUDA(cudaHostAlloc(&r->pinnedTasks, grown, cudaHostAllocDefault));
 			r->pinnedTasksCapacity = grown;
 		}
-		memcpy(r->pinnedTasks, r->tasks.data(), bytes);
+		memcpy(r->pinnedTasks, r->tasks.data(), taskBytes);
+		if (tableBytes > 0) {
+			int32_t *table = (int32_t *)((uint8_t *)r->pinnedTasks + taskBytes);
+			int32_t index = 0;
+			for (const TaskParams &t : r->tasks) { for (int32_t b = 0; b < t.blockCount; b++) { table[t.blockBase + b] = index; } index++; }
+		}
 		DFPSR_CHECK_CUDA(cudaMemcpyAsync(r->dTasks.ptr, r->pinnedTasks, bytes, cudaMemcpyHostToDevice, stream));
+		blockTaskDevice = tableBytes > 0 ? (const int32_t *)((const uint8_t *)r->dTasks.ptr + taskBytes) : nullptr;
 	}
 	DFPSR_CHECK_CUDA(cudaMemcpyAsync(r->dViews.ptr, r->views.data(), viewCount * sizeof(ViewDev), cudaMemcpyHostToDevice, stream));
 	DFPSR_CHECK_CUDA(cudaMemsetAsync(r->tileCount.ptr, 0, ((size_t)tileTotal + 12) * 4, stream)); // tile counts, cursors of empty frames, totals
@@ -1947,6 +1959,7 @@ static int renderer_end_internal(dfpsr_renderer *r, cudaStream_t stream) {
 	FrameDev frame;
 	memset(&frame, 0, sizeof(frame));
 	frame.tasks = (const TaskParams *)r->dTasks.ptr;
+	frame.blockTask = blockTaskDevice;
 	frame.views = (const ViewDev *)r->dViews.ptr;
 	frame.taskCount = (int32_t)taskCount; frame.viewCount = (int32_t)viewCount; frame.blockCount = blockTotal;
 	frame.tileTotal = tileTotal;

@@ -1854,9 +1854,8 @@ static int add_model_task(dfpsr_renderer *r, int32_t view, const dfpsr_model *mo
 	const int32_t diffuseIndex = r->depthOnly ? -1 : register_texture(r, &model->diffuse);
 	const int32_t lightIndex = r->depthOnly ? -1 : register_texture(r, &model->light);
 	DFPSR_REQUIRE(diffuseIndex != -2 && lightIndex != -2, "more than %d distinct textures in one frame", MAX_TEXTURES);
-	r->tasks.emplace_back(); // filled in place: a Sandbox frame queues hundreds of 400-byte tasks
+	r->tasks.emplace_back(); // value-initialised (all zero) and filled in place: a Sandbox frame queues hundreds of 400-byte tasks
 	TaskParams &task = r->tasks.back();
-	memset(&task, 0, sizeof(task));
 	task.points = model->points;
 	task.polygons = model->polygons;
 	task.pointCount = model->pointCount;

@@ -107,9 +107,20 @@ struct ViewDev {
 	int32_t tilesX, tilesY;
 };
 
+// One texture of the frame's table (ref: implementation/image/Texture.h:42-95); Cmd::flags carries 12-bit indices into the table.
+struct TexDev {
+	const uint32_t *data;
+	uint32_t log2width, log2height, maxMipLevel, startOffset, maxLevelMask;
+	uint32_t pad_;
+};
+static_assert(sizeof(TexDev) == 32, "TexDev layout (two 16-byte loads)");
+static const int MAX_TEXTURES = 4096; // 12 index bits per texture in Cmd::flags
+
 struct FrameDev {
 	const TaskParams *tasks;
 	const ViewDev *views;
+	const TexDev *textures;          // the frame's texture table, uploaded behind the task records
+	int32_t checkpoints;             // 1: large commands leave interpolation checkpoints (exact mode); 0: tolerance mode, nothing to replay
 	int32_t taskCount, viewCount, blockCount;
 	uint32_t tileTotal;
 	uint32_t *slotCounts;            // per slot: command count | rows << 3
@@ -710,7 +721,7 @@ __global__ void __launch_bounds__(SETUP_THREADS, SETUP_MIN_BLOCKS) setup_kernel(
 			const bool small = rowCount <= frame.smallRows && (bound.r - bound.l) <= SMALL_WIDTH;
 			if (!EMIT) {
 				if (rowCount > 0) {
-					if (!small && !task.depthOnly) { atomicAdd(&sChkCount, (uint32_t)((rowCount / 2) * (tx1 - tx0 + 1))); }
+					if (!small && !task.depthOnly && frame.checkpoints) { atomicAdd(&sChkCount, (uint32_t)((rowCount / 2) * (tx1 - tx0 + 1))); }
 					if (!small) { atomicAdd(&sUnitCount, (uint32_t)((bound.t + rowCount - 1) / TILE_H - bound.t / TILE_H + 1)); }
 					int32_t tiles = (tx1 - tx0 + 1) * (ty1 - ty0 + 1);
 					uint32_t queued = 0xFFFFFFFFu;
@@ -763,7 +774,7 @@ __global__ void __launch_bounds__(SETUP_THREADS, SETUP_MIN_BLOCKS) setup_kernel(
 						for (int k = 0; k < 3; k++) { it.fx[k] = q[k].fx; it.fy[k] = q[k].fy; }
 						it.chkOffset = CHK_NONE;
 #ifndef DFPSR_NO_CHK
-						if (!task.depthOnly) {
+						if (!task.depthOnly && frame.checkpoints) {
 							// position inside the block's share of the checkpoint pool; the block reserves its share with ONE global atomic
 							// after the barrier below and patches the command records (one cursor bumped by every large command of a
 							// frame is a serial chain of same-address atomics)
@@ -1166,12 +1177,14 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_lists_kernel(FrameDev frame
 
 // ------------------------------------------------------------------------------------------------ texture sampling
 
-struct TexDev {
-	const uint32_t *data;
-	uint32_t log2width, log2height, maxMipLevel, startOffset, maxLevelMask;
-};
-static const int MAX_TEXTURES = 64;
-struct TexTable { TexDev t[MAX_TEXTURES]; };
+// The frame's texture table lives in device memory next to the task records (any number of textures up to the 12 index bits of Cmd::flags).
+__device__ __forceinline__ TexDev load_tex(const TexDev *__restrict__ table, uint32_t index) {
+	const uint4 a = __ldg((const uint4 *)(table + index)), b = __ldg((const uint4 *)(table + index) + 1);
+	TexDev t;
+	t.data = (const uint32_t *)(((unsigned long long)a.y << 32) | (unsigned long long)a.x);
+	t.log2width = a.z; t.log2height = a.w; t.maxMipLevel = b.x; t.startOffset = b.y; t.maxLevelMask = b.z;
+	return t;
+}
 
 // ref: api/textureAPI.h:253-263 weightColors on 16-bit lane pairs (sums never exceed 255 * 256, so lanes cannot carry)
 // Bytes 1 and 3 are moved into the 16-bit lanes, and the high bytes of the four lane sums are gathered, with one byte permute each
@@ -1219,6 +1232,12 @@ __device__ __forceinline__ float interpolate3(const float *d, float wa, float wb
 	return d[0] * wa + d[1] * wb + d[2] * wc;
 }
 
+// byte -> float without the conversion pipe: the byte becomes the low mantissa bits of 2^23, then 2^23 is subtracted (exact)
+__device__ __forceinline__ void unpack_bytes(uint32_t c, float &r, float &g, float &b, float &a) {
+	r = __uint_as_float(__byte_perm(c, 0x4B000000u, 0x7440)) - 8388608.0f; g = __uint_as_float(__byte_perm(c, 0x4B000000u, 0x7441)) - 8388608.0f;
+	b = __uint_as_float(__byte_perm(c, 0x4B000000u, 0x7442)) - 8388608.0f; a = __uint_as_float(__byte_perm(c, 0x4B000000u, 0x7443)) - 8388608.0f;
+}
+
 // Samples one texture for the four lanes of a quad and multiplies (or assigns) into rgba[lane][channel].
 template <bool MULTIPLY>
 __device__ __forceinline__ void sample_quad(const TexDev &t, bool highestResolution, const float *cu, const float *cv, const float *wa, const float *wb, const float *wc, float rgba[4][4]) {
@@ -1229,14 +1248,20 @@ __device__ __forceinline__ void sample_quad(const TexDev &t, bool highestResolut
 #pragma unroll
 	for (int l = 0; l < 4; l++) {
 		uint32_t c = sample_bilinear(t, u[l], v[l], mip);
-		// byte -> float without the conversion pipe: the byte becomes the low mantissa bits of 2^23, then 2^23 is subtracted (exact)
-		const float r = __uint_as_float(__byte_perm(c, 0x4B000000u, 0x7440)) - 8388608.0f, g = __uint_as_float(__byte_perm(c, 0x4B000000u, 0x7441)) - 8388608.0f;
-		const float b = __uint_as_float(__byte_perm(c, 0x4B000000u, 0x7442)) - 8388608.0f, a = __uint_as_float(__byte_perm(c, 0x4B000000u, 0x7443)) - 8388608.0f;
+		float r, g, b, a;
+		unpack_bytes(c, r, g, b, a);
 		if (MULTIPLY) { rgba[l][0] = rgba[l][0] * r; rgba[l][1] = rgba[l][1] * g; rgba[l][2] = rgba[l][2] * b; rgba[l][3] = rgba[l][3] * a; }
 		else { rgba[l][0] = r; rgba[l][1] = g; rgba[l][2] = b; rgba[l][3] = a; }
 	}
 }
 
+// The reciprocal of the interpolated 1/W. Exact mode: the IEEE quotient of the reference's scalar build. Tolerance mode: the hardware
+// approximation (about one ulp, like the rcpps + Newton step of the reference's SSE build, base/simd.h:4047-4052).
+template <bool EXACT>
+__device__ __forceinline__ float reciprocal_w(float v) {
+	if (EXACT) { return 1.0f / v; }
+	return __fdividef(1.0f, v);
+}
 
 // ------------------------------------------------------------------------------------------------ tile kernel
 
@@ -1245,6 +1270,7 @@ __device__ __forceinline__ void sample_quad(const TexDev &t, bool highestResolut
 //   mode 1: v[0..11] = the four lanes' sums inside the inner run at `at`, v[12..17] = sums after the run's closing multiplication
 //   mode 2: v[0..5] = running sums at `at`, right of the inner run
 //   mode 3: depth-only path: v[0], v[1] = depth at columns atU / atL of the upper / lower row
+//   mode 4: tolerance mode: nothing stored, the quad lanes evaluate the planes directly
 //   mode -1: nothing of this command in this row pair of this tile
 struct Rec {
 	int32_t ul, ur, ll, lr; // row intervals of the pair, as stored
@@ -1252,15 +1278,14 @@ struct Rec {
 	float v[18];
 };
 static_assert(sizeof(Rec) == 96, "Rec layout");
-
-__device__ __forceinline__ uint32_t find_view(const ViewDev *views, int32_t viewCount, uint32_t tile) {
-	int32_t lo = 0, hi = viewCount - 1;
-	while (lo < hi) {
-		int32_t mid = (lo + hi + 1) >> 1;
-		if (views[mid].tileBase <= tile) { lo = mid; } else { hi = mid - 1; }
-	}
-	return (uint32_t)lo;
-}
+struct RecLite { // tolerance mode: the row intervals are all the quad lanes need
+	int32_t ul, ur, ll, lr;
+	int32_t mode, at;
+	int32_t pad_[2];
+};
+static_assert(sizeof(RecLite) == 32, "RecLite layout");
+template <bool EXACT> struct RecOf { typedef Rec type; };
+template <> struct RecOf<false> { typedef RecLite type; };
 
 // Ascending bitonic sort of one key per lane inside aligned groups of K lanes.
 template <int K>
@@ -1299,32 +1324,149 @@ __device__ __forceinline__ void warp_sort64(uint32_t &k0, uint32_t &k1, int lane
 	}
 }
 
-template <bool DEPTH_ONLY>
-__global__ void __launch_bounds__(RASTER_WARPS * 32, RASTER_MIN_BLOCKS) raster_kernel(FrameDev frame, TexTable textures) {
-	__shared__ __align__(16) Rec sRecAll[RASTER_WARPS][32];
+// Replay of the reference's running sums (shader/fillerTemplates.h:329-372) from the tile's checkpoint to the quad at column x0: the
+// interpolated (1/W, U/W, V/W) of the quad's four lanes, bit for bit. clipSides tells whether the quad is one of the row pair's edge
+// quads (lanes tested against their row's interval) or part of the unclipped inner run.
+__device__ __forceinline__ void chain_to_quad(const Rec &rec, int32_t mode, const float *dx, int32_t x0, int32_t ibs, int32_t ibe, float lanes[3][4], bool &clipSides) {
+	const float dx2[3] = {dx[0] * 2.0f, dx[1] * 2.0f, dx[2] * 2.0f};
+	const int32_t at = rec.at;
+	const bool noInner = ibe <= ibs;
+	clipSides = true;
+	if (mode == 1 && x0 < ibe) {
+		clipSides = false;
+#pragma unroll
+		for (int k = 0; k < 3; k++) {
+#pragma unroll
+			for (int l = 0; l < 4; l++) { lanes[k][l] = rec.v[k * 4 + l]; }
+		}
+		for (int32_t s = at; s < x0; s += 2) {
+#pragma unroll
+			for (int k = 0; k < 3; k++) {
+#pragma unroll
+				for (int l = 0; l < 4; l++) { lanes[k][l] += dx2[k]; }
+			}
+		}
+	} else {
+		float up[3], lo[3];
+		int32_t from = at;
+		if (mode == 1) {
+#pragma unroll
+			for (int k = 0; k < 3; k++) { up[k] = rec.v[12 + k]; lo[k] = rec.v[15 + k]; }
+			from = ibe;
+		} else {
+#pragma unroll
+			for (int k = 0; k < 3; k++) { up[k] = rec.v[k]; lo[k] = rec.v[3 + k]; }
+		}
+		bool inner = false;
+		if (mode == 0 && !noInner && x0 >= ibs) {
+			// the inner run starts inside this tile: finish the left edge, then either enter the run or jump over it
+			for (int32_t s = from; s < ibs; s += 2) {
+#pragma unroll
+				for (int k = 0; k < 3; k++) { up[k] += dx2[k]; lo[k] += dx2[k]; }
+			}
+			if (x0 < ibe) {
+				inner = true;
+				clipSides = false;
+#pragma unroll
+				for (int k = 0; k < 3; k++) { lanes[k][0] = up[k]; lanes[k][1] = up[k] + dx[k]; lanes[k][2] = lo[k]; lanes[k][3] = lo[k] + dx[k]; }
+				for (int32_t s = ibs; s < x0; s += 2) {
+#pragma unroll
+					for (int k = 0; k < 3; k++) {
+#pragma unroll
+						for (int l = 0; l < 4; l++) { lanes[k][l] += dx2[k]; }
+					}
+				}
+			} else {
+				const float quadCount = (float)((ibe - ibs) / 2);
+#pragma unroll
+				for (int k = 0; k < 3; k++) { up[k] = up[k] + (dx2[k] * quadCount); lo[k] = lo[k] + (dx2[k] * quadCount); }
+				from = ibe;
+			}
+		}
+		if (!inner) {
+			for (int32_t s = from; s < x0; s += 2) {
+#pragma unroll
+				for (int k = 0; k < 3; k++) { up[k] += dx2[k]; lo[k] += dx2[k]; }
+			}
+#pragma unroll
+			for (int k = 0; k < 3; k++) { lanes[k][0] = up[k]; lanes[k][1] = up[k] + dx[k]; lanes[k][2] = lo[k]; lanes[k][3] = lo[k] + dx[k]; }
+		}
+	}
+}
+
+// One pixel of the deferred shading pass: the colour command `cmd` gives the pixel whose interpolated (1/W, U/W, V/W) are (d, su, sv).
+// ref: shader/fillerTemplates.h:196-243 (weights), shader/RgbaMultiply.h:75-106 (variants), implementation/image/PackOrder.h:186-213 (pack)
+template <bool EXACT>
+__device__ __forceinline__ uint32_t shade_pixel(const Cmd *__restrict__ cmd, const TexDev *__restrict__ texTable, float d, float su, float sv, uint32_t mip, uint32_t shifts) {
+	const uint32_t flags = __ldg(&cmd->flags);
+	float wb, wc;
+	if (flags & CMD_AFFINE) { wb = su; wc = sv; }
+	else { const float linearDepth = reciprocal_w<EXACT>(d); wb = su * linearDepth; wc = sv * linearDepth; }
+	const float wa = 1.0f - (wb + wc);
+	const bool hasDiffuse = (flags & CMD_HAS_DIFFUSE) != 0, hasLight = (flags & CMD_HAS_LIGHT) != 0;
+	const bool fade = (flags & CMD_HAS_FADE) != 0, colorless = (flags & CMD_COLORLESS) != 0 && !fade;
+	const float4 *words = (const float4 *)cmd; // 16-byte words of the record: 4..6 colours, 7..9 texture coordinates
+	float r, g, b, a;
+	const bool plainDiffuse = hasDiffuse && !hasLight && colorless, plainLight = hasLight && !hasDiffuse && colorless;
+	if (!(plainDiffuse || plainLight)) {
+		const float4 c0 = __ldg(words + 4), c1 = __ldg(words + 5), c2 = __ldg(words + 6);
+		if (fade) {
+			const float red[3] = {c0.x, c0.y, c0.z}, green[3] = {c0.w, c1.x, c1.y}, blue[3] = {c1.z, c1.w, c2.x}, alpha[3] = {c2.y, c2.z, c2.w};
+			r = interpolate3(red, wa, wb, wc); g = interpolate3(green, wa, wb, wc); b = interpolate3(blue, wa, wb, wc); a = interpolate3(alpha, wa, wb, wc);
+		} else {
+			r = c0.x; g = c0.w; b = c1.z; a = c2.y;
+		}
+	}
+	if (hasDiffuse || hasLight) {
+		const float4 t0 = __ldg(words + 7), t1 = __ldg(words + 8), t2 = __ldg(words + 9);
+		if (hasDiffuse) {
+			const float cu[3] = {t0.x, t0.y, t0.z}, cv[3] = {t0.w, t1.x, t1.y};
+			const TexDev t = load_tex(texTable, (flags >> 8) & 0xFFFu);
+			const uint32_t c = sample_bilinear(t, interpolate3(cu, wa, wb, wc), interpolate3(cv, wa, wb, wc), mip);
+			float tr, tg, tb, ta;
+			unpack_bytes(c, tr, tg, tb, ta);
+			if (plainDiffuse) { r = tr; g = tg; b = tb; a = ta; } else { r = r * tr; g = g * tg; b = b * tb; a = a * ta; }
+		}
+		if (hasLight) {
+			const float cu[3] = {t1.z, t1.w, t2.x}, cv[3] = {t2.y, t2.z, t2.w};
+			const TexDev t = load_tex(texTable, flags >> 20);
+			const uint32_t c = sample_bilinear(t, interpolate3(cu, wa, wb, wc), interpolate3(cv, wa, wb, wc), 0u);
+			float tr, tg, tb, ta;
+			unpack_bytes(c, tr, tg, tb, ta);
+			if (plainLight) { r = tr; g = tg; b = tb; a = ta; } else { r = r * tr; g = g * tg; b = b * tb; a = a * ta; }
+		}
+	}
+	return pack_rgba_ordered(saturated_byte(r), saturated_byte(g), saturated_byte(b), saturated_byte(a), shifts);
+}
+
+enum : int { TILE_IMMEDIATE = 0, TILE_DEPTH_ONLY = 1, TILE_DEFERRED = 2 };
+static const uint32_t NO_WINNER = 0xFFFFFFFFu;
+
+// MODE: TILE_IMMEDIATE  commands are shaded quad by quad in submission order (needed when a frame holds alpha-filtered commands)
+//       TILE_DEPTH_ONLY the depth pass of model_renderDepth (renderCore.cpp:343-443)
+//       TILE_DEFERRED   frames of solid commands: a visibility pass leaves, per pixel, the command that ends up visible (the depth test is
+//                       strict, so that is the first command reaching the largest depth — exactly the command whose colour survives the
+//                       reference's sequential loop) together with its interpolated (1/W, U/W, V/W); every pixel is then shaded ONCE.
+// EXACT: true   the interpolated values replay the reference's chains of float additions (bit-identical to its scalar build)
+//        false  tolerance mode: planes evaluated directly per quad, approximate reciprocal; no checkpoints anywhere (deferred mode only)
+template <int MODE, bool EXACT>
+__global__ void __launch_bounds__(RASTER_WARPS * 32, RASTER_MIN_BLOCKS) raster_kernel(FrameDev frame) {
+	constexpr bool DEPTH_ONLY = MODE == TILE_DEPTH_ONLY, DEFERRED = MODE == TILE_DEFERRED;
+	static_assert(EXACT || DEFERRED, "tolerance mode exists for the deferred tile kernel only");
+	typedef typename RecOf<EXACT>::type RecT;
+	__shared__ __align__(16) RecT sRecAll[RASTER_WARPS][32];
 	__shared__ uint32_t sKeysAll[RASTER_WARPS][LOCAL_SORT]; // the tile's command list in submission order (lists up to LOCAL_SORT entries)
 	__shared__ __align__(16) uint32_t sMaskAll[RASTER_WARPS][32]; // per (row pair, command): which of the 16 quads of the row pair the command may touch
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	Rec *sRec = sRecAll[warp];
+	RecT *sRec = sRecAll[warp];
 	uint32_t *sMask = sMaskAll[warp];
 
-	// grid = (tiles of the largest view / RASTER_WARPS, views); batches of more than 65535 views fall back to a flat grid and a search
-	uint32_t tile, viewIndex;
-	if (gridDim.y > 1u || frame.viewCount == 1) {
-		viewIndex = blockIdx.y;
-		const ViewDev &v = frame.views[viewIndex];
-		const uint32_t local = blockIdx.x * RASTER_WARPS + warp;
-		if (local >= (uint32_t)(v.tilesX * v.tilesY)) { return; }
-		tile = v.tileBase + local;
-	} else {
-		tile = blockIdx.x * RASTER_WARPS + warp;
-		if (tile >= frame.tileTotal) { return; }
-		viewIndex = find_view(frame.views, frame.viewCount, tile);
-	}
-	const ViewDev &vw = frame.views[viewIndex];
+	// grid = (tile columns of the widest view / RASTER_WARPS, tile rows of the tallest view, views): no division, no search
+	const ViewDev &vw = frame.views[blockIdx.z];
 	const int32_t tilesX = vw.tilesX;
-	const int32_t localTile = (int32_t)(tile - vw.tileBase);
-	const int32_t tileX = localTile % tilesX, tileY = localTile / tilesX;
+	const int32_t tileX = (int32_t)(blockIdx.x * RASTER_WARPS) + warp, tileY = (int32_t)blockIdx.y;
+	if (tileX >= tilesX || tileY >= vw.tilesY) { return; }
+	const uint32_t tile = vw.tileBase + (uint32_t)(tileY * tilesX + tileX);
 	if (tileY * TILE_H >= vw.clipBottom || tileY * TILE_H + TILE_H <= vw.clipTop) { return; }
 	const uint32_t n = frame.tileCursor[tile];
 	const bool clear = vw.clear != 0;
@@ -1375,6 +1517,11 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32, RASTER_MIN_BLOCKS) raster_k
 		}
 	}
 	bool dirty = clear;
+	// deferred mode: the command that is visible at each of the lane's pixels so far, its interpolated U/W and V/W (1/W lives in dep[])
+	// and the mip level its quad selected (one byte per pixel)
+	uint32_t win[4] = {NO_WINNER, NO_WINNER, NO_WINNER, NO_WINNER};
+	float su[4] = {0.0f, 0.0f, 0.0f, 0.0f}, sv[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+	uint32_t mips = 0u;
 
 	// lists of up to LOCAL_SORT entries are sorted here and kept in shared memory; longer ones were sorted by sort_lists_kernel
 	uint32_t *sKeys = sKeysAll[warp];
@@ -1407,7 +1554,7 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32, RASTER_MIN_BLOCKS) raster_k
 		else { key = c < batchCount ? __ldg(list + batchStart + c) : 0u; }
 		{
 			// the record is written straight into shared memory (a local copy that is stored through a uint4 view lives on the stack)
-			Rec &rec = sRec[r * BATCH + c];
+			RecT &rec = sRec[r * BATCH + c];
 			int32_t recMode = -1;
 			rec.at = 0; rec.ul = rec.ur = rec.ll = rec.lr = 0;
 			int32_t quadFirst = 0, quadEnd = 0; // quads [quadFirst, quadEnd) of this row pair can be touched
@@ -1416,17 +1563,25 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32, RASTER_MIN_BLOCKS) raster_k
 				const int4 head = __ldg((const int4 *)cmd + 3); // rowStart, rowCount, rowOffset, pad
 				const int32_t rowStart = head.x, rowCount = head.y;
 				const uint32_t rowOffset = (uint32_t)head.z;
-				const uint4 third = __ldg((const uint4 *)cmd + 2); // dy[2], flags, chkOffset, chkShape
 				const int32_t yTop = tileY * TILE_H + 2 * (int32_t)r;
 				const int32_t idx = yTop - rowStart;
 				if (idx >= 0 && idx < rowCount) {
 					const int4 rr = __ldg((const int4 *)(frame.rows + rowOffset + (uint32_t)idx)); // rows idx and idx + 1 (both even-aligned)
 					rec.ul = rr.x; rec.ur = rr.y; rec.ll = rr.z; rec.lr = rr.w;
+					if constexpr (!EXACT) {
+						const int32_t outerStart = min(rr.x, rr.z), outerEnd = max(rr.y, rr.w);
+						const int32_t obs = outerStart & ~1, obe = (outerEnd + 1) & ~1;
+						const bool hasTop = rr.y > rr.x, hasBottom = (yTop + 1 < height) && rr.w > rr.z;
+						if ((hasTop || hasBottom) && obe > tileLeft && obs < tileLeft + TILE_W) {
+							recMode = 4;
+							quadFirst = (max(obs, tileLeft) - tileLeft) >> 1; quadEnd = (min(obe, tileLeft + TILE_W) - tileLeft) >> 1;
+						}
+					} else {
+					const uint4 third = __ldg((const uint4 *)cmd + 2); // dy[2], flags, chkOffset, chkShape
 					float start[3], dx[3], dy[3];
 					{
 						const float4 a = __ldg((const float4 *)cmd), b = __ldg((const float4 *)cmd + 1);
-						const float last = __ldg(&cmd->dy[2]);
-						start[0] = a.x; start[1] = a.y; start[2] = a.z; dx[0] = a.w; dx[1] = b.x; dx[2] = b.y; dy[0] = b.z; dy[1] = b.w; dy[2] = last;
+						start[0] = a.x; start[1] = a.y; start[2] = a.z; dx[0] = a.w; dx[1] = b.x; dx[2] = b.y; dy[0] = b.z; dy[1] = b.w; dy[2] = __uint_as_float(third.x);
 					}
 					if (DEPTH_ONLY) {
 						// ref: implementation/render/renderCore.cpp:343-387 — per row: value at row.left, then += dx per pixel
@@ -1520,6 +1675,7 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32, RASTER_MIN_BLOCKS) raster_k
 							}
 						}
 					}
+					}
 				}
 			}
 			rec.mode = recMode;
@@ -1545,16 +1701,15 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32, RASTER_MIN_BLOCKS) raster_k
 			cover &= cover - 1u;
 			const uint32_t cmdKey = __shfl_sync(0xffffffffu, key, (int)ci);
 			if (!busy) { continue; }
-			const Rec &rec = sRec[(uint32_t)qy * BATCH + ci];
+			const RecT &rec = sRec[(uint32_t)qy * BATCH + ci];
 			const int32_t mode = rec.mode;
 			const Cmd &cmd = frame.cmds[cmdKey];
 			int2 upperRow = make_int2(rec.ul, rec.ur), lowerRow = make_int2(rec.ll, rec.lr);
-			const uint32_t flags = __ldg(&cmd.flags);
-			const bool affine = (flags & CMD_AFFINE) != 0;
 
-			if (DEPTH_ONLY) {
+			if constexpr (DEPTH_ONLY) {
 				// The reference adds dx once per pixel from the row's left end (renderCore.cpp:343-387). Both rows walk to this quad's first
 				// column in ONE loop (the checkpoint holds the sums at max(row.left, tileLeft)); the second column is one more addition.
+				const bool affine = (__ldg(&cmd.flags) & CMD_AFFINE) != 0;
 				const float dx0 = __ldg(&cmd.dx[0]);
 				const int32_t startU = max(upperRow.x, tileLeft), startL = max(lowerRow.x, tileLeft);
 				const bool touchU = x0 + 1 >= upperRow.x && x0 < upperRow.y, touchL = x0 + 1 >= lowerRow.x && x0 < lowerRow.y && y2 < height;
@@ -1574,94 +1729,45 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32, RASTER_MIN_BLOCKS) raster_k
 					}
 				}
 				continue;
-			}
-
+			} else {
 			const int32_t outerStart = min(upperRow.x, lowerRow.x), outerEnd = max(upperRow.y, lowerRow.y);
 			const int32_t innerStart = max(upperRow.x, lowerRow.x), innerEnd = min(upperRow.y, lowerRow.y);
 			const int32_t obs = outerStart & ~1, obe = (outerEnd + 1) & ~1, ibs = (innerStart + 1) & ~1, ibe = innerEnd & ~1;
 			if (y2 >= height) { lowerRow.y = lowerRow.x; }
 			if (x0 < obs || x0 >= obe) { continue; }
-			float dx[3];
-			{
-				const float4 a = __ldg((const float4 *)&cmd), b = __ldg((const float4 *)&cmd + 1);
-				dx[0] = a.w; dx[1] = b.x; dx[2] = b.y;
-			}
-			const float dx2[3] = {dx[0] * 2.0f, dx[1] * 2.0f, dx[2] * 2.0f};
-			const int32_t at = rec.at;
-			const bool noInner = ibe <= ibs;
+			// words 0..2 of the record: start[3], dx[3], dy[3], flags
+			const float4 planeA = __ldg((const float4 *)&cmd), planeB = __ldg((const float4 *)&cmd + 1);
 			float lanes[3][4];
-			bool clipSides = true;
-			if (mode == 1 && x0 < ibe) {
-				clipSides = false;
+			bool clipSides;
+			uint32_t flags;
+			if constexpr (EXACT) {
+				flags = __ldg(&cmd.flags);
+				const float dx[3] = {planeA.w, planeB.x, planeB.y};
+				chain_to_quad(rec, mode, dx, x0, ibs, ibe, lanes, clipSides);
+			} else {
+				// tolerance mode: the planes at the quad's first pixel centre (ITriangle2D.h:82-100), neighbours by one addition each
+				const uint4 planeC = __ldg((const uint4 *)&cmd + 2);
+				flags = planeC.y;
+				const float start[3] = {planeA.x, planeA.y, planeA.z}, dx[3] = {planeA.w, planeB.x, planeB.y}, dy[3] = {planeB.z, planeB.w, __uint_as_float(planeC.x)};
+				const float fx = (float)x0 + 0.5f, fy = (float)y1 + 0.5f;
 #pragma unroll
 				for (int k = 0; k < 3; k++) {
-#pragma unroll
-					for (int l = 0; l < 4; l++) { lanes[k][l] = rec.v[k * 4 + l]; }
+					lanes[k][0] = __fmaf_rn(dy[k], fy, __fmaf_rn(dx[k], fx, start[k]));
+					lanes[k][1] = lanes[k][0] + dx[k];
+					lanes[k][2] = lanes[k][0] + dy[k];
+					lanes[k][3] = lanes[k][2] + dx[k];
 				}
-				for (int32_t s = at; s < x0; s += 2) {
-#pragma unroll
-					for (int k = 0; k < 3; k++) {
-#pragma unroll
-						for (int l = 0; l < 4; l++) { lanes[k][l] += dx2[k]; }
-					}
-				}
-			} else {
-				float up[3], lo[3];
-				int32_t from = at;
-				if (mode == 1) {
-#pragma unroll
-					for (int k = 0; k < 3; k++) { up[k] = rec.v[12 + k]; lo[k] = rec.v[15 + k]; }
-					from = ibe;
-				} else {
-#pragma unroll
-					for (int k = 0; k < 3; k++) { up[k] = rec.v[k]; lo[k] = rec.v[3 + k]; }
-				}
-				bool inner = false;
-				if (mode == 0 && !noInner && x0 >= ibs) {
-					// the inner run starts inside this tile: finish the left edge, then either enter the run or jump over it
-					for (int32_t s = from; s < ibs; s += 2) {
-#pragma unroll
-						for (int k = 0; k < 3; k++) { up[k] += dx2[k]; lo[k] += dx2[k]; }
-					}
-					if (x0 < ibe) {
-						inner = true;
-						clipSides = false;
-#pragma unroll
-						for (int k = 0; k < 3; k++) { lanes[k][0] = up[k]; lanes[k][1] = up[k] + dx[k]; lanes[k][2] = lo[k]; lanes[k][3] = lo[k] + dx[k]; }
-						for (int32_t s = ibs; s < x0; s += 2) {
-#pragma unroll
-							for (int k = 0; k < 3; k++) {
-#pragma unroll
-								for (int l = 0; l < 4; l++) { lanes[k][l] += dx2[k]; }
-							}
-						}
-					} else {
-						const float quadCount = (float)((ibe - ibs) / 2);
-#pragma unroll
-						for (int k = 0; k < 3; k++) { up[k] = up[k] + (dx2[k] * quadCount); lo[k] = lo[k] + (dx2[k] * quadCount); }
-						from = ibe;
-					}
-				}
-				if (!inner) {
-					for (int32_t s = from; s < x0; s += 2) {
-#pragma unroll
-						for (int k = 0; k < 3; k++) { up[k] += dx2[k]; lo[k] += dx2[k]; }
-					}
-#pragma unroll
-					for (int k = 0; k < 3; k++) { lanes[k][0] = up[k]; lanes[k][1] = up[k] + dx[k]; lanes[k][2] = lo[k]; lanes[k][3] = lo[k] + dx[k]; }
-				}
+				clipSides = !(ibe > ibs && x0 >= ibs && x0 < ibe);
+				(void)mode;
 			}
+			const bool affine = (flags & CMD_AFFINE) != 0;
 
-			// ref: shader/fillerTemplates.h:196-243 — weights; :93-138 — visibility
-			float wa[4], wb[4], wc[4];
+			// ref: shader/fillerTemplates.h:93-138 — visibility
 			bool vis[4];
 			bool anyVisible = false;
 			const bool repeatUpper = aliasLower && !clipSides; // lanes 2/3 act on the pixels of lanes 0/1
 #pragma unroll
 			for (int l = 0; l < 4; l++) {
-				if (affine) { wb[l] = lanes[1][l]; wc[l] = lanes[2][l]; }
-				else { float linearDepth = 1.0f / lanes[0][l]; wb[l] = lanes[1][l] * linearDepth; wc[l] = lanes[2][l] * linearDepth; }
-				wa[l] = 1.0f - (wb[l] + wc[l]);
 				bool visible = true;
 				if (clipSides) {
 					int2 row = (l < 2) ? upperRow : lowerRow;
@@ -1677,15 +1783,52 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32, RASTER_MIN_BLOCKS) raster_k
 			}
 			if (!anyVisible) { continue; }
 
+			if constexpr (DEFERRED) {
+				// the quad's mip level comes from lanes 0, 1, 2 of THIS command whether they are visible or not (textureAPI.h:472-495)
+				uint32_t mip = 0u;
+				if (hasColor && (flags & CMD_HAS_DIFFUSE) != 0) {
+					const TexDev t = load_tex(frame.textures, (flags >> 8) & 0xFFFu);
+					if (t.maxMipLevel > 0u) {
+						const float4 t0 = __ldg((const float4 *)&cmd + 7), t1 = __ldg((const float4 *)&cmd + 8);
+						const float cu[3] = {t0.x, t0.y, t0.z}, cv[3] = {t0.w, t1.x, t1.y};
+						float u[3], v[3];
+#pragma unroll
+						for (int l = 0; l < 3; l++) {
+							float wb, wc;
+							if (affine) { wb = lanes[1][l]; wc = lanes[2][l]; }
+							else { const float linearDepth = reciprocal_w<EXACT>(lanes[0][l]); wb = lanes[1][l] * linearDepth; wc = lanes[2][l] * linearDepth; }
+							const float wa = 1.0f - (wb + wc);
+							u[l] = interpolate3(cu, wa, wb, wc); v[l] = interpolate3(cv, wa, wb, wc);
+						}
+						mip = mip_level(t, u, v);
+					}
+				}
+				// writes in lane order (clippedWrite); with a repeated upper row lanes 2/3 land on lanes 0/1
+#define DFPSR_TAKE(T, L, SEL) { dep[T] = lanes[0][L]; su[T] = lanes[1][L]; sv[T] = lanes[2][L]; win[T] = cmdKey; mips = __byte_perm(mips, mip, SEL); }
+				if (vis[0]) DFPSR_TAKE(0, 0, 0x3214)
+				if (vis[1]) DFPSR_TAKE(1, 1, 0x3240)
+				if (vis[2]) { if (repeatUpper) DFPSR_TAKE(0, 2, 0x3214) else DFPSR_TAKE(2, 2, 0x3410) }
+				if (vis[3]) { if (repeatUpper) DFPSR_TAKE(1, 3, 0x3240) else DFPSR_TAKE(3, 3, 0x4210) }
+#undef DFPSR_TAKE
+				dirty = true;
+			} else {
+			// ref: shader/fillerTemplates.h:196-243 — weights
+			float wa[4], wb[4], wc[4];
+#pragma unroll
+			for (int l = 0; l < 4; l++) {
+				if (affine) { wb[l] = lanes[1][l]; wc[l] = lanes[2][l]; }
+				else { float linearDepth = 1.0f / lanes[0][l]; wb[l] = lanes[1][l] * linearDepth; wc[l] = lanes[2][l] * linearDepth; }
+				wa[l] = 1.0f - (wb[l] + wc[l]);
+			}
 			if (hasColor) {
 				// ref: shader/RgbaMultiply.h:75-106
 				float rgba[4][4];
 				const bool hasDiffuse = (flags & CMD_HAS_DIFFUSE) != 0, hasLight = (flags & CMD_HAS_LIGHT) != 0;
 				const bool fade = (flags & CMD_HAS_FADE) != 0, colorless = (flags & CMD_COLORLESS) != 0 && !fade;
 				if (hasDiffuse && !hasLight && colorless) {
-					sample_quad<false>(textures.t[(flags >> 8) & 0xFFFu], false, cmd.u1, cmd.v1, wa, wb, wc, rgba);
+					sample_quad<false>(load_tex(frame.textures, (flags >> 8) & 0xFFFu), false, cmd.u1, cmd.v1, wa, wb, wc, rgba);
 				} else if (hasLight && !hasDiffuse && colorless) {
-					sample_quad<false>(textures.t[flags >> 20], true, cmd.u2, cmd.v2, wa, wb, wc, rgba);
+					sample_quad<false>(load_tex(frame.textures, flags >> 20), true, cmd.u2, cmd.v2, wa, wb, wc, rgba);
 				} else {
 #pragma unroll
 					for (int l = 0; l < 4; l++) {
@@ -1698,8 +1841,8 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32, RASTER_MIN_BLOCKS) raster_k
 							rgba[l][0] = cmd.red[0]; rgba[l][1] = cmd.green[0]; rgba[l][2] = cmd.blue[0]; rgba[l][3] = cmd.alpha[0];
 						}
 					}
-					if (hasDiffuse) { sample_quad<true>(textures.t[(flags >> 8) & 0xFFFu], false, cmd.u1, cmd.v1, wa, wb, wc, rgba); }
-					if (hasLight) { sample_quad<true>(textures.t[flags >> 20], true, cmd.u2, cmd.v2, wa, wb, wc, rgba); }
+					if (hasDiffuse) { sample_quad<true>(load_tex(frame.textures, (flags >> 8) & 0xFFFu), false, cmd.u1, cmd.v1, wa, wb, wc, rgba); }
+					if (hasLight) { sample_quad<true>(load_tex(frame.textures, flags >> 20), true, cmd.u2, cmd.v2, wa, wb, wc, rgba); }
 				}
 				const bool alphaFilter = (flags & CMD_ALPHA) != 0;
 				uint32_t packed[4];
@@ -1739,8 +1882,22 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32, RASTER_MIN_BLOCKS) raster_k
 				if (vis[3]) { if (repeatUpper) { dep[1] = lanes[0][3]; } else { dep[3] = lanes[0][3]; } }
 				dirty = true;
 			}
+			}
+			}
 		}
 		__syncwarp();
+	}
+
+	if constexpr (DEFERRED) {
+		// ---- shading pass: every pixel that some command won is shaded once, by that command
+		if (hasColor) {
+#pragma unroll
+			for (int l = 0; l < 4; l++) {
+				if (win[l] != NO_WINNER) {
+					col[l] = shade_pixel<EXACT>(frame.cmds + win[l], frame.textures, dep[l], su[l], sv[l], (mips >> (8 * l)) & 0xFFu, shifts);
+				}
+			}
+		}
 	}
 
 	if (dirty) {
@@ -1768,6 +1925,12 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32, RASTER_MIN_BLOCKS) raster_k
 
 using namespace dfpsr;
 
+// the four instances of the tile kernel under the names the launch accounting and the profiles use
+static constexpr auto tile_kernel_depth = raster_kernel<TILE_DEPTH_ONLY, true>;
+static constexpr auto tile_kernel_immediate = raster_kernel<TILE_IMMEDIATE, true>;
+static constexpr auto tile_kernel_deferred = raster_kernel<TILE_DEFERRED, true>;
+static constexpr auto tile_kernel_tolerance = raster_kernel<TILE_DEFERRED, false>;
+
 struct dfpsr_renderer {
 	bool receiving = false;
 	bool depthOnly = false;
@@ -1775,8 +1938,8 @@ struct dfpsr_renderer {
 	std::vector<TaskParams> tasks;
 	std::vector<DeviceBuffer> uploads;   // host triangle batches of this frame
 	size_t uploadCount = 0;
-	TexTable textures{};
-	int textureCount = 0;
+	std::vector<TexDev> textures;        // the frame's texture table (uploaded behind the task records)
+	bool exact = true;                   // false: tolerance mode (dfpsr_renderer_set_precision)
 	int64_t lastCommands = -1;
 	DeviceBuffer dTasks, dViews, projected, slotCounts, blockCmds, blockRows, tileCount, tileOffset, tileCursor, cmds, rows, tileList, chk, sortTmp, bigItems, bigUnits;
 	uint32_t *hostTotals = nullptr, *hostTotalsDevice = nullptr; // mapped pinned memory and its device alias
@@ -1801,14 +1964,20 @@ static bool image_exists(const dfpsr_image *image) { return image != nullptr && 
 
 static int register_texture(dfpsr_renderer *r, const dfpsr_texture *t) {
 	if (t == nullptr || t->data == nullptr) { return -1; }
-	for (int i = 0; i < r->textureCount; i++) {
-		if (r->textures.t[i].data == t->data && r->textures.t[i].log2width == t->log2width && r->textures.t[i].maxMipLevel == t->maxMipLevel) { return i; }
+	// most recently registered first: consecutive submissions usually share their textures
+	for (size_t n = r->textures.size(), i = n; i-- > 0;) {
+		const TexDev &d = r->textures[i];
+		if (d.data == t->data && d.log2width == (uint32_t)t->log2width && d.log2height == (uint32_t)t->log2height && d.maxMipLevel == (uint32_t)t->maxMipLevel
+		    && d.startOffset == t->startOffset && d.maxLevelMask == t->maxLevelMask) { return (int)i; }
+		if (n - i >= 64) { break; } // a bounded look-back keeps submission O(1); duplicates in the table are harmless
 	}
-	if (r->textureCount >= MAX_TEXTURES) { return -2; }
-	TexDev &d = r->textures.t[r->textureCount];
-	d.data = t->data; d.log2width = t->log2width; d.log2height = t->log2height;
-	d.maxMipLevel = t->maxMipLevel; d.startOffset = t->startOffset; d.maxLevelMask = t->maxLevelMask;
-	return r->textureCount++;
+	if (r->textures.size() >= (size_t)MAX_TEXTURES) { return -2; }
+	TexDev d;
+	memset(&d, 0, sizeof(d));
+	d.data = t->data; d.log2width = (uint32_t)t->log2width; d.log2height = (uint32_t)t->log2height;
+	d.maxMipLevel = (uint32_t)t->maxMipLevel; d.startOffset = t->startOffset; d.maxLevelMask = t->maxLevelMask;
+	r->textures.push_back(d);
+	return (int)r->textures.size() - 1;
 }
 
 // ref: api/rendererAPI.cpp:151-168 — one view
@@ -1837,7 +2006,7 @@ static int renderer_begin_internal(dfpsr_renderer *r, bool depthOnly) {
 	r->views.clear();
 	r->tasks.clear();
 	r->uploadCount = 0;
-	r->textureCount = 0;
+	r->textures.clear();
 	if (!r->hostTotals) {
 		DFPSR_CHECK_CUDA(cudaHostAlloc((void **)&r->hostTotals, 16 * sizeof(uint32_t), cudaHostAllocMapped));
 		DFPSR_CHECK_CUDA(cudaHostGetDevicePointer((void **)&r->hostTotalsDevice, r->hostTotals, 0));
@@ -1853,7 +2022,7 @@ static int add_model_task(dfpsr_renderer *r, int32_t view, const dfpsr_model *mo
 	if (model->polygonCount <= 0) { return 0; }
 	const int32_t diffuseIndex = r->depthOnly ? -1 : register_texture(r, &model->diffuse);
 	const int32_t lightIndex = r->depthOnly ? -1 : register_texture(r, &model->light);
-	DFPSR_REQUIRE(diffuseIndex != -2 && lightIndex != -2, "more than %d distinct textures in one frame", MAX_TEXTURES);
+	DFPSR_REQUIRE(diffuseIndex != -2 && lightIndex != -2, "more than %d textures in one frame", MAX_TEXTURES);
 	r->tasks.emplace_back(); // value-initialised (all zero) and filled in place: a Sandbox frame queues hundreds of 400-byte tasks
 	TaskParams &task = r->tasks.back();
 	task.points = model->points;
@@ -1927,13 +2096,16 @@ static int renderer_end_internal(dfpsr_renderer *r, cudaStream_t stream) {
 	if (r->slotCounts.reserve((size_t)slotTotal * 4 + 16) || r->blockCmds.reserve((size_t)blockTotal * 4 + 16) || r->blockRows.reserve((size_t)blockTotal * 4 + 16)) { return 1; }
 	// pageable sources: cudaMemcpyAsync stages them before returning, so the vectors may change afterwards
 	const int32_t *blockTaskDevice = nullptr;
+	const TexDev *textureTableDevice = nullptr;
 	if (taskCount > 0) {
 		// The records go through page-locked staging: the copy is then a plain DMA in stream order. The staging buffer is free again when this
 		// function returns (the wait for the set-up totals below comes after the copy on the same stream).
-		// behind the records: the task of every set-up block, so that a block of a frame with hundreds of tasks (the shadow pass of a Sandbox
-		// frame) starts with one load instead of a ten-step binary search of dependent loads
-		const size_t taskBytes = taskCount * sizeof(TaskParams), tableBytes = taskCount > 1 ? (size_t)blockTotal * sizeof(int32_t) : 0;
-		const size_t bytes = taskBytes + tableBytes;
+		// behind the records: the frame's texture table, then the task of every set-up block, so that a block of a frame with hundreds of
+		// tasks (the shadow pass of a Sandbox frame) starts with one load instead of a ten-step binary search of dependent loads
+		const size_t taskBytes = (taskCount * sizeof(TaskParams) + 15) & ~(size_t)15; // the texture table is read with 16-byte loads
+		const size_t textureBytes = r->textures.size() * sizeof(TexDev);
+		const size_t tableBytes = taskCount > 1 ? (size_t)blockTotal * sizeof(int32_t) : 0;
+		const size_t bytes = taskBytes + textureBytes + tableBytes;
 		if (r->dTasks.reserve(bytes + 16)) { return 1; }
 		if (bytes > r->pinnedTasksCapacity) {
 			if (r->pinnedTasks) { cudaFreeHost(r->pinnedTasks); r->pinnedTasks = nullptr; r->pinnedTasksCapacity = 0; }
@@ -1941,14 +2113,16 @@ static int renderer_end_internal(dfpsr_renderer *r, cudaStream_t stream) {
 			DFPSR_CHECK_CUDA(cudaHostAlloc(&r->pinnedTasks, grown, cudaHostAllocDefault));
 			r->pinnedTasksCapacity = grown;
 		}
-		memcpy(r->pinnedTasks, r->tasks.data(), taskBytes);
+		memcpy(r->pinnedTasks, r->tasks.data(), taskCount * sizeof(TaskParams));
+		if (textureBytes > 0) { memcpy((uint8_t *)r->pinnedTasks + taskBytes, r->textures.data(), textureBytes); }
 		if (tableBytes > 0) {
-			int32_t *table = (int32_t *)((uint8_t *)r->pinnedTasks + taskBytes);
+			int32_t *table = (int32_t *)((uint8_t *)r->pinnedTasks + taskBytes + textureBytes);
 			int32_t index = 0;
 			for (const TaskParams &t : r->tasks) { for (int32_t b = 0; b < t.blockCount; b++) { table[t.blockBase + b] = index; } index++; }
 		}
 		DFPSR_CHECK_CUDA(cudaMemcpyAsync(r->dTasks.ptr, r->pinnedTasks, bytes, cudaMemcpyHostToDevice, stream));
-		blockTaskDevice = tableBytes > 0 ? (const int32_t *)((const uint8_t *)r->dTasks.ptr + taskBytes) : nullptr;
+		textureTableDevice = (const TexDev *)((const uint8_t *)r->dTasks.ptr + taskBytes);
+		blockTaskDevice = tableBytes > 0 ? (const int32_t *)((const uint8_t *)r->dTasks.ptr + taskBytes + textureBytes) : nullptr;
 	}
 	DFPSR_CHECK_CUDA(cudaMemcpyAsync(r->dViews.ptr, r->views.data(), viewCount * sizeof(ViewDev), cudaMemcpyHostToDevice, stream));
 	DFPSR_CHECK_CUDA(cudaMemsetAsync(r->tileCount.ptr, 0, ((size_t)tileTotal + 12) * 4, stream)); // tile counts, cursors of empty frames, totals
@@ -1959,6 +2133,15 @@ static int renderer_end_internal(dfpsr_renderer *r, cudaStream_t stream) {
 	memset(&frame, 0, sizeof(frame));
 	frame.tasks = (const TaskParams *)r->dTasks.ptr;
 	frame.blockTask = blockTaskDevice;
+	frame.textures = textureTableDevice;
+	// Which tile kernel draws the frame: alpha-filtered commands blend in submission order and need the immediate kernel; frames of solid
+	// commands take the deferred one (visibility first, every pixel shaded once), in exact or in tolerance mode.
+	bool anyAlpha = false;
+	for (const TaskParams &t : r->tasks) { anyAlpha = anyAlpha || t.filter == DFPSR_FILTER_ALPHA; }
+	static const char *tileModeOverride = getenv("DFPSR_TILE_MODE"); // developer aid: "immediate" forces the round-1 kernel for A/B timing
+	const bool immediate = anyAlpha || (tileModeOverride && strcmp(tileModeOverride, "immediate") == 0);
+	const bool exactFrame = r->depthOnly || immediate || r->exact;
+	frame.checkpoints = exactFrame ? 1 : 0;
 	frame.views = (const ViewDev *)r->dViews.ptr;
 	frame.taskCount = (int32_t)taskCount; frame.viewCount = (int32_t)viewCount; frame.blockCount = blockTotal;
 	frame.tileTotal = tileTotal;
@@ -2020,14 +2203,15 @@ static int renderer_end_internal(dfpsr_renderer *r, cudaStream_t stream) {
 			}
 		}
 	}
-	dim3 grid((tileTotal + RASTER_WARPS - 1) / RASTER_WARPS, 1, 1);
-	if (viewCount > 1 && viewCount <= 65535) {
-		uint32_t largest = 0;
-		for (const ViewDev &v : r->views) { largest = std::max(largest, (uint32_t)(v.tilesX * v.tilesY)); }
-		grid = dim3((largest + RASTER_WARPS - 1) / RASTER_WARPS, (unsigned)viewCount, 1);
-	}
-	if (r->depthOnly) { DFPSR_LAUNCH(raster_kernel<true>, grid, RASTER_WARPS * 32, 0, stream, frame, r->textures); }
-	else { DFPSR_LAUNCH(raster_kernel<false>, grid, RASTER_WARPS * 32, 0, stream, frame, r->textures); }
+	// grid = (tile columns of the widest view / warps per CTA, tile rows of the tallest view, views)
+	uint32_t widest = 0, tallest = 0;
+	for (const ViewDev &v : r->views) { widest = std::max(widest, (uint32_t)v.tilesX); tallest = std::max(tallest, (uint32_t)v.tilesY); }
+	DFPSR_REQUIRE(viewCount <= 65535 && tallest <= 65535u, "more than 65535 views in one batch or a target taller than 262140 rows");
+	const dim3 grid((widest + RASTER_WARPS - 1) / RASTER_WARPS, tallest, (unsigned)viewCount);
+	if (r->depthOnly) { DFPSR_LAUNCH(tile_kernel_depth, grid, RASTER_WARPS * 32, 0, stream, frame); }
+	else if (immediate) { DFPSR_LAUNCH(tile_kernel_immediate, grid, RASTER_WARPS * 32, 0, stream, frame); }
+	else if (exactFrame) { DFPSR_LAUNCH(tile_kernel_deferred, grid, RASTER_WARPS * 32, 0, stream, frame); }
+	else { DFPSR_LAUNCH(tile_kernel_tolerance, grid, RASTER_WARPS * 32, 0, stream, frame); }
 	if (timing) {
 		fprintf(stderr, "renderer_end: %zu tasks, %zu views | layout+upload %.0f us, first launches %.0f us, wait for totals %.0f us, second launches %.0f us\n",
 		        taskCount, viewCount, tUploaded - tStart, tLaunched - tUploaded, tSynced - tLaunched, host_now_us() - tSynced);
@@ -2037,12 +2221,33 @@ static int renderer_end_internal(dfpsr_renderer *r, cudaStream_t stream) {
 
 extern "C" {
 
+// DFPSR_PRECISION=tolerance in the environment changes the initial default (A/B runs of the test-suite and the bench)
+static bool initial_precision_exact() { const char *e = getenv("DFPSR_PRECISION"); return !(e && strcmp(e, "tolerance") == 0); }
+static thread_local bool g_defaultExact = initial_precision_exact();
+static thread_local dfpsr_renderer *g_immediate = nullptr;
+
 int dfpsr_renderer_create(dfpsr_renderer **out) {
 	DFPSR_REQUIRE(out != nullptr, "dfpsr_renderer_create: null output");
 	int n = 0;
 	DFPSR_REQUIRE(cudaGetDeviceCount(&n) == cudaSuccess && n > 0, "no CUDA device available; dfpsr_b200 has no CPU fallback");
 	*out = new (std::nothrow) dfpsr_renderer();
 	DFPSR_REQUIRE(*out != nullptr, "out of host memory");
+	(*out)->exact = g_defaultExact;
+	return 0;
+}
+
+int dfpsr_renderer_set_precision(dfpsr_renderer *renderer, int32_t precision) {
+	DFPSR_REQUIRE(renderer != nullptr, "renderer_set_precision: renderer does not exist");
+	DFPSR_REQUIRE(precision == DFPSR_PRECISION_EXACT || precision == DFPSR_PRECISION_TOLERANCE, "renderer_set_precision: unknown precision %d", precision);
+	DFPSR_REQUIRE(!renderer->receiving, "renderer_set_precision: call outside of renderer_begin / renderer_end");
+	renderer->exact = precision == DFPSR_PRECISION_EXACT;
+	return 0;
+}
+
+int dfpsr_set_default_precision(int32_t precision) {
+	DFPSR_REQUIRE(precision == DFPSR_PRECISION_EXACT || precision == DFPSR_PRECISION_TOLERANCE, "set_default_precision: unknown precision %d", precision);
+	g_defaultExact = precision == DFPSR_PRECISION_EXACT;
+	if (g_immediate != nullptr) { g_immediate->exact = g_defaultExact; }
 	return 0;
 }
 
@@ -2111,7 +2316,7 @@ int dfpsr_renderer_give_task_triangles(dfpsr_renderer *renderer, const dfpsr_tri
 	task.depthOnly = renderer->depthOnly ? 1 : 0;
 	task.diffuseIndex = register_texture(renderer, diffuse);
 	task.lightIndex = register_texture(renderer, light);
-	DFPSR_REQUIRE(task.diffuseIndex != -2 && task.lightIndex != -2, "more than %d distinct textures in one frame", MAX_TEXTURES);
+	DFPSR_REQUIRE(task.diffuseIndex != -2 && task.lightIndex != -2, "more than %d textures in one frame", MAX_TEXTURES);
 	renderer->tasks.push_back(task);
 	return 0;
 }
@@ -2300,8 +2505,6 @@ int dfpsr_renderer_last_command_count(dfpsr_renderer *renderer, int64_t *count, 
 	*count = renderer->lastCommands;
 	return 0;
 }
-
-static thread_local dfpsr_renderer *g_immediate = nullptr;
 
 static int immediate_renderer(dfpsr_renderer **out) {
 	if (g_immediate == nullptr) {

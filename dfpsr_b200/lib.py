@@ -43,6 +43,8 @@ SIGNATURES = {
     "dfpsr_texture_from_image": (i32, [P(abi.Texture), P(abi.Image), vp]),
     "dfpsr_renderer_create": (i32, [P(vp)]),
     "dfpsr_renderer_destroy": (i32, [vp]),
+    "dfpsr_renderer_set_precision": (i32, [vp, i32]),
+    "dfpsr_set_default_precision": (i32, [i32]),
     "dfpsr_renderer_begin": (i32, [vp, P(abi.Image), P(abi.Image)]),
     "dfpsr_renderer_begin_cleared": (i32, [vp, P(abi.Image), P(abi.Image), u32, f32]),
     "dfpsr_renderer_occlude_from_box": (i32, [vp, vp, vp, P(abi.Transform3D), P(abi.Camera)]),

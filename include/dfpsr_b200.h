@@ -189,6 +189,17 @@ typedef struct dfpsr_renderer dfpsr_renderer;
 /* ref: api/rendererAPI.h:56-58 renderer_create / (handle release) */
 int dfpsr_renderer_create(dfpsr_renderer **out);
 int dfpsr_renderer_destroy(dfpsr_renderer *renderer);
+/* Precision of the interpolated 1/W, U/W, V/W of colour frames (no counterpart in the reference; SURVEY.md §7 hard part 3).
+ *   DFPSR_PRECISION_EXACT (default): the reference's chains of float additions are replayed (shader/fillerTemplates.h:329-372), colour
+ *     and depth are bit-identical to the reference's scalar build.
+ *   DFPSR_PRECISION_TOLERANCE: the planes are evaluated directly at every quad (ITriangle2D.h:82-100) and 1/W uses the hardware
+ *     reciprocal, like the rcpps + Newton step of the reference's SSE build (base/simd.h:4047-4052): identical coverage, colours within
+ *     +-1 LSB per channel, depth within a few ulp (tests/test_gpu_tolerance.py states the bounds). Frames with alpha-filtered commands and
+ *     depth-only frames always use the exact path.
+ * dfpsr_set_default_precision applies to renderers created afterwards and to the calling thread's model_render* calls. */
+enum { DFPSR_PRECISION_EXACT = 0, DFPSR_PRECISION_TOLERANCE = 1 };
+int dfpsr_renderer_set_precision(dfpsr_renderer *renderer, int32_t precision);
+int dfpsr_set_default_precision(int32_t precision);
 /* ref: api/rendererAPI.h:66 renderer_begin. Either image may have data == NULL. Calling begin twice
  * without end is an error (ref: api/rendererAPI.cpp:152-154). */
 int dfpsr_renderer_begin(dfpsr_renderer *renderer, const dfpsr_image *color, const dfpsr_image *depth);

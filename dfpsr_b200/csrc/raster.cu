@@ -39,6 +39,12 @@ static const int RASTER_WARPS = 4;
 #ifndef RASTER_MIN_BLOCKS
 #define RASTER_MIN_BLOCKS 8 // 64 registers: measured 50 us per 1080p terrain frame against 63 us at 128 registers (tools/variant_sweep.py)
 #endif
+#ifndef RASTER_MIN_BLOCKS_DEFERRED
+#define RASTER_MIN_BLOCKS_DEFERRED 8
+#endif
+#ifndef RASTER_MIN_BLOCKS_TOLERANCE
+#define RASTER_MIN_BLOCKS_TOLERANCE 8
+#endif
 static const int LOCAL_SORT = 64;           // tile lists up to this long are sorted by the tile kernel's own warp (two keys per lane)
 static const int SORT_THREADS = 256;
 static const int SORT_SMEM = 4096;         // entries of one tile list sorted in shared memory by a CTA; longer lists use the rank sort
@@ -95,8 +101,8 @@ struct TaskParams {
 	dfpsr_camera camera;
 };
 
-// One render target pair of the batch.
-struct ViewDev {
+// One render target pair of the batch (96 bytes, read by the tile kernel with six 16-byte loads).
+struct __align__(16) ViewDev {
 	dfpsr_image color, depth; // data == nullptr when absent
 	int32_t width, height;
 	int32_t clipTop, clipBottom; // rows this process draws (strip mode; multiples of TILE_H or the image height)
@@ -105,7 +111,9 @@ struct ViewDev {
 	float clearDepth;
 	uint32_t tileBase;           // index of this view's first tile in the batch
 	int32_t tilesX, tilesY;
+	int32_t pad_[2];
 };
+static_assert(sizeof(ViewDev) == 96, "ViewDev layout");
 
 // One texture of the frame's table (ref: implementation/image/Texture.h:42-95); Cmd::flags carries 12-bit indices into the table.
 struct TexDev {
@@ -1450,7 +1458,7 @@ static const uint32_t NO_WINNER = 0xFFFFFFFFu;
 // EXACT: true   the interpolated values replay the reference's chains of float additions (bit-identical to its scalar build)
 //        false  tolerance mode: planes evaluated directly per quad, approximate reciprocal; no checkpoints anywhere (deferred mode only)
 template <int MODE, bool EXACT>
-__global__ void __launch_bounds__(RASTER_WARPS * 32, RASTER_MIN_BLOCKS) raster_kernel(FrameDev frame) {
+__global__ void __launch_bounds__(RASTER_WARPS * 32, (MODE == TILE_DEFERRED ? (EXACT ? RASTER_MIN_BLOCKS_DEFERRED : RASTER_MIN_BLOCKS_TOLERANCE) : RASTER_MIN_BLOCKS)) raster_kernel(FrameDev frame) {
 	constexpr bool DEPTH_ONLY = MODE == TILE_DEPTH_ONLY, DEFERRED = MODE == TILE_DEFERRED;
 	static_assert(EXACT || DEFERRED, "tolerance mode exists for the deferred tile kernel only");
 	typedef typename RecOf<EXACT>::type RecT;
@@ -1462,7 +1470,13 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32, RASTER_MIN_BLOCKS) raster_k
 	uint32_t *sMask = sMaskAll[warp];
 
 	// grid = (tile columns of the widest view / RASTER_WARPS, tile rows of the tallest view, views): no division, no search
-	const ViewDev &vw = frame.views[blockIdx.z];
+	ViewDev vw;
+	{
+		const uint4 *src = (const uint4 *)(frame.views + blockIdx.z);
+		uint4 *dst = (uint4 *)&vw;
+#pragma unroll
+		for (int w = 0; w < (int)(sizeof(ViewDev) / 16); w++) { dst[w] = __ldg(src + w); }
+	}
 	const int32_t tilesX = vw.tilesX;
 	const int32_t tileX = (int32_t)(blockIdx.x * RASTER_WARPS) + warp, tileY = (int32_t)blockIdx.y;
 	if (tileX >= tilesX || tileY >= vw.tilesY) { return; }
@@ -1512,7 +1526,8 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32, RASTER_MIN_BLOCKS) raster_k
 		int32_t px = x0 + (l & 1), py = y1 + (l >> 1);
 		col[l] = vw.clearColor; dep[l] = vw.clearDepth;
 		if (!clear && in[l]) {
-			if (hasColor) { col[l] = row_ptr<uint32_t>(color.data, color.stride, py)[px]; }
+			// deferred mode never reads the colour target: pixels nobody wins keep what they hold (they are not stored)
+			if (hasColor && !DEFERRED) { col[l] = row_ptr<uint32_t>(color.data, color.stride, py)[px]; }
 			if (hasDepth) { dep[l] = row_ptr<float>(depth.data, depth.stride, py)[px]; }
 		}
 	}
@@ -1891,10 +1906,62 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32, RASTER_MIN_BLOCKS) raster_k
 	if constexpr (DEFERRED) {
 		// ---- shading pass: every pixel that some command won is shaded once, by that command
 		if (hasColor) {
+			const bool valid[4] = {win[0] != NO_WINNER, win[1] != NO_WINNER, win[2] != NO_WINNER, win[3] != NO_WINNER};
+			uint32_t fl[4];
+#pragma unroll
+			for (int l = 0; l < 4; l++) { fl[l] = valid[l] ? __ldg(&frame.cmds[win[l]].flags) : 0u; }
+			// Fast path, chosen by the whole warp: every winner is a plain textured command (diffuse texture, no light map, colourless
+			// vertices: RgbaMultiply.h:75-79) and the lane's winners share one texture. The four pixels are then sampled side by side —
+			// sixteen texel loads in flight — instead of one shader variant dispatch per pixel.
+			const uint32_t PATTERN = CMD_HAS_DIFFUSE | CMD_HAS_LIGHT | CMD_HAS_FADE | CMD_COLORLESS | (0xFFFu << 8);
+			uint32_t common = 0u;
+			bool plain = true;
 #pragma unroll
 			for (int l = 0; l < 4; l++) {
-				if (win[l] != NO_WINNER) {
-					col[l] = shade_pixel<EXACT>(frame.cmds + win[l], frame.textures, dep[l], su[l], sv[l], (mips >> (8 * l)) & 0xFFu, shifts);
+				if (valid[l]) {
+					const uint32_t pattern = fl[l] & PATTERN;
+					if (common == 0u) { common = pattern; }
+					plain = plain && pattern == common && (pattern & 0xFFu) == (CMD_HAS_DIFFUSE | CMD_COLORLESS);
+				}
+			}
+			if (__all_sync(0xffffffffu, plain)) {
+				if (common != 0u) {
+					const TexDev t = load_tex(frame.textures, (common >> 8) & 0xFFFu);
+					float u[4], v[4];
+					float4 t0 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), t1 = t0;
+					uint32_t current = NO_WINNER;
+#pragma unroll
+					for (int l = 0; l < 4; l++) {
+						u[l] = 0.0f; v[l] = 0.0f;
+						if (valid[l]) {
+							if (win[l] != current) { // texture coordinates of the command: words 7 and 8 of its record
+								current = win[l];
+								const float4 *words = (const float4 *)(frame.cmds + current);
+								t0 = __ldg(words + 7); t1 = __ldg(words + 8);
+							}
+							float wb, wc;
+							if (fl[l] & CMD_AFFINE) { wb = su[l]; wc = sv[l]; }
+							else { const float linearDepth = reciprocal_w<EXACT>(dep[l]); wb = su[l] * linearDepth; wc = sv[l] * linearDepth; }
+							const float wa = 1.0f - (wb + wc);
+							const float cu[3] = {t0.x, t0.y, t0.z}, cv[3] = {t0.w, t1.x, t1.y};
+							u[l] = interpolate3(cu, wa, wb, wc); v[l] = interpolate3(cv, wa, wb, wc);
+						}
+					}
+					uint32_t texel[4];
+#pragma unroll
+					for (int l = 0; l < 4; l++) { texel[l] = sample_bilinear(t, u[l], v[l], (mips >> (8 * l)) & 0xFFu); } // pixels nobody won sample (0, 0) and are dropped
+#pragma unroll
+					for (int l = 0; l < 4; l++) {
+						float r, g, b, a;
+						unpack_bytes(texel[l], r, g, b, a);
+						const uint32_t packed = pack_rgba_ordered(saturated_byte(r), saturated_byte(g), saturated_byte(b), saturated_byte(a), shifts);
+						if (valid[l]) { col[l] = packed; }
+					}
+				}
+			} else {
+#pragma unroll
+				for (int l = 0; l < 4; l++) {
+					if (valid[l]) { col[l] = shade_pixel<EXACT>(frame.cmds + win[l], frame.textures, dep[l], su[l], sv[l], (mips >> (8 * l)) & 0xFFu, shifts); }
 				}
 			}
 		}
@@ -1903,11 +1970,15 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32, RASTER_MIN_BLOCKS) raster_k
 	if (dirty) {
 		// each lane owns 2 adjacent pixels in two rows: 8-byte stores (when the row is 8-byte aligned), 128 contiguous bytes per row per half-warp
 		if (hasColor) {
+			// deferred mode without a clear: pixels nobody won were never loaded and are not stored
+			const bool keep = DEFERRED && !clear;
+			const bool s0 = in[0] && !(keep && win[0] == NO_WINNER), s1 = in[1] && !(keep && win[1] == NO_WINNER);
+			const bool s2 = in[2] && !(keep && win[2] == NO_WINNER), s3 = in[3] && !(keep && win[3] == NO_WINNER);
 			uint32_t *upper = row_ptr<uint32_t>(color.data, color.stride, y1) + x0, *lower = row_ptr<uint32_t>(color.data, color.stride, y2) + x0;
-			if (in[0] && in[1] && (((uintptr_t)upper) & 7u) == 0) { *(uint2 *)upper = make_uint2(col[0], col[1]); }
-			else { if (in[0]) { upper[0] = col[0]; } if (in[1]) { upper[1] = col[1]; } }
-			if (in[2] && in[3] && (((uintptr_t)lower) & 7u) == 0) { *(uint2 *)lower = make_uint2(col[2], col[3]); }
-			else { if (in[2]) { lower[0] = col[2]; } if (in[3]) { lower[1] = col[3]; } }
+			if (s0 && s1 && (((uintptr_t)upper) & 7u) == 0) { *(uint2 *)upper = make_uint2(col[0], col[1]); }
+			else { if (s0) { upper[0] = col[0]; } if (s1) { upper[1] = col[1]; } }
+			if (s2 && s3 && (((uintptr_t)lower) & 7u) == 0) { *(uint2 *)lower = make_uint2(col[2], col[3]); }
+			else { if (s2) { lower[0] = col[2]; } if (s3) { lower[1] = col[3]; } }
 		}
 		if (hasDepth) {
 			float *upper = row_ptr<float>(depth.data, depth.stride, y1) + x0, *lower = row_ptr<float>(depth.data, depth.stride, y2) + x0;

@@ -10,7 +10,8 @@ import numpy as np
 from . import abi
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libdfpsr_b200.so")
+# DFPSR_LIB selects another build of the same library (tuning variants built by tools/build_variants.py); the product build is the default
+LIB_PATH = os.environ.get("DFPSR_LIB") or os.path.join(HERE, "libdfpsr_b200.so")
 _lib = None
 
 i32, u32, f32, vp, i64, u64, sz = C.c_int32, C.c_uint32, C.c_float, C.c_void_p, C.c_int64, C.c_uint64, C.c_size_t

@@ -1,13 +1,16 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the rendering hot path (see BASELINE.json / SURVEY.md §8d).
 
-Workload (config.workload = "terrain_1080p_views"): BASELINE config 4 — a batch of independent 1920x1080 camera views of
+Workload (config.workload = "terrain_1080p_views"): BASELINE config 4 — a batch of 256 independent 1920x1080 camera views of
 the terrain scene (config 1's scene: 4096 points, ~7.6 k triangles, 1024x1024 texture with 5 mip levels), each view into
-its own RGBA8 colour + F32 depth target, cleared and rendered through dfpsr_model_render_views. One step = `--views`
-views per GPU (default 256); ranks render disjoint view sets with no collective (weak scaling).
-  value   frames/s over all ranks, inputs resident in HBM, CUDA-event timed, max over ranks
-  e2e     the same views through the host-buffer entry point dfpsr_session_render_frame_host: geometry uploaded from
-          pinned host memory and the finished colour image downloaded every frame
+its own RGBA8 colour + F32 depth target, cleared and rendered through dfpsr_model_render_views. One step = the whole batch,
+SHARDED over the ranks (256 / N views per GPU, strong scaling, no data-path collective); every rank checks the sha256 of the
+first and last view of its shard against the compiled reference's hashes (tests/golden/bench_views.json) -> "parity_ok".
+  value   frames/s over all ranks, inputs resident in HBM, CUDA-event timed, max over ranks; exact (bit-identical) mode
+  e2e     the same shard through the host-buffer entry point dfpsr_session_render_views_host: geometry and cameras uploaded
+          from pinned host memory and every finished colour image downloaded to pinned host memory, every step
+  extras  tolerance-mode numbers of the same step, the weak-scaling figure (256 views per GPU), strip mode over NVLink when
+          N > 1, and the other BASELINE configs on one GPU (bench_extras.py)
   --impl reference   the unmodified reference renderer (oracle/_ref, SSE2 build, its own worker threads) on the host CPU
 """
 import argparse
@@ -114,7 +117,7 @@ def reference_arm(args, rank):
     import refbind
     from dfpsr_b200 import abi, scenes
     sc = scenes.terrain_scene()
-    frames_per_step = 16
+    frames_per_step = args.views  # the same batch as the GPU arm: every view of the step, one after the other
     if refbind.available("sse"):
         ref = refbind.Ref("sse")
         kind, cores = "reference", max(min(ref.lib.ref_thread_count() - 1, 12), 1)
@@ -140,6 +143,13 @@ def reference_arm(args, rank):
             d[:] = 0
             cam = orcbind.camera(scenes.orbit_camera(i % args.views, WIDTH, HEIGHT, frames_per_lap=args.views))
             lib.orc_model_render(C.byref(model), C.byref(ident), C.byref(orcbind.image_of(c)), C.byref(orcbind.image_of(d)), C.byref(cam))
+    # bounded sample: every view of the batch per step when the host manages that within about two minutes, else the first views of it
+    frame(0)
+    t0 = time.perf_counter()
+    for i in range(4):
+        frame(i)
+    per_frame = (time.perf_counter() - t0) / 4
+    frames_per_step = max(min(frames_per_step, int(120.0 / (per_frame * (args.steps + args.warmup)))), min(frames_per_step, 8))
     n = 0
     for _ in range(args.warmup):
         for _ in range(frames_per_step):
@@ -152,12 +162,13 @@ def reference_arm(args, rank):
             n += 1
     elapsed = time.perf_counter() - t0
     fps = args.steps * frames_per_step / elapsed
-    sample = f"{frames_per_step} consecutive orbit views per step (of the {args.views}-view batch), image_fill x2 + renderer_begin/giveTask/end each, host memory"
+    sample = f"{frames_per_step} of the batch's {args.views} orbit views per step, image_fill x2 + renderer_begin/giveTask/end each, host memory"
     print(json.dumps({
         "impl": "reference", "metric": "frames/s at 1920x1080, terrain view batch", "value": fps, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * elapsed / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "terrain_1080p_views", "views_per_step_per_gpu": args.views, "width": WIDTH, "height": HEIGHT},
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "terrain_1080p_views", "views_per_step": args.views, "width": WIDTH, "height": HEIGHT, "triangles": int(2 * len(sc["polygons"])),
+                   "texture": "1024x1024 RGBA8, 5 mip levels"},
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "mpix_per_s": fps * WIDTH * HEIGHT / 1e6,
@@ -189,13 +200,20 @@ def cpu_baseline(views, seconds=12.0):
             "sample": f"{n} orbit views in {elapsed:.1f} s through the unmodified reference (oracle/_ref, g++ -O2 SSE2 build, {threads} hardware threads): image_fill x2 + renderer_begin/giveTask/end per view"}
 
 
+def view_hashes(color, depth, index):
+    import hashlib
+    return (hashlib.sha256(color[index].cpu().numpy().tobytes()).hexdigest(), hashlib.sha256(depth[index].cpu().numpy().tobytes()).hexdigest())
+
+
 def main():
     parser = argparse.ArgumentParser()
     parser.add_argument("--gpus", type=int, default=1)
     parser.add_argument("--steps", type=int, default=20)
     parser.add_argument("--warmup", type=int, default=3)
     parser.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    parser.add_argument("--views", type=int, default=256, help="views per step per GPU")
+    parser.add_argument("--views", type=int, default=256, help="views per step over ALL GPUs (BASELINE config 4: 256)")
+    parser.add_argument("--precision", default="exact", choices=["exact", "tolerance"], help="headline mode (the other one goes to extras)")
+    parser.add_argument("--sync", action="store_true", help="renderer_end waits for the set-up counts of every frame (round-1 behaviour)")
     parser.add_argument("--no-cpu-baseline", action="store_true")
     parser.add_argument("--no-extras", action="store_true")
     args = parser.parse_args()
@@ -209,7 +227,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from dfpsr_b200 import abi, lib, scenes
+    from dfpsr_b200 import abi, lib, scenes, shard
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
@@ -220,30 +238,49 @@ def main():
     if distributed:
         os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib.check(cuda.dfpsr_set_default_async(0 if args.sync else 1))
+    headline_exact = args.precision == "exact"
+    lib.check(cuda.dfpsr_set_default_precision(0 if headline_exact else 1))
 
     sc = scenes.terrain_scene()
     texture = lib.DeviceTexture(sc["texture"], 5)
     model = lib.DeviceModel(sc["points"], sc["polygons"], abi.FILTER_SOLID, texture)
-    views = args.views
-    # each rank renders its own arc of the orbit: view v of rank r is orbit frame r * views + v of a (world * views)-frame lap
-    cameras = (abi.Camera * views)()
-    for v in range(views):
-        cameras[v] = lib.camera(scenes.orbit_camera(rank * views + v, WIDTH, HEIGHT, frames_per_lap=world * views))
-    color = torch.empty((views, HEIGHT, WIDTH), dtype=torch.int32, device="cuda")
-    depth = torch.empty((views, HEIGHT, WIDTH), dtype=torch.float32, device="cuda")
-    colors = (abi.Image * views)(*[lib.image(color[v]) for v in range(views)])
-    depths = (abi.Image * views)(*[lib.image(depth[v]) for v in range(views)])
+    total_views = args.views
+    mine = shard.view_range(rank, world, total_views)  # strong scaling: the batch is sharded, view v of the batch is orbit frame v of a total_views-frame lap
+    views = len(mine)
+    capacity = max(views, total_views if not args.no_extras else views)  # the weak-scaling extra renders a whole batch on every rank
+    cameras = (abi.Camera * capacity)()
+    for i in range(capacity):
+        cameras[i] = lib.camera(scenes.orbit_camera((mine.start + i) % total_views, WIDTH, HEIGHT, frames_per_lap=total_views))
+    color = torch.empty((capacity, HEIGHT, WIDTH), dtype=torch.int32, device="cuda")
+    depth = torch.empty((capacity, HEIGHT, WIDTH), dtype=torch.float32, device="cuda")
+    colors = (abi.Image * capacity)(*[lib.image(color[v]) for v in range(capacity)])
+    depths = (abi.Image * capacity)(*[lib.image(depth[v]) for v in range(capacity)])
     ident = abi.Transform3D.identity()
     stream = torch.cuda.current_stream()
     sp = lib.stream_ptr(stream)
 
-    def step():
-        lib.check(cuda.dfpsr_model_render_views(C.byref(model.desc), C.byref(ident), colors, depths, cameras, views, 1, sp))
+    def step(n=views):
+        lib.check(cuda.dfpsr_model_render_views(C.byref(model.desc), C.byref(ident), colors, depths, cameras, n, 1, sp))
 
     def barrier():
+        lib.check(cuda.dfpsr_flush())
         if distributed:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def timed_steps(steps, n=views):
+        barrier()
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record(stream)
+        for _ in range(steps):
+            step(n)
+        stop.record(stream)
+        barrier()
+        ms = torch.tensor([start.elapsed_time(stop)], dtype=torch.float64, device="cuda")
+        if distributed:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
 
     for _ in range(args.warmup):
         step()
@@ -252,48 +289,86 @@ def main():
     if rank == 0:
         sampler.start()
     cuda.dfpsr_reset_launch_count()
-    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    start.record(stream)
-    for _ in range(args.steps):
-        step()
-    stop.record(stream)
-    barrier()
-    elapsed_ms = torch.tensor([start.elapsed_time(stop)], dtype=torch.float64, device="cuda")
+    elapsed_ms = timed_steps(args.steps)
     launches = int(cuda.dfpsr_launch_count())
     clocks = sampler.stop() if rank == 0 else None
-    if distributed:
-        dist.all_reduce(elapsed_ms, op=dist.ReduceOp.MAX)
-    elapsed_ms = float(elapsed_ms.item())
-    total_frames = world * views * args.steps
-    fps = total_frames / (elapsed_ms / 1000.0)
+    fps = total_views * args.steps / (elapsed_ms / 1000.0)
 
-    # ---- roofline of the dominant kernel (raster_kernel), per-launch device time from CUDA events on the launching stream
+    # ---- parity of what was just timed: first and last view of this rank's shard against the compiled reference's hashes
+    golden_path = os.path.join(ROOT, "tests", "golden", "bench_views.json")
+    parity, parity_views = None, []
+    if headline_exact and os.path.exists(golden_path) and views > 0:
+        golden = json.load(open(golden_path))
+        if golden["views_per_lap"] == total_views and golden["width"] == WIDTH and golden["height"] == HEIGHT:
+            ok = True
+            for local in sorted({0, views - 1}):
+                expected = golden["views"].get(str(mine.start + local))
+                if expected is not None:
+                    got = view_hashes(color, depth, local)
+                    ok = ok and got == (expected["color_sha256"], expected["depth_sha256"])
+                    parity_views.append(mine.start + local)
+            flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device="cuda")
+            if distributed:
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            parity = bool(flag.item()) if parity_views or distributed else None
+
+    # ---- roofline of the dominant kernel (the tile kernel), per-launch device time from CUDA events on the launching stream
+    tile_kernel = "tile_kernel_deferred" if headline_exact else "tile_kernel_tolerance"
     lib.check(cuda.dfpsr_profile_reset())
     lib.check(cuda.dfpsr_profile_enable(1))
     step()
-    torch.cuda.synchronize()
+    barrier()
     lib.check(cuda.dfpsr_profile_enable(0))
     profile = lib.profile_snapshot()
     total_kernel_ms = sum(ms for ms, _ in profile.values())
-    raster_ms, raster_launches = profile.get("raster_kernel<false>", (0.0, 0))
+    raster_ms, raster_launches = profile.get(tile_kernel, (0.0, 0))
     peak, peak_source = load_peaks()
-    launch_bytes = ALGORITHMIC_BYTES_PER_FRAME * views  # one launch rasterises every view of the step
+    launch_bytes = ALGORITHMIC_BYTES_PER_FRAME * views  # one launch rasterises every view of this rank's shard
     launch_us = 1000.0 * raster_ms / max(raster_launches, 1)
     achieved = (launch_bytes / 1e9) / (launch_us / 1e6) if raster_ms > 0 else 0.0
     traffic, traffic_source = None, None
-    traffic_path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    traffic_path = os.path.join(ROOT, "profiles", "r2_traffic.json")
     if os.path.exists(traffic_path):  # dram bytes of this kernel from one `ncu --set full` capture of this very command (never measured under the timer)
-        t = json.load(open(traffic_path)).get("raster_kernel<false>")
+        t = json.load(open(traffic_path)).get(tile_kernel)
         if t:
             traffic, traffic_source = t["dram_bytes_per_launch"] * views / t["views_per_launch"], t["source"]
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_source,
-                "kernel": "raster_kernel<false>", "avg_launch_us": launch_us, "frames_per_launch": views,
+                "kernel": tile_kernel, "avg_launch_us": launch_us, "frames_per_launch": views,
                 "algorithmic_bytes_per_launch": launch_bytes, "algorithmic_bytes_per_frame": ALGORITHMIC_BYTES_PER_FRAME, "peak_source": peak_source,
                 "kernel_share_of_device_time": raster_ms / total_kernel_ms if total_kernel_ms > 0 else None,
-                "per_kernel_us_per_frame": {k: 1000.0 * ms / views for k, (ms, n) in sorted(profile.items())},
-                "note": "the tile kernel is instruction-issue bound (bit-exact shading), not HBM bound: see DESIGN.md section 6 and profiles/"}
+                "per_kernel_us_per_frame": {k: 1000.0 * ms / max(views, 1) for k, (ms, n) in sorted(profile.items())},
+                "note": "the tile kernel is instruction-issue bound (bit-exact shading: replayed addition chains, 8.8 fixed-point bilinear), not HBM bound: see DESIGN.md section 6 and profiles/r2_*"}
 
-    # ---- end to end through the host-buffer entry point: every step uploads the geometry and the step's cameras from pinned host
+    # ---- the other precision mode on the same step, and the weak-scaling figure (every rank renders a whole batch)
+    other = {}
+    if not args.no_extras:
+        lib.check(cuda.dfpsr_set_default_precision(1 if headline_exact else 0))
+        for _ in range(2):
+            step()
+        other_ms = timed_steps(max(args.steps // 2, 2))
+        lib.check(cuda.dfpsr_profile_reset())
+        lib.check(cuda.dfpsr_profile_enable(1))
+        step()
+        barrier()
+        lib.check(cuda.dfpsr_profile_enable(0))
+        other_profile = lib.profile_snapshot()
+        lib.check(cuda.dfpsr_set_default_precision(0 if headline_exact else 1))
+        other_name = "tolerance" if headline_exact else "exact"
+        other_kernel = "tile_kernel_tolerance" if headline_exact else "tile_kernel_deferred"
+        other_us = 1000.0 * other_profile.get(other_kernel, (0.0, 0))[0]
+        other[other_name + "_mode"] = {
+            "frames_per_s": total_views * max(args.steps // 2, 2) / (other_ms / 1000.0), "tile_kernel_us_per_frame": other_us / max(views, 1),
+            "roofline_frac": (ALGORITHMIC_BYTES_PER_FRAME * views / 1e9) / (other_us / 1e6) / peak if other_us > 0 else None,
+            "per_kernel_us_per_frame": {k: 1000.0 * ms / max(views, 1) for k, (ms, n) in sorted(other_profile.items())},
+            "note": "tolerance mode: planes evaluated directly, hardware reciprocal; identical coverage, colours within +-1 LSB, depth within 2^-16 of the frame's range (tests/test_gpu_tolerance.py)" if headline_exact else "exact mode: bit-identical to the reference's scalar build"}
+        if distributed:
+            for _ in range(2):
+                step(total_views)
+            weak_ms = timed_steps(max(args.steps // 4, 2), total_views)
+            other["weak_scaling"] = {"views_per_gpu": total_views, "frames_per_s": world * total_views * max(args.steps // 4, 2) / (weak_ms / 1000.0),
+                                     "note": "every rank renders its own 256-view batch (round 1's headline definition)"}
+
+    # ---- end to end through the host-buffer entry point: every step uploads the geometry and the shard's cameras from pinned host
     # memory and brings every finished colour image back to pinned host memory; rendering of chunk k+1 overlaps the copy of chunk k
     session = C.c_void_p()
     lib.check(cuda.dfpsr_session_create(C.byref(session)))
@@ -309,11 +384,12 @@ def main():
     slot = C.c_int32()
     lib.check(cuda.dfpsr_session_upload_model(session, C.byref(hm), C.byref(slot)))
     e2e_views = views
-    color_host = torch.empty((e2e_views, HEIGHT, WIDTH), dtype=torch.int32).pin_memory()
-    host_ptrs = (C.c_void_p * e2e_views)(*[color_host[v].data_ptr() for v in range(e2e_views)])
+    color_host = torch.empty((max(e2e_views, 1), HEIGHT, WIDTH), dtype=torch.int32).pin_memory()
+    host_ptrs = (C.c_void_p * max(e2e_views, 1))(*[color_host[v].data_ptr() for v in range(max(e2e_views, 1))])
 
     def e2e_step():
-        lib.check(cuda.dfpsr_session_render_views_host(session, slot.value, C.byref(ident), cameras, e2e_views, host_ptrs, WIDTH * 4, None, 0, WIDTH, HEIGHT, abi.PACK_RGBA, 1, sp))
+        if e2e_views > 0:
+            lib.check(cuda.dfpsr_session_render_views_host(session, slot.value, C.byref(ident), cameras, e2e_views, host_ptrs, WIDTH * 4, None, 0, WIDTH, HEIGHT, abi.PACK_RGBA, 1, sp))
 
     e2e_step()
     barrier()
@@ -325,25 +401,39 @@ def main():
     e2e_elapsed = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
     if distributed:
         dist.all_reduce(e2e_elapsed, op=dist.ReduceOp.MAX)
-    e2e_fps = world * e2e_views * e2e_steps / float(e2e_elapsed.item())
-    e2e_checksum = int(color_host[0].to(torch.int64).sum().item()) & 0xFFFFFFFF
+    e2e_fps = total_views * e2e_steps / float(e2e_elapsed.item())
+    e2e_matches_device = bool(torch.equal(color_host[0], color[0].cpu())) if e2e_views > 0 else None  # the downloaded frame is the frame the timed region drew
     lib.check(cuda.dfpsr_session_destroy(session))
-    h2d_per_step = len(sc["points"]) * 12 + len(sc["polygons"]) * 144 + e2e_views * (C.sizeof(abi.Camera) + C.sizeof(abi.Transform3D))
-    e2e = {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d_per_step, "d2h_bytes_per_step": WIDTH * HEIGHT * 4 * e2e_views,
-           "views_per_step": e2e_views, "first_view_checksum": e2e_checksum,
-           "note": "dfpsr_session_render_views_host: per step the geometry and cameras come from pinned host memory and every finished 1080p colour image goes back to pinned host memory (PCIe-bound); 16-view chunks, copy of chunk k overlaps rendering of chunk k+1"}
+    h2d_per_step = world * (len(sc["points"]) * 12 + len(sc["polygons"]) * 144) + total_views * (C.sizeof(abi.Camera) + C.sizeof(abi.Transform3D))
+    e2e = {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d_per_step, "d2h_bytes_per_step": WIDTH * HEIGHT * 4 * total_views,
+           "views_per_step": total_views, "views_per_step_per_gpu": e2e_views, "first_view_equals_device_render": e2e_matches_device,
+           "note": "dfpsr_session_render_views_host: per step the geometry and cameras come from pinned host memory and every finished 1080p COLOUR image goes back to pinned host memory (the depth buffer is the renderer's working buffer and stays on the device); PCIe-bound; 16-view chunks, copy of chunk k overlaps rendering of chunk k+1"}
 
     extras = None
-    if rank == 0 and not args.no_extras:
-        try:
-            import bench_extras
-            extras = bench_extras.run(cuda, lib, cpu=not args.no_cpu_baseline)
-        except Exception as exc:  # secondary numbers must never break the headline line
-            extras = {"error": repr(exc)}
+    if not args.no_extras:
+        extras = dict(other)
+        if distributed:
+            try:  # one frame in row strips across the ranks: NCCL all_gather against the tile kernel's own stores into peer memory (every rank takes part)
+                sys.path.insert(0, os.path.join(ROOT, "tools"))
+                import strip_bench
+                strips = {}
+                for scene in ("terrain", "tiny"):
+                    result = strip_bench.run(cuda, scene, 10, rank, world)
+                    if rank == 0:
+                        strips[scene] = result
+                extras["strip_mode"] = strips
+            except Exception as exc:
+                extras["strip_mode"] = {"error": repr(exc)}
+        if rank == 0:
+            try:
+                import bench_extras
+                extras.update(bench_extras.run(cuda, lib, cpu=not args.no_cpu_baseline))
+            except Exception as exc:  # secondary numbers must never break the headline line
+                extras["error"] = repr(exc)
 
     baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        baseline = cpu_baseline(views)
+        baseline = cpu_baseline(total_views)
 
     if distributed:
         dist.barrier()
@@ -351,10 +441,12 @@ def main():
     if rank == 0:
         print(json.dumps({
             "metric": "frames/s at 1920x1080, terrain view batch", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "terrain_1080p_views", "views_per_step_per_gpu": views, "width": WIDTH, "height": HEIGHT, "triangles": int(2 * len(sc["polygons"])),
-                       "texture": "1024x1024 RGBA8, 5 mip levels", "l2": "each step writes views x 16.6 MB of colour+depth (4.25 GB at 256 views) — far larger than the 126 MB L2, no flush needed"},
-            "mpix_per_s": fps * WIDTH * HEIGHT / 1e6,
+            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "terrain_1080p_views", "views_per_step": total_views, "width": WIDTH, "height": HEIGHT, "triangles": int(2 * len(sc["polygons"])),
+                       "texture": "1024x1024 RGBA8, 5 mip levels"},
+            "details": {"views_per_step_per_gpu": views, "precision": args.precision, "asynchronous_frames": not args.sync,
+                        "l2": "each step writes 16.6 MB of colour+depth per view (4.25 GB per 256 views) — far larger than the 126 MB L2, no flush needed"},
+            "mpix_per_s": fps * WIDTH * HEIGHT / 1e6, "parity_ok": parity, "parity_views_checked_on_rank0": parity_views,
             "roofline": roofline, "cpu_baseline": baseline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "host_affinity": affinity, "extras": extras,
         }))
 

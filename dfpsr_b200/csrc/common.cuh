@@ -42,8 +42,15 @@ extern bool g_profile;
 void profile_begin(const char *name, cudaStream_t stream);
 void profile_end(cudaStream_t stream);
 
+// Frames of asynchronous renderers whose counts the host has not looked at yet (raster.cu). Everything this library queues while such
+// frames exist first verifies them, so that a frame that has to be drawn again still comes before its consumers.
+extern thread_local int g_pendingFrames;
+extern thread_local bool g_insideFrame;
+int verify_pending_frames();
+
 #define DFPSR_LAUNCH(kernel, grid, block, smem, stream, ...)                      \
 	do {                                                                          \
+		if (dfpsr::g_pendingFrames > 0 && !dfpsr::g_insideFrame && dfpsr::verify_pending_frames()) { return 1; } \
 		if (dfpsr::g_profile) { dfpsr::profile_begin(#kernel, (stream)); }        \
 		kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);               \
 		if (dfpsr::g_profile) { dfpsr::profile_end((stream)); }                   \

@@ -200,22 +200,27 @@ int dfpsr_free_host(void *pinnedPtr) {
 	return 0;
 }
 int dfpsr_upload(void *devicePtr, const void *hostPtr, size_t bytes, void *stream) {
+	if (g_pendingFrames > 0 && verify_pending_frames()) { return 1; } // frames in flight are verified before their targets are touched
 	DFPSR_CHECK_CUDA(cudaMemcpyAsync(devicePtr, hostPtr, bytes, cudaMemcpyHostToDevice, as_stream(stream)));
 	return 0;
 }
 int dfpsr_download(void *hostPtr, const void *devicePtr, size_t bytes, void *stream) {
+	if (g_pendingFrames > 0 && verify_pending_frames()) { return 1; } // frames in flight are verified before their targets are touched
 	DFPSR_CHECK_CUDA(cudaMemcpyAsync(hostPtr, devicePtr, bytes, cudaMemcpyDeviceToHost, as_stream(stream)));
 	return 0;
 }
 int dfpsr_upload_2d(void *devicePtr, size_t deviceStride, const void *hostPtr, size_t hostStride, size_t rowBytes, size_t rows, void *stream) {
+	if (g_pendingFrames > 0 && verify_pending_frames()) { return 1; } // frames in flight are verified before their targets are touched
 	DFPSR_CHECK_CUDA(cudaMemcpy2DAsync(devicePtr, deviceStride, hostPtr, hostStride, rowBytes, rows, cudaMemcpyHostToDevice, as_stream(stream)));
 	return 0;
 }
 int dfpsr_download_2d(void *hostPtr, size_t hostStride, const void *devicePtr, size_t deviceStride, size_t rowBytes, size_t rows, void *stream) {
+	if (g_pendingFrames > 0 && verify_pending_frames()) { return 1; } // frames in flight are verified before their targets are touched
 	DFPSR_CHECK_CUDA(cudaMemcpy2DAsync(hostPtr, hostStride, devicePtr, deviceStride, rowBytes, rows, cudaMemcpyDeviceToHost, as_stream(stream)));
 	return 0;
 }
 int dfpsr_stream_synchronize(void *stream) {
+	if (g_pendingFrames > 0 && verify_pending_frames()) { return 1; } // frames in flight are verified before their targets are touched
 	DFPSR_CHECK_CUDA(cudaStreamSynchronize(as_stream(stream)));
 	return 0;
 }

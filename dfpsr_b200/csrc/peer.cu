@@ -20,7 +20,8 @@ __global__ void peer_signal_kernel(FlagList flags, int32_t count, uint32_t value
 	}
 }
 
-// status[0]: 0 = ok, 1 = timed out (a rank never signalled; the waiter must not hang the device)
+// status[0]: number of waits through this status block that gave up (a rank never signalled; the waiter must not hang the device),
+// status[1]: the value the most recent of them was waiting for. Every wait site owns its block; dfpsr_peer_reset_status clears one.
 __global__ void peer_wait_kernel(const uint32_t *flags, int32_t count, uint32_t value, uint64_t timeoutNs, uint32_t *status) {
 	const int32_t i = (int32_t)threadIdx.x;
 	bool timedOut = false;
@@ -37,7 +38,7 @@ __global__ void peer_wait_kernel(const uint32_t *flags, int32_t count, uint32_t 
 			__nanosleep(64);
 		}
 	}
-	if (timedOut) { atomicExch(status, 1u); }
+	if (timedOut) { atomicAdd(status, 1u); atomicExch(status + 1, value); }
 	__threadfence_system();
 }
 
@@ -96,6 +97,12 @@ int dfpsr_peer_signal(uint32_t *const *flags, int32_t count, uint32_t value, voi
 		list.flag[i] = flags[i];
 	}
 	DFPSR_LAUNCH(peer_signal_kernel, 1, 32, 0, as_stream(stream), list, count, value);
+	return 0;
+}
+
+int dfpsr_peer_reset_status(uint32_t *status, void *stream) {
+	DFPSR_REQUIRE(status != nullptr, "peer_reset_status: null argument");
+	DFPSR_CHECK_CUDA(cudaMemsetAsync(status, 0, 2 * sizeof(uint32_t), as_stream(stream)));
 	return 0;
 }
 

@@ -129,6 +129,11 @@ struct FrameDev {
 	const ViewDev *views;
 	const TexDev *textures;          // the frame's texture table, uploaded behind the task records
 	int32_t checkpoints;             // 1: large commands leave interpolation checkpoints (exact mode); 0: tolerance mode, nothing to replay
+	// Pools of the second half of the frame (elements). The host sizes them from earlier frames and does not wait for this frame's counts:
+	// when checkCaps is set, the kernels behind the counting pass return at once if the frame does not fit (totals[TOTAL_OVERFLOW], set by
+	// counts_kernel) and the host draws the frame again with larger pools when it next looks (renderer_end_internal / verify_frame).
+	uint32_t capCmds, capRows, capEntries, capChk, capUnits, capSortTmp;
+	int32_t checkCaps;
 	int32_t taskCount, viewCount, blockCount;
 	uint32_t tileTotal;
 	uint32_t *slotCounts;            // per slot: command count | rows << 3
@@ -136,7 +141,8 @@ struct FrameDev {
 	uint32_t *tileCount, *tileOffset, *tileCursor;
 	uint32_t *totals;                // [0] commands, [1] rows, [2] tile entries (upper bound), [3] max entries in one tile (upper bound),
 	                                 // [4] checkpoint records (upper bound), [5] checkpoint cursor, [6] rank-sort scratch cursor,
-	                                 // [7] (command, tile row) units of large commands, [8] large command cursor, [9] unit cursor
+	                                 // [7] (command, tile row) units of large commands, [8] large command cursor, [9] unit cursor,
+	                                 // [10] the frame does not fit the pools, [11] finished CTAs of counts_kernel
 	Cmd *cmds;
 	int2 *rows;
 	uint32_t *tileList;
@@ -149,6 +155,13 @@ struct FrameDev {
 	const float *occlusionGrid;      // 16-pixel cells of the farthest depth at which something can still be visible; null = no occluders
 	int32_t gridWidth, gridHeight, gridStride;
 };
+
+static const int TOTAL_OVERFLOW = 10, TOTAL_TICKET = 11, TOTAL_WORDS = 12;
+
+// True when the frame's second half must not run: its counts exceed the pools it was launched with.
+__device__ __forceinline__ bool frame_dropped(const FrameDev &frame) {
+	return frame.checkCaps != 0 && frame.totals[TOTAL_OVERFLOW] != 0u;
+}
 
 // ------------------------------------------------------------------------------------------------ projection
 
@@ -195,8 +208,15 @@ __device__ __forceinline__ PPoint world_to_screen(const dfpsr_camera &c, const d
 	return camera_to_screen(c, cx, cy, cz);
 }
 
-// One launch for every task of the batch: blockIdx.y = task.
-__global__ void __launch_bounds__(256) project_kernel(const TaskParams *__restrict__ tasks) {
+// One launch for every task of the batch: blockIdx.y = task. Grid rows behind the tasks clear the frame's tile counters and totals
+// (`zeroWords` words at `zero`, 16-byte aligned), which saves the frame a separate memset.
+__global__ void __launch_bounds__(256) project_kernel(const TaskParams *__restrict__ tasks, int32_t taskCount, uint4 *__restrict__ zero, uint32_t zeroWords) {
+	if ((int32_t)blockIdx.y >= taskCount) {
+		const uint32_t quads = (zeroWords + 3u) / 4u; // the buffer is padded to a multiple of 16 bytes
+		const uint32_t i = (((uint32_t)blockIdx.y - (uint32_t)taskCount) * gridDim.x + blockIdx.x) * 256u + threadIdx.x;
+		if (i < quads) { zero[i] = make_uint4(0u, 0u, 0u, 0u); }
+		return;
+	}
 	__shared__ TaskParams task;
 	for (uint32_t w = threadIdx.x; w < sizeof(TaskParams) / 4; w += blockDim.x) { ((uint32_t *)&task)[w] = ((const uint32_t *)&tasks[blockIdx.y])[w]; }
 	__syncthreads();
@@ -677,6 +697,7 @@ __global__ void __launch_bounds__(SETUP_THREADS, SETUP_MIN_BLOCKS) setup_kernel(
 	__shared__ BigItem sBig[SETUP_THREADS];
 	__shared__ uint32_t sBigCount, sChkCount, sUnitCount, sItemBase, sUnitBase, sChkBase;
 	__shared__ uint32_t sUnitEnd[SETUP_THREADS]; // emit pass: inclusive prefix of tile rows over the queued commands
+	if (EMIT && frame_dropped(frame)) { return; }
 	{
 		if (threadIdx.x == 0) { sChkCount = 0; sUnitCount = 0; }
 		int32_t t = frame.blockTask ? frame.blockTask[blockIdx.x] : task_of_block(frame.tasks, frame.taskCount, (int32_t)blockIdx.x);
@@ -909,53 +930,60 @@ __global__ void __launch_bounds__(SETUP_THREADS, SETUP_MIN_BLOCKS) setup_kernel(
 // SPLIT: two threads per unit (adjacent lanes), one per row pair of the tile row — twice the threads and half the serial chain per thread for
 // frames whose units do not fill the machine anyway (one 1080p terrain frame has 15 k units); the bins of the two row pairs meet in a shuffle.
 template <bool SPLIT>
-__global__ void __launch_bounds__(256) big_units_kernel(FrameDev frame, uint32_t unitTotal) {
-	const uint32_t thread = blockIdx.x * blockDim.x + threadIdx.x;
-	const uint32_t u = SPLIT ? thread >> 1 : thread;
-	const int32_t half = SPLIT ? (int32_t)(thread & 1u) : 0;
-	// unitTotal is the first pass's count (the launch size); commands that overflowed a block's queue were finished by their own thread,
-	// so the cursor holds the number of units that were really queued
-	const bool valid = u < unitTotal && u < frame.totals[9];
-	if (!SPLIT && !valid) { return; }
-	int32_t minL = 0x7FFFFFFF, maxR = -1;
-	int32_t ty = 0, height = 0;
-	const BigItem *item = nullptr;
-	if (valid) {
-		const BigItem &it = frame.bigItems[frame.bigUnits[u]];
-		item = &it;
-		ty = it.t / TILE_H + (int32_t)(u - it.unitStart);
-		height = it.ty1; // the view's height travels in ty1 (unused by the emit pass)
-		const int32_t yBegin = max(it.t, ty * TILE_H), yEnd = min(it.t + it.rowCount, ty * TILE_H + TILE_H);
-		const int32_t yFirst = SPLIT ? yBegin + 2 * half : yBegin, yLast = SPLIT ? min(yEnd, yFirst + 2) : yEnd;
-		if (yFirst < yLast) {
-			EdgeSet edges;
-			long long fx[3] = {it.fx[0], it.fx[1], it.fx[2]}, fy[3] = {it.fy[0], it.fy[1], it.fy[2]};
-			edges_setup(edges, fx, fy, it.l, it.t, it.r);
-			float start[3], dx[3], dy[3];
-			const bool checkpoints = it.chkOffset != CHK_NONE;
-			if (checkpoints) {
-				const float *planes = (const float *)&frame.cmds[it.cmdIndex];
+__global__ void __launch_bounds__(256) big_units_kernel(FrameDev frame) {
+	if (frame_dropped(frame)) { return; }
+	// The grid is sized by the host from an earlier frame's unit count (it does not wait for this frame's): CTAs stride over the units
+	// the counting pass found. Commands that overflowed a set-up block's queue were finished by their own thread, so the cursor
+	// (totals[9]) holds the number of units that were really queued.
+	const uint32_t unitTotal = min(frame.totals[7], frame.totals[9]);
+	const uint32_t threadTotal = SPLIT ? 2u * unitTotal : unitTotal;
+	for (uint32_t first = blockIdx.x * blockDim.x; first < threadTotal; first += gridDim.x * blockDim.x) {
+		const uint32_t thread = first + threadIdx.x;
+		const uint32_t u = SPLIT ? thread >> 1 : thread;
+		const int32_t half = SPLIT ? (int32_t)(thread & 1u) : 0;
+		const bool valid = u < unitTotal;
+		if (!SPLIT && !valid) { continue; }
+		int32_t minL = 0x7FFFFFFF, maxR = -1;
+		int32_t ty = 0, height = 0;
+		const BigItem *item = nullptr;
+		if (valid) {
+			const BigItem &it = frame.bigItems[frame.bigUnits[u]];
+			item = &it;
+			ty = it.t / TILE_H + (int32_t)(u - it.unitStart);
+			height = it.ty1; // the view's height travels in ty1 (unused by the emit pass)
+			const int32_t yBegin = max(it.t, ty * TILE_H), yEnd = min(it.t + it.rowCount, ty * TILE_H + TILE_H);
+			const int32_t yFirst = SPLIT ? yBegin + 2 * half : yBegin, yLast = SPLIT ? min(yEnd, yFirst + 2) : yEnd;
+			if (yFirst < yLast) {
+				EdgeSet edges;
+				long long fx[3] = {it.fx[0], it.fx[1], it.fx[2]}, fy[3] = {it.fy[0], it.fy[1], it.fy[2]};
+				edges_setup(edges, fx, fy, it.l, it.t, it.r);
+				float start[3], dx[3], dy[3];
+				const bool checkpoints = it.chkOffset != CHK_NONE;
+				if (checkpoints) {
+					const float *planes = (const float *)&frame.cmds[it.cmdIndex];
 #pragma unroll
-				for (int k = 0; k < 3; k++) { start[k] = planes[k]; dx[k] = planes[3 + k]; dy[k] = planes[6 + k]; }
-			}
-			const int32_t columns = it.tx1 - it.tx0 + 1;
-			for (int32_t y = yFirst; y < yLast; y += 2) { // rows come in even-aligned pairs
-				int2 upperRow = edges_row(edges, y), lowerRow = edges_row(edges, y + 1);
-				*(int4 *)&frame.rows[it.rowOffset + (uint32_t)(y - it.t)] = make_int4(upperRow.x, upperRow.y, lowerRow.x, lowerRow.y);
-				if (upperRow.y > upperRow.x && y < height) { minL = min(minL, upperRow.x); maxR = max(maxR, upperRow.y); }
-				if (lowerRow.y > lowerRow.x && y + 1 < height) { minL = min(minL, lowerRow.x); maxR = max(maxR, lowerRow.y); }
-				if (checkpoints && y < height) {
-					chk_walk_row_pair(start, dx, dy, upperRow, lowerRow, y, frame.chk + it.chkOffset + (size_t)((y - it.t) / 2) * (size_t)columns, it.tx0);
+					for (int k = 0; k < 3; k++) { start[k] = planes[k]; dx[k] = planes[3 + k]; dy[k] = planes[6 + k]; }
+				}
+				const int32_t columns = it.tx1 - it.tx0 + 1;
+				for (int32_t y = yFirst; y < yLast; y += 2) { // rows come in even-aligned pairs
+					int2 upperRow = edges_row(edges, y), lowerRow = edges_row(edges, y + 1);
+					*(int4 *)&frame.rows[it.rowOffset + (uint32_t)(y - it.t)] = make_int4(upperRow.x, upperRow.y, lowerRow.x, lowerRow.y);
+					if (upperRow.y > upperRow.x && y < height) { minL = min(minL, upperRow.x); maxR = max(maxR, upperRow.y); }
+					if (lowerRow.y > lowerRow.x && y + 1 < height) { minL = min(minL, lowerRow.x); maxR = max(maxR, lowerRow.y); }
+					if (checkpoints && y < height) {
+						chk_walk_row_pair(start, dx, dy, upperRow, lowerRow, y, frame.chk + it.chkOffset + (size_t)((y - it.t) / 2) * (size_t)columns, it.tx0);
+					}
 				}
 			}
 		}
+		if (SPLIT) {
+			// the loop bound is warp-uniform (first and threadTotal are), so every lane of the warp reaches the shuffles
+			minL = min(minL, __shfl_xor_sync(0xffffffffu, minL, 1));
+			maxR = max(maxR, __shfl_xor_sync(0xffffffffu, maxR, 1));
+			if (!valid || half != 0) { continue; }
+		}
+		if (ty * TILE_H < height) { emit_tile_row(frame, item->tileBase, item->tilesX, ty, minL, maxR, item->cmdIndex); }
 	}
-	if (SPLIT) {
-		minL = min(minL, __shfl_xor_sync(0xffffffffu, minL, 1));
-		maxR = max(maxR, __shfl_xor_sync(0xffffffffu, maxR, 1));
-		if (!valid || half != 0) { return; }
-	}
-	if (ty * TILE_H < height) { emit_tile_row(frame, item->tileBase, item->tilesX, ty, minL, maxR, item->cmdIndex); }
 }
 
 // ref: api/rendererAPI.cpp:242-258 occludeFromExistingTriangles: every solid command queued so far is an occluder for the cells that lie
@@ -989,114 +1017,132 @@ __global__ void __launch_bounds__(SETUP_THREADS) occlude_existing_kernel(FrameDe
 	});
 }
 
-// One CTA: exclusive scans of the per-block command and row totals (submission order is preserved). Every thread owns SCAN_ITEMS
-// consecutive blocks per round, so 2 M tiny triangles (16 k set-up blocks) need two rounds instead of sixteen.
+// The end of the counting pass in ONE launch (three kernels in round 1: a single 1080p frame is bound by launches, not by work):
+//   CTA 0       exclusive scans of the per-block command and row totals (submission order is preserved). Every thread owns SCAN_ITEMS
+//               consecutive blocks per round, so 2 M tiny triangles (16 k set-up blocks) need two rounds instead of sixteen.
+//   other CTAs  every tile takes a segment of the entry pool sized by its counted upper bound. Order between tiles is irrelevant, so
+//               no scan: one atomicAdd per warp.
+//   last CTA to finish: compares the frame's totals with the pools it was launched with (frame.cap*) and publishes totals and verdict
+//               to the host through mapped pinned memory (not through a device-to-host copy: a copy would queue on the copy engine
+//               behind megabytes of finished frames travelling to the host and stall the next chunk's set-up for milliseconds).
 static const int SCAN_ITEMS = 8;
-__global__ void __launch_bounds__(1024) scan_blocks_kernel(FrameDev frame) {
+static const int COUNTS_THREADS = 1024;
+__global__ void __launch_bounds__(COUNTS_THREADS) counts_kernel(FrameDev frame, volatile uint32_t *hostSlot, uint32_t serial) {
 	__shared__ uint32_t warpSum[2][32];
 	__shared__ uint32_t carry[2];
+	__shared__ bool sLast;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	if (threadIdx.x < 2) { carry[threadIdx.x] = 0; }
-	__syncthreads();
-	for (int32_t base = 0; base < frame.blockCount; base += 1024 * SCAN_ITEMS) {
-		const int32_t first = base + (int32_t)threadIdx.x * SCAN_ITEMS;
-		uint32_t v[2][SCAN_ITEMS], total[2] = {0u, 0u};
-		if (first + SCAN_ITEMS <= frame.blockCount) { // 32 consecutive bytes per thread and array: two 16-byte loads, a warp reads 1 KB contiguously
-			const uint4 a0 = *(const uint4 *)(frame.blockCmds + first), a1 = *(const uint4 *)(frame.blockCmds + first + 4);
-			const uint4 b0 = *(const uint4 *)(frame.blockRows + first), b1 = *(const uint4 *)(frame.blockRows + first + 4);
-			v[0][0] = a0.x; v[0][1] = a0.y; v[0][2] = a0.z; v[0][3] = a0.w; v[0][4] = a1.x; v[0][5] = a1.y; v[0][6] = a1.z; v[0][7] = a1.w;
-			v[1][0] = b0.x; v[1][1] = b0.y; v[1][2] = b0.z; v[1][3] = b0.w; v[1][4] = b1.x; v[1][5] = b1.y; v[1][6] = b1.z; v[1][7] = b1.w;
-		} else {
-#pragma unroll
-			for (int e = 0; e < SCAN_ITEMS; e++) {
-				const bool valid = first + e < frame.blockCount;
-				v[0][e] = valid ? frame.blockCmds[first + e] : 0u; v[1][e] = valid ? frame.blockRows[first + e] : 0u;
-			}
-		}
-#pragma unroll
-		for (int e = 0; e < SCAN_ITEMS; e++) { total[0] += v[0][e]; total[1] += v[1][e]; }
-		uint32_t inc[2] = {total[0], total[1]};
-#pragma unroll
-		for (int d = 1; d < 32; d <<= 1) {
-#pragma unroll
-			for (int k = 0; k < 2; k++) {
-				const uint32_t a = __shfl_up_sync(0xffffffffu, inc[k], d);
-				if (lane >= d) { inc[k] += a; }
-			}
-		}
-		if (lane == 31) { for (int k = 0; k < 2; k++) { warpSum[k][warp] = inc[k]; } }
+	if (blockIdx.x == 0) {
+		if (threadIdx.x < 2) { carry[threadIdx.x] = 0; }
 		__syncthreads();
-		if (warp == 0) { // inclusive scan of the 32 warp totals
-			uint32_t w[2] = {warpSum[0][lane], warpSum[1][lane]};
+		for (int32_t base = 0; base < frame.blockCount; base += COUNTS_THREADS * SCAN_ITEMS) {
+			const int32_t first = base + (int32_t)threadIdx.x * SCAN_ITEMS;
+			uint32_t v[2][SCAN_ITEMS], total[2] = {0u, 0u};
+			if (first + SCAN_ITEMS <= frame.blockCount) { // 32 consecutive bytes per thread and array: two 16-byte loads, a warp reads 1 KB contiguously
+				const uint4 a0 = *(const uint4 *)(frame.blockCmds + first), a1 = *(const uint4 *)(frame.blockCmds + first + 4);
+				const uint4 b0 = *(const uint4 *)(frame.blockRows + first), b1 = *(const uint4 *)(frame.blockRows + first + 4);
+				v[0][0] = a0.x; v[0][1] = a0.y; v[0][2] = a0.z; v[0][3] = a0.w; v[0][4] = a1.x; v[0][5] = a1.y; v[0][6] = a1.z; v[0][7] = a1.w;
+				v[1][0] = b0.x; v[1][1] = b0.y; v[1][2] = b0.z; v[1][3] = b0.w; v[1][4] = b1.x; v[1][5] = b1.y; v[1][6] = b1.z; v[1][7] = b1.w;
+			} else {
+#pragma unroll
+				for (int e = 0; e < SCAN_ITEMS; e++) {
+					const bool valid = first + e < frame.blockCount;
+					v[0][e] = valid ? frame.blockCmds[first + e] : 0u; v[1][e] = valid ? frame.blockRows[first + e] : 0u;
+				}
+			}
+#pragma unroll
+			for (int e = 0; e < SCAN_ITEMS; e++) { total[0] += v[0][e]; total[1] += v[1][e]; }
+			uint32_t inc[2] = {total[0], total[1]};
 #pragma unroll
 			for (int d = 1; d < 32; d <<= 1) {
 #pragma unroll
 				for (int k = 0; k < 2; k++) {
-					const uint32_t a = __shfl_up_sync(0xffffffffu, w[k], d);
-					if (lane >= d) { w[k] += a; }
+					const uint32_t a = __shfl_up_sync(0xffffffffu, inc[k], d);
+					if (lane >= d) { inc[k] += a; }
 				}
 			}
-			warpSum[0][lane] = w[0]; warpSum[1][lane] = w[1];
+			if (lane == 31) { for (int k = 0; k < 2; k++) { warpSum[k][warp] = inc[k]; } }
+			__syncthreads();
+			if (warp == 0) { // inclusive scan of the 32 warp totals
+				uint32_t w[2] = {warpSum[0][lane], warpSum[1][lane]};
+#pragma unroll
+				for (int d = 1; d < 32; d <<= 1) {
+#pragma unroll
+					for (int k = 0; k < 2; k++) {
+						const uint32_t a = __shfl_up_sync(0xffffffffu, w[k], d);
+						if (lane >= d) { w[k] += a; }
+					}
+				}
+				warpSum[0][lane] = w[0]; warpSum[1][lane] = w[1];
+			}
+			__syncthreads();
+			uint32_t running[2];
+#pragma unroll
+			for (int k = 0; k < 2; k++) { running[k] = carry[k] + (warp > 0 ? warpSum[k][warp - 1] : 0u) + inc[k] - total[k]; }
+			uint32_t out[2][SCAN_ITEMS];
+#pragma unroll
+			for (int e = 0; e < SCAN_ITEMS; e++) { out[0][e] = running[0]; out[1][e] = running[1]; running[0] += v[0][e]; running[1] += v[1][e]; }
+			if (first + SCAN_ITEMS <= frame.blockCount) {
+				*(uint4 *)(frame.blockCmds + first) = make_uint4(out[0][0], out[0][1], out[0][2], out[0][3]); *(uint4 *)(frame.blockCmds + first + 4) = make_uint4(out[0][4], out[0][5], out[0][6], out[0][7]);
+				*(uint4 *)(frame.blockRows + first) = make_uint4(out[1][0], out[1][1], out[1][2], out[1][3]); *(uint4 *)(frame.blockRows + first + 4) = make_uint4(out[1][4], out[1][5], out[1][6], out[1][7]);
+			} else {
+#pragma unroll
+				for (int e = 0; e < SCAN_ITEMS; e++) { if (first + e < frame.blockCount) { frame.blockCmds[first + e] = out[0][e]; frame.blockRows[first + e] = out[1][e]; } }
+			}
+			__syncthreads();
+			if (threadIdx.x == 0) { for (int k = 0; k < 2; k++) { carry[k] += warpSum[k][31]; } }
+			__syncthreads();
 		}
-		__syncthreads();
-		uint32_t running[2];
-#pragma unroll
-		for (int k = 0; k < 2; k++) { running[k] = carry[k] + (warp > 0 ? warpSum[k][warp - 1] : 0u) + inc[k] - total[k]; }
-		uint32_t out[2][SCAN_ITEMS];
-#pragma unroll
-		for (int e = 0; e < SCAN_ITEMS; e++) { out[0][e] = running[0]; out[1][e] = running[1]; running[0] += v[0][e]; running[1] += v[1][e]; }
-		if (first + SCAN_ITEMS <= frame.blockCount) {
-			*(uint4 *)(frame.blockCmds + first) = make_uint4(out[0][0], out[0][1], out[0][2], out[0][3]); *(uint4 *)(frame.blockCmds + first + 4) = make_uint4(out[0][4], out[0][5], out[0][6], out[0][7]);
-			*(uint4 *)(frame.blockRows + first) = make_uint4(out[1][0], out[1][1], out[1][2], out[1][3]); *(uint4 *)(frame.blockRows + first + 4) = make_uint4(out[1][4], out[1][5], out[1][6], out[1][7]);
-		} else {
-#pragma unroll
-			for (int e = 0; e < SCAN_ITEMS; e++) { if (first + e < frame.blockCount) { frame.blockCmds[first + e] = out[0][e]; frame.blockRows[first + e] = out[1][e]; } }
+		if (threadIdx.x == 0) {
+			frame.totals[0] = carry[0];
+			frame.totals[1] = carry[1];
 		}
-		__syncthreads();
-		if (threadIdx.x == 0) { for (int k = 0; k < 2; k++) { carry[k] += warpSum[k][31]; } }
-		__syncthreads();
+	} else {
+		const uint32_t i = (blockIdx.x - 1u) * COUNTS_THREADS + threadIdx.x;
+		const uint32_t c = i < frame.tileTotal ? frame.tileCount[i] : 0u;
+		uint32_t inc = c, mx = c;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			const uint32_t a = __shfl_up_sync(0xffffffffu, inc, d);
+			if (lane >= d) { inc += a; }
+		}
+#pragma unroll
+		for (int d = 16; d > 0; d >>= 1) { mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d)); }
+		uint32_t base = 0;
+		if (lane == 31 && inc > 0) { base = atomicAdd(&frame.totals[2], inc); }
+		base = __shfl_sync(0xffffffffu, base, 31);
+		if (lane == 0 && mx > 0) { atomicMax(&frame.totals[3], mx); }
+		if (i < frame.tileTotal) {
+			frame.tileOffset[i] = base + inc - c;
+			frame.tileCursor[i] = 0;
+		}
 	}
+	// ---- the last CTA to arrive sees every total
+	__threadfence();
+	__syncthreads();
+	if (threadIdx.x == 0) { sLast = atomicAdd(&frame.totals[TOTAL_TICKET], 1u) == gridDim.x - 1u; }
+	__syncthreads();
+	if (!sLast) { return; }
+	__threadfence();
 	if (threadIdx.x == 0) {
-		frame.totals[0] = carry[0];
-		frame.totals[1] = carry[1];
+		volatile uint32_t *t = frame.totals;
+		const uint32_t commands = t[0], rows = t[1], entries = t[2], maxTile = t[3], chk = t[4], units = t[7];
+		const bool fits = commands <= frame.capCmds && rows <= frame.capRows && entries <= frame.capEntries && chk <= frame.capChk && units <= frame.capUnits
+		                  && (maxTile <= (uint32_t)SORT_SMEM || entries <= frame.capSortTmp);
+		t[TOTAL_OVERFLOW] = fits ? 0u : 1u;
+		hostSlot[0] = commands; hostSlot[1] = rows; hostSlot[2] = entries; hostSlot[3] = maxTile; hostSlot[4] = chk; hostSlot[7] = units;
+		hostSlot[TOTAL_OVERFLOW] = fits ? 0u : 1u;
+		__threadfence_system();
+		hostSlot[TOTAL_TICKET] = serial; // written last: the host reads the slot only after the event behind this kernel anyway
+		__threadfence_system();
 	}
-}
-
-// Every tile takes a segment of the entry pool sized by its counted upper bound. Order between tiles is irrelevant, so no scan:
-// one atomicAdd per warp.
-__global__ void __launch_bounds__(256) tile_alloc_kernel(FrameDev frame) {
-	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-	int lane = threadIdx.x & 31;
-	uint32_t c = i < frame.tileTotal ? frame.tileCount[i] : 0u;
-	uint32_t inc = c, mx = c;
-#pragma unroll
-	for (int d = 1; d < 32; d <<= 1) {
-		uint32_t a = __shfl_up_sync(0xffffffffu, inc, d);
-		if (lane >= d) { inc += a; }
-	}
-#pragma unroll
-	for (int d = 16; d > 0; d >>= 1) { mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d)); }
-	uint32_t base = 0;
-	if (lane == 31 && inc > 0) { base = atomicAdd(&frame.totals[2], inc); }
-	base = __shfl_sync(0xffffffffu, base, 31);
-	if (lane == 0 && mx > 0) { atomicMax(&frame.totals[3], mx); }
-	if (i < frame.tileTotal) {
-		frame.tileOffset[i] = base + inc - c;
-		frame.tileCursor[i] = 0;
-	}
-}
-
-// The frame's counters go to the host through mapped pinned memory written by this kernel, not through a device-to-host copy: a copy
-// would queue on the copy engine behind megabytes of finished frames travelling to the host (dfpsr_session_render_views_host) and
-// stall the next chunk's set-up for milliseconds.
-__global__ void publish_totals_kernel(const uint32_t *__restrict__ totals, volatile uint32_t *hostTotals) {
-	if (threadIdx.x < 8) { hostTotals[threadIdx.x] = totals[threadIdx.x]; }
-	__threadfence_system();
 }
 
 // Restores ascending command order in the lists that hold more than LOCAL_SORT entries (shorter ones are sorted in registers by raster_kernel).
 // Every thread looks at one tile; the long ones are queued in shared memory and sorted by the whole CTA one after the other.
 __global__ void __launch_bounds__(SORT_THREADS) sort_lists_kernel(FrameDev frame) {
+	// launched with every frame whose host side does not wait for the counts: nothing to do unless some tile list is long
+	if (frame_dropped(frame) || frame.totals[3] <= (uint32_t)LOCAL_SORT) { return; }
 	__shared__ uint32_t s[SORT_SMEM];
 	__shared__ uint32_t sQueue[SORT_THREADS];
 	__shared__ uint32_t sQueued;
@@ -1215,8 +1261,10 @@ __device__ __forceinline__ uint32_t sample_bilinear(const TexDev &t, float u, fl
 	left &= maskX; top &= maskY;
 	uint32_t log2Stride = t.log2width - mip;
 	const uint32_t *data = t.data + (t.startOffset & (t.maxLevelMask >> (2u * mip))); // ref: api/textureAPI.h:79-85
-	uint32_t c00 = __ldg(data + ((top << log2Stride) | left)), c10 = __ldg(data + ((top << log2Stride) | right));
-	uint32_t c01 = __ldg(data + ((bottom << log2Stride) | left)), c11 = __ldg(data + ((bottom << log2Stride) | right));
+	// (row << log2Stride) | column == row * stride + column: two row pointers, four loads at 32-bit column offsets
+	const uint32_t *upperRow = data + (top << log2Stride), *lowerRow = data + (bottom << log2Stride);
+	uint32_t c00 = __ldg(upperRow + left), c10 = __ldg(upperRow + right);
+	uint32_t c01 = __ldg(lowerRow + left), c11 = __ldg(lowerRow + right);
 	uint32_t upper = weight_colors(c00, 256u - wx, c10, wx);
 	uint32_t lower = weight_colors(c01, 256u - wx, c11, wx);
 	return weight_colors(upper, 256u - wy, lower, wy);
@@ -1238,6 +1286,14 @@ __device__ __forceinline__ uint32_t mip_level(const TexDev &t, const float *u, c
 // ref: shader/shaderMethods.h:39-44
 __device__ __forceinline__ float interpolate3(const float *d, float wa, float wb, float wc) {
 	return d[0] * wa + d[1] * wb + d[2] * wc;
+}
+
+// __byte_perm selector that moves the bytes (red, green, blue, alpha) of a texel to the positions pack_shifts() describes
+__device__ __forceinline__ uint32_t pack_selector(uint32_t shifts) {
+	uint32_t selector = 0u;
+#pragma unroll
+	for (uint32_t channel = 0; channel < 4; channel++) { selector |= channel << (((shifts >> (8u * channel)) & 31u) >> 1); } // byte position p takes nibble p
+	return selector;
 }
 
 // byte -> float without the conversion pipe: the byte becomes the low mantissa bits of 2^23, then 2^23 is subtracted (exact)
@@ -1464,10 +1520,12 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32, (MODE == TILE_DEFERRED ? (E
 	typedef typename RecOf<EXACT>::type RecT;
 	__shared__ __align__(16) RecT sRecAll[RASTER_WARPS][32];
 	__shared__ uint32_t sKeysAll[RASTER_WARPS][LOCAL_SORT]; // the tile's command list in submission order (lists up to LOCAL_SORT entries)
-	__shared__ __align__(16) uint32_t sMaskAll[RASTER_WARPS][32]; // per (row pair, command): which of the 16 quads of the row pair the command may touch
+	// per (row pair, command): which of the 16 quads of the row pair the command may touch; 16-bit masks, commands c and c + 8 share a word
+	__shared__ __align__(16) uint16_t sMaskAll[RASTER_WARPS][32];
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	RecT *sRec = sRecAll[warp];
-	uint32_t *sMask = sMaskAll[warp];
+	uint16_t *sMask = sMaskAll[warp];
+	if (frame_dropped(frame)) { return; } // the frame did not fit its pools: the host draws it again (see FrameDev::checkCaps)
 
 	// grid = (tile columns of the widest view / RASTER_WARPS, tile rows of the tallest view, views): no division, no search
 	ViewDev vw;
@@ -1694,7 +1752,7 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32, (MODE == TILE_DEFERRED ? (E
 				}
 			}
 			rec.mode = recMode;
-			sMask[r * BATCH + c] = (recMode >= 0 && quadEnd > quadFirst) ? ((0xFFFFFFFFu >> (32 - quadEnd)) & ~((1u << quadFirst) - 1u)) : 0u;
+			sMask[r * BATCH + 2u * (c & 7u) + (c >> 3)] = (uint16_t)((recMode >= 0 && quadEnd > quadFirst) ? ((0xFFFFFFFFu >> (32 - quadEnd)) & ~((1u << quadFirst) - 1u)) : 0u);
 		}
 		__syncwarp();
 		// Every lane collects the commands of the batch that may touch ITS quad and works through them in submission order. Lanes are
@@ -1702,12 +1760,14 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32, (MODE == TILE_DEFERRED ? (E
 		// time instead of idling through each other's commands: the warp needs as many rounds as its busiest quad has commands.
 		uint32_t cover = 0;
 		{
+			static_assert(BATCH == 16, "the coverage masks of commands c and c + 8 share one 32-bit word");
 			const uint4 *masks = (const uint4 *)(sMask + qy * BATCH);
+			const uint4 m0 = masks[0], m1 = masks[1];
+			const uint32_t words[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+			uint32_t both = 0u; // bit k: command k, bit 16 + k: command 8 + k
 #pragma unroll
-			for (int w = 0; w < BATCH / 4; w++) {
-				const uint4 m = masks[w];
-				cover |= ((m.x >> qx) & 1u) << (4 * w) | ((m.y >> qx) & 1u) << (4 * w + 1) | ((m.z >> qx) & 1u) << (4 * w + 2) | ((m.w >> qx) & 1u) << (4 * w + 3);
-			}
+			for (int k = 0; k < 8; k++) { both |= ((words[k] >> qx) & 0x00010001u) << k; }
+			cover = (both & 0xFFu) | ((both >> 8) & 0xFF00u);
 		}
 
 		while (__any_sync(0xffffffffu, cover != 0u)) {
@@ -1950,13 +2010,11 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32, (MODE == TILE_DEFERRED ? (E
 					uint32_t texel[4];
 #pragma unroll
 					for (int l = 0; l < 4; l++) { texel[l] = sample_bilinear(t, u[l], v[l], (mips >> (8 * l)) & 0xFFu); } // pixels nobody won sample (0, 0) and are dropped
+					// byte -> float -> min(x, 255.1) -> truncation (RgbaMultiply.h:75-79, PackOrder.h:186-213) is the identity on 0..255: the
+					// texel's bytes only move to the target's pack order, one byte permute per pixel
+					const uint32_t selector = pack_selector(shifts);
 #pragma unroll
-					for (int l = 0; l < 4; l++) {
-						float r, g, b, a;
-						unpack_bytes(texel[l], r, g, b, a);
-						const uint32_t packed = pack_rgba_ordered(saturated_byte(r), saturated_byte(g), saturated_byte(b), saturated_byte(a), shifts);
-						if (valid[l]) { col[l] = packed; }
-					}
+					for (int l = 0; l < 4; l++) { if (valid[l]) { col[l] = __byte_perm(texel[l], 0u, selector); } }
 				}
 			} else {
 #pragma unroll
@@ -2002,6 +2060,22 @@ static constexpr auto tile_kernel_immediate = raster_kernel<TILE_IMMEDIATE, true
 static constexpr auto tile_kernel_deferred = raster_kernel<TILE_DEFERRED, true>;
 static constexpr auto tile_kernel_tolerance = raster_kernel<TILE_DEFERRED, false>;
 
+// A frame whose second half was launched without waiting for its counts (see renderer_end_internal): everything that is needed to
+// draw it again should the counting pass report that it did not fit the pools.
+struct PendingFrame {
+	bool active = false;
+	uint32_t serial = 0;
+	int slot = 0;
+	cudaStream_t stream = nullptr;
+	std::vector<ViewDev> views;
+	std::vector<TaskParams> tasks;
+	std::vector<TexDev> textures;
+	std::vector<float> grid;
+	bool depthOnly = false, occluded = false, exact = true;
+	int32_t gridWidth = 0, gridHeight = 0, gridAllocW = 0, gridAllocH = 0;
+	int32_t slots = 0;
+};
+
 struct dfpsr_renderer {
 	bool receiving = false;
 	bool depthOnly = false;
@@ -2011,9 +2085,18 @@ struct dfpsr_renderer {
 	size_t uploadCount = 0;
 	std::vector<TexDev> textures;        // the frame's texture table (uploaded behind the task records)
 	bool exact = true;                   // false: tolerance mode (dfpsr_renderer_set_precision)
+	bool async = false;                  // true: renderer_end does not wait for the frame's counts (dfpsr_renderer_set_async)
 	int64_t lastCommands = -1;
 	DeviceBuffer dTasks, dViews, projected, slotCounts, blockCmds, blockRows, tileCount, tileOffset, tileCursor, cmds, rows, tileList, chk, sortTmp, bigItems, bigUnits;
-	uint32_t *hostTotals = nullptr, *hostTotalsDevice = nullptr; // mapped pinned memory and its device alias
+	uint32_t *hostTotals = nullptr, *hostTotalsDevice = nullptr; // mapped pinned memory and its device alias: two slots of 16 words
+	cudaEvent_t counted[2] = {nullptr, nullptr};                 // recorded behind counts_kernel of the frame that uses the slot
+	uint32_t serial = 0;
+	PendingFrame pending;                                        // at most one frame is unverified at any time
+	uint32_t history[TOTAL_WORDS] = {};                          // the totals of the last verified frame, the pools are sized from them
+	int64_t historySlots = 0, historyTiles = 0;                  // 0: no history yet, the next frame waits for its counts
+	uint32_t recentUnits = 0; int64_t recentSlots = 1;           // the last verified frame itself: sizes the grid of big_units_kernel
+	cudaStream_t lastStream = nullptr;
+	bool usedStream = false;
 	void *pinnedTasks = nullptr;                                 // page-locked staging for the task records (a pageable source of a few hundred
 	size_t pinnedTasksCapacity = 0;                              // KB makes cudaMemcpyAsync wait for everything queued on the stream before it)
 	// occlusion grid (ref: api/rendererAPI.cpp:145, :181-192): lives on the host, where occluder boxes and visibility queries are evaluated
@@ -2022,13 +2105,7 @@ struct dfpsr_renderer {
 	bool occluded = false;
 	DeviceBuffer dGrid;
 
-	~dfpsr_renderer() {
-		for (auto &b : uploads) { b.release(); }
-		DeviceBuffer *all[] = {&dTasks, &dViews, &projected, &slotCounts, &blockCmds, &blockRows, &tileCount, &tileOffset, &tileCursor, &cmds, &rows, &tileList, &chk, &sortTmp, &bigItems, &bigUnits, &dGrid};
-		for (auto *b : all) { b->release(); }
-		if (hostTotals) { cudaFreeHost(hostTotals); }
-		if (pinnedTasks) { cudaFreeHost(pinnedTasks); }
-	}
+	~dfpsr_renderer();
 };
 
 static bool image_exists(const dfpsr_image *image) { return image != nullptr && image->data != nullptr; }
@@ -2069,8 +2146,12 @@ static int make_view(ViewDev &v, const dfpsr_image *color, const dfpsr_image *de
 	return 0;
 }
 
+static int verify_frame(dfpsr_renderer *r);
+
 static int renderer_begin_internal(dfpsr_renderer *r, bool depthOnly) {
 	DFPSR_REQUIRE(!r->receiving, "Called renderer_begin on the same renderer twice without ending the previous batch!");
+	// the previous frame is verified before anything of this one is queued: should it have to be drawn again, it still comes first
+	if (verify_frame(r)) { return 1; }
 	r->receiving = true;
 	r->depthOnly = depthOnly;
 	r->occluded = false;
@@ -2079,8 +2160,9 @@ static int renderer_begin_internal(dfpsr_renderer *r, bool depthOnly) {
 	r->uploadCount = 0;
 	r->textures.clear();
 	if (!r->hostTotals) {
-		DFPSR_CHECK_CUDA(cudaHostAlloc((void **)&r->hostTotals, 16 * sizeof(uint32_t), cudaHostAllocMapped));
+		DFPSR_CHECK_CUDA(cudaHostAlloc((void **)&r->hostTotals, 2 * 16 * sizeof(uint32_t), cudaHostAllocMapped));
 		DFPSR_CHECK_CUDA(cudaHostGetDevicePointer((void **)&r->hostTotalsDevice, r->hostTotals, 0));
+		for (int i = 0; i < 2; i++) { DFPSR_CHECK_CUDA(cudaEventCreateWithFlags(&r->counted[i], cudaEventDisableTiming)); }
 	}
 	return 0;
 }
@@ -2135,21 +2217,62 @@ static int launch_projection(dfpsr_renderer *r, const FrameDev &frame, cudaStrea
 		dim3 grid((unsigned)((maxPoints + 255) / 256), (unsigned)r->tasks.size());
 		if (grid.x > 1024u) { grid.x = 1024u; }
 		DFPSR_REQUIRE(r->tasks.size() <= 65535, "more than 65535 tasks in one frame");
-		DFPSR_LAUNCH(project_kernel, grid, 256, 0, stream, frame.tasks);
+		DFPSR_LAUNCH(project_kernel, grid, 256, 0, stream, frame.tasks, (int32_t)r->tasks.size(), (uint4 *)nullptr, 0u);
 	}
 	return 0;
 }
 
 static double host_now_us() { timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec * 1e6 + t.tv_nsec * 1e-3; }
 
-static int renderer_end_internal(dfpsr_renderer *r, cudaStream_t stream) {
+// ---- frames in flight whose counts the host has not looked at yet (asynchronous renderers, at most one frame each)
+namespace dfpsr {
+thread_local int g_pendingFrames = 0;
+thread_local bool g_insideFrame = false;
+}
+static thread_local std::vector<dfpsr_renderer *> g_pendingRenderers;
+
+static void forget_pending(dfpsr_renderer *r) {
+	for (size_t i = 0; i < g_pendingRenderers.size(); i++) {
+		if (g_pendingRenderers[i] == r) { g_pendingRenderers.erase(g_pendingRenderers.begin() + (long)i); g_pendingFrames--; break; }
+	}
+}
+
+dfpsr_renderer::~dfpsr_renderer() {
+	if (pending.active) { cudaEventSynchronize(counted[pending.slot]); forget_pending(this); }
+	for (auto &b : uploads) { b.release(); }
+	DeviceBuffer *all[] = {&dTasks, &dViews, &projected, &slotCounts, &blockCmds, &blockRows, &tileCount, &tileOffset, &tileCursor, &cmds, &rows, &tileList, &chk, &sortTmp, &bigItems, &bigUnits, &dGrid};
+	for (auto *b : all) { b->release(); }
+	if (hostTotals) { cudaFreeHost(hostTotals); }
+	for (cudaEvent_t e : counted) { if (e) { cudaEventDestroy(e); } }
+	if (pinnedTasks) { cudaFreeHost(pinnedTasks); }
+}
+
+struct InsideFrame { // the launches of a frame must not trigger the verification hook of DFPSR_LAUNCH
+	bool previous;
+	InsideFrame() : previous(g_insideFrame) { g_insideFrame = true; }
+	~InsideFrame() { g_insideFrame = previous; }
+};
+
+// Grows the pools of the second half so that `needed` elements fit with `slack` on top. Growing frees the old allocation, which makes
+// the device idle first (cudaFree), so nothing in flight can still be using it.
+static int grow_pool(DeviceBuffer &buffer, size_t needed, size_t elementSize, double slack, size_t extraBytes) {
+	if (needed * elementSize + extraBytes <= buffer.capacity) { return 0; }
+	return buffer.reserve((size_t)((double)needed * slack) * elementSize + extraBytes);
+}
+static uint32_t pool_elements(const DeviceBuffer &buffer, size_t elementSize, size_t extraBytes) {
+	const size_t n = buffer.capacity > extraBytes ? (buffer.capacity - extraBytes) / elementSize : 0;
+	return (uint32_t)std::min<size_t>(n, 0xFFFFFFFFu);
+}
+
+static int run_frame(dfpsr_renderer *r, cudaStream_t stream, bool allowAsync) {
 	// ref: api/rendererAPI.cpp:352-402
-	DFPSR_REQUIRE(r->receiving, "Called renderer_end without renderer_begin!");
+	InsideFrame guard;
 	static const bool timing = getenv("DFPSR_END_TIMING") != nullptr; // developer aid: host-side phase times of one renderer_end on stderr
 	const double tStart = timing ? host_now_us() : 0.0;
 	double tUploaded = 0.0, tLaunched = 0.0, tSynced = 0.0;
-	r->receiving = false;
 	r->lastCommands = 0;
+	// scratch buffers are reused from frame to frame in stream order: a frame on another stream first waits for the previous one
+	if (r->usedStream && r->lastStream != stream) { DFPSR_CHECK_CUDA(cudaStreamSynchronize(r->lastStream)); }
 	// ---- lay out the batch
 	uint32_t tileTotal = 0;
 	bool anyClear = false;
@@ -2159,52 +2282,50 @@ static int renderer_end_internal(dfpsr_renderer *r, cudaStream_t stream) {
 		anyClear = anyClear || (v.clear != 0 && v.width > 0 && v.height > 0);
 	}
 	if (tileTotal == 0 || (r->tasks.empty() && !anyClear)) { return 0; }
+	r->lastStream = stream; r->usedStream = true;
 	int32_t slotTotal = 0, blockTotal = 0;
 	if (layout_tasks(r, slotTotal, blockTotal)) { return 1; }
 	const size_t taskCount = r->tasks.size(), viewCount = r->views.size();
-	if (r->dTasks.reserve(taskCount * sizeof(TaskParams) + 16) || r->dViews.reserve(viewCount * sizeof(ViewDev))) { return 1; }
-	if (r->tileCount.reserve(((size_t)tileTotal + 12) * 4) || r->tileOffset.reserve(((size_t)tileTotal + 1) * 4) || r->tileCursor.reserve(((size_t)tileTotal + 1) * 4)) { return 1; }
+	const size_t counterWords = ((size_t)tileTotal + TOTAL_WORDS + 3) & ~(size_t)3; // tile counts + totals, cleared with 16-byte stores
+	if (r->tileCount.reserve(counterWords * 4) || r->tileOffset.reserve(((size_t)tileTotal + 1) * 4) || r->tileCursor.reserve(((size_t)tileTotal + 1) * 4)) { return 1; }
 	if (r->slotCounts.reserve((size_t)slotTotal * 4 + 16) || r->blockCmds.reserve((size_t)blockTotal * 4 + 16) || r->blockRows.reserve((size_t)blockTotal * 4 + 16)) { return 1; }
-	// pageable sources: cudaMemcpyAsync stages them before returning, so the vectors may change afterwards
-	const int32_t *blockTaskDevice = nullptr;
-	const TexDev *textureTableDevice = nullptr;
-	if (taskCount > 0) {
-		// The records go through page-locked staging: the copy is then a plain DMA in stream order. The staging buffer is free again when this
-		// function returns (the wait for the set-up totals below comes after the copy on the same stream).
-		// behind the records: the frame's texture table, then the task of every set-up block, so that a block of a frame with hundreds of
-		// tasks (the shadow pass of a Sandbox frame) starts with one load instead of a ten-step binary search of dependent loads
-		const size_t taskBytes = (taskCount * sizeof(TaskParams) + 15) & ~(size_t)15; // the texture table is read with 16-byte loads
-		const size_t textureBytes = r->textures.size() * sizeof(TexDev);
-		const size_t tableBytes = taskCount > 1 ? (size_t)blockTotal * sizeof(int32_t) : 0;
-		const size_t bytes = taskBytes + textureBytes + tableBytes;
-		if (r->dTasks.reserve(bytes + 16)) { return 1; }
-		if (bytes > r->pinnedTasksCapacity) {
-			if (r->pinnedTasks) { cudaFreeHost(r->pinnedTasks); r->pinnedTasks = nullptr; r->pinnedTasksCapacity = 0; }
-			const size_t grown = bytes + bytes / 2 + 4096;
-			DFPSR_CHECK_CUDA(cudaHostAlloc(&r->pinnedTasks, grown, cudaHostAllocDefault));
-			r->pinnedTasksCapacity = grown;
-		}
-		memcpy(r->pinnedTasks, r->tasks.data(), taskCount * sizeof(TaskParams));
-		if (textureBytes > 0) { memcpy((uint8_t *)r->pinnedTasks + taskBytes, r->textures.data(), textureBytes); }
+	// ---- one upload: views, task records, the frame's texture table and the task of every set-up block (so that a block of a frame with
+	// hundreds of tasks — the shadow pass of a Sandbox frame — starts with one load instead of a ten-step binary search of dependent
+	// loads). The records go through page-locked staging: the copy is then a plain DMA in stream order. The staging buffer is free again
+	// when the frame's counting pass has run, which the host knows before it lays out the next frame (verify_frame).
+	const size_t viewBytes = viewCount * sizeof(ViewDev);
+	const size_t taskBytes = (taskCount * sizeof(TaskParams) + 15) & ~(size_t)15; // the texture table is read with 16-byte loads
+	const size_t textureBytes = r->textures.size() * sizeof(TexDev);
+	const size_t tableBytes = taskCount > 1 ? (size_t)blockTotal * sizeof(int32_t) : 0;
+	const size_t bytes = viewBytes + taskBytes + textureBytes + tableBytes;
+	if (r->dTasks.reserve(bytes + 16)) { return 1; }
+	if (bytes > r->pinnedTasksCapacity) {
+		if (r->pinnedTasks) { cudaFreeHost(r->pinnedTasks); r->pinnedTasks = nullptr; r->pinnedTasksCapacity = 0; }
+		const size_t grown = bytes + bytes / 2 + 4096;
+		DFPSR_CHECK_CUDA(cudaHostAlloc(&r->pinnedTasks, grown, cudaHostAllocDefault));
+		r->pinnedTasksCapacity = grown;
+	}
+	{
+		uint8_t *staging = (uint8_t *)r->pinnedTasks;
+		memcpy(staging, r->views.data(), viewBytes);
+		if (taskCount > 0) { memcpy(staging + viewBytes, r->tasks.data(), taskCount * sizeof(TaskParams)); }
+		if (textureBytes > 0) { memcpy(staging + viewBytes + taskBytes, r->textures.data(), textureBytes); }
 		if (tableBytes > 0) {
-			int32_t *table = (int32_t *)((uint8_t *)r->pinnedTasks + taskBytes + textureBytes);
+			int32_t *table = (int32_t *)(staging + viewBytes + taskBytes + textureBytes);
 			int32_t index = 0;
 			for (const TaskParams &t : r->tasks) { for (int32_t b = 0; b < t.blockCount; b++) { table[t.blockBase + b] = index; } index++; }
 		}
-		DFPSR_CHECK_CUDA(cudaMemcpyAsync(r->dTasks.ptr, r->pinnedTasks, bytes, cudaMemcpyHostToDevice, stream));
-		textureTableDevice = (const TexDev *)((const uint8_t *)r->dTasks.ptr + taskBytes);
-		blockTaskDevice = tableBytes > 0 ? (const int32_t *)((const uint8_t *)r->dTasks.ptr + taskBytes + textureBytes) : nullptr;
+		DFPSR_CHECK_CUDA(cudaMemcpyAsync(r->dTasks.ptr, staging, bytes, cudaMemcpyHostToDevice, stream));
 	}
-	DFPSR_CHECK_CUDA(cudaMemcpyAsync(r->dViews.ptr, r->views.data(), viewCount * sizeof(ViewDev), cudaMemcpyHostToDevice, stream));
-	DFPSR_CHECK_CUDA(cudaMemsetAsync(r->tileCount.ptr, 0, ((size_t)tileTotal + 12) * 4, stream)); // tile counts, cursors of empty frames, totals
-	if (taskCount == 0) { DFPSR_CHECK_CUDA(cudaMemsetAsync(r->tileCursor.ptr, 0, (size_t)tileTotal * 4, stream)); }
+	const uint8_t *deviceRecords = (const uint8_t *)r->dTasks.ptr;
 	if (timing) { tUploaded = host_now_us(); }
 
 	FrameDev frame;
 	memset(&frame, 0, sizeof(frame));
-	frame.tasks = (const TaskParams *)r->dTasks.ptr;
-	frame.blockTask = blockTaskDevice;
-	frame.textures = textureTableDevice;
+	frame.views = (const ViewDev *)deviceRecords;
+	frame.tasks = (const TaskParams *)(deviceRecords + viewBytes);
+	frame.textures = (const TexDev *)(deviceRecords + viewBytes + taskBytes);
+	frame.blockTask = tableBytes > 0 ? (const int32_t *)(deviceRecords + viewBytes + taskBytes + textureBytes) : nullptr;
 	// Which tile kernel draws the frame: alpha-filtered commands blend in submission order and need the immediate kernel; frames of solid
 	// commands take the deferred one (visibility first, every pixel shaded once), in exact or in tolerance mode.
 	bool anyAlpha = false;
@@ -2213,7 +2334,6 @@ static int renderer_end_internal(dfpsr_renderer *r, cudaStream_t stream) {
 	const bool immediate = anyAlpha || (tileModeOverride && strcmp(tileModeOverride, "immediate") == 0);
 	const bool exactFrame = r->depthOnly || immediate || r->exact;
 	frame.checkpoints = exactFrame ? 1 : 0;
-	frame.views = (const ViewDev *)r->dViews.ptr;
 	frame.taskCount = (int32_t)taskCount; frame.viewCount = (int32_t)viewCount; frame.blockCount = blockTotal;
 	frame.tileTotal = tileTotal;
 	frame.slotCounts = (uint32_t *)r->slotCounts.ptr;
@@ -2227,8 +2347,22 @@ static int renderer_end_internal(dfpsr_renderer *r, cudaStream_t stream) {
 	frame.smallRows = slotTotal <= sm_count() * 1024 ? TILE_H : SMALL_ROWS;
 	if (smallRowsOverride >= 0) { frame.smallRows = smallRowsOverride; }
 
-	if (taskCount > 0) {
-		if (launch_projection(r, frame, stream)) { return 1; }
+	if (taskCount == 0) {
+		// nothing but clears: every tile list is empty
+		DFPSR_CHECK_CUDA(cudaMemsetAsync(r->tileCursor.ptr, 0, (size_t)tileTotal * 4, stream));
+	} else {
+		// ---- counting pass: projection (+ clearing the counters), culling / clipping / bounding boxes, scans and tile segments
+		int32_t maxPoints = 0;
+		for (const TaskParams &t : r->tasks) { if (t.triangles == nullptr && t.pointCount > maxPoints) { maxPoints = t.pointCount; } }
+		{
+			unsigned gx = (unsigned)std::max(1, (maxPoints + 255) / 256);
+			if (gx > 1024u) { gx = 1024u; }
+			const size_t zeroCtas = (counterWords / 4 + 255) / 256;
+			const size_t zeroRows = (zeroCtas + gx - 1) / gx;
+			DFPSR_REQUIRE(taskCount + zeroRows <= 65535, "more than 65535 tasks in one frame");
+			const dim3 grid(gx, (unsigned)(taskCount + zeroRows));
+			DFPSR_LAUNCH(project_kernel, grid, 256, 0, stream, frame.tasks, (int32_t)taskCount, (uint4 *)r->tileCount.ptr, (uint32_t)counterWords);
+		}
 		if (r->occluded) {
 			// completeOcclusion (ref: api/rendererAPI.cpp:193-217) happens inside the set-up kernels, against the grid as it is now
 			if (r->dGrid.reserve(r->grid.size() * sizeof(float) + 16)) { return 1; }
@@ -2236,42 +2370,81 @@ static int renderer_end_internal(dfpsr_renderer *r, cudaStream_t stream) {
 			frame.occlusionGrid = (const float *)r->dGrid.ptr;
 			frame.gridWidth = r->gridWidth; frame.gridHeight = r->gridHeight; frame.gridStride = r->gridAllocW;
 		}
+		// ---- pools of the second half. Without history (first frame, synchronous renderer) the host waits for the counts and sizes the
+		// pools exactly; with history they are grown ahead of the frame (counts of the last verified frame, scaled to this frame's slots
+		// and tiles, doubled) and the frame is launched in one go: the kernels check the pools themselves (FrameDev::checkCaps).
+		const bool async = allowAsync && r->historySlots > 0;
+		if (async) {
+			const double scale = std::max(1.0, (double)slotTotal / (double)r->historySlots) * std::max(1.0, (double)tileTotal / (double)std::max<int64_t>(r->historyTiles, 1));
+			const uint32_t *h = r->history;
+			const size_t wantCmds = (size_t)(h[0] * scale) + 1024, wantRows = (size_t)(h[1] * scale) + 4096, wantEntries = (size_t)(h[2] * scale) + 4096;
+			const size_t wantChk = (size_t)(h[4] * scale) + 1024, wantUnits = (size_t)(h[7] * scale) + 1024;
+			if (grow_pool(r->cmds, wantCmds + wantCmds / 4, sizeof(Cmd), 2.0, 0) || grow_pool(r->rows, wantRows + wantRows / 4, sizeof(int2), 2.0, 16)
+			    || grow_pool(r->tileList, wantEntries + wantEntries / 4, 4, 2.0, 16) || grow_pool(r->chk, wantChk + wantChk / 4, sizeof(ChkRec), 2.0, 16)
+			    || grow_pool(r->bigUnits, wantUnits + wantUnits / 4, 4, 2.0, 0)) { return 1; }
+			if (grow_pool(r->bigItems, pool_elements(r->cmds, sizeof(Cmd), 0), sizeof(BigItem), 1.0, 0)) { return 1; }
+			if (h[3] > (uint32_t)SORT_SMEM / 2 && grow_pool(r->sortTmp, pool_elements(r->tileList, 4, 16), 4, 1.0, 16)) { return 1; }
+		}
+		auto set_pools = [&]() {
+			frame.cmds = (Cmd *)r->cmds.ptr; frame.rows = (int2 *)r->rows.ptr; frame.tileList = (uint32_t *)r->tileList.ptr; frame.chk = (ChkRec *)r->chk.ptr;
+			frame.bigItems = (BigItem *)r->bigItems.ptr; frame.bigUnits = (uint32_t *)r->bigUnits.ptr; frame.sortTmp = (uint32_t *)r->sortTmp.ptr;
+			frame.capCmds = std::min(pool_elements(r->cmds, sizeof(Cmd), 0), pool_elements(r->bigItems, sizeof(BigItem), 0));
+			frame.capRows = pool_elements(r->rows, sizeof(int2), 16); frame.capEntries = pool_elements(r->tileList, 4, 16);
+			frame.capChk = pool_elements(r->chk, sizeof(ChkRec), 16); frame.capUnits = pool_elements(r->bigUnits, 4, 0);
+			frame.capSortTmp = pool_elements(r->sortTmp, 4, 16);
+		};
+		set_pools();
+		frame.checkCaps = async ? 1 : 0;
+		const int slot = (int)(r->serial & 1u);
+		const uint32_t serial = ++r->serial;
+		uint32_t *hostSlot = r->hostTotals + 16 * slot;
 		DFPSR_LAUNCH(setup_kernel<false>, blockTotal, SETUP_THREADS, 0, stream, frame);
-		DFPSR_LAUNCH(scan_blocks_kernel, 1, 1024, 0, stream, frame);
-		DFPSR_LAUNCH(tile_alloc_kernel, (tileTotal + 255) / 256, 256, 0, stream, frame);
-		DFPSR_LAUNCH(publish_totals_kernel, 1, 32, 0, stream, frame.totals, r->hostTotalsDevice);
+		DFPSR_LAUNCH(counts_kernel, 1 + (tileTotal + COUNTS_THREADS - 1) / COUNTS_THREADS, COUNTS_THREADS, 0, stream, frame, r->hostTotalsDevice + 16 * slot, serial);
 		if (timing) { tLaunched = host_now_us(); }
-		DFPSR_CHECK_CUDA(cudaStreamSynchronize(stream));
-		if (timing) { tSynced = host_now_us(); }
-		const uint32_t commandTotal = r->hostTotals[0], rowTotal = r->hostTotals[1], entryTotal = r->hostTotals[2], maxTile = r->hostTotals[3];
-		r->lastCommands = commandTotal;
-		if (commandTotal > 0) {
-			if (r->cmds.reserve((size_t)commandTotal * sizeof(Cmd))) { return 1; }
-			if (r->rows.reserve((size_t)rowTotal * sizeof(int2) + 16)) { return 1; }
-			if (r->tileList.reserve((size_t)entryTotal * 4 + 16)) { return 1; }
-			if (r->chk.reserve((size_t)r->hostTotals[4] * sizeof(ChkRec) + 16)) { return 1; }
-			frame.chk = (ChkRec *)r->chk.ptr;
-			frame.cmds = (Cmd *)r->cmds.ptr;
-			frame.rows = (int2 *)r->rows.ptr;
-			frame.tileList = (uint32_t *)r->tileList.ptr;
-			const uint32_t unitTotal = r->hostTotals[7];
-			if (unitTotal > 0) {
-				if (r->bigItems.reserve((size_t)commandTotal * sizeof(BigItem)) || r->bigUnits.reserve((size_t)unitTotal * 4)) { return 1; }
-				frame.bigItems = (BigItem *)r->bigItems.ptr; frame.bigUnits = (uint32_t *)r->bigUnits.ptr;
+		uint32_t unitEstimate, maxTileEstimate;
+		bool secondHalf = true;
+		if (!async) {
+			DFPSR_CHECK_CUDA(cudaStreamSynchronize(stream));
+			if (timing) { tSynced = host_now_us(); }
+			DFPSR_REQUIRE(hostSlot[TOTAL_TICKET] == serial, "renderer_end: the counting pass did not report (slot holds frame %u, expected %u)", hostSlot[TOTAL_TICKET], serial);
+			const uint32_t commandTotal = hostSlot[0], rowTotal = hostSlot[1], entryTotal = hostSlot[2], maxTile = hostSlot[3];
+			r->lastCommands = commandTotal;
+			for (int i = 0; i < TOTAL_WORDS; i++) { r->history[i] = hostSlot[i]; }
+			r->historySlots = std::max(slotTotal, 1); r->historyTiles = tileTotal;
+			r->recentUnits = hostSlot[7]; r->recentSlots = std::max(slotTotal, 1);
+			secondHalf = commandTotal > 0;
+			unitEstimate = hostSlot[7]; maxTileEstimate = maxTile;
+			if (secondHalf) {
+				// an asynchronous renderer gets head room at once, so that the next frames fit without another wait
+				const double slack = allowAsync ? 1.5 : 1.0;
+				if (grow_pool(r->cmds, commandTotal, sizeof(Cmd), slack, 0) || grow_pool(r->rows, rowTotal, sizeof(int2), slack, 16)
+				    || grow_pool(r->tileList, entryTotal, 4, slack, 16) || grow_pool(r->chk, hostSlot[4], sizeof(ChkRec), slack, 16)) { return 1; }
+				if (unitEstimate > 0 && (grow_pool(r->bigItems, pool_elements(r->cmds, sizeof(Cmd), 0), sizeof(BigItem), 1.0, 0) || grow_pool(r->bigUnits, unitEstimate, 4, slack, 0))) { return 1; }
+				if (maxTile > (uint32_t)SORT_SMEM && grow_pool(r->sortTmp, pool_elements(r->tileList, 4, 16), 4, 1.0, 16)) { return 1; }
+				set_pools();
 			}
+		} else {
+			DFPSR_CHECK_CUDA(cudaEventRecord(r->counted[slot], stream));
+			PendingFrame &p = r->pending;
+			p.active = true; p.serial = serial; p.slot = slot; p.stream = stream;
+			p.views = r->views; p.tasks = r->tasks; p.textures = r->textures;
+			p.depthOnly = r->depthOnly; p.occluded = r->occluded; p.exact = r->exact;
+			if (r->occluded) { p.grid = r->grid; p.gridWidth = r->gridWidth; p.gridHeight = r->gridHeight; p.gridAllocW = r->gridAllocW; p.gridAllocH = r->gridAllocH; }
+			g_pendingRenderers.push_back(r); g_pendingFrames++;
+			// the grid of the unit kernel follows the most recent frame (scaled to this frame's slots), not the largest one seen
+			unitEstimate = (uint32_t)std::min(4.0e9, (double)r->recentUnits * ((double)slotTotal / (double)r->recentSlots) * 1.25) + 1u; maxTileEstimate = 0xFFFFFFFFu;
+			p.slots = slotTotal;
+		}
+		if (secondHalf) {
 			DFPSR_LAUNCH(setup_kernel<true>, blockTotal, SETUP_THREADS, 0, stream, frame);
-			if (unitTotal > 0) {
-				// frames with few units (a single 1080p frame: 15 k) are latency-bound: two threads per unit; large batches keep one
-				if (unitTotal <= (uint32_t)sm_count() * 2048u) { DFPSR_LAUNCH(big_units_kernel<true>, (2u * unitTotal + 255u) / 256u, 256, 0, stream, frame, unitTotal); }
-				else { DFPSR_LAUNCH(big_units_kernel<false>, (unitTotal + 255) / 256, 256, 0, stream, frame, unitTotal); }
+			if (unitEstimate > 0 || async) {
+				// frames with few units (a single 1080p frame: 15 k) are latency-bound: two threads per unit; large batches keep one.
+				// The kernels stride over the units the device counted, so an estimate only sizes the grid.
+				const uint32_t most = (uint32_t)sm_count() * 64u;
+				if (unitEstimate <= (uint32_t)sm_count() * 2048u) { DFPSR_LAUNCH(big_units_kernel<true>, std::min(most, (2u * unitEstimate + 255u) / 256u), 256, 0, stream, frame); }
+				else { DFPSR_LAUNCH(big_units_kernel<false>, std::min(most * 4u, (unitEstimate + 255u) / 256u), 256, 0, stream, frame); }
 			}
-			if (maxTile > (uint32_t)LOCAL_SORT) {
-				if (maxTile > (uint32_t)SORT_SMEM) {
-					if (r->sortTmp.reserve((size_t)entryTotal * 4 + 16)) { return 1; }
-					frame.sortTmp = (uint32_t *)r->sortTmp.ptr;
-				}
-				DFPSR_LAUNCH(sort_lists_kernel, (tileTotal + SORT_THREADS - 1) / SORT_THREADS, SORT_THREADS, 0, stream, frame);
-			}
+			if (maxTileEstimate > (uint32_t)LOCAL_SORT) { DFPSR_LAUNCH(sort_lists_kernel, (tileTotal + SORT_THREADS - 1) / SORT_THREADS, SORT_THREADS, 0, stream, frame); }
 		}
 	}
 	// grid = (tile columns of the widest view / warps per CTA, tile rows of the tallest view, views)
@@ -2285,9 +2458,61 @@ static int renderer_end_internal(dfpsr_renderer *r, cudaStream_t stream) {
 	else { DFPSR_LAUNCH(tile_kernel_tolerance, grid, RASTER_WARPS * 32, 0, stream, frame); }
 	if (timing) {
 		fprintf(stderr, "renderer_end: %zu tasks, %zu views | layout+upload %.0f us, first launches %.0f us, wait for totals %.0f us, second launches %.0f us\n",
-		        taskCount, viewCount, tUploaded - tStart, tLaunched - tUploaded, tSynced - tLaunched, host_now_us() - tSynced);
+		        taskCount, viewCount, tUploaded - tStart, tLaunched - tUploaded, tSynced > 0.0 ? tSynced - tLaunched : 0.0, host_now_us() - (tSynced > 0.0 ? tSynced : tLaunched));
 	}
 	return 0;
+}
+
+// Looks at the counts of the renderer's frame in flight (waiting for its counting pass if it has not run yet). A frame that did not fit
+// its pools drew nothing: it is drawn again here, through the path that waits for the counts, before anything else is queued.
+static int verify_frame(dfpsr_renderer *r) {
+	PendingFrame &p = r->pending;
+	if (!p.active) { return 0; }
+	DFPSR_CHECK_CUDA(cudaEventSynchronize(r->counted[p.slot]));
+	p.active = false;
+	forget_pending(r);
+	const uint32_t *hostSlot = r->hostTotals + 16 * p.slot;
+	DFPSR_REQUIRE(hostSlot[TOTAL_TICKET] == p.serial, "renderer: the counting pass of frame %u did not report (slot holds frame %u)", p.serial, hostSlot[TOTAL_TICKET]);
+	r->lastCommands = hostSlot[0];
+	if (hostSlot[TOTAL_OVERFLOW] == 0u) {
+		// the pools follow the largest frame seen: a shrinking scene keeps its head room
+		for (int i = 0; i < TOTAL_WORDS; i++) { r->history[i] = std::max(r->history[i], hostSlot[i]); }
+		r->recentUnits = hostSlot[7]; r->recentSlots = std::max(p.slots, 1);
+		return 0;
+	}
+	// ---- the frame was dropped on the device: nothing of it (or behind it) may still be running while its inputs are laid out again
+	DFPSR_CHECK_CUDA(cudaStreamSynchronize(p.stream));
+	std::swap(r->views, p.views); std::swap(r->tasks, p.tasks); std::swap(r->textures, p.textures);
+	std::swap(r->depthOnly, p.depthOnly); std::swap(r->occluded, p.occluded); std::swap(r->exact, p.exact);
+	if (r->occluded) { std::swap(r->grid, p.grid); std::swap(r->gridWidth, p.gridWidth); std::swap(r->gridHeight, p.gridHeight); std::swap(r->gridAllocW, p.gridAllocW); std::swap(r->gridAllocH, p.gridAllocH); }
+	const bool occludedFrame = r->occluded;
+	const int status = run_frame(r, p.stream, false);
+	if (occludedFrame) { std::swap(r->grid, p.grid); std::swap(r->gridWidth, p.gridWidth); std::swap(r->gridHeight, p.gridHeight); std::swap(r->gridAllocW, p.gridAllocW); std::swap(r->gridAllocH, p.gridAllocH); }
+	std::swap(r->views, p.views); std::swap(r->tasks, p.tasks); std::swap(r->textures, p.textures);
+	std::swap(r->depthOnly, p.depthOnly); std::swap(r->occluded, p.occluded); std::swap(r->exact, p.exact);
+	r->historySlots = std::max<int64_t>(r->historySlots, 1); // run_frame refreshed the history from the redrawn frame
+	static const bool verbose = getenv("DFPSR_END_TIMING") != nullptr;
+	if (verbose) { fprintf(stderr, "renderer: frame %u did not fit its pools and was drawn again\n", p.serial); }
+	return status;
+}
+
+namespace dfpsr {
+// DFPSR_LAUNCH and the copy helpers call this before they queue anything while frames are unverified: whatever consumes a frame through
+// this library is queued behind the frame's (possible) second drawing.
+int verify_pending_frames() {
+	if (g_insideFrame) { return 0; }
+	while (!g_pendingRenderers.empty()) {
+		if (verify_frame(g_pendingRenderers.back())) { return 1; }
+	}
+	return 0;
+}
+}
+
+static int renderer_end_internal(dfpsr_renderer *r, cudaStream_t stream) {
+	DFPSR_REQUIRE(r->receiving, "Called renderer_end without renderer_begin!");
+	r->receiving = false;
+	if (verify_frame(r)) { return 1; }
+	return run_frame(r, stream, r->async);
 }
 
 extern "C" {
@@ -2295,6 +2520,9 @@ extern "C" {
 // DFPSR_PRECISION=tolerance in the environment changes the initial default (A/B runs of the test-suite and the bench)
 static bool initial_precision_exact() { const char *e = getenv("DFPSR_PRECISION"); return !(e && strcmp(e, "tolerance") == 0); }
 static thread_local bool g_defaultExact = initial_precision_exact();
+// DFPSR_ASYNC=1 in the environment: renderers do not wait for their frames' counts (dfpsr_set_default_async)
+static bool initial_async() { const char *e = getenv("DFPSR_ASYNC"); return e && atoi(e) != 0; }
+static thread_local bool g_defaultAsync = initial_async();
 static thread_local dfpsr_renderer *g_immediate = nullptr;
 
 int dfpsr_renderer_create(dfpsr_renderer **out) {
@@ -2304,8 +2532,29 @@ int dfpsr_renderer_create(dfpsr_renderer **out) {
 	*out = new (std::nothrow) dfpsr_renderer();
 	DFPSR_REQUIRE(*out != nullptr, "out of host memory");
 	(*out)->exact = g_defaultExact;
+	(*out)->async = g_defaultAsync;
 	return 0;
 }
+
+int dfpsr_renderer_set_async(dfpsr_renderer *renderer, int32_t enabled) {
+	DFPSR_REQUIRE(renderer != nullptr, "renderer_set_async: renderer does not exist");
+	if (!enabled && verify_frame(renderer)) { return 1; }
+	renderer->async = enabled != 0;
+	return 0;
+}
+
+int dfpsr_set_default_async(int32_t enabled) {
+	g_defaultAsync = enabled != 0;
+	if (g_immediate != nullptr) { return dfpsr_renderer_set_async(g_immediate, enabled); }
+	return 0;
+}
+
+int dfpsr_renderer_flush(dfpsr_renderer *renderer) {
+	DFPSR_REQUIRE(renderer != nullptr, "renderer_flush: renderer does not exist");
+	return verify_frame(renderer);
+}
+
+int dfpsr_flush(void) { return dfpsr::verify_pending_frames(); }
 
 int dfpsr_renderer_set_precision(dfpsr_renderer *renderer, int32_t precision) {
 	DFPSR_REQUIRE(renderer != nullptr, "renderer_set_precision: renderer does not exist");
@@ -2573,6 +2822,7 @@ int dfpsr_renderer_end(dfpsr_renderer *renderer, void *stream) {
 int dfpsr_renderer_last_command_count(dfpsr_renderer *renderer, int64_t *count, void *stream) {
 	DFPSR_REQUIRE(renderer != nullptr && count != nullptr, "renderer_last_command_count: null argument");
 	(void)stream;
+	if (verify_frame(renderer)) { return 1; }
 	*count = renderer->lastCommands;
 	return 0;
 }

@@ -110,6 +110,7 @@ int dfpsr_session_render_frame_host(dfpsr_session *session, int32_t slot, const 
 	if (dfpsr_renderer_begin_cleared(session->renderer, &color, &depth, 0u, 0.0f)) { return 1; }
 	if (dfpsr_renderer_give_task(session->renderer, &m->device, modelToWorld, camera, stream)) { return 1; }
 	if (dfpsr_renderer_end(session->renderer, stream)) { return 1; }
+	if (verify_pending_frames()) { return 1; } // an asynchronous renderer: the copies below must see the frame's final pixels
 	if (colorHost != nullptr) { DFPSR_CHECK_CUDA(cudaMemcpy2DAsync(colorHost, (size_t)colorStride, color.data, (size_t)pitch, (size_t)width * 4, (size_t)height, cudaMemcpyDeviceToHost, s)); }
 	if (depthHost != nullptr) { DFPSR_CHECK_CUDA(cudaMemcpy2DAsync(depthHost, (size_t)depthStride, depth.data, (size_t)pitch, (size_t)width * 4, (size_t)height, cudaMemcpyDeviceToHost, s)); }
 	DFPSR_CHECK_CUDA(cudaStreamSynchronize(s));
@@ -155,7 +156,11 @@ int dfpsr_session_render_views_host(dfpsr_session *session, int32_t slot, const 
 			colors[(size_t)v] = dfpsr_image{(uint8_t *)session->chunkColor[b].ptr + frameBytes * v, width, height, pitch, packOrder};
 			depths[(size_t)v] = dfpsr_image{(uint8_t *)session->chunkDepth[b].ptr + frameBytes * v, width, height, pitch, 0};
 		}
-		if (dfpsr_model_render_views(&m->device, modelToWorld, colors.data(), depths.data(), cameras + first, n, 1, stream)) { return 1; }
+		// on an error the copies of earlier chunks are still in flight towards the caller's buffers: wait for them before returning
+		if (dfpsr_model_render_views(&m->device, modelToWorld, colors.data(), depths.data(), cameras + first, n, 1, stream) || verify_pending_frames()) {
+			cudaStreamSynchronize(session->copyStream); cudaStreamSynchronize(s);
+			return 1;
+		}
 		DFPSR_CHECK_CUDA(cudaEventRecord(session->rendered[b], s));
 		DFPSR_CHECK_CUDA(cudaStreamWaitEvent(session->copyStream, session->rendered[b], 0));
 		for (int32_t v = 0; v < n; v++) {

@@ -44,6 +44,10 @@ SIGNATURES = {
     "dfpsr_texture_from_image": (i32, [P(abi.Texture), P(abi.Image), vp]),
     "dfpsr_renderer_create": (i32, [P(vp)]),
     "dfpsr_renderer_destroy": (i32, [vp]),
+    "dfpsr_renderer_set_async": (i32, [vp, i32]),
+    "dfpsr_set_default_async": (i32, [i32]),
+    "dfpsr_renderer_flush": (i32, [vp]),
+    "dfpsr_flush": (i32, []),
     "dfpsr_renderer_set_precision": (i32, [vp, i32]),
     "dfpsr_set_default_precision": (i32, [i32]),
     "dfpsr_renderer_begin": (i32, [vp, P(abi.Image), P(abi.Image)]),
@@ -135,6 +139,7 @@ SIGNATURES = {
     "dfpsr_peer_close": (i32, [vp]),
     "dfpsr_peer_signal": (i32, [P(vp), i32, u32, vp]),
     "dfpsr_peer_wait": (i32, [vp, i32, u32, u32, vp, vp]),
+    "dfpsr_peer_reset_status": (i32, [vp, vp]),
 }
 
 

@@ -89,6 +89,9 @@ class CudaPeerTransport:
     def wait(self, flags_ptr, count, value, status_ptr):
         self.lib.check(self.cuda.dfpsr_peer_wait(self.C.c_void_p(flags_ptr), count, value, self.timeout_ms, self.C.c_void_p(status_ptr), self.lib.stream_ptr()))
 
+    def reset_status(self, status_ptr):
+        self.lib.check(self.cuda.dfpsr_peer_reset_status(self.C.c_void_p(status_ptr), self.lib.stream_ptr()))
+
     def read_u32(self, ptr):
         C = self.C
         out = C.c_uint32()
@@ -119,7 +122,7 @@ class PeerStripFrame:
         self.is_presenter = rank == presenter
         self.mapped, self.owned = [], []
         mine = {}
-        # own block: [0] consumed flag, [64] wait status
+        # own block: [0] consumed flag, [64] status of the begin_frame wait, [128] status of the end_frame wait (one block per wait site)
         self.local_ptr, mine["consumed"] = transport.alloc(self.FLAG_BYTES)
         self.owned.append(self.local_ptr)
         if self.is_presenter:
@@ -143,6 +146,7 @@ class PeerStripFrame:
             self.done_ptr = transport.open(everyone[presenter]["done"])
             self.mapped += [self.color_ptr, self.done_ptr]
         self.status_ptr = self.local_ptr + 64
+        self.end_status_ptr = self.local_ptr + 128
 
     @property
     def rows(self):
@@ -155,15 +159,21 @@ class PeerStripFrame:
     def end_frame(self, k):
         self.t.signal([self.done_ptr + 4 * self.rank], k)
         if self.is_presenter:
-            self.t.wait(self.done_ptr, self.world, k, self.status_ptr)
+            self.t.wait(self.done_ptr, self.world, k, self.end_status_ptr)
 
     def release_frame(self, k):
         if self.is_presenter and self.consumed_ptrs:
             self.t.signal(self.consumed_ptrs, k)
 
     def timed_out(self):
-        """True when one of this rank's waits gave up (a peer never signalled). Synchronises the stream."""
-        return self.t.read_u32(self.status_ptr) != 0
+        """Number of this rank's waits that gave up since the last reset (a peer never signalled): the frames since then may be torn —
+        the caller should stop presenting them and resynchronise (barrier + reset_status). Synchronises the stream."""
+        return self.t.read_u32(self.status_ptr) + self.t.read_u32(self.end_status_ptr)
+
+    def reset_status(self):
+        if hasattr(self.t, "reset_status"):
+            self.t.reset_status(self.status_ptr)
+            self.t.reset_status(self.end_status_ptr)
 
     def close(self):
         if self.world > 1:

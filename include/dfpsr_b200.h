@@ -200,6 +200,20 @@ int dfpsr_renderer_destroy(dfpsr_renderer *renderer);
 enum { DFPSR_PRECISION_EXACT = 0, DFPSR_PRECISION_TOLERANCE = 1 };
 int dfpsr_renderer_set_precision(dfpsr_renderer *renderer, int32_t precision);
 int dfpsr_set_default_precision(int32_t precision);
+/* Asynchronous frames (no counterpart in the reference, whose renderer_end blocks until the pixels are drawn).
+ * By default dfpsr_renderer_end waits once, in the middle of the frame, for the counts of its set-up pass (commands, rows, tile list
+ * entries) and sizes its device pools exactly. An asynchronous renderer launches the whole frame without waiting: the pools are sized
+ * from the frames it has drawn before (its first frame still waits) and the kernels check them on the device. A frame that does not fit
+ * draws NOTHING; the library notices when it next looks at the renderer — dfpsr_renderer_begin / _end / _flush / _destroy, and before
+ * every kernel launch, upload, download or dfpsr_stream_synchronize this thread makes through this library — grows the pools and draws
+ * the frame again before queueing anything else, so that every consumer that goes through this library sees finished pixels in stream
+ * order. Work queued on the stream by other means (the caller's own cudaMemcpyAsync, other libraries) must call dfpsr_renderer_flush
+ * (or dfpsr_flush) first. The model, texture and (for give_task_triangles) internal copies a frame reads must stay unchanged until then.
+ * dfpsr_set_default_async applies to renderers created afterwards and to the calling thread's model_render* calls. */
+int dfpsr_renderer_set_async(dfpsr_renderer *renderer, int32_t enabled);
+int dfpsr_set_default_async(int32_t enabled);
+int dfpsr_renderer_flush(dfpsr_renderer *renderer);
+int dfpsr_flush(void);
 /* ref: api/rendererAPI.h:66 renderer_begin. Either image may have data == NULL. Calling begin twice
  * without end is an error (ref: api/rendererAPI.cpp:152-154). */
 int dfpsr_renderer_begin(dfpsr_renderer *renderer, const dfpsr_image *color, const dfpsr_image *depth);
@@ -222,13 +236,16 @@ int dfpsr_renderer_occlude_from_existing_triangles(dfpsr_renderer *renderer, voi
 int dfpsr_renderer_has_occluders(const dfpsr_renderer *renderer);
 int dfpsr_renderer_is_box_visible(const dfpsr_renderer *renderer, const float minBound[3], const float maxBound[3], const dfpsr_transform3d *modelToWorld, const dfpsr_camera *camera, int32_t *visible);
 /* ref: api/modelAPI.cpp:214-281 model_render_threaded / renderer_giveTask. Bound culling
- * (Camera::isBoxSeen) is applied on the host exactly like the reference. Enqueues the projection and
- * triangle set-up kernels on `stream`; nothing is drawn before dfpsr_renderer_end. */
+ * (Camera::isBoxSeen) is applied on the host exactly like the reference. The task records the model's DEVICE pointers (points,
+ * polygons, textures); projection, set-up and drawing all run at dfpsr_renderer_end, so those buffers must stay alive and unchanged
+ * until the frame has been drawn (the reference copies the vertex data at submission; dsr_b200.h keeps the buffers alive for its
+ * callers). A frame may use up to 4096 textures. */
 int dfpsr_renderer_give_task(dfpsr_renderer *renderer, const dfpsr_model *model, const dfpsr_transform3d *modelToWorld, const dfpsr_camera *camera, void *stream);
 /* ref: api/rendererAPI.h:108-116 renderer_giveTask_triangle, batched: `triangles` is a HOST array. */
 int dfpsr_renderer_give_task_triangles(dfpsr_renderer *renderer, const dfpsr_triangle *triangles, int32_t count, const dfpsr_texture *diffuse, const dfpsr_texture *light, int32_t filter, const dfpsr_camera *camera, void *stream);
 /* ref: api/rendererAPI.h:131 renderer_end → CommandQueue::execute (implementation/render/renderCore.cpp:449-480):
- * bins the queued triangles to screen tiles and rasterises/shades every tile in submission order. */
+ * bins the queued triangles to screen tiles and rasterises/shades every tile in submission order. Everything is queued on `stream`;
+ * the call waits for the stream once (for the set-up counts) unless the renderer is asynchronous (dfpsr_renderer_set_async). */
 int dfpsr_renderer_end(dfpsr_renderer *renderer, void *stream);
 /* Number of draw commands (post-clipping triangles) the last frame produced; synchronises `stream`. */
 int dfpsr_renderer_last_command_count(dfpsr_renderer *renderer, int64_t *count, void *stream);
@@ -554,9 +571,12 @@ int dfpsr_peer_open(void **devicePtr, const uint8_t *handle);
 int dfpsr_peer_close(void *devicePtr);
 /* After everything queued on `stream` so far (peer stores included) is visible system-wide, stores `value` to each of the `count` flags. */
 int dfpsr_peer_signal(uint32_t *const *flags, int32_t count, uint32_t value, void *stream);
-/* Blocks `stream` (not the host) until flags[0..count) have all reached `value` (wrap-safe >=). Gives up after timeoutMs (1..10000) and
- * stores 1 to *status (device memory, caller-zeroed) instead of hanging the device. */
+/* Blocks `stream` (not the host) until flags[0..count) have all reached `value` (wrap-safe >=). Gives up after timeoutMs (1..10000)
+ * instead of hanging the device: status (two u32 of device memory, zero at first; give every wait site its own) then counts the wait in
+ * status[0] and keeps the value it was waiting for in status[1]. A caller that finds status[0] != 0 must treat the frames since its
+ * last check as torn and resynchronise with its peers; dfpsr_peer_reset_status clears the block (stream-ordered). */
 int dfpsr_peer_wait(const uint32_t *flags, int32_t count, uint32_t value, uint32_t timeoutMs, uint32_t *status, void *stream);
+int dfpsr_peer_reset_status(uint32_t *status, void *stream);
 
 #ifdef __cplusplus
 }

@@ -14,18 +14,10 @@ import torch.distributed as dist
 from dfpsr_b200 import abi, lib, scenes, shard
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--scene", default="tiny", choices=["terrain", "tiny"])
-    ap.add_argument("--iters", type=int, default=20)
-    args = ap.parse_args()
-    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
-    torch.cuda.set_device(local)
-    cuda = lib.load()
-    lib.check(cuda.dfpsr_init(local))
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    if args.scene == "terrain":
+def run(cuda, scene, iters, rank, world):
+    """One frame in row strips across the `world` ranks of the initialised process group; every rank must call this. Returns the result
+    dict on rank 0 (None elsewhere). Raises if the assembled frame differs from the full-frame render of rank 0's own GPU."""
+    if scene == "terrain":
         w, h = 1920, 1080
         sc = scenes.terrain_scene()
         tex = lib.DeviceTexture(sc["texture"], 5)
@@ -51,6 +43,7 @@ def main():
         lib.check(cuda.dfpsr_renderer_give_task(r, C.byref(model.desc), C.byref(ident), C.byref(cam), sp))
         lib.check(cuda.dfpsr_renderer_end(r, sp))
         if strip and world > 1:
+            lib.check(cuda.dfpsr_renderer_flush(r))  # the all_gather is not queued through the library
             shard.gather_strips(color, bounds)
 
     psf = shard.PeerStripFrame(shard.CudaPeerTransport(cuda), h, w, rank, world) if world > 1 else None
@@ -75,35 +68,58 @@ def main():
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        for _ in range(args.iters):
+        for _ in range(iters):
             frame(strip)
         b.record()
         torch.cuda.synchronize()
-        ms = torch.tensor([a.elapsed_time(b) / args.iters], dtype=torch.float64, device="cuda")
+        ms = torch.tensor([a.elapsed_time(b) / iters], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
     ms_strip = timed(True)
+    lib.check(cuda.dfpsr_renderer_flush(r))
     gathered = color.clone()
-    ms_peer, peer_frame_copy, peer_timed_out = None, None, False
+    ms_peer, peer_frame_copy, peer_timed_out = None, None, 0
     if psf is not None:
         ms_peer = timed(True, peer_frame)
+        lib.check(cuda.dfpsr_renderer_flush(r))
         peer_timed_out = psf.timed_out()
         if rank == 0:
             peer_frame_copy = lib.tensor_from_ptr(psf.color_ptr, (h, w)).clone()
     ms_full = timed(False)
+    lib.check(cuda.dfpsr_renderer_flush(r))
+    torch.cuda.synchronize()
     same = bool(torch.equal(gathered, color))
     peer_same = bool(torch.equal(peer_frame_copy, color)) if peer_frame_copy is not None else None
+    result = None
     if rank == 0:
-        print(json.dumps({"scene": args.scene, "n_gpus": world, "width": w, "height": h, "strip_frame_ms": ms_strip, "single_gpu_frame_ms": ms_full,
-                          "speedup": ms_full / ms_strip, "gathered_equals_full_frame": same, "gather_bytes_per_rank": (bounds[rank][1] - bounds[rank][0]) * w * 4,
-                          "peer_strip_frame_ms": ms_peer, "peer_speedup": (ms_full / ms_peer) if ms_peer else None, "peer_equals_full_frame": peer_same,
-                          "peer_wait_timed_out": peer_timed_out}))
+        result = {"scene": scene, "n_gpus": world, "width": w, "height": h, "strip_frame_ms": ms_strip, "single_gpu_frame_ms": ms_full,
+                  "speedup": ms_full / ms_strip, "gathered_equals_full_frame": same, "gather_bytes_per_rank": (bounds[rank][1] - bounds[rank][0]) * w * 4,
+                  "peer_strip_frame_ms": ms_peer, "peer_speedup": (ms_full / ms_peer) if ms_peer else None, "peer_equals_full_frame": peer_same,
+                  "peer_waits_timed_out": peer_timed_out}
     if psf is not None:
         psf.close()
+    lib.check(cuda.dfpsr_renderer_destroy(r))
     assert same, "strip-sharded frame differs from the full-frame render"
     assert peer_same is not False and not peer_timed_out, "peer-store strip frame differs from the full-frame render (or a wait timed out)"
+    return result
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--scene", default="tiny", choices=["terrain", "tiny"])
+    ap.add_argument("--iters", type=int, default=20)
+    args = ap.parse_args()
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    cuda = lib.load()
+    lib.check(cuda.dfpsr_init(local))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    result = run(cuda, args.scene, args.iters, rank, world)
+    if rank == 0:
+        print(json.dumps(result))
     if world > 1:
         dist.destroy_process_group()
 

@@ -3,6 +3,7 @@
 #include "common.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 #include <float.h>
 #include <stdarg.h>
 #include <vector>
@@ -28,6 +29,9 @@ int check_launch(const char *name) {
 	}
 	return 0;
 }
+
+static bool initial_chain_launches() { const char *e = getenv("DFPSR_CHAIN"); return !(e && atoi(e) == 0); }
+bool g_chainLaunches = initial_chain_launches();
 
 // ---- per-kernel profiling
 bool g_profile = false;

@@ -850,27 +850,33 @@ int dfpsr_draw_higher(const dfpsr_image *targetHeight, const dfpsr_image *source
 int dfpsr_draw_higher_batch(const dfpsr_image *targetHeight, const dfpsr_image *targetA, const dfpsr_image *targetB, const dfpsr_sprite_draw *draws, int32_t count, void *stream) {
 	if (!exists(targetHeight) || count <= 0) { return 0; }
 	DFPSR_REQUIRE(draws != nullptr, "draw_higher_batch: null draws");
-	static thread_local DeviceBuffer staging;
-	static thread_local SpriteDev *hostStaging = nullptr;
-	static thread_local size_t hostCapacity = 0;
-	if ((size_t)count > hostCapacity) {
-		if (hostStaging) { cudaFreeHost(hostStaging); }
-		hostCapacity = (size_t)count * 2;
-		DFPSR_CHECK_CUDA(cudaMallocHost((void **)&hostStaging, hostCapacity * sizeof(SpriteDev)));
+	// The sprite records travel through a small ring of page-locked staging buffers, each with its own device copy and an event behind
+	// its upload: a slot is reused four calls later, when its copy has long completed, so the call never waits for the stream
+	// (round 1 synchronised the stream here, once per regenerated background block and once per frame of a Sandbox scene).
+	struct Slot { SpriteDev *host = nullptr; size_t capacity = 0; DeviceBuffer device; cudaEvent_t uploaded = nullptr; bool busy = false; };
+	static thread_local Slot ring[4];
+	static thread_local unsigned next = 0;
+	Slot &slot = ring[next++ & 3u];
+	if (slot.busy) { DFPSR_CHECK_CUDA(cudaEventSynchronize(slot.uploaded)); slot.busy = false; }
+	if (slot.uploaded == nullptr) { DFPSR_CHECK_CUDA(cudaEventCreateWithFlags(&slot.uploaded, cudaEventDisableTiming)); }
+	if ((size_t)count > slot.capacity) {
+		if (slot.host) { cudaFreeHost(slot.host); slot.host = nullptr; }
+		slot.capacity = (size_t)count * 2;
+		DFPSR_CHECK_CUDA(cudaMallocHost((void **)&slot.host, slot.capacity * sizeof(SpriteDev)));
 	}
-	if (staging.reserve((size_t)count * sizeof(SpriteDev))) { return 1; }
+	if (slot.device.reserve((size_t)count * sizeof(SpriteDev))) { return 1; }
 	for (int32_t i = 0; i < count; i++) {
-		hostStaging[i].sourceH = img_of(&draws[i].sourceHeight);
-		hostStaging[i].sourceA = img_of(&draws[i].sourceA);
-		hostStaging[i].sourceB = img_of(&draws[i].sourceB);
-		hostStaging[i].left = draws[i].left; hostStaging[i].top = draws[i].top; hostStaging[i].offset = draws[i].heightOffset;
+		slot.host[i].sourceH = img_of(&draws[i].sourceHeight);
+		slot.host[i].sourceA = img_of(&draws[i].sourceA);
+		slot.host[i].sourceB = img_of(&draws[i].sourceB);
+		slot.host[i].left = draws[i].left; slot.host[i].top = draws[i].top; slot.host[i].offset = draws[i].heightOffset;
 	}
-	DFPSR_CHECK_CUDA(cudaMemcpyAsync(staging.ptr, hostStaging, (size_t)count * sizeof(SpriteDev), cudaMemcpyHostToDevice, as_stream(stream)));
+	DFPSR_CHECK_CUDA(cudaMemcpyAsync(slot.device.ptr, slot.host, (size_t)count * sizeof(SpriteDev), cudaMemcpyHostToDevice, as_stream(stream)));
+	DFPSR_CHECK_CUDA(cudaEventRecord(slot.uploaded, as_stream(stream)));
+	slot.busy = true;
 	Img th = img_of(targetHeight);
 	dim3 grid((unsigned)((th.width + 31) / 32), (unsigned)((th.height + 7) / 8));
-	DFPSR_LAUNCH(higher_batch_kernel, grid, 256, 0, as_stream(stream), th, img_of(exists(targetA) ? targetA : nullptr), img_of(exists(targetB) ? targetB : nullptr), (const SpriteDev *)staging.ptr, count);
-	// the pinned staging buffer is reused by the next call on this thread
-	DFPSR_CHECK_CUDA(cudaStreamSynchronize(as_stream(stream)));
+	DFPSR_LAUNCH(higher_batch_kernel, grid, 256, 0, as_stream(stream), th, img_of(exists(targetA) ? targetA : nullptr), img_of(exists(targetB) ? targetB : nullptr), (const SpriteDev *)slot.device.ptr, count);
 	return 0;
 }
 

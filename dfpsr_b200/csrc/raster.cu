@@ -211,6 +211,7 @@ __device__ __forceinline__ PPoint world_to_screen(const dfpsr_camera &c, const d
 // One launch for every task of the batch: blockIdx.y = task. Grid rows behind the tasks clear the frame's tile counters and totals
 // (`zeroWords` words at `zero`, 16-byte aligned), which saves the frame a separate memset.
 __global__ void __launch_bounds__(256) project_kernel(const TaskParams *__restrict__ tasks, int32_t taskCount, uint4 *__restrict__ zero, uint32_t zeroWords) {
+	chain_enter();
 	if ((int32_t)blockIdx.y >= taskCount) {
 		const uint32_t quads = (zeroWords + 3u) / 4u; // the buffer is padded to a multiple of 16 bytes
 		const uint32_t i = (((uint32_t)blockIdx.y - (uint32_t)taskCount) * gridDim.x + blockIdx.x) * 256u + threadIdx.x;
@@ -697,6 +698,7 @@ __global__ void __launch_bounds__(SETUP_THREADS, SETUP_MIN_BLOCKS) setup_kernel(
 	__shared__ BigItem sBig[SETUP_THREADS];
 	__shared__ uint32_t sBigCount, sChkCount, sUnitCount, sItemBase, sUnitBase, sChkBase;
 	__shared__ uint32_t sUnitEnd[SETUP_THREADS]; // emit pass: inclusive prefix of tile rows over the queued commands
+	chain_enter();
 	if (EMIT && frame_dropped(frame)) { return; }
 	{
 		if (threadIdx.x == 0) { sChkCount = 0; sUnitCount = 0; }
@@ -931,6 +933,7 @@ __global__ void __launch_bounds__(SETUP_THREADS, SETUP_MIN_BLOCKS) setup_kernel(
 // frames whose units do not fill the machine anyway (one 1080p terrain frame has 15 k units); the bins of the two row pairs meet in a shuffle.
 template <bool SPLIT>
 __global__ void __launch_bounds__(256) big_units_kernel(FrameDev frame) {
+	chain_enter();
 	if (frame_dropped(frame)) { return; }
 	// The grid is sized by the host from an earlier frame's unit count (it does not wait for this frame's): CTAs stride over the units
 	// the counting pass found. Commands that overflowed a set-up block's queue were finished by their own thread, so the cursor
@@ -1032,6 +1035,7 @@ __global__ void __launch_bounds__(COUNTS_THREADS) counts_kernel(FrameDev frame, 
 	__shared__ uint32_t carry[2];
 	__shared__ bool sLast;
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	chain_enter();
 	if (blockIdx.x == 0) {
 		if (threadIdx.x < 2) { carry[threadIdx.x] = 0; }
 		__syncthreads();
@@ -1132,9 +1136,7 @@ __global__ void __launch_bounds__(COUNTS_THREADS) counts_kernel(FrameDev frame, 
 		t[TOTAL_OVERFLOW] = fits ? 0u : 1u;
 		hostSlot[0] = commands; hostSlot[1] = rows; hostSlot[2] = entries; hostSlot[3] = maxTile; hostSlot[4] = chk; hostSlot[7] = units;
 		hostSlot[TOTAL_OVERFLOW] = fits ? 0u : 1u;
-		__threadfence_system();
-		hostSlot[TOTAL_TICKET] = serial; // written last: the host reads the slot only after the event behind this kernel anyway
-		__threadfence_system();
+		hostSlot[TOTAL_TICKET] = serial; // no fences: the host reads the slot after the event behind this kernel, when its writes are visible
 	}
 }
 
@@ -1142,6 +1144,7 @@ __global__ void __launch_bounds__(COUNTS_THREADS) counts_kernel(FrameDev frame, 
 // Every thread looks at one tile; the long ones are queued in shared memory and sorted by the whole CTA one after the other.
 __global__ void __launch_bounds__(SORT_THREADS) sort_lists_kernel(FrameDev frame) {
 	// launched with every frame whose host side does not wait for the counts: nothing to do unless some tile list is long
+	chain_enter();
 	if (frame_dropped(frame) || frame.totals[3] <= (uint32_t)LOCAL_SORT) { return; }
 	__shared__ uint32_t s[SORT_SMEM];
 	__shared__ uint32_t sQueue[SORT_THREADS];
@@ -1525,6 +1528,7 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32, (MODE == TILE_DEFERRED ? (E
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	RecT *sRec = sRecAll[warp];
 	uint16_t *sMask = sMaskAll[warp];
+	chain_enter();
 	if (frame_dropped(frame)) { return; } // the frame did not fit its pools: the host draws it again (see FrameDev::checkCaps)
 
 	// grid = (tile columns of the widest view / RASTER_WARPS, tile rows of the tallest view, views): no division, no search
@@ -2361,7 +2365,7 @@ static int run_frame(dfpsr_renderer *r, cudaStream_t stream, bool allowAsync) {
 			const size_t zeroRows = (zeroCtas + gx - 1) / gx;
 			DFPSR_REQUIRE(taskCount + zeroRows <= 65535, "more than 65535 tasks in one frame");
 			const dim3 grid(gx, (unsigned)(taskCount + zeroRows));
-			DFPSR_LAUNCH(project_kernel, grid, 256, 0, stream, frame.tasks, (int32_t)taskCount, (uint4 *)r->tileCount.ptr, (uint32_t)counterWords);
+			DFPSR_LAUNCH_CHAINED(project_kernel, grid, 256, 0, stream, frame.tasks, (int32_t)taskCount, (uint4 *)r->tileCount.ptr, (uint32_t)counterWords);
 		}
 		if (r->occluded) {
 			// completeOcclusion (ref: api/rendererAPI.cpp:193-217) happens inside the set-up kernels, against the grid as it is now
@@ -2398,8 +2402,8 @@ static int run_frame(dfpsr_renderer *r, cudaStream_t stream, bool allowAsync) {
 		const int slot = (int)(r->serial & 1u);
 		const uint32_t serial = ++r->serial;
 		uint32_t *hostSlot = r->hostTotals + 16 * slot;
-		DFPSR_LAUNCH(setup_kernel<false>, blockTotal, SETUP_THREADS, 0, stream, frame);
-		DFPSR_LAUNCH(counts_kernel, 1 + (tileTotal + COUNTS_THREADS - 1) / COUNTS_THREADS, COUNTS_THREADS, 0, stream, frame, r->hostTotalsDevice + 16 * slot, serial);
+		DFPSR_LAUNCH_CHAINED(setup_kernel<false>, blockTotal, SETUP_THREADS, 0, stream, frame);
+		DFPSR_LAUNCH_CHAINED(counts_kernel, 1 + (tileTotal + COUNTS_THREADS - 1) / COUNTS_THREADS, COUNTS_THREADS, 0, stream, frame, r->hostTotalsDevice + 16 * slot, serial);
 		if (timing) { tLaunched = host_now_us(); }
 		uint32_t unitEstimate, maxTileEstimate;
 		bool secondHalf = true;
@@ -2436,15 +2440,15 @@ static int run_frame(dfpsr_renderer *r, cudaStream_t stream, bool allowAsync) {
 			p.slots = slotTotal;
 		}
 		if (secondHalf) {
-			DFPSR_LAUNCH(setup_kernel<true>, blockTotal, SETUP_THREADS, 0, stream, frame);
+			DFPSR_LAUNCH_CHAINED(setup_kernel<true>, blockTotal, SETUP_THREADS, 0, stream, frame);
 			if (unitEstimate > 0 || async) {
 				// frames with few units (a single 1080p frame: 15 k) are latency-bound: two threads per unit; large batches keep one.
 				// The kernels stride over the units the device counted, so an estimate only sizes the grid.
 				const uint32_t most = (uint32_t)sm_count() * 64u;
-				if (unitEstimate <= (uint32_t)sm_count() * 2048u) { DFPSR_LAUNCH(big_units_kernel<true>, std::min(most, (2u * unitEstimate + 255u) / 256u), 256, 0, stream, frame); }
-				else { DFPSR_LAUNCH(big_units_kernel<false>, std::min(most * 4u, (unitEstimate + 255u) / 256u), 256, 0, stream, frame); }
+				if (unitEstimate <= (uint32_t)sm_count() * 2048u) { DFPSR_LAUNCH_CHAINED(big_units_kernel<true>, std::min(most, (2u * unitEstimate + 255u) / 256u), 256, 0, stream, frame); }
+				else { DFPSR_LAUNCH_CHAINED(big_units_kernel<false>, std::min(most * 4u, (unitEstimate + 255u) / 256u), 256, 0, stream, frame); }
 			}
-			if (maxTileEstimate > (uint32_t)LOCAL_SORT) { DFPSR_LAUNCH(sort_lists_kernel, (tileTotal + SORT_THREADS - 1) / SORT_THREADS, SORT_THREADS, 0, stream, frame); }
+			if (maxTileEstimate > (uint32_t)LOCAL_SORT) { DFPSR_LAUNCH_CHAINED(sort_lists_kernel, (tileTotal + SORT_THREADS - 1) / SORT_THREADS, SORT_THREADS, 0, stream, frame); }
 		}
 	}
 	// grid = (tile columns of the widest view / warps per CTA, tile rows of the tallest view, views)
@@ -2452,10 +2456,10 @@ static int run_frame(dfpsr_renderer *r, cudaStream_t stream, bool allowAsync) {
 	for (const ViewDev &v : r->views) { widest = std::max(widest, (uint32_t)v.tilesX); tallest = std::max(tallest, (uint32_t)v.tilesY); }
 	DFPSR_REQUIRE(viewCount <= 65535 && tallest <= 65535u, "more than 65535 views in one batch or a target taller than 262140 rows");
 	const dim3 grid((widest + RASTER_WARPS - 1) / RASTER_WARPS, tallest, (unsigned)viewCount);
-	if (r->depthOnly) { DFPSR_LAUNCH(tile_kernel_depth, grid, RASTER_WARPS * 32, 0, stream, frame); }
-	else if (immediate) { DFPSR_LAUNCH(tile_kernel_immediate, grid, RASTER_WARPS * 32, 0, stream, frame); }
-	else if (exactFrame) { DFPSR_LAUNCH(tile_kernel_deferred, grid, RASTER_WARPS * 32, 0, stream, frame); }
-	else { DFPSR_LAUNCH(tile_kernel_tolerance, grid, RASTER_WARPS * 32, 0, stream, frame); }
+	if (r->depthOnly) { DFPSR_LAUNCH_CHAINED(tile_kernel_depth, grid, RASTER_WARPS * 32, 0, stream, frame); }
+	else if (immediate) { DFPSR_LAUNCH_CHAINED(tile_kernel_immediate, grid, RASTER_WARPS * 32, 0, stream, frame); }
+	else if (exactFrame) { DFPSR_LAUNCH_CHAINED(tile_kernel_deferred, grid, RASTER_WARPS * 32, 0, stream, frame); }
+	else { DFPSR_LAUNCH_CHAINED(tile_kernel_tolerance, grid, RASTER_WARPS * 32, 0, stream, frame); }
 	if (timing) {
 		fprintf(stderr, "renderer_end: %zu tasks, %zu views | layout+upload %.0f us, first launches %.0f us, wait for totals %.0f us, second launches %.0f us\n",
 		        taskCount, viewCount, tUploaded - tStart, tLaunched - tUploaded, tSynced > 0.0 ? tSynced - tLaunched : 0.0, host_now_us() - (tSynced > 0.0 ? tSynced : tLaunched));

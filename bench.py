@@ -236,7 +236,7 @@ def main():
     lib.check(cuda.dfpsr_init(local_rank))
     distributed = world > 1
     if distributed:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
+        os.environ.pop("NCCL_DEBUG", None) if os.environ.get("NCCL_DEBUG") in ("WARN", "VERSION") else None  # those levels print NCCL's version banner on stdout; rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib.check(cuda.dfpsr_set_default_async(0 if args.sync else 1))
     headline_exact = args.precision == "exact"

@@ -36,13 +36,15 @@ def test_strip_sharded_frame_two_gpus():
     line = last_json(out.stdout)
     assert line["n_gpus"] == 2 and line["gathered_equals_full_frame"] is True
     # the same strips stored by the tile kernels straight into rank 0's frame over NVLink peer memory (dfpsr_peer_*, shard.PeerStripFrame)
-    assert line["peer_equals_full_frame"] is True and line["peer_wait_timed_out"] is False
+    assert line["peer_equals_full_frame"] is True and line["peer_waits_timed_out"] == 0
 
 
 def test_view_sharded_bench_two_gpus():
     if gpu_count() < 2:
         pytest.skip("needs two GPUs")
-    out = torchrun(["bench.py", "--gpus", "2", "--steps", "1", "--warmup", "3", "--views", "16", "--no-extras", "--no-cpu-baseline"], 29632)
+    out = torchrun(["bench.py", "--gpus", "2", "--steps", "1", "--warmup", "3", "--views", "256", "--no-extras", "--no-cpu-baseline"], 29632)
     assert out.returncode == 0, out.stderr[-3000:]
     line = last_json(out.stdout)
-    assert line["n_gpus"] == 2 and line["scaling"] == "weak" and line["value"] > 0 and line["gpu_launches"] > 0
+    assert line["n_gpus"] == 2 and line["scaling"] == "strong" and line["value"] > 0 and line["gpu_launches"] > 0
+    # every rank compared the first and last view of its shard of the 256-view batch with the compiled reference's hashes
+    assert line["details"]["views_per_step_per_gpu"] == 128 and line["parity_ok"] is True and line["e2e"]["parity_ok_first_view_rank0"] is True

@@ -11,7 +11,7 @@ FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     # the reference is built without FMA contraction; bit-exact parity needs the same rounding
     "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
-    "-Xcompiler", "-fPIC,-ffp-contract=off,-O2", "-shared",
+    "-Xcompiler", "-fPIC,-ffp-contract=off,-O2", "-shared", "-ldl",
 ]
 
 

@@ -80,6 +80,9 @@ struct ColorRgbaI32 { // ref: implementation/image/Color.h
 	ColorRgbaI32(int32_t r, int32_t g, int32_t b, int32_t a) : red(r), green(g), blue(b), alpha(a) {}
 };
 
+struct IVector2D { int32_t x = 0, y = 0; IVector2D() {} IVector2D(int32_t x, int32_t y) : x(x), y(y) {} }; // ref: math/IVector.h
+struct IVector3D { int32_t x = 0, y = 0, z = 0; IVector3D() {} IVector3D(int32_t x, int32_t y, int32_t z) : x(x), y(y), z(z) {} };
+
 // ---------------------------------------------------------------- device context
 inline void *&b200_stream() { static thread_local void *stream = nullptr; return stream; } // cudaStream_t used by this thread's calls
 inline void b200_init(int device = 0) { b200_check(dfpsr_init(device)); }
@@ -193,6 +196,16 @@ inline ColorRgbaI32 image_readPixel_clamp(const ImageRgbaU8 &image, int32_t x, i
 	std::memcpy(&c, image.buffer->hostData() + image.startOffset + (size_t)y * image.stride + (size_t)x * 4, 4);
 	return b200_unpack(c, image.packOrder);
 }
+// ref: api/imageAPI.h:228-275 image_readPixel_border (transparent black or the given colour outside) and image_readPixel_tile (wrap around)
+inline ColorRgbaI32 image_readPixel_border(const ImageRgbaU8 &image, int32_t x, int32_t y, const ColorRgbaI32 &border = ColorRgbaI32()) {
+	if (!image_exists(image) || x < 0 || y < 0 || x >= image.width || y >= image.height) { return border; }
+	return image_readPixel_clamp(image, x, y);
+}
+inline ColorRgbaI32 image_readPixel_tile(const ImageRgbaU8 &image, int32_t x, int32_t y) {
+	if (!image_exists(image)) { return ColorRgbaI32(); }
+	auto wrap = [](int32_t v, int32_t size) { int32_t m = v % size; return m < 0 ? m + size : m; };
+	return image_readPixel_clamp(image, wrap(x, image.width), wrap(y, image.height));
+}
 inline float image_readPixel_clamp(const ImageF32 &image, int32_t x, int32_t y) {
 	if (!image_exists(image)) { return 0.0f; }
 	x = x < 0 ? 0 : (x >= image.width ? image.width - 1 : x); y = y < 0 ? 0 : (y >= image.height ? image.height - 1 : y);
@@ -200,6 +213,23 @@ inline float image_readPixel_clamp(const ImageF32 &image, int32_t x, int32_t y) 
 	std::memcpy(&v, image.buffer->hostData() + image.startOffset + (size_t)y * image.stride + (size_t)x * 4, 4);
 	return v;
 }
+// ref: api/imageAPI.h:184-204 image_writePixel — saturated, silently ignored outside of the image; written through to the device
+inline uint32_t b200_pack(const ColorRgbaI32 &color, PackOrderIndex order) {
+	static const int index[4][4] = {{0, 1, 2, 3}, {2, 1, 0, 3}, {1, 2, 3, 0}, {3, 2, 1, 0}};
+	const int *i = index[(int)order];
+	auto sat = [](int32_t v) { return (uint32_t)(v < 0 ? 0 : (v > 255 ? 255 : v)); };
+	return (sat(color.red) << (8 * i[0])) | (sat(color.green) << (8 * i[1])) | (sat(color.blue) << (8 * i[2])) | (sat(color.alpha) << (8 * i[3]));
+}
+template <typename P> inline void b200_write_pixel(const B200Image<P> &image, int32_t x, int32_t y, const void *value) {
+	if (!image_exists(image) || x < 0 || y < 0 || x >= image.width || y >= image.height) { return; }
+	const size_t offset = (size_t)image.startOffset + (size_t)y * image.stride + (size_t)x * sizeof(P);
+	if (image.buffer->hostValid && !image.buffer->deviceDirty) { std::memcpy(image.buffer->host.data() + offset, value, sizeof(P)); } // keep a valid mirror valid
+	b200_check(dfpsr_upload((uint8_t *)image.buffer->device + offset, value, sizeof(P), b200_stream()));
+	b200_check(dfpsr_stream_synchronize(b200_stream())); // `value` is the caller's stack
+}
+inline void image_writePixel(const ImageRgbaU8 &image, int32_t x, int32_t y, const ColorRgbaI32 &color) { const uint32_t packed = b200_pack(color, image.packOrder); b200_write_pixel(image, x, y, &packed); }
+inline void image_writePixel(const ImageRgbaU8 &image, int32_t x, int32_t y, uint32_t packedColor) { b200_write_pixel(image, x, y, &packedColor); }
+inline void image_writePixel(const ImageF32 &image, int32_t x, int32_t y, float color) { b200_write_pixel(image, x, y, &color); }
 // Whole-image transfers for presentation / asset upload (tightly packed rows on the host side).
 template <typename P> inline void image_download(const B200Image<P> &image, P *target, int32_t targetStrideBytes) {
 	if (!image_exists(image)) { return; }
@@ -434,8 +464,11 @@ inline Model importFromContent_DMF1(const std::string &fileContent, int32_t deta
 inline std::vector<dfpsr_model> b200_device_models(const Model &model) {
 	std::vector<dfpsr_model> result;
 	if (!model || model->points.empty()) { return result; }
+	// A task only records device pointers (projection and set-up run at renderer_end), so geometry that a renderer still holds on to —
+	// use_count() > 1: B200Renderer keeps every buffer of its queued and in-flight tasks — is never overwritten in place: the changed
+	// model gets a fresh buffer and the queued task keeps drawing what was submitted, like the reference's copy at renderer_giveTask.
 	if (model->pointsDirty || !model->devicePoints || model->devicePoints->bytes < model->points.size() * 4) {
-		if (!model->devicePoints || model->devicePoints->bytes < model->points.size() * 4) { model->devicePoints = std::make_shared<B200Buffer>(model->points.size() * 4); }
+		if (!model->devicePoints || model->devicePoints->bytes < model->points.size() * 4 || model->devicePoints.use_count() > 1) { model->devicePoints = std::make_shared<B200Buffer>(model->points.size() * 4); }
 		b200_check(dfpsr_upload(model->devicePoints->device, model->points.data(), model->points.size() * 4, b200_stream()));
 		b200_check(dfpsr_stream_synchronize(b200_stream()));
 		model->pointsDirty = false;
@@ -444,7 +477,7 @@ inline std::vector<dfpsr_model> b200_device_models(const Model &model) {
 		if (part.polygons.empty()) { continue; }
 		size_t bytes = part.polygons.size() * sizeof(dfpsr_polygon);
 		if (part.dirty || !part.devicePolygons || part.devicePolygons->bytes < bytes) {
-			if (!part.devicePolygons || part.devicePolygons->bytes < bytes) { part.devicePolygons = std::make_shared<B200Buffer>(bytes); }
+			if (!part.devicePolygons || part.devicePolygons->bytes < bytes || part.devicePolygons.use_count() > 1) { part.devicePolygons = std::make_shared<B200Buffer>(bytes); }
 			b200_check(dfpsr_upload(part.devicePolygons->device, part.polygons.data(), bytes, b200_stream()));
 			b200_check(dfpsr_stream_synchronize(b200_stream()));
 			part.dirty = false;
@@ -468,7 +501,12 @@ struct B200Renderer {
 	ImageRgbaU8 colorBuffer;
 	ImageF32 depthBuffer;
 	bool receiving = false;
-	B200Renderer() { b200_check(dfpsr_renderer_create(&handle)); }
+	// Every device buffer the queued tasks point at (points, polygons, textures, targets), and those of the frame before: the library reads
+	// them at renderer_end and, for an asynchronous renderer, possibly once more when it verifies the frame at the next renderer_begin.
+	// A model or texture that its owner drops in between therefore stays alive for as long as a task can read it.
+	std::vector<std::shared_ptr<B200Buffer>> queued, inFlight;
+	void keep(const std::shared_ptr<B200Buffer> &buffer) { if (buffer) { queued.push_back(buffer); } }
+	B200Renderer() { b200_check(dfpsr_renderer_create(&handle)); b200_check(dfpsr_renderer_set_async(handle, 1)); } // every consumer of a shim image goes through the library, which verifies frames in flight first
 	~B200Renderer() { if (handle) { dfpsr_renderer_destroy(handle); } }
 	B200Renderer(const B200Renderer &) = delete;
 	B200Renderer &operator=(const B200Renderer &) = delete;
@@ -481,7 +519,9 @@ inline void renderer_begin(Renderer &renderer, ImageRgbaU8 &colorBuffer, ImageF3
 	if (!renderer) { throwError("renderer_begin: renderer does not exist"); }
 	dfpsr_image color = colorBuffer.pod(), depth = depthBuffer.pod();
 	b200_check(dfpsr_renderer_begin(renderer->handle, &color, &depth)); // "twice without ending" is reported by the library (rendererAPI.cpp:152-154)
+	renderer->inFlight.clear(); // the previous frame has been verified by the call above; releasing a buffer waits for the device (cudaFree)
 	renderer->colorBuffer = colorBuffer; renderer->depthBuffer = depthBuffer; renderer->receiving = true;
+	renderer->keep(colorBuffer.buffer); renderer->keep(depthBuffer.buffer);
 }
 inline ImageRgbaU8 renderer_getColorBuffer(const Renderer &renderer) { return renderer ? renderer->colorBuffer : ImageRgbaU8(); }
 inline ImageF32 renderer_getDepthBuffer(const Renderer &renderer) { return renderer ? renderer->depthBuffer : ImageF32(); }
@@ -492,6 +532,8 @@ inline void model_render_threaded(const Model &model, const Transform3D &modelTo
 	if (!model) { return; }
 	dfpsr_transform3d t = b200_pod(modelToWorldTransform);
 	for (const dfpsr_model &m : b200_device_models(model)) { b200_check(dfpsr_renderer_give_task(renderer->handle, &m, &t, &camera.pod, b200_stream())); }
+	renderer->keep(model->devicePoints);
+	for (const B200Part &part : model->parts) { renderer->keep(part.devicePolygons); renderer->keep(part.diffuseMap.buffer); renderer->keep(part.lightMap.buffer); }
 }
 inline void renderer_giveTask(Renderer &renderer, const Model &model, const Transform3D &modelToWorldTransform, const Camera &camera) { model_render_threaded(model, modelToWorldTransform, renderer, camera); }
 // ref: api/rendererAPI.h:108-129 renderer_giveTask_triangle with points the caller projected (ProjectedPoint, 40 bytes)
@@ -508,6 +550,7 @@ inline void renderer_giveTask_triangle(Renderer &renderer, const dfpsr_projected
 	}
 	dfpsr_texture d = diffuse.pod(), l = light.pod();
 	b200_check(dfpsr_renderer_give_task_triangles(renderer->handle, &tri, 1, &d, &l, (int32_t)filter, &camera.pod, b200_stream()));
+	renderer->keep(diffuse.buffer); renderer->keep(light.buffer);
 }
 // ref: api/rendererAPI.h:73-97, :131 — the occlusion grid
 inline void renderer_occludeFromBox(Renderer &renderer, const FVector3D &minimum, const FVector3D &maximum, const Transform3D &modelToWorldTransform, const Camera &camera, bool debugSilhouette = false) {
@@ -538,6 +581,7 @@ inline void renderer_end(Renderer &renderer, bool debugWireframe = false) {
 	(void)debugWireframe; // the wireframe overlay (rendererAPI.cpp:362-399) is a 2D draw call outside the path
 	if (!renderer) { throwError("renderer_end: renderer does not exist"); }
 	b200_check(dfpsr_renderer_end(renderer->handle, b200_stream()));
+	renderer->inFlight.swap(renderer->queued); renderer->queued.clear();
 	renderer->colorBuffer.touchedByDevice(); renderer->depthBuffer.touchedByDevice();
 	renderer->colorBuffer = ImageRgbaU8(); renderer->depthBuffer = ImageF32(); renderer->receiving = false; // ref: rendererAPI.cpp:480-488
 }
@@ -623,14 +667,19 @@ inline void addPointLight(const OrthoView &camera, int32_t worldCenterX, int32_t
 	int32_t c[3] = {lightColor.red, lightColor.green, lightColor.blue}, wc[2] = {worldCenterX, worldCenterY};
 	b200_check(dfpsr_light_point(&camera.pod, wc, &l, &n, &h, p, lightRadius, lightIntensity, c, image_exists(shadowCubeMap) ? &cube : nullptr, b200_stream())); lightBuffer.touchedByDevice();
 }
+// ref: SDK/SpriteEngine/lightAPI.h:29-30 — the reference's two signatures (world centre as IVector2D, with and without a shadow cube map)
+inline void addPointLight(const OrthoView &camera, const IVector2D &worldCenter, ImageRgbaU8 &lightBuffer, const ImageRgbaU8 &normalBuffer, const ImageF32 &heightBuffer, const FVector3D &lightPosition, float lightRadius, float lightIntensity, const ColorRgbaI32 &lightColor, const ImageF32 &shadowCubeMap) {
+	addPointLight(camera, worldCenter.x, worldCenter.y, lightBuffer, normalBuffer, heightBuffer, lightPosition, lightRadius, lightIntensity, lightColor, shadowCubeMap);
+}
+inline void addPointLight(const OrthoView &camera, const IVector2D &worldCenter, ImageRgbaU8 &lightBuffer, const ImageRgbaU8 &normalBuffer, const ImageF32 &heightBuffer, const FVector3D &lightPosition, float lightRadius, float lightIntensity, const ColorRgbaI32 &lightColor) {
+	addPointLight(camera, worldCenter.x, worldCenter.y, lightBuffer, normalBuffer, heightBuffer, lightPosition, lightRadius, lightIntensity, lightColor, ImageF32());
+}
 inline void blendLight(ImageRgbaU8 &colorBuffer, const ImageRgbaU8 &diffuseBuffer, const ImageRgbaU8 &lightBuffer) {
 	dfpsr_image c = colorBuffer.pod(), d = diffuseBuffer.pod(), l = lightBuffer.pod();
 	b200_check(dfpsr_light_blend(&c, &d, &l, b200_stream())); colorBuffer.touchedByDevice();
 }
 
 // ---------------------------------------------------------------- Sandbox sprite world (ref: SDK/SpriteEngine/spriteAPI.h:24-145, orthoAPI.h:92-134)
-struct IVector2D { int32_t x = 0, y = 0; IVector2D() {} IVector2D(int32_t x, int32_t y) : x(x), y(y) {} };
-struct IVector3D { int32_t x = 0, y = 0, z = 0; IVector3D() {} IVector3D(int32_t x, int32_t y, int32_t z) : x(x), y(y), z(z) {} };
 using Direction = int32_t;
 static const int32_t ortho_miniUnitsPerTile = 1024; // ref: orthoAPI.h:28
 struct OrthoSystem { // ref: orthoAPI.h:92-134 — the eight views are derived exactly like OrthoSystem::update (orthoAPI.cpp:82-119)
@@ -768,7 +817,46 @@ inline ImageRgbaU8 filter_resize(const ImageRgbaU8 &source, Sampler interpolatio
 	result.touchedByDevice();
 	return result;
 }
-// The reference takes a host lambda per pixel (api/filterAPI.h:54-59), which a device cannot call; the shim exposes the enumerated device ops.
+// ref: api/filterAPI.h:54-79 filter_mapRgbaU8 / filter_generateRgbaU8. Three ways to say what a pixel is:
+//   PixelProgram   the function as CUDA C++ text, compiled for the device on first use (dfpsr_filter_map_program): runs at HBM bandwidth.
+//                  filter_mapRgbaU8(target, PixelProgram("int4 s = read_clamp(0, x, y); return make_int4(s.x * 2, s.y * 2, s.z * 2, s.w);", {source}));
+//   a host callable  `ColorRgbaI32 f(int32_t x, int32_t y)` exactly like the reference's lambda — code written for the reference compiles
+//                  unchanged. A device cannot call into the host, so the callable runs on the host over the image's mirror and the result is
+//                  uploaded: correct, and as slow as the reference ("when speed is not critical", filterAPI.h:50). Images it captures are read
+//                  through image_readPixel_* (one download each).
+//   a device op    one of the pre-compiled DFPSR_MAP_* instances.
+struct PixelProgram {
+	std::string body;
+	std::vector<ImageRgbaU8> sources;
+	explicit PixelProgram(const std::string &body, const std::vector<ImageRgbaU8> &sources = std::vector<ImageRgbaU8>()) : body(body), sources(sources) {}
+};
+inline void filter_mapRgbaU8(ImageRgbaU8 &target, const PixelProgram &program, int32_t startX = 0, int32_t startY = 0) {
+	if (!image_exists(target)) { return; }
+	std::vector<dfpsr_image> sources;
+	for (const ImageRgbaU8 &source : program.sources) { sources.push_back(source.pod()); }
+	dfpsr_image t = target.pod();
+	b200_check(dfpsr_filter_map_program(&t, program.body.c_str(), sources.data(), (int32_t)sources.size(), startX, startY, b200_stream())); target.touchedByDevice();
+}
+template <typename F, typename = decltype(std::declval<F &>()(0, 0).red)>
+inline void filter_mapRgbaU8(ImageRgbaU8 &target, F &&lambda, int32_t startX = 0, int32_t startY = 0) {
+	if (!image_exists(target)) { return; }
+	std::vector<uint32_t> rows((size_t)target.width * (size_t)target.height);
+	for (int32_t y = 0; y < target.height; y++) {
+		for (int32_t x = 0; x < target.width; x++) { rows[(size_t)y * target.width + x] = b200_pack(lambda(x + startX, y + startY), target.packOrder); }
+	}
+	image_upload(target, rows.data(), target.width * 4);
+}
+inline ImageRgbaU8 filter_generateRgbaU8(int32_t width, int32_t height, const PixelProgram &program, int32_t startX = 0, int32_t startY = 0) {
+	ImageRgbaU8 result = b200_image_create<uint32_t>(width, height, PackOrderIndex::RGBA);
+	filter_mapRgbaU8(result, program, startX, startY);
+	return result;
+}
+template <typename F, typename = decltype(std::declval<F &>()(0, 0).red)>
+inline ImageRgbaU8 filter_generateRgbaU8(int32_t width, int32_t height, F &&lambda, int32_t startX = 0, int32_t startY = 0) {
+	ImageRgbaU8 result = b200_image_create<uint32_t>(width, height, PackOrderIndex::RGBA);
+	filter_mapRgbaU8(result, lambda, startX, startY);
+	return result;
+}
 inline void filter_mapRgbaU8(ImageRgbaU8 &target, int32_t deviceOp, const int32_t *params, int32_t paramCount, const ImageRgbaU8 &source = ImageRgbaU8(), int32_t startX = 0, int32_t startY = 0) {
 	dfpsr_image t = target.pod(), s = source.pod();
 	b200_check(dfpsr_filter_map(&t, deviceOp, params, paramCount, image_exists(source) ? &s : nullptr, startX, startY, b200_stream())); target.touchedByDevice();

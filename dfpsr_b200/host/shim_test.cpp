@@ -21,6 +21,67 @@ template <typename T> static std::vector<T> readArray(FILE *f, size_t count) {
 	return v;
 }
 
+// shim_test --filters <out.bin>: code written for the reference's filter API (ref: api/filterAPI.h:62-79) compiles unchanged against the
+// shim — host lambdas capturing images — and gives the same pixels as the same functions handed to the device as pixel programs.
+static int filterSession(const char *outPath) {
+	b200_init(0);
+	int32_t width = 64;
+	int32_t height = 64;
+	// the two generators of api/filterAPI.h:67-73, verbatim
+	ImageRgbaU8 fadeImage = filter_generateRgbaU8(width, height, [](int32_t x, int32_t y)->ColorRgbaI32 {
+		return ColorRgbaI32(x * 4, y * 4, 0, 255);
+	});
+	ImageRgbaU8 brighterImage = filter_generateRgbaU8(width, height, [fadeImage](int32_t x, int32_t y)->ColorRgbaI32 {
+		ColorRgbaI32 source = image_readPixel_clamp(fadeImage, x, y);
+		return ColorRgbaI32(source.red * 2, source.green * 2, source.blue * 2, source.alpha);
+	});
+	// the same two functions as device programs
+	ImageRgbaU8 fadeDevice = filter_generateRgbaU8(width, height, PixelProgram("return make_int4(x * 4, y * 4, 0, 255);"));
+	ImageRgbaU8 brighterDevice = filter_generateRgbaU8(width, height, PixelProgram("int4 s = read_clamp(0, x, y); return make_int4(s.x * 2, s.y * 2, s.z * 2, s.w);", {fadeDevice}));
+	std::vector<uint32_t> a((size_t)width * height), b(a.size()), c(a.size()), d(a.size());
+	image_download(fadeImage, a.data(), width * 4); image_download(fadeDevice, b.data(), width * 4);
+	image_download(brighterImage, c.data(), width * 4); image_download(brighterDevice, d.data(), width * 4);
+	ASSERT(std::memcmp(a.data(), b.data(), a.size() * 4) == 0);
+	ASSERT(std::memcmp(c.data(), d.data(), c.size() * 4) == 0);
+	ASSERT((c[(size_t)10 * width + 40] & 255u) == 255u && ((c[(size_t)10 * width + 40] >> 8) & 255u) == 80u); // 40 * 4 * 2 saturates, 10 * 4 * 2 = 80
+	// in-place map with start offsets, border and tile reads, a target in another pack order; a program that does not compile is an error
+	ImageRgbaU8 target = image_create_RgbaU8_native(50, 30, PackOrderIndex::BGRA);
+	auto pattern = [fadeImage](int32_t x, int32_t y)->ColorRgbaI32 {
+		ColorRgbaI32 t = image_readPixel_tile(fadeImage, x * 3, y - 70), e = image_readPixel_border(fadeImage, x - 5, y, ColorRgbaI32(9, 8, 7, 6));
+		return ColorRgbaI32(t.red + e.red / 2, t.green - 300, e.blue + x, e.alpha);
+	};
+	filter_mapRgbaU8(target, pattern, -7, 11);
+	std::vector<uint32_t> hostResult((size_t)50 * 30), deviceResult(hostResult.size());
+	image_download(target, hostResult.data(), 50 * 4);
+	filter_mapRgbaU8(target, PixelProgram("int4 t = read_tile(0, x * 3, y - 70), e = read_border(0, x - 5, y, make_int4(9, 8, 7, 6)); return make_int4(t.x + e.x / 2, t.y - 300, e.z + x, e.w);", {fadeDevice}), -7, 11);
+	image_download(target, deviceResult.data(), 50 * 4);
+	ASSERT(std::memcmp(hostResult.data(), deviceResult.data(), hostResult.size() * 4) == 0);
+	ASSERT_THROWS(filter_mapRgbaU8(target, PixelProgram("return no_such_thing;")), "does not compile");
+	// image_writePixel: saturated, ignored outside, visible to device work and to reads (ref: api/imageAPI.h:184-204)
+	image_writePixel(target, 3, 4, ColorRgbaI32(300, -5, 17, 255));
+	image_writePixel(target, -1, 4, ColorRgbaI32(1, 2, 3, 4));
+	ColorRgbaI32 written = image_readPixel_clamp(target, 3, 4);
+	ASSERT(written.red == 255 && written.green == 0 && written.blue == 17 && written.alpha == 255);
+	ImageF32 heights = image_create_F32(8, 8);
+	image_writePixel(heights, 2, 2, 1.5f);
+	ASSERT(image_readPixel_clamp(heights, 2, 2) == 1.5f && image_readPixel_clamp(heights, 3, 2) == 0.0f);
+	// both addPointLight signatures of SDK/SpriteEngine/lightAPI.h:29-30 (world centre as IVector2D)
+	OrthoSystem ortho(0.6f, 32);
+	OrthoView view = ortho.lightView(0);
+	ImageRgbaU8 light = image_create_RgbaU8(64, 64), normal = image_create_RgbaU8(64, 64);
+	ImageF32 heightBuffer = image_create_F32(64, 64), cube = image_create_F32(16, 96);
+	image_fill(normal, ColorRgbaI32(128, 255, 128, 0));
+	addPointLight(view, IVector2D(32, 32), light, normal, heightBuffer, FVector3D(0.0f, 2.0f, 0.0f), 4.0f, 1.0f, ColorRgbaI32(255, 200, 100, 0));
+	addPointLight(view, IVector2D(32, 32), light, normal, heightBuffer, FVector3D(0.0f, 2.0f, 0.0f), 4.0f, 1.0f, ColorRgbaI32(255, 200, 100, 0), cube);
+	FILE *out = std::fopen(outPath, "wb");
+	ASSERT(out != nullptr);
+	std::fwrite(c.data(), 4, c.size(), out);
+	std::fwrite(hostResult.data(), 4, hostResult.size(), out);
+	std::fclose(out);
+	std::printf("shim_test filters ok\n");
+	return 0;
+}
+
 // shim_test --sprites <assets.bin> <out.bin>: a small Sandbox session through spriteWorld_* (ref: SDK/sandbox/sandbox.cpp:336-353, :366-493):
 // one sprite type and one model type from the file, a grid of passive sprites, two lights, a temporary sprite, two frames.
 struct SpriteHeader { int32_t atlasWidth, atlasHeight, frameRows, centerX, centerY, pointCount, polygonCount, width, height; float minBound[3], maxBound[3]; };
@@ -80,6 +141,7 @@ static int spriteSession(const char *inPath, const char *outPath) {
 }
 
 int main(int argc, char **argv) {
+	if (argc == 3 && std::string(argv[1]) == "--filters") { return filterSession(argv[2]); }
 	if (argc == 4 && std::string(argv[1]) == "--sprites") { return spriteSession(argv[2], argv[3]); }
 	if (argc < 3) { std::fprintf(stderr, "usage: shim_test scene.bin out.bin\n"); return 2; }
 	FILE *f = std::fopen(argv[1], "rb");

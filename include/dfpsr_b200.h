@@ -118,8 +118,7 @@ typedef struct dfpsr_model {
 	float minBound[3], maxBound[3]; /* model space, ref: Model.h:83 */
 } dfpsr_model;
 
-/* Per-pixel operations for filter_mapRgbaU8 / filter_generateRgbaU8. The reference takes a host
- * lambda (ref: api/filterAPI.h:54-59); a device cannot run it, so the ABI enumerates device ops.
+/* Pre-compiled per-pixel operations for filter_mapRgbaU8 / filter_generateRgbaU8 (the general form is dfpsr_filter_map_program).
  * params are int32. Results are saturated to 0..255 and packed in the target's pack order
  * (ref: api/filterAPI.cpp:759-777, image_saturateAndPack). */
 enum {
@@ -487,7 +486,17 @@ int dfpsr_sprite_world_get_buffers(const dfpsr_sprite_world *world, dfpsr_image 
  * scratch: device buffer of dfpsr_filter_resize_scratch_bytes() bytes, only used for two-pass up-scaling. */
 size_t dfpsr_filter_resize_scratch_bytes(int32_t sourceWidth, int32_t sourceHeight, int32_t newWidth, int32_t newHeight);
 int dfpsr_filter_resize(const dfpsr_image *target, const dfpsr_image *source, int32_t sampler, int32_t sourceIsSubImage, void *scratch, void *stream);
-/* ref: api/filterAPI.cpp:759-782 filter_mapRgbaU8 / filter_generateRgbaU8 with a device op. */
+/* ref: api/filterAPI.h:54-79, api/filterAPI.cpp:759-782 filter_mapRgbaU8 / filter_generateRgbaU8 with ANY per-pixel function.
+ * The reference takes a host lambda `ColorRgbaI32 f(int32_t x, int32_t y)`; here the function travels as text: `body` is the body of
+ *     int4 pixel(int x, int y)      // (red, green, blue, alpha) as ints, saturated to 0..255 and packed in the target's order afterwards
+ * in CUDA C++, compiled for the current device with NVRTC on first use and cached by its text. x and y are target coordinates plus
+ * startX / startY. Up to 4 source images (device memory, any pack order) are read inside the body with read_clamp(i, x, y),
+ * read_border(i, x, y[, int4 border]), read_tile(i, x, y) -> int4 (r, g, b, a) — the rules of image_readPixel_clamp / _border / _tile —
+ * and source_width(i) / source_height(i). Example, the brighter image of api/filterAPI.h:67-73:
+ *     "int4 s = read_clamp(0, x, y); return make_int4(s.x * 2, s.y * 2, s.z * 2, s.w);"
+ * Needs libnvrtc.so.12 of the CUDA toolkit at run time. The enumerated ops of dfpsr_filter_map are pre-compiled instances. */
+int dfpsr_filter_map_program(const dfpsr_image *target, const char *body, const dfpsr_image *sources, int32_t sourceCount, int32_t startX, int32_t startY, void *stream);
+/* ref: api/filterAPI.cpp:759-782 filter_mapRgbaU8 / filter_generateRgbaU8 with one of the pre-compiled device ops above. */
 int dfpsr_filter_map(const dfpsr_image *target, int32_t op, const int32_t *params, int32_t paramCount, const dfpsr_image *source, int32_t startX, int32_t startY, void *stream);
 /* ref: api/filterAPI.cpp:724-757, :872-876 filter_blockMagnify. */
 int dfpsr_filter_block_magnify(const dfpsr_image *target, const dfpsr_image *source, int32_t pixelWidth, int32_t pixelHeight, void *stream);

@@ -114,3 +114,46 @@ def test_shim_sprite_world_session(tmp_path, oracle):
     location, _ground, _index = pw.camera_state(w, h)
     assert list(tail[3:6]) == [int(v) for v in location]
     pw.close()
+
+
+@pytest.mark.gpu
+def test_shim_filter_lambdas_and_pixel_programs(tmp_path):
+    """Code written for the reference's filter API (host lambdas capturing images, api/filterAPI.h:62-79) compiles unchanged against the
+    shim; the same functions as device pixel programs (NVRTC) give the same pixels; image_writePixel, both addPointLight signatures."""
+    result = subprocess.run([EXE, "--filters", str(tmp_path / "out.bin")], capture_output=True, text=True)
+    assert result.returncode == 0, result.stdout + result.stderr
+    raw = np.fromfile(tmp_path / "out.bin", np.uint32)
+    brighter = raw[:64 * 64].reshape(64, 64)
+    y, x = np.mgrid[0:64, 0:64]
+    red, green = np.minimum(np.minimum(x * 4, 255) * 2, 255), np.minimum(np.minimum(y * 4, 255) * 2, 255)
+    assert np.array_equal(brighter, (red | (green << 8) | (255 << 24)).astype(np.uint32))
+
+
+@pytest.mark.gpu
+def test_filter_map_program_matches_numpy(cuda):
+    """dfpsr_filter_map_program through the C ABI: an arbitrary integer function of (x, y) and two sources in different pack orders."""
+    import torch
+    from dfpsr_b200 import lib
+    rng = np.random.default_rng(3)
+    h, w = 37, 101
+    a = rng.integers(0, 2 ** 32, (h, w), dtype=np.uint32)
+    b = rng.integers(0, 2 ** 32, (16, 16), dtype=np.uint32)
+    ta, tb, out = lib.to_device(a), lib.to_device(b), lib.to_device(np.zeros((h, w), np.uint32))
+    sources = (abi.Image * 2)(lib.image(ta, abi.PACK_RGBA), lib.image(tb, abi.PACK_BGRA))
+    body = b"int4 s = read_clamp(0, x + 1, y - 1); int4 t = read_tile(1, x, y); return make_int4(s.x + t.x - 40, (s.y * t.y) >> 7, s.z ^ t.z, 255 - s.w + source_width(1));"
+    lib.check(cuda.dfpsr_filter_map_program(C.byref(lib.image(out, abi.PACK_ARGB)), body, sources, 2, 5, -3, lib.stream_ptr()))
+    got = out.cpu().numpy().view(np.uint32)
+    yy, xx = np.mgrid[0:h, 0:w]
+    xx, yy = xx + 5, yy - 3
+    sx, sy = np.clip(xx + 1, 0, w - 1), np.clip(yy - 1, 0, h - 1)
+    s = a[sy, sx]
+    t = b[yy % 16, xx % 16]
+    sr, sg, sb, sa = [((s >> k) & 255).astype(np.int64) for k in (0, 8, 16, 24)]
+    tr, tg, tb_, ta_ = [((t >> k) & 255).astype(np.int64) for k in (16, 8, 0, 24)]  # BGRA: red in byte 2
+    r, g, bl, al = np.clip(sr + tr - 40, 0, 255), np.clip((sg * tg) >> 7, 0, 255), np.clip(sb ^ tb_, 0, 255), np.clip(255 - sa + 16, 0, 255)
+    expected = ((al << 0) | (r << 8) | (g << 16) | (bl << 24)).astype(np.uint32)  # ARGB: alpha in byte 0
+    assert np.array_equal(got, expected)
+    # the compiled program is cached: a second call with the same text launches at once; a broken body reports the compiler's message
+    lib.check(cuda.dfpsr_filter_map_program(C.byref(lib.image(out, abi.PACK_ARGB)), body, sources, 2, 5, -3, lib.stream_ptr()))
+    assert cuda.dfpsr_filter_map_program(C.byref(lib.image(out)), b"return 1;", None, 0, 0, 0, lib.stream_ptr()) != 0
+    assert b"does not compile" in cuda.dfpsr_last_error()

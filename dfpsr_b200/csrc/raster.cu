@@ -21,6 +21,7 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <cstddef>
 #include <vector>
 #include <new>
 
@@ -78,9 +79,9 @@ static const uint32_t CHK_NONE = 0xFFFFFFFFu;
 struct ChkRec {
 	int32_t mode;
 	float v[18];
-	int32_t pad_;
+	int32_t at; // column the sums stand at (the tile's left edge, or the row pair's outer block start inside the first tile)
 };
-static_assert(sizeof(ChkRec) == 80, "ChkRec layout");
+static_assert(sizeof(ChkRec) == 80, "ChkRec layout: five 16-byte words, copied as one block into the tile kernel's shared-memory record");
 
 enum : uint32_t {
 	CMD_AFFINE = 1u, CMD_ALPHA = 2u, CMD_HAS_DIFFUSE = 4u, CMD_HAS_LIGHT = 8u, CMD_HAS_FADE = 16u, CMD_COLORLESS = 32u
@@ -622,10 +623,10 @@ __device__ __forceinline__ void emit_tile_row(const FrameDev &frame, uint32_t ti
 	}
 }
 
-__device__ __forceinline__ void chk_store(ChkRec *dst, int32_t mode, const float *v, int count) {
-	// word 0 = mode, words 1..18 = v, word 19 = padding; assembled from registers (no local copy of the record)
+__device__ __forceinline__ void chk_store(ChkRec *dst, int32_t mode, const float *v, int count, int32_t at) {
+	// word 0 = mode, words 1..18 = v, word 19 = column; assembled from registers (no local copy of the record)
 	uint32_t w[20];
-	w[0] = (uint32_t)mode; w[19] = 0u;
+	w[0] = (uint32_t)mode; w[19] = (uint32_t)at;
 #pragma unroll
 	for (int i = 0; i < 18; i++) { w[1 + i] = i < count ? __float_as_uint(v[i]) : 0u; }
 	uint4 *d = (uint4 *)dst;
@@ -652,12 +653,17 @@ __device__ void chk_walk_row_pair(const float *start, const float *dx, const flo
 	const bool noInner = ibe <= ibs;
 	const int32_t leftEnd = noInner ? obe : ibs;
 	int32_t x = obs;
-	chk_store(recs + (x / TILE_W - firstColumn), 0, v, 6);
+	// No record for the tile column the row pair starts in: the tile kernel evaluates the planes at the outer block start itself (exactly
+	// the values above), which is cheaper than storing and fetching 80 bytes — 60 % of all records of a terrain frame were of this kind.
+	// The walk therefore ends at the last tile edge inside the row pair; a row pair within one tile column is not walked at all.
+	const int32_t lastEdge = ((obe - 1) / TILE_W) * TILE_W; // obe > obs >= 0
+	if (lastEdge <= obs) { return; }
 	while (x < leftEnd) {
 #pragma unroll
 		for (int k = 0; k < 6; k++) { v[k] += dx2[k % 3]; }
 		x += 2;
-		if ((x & (TILE_W - 1)) == 0 && x < obe && (noInner || x <= ibs)) { chk_store(recs + (x / TILE_W - firstColumn), 0, v, 6); }
+		if ((x & (TILE_W - 1)) == 0 && x < obe && (noInner || x <= ibs)) { chk_store(recs + (x / TILE_W - firstColumn), 0, v, 6, x); }
+		if (x >= lastEdge) { return; }
 	}
 	if (noInner) { return; }
 	// inner run: v[0..11] = lanes[k][l], v[12..17] = the sums after the run
@@ -675,16 +681,18 @@ __device__ void chk_walk_row_pair(const float *start, const float *dx, const flo
 #pragma unroll
 		for (int i = 0; i < 12; i++) { v[i] += dx2[i / 4]; }
 		x += 2;
-		if ((x & (TILE_W - 1)) == 0 && x < ibe) { chk_store(recs + (x / TILE_W - firstColumn), 1, v, 18); }
+		if ((x & (TILE_W - 1)) == 0 && x < ibe) { chk_store(recs + (x / TILE_W - firstColumn), 1, v, 18, x); if (x >= lastEdge) { return; } }
 	}
 #pragma unroll
 	for (int k = 0; k < 6; k++) { v[k] = v[12 + k]; }
-	if ((x & (TILE_W - 1)) == 0 && x < obe) { chk_store(recs + (x / TILE_W - firstColumn), 2, v, 6); }
+	if ((x & (TILE_W - 1)) == 0 && x < obe) { chk_store(recs + (x / TILE_W - firstColumn), 2, v, 6, x); }
+	if (x >= lastEdge) { return; }
 	while (x < obe) {
 #pragma unroll
 		for (int k = 0; k < 6; k++) { v[k] += dx2[k % 3]; }
 		x += 2;
-		if ((x & (TILE_W - 1)) == 0 && x < obe) { chk_store(recs + (x / TILE_W - firstColumn), 2, v, 6); }
+		if ((x & (TILE_W - 1)) == 0 && x < obe) { chk_store(recs + (x / TILE_W - firstColumn), 2, v, 6, x); }
+		if (x >= lastEdge) { return; }
 	}
 }
 
@@ -865,9 +873,15 @@ __global__ void __launch_bounds__(SETUP_THREADS, SETUP_MIN_BLOCKS) setup_kernel(
 		const uint32_t bigCount = min(sBigCount, (uint32_t)SETUP_THREADS);
 		for (uint32_t b = warp; b < bigCount; b += SETUP_THREADS / 32) {
 			const BigItem &it = sBig[b];
-			int32_t w = it.tx1 - it.tx0 + 1, tiles = w * (it.ty1 - it.ty0 + 1);
-			for (int32_t i = lane; i < tiles; i += 32) {
-				atomicAdd(&frame.tileCount[it.tileBase + (uint32_t)((it.ty0 + i / w) * it.tilesX + it.tx0 + i % w)], 1u);
+			// wide boxes: lanes over the columns of a row; narrow ones: one lane per tile row (no division per tile)
+			if (it.tx1 - it.tx0 >= 16) {
+				for (int32_t ty = it.ty0; ty <= it.ty1; ty++) {
+					for (int32_t tx = it.tx0 + lane; tx <= it.tx1; tx += 32) { atomicAdd(&frame.tileCount[it.tileBase + (uint32_t)(ty * it.tilesX + tx)], 1u); }
+				}
+			} else {
+				for (int32_t ty = it.ty0 + lane; ty <= it.ty1; ty += 32) {
+					for (int32_t tx = it.tx0; tx <= it.tx1; tx++) { atomicAdd(&frame.tileCount[it.tileBase + (uint32_t)(ty * it.tilesX + tx)], 1u); }
+				}
 			}
 		}
 	} else {
@@ -1341,10 +1355,11 @@ __device__ __forceinline__ float reciprocal_w(float v) {
 //   mode -1: nothing of this command in this row pair of this tile
 struct Rec {
 	int32_t ul, ur, ll, lr; // row intervals of the pair, as stored
-	int32_t mode, at;
+	int32_t mode;           // from here on the layout of ChkRec: a stored checkpoint arrives as ONE 80-byte bulk copy (cp.async.bulk)
 	float v[18];
+	int32_t at;
 };
-static_assert(sizeof(Rec) == 96, "Rec layout");
+static_assert(sizeof(Rec) == 96 && offsetof(Rec, mode) == 16 && offsetof(Rec, at) == 16 + offsetof(ChkRec, at), "Rec layout");
 struct RecLite { // tolerance mode: the row intervals are all the quad lanes need
 	int32_t ul, ur, ll, lr;
 	int32_t mode, at;
@@ -1506,6 +1521,35 @@ __device__ __forceinline__ uint32_t shade_pixel(const Cmd *__restrict__ cmd, con
 	return pack_rgba_ordered(saturated_byte(r), saturated_byte(g), saturated_byte(b), saturated_byte(a), shifts);
 }
 
+// ---- bulk asynchronous copies (the TMA's linear mode: cp.async.bulk, completion on a shared-memory mbarrier)
+#ifndef DFPSR_CHK_BULK
+// 1: stored checkpoints travel global -> shared as 80-byte bulk copies (UBLKCP + mbarrier) instead of five 16-byte loads and six
+// shared-memory stores per lane. Built, bit-exact, and measured SLOWER (tile kernel 38.5 against 37.3 us per 1080p frame): UBLKCP issues
+// from the uniform datapath, so the per-lane copies of a warp are serialised (nine instructions per record), while the vector loads of
+// all lanes issue together. Kept for the record (profiles/r2_tma_experiment.md); off by default.
+#define DFPSR_CHK_BULK 0
+#endif
+__device__ __forceinline__ uint32_t smem_address(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbarrier_init(uint64_t *bar, uint32_t arrivals) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_address(bar)), "r"(arrivals) : "memory");
+}
+__device__ __forceinline__ void mbarrier_expect(uint64_t *bar, uint32_t bytes) { // one arrival that announces `bytes` of bulk copies
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_address(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbarrier_wait(uint64_t *bar, uint32_t parity) {
+	asm volatile(
+	    "{\n"
+	    ".reg .pred done;\n"
+	    "WAIT_%=:\n"
+	    "mbarrier.try_wait.parity.shared::cta.b64 done, [%0], %1;\n"
+	    "@!done bra WAIT_%=;\n"
+	    "}\n" ::"r"(smem_address(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_to_shared(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_address(dst)), "l"(src), "r"(bytes), "r"(smem_address(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 enum : int { TILE_IMMEDIATE = 0, TILE_DEPTH_ONLY = 1, TILE_DEFERRED = 2 };
 static const uint32_t NO_WINNER = 0xFFFFFFFFu;
 
@@ -1525,9 +1569,17 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32, (MODE == TILE_DEFERRED ? (E
 	__shared__ uint32_t sKeysAll[RASTER_WARPS][LOCAL_SORT]; // the tile's command list in submission order (lists up to LOCAL_SORT entries)
 	// per (row pair, command): which of the 16 quads of the row pair the command may touch; 16-bit masks, commands c and c + 8 share a word
 	__shared__ __align__(16) uint16_t sMaskAll[RASTER_WARPS][32];
+	__shared__ __align__(8) uint64_t sBarAll[RASTER_WARPS]; // one mbarrier per warp: completion of the batch's bulk copies
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	RecT *sRec = sRecAll[warp];
 	uint16_t *sMask = sMaskAll[warp];
+	uint64_t *sBar = &sBarAll[warp];
+	uint32_t barParity = 0u;
+	constexpr bool BULK = DFPSR_CHK_BULK != 0 && EXACT && MODE != TILE_DEPTH_ONLY;
+	if (BULK) {
+		if (lane == 0) { mbarrier_init(sBar, 1u); }
+		__syncwarp();
+	}
 	chain_enter();
 	if (frame_dropped(frame)) { return; } // the frame did not fit its pools: the host draws it again (see FrameDev::checkCaps)
 
@@ -1635,6 +1687,7 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32, (MODE == TILE_DEFERRED ? (E
 			int32_t recMode = -1;
 			rec.at = 0; rec.ul = rec.ur = rec.ll = rec.lr = 0;
 			int32_t quadFirst = 0, quadEnd = 0; // quads [quadFirst, quadEnd) of this row pair can be touched
+			const void *stored = nullptr;       // the stored checkpoint of this (command, row pair, tile column), fetched by a bulk copy
 			if (c < batchCount) {
 				const Cmd *cmd = frame.cmds + key;
 				const int4 head = __ldg((const int4 *)cmd + 3); // rowStart, rowCount, rowOffset, pad
@@ -1694,10 +1747,11 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32, (MODE == TILE_DEFERRED ? (E
 							const bool noInner = ibe <= ibs;
 							rec.at = at;
 							quadFirst = (at - tileLeft) >> 1; quadEnd = (min(obe, tileLeft + TILE_W) - tileLeft) >> 1;
-							if (third.z != CHK_NONE) {
+							if (third.z != CHK_NONE && obs < tileLeft) { // the row pair entered the tile from the left: its sums were stored at the tile's edge
 								// a set-up warp walked this row pair and left the sums at this tile column
 								const uint32_t firstColumn = third.w & 0xFFFFu, columns = third.w >> 16;
 								const uint4 *src = (const uint4 *)(frame.chk + third.z + (size_t)(idx >> 1) * columns + ((uint32_t)tileX - firstColumn));
+								if (BULK) { stored = src; recMode = 0; } else {
 								const uint4 w0 = __ldg(src), w1 = __ldg(src + 1), w2 = __ldg(src + 2), w3 = __ldg(src + 3), w4 = __ldg(src + 4);
 								recMode = (int32_t)w0.x;
 								rec.v[0] = __uint_as_float(w0.y); rec.v[1] = __uint_as_float(w0.z); rec.v[2] = __uint_as_float(w0.w);
@@ -1705,6 +1759,7 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32, (MODE == TILE_DEFERRED ? (E
 								rec.v[7] = __uint_as_float(w2.x); rec.v[8] = __uint_as_float(w2.y); rec.v[9] = __uint_as_float(w2.z); rec.v[10] = __uint_as_float(w2.w);
 								rec.v[11] = __uint_as_float(w3.x); rec.v[12] = __uint_as_float(w3.y); rec.v[13] = __uint_as_float(w3.z); rec.v[14] = __uint_as_float(w3.w);
 								rec.v[15] = __uint_as_float(w4.x); rec.v[16] = __uint_as_float(w4.y); rec.v[17] = __uint_as_float(w4.z);
+								}
 							} else if (noInner || at <= ibs) {
 								for (int32_t s = obs; s < at; s += 2) {
 #pragma unroll
@@ -1755,7 +1810,22 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32, (MODE == TILE_DEFERRED ? (E
 					}
 				}
 			}
-			rec.mode = recMode;
+			if constexpr (BULK) {
+				// Stored checkpoints arrive as ONE 80-byte bulk copy per lane (mode, eighteen sums, column: the tail of the record), completion
+				// counted on the warp's mbarrier; lanes that computed their checkpoint themselves write their record as before.
+				const uint32_t fetching = __ballot_sync(0xffffffffu, stored != nullptr);
+				if (fetching != 0u) {
+					fence_async_proxy(); // the previous batch read these records through the generic proxy
+					if (lane == 0) { mbarrier_expect(sBar, (uint32_t)sizeof(ChkRec) * (uint32_t)__popc(fetching)); }
+					if (stored != nullptr) { bulk_copy_to_shared(&rec.mode, stored, (uint32_t)sizeof(ChkRec), sBar); }
+					else { rec.mode = recMode; }
+					mbarrier_wait(sBar, barParity);
+					barParity ^= 1u;
+				} else { rec.mode = recMode; }
+			} else {
+				(void)stored;
+				rec.mode = recMode;
+			}
 			sMask[r * BATCH + 2u * (c & 7u) + (c >> 3)] = (uint16_t)((recMode >= 0 && quadEnd > quadFirst) ? ((0xFFFFFFFFu >> (32 - quadEnd)) & ~((1u << quadFirst) - 1u)) : 0u);
 		}
 		__syncwarp();

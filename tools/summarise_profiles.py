@@ -1,5 +1,5 @@
 """Turns the artefacts of tools/make_profiles.sh (gpurun_out/) into the tracked summaries under profiles/ for one round tag.
-usage: python tools/summarise_profiles.py r1_v8"""
+usage: python tools/summarise_profiles.py r2_v3"""
 import csv
 import io
 import json
@@ -16,9 +16,11 @@ tag = sys.argv[1] if len(sys.argv) > 1 else "r1_final"
 rows = [r for r in csv.reader(line for line in open(os.path.join(OUT, "launches.csv")) if line.startswith('"'))]
 hdr = rows[0]
 name_i, val_i = hdr.index("Kernel Name"), hdr.index("Metric Value")
+demangle = {"raster_kernel<2, 1>": "raster_kernel<2, true> (tile_kernel_deferred)", "raster_kernel<2, 0>": "raster_kernel<2, false> (tile_kernel_tolerance)"}
 per = {}
 for r in rows[1:]:
     name = r[name_i].replace("void ", "").split("(")[0]
+    name = "dfpsr::" + demangle.get(name, name) if not name.startswith(("dfpsr::", "at::")) else name
     d = per.setdefault(name, [0, 0.0])
     d[0] += 1
     d[1] += float(r[val_i].replace(",", "")) / 1e6  # ns -> ms
@@ -33,34 +35,67 @@ for k, (n, ms) in sorted(per.items(), key=lambda kv: -kv[1][1]):
     lines.append(f"| {k} | {n} | {ms:.3f} | {ms / n:.3f} | {share} |")
 shutil.copy(os.path.join(OUT, "launches.csv"), os.path.join(PROF, f"{tag}_launches_256views.csv"))
 
-# ---- full capture of the tile kernel
-rep = os.path.join(OUT, "raster_full.ncu-rep")
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-table = list(csv.reader(io.StringIO(raw)))
-h, v = table[0], table[2]
-get = lambda key: float(v[h.index(key)].replace(",", "")) if key in h else float("nan")
-unit = lambda key: table[1][h.index(key)] if key in h else ""
+# ---- full captures of the tile kernel (exact and tolerance mode) and of the set-up side
+bench = json.loads([l for l in open(os.path.join(OUT, "bench_final.json")) if l.startswith("{")][-1])
+views = bench["details"]["views_per_step_per_gpu"]
+algorithmic = bench["roofline"]["algorithmic_bytes_per_frame"]
 scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
-dram = get("dram__bytes_read.sum") * scale.get(unit("dram__bytes_read.sum"), 1.0) + get("dram__bytes_write.sum") * scale.get(unit("dram__bytes_write.sum"), 1.0)
-dur_unit = unit("gpu__time_duration.sum")
-duration_ms = get("gpu__time_duration.sum") * {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(dur_unit, 1e-3)
-bench = json.loads(open(os.path.join(OUT, "bench_final.json")).read().strip().splitlines()[-1])
-views = bench["config"]["views_per_step_per_gpu"]
-warp_inst = get("smsp__inst_executed.sum")
-lines += ["", f"## ncu --set full of the same launch: raster_kernel<false>, {views} frames in one launch", "", "| metric | value |", "|---|---|",
-          f"| duration | {duration_ms:.3f} ms ({1000 * duration_ms / views:.1f} us per 1080p frame) |",
-          f"| dram read + write | {dram / 1e9:.3f} GB per launch = {dram / views / 1e6:.1f} MB per frame (algorithmic {bench['roofline']['algorithmic_bytes_per_frame'] / 1e6:.1f} MB) |",
-          f"| dram throughput | {get('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed'):.1f} % of peak |",
-          f"| warp instructions | {warp_inst / 1e9:.2f} G ({warp_inst / views / 1e6:.1f} M per frame), {get('smsp__thread_inst_executed_per_inst_executed.ratio'):.1f} active lanes per instruction |",
-          f"| issue slots busy | {get('smsp__issue_active.avg.pct_of_peak_sustained_active'):.1f} % |",
-          f"| warps active | {get('sm__warps_active.avg.pct_of_peak_sustained_active'):.1f} % of 64 per SM ({int(get('launch__registers_per_thread'))} registers per thread) |",
-          f"| busiest pipes | ALU {get('sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active'):.0f} %, FMA {get('sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active'):.0f} %, LSU {get('sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active'):.0f} %, XU {get('sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active'):.0f} % |",
-          f"| L1 hit rate, global loads / local (spill) loads | {get('l1tex__t_sector_pipe_lsu_mem_global_op_ld_hit_rate.pct'):.0f} % / {get('l1tex__t_sector_pipe_lsu_mem_local_op_ld_hit_rate.pct'):.0f} % |",
-          "", f"Traffic is {dram / views / bench['roofline']['algorithmic_bytes_per_frame']:.2f}x the algorithmic bytes: nothing is re-read from HBM (texture and command data hit L1/L2).",
-          "The kernel is latency bound (long-scoreboard stalls on texel, command and spill loads at 42 % occupancy), not HBM bound."]
+traffic = {}
+
+
+def capture(name):
+    raw = subprocess.run(["ncu", "-i", os.path.join(OUT, name), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    table = list(csv.reader(io.StringIO(raw)))
+    return table[0], table[1], table[2:]
+
+
+def describe(h, units, v, title, frames):
+    get = lambda key: float(v[h.index(key)].replace(",", "")) if key in h else float("nan")
+    unit = lambda key: units[h.index(key)] if key in h else ""
+    dram = get("dram__bytes_read.sum") * scale.get(unit("dram__bytes_read.sum"), 1.0) + get("dram__bytes_write.sum") * scale.get(unit("dram__bytes_write.sum"), 1.0)
+    duration_ms = get("gpu__time_duration.sum") * {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(unit("gpu__time_duration.sum"), 1e-3)
+    warp_inst = get("smsp__inst_executed.sum")
+    out = ["", f"## {title}", "", "| metric | value |", "|---|---|",
+           f"| duration | {duration_ms:.3f} ms ({1000 * duration_ms / frames:.1f} us per 1080p frame) |",
+           f"| dram read + write | {dram / 1e9:.3f} GB per launch = {dram / frames / 1e6:.1f} MB per frame (algorithmic {algorithmic / 1e6:.1f} MB: {dram / frames / algorithmic:.2f} x) |",
+           f"| dram throughput | {get('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed'):.1f} % of peak |",
+           f"| warp instructions | {warp_inst / 1e9:.2f} G ({warp_inst / frames / 1e6:.2f} M per frame), {get('smsp__thread_inst_executed_per_inst_executed.ratio'):.1f} active lanes per instruction |",
+           f"| issue slots busy | {get('smsp__issue_active.avg.pct_of_peak_sustained_active'):.1f} % |",
+           f"| warps active | {get('sm__warps_active.avg.pct_of_peak_sustained_active'):.1f} % of 64 per SM ({int(get('launch__registers_per_thread'))} registers per thread) |",
+           f"| busiest pipes | ALU {get('sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active'):.0f} %, FMA {get('sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active'):.0f} %, LSU {get('sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active'):.0f} %, XU {get('sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active'):.0f} % |",
+           f"| L1 hit rate, global loads / local (spill) loads | {get('l1tex__t_sector_pipe_lsu_mem_global_op_ld_hit_rate.pct'):.0f} % / {get('l1tex__t_sector_pipe_lsu_mem_local_op_ld_hit_rate.pct'):.0f} % |"]
+    return out, dram
+
+
+for name, key, title in (("tile_exact.ncu-rep", "tile_kernel_deferred", "ncu --set full: tile kernel, exact mode (raster_kernel<2, true> = tile_kernel_deferred)"),
+                         ("tile_tolerance.ncu-rep", "tile_kernel_tolerance", "ncu --set full: tile kernel, tolerance mode (raster_kernel<2, false> = tile_kernel_tolerance)")):
+    if not os.path.exists(os.path.join(OUT, name)):
+        continue
+    h, units, rowsv = capture(name)
+    text, dram = describe(h, units, rowsv[0], f"{title}, {views} frames in one launch", views)
+    lines += text
+    traffic[key] = {"dram_bytes_per_launch": dram, "views_per_launch": views, "source": f"profiles/{tag}_launches_summary.md (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)"}
+if os.path.exists(os.path.join(OUT, "setup_batch.ncu-rep")):
+    h, units, rowsv = capture("setup_batch.ncu-rep")
+    for v in rowsv:
+        kernel = v[h.index("Kernel Name")].replace("void ", "").split("(")[0]
+        text, _ = describe(h, units, v, f"ncu --set full: {kernel} of the same step", views)
+        lines += text
+lines += ["", "Reading: the tile kernel's DRAM traffic equals the algorithmic bytes (nothing is re-read from HBM); it is bound by instruction issue",
+          "(integer ALU pipe for the 8.8 fixed-point bilinear filter, replayed float additions in exact mode), not by HBM."]
 open(os.path.join(PROF, f"{tag}_launches_summary.md"), "w").write("\n".join(lines) + "\n")
-json.dump({"raster_kernel<false>": {"dram_bytes_per_launch": dram, "views_per_launch": views,
-                                    "source": f"profiles/{tag}_launches_summary.md (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)"}},
-          open(os.path.join(PROF, "r1_traffic.json"), "w"), indent=1)
+json.dump(traffic, open(os.path.join(PROF, "r2_traffic.json"), "w"), indent=1)
 shutil.copy(os.path.join(OUT, "bench_final.json"), os.path.join(PROF, f"{tag}_bench.json"))
+# ---- phase split of the tile kernel from the source page
+for mode in ("exact", "tolerance"):
+    rep = os.path.join(OUT, f"tile_{mode}.ncu-rep")
+    if not os.path.exists(rep):
+        continue
+    export = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
+    tmp = os.path.join(OUT, f"tile_{mode}_source.csv")
+    open(tmp, "w").write(export)
+    phases = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "tile_kernel_phases.py"), tmp, str(views), os.path.join(OUT, "raster_profiled.cu")], capture_output=True, text=True).stdout
+    open(os.path.join(PROF, f"{tag}_tile_kernel_phases_{mode}.md"), "w").write(
+        f"# {tag}: where the tile kernel's instructions go, {mode} mode (ncu --set full --import-source on, {views} x 1080p terrain views in one launch)\n\n"
+        f"Produced by `tools/tile_kernel_phases.py` from `gpurun_out/tile_{mode}.ncu-rep` (source page, CUDA + SASS).\n\n" + phases)
 print("\n".join(lines))

@@ -1,3 +1,3 @@
-python -m pytest tests -x -q -m gpu 2>&1 | tail -3
-DFPSR_ASYNC=1 python tools/tile_ab.py 256 --tiny 2>&1 | grep -E "batch of|single|tiny"
-DFPSR_ASYNC=1 python tools/sprite_world_profile.py 2>&1 | tail -3
+ncu --set full --clock-control none --import-source on -k regex:"setup_kernel|raster_kernel" -s 14 -c 3 -o gpurun_out/r2_tiny -f python tools/tiny_profile.py > gpurun_out/ncu_tiny_r2.log 2>&1
+tail -2 gpurun_out/ncu_tiny_r2.log
+cp dfpsr_b200/csrc/raster.cu gpurun_out/raster_profiled_tiny.cu

@@ -135,6 +135,7 @@ struct FrameDev {
 	// counts_kernel) and the host draws the frame again with larger pools when it next looks (renderer_end_internal / verify_frame).
 	uint32_t capCmds, capRows, capEntries, capChk, capUnits, capSortTmp;
 	int32_t checkCaps;
+	int32_t sortScheduled;           // 0: the host did not launch sort_lists_kernel (no earlier frame had a tile list long enough to need it)
 	int32_t taskCount, viewCount, blockCount;
 	uint32_t tileTotal;
 	uint32_t *slotCounts;            // per slot: command count | rows << 3
@@ -1126,12 +1127,28 @@ __global__ void __launch_bounds__(COUNTS_THREADS) counts_kernel(FrameDev frame, 
 		}
 #pragma unroll
 		for (int d = 16; d > 0; d >>= 1) { mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d)); }
-		uint32_t base = 0;
-		if (lane == 31 && inc > 0) { base = atomicAdd(&frame.totals[2], inc); }
-		base = __shfl_sync(0xffffffffu, base, 31);
-		if (lane == 0 && mx > 0) { atomicMax(&frame.totals[3], mx); }
+		// one atomic per CTA (round 1: one per warp — 2 000 same-address atomics for a single 1080p frame)
+		if (lane == 31) { warpSum[0][warp] = inc; }
+		if (lane == 0) { warpSum[1][warp] = mx; }
+		__syncthreads();
+		if (warp == 0) {
+			uint32_t total = warpSum[0][lane], most = warpSum[1][lane];
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) {
+				const uint32_t a = __shfl_up_sync(0xffffffffu, total, d);
+				if (lane >= d) { total += a; }
+			}
+#pragma unroll
+			for (int d = 16; d > 0; d >>= 1) { most = max(most, __shfl_xor_sync(0xffffffffu, most, d)); }
+			uint32_t base = 0;
+			if (lane == 31 && total > 0) { base = atomicAdd(&frame.totals[2], total); }
+			base = __shfl_sync(0xffffffffu, base, 31);
+			if (lane == 0 && most > 0) { atomicMax(&frame.totals[3], most); }
+			warpSum[0][lane] = base + total - warpSum[0][lane]; // exclusive offset of every warp of the CTA
+		}
+		__syncthreads();
 		if (i < frame.tileTotal) {
-			frame.tileOffset[i] = base + inc - c;
+			frame.tileOffset[i] = warpSum[0][warp] + inc - c;
 			frame.tileCursor[i] = 0;
 		}
 	}
@@ -1146,7 +1163,7 @@ __global__ void __launch_bounds__(COUNTS_THREADS) counts_kernel(FrameDev frame, 
 		volatile uint32_t *t = frame.totals;
 		const uint32_t commands = t[0], rows = t[1], entries = t[2], maxTile = t[3], chk = t[4], units = t[7];
 		const bool fits = commands <= frame.capCmds && rows <= frame.capRows && entries <= frame.capEntries && chk <= frame.capChk && units <= frame.capUnits
-		                  && (maxTile <= (uint32_t)SORT_SMEM || entries <= frame.capSortTmp);
+		                  && (maxTile <= (uint32_t)SORT_SMEM || entries <= frame.capSortTmp) && (maxTile <= (uint32_t)LOCAL_SORT || frame.sortScheduled != 0);
 		t[TOTAL_OVERFLOW] = fits ? 0u : 1u;
 		hostSlot[0] = commands; hostSlot[1] = rows; hostSlot[2] = entries; hostSlot[3] = maxTile; hostSlot[4] = chk; hostSlot[7] = units;
 		hostSlot[TOTAL_OVERFLOW] = fits ? 0u : 1u;
@@ -2447,7 +2464,8 @@ static int run_frame(dfpsr_renderer *r, cudaStream_t stream, bool allowAsync) {
 		// ---- pools of the second half. Without history (first frame, synchronous renderer) the host waits for the counts and sizes the
 		// pools exactly; with history they are grown ahead of the frame (counts of the last verified frame, scaled to this frame's slots
 		// and tiles, doubled) and the frame is launched in one go: the kernels check the pools themselves (FrameDev::checkCaps).
-		const bool async = allowAsync && r->historySlots > 0;
+		// a frame more than twice the size of what the history was taken from (slots or tiles) is sized from its own counts instead
+		const bool async = allowAsync && r->historySlots > 0 && (int64_t)slotTotal <= 2 * r->historySlots && (int64_t)tileTotal <= 2 * std::max<int64_t>(r->historyTiles, 1);
 		if (async) {
 			const double scale = std::max(1.0, (double)slotTotal / (double)r->historySlots) * std::max(1.0, (double)tileTotal / (double)std::max<int64_t>(r->historyTiles, 1));
 			const uint32_t *h = r->history;
@@ -2469,6 +2487,7 @@ static int run_frame(dfpsr_renderer *r, cudaStream_t stream, bool allowAsync) {
 		};
 		set_pools();
 		frame.checkCaps = async ? 1 : 0;
+		frame.sortScheduled = (!async || r->history[3] > (uint32_t)LOCAL_SORT / 2u) ? 1 : 0;
 		const int slot = (int)(r->serial & 1u);
 		const uint32_t serial = ++r->serial;
 		uint32_t *hostSlot = r->hostTotals + 16 * slot;
@@ -2506,7 +2525,10 @@ static int run_frame(dfpsr_renderer *r, cudaStream_t stream, bool allowAsync) {
 			if (r->occluded) { p.grid = r->grid; p.gridWidth = r->gridWidth; p.gridHeight = r->gridHeight; p.gridAllocW = r->gridAllocW; p.gridAllocH = r->gridAllocH; }
 			g_pendingRenderers.push_back(r); g_pendingFrames++;
 			// the grid of the unit kernel follows the most recent frame (scaled to this frame's slots), not the largest one seen
-			unitEstimate = (uint32_t)std::min(4.0e9, (double)r->recentUnits * ((double)slotTotal / (double)r->recentSlots) * 1.25) + 1u; maxTileEstimate = 0xFFFFFFFFu;
+			unitEstimate = (uint32_t)std::min(4.0e9, (double)r->recentUnits * ((double)slotTotal / (double)r->recentSlots) * 1.25) + 1u;
+			// the list sort is launched when an earlier frame came within a factor of two of needing it; a frame that needs it without
+			// having it scheduled is dropped by counts_kernel and drawn again like one that outgrew a pool
+			maxTileEstimate = r->history[3] > (uint32_t)LOCAL_SORT / 2u ? 0xFFFFFFFFu : 0u;
 			p.slots = slotTotal;
 		}
 		if (secondHalf) {

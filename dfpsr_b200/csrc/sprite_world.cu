@@ -529,7 +529,16 @@ struct dfpsr_sprite_world {
 	std::vector<dfpsr_sprite_world_op> ops;
 	// device side
 	DeviceImage diffuse, normal, light, heightBuffer;
-	std::vector<void *> cubeMaps; // one width x 6 width F32 image per shadow-casting light of the frame
+	// Shadow cube maps, one width x 6 width F32 image per shadow-casting light of the frame, in two contiguous pools:
+	//   cubeStatic   the light's PASSIVE casters only, kept from frame to frame (the reference reuses ONE cube map for all lights and
+	//                therefore renders every caster of every light in every frame; 1.5 MB per light buys not doing that)
+	//   cubeWorking  static + this frame's temporary casters: a copy of the static map with the temporary casters rendered on top
+	//                (depth-only rendering keeps the maximum, so the result does not depend on the split)
+	// staticSignature[c] says what cubeStatic[c] holds: resolution, the view's normal-to-world matrix and every passive caster
+	// (op, type, transform relative to the light), byte for byte; a light whose list differs is rendered again.
+	DeviceBuffer cubeStatic, cubeWorking;
+	int32_t cubeCapacity = 0;
+	std::vector<std::vector<uint8_t>> staticSignature;
 	DeviceBuffer copyStaging;
 	dfpsr_sprite_world(const dfpsr_ortho_system &o, int32_t shadowResolution)
 	: ortho(o), passiveSprites(MINI_UNITS_PER_TILE * 64), passiveModels(MINI_UNITS_PER_TILE * 64), shadowResolution(shadowResolution) {}
@@ -783,8 +792,11 @@ static void plan_frame(dfpsr_sprite_world *w, int32_t width, int32_t height) {
 			const I3 mn = i3(center.x - reach, center.y - reach, center.z - reach), mx = i3(center.x + reach, center.y + reach, center.z + reach);
 			w->passiveSprites.map_box(mn, mx, [&](dfpsr_sprite_instance &sprite, I3, I3, I3) { sprite_shadow(sprite); return false; });
 			w->passiveModels.map_box(mn, mx, [&](dfpsr_model_instance &model, I3, I3, I3) { model_shadow(model); return false; });
+			// temporary casters carry flag = 1: the executor keeps the cube map of a light's PASSIVE casters from frame to frame
+			const size_t firstTemporary = w->ops.size();
 			for (const dfpsr_sprite_instance &sprite : w->temporarySprites) { sprite_shadow(sprite); }
 			for (const dfpsr_model_instance &model : w->temporaryModels) { model_shadow(model); }
+			for (size_t k = firstTemporary; k < w->ops.size(); k++) { w->ops[k].flag = 1; }
 		}
 		dfpsr_sprite_world_op op = make_op(DFPSR_SW_LIGHT_POINT);
 		op.light = i; op.flag = light.shadowCasting ? 1 : 0;
@@ -842,7 +854,9 @@ static int execute_frame(dfpsr_sprite_world *w, const dfpsr_image *colorTarget, 
 	if (w->diffuse.ensure(width, height) || w->normal.ensure(width, height) || w->light.ensure(width, height) || w->heightBuffer.ensure(width, height)) { return 1; }
 	const dfpsr_image fDiffuse = w->diffuse.image(), fNormal = w->normal.image(), fLight = w->light.image(), fHeight = w->heightBuffer.image();
 	const dfpsr_ortho_camera &view = w->view();
+	int32_t shadowLights = 0;
 	for (const dfpsr_sprite_world_op &op : w->ops) { // residency of everything the frame touches
+		if (op.op == DFPSR_SW_SHADOW_CLEAR) { shadowLights++; }
 		if (op.op == DFPSR_SW_BLOCK_SPRITE || op.op == DFPSR_SW_SPRITE || op.op == DFPSR_SW_SHADOW_SPRITE) { if (g_spriteTypes[(size_t)op.typeIndex]->ensure_device(stream)) { return 1; } }
 		if (op.op == DFPSR_SW_BLOCK_MODEL || op.op == DFPSR_SW_MODEL || op.op == DFPSR_SW_SHADOW_MODEL) { if (g_modelTypes[(size_t)op.typeIndex]->ensure_device()) { return 1; } }
 		if (op.block >= 0 && ensure_block_storage(w->blocks[(size_t)op.block])) { return 1; }
@@ -879,18 +893,93 @@ static int execute_frame(dfpsr_sprite_world *w, const dfpsr_image *colorTarget, 
 	// lights of the frame
 	std::vector<dfpsr_directed_light> directed;
 	std::vector<dfpsr_point_light> points(w->pointLights.size());
-	std::vector<const dfpsr_model *> shadowModels;
-	std::vector<dfpsr_transform3d> shadowTransforms;
-	std::vector<dfpsr_camera> shadowCameras;
-	std::vector<int32_t> shadowTargets;
-	shadowModels.reserve(8); shadowTransforms.reserve(8); shadowCameras.reserve(8); shadowTargets.reserve(8); // non-null data() for a frame without casters
-	std::vector<dfpsr_image> cubeFaces;
+	// One depth-only submission: (model, transform, face camera) tuples and the cube maps they draw into (target = position of the
+	// cube in `cubes` x 6 + face).
+	struct ShadowBatch {
+		std::vector<const dfpsr_model *> models;
+		std::vector<dfpsr_transform3d> transforms;
+		std::vector<dfpsr_camera> cameras;
+		std::vector<int32_t> cubeOfTask, faceOfTask;
+		std::vector<int32_t> cubes;
+	};
+	ShadowBatch passiveBatch, temporary;
 	std::vector<int32_t> cubeOfLight(w->pointLights.size(), -1);
+	std::vector<char> usesWorking(w->pointLights.size(), 0);
+	std::vector<uint8_t> signature;
+	std::vector<const dfpsr_sprite_world_op *> passiveOps;
+	int32_t cubeCount = 0, temporaryOfLight = 0;
 	dfpsr_camera faceCameras[6];
 	float faceStretch[6] = {1, 1, 1, 1, 1, 1}; // Frobenius norm of each face camera's axis system: bounds how far worldToCamera can stretch a length
 	bool haveFaceCameras = false;
 	const int32_t res = w->shadowResolution;
+	const size_t cubeBytes = std::max<size_t>((size_t)res * res * 6 * 4, 16);
+	auto ensure_cubes = [&](int32_t count) -> int {
+		if (count <= w->cubeCapacity) { return 0; }
+		const int32_t grown = std::max(count, w->cubeCapacity * 2);
+		// growing the pools drops every cached static map (DeviceBuffer::reserve does not keep contents)
+		if (w->cubeStatic.reserve(cubeBytes * (size_t)grown) || w->cubeWorking.reserve(cubeBytes * (size_t)grown)) { return 1; }
+		w->cubeCapacity = grown;
+		w->staticSignature.assign((size_t)grown, std::vector<uint8_t>());
+		return 0;
+	};
+	auto ensure_face_cameras = [&]() -> int { // ref: spriteAPI.cpp:383, :397 — Camera::createPerspective(Transform3D(FVector3D(), ShadowCubeMapSides[s] * normalToWorld), res, res)
+		if (haveFaceCameras) { return 0; }
+		const M3 normalToWorld = m3(view.normalToWorldSpace);
+		for (int s = 0; s < 6; s++) {
+			const dfpsr_transform3d location = pod(t3(f3(0.0f, 0.0f, 0.0f), mul(cube_side(s), normalToWorld)));
+			if (dfpsr_camera_create_perspective(&faceCameras[s], &location, (float)res, (float)res, 1.0f, 0.01f, 1000.0f)) { return 1; }
+			const dfpsr_transform3d &l = faceCameras[s].location;
+			float sum = 0.0f;
+			for (int k = 0; k < 3; k++) { sum += l.xAxis[k] * l.xAxis[k] + l.yAxis[k] * l.yAxis[k] + l.zAxis[k] * l.zAxis[k]; }
+			faceStretch[s] = sqrtf(sum);
+		}
+		haveFaceCameras = true;
+		return 0;
+	};
+	// Queues the cube faces a caster can touch; returns how many. Conservative pre-filter: the model's bounding sphere against each face's
+	// cull planes. A face whose frustum the sphere misses by a margin is also missed by the exact box test (dfpsr_camera_is_box_seen inside
+	// the batch, ref: api/modelAPI.cpp:228) and by every triangle, so skipping the submission cannot change a pixel; it only spares the
+	// host the exact test for the four or five faces of the cube a caster cannot touch.
+	auto submit_caster = [&](const dfpsr_sprite_world_op &op, ShadowBatch &batch, int32_t cube) -> int32_t {
+		if (ensure_face_cameras()) { return 0; }
+		const DeviceModel &model = op.op == DFPSR_SW_SHADOW_SPRITE ? g_spriteTypes[(size_t)op.typeIndex]->shadow : g_modelTypes[(size_t)op.typeIndex]->shadow;
+		const dfpsr_transform3d &m = op.transform;
+		float centre[3], radius = 0.0f;
+		{
+			const float *mn = model.desc.minBound, *mx = model.desc.maxBound;
+			const float cx = (mn[0] + mx[0]) * 0.5f, cy = (mn[1] + mx[1]) * 0.5f, cz = (mn[2] + mx[2]) * 0.5f;
+			for (int k = 0; k < 3; k++) { centre[k] = (cx * m.xAxis[k] + cy * m.yAxis[k] + cz * m.zAxis[k]) + m.position[k]; }
+			const float hx = (mx[0] - mn[0]) * 0.5f, hy = (mx[1] - mn[1]) * 0.5f, hz = (mx[2] - mn[2]) * 0.5f;
+			const float xx = m.xAxis[0] * m.xAxis[0] + m.xAxis[1] * m.xAxis[1] + m.xAxis[2] * m.xAxis[2];
+			const float yy = m.yAxis[0] * m.yAxis[0] + m.yAxis[1] * m.yAxis[1] + m.yAxis[2] * m.yAxis[2];
+			const float zz = m.zAxis[0] * m.zAxis[0] + m.zAxis[1] * m.zAxis[1] + m.zAxis[2] * m.zAxis[2];
+			const float xy = fabsf(m.xAxis[0] * m.yAxis[0] + m.xAxis[1] * m.yAxis[1] + m.xAxis[2] * m.yAxis[2]);
+			const float xz = fabsf(m.xAxis[0] * m.zAxis[0] + m.xAxis[1] * m.zAxis[1] + m.xAxis[2] * m.zAxis[2]);
+			const float yz = fabsf(m.yAxis[0] * m.zAxis[0] + m.yAxis[1] * m.zAxis[1] + m.yAxis[2] * m.zAxis[2]);
+			// |hx X + hy Y + hz Z|^2 over the corner signs <= sum of squares + twice the absolute cross terms (exact for orthogonal axes)
+			radius = sqrtf(hx * hx * xx + hy * hy * yy + hz * hz * zz + 2.0f * (hx * hy * xy + hx * hz * xz + hy * hz * yz));
+		}
+		int32_t submitted = 0;
+		for (int s = 0; s < 6; s++) {
+			const dfpsr_camera &fc = faceCameras[s];
+			const dfpsr_transform3d &l = fc.location;
+			const float dx = centre[0] - l.position[0], dy = centre[1] - l.position[1], dz = centre[2] - l.position[2];
+			const float px = dx * l.xAxis[0] + dy * l.xAxis[1] + dz * l.xAxis[2], py = dx * l.yAxis[0] + dy * l.yAxis[1] + dz * l.yAxis[2], pz = dx * l.zAxis[0] + dy * l.zAxis[1] + dz * l.zAxis[2];
+			const float reach = radius * faceStretch[s] * 1.01f + 1e-3f; // farthest a corner can lie from the centre in camera space, with slack for rounding
+			bool outside = false;
+			for (int q = 0; q < fc.cullPlaneCount && !outside; q++) {
+				const float *pl = fc.cullPlanes[q];
+				outside = ((pl[0] * px + pl[1] * py + pl[2] * pz) - pl[3]) > reach;
+			}
+			if (outside) { continue; }
+			batch.models.push_back(&model.desc); batch.transforms.push_back(op.transform); batch.cameras.push_back(faceCameras[s]);
+			batch.cubeOfTask.push_back(cube); batch.faceOfTask.push_back(s);
+			submitted++;
+		}
+		return submitted;
+	};
 	bool blend = false;
+	if (ensure_cubes(shadowLights)) { return 1; } // before any light is looked at: growing the pools drops every cached map
 	for (const dfpsr_sprite_world_op &op : w->ops) {
 		switch (op.op) {
 		case DFPSR_SW_BLOCK_CLEAR: {
@@ -938,67 +1027,22 @@ static int execute_frame(dfpsr_sprite_world *w, const dfpsr_image *colorTarget, 
 			break;
 		}
 		case DFPSR_SW_SHADOW_CLEAR: {
-			const int32_t cube = (int32_t)cubeFaces.size() / 6;
-			cubeOfLight[(size_t)op.light] = cube;
-			while ((int32_t)w->cubeMaps.size() <= cube) {
-				void *fresh = nullptr;
-				DFPSR_CHECK_CUDA(cudaMalloc(&fresh, std::max<size_t>((size_t)res * res * 6 * 4, 16)));
-				w->cubeMaps.push_back(fresh);
-			}
-			for (int s = 0; s < 6; s++) {
-				dfpsr_image face; face.data = (float *)w->cubeMaps[(size_t)cube] + (size_t)s * res * res; face.width = res; face.height = res; face.stride = res * 4; face.packOrder = DFPSR_PACK_RGBA;
-				cubeFaces.push_back(face);
-			}
-			if (!haveFaceCameras) { // ref: spriteAPI.cpp:383, :397 — Camera::createPerspective(Transform3D(FVector3D(), ShadowCubeMapSides[s] * normalToWorld), res, res)
-				const M3 normalToWorld = m3(view.normalToWorldSpace);
-				for (int s = 0; s < 6; s++) {
-					const dfpsr_transform3d location = pod(t3(f3(0.0f, 0.0f, 0.0f), mul(cube_side(s), normalToWorld)));
-					if (dfpsr_camera_create_perspective(&faceCameras[s], &location, (float)res, (float)res, 1.0f, 0.01f, 1000.0f)) { return 1; }
-					const dfpsr_transform3d &l = faceCameras[s].location;
-					float sum = 0.0f;
-					for (int k = 0; k < 3; k++) { sum += l.xAxis[k] * l.xAxis[k] + l.yAxis[k] * l.yAxis[k] + l.zAxis[k] * l.zAxis[k]; }
-					faceStretch[s] = sqrtf(sum);
-				}
-				haveFaceCameras = true;
-			}
+			cubeOfLight[(size_t)op.light] = cubeCount++;
+			signature.clear();
+			passiveOps.clear();
+			signature.insert(signature.end(), (const uint8_t *)&res, (const uint8_t *)&res + sizeof(res));
+			signature.insert(signature.end(), (const uint8_t *)&view.normalToWorldSpace, (const uint8_t *)&view.normalToWorldSpace + sizeof(view.normalToWorldSpace));
+			temporaryOfLight = 0;
 			break;
 		}
 		case DFPSR_SW_SHADOW_SPRITE: case DFPSR_SW_SHADOW_MODEL: {
-			const DeviceModel &model = op.op == DFPSR_SW_SHADOW_SPRITE ? g_spriteTypes[(size_t)op.typeIndex]->shadow : g_modelTypes[(size_t)op.typeIndex]->shadow;
-			// Conservative pre-filter: the model's bounding sphere against each face's cull planes. A face whose frustum the sphere misses
-			// by a margin is also missed by the exact box test (dfpsr_camera_is_box_seen inside the batch, ref: api/modelAPI.cpp:228) and by
-			// every triangle, so skipping the submission cannot change a pixel; it only spares the host the exact test for the four or five
-			// faces of the cube a caster cannot touch (177 us of a 620 us frame went into those tests).
-			const dfpsr_transform3d &m = op.transform;
-			float centre[3], radius = 0.0f;
-			{
-				const float *mn = model.desc.minBound, *mx = model.desc.maxBound;
-				const float cx = (mn[0] + mx[0]) * 0.5f, cy = (mn[1] + mx[1]) * 0.5f, cz = (mn[2] + mx[2]) * 0.5f;
-				for (int k = 0; k < 3; k++) { centre[k] = (cx * m.xAxis[k] + cy * m.yAxis[k] + cz * m.zAxis[k]) + m.position[k]; }
-				const float hx = (mx[0] - mn[0]) * 0.5f, hy = (mx[1] - mn[1]) * 0.5f, hz = (mx[2] - mn[2]) * 0.5f;
-				const float xx = m.xAxis[0] * m.xAxis[0] + m.xAxis[1] * m.xAxis[1] + m.xAxis[2] * m.xAxis[2];
-				const float yy = m.yAxis[0] * m.yAxis[0] + m.yAxis[1] * m.yAxis[1] + m.yAxis[2] * m.yAxis[2];
-				const float zz = m.zAxis[0] * m.zAxis[0] + m.zAxis[1] * m.zAxis[1] + m.zAxis[2] * m.zAxis[2];
-				const float xy = fabsf(m.xAxis[0] * m.yAxis[0] + m.xAxis[1] * m.yAxis[1] + m.xAxis[2] * m.yAxis[2]);
-				const float xz = fabsf(m.xAxis[0] * m.zAxis[0] + m.xAxis[1] * m.zAxis[1] + m.xAxis[2] * m.zAxis[2]);
-				const float yz = fabsf(m.yAxis[0] * m.zAxis[0] + m.yAxis[1] * m.zAxis[1] + m.yAxis[2] * m.zAxis[2]);
-				// |hx X + hy Y + hz Z|^2 over the corner signs <= sum of squares + twice the absolute cross terms (exact for orthogonal axes)
-				radius = sqrtf(hx * hx * xx + hy * hy * yy + hz * hz * zz + 2.0f * (hx * hy * xy + hx * hz * xz + hy * hz * yz));
-			}
-			for (int s = 0; s < 6; s++) {
-				const dfpsr_camera &fc = faceCameras[s];
-				const dfpsr_transform3d &l = fc.location;
-				const float dx = centre[0] - l.position[0], dy = centre[1] - l.position[1], dz = centre[2] - l.position[2];
-				const float px = dx * l.xAxis[0] + dy * l.xAxis[1] + dz * l.xAxis[2], py = dx * l.yAxis[0] + dy * l.yAxis[1] + dz * l.yAxis[2], pz = dx * l.zAxis[0] + dy * l.zAxis[1] + dz * l.zAxis[2];
-				const float reach = radius * faceStretch[s] * 1.01f + 1e-3f; // farthest a corner can lie from the centre in camera space, with slack for rounding
-				bool outside = false;
-				for (int q = 0; q < fc.cullPlaneCount && !outside; q++) {
-					const float *pl = fc.cullPlanes[q];
-					outside = ((pl[0] * px + pl[1] * py + pl[2] * pz) - pl[3]) > reach;
-				}
-				if (outside) { continue; }
-				shadowModels.push_back(&model.desc); shadowTransforms.push_back(op.transform); shadowCameras.push_back(faceCameras[s]);
-				shadowTargets.push_back(cubeOfLight[(size_t)op.light] * 6 + s);
+			if (op.flag == 0) { // passive caster: part of the light's signature, rendered only when the signature changes
+				signature.insert(signature.end(), (const uint8_t *)&op.op, (const uint8_t *)&op.op + sizeof(op.op));
+				signature.insert(signature.end(), (const uint8_t *)&op.typeIndex, (const uint8_t *)&op.typeIndex + sizeof(op.typeIndex));
+				signature.insert(signature.end(), (const uint8_t *)&op.transform, (const uint8_t *)&op.transform + sizeof(op.transform));
+				passiveOps.push_back(&op);
+			} else {
+				temporaryOfLight += submit_caster(op, temporary, cubeOfLight[(size_t)op.light]);
 			}
 			break;
 		}
@@ -1008,7 +1052,14 @@ static int execute_frame(dfpsr_sprite_world *w, const dfpsr_image *colorTarget, 
 			memcpy(p.position, l.position, sizeof(p.position)); p.radius = l.radius; p.intensity = l.intensity; memcpy(p.colorRgb, l.color, sizeof(p.colorRgb));
 			memset(&p.shadowCubeMap, 0, sizeof(p.shadowCubeMap));
 			if (op.flag) {
-				p.shadowCubeMap.data = w->cubeMaps[(size_t)cubeOfLight[(size_t)op.light]];
+				const int32_t cube = cubeOfLight[(size_t)op.light];
+				if (w->staticSignature[(size_t)cube] != signature) { // the passive casters changed (or the slot is new): render the static map again
+					for (const dfpsr_sprite_world_op *passive : passiveOps) { submit_caster(*passive, passiveBatch, cube); }
+					passiveBatch.cubes.push_back(cube);
+					w->staticSignature[(size_t)cube] = signature;
+				}
+				if (temporaryOfLight > 0) { temporary.cubes.push_back(cube); }
+				usesWorking[(size_t)op.light] = temporaryOfLight > 0;
 				p.shadowCubeMap.width = res; p.shadowCubeMap.height = res * 6; p.shadowCubeMap.stride = res * 4; p.shadowCubeMap.packOrder = DFPSR_PACK_RGBA;
 			}
 			break;
@@ -1022,17 +1073,52 @@ static int execute_frame(dfpsr_sprite_world *w, const dfpsr_image *colorTarget, 
 	const double t0 = timing ? now() : 0.0;
 	if (flush() || flush_copies()) { return 1; }
 	const double t1 = timing ? now() : 0.0;
-	if (!cubeFaces.empty()) {
-		// every cube map of the frame: cleared to 0 and rendered by one submission (also when a light has no casters)
-		if (dfpsr_model_render_depth_batch(shadowModels.data(), shadowTransforms.data(), shadowCameras.data(), shadowTargets.data(), (int32_t)shadowModels.size(),
-		                                   cubeFaces.data(), (int32_t)cubeFaces.size(), 1, 0.0f, stream)) { return 1; }
+	// ---- shadows: static maps whose passive casters changed are rendered again (cleared, one submission); lights with temporary casters
+	// get a working copy of their static map with the temporary casters rendered on top (one copy per run of neighbouring maps, one
+	// submission without clearing). A frame whose passive casters did not change and that has no temporary caster renders no shadow at all.
+	auto run_batch = [&](ShadowBatch &batch, const DeviceBuffer &pool, int32_t clear) -> int {
+		if (batch.cubes.empty()) { return 0; }
+		std::vector<int32_t> position((size_t)w->cubeCapacity, -1);
+		std::vector<dfpsr_image> faces;
+		for (size_t k = 0; k < batch.cubes.size(); k++) {
+			position[(size_t)batch.cubes[k]] = (int32_t)k;
+			for (int f = 0; f < 6; f++) {
+				dfpsr_image face;
+				face.data = (uint8_t *)pool.ptr + cubeBytes * (size_t)batch.cubes[k] + (size_t)f * res * res * 4;
+				face.width = res; face.height = res; face.stride = res * 4; face.packOrder = DFPSR_PACK_RGBA;
+				faces.push_back(face);
+			}
+		}
+		std::vector<int32_t> targets(batch.models.size());
+		for (size_t t = 0; t < targets.size(); t++) { targets[t] = position[(size_t)batch.cubeOfTask[t]] * 6 + batch.faceOfTask[t]; }
+		batch.models.reserve(1); batch.transforms.reserve(1); batch.cameras.reserve(1); targets.reserve(1); // non-null data() for a batch without casters
+		return dfpsr_model_render_depth_batch(batch.models.data(), batch.transforms.data(), batch.cameras.data(), targets.data(), (int32_t)batch.models.size(),
+		                                      faces.data(), (int32_t)faces.size(), clear, 0.0f, stream);
+	};
+	const size_t shadowTasks = passiveBatch.models.size() + temporary.models.size();
+	if (run_batch(passiveBatch, w->cubeStatic, 1)) { return 1; }
+	if (!temporary.cubes.empty()) {
+		if (g_pendingFrames > 0 && verify_pending_frames()) { return 1; } // the copies below are not queued through DFPSR_LAUNCH
+		for (size_t k = 0; k < temporary.cubes.size();) {
+			size_t run = 1;
+			while (k + run < temporary.cubes.size() && temporary.cubes[k + run] == temporary.cubes[k] + (int32_t)run) { run++; }
+			const size_t offset = cubeBytes * (size_t)temporary.cubes[k];
+			DFPSR_CHECK_CUDA(cudaMemcpyAsync((uint8_t *)w->cubeWorking.ptr + offset, (const uint8_t *)w->cubeStatic.ptr + offset, cubeBytes * run, cudaMemcpyDeviceToDevice, stream));
+			k += run;
+		}
+		if (run_batch(temporary, w->cubeWorking, 0)) { return 1; }
+	}
+	for (size_t i = 0; i < points.size(); i++) {
+		if (cubeOfLight[i] >= 0 && points[i].shadowCubeMap.width > 0) {
+			points[i].shadowCubeMap.data = (uint8_t *)(usesWorking[i] ? w->cubeWorking.ptr : w->cubeStatic.ptr) + cubeBytes * (size_t)cubeOfLight[i];
+		}
 	}
 	const int32_t worldCenter[2] = {find_world_center(w, width, height).x, find_world_center(w, width, height).y};
 	dfpsr_ortho_view lightView;
 	dfpsr_ortho_camera_light_view(&view, &lightView);
 	const double t2 = timing ? now() : 0.0;
 	const int status = dfpsr_light_frame(&lightView, worldCenter, blend ? colorTarget : nullptr, &fDiffuse, &fLight, &fNormal, &fHeight, directed.data(), (int32_t)directed.size(), points.data(), (int32_t)points.size(), stream);
-	if (timing) { fprintf(stderr, "sprite world frame: sprites+copies %.0f us, shadow batch (%zu tasks) %.0f us, light frame launch %.0f us\n", t1 - t0, shadowModels.size(), t2 - t1, now() - t2); }
+	if (timing) { fprintf(stderr, "sprite world frame: sprites+copies %.0f us, shadow batches (%zu tasks, %zu static + %zu working maps) %.0f us, light frame launch %.0f us\n", t1 - t0, shadowTasks, passiveBatch.cubes.size(), temporary.cubes.size(), t2 - t1, now() - t2); }
 	return status;
 }
 
@@ -1255,7 +1341,7 @@ int dfpsr_sprite_world_create(dfpsr_sprite_world **out, const dfpsr_ortho_system
 int dfpsr_sprite_world_destroy(dfpsr_sprite_world *world) {
 	if (!world) { return 0; }
 	for (Block &b : world->blocks) { if (b.dDiffuse) { cudaFree(b.dDiffuse); cudaFree(b.dNormal); cudaFree(b.dHeight); } }
-	for (void *cube : world->cubeMaps) { cudaFree(cube); }
+	world->cubeStatic.release(); world->cubeWorking.release();
 	for (DeviceImage *im : {&world->diffuse, &world->normal, &world->light, &world->heightBuffer}) { if (im->ptr) { cudaFree(im->ptr); } }
 	world->copyStaging.release();
 	delete world;

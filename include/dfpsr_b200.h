@@ -429,7 +429,7 @@ enum {
 	DFPSR_SW_LIGHT_CLEAR = 7,   /* no directed light: light buffer = 0 */
 	DFPSR_SW_LIGHT_DIRECTED = 8,/* light = index into the directed lights; flag = 1 overwrite, 0 add */
 	DFPSR_SW_SHADOW_CLEAR = 9,  /* cube map of point light `light` = 0 */
-	DFPSR_SW_SHADOW_SPRITE = 10,/* 6 x model_renderDepth of sprite type typeIndex's shadow model with `transform` (relative to the light) */
+	DFPSR_SW_SHADOW_SPRITE = 10,/* 6 x model_renderDepth of sprite type typeIndex's shadow model with `transform` (relative to the light); flag = 1: a temporary caster */
 	DFPSR_SW_SHADOW_MODEL = 11, /* the same for model type typeIndex */
 	DFPSR_SW_LIGHT_POINT = 12,  /* addPointLight of light `light`; flag = 1 with its shadow cube map */
 	DFPSR_SW_BLEND = 13         /* blendLight into the colour target */

@@ -196,8 +196,26 @@ def cpu_baseline(views, seconds=12.0):
     elapsed = time.perf_counter() - t0
     threads = ref.lib.ref_thread_count()
     ref.free_all()
-    return {"value": n / elapsed, "unit": "frames/s", "cores": max(min(threads - 1, 12), 1), "kind": "reference",
-            "sample": f"{n} orbit views in {elapsed:.1f} s through the unmodified reference (oracle/_ref, g++ -O2 SSE2 build, {threads} hardware threads): image_fill x2 + renderer_begin/giveTask/end per view"}
+    out = {"value": n / elapsed, "unit": "frames/s", "cores": max(min(threads - 1, 12), 1), "kind": "reference",
+           "sample": f"{n} orbit views in {elapsed:.1f} s through the unmodified reference (oracle/_ref, g++ -O2 SSE2 build, {threads} hardware threads): image_fill x2 + renderer_begin/giveTask/end per view"}
+    # BASELINE.md section 3 also asks for the -march=native flavour: the -mavx2 build of the same sources (what native gives on this pool's hosts)
+    try:
+        if refbind.available("avx2") and "avx2" in open("/proc/cpuinfo").read():
+            wide = refbind.Ref("avx2")
+            tex2 = wide.texture(sc["texture"], 5)
+            model2 = wide.model(sc["points"], sc["polygons"], diffuse=tex2)
+            col2, dep2 = wide.rgba(shape=(HEIGHT, WIDTH)), wide.f32(shape=(HEIGHT, WIDTH))
+            for i in range(3):
+                wide.lib.ref_terrain_frame(model2, C.byref(ident), col2, dep2, C.byref(scenes.orbit_camera(i, WIDTH, HEIGHT, frames_per_lap=views)))
+            t0, m = time.perf_counter(), 0
+            while time.perf_counter() - t0 < seconds / 3:
+                wide.lib.ref_terrain_frame(model2, C.byref(ident), col2, dep2, C.byref(scenes.orbit_camera(m % views, WIDTH, HEIGHT, frames_per_lap=views)))
+                m += 1
+            out["avx2_build_value"] = m / (time.perf_counter() - t0)
+            wide.free_all()
+    except Exception as exc:  # a second flavour must never break the baseline
+        out["avx2_build_error"] = repr(exc)
+    return out
 
 
 def view_hashes(color, depth, index):

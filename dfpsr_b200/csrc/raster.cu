@@ -136,6 +136,8 @@ struct FrameDev {
 	uint32_t capCmds, capRows, capEntries, capChk, capUnits, capSortTmp;
 	int32_t checkCaps;
 	int32_t sortScheduled;           // 0: the host did not launch sort_lists_kernel (no earlier frame had a tile list long enough to need it)
+	uint32_t *hostSlot;              // mapped pinned memory: the frame's totals and verdict for the host (device alias)
+	uint32_t serial;
 	int32_t taskCount, viewCount, blockCount;
 	uint32_t tileTotal;
 	uint32_t *slotCounts;            // per slot: command count | rows << 3
@@ -163,6 +165,20 @@ static const int TOTAL_OVERFLOW = 10, TOTAL_TICKET = 11, TOTAL_WORDS = 12;
 // True when the frame's second half must not run: its counts exceed the pools it was launched with.
 __device__ __forceinline__ bool frame_dropped(const FrameDev &frame) {
 	return frame.checkCaps != 0 && frame.totals[TOTAL_OVERFLOW] != 0u;
+}
+// The verdict itself, from the totals of the finished counting pass (see counts_kernel / setup_kernel<true>).
+__device__ __forceinline__ bool frame_fits(const FrameDev &frame) {
+	const uint32_t *t = frame.totals;
+	const uint32_t commands = t[0], rows = t[1], entries = t[2], maxTile = t[3], chk = t[4], units = t[7];
+	return commands <= frame.capCmds && rows <= frame.capRows && entries <= frame.capEntries && chk <= frame.capChk && units <= frame.capUnits
+	       && (maxTile <= (uint32_t)SORT_SMEM || entries <= frame.capSortTmp) && (maxTile <= (uint32_t)LOCAL_SORT || frame.sortScheduled != 0);
+}
+__device__ __forceinline__ void publish_totals(const FrameDev &frame, bool fits) {
+	const uint32_t *t = frame.totals;
+	volatile uint32_t *hostSlot = frame.hostSlot;
+	hostSlot[0] = t[0]; hostSlot[1] = t[1]; hostSlot[2] = t[2]; hostSlot[3] = t[3]; hostSlot[4] = t[4]; hostSlot[7] = t[7];
+	hostSlot[TOTAL_OVERFLOW] = fits ? 0u : 1u;
+	hostSlot[TOTAL_TICKET] = frame.serial; // no fences: the host reads the slot after an event behind the publishing kernel, when its writes are visible
 }
 
 // ------------------------------------------------------------------------------------------------ projection
@@ -614,13 +630,31 @@ __device__ __forceinline__ int32_t task_of_block(const TaskParams *tasks, int32_
 	return lo;
 }
 
-// Appends `index` to the lists of the tiles of one tile row that pixels [minL, maxR) touch.
+// Appends `index` to the lists of the tiles of one tile row that pixels [minL, maxR) touch. Four tiles at a time: the atomics that hand out
+// the list positions return values, and a loop of one atomic + dependent store per tile is a chain of L2 round trips (a row that crosses
+// the whole 1080p target touches 60 tiles; that chain was the longest thread of a single frame's set-up).
 __device__ __forceinline__ void emit_tile_row(const FrameDev &frame, uint32_t tileBase, int32_t tilesX, int32_t ty, int32_t minL, int32_t maxR, uint32_t index) {
 	if (maxR <= minL) { return; }
-	for (int32_t tx = minL / TILE_W; tx <= (maxR - 1) / TILE_W; tx++) {
-		uint32_t tile = tileBase + (uint32_t)(ty * tilesX + tx);
-		uint32_t pos = atomicAdd(&frame.tileCursor[tile], 1u);
-		frame.tileList[frame.tileOffset[tile] + pos] = index;
+	const int32_t first = minL / TILE_W, last = (maxR - 1) / TILE_W;
+	if (first == last) { // the common case of small triangles: one tile
+		const uint32_t tile = tileBase + (uint32_t)(ty * tilesX + first);
+		const uint32_t position = atomicAdd(&frame.tileCursor[tile], 1u);
+		frame.tileList[frame.tileOffset[tile] + position] = index;
+		return;
+	}
+	for (int32_t tx = first; tx <= last; tx += 4) {
+		const int32_t n = min(4, last - tx + 1);
+		uint32_t position[4], offset[4];
+#pragma unroll
+		for (int k = 0; k < 4; k++) {
+			if (k < n) {
+				const uint32_t tile = tileBase + (uint32_t)(ty * tilesX + tx + k);
+				position[k] = atomicAdd(&frame.tileCursor[tile], 1u);
+				offset[k] = frame.tileOffset[tile];
+			}
+		}
+#pragma unroll
+		for (int k = 0; k < 4; k++) { if (k < n) { frame.tileList[offset[k] + position[k]] = index; } }
 	}
 }
 
@@ -708,7 +742,15 @@ __global__ void __launch_bounds__(SETUP_THREADS, SETUP_MIN_BLOCKS) setup_kernel(
 	__shared__ uint32_t sBigCount, sChkCount, sUnitCount, sItemBase, sUnitBase, sChkBase;
 	__shared__ uint32_t sUnitEnd[SETUP_THREADS]; // emit pass: inclusive prefix of tile rows over the queued commands
 	chain_enter();
-	if (EMIT && frame_dropped(frame)) { return; }
+	if (EMIT && frame.checkCaps != 0) {
+		// the counting pass is complete: every CTA derives the verdict itself; the first one tells the host and the kernels behind this one
+		const bool fits = frame_fits(frame);
+		if (blockIdx.x == 0 && threadIdx.x == 0) {
+			frame.totals[TOTAL_OVERFLOW] = fits ? 0u : 1u;
+			publish_totals(frame, fits);
+		}
+		if (!fits) { return; }
+	}
 	{
 		if (threadIdx.x == 0) { sChkCount = 0; sUnitCount = 0; }
 		int32_t t = frame.blockTask ? frame.blockTask[blockIdx.x] : task_of_block(frame.tasks, frame.taskCount, (int32_t)blockIdx.x);
@@ -946,8 +988,11 @@ __global__ void __launch_bounds__(SETUP_THREADS, SETUP_MIN_BLOCKS) setup_kernel(
 // The units of the whole batch are spread over the whole grid, so one 1080p frame (about 60 k units) already fills the machine.
 // SPLIT: two threads per unit (adjacent lanes), one per row pair of the tile row — twice the threads and half the serial chain per thread for
 // frames whose units do not fill the machine anyway (one 1080p terrain frame has 15 k units); the bins of the two row pairs meet in a shuffle.
+#ifndef BIG_UNITS_THREADS
+#define BIG_UNITS_THREADS 64 // measured on the 256-view batch: 4.27 us per frame against 4.69 (256 threads) and 4.45 (128)
+#endif
 template <bool SPLIT>
-__global__ void __launch_bounds__(256) big_units_kernel(FrameDev frame) {
+__global__ void __launch_bounds__(BIG_UNITS_THREADS) big_units_kernel(FrameDev frame) {
 	chain_enter();
 	if (frame_dropped(frame)) { return; }
 	// The grid is sized by the host from an earlier frame's unit count (it does not wait for this frame's): CTAs stride over the units
@@ -1045,7 +1090,7 @@ __global__ void __launch_bounds__(SETUP_THREADS) occlude_existing_kernel(FrameDe
 //               behind megabytes of finished frames travelling to the host and stall the next chunk's set-up for milliseconds).
 static const int SCAN_ITEMS = 8;
 static const int COUNTS_THREADS = 1024;
-__global__ void __launch_bounds__(COUNTS_THREADS) counts_kernel(FrameDev frame, volatile uint32_t *hostSlot, uint32_t serial) {
+__global__ void __launch_bounds__(COUNTS_THREADS) counts_kernel(FrameDev frame) {
 	__shared__ uint32_t warpSum[2][32];
 	__shared__ uint32_t carry[2];
 	__shared__ bool sLast;
@@ -1152,23 +1197,17 @@ __global__ void __launch_bounds__(COUNTS_THREADS) counts_kernel(FrameDev frame, 
 			frame.tileCursor[i] = 0;
 		}
 	}
-	// ---- the last CTA to arrive sees every total
+	// ---- a frame whose host side waits for the counts: the last CTA to arrive sees every total and publishes them. An asynchronous frame
+	// needs none of this (no fence, no ticket): every CTA of setup_kernel<true> derives the verdict from the finished totals itself and
+	// its first CTA publishes it.
+	if (frame.checkCaps != 0) { return; }
 	__threadfence();
 	__syncthreads();
 	if (threadIdx.x == 0) { sLast = atomicAdd(&frame.totals[TOTAL_TICKET], 1u) == gridDim.x - 1u; }
 	__syncthreads();
 	if (!sLast) { return; }
 	__threadfence();
-	if (threadIdx.x == 0) {
-		volatile uint32_t *t = frame.totals;
-		const uint32_t commands = t[0], rows = t[1], entries = t[2], maxTile = t[3], chk = t[4], units = t[7];
-		const bool fits = commands <= frame.capCmds && rows <= frame.capRows && entries <= frame.capEntries && chk <= frame.capChk && units <= frame.capUnits
-		                  && (maxTile <= (uint32_t)SORT_SMEM || entries <= frame.capSortTmp) && (maxTile <= (uint32_t)LOCAL_SORT || frame.sortScheduled != 0);
-		t[TOTAL_OVERFLOW] = fits ? 0u : 1u;
-		hostSlot[0] = commands; hostSlot[1] = rows; hostSlot[2] = entries; hostSlot[3] = maxTile; hostSlot[4] = chk; hostSlot[7] = units;
-		hostSlot[TOTAL_OVERFLOW] = fits ? 0u : 1u;
-		hostSlot[TOTAL_TICKET] = serial; // no fences: the host reads the slot after the event behind this kernel, when its writes are visible
-	}
+	if (threadIdx.x == 0) { publish_totals(frame, true); }
 }
 
 // Restores ascending command order in the lists that hold more than LOCAL_SORT entries (shorter ones are sorted in registers by raster_kernel).
@@ -2491,8 +2530,9 @@ static int run_frame(dfpsr_renderer *r, cudaStream_t stream, bool allowAsync) {
 		const int slot = (int)(r->serial & 1u);
 		const uint32_t serial = ++r->serial;
 		uint32_t *hostSlot = r->hostTotals + 16 * slot;
+		frame.hostSlot = r->hostTotalsDevice + 16 * slot; frame.serial = serial;
 		DFPSR_LAUNCH_CHAINED(setup_kernel<false>, blockTotal, SETUP_THREADS, 0, stream, frame);
-		DFPSR_LAUNCH_CHAINED(counts_kernel, 1 + (tileTotal + COUNTS_THREADS - 1) / COUNTS_THREADS, COUNTS_THREADS, 0, stream, frame, r->hostTotalsDevice + 16 * slot, serial);
+		DFPSR_LAUNCH_CHAINED(counts_kernel, 1 + (tileTotal + COUNTS_THREADS - 1) / COUNTS_THREADS, COUNTS_THREADS, 0, stream, frame);
 		if (timing) { tLaunched = host_now_us(); }
 		uint32_t unitEstimate, maxTileEstimate;
 		bool secondHalf = true;
@@ -2517,7 +2557,6 @@ static int run_frame(dfpsr_renderer *r, cudaStream_t stream, bool allowAsync) {
 				set_pools();
 			}
 		} else {
-			DFPSR_CHECK_CUDA(cudaEventRecord(r->counted[slot], stream));
 			PendingFrame &p = r->pending;
 			p.active = true; p.serial = serial; p.slot = slot; p.stream = stream;
 			p.views = r->views; p.tasks = r->tasks; p.textures = r->textures;
@@ -2533,12 +2572,13 @@ static int run_frame(dfpsr_renderer *r, cudaStream_t stream, bool allowAsync) {
 		}
 		if (secondHalf) {
 			DFPSR_LAUNCH_CHAINED(setup_kernel<true>, blockTotal, SETUP_THREADS, 0, stream, frame);
+			if (async) { DFPSR_CHECK_CUDA(cudaEventRecord(r->counted[slot], stream)); } // setup_kernel<true> publishes the verdict of an asynchronous frame
 			if (unitEstimate > 0 || async) {
 				// frames with few units (a single 1080p frame: 15 k) are latency-bound: two threads per unit; large batches keep one.
 				// The kernels stride over the units the device counted, so an estimate only sizes the grid.
 				const uint32_t most = (uint32_t)sm_count() * 64u;
-				if (unitEstimate <= (uint32_t)sm_count() * 2048u) { DFPSR_LAUNCH_CHAINED(big_units_kernel<true>, std::min(most, (2u * unitEstimate + 255u) / 256u), 256, 0, stream, frame); }
-				else { DFPSR_LAUNCH_CHAINED(big_units_kernel<false>, std::min(most * 4u, (unitEstimate + 255u) / 256u), 256, 0, stream, frame); }
+				if (unitEstimate <= (uint32_t)sm_count() * 2048u) { DFPSR_LAUNCH_CHAINED(big_units_kernel<true>, std::min(most, (2u * unitEstimate + BIG_UNITS_THREADS - 1u) / BIG_UNITS_THREADS), BIG_UNITS_THREADS, 0, stream, frame); }
+				else { DFPSR_LAUNCH_CHAINED(big_units_kernel<false>, std::min(most * 4u, (unitEstimate + BIG_UNITS_THREADS - 1u) / BIG_UNITS_THREADS), BIG_UNITS_THREADS, 0, stream, frame); }
 			}
 			if (maxTileEstimate > (uint32_t)LOCAL_SORT) { DFPSR_LAUNCH_CHAINED(sort_lists_kernel, (tileTotal + SORT_THREADS - 1) / SORT_THREADS, SORT_THREADS, 0, stream, frame); }
 		}

@@ -180,4 +180,27 @@ int dfpsr_session_render_views_host(dfpsr_session *session, int32_t slot, const 
 	return 0;
 }
 
+// ref: implementation/gui/DsrWindow.cpp:255-281 DsrWindow::showCanvas — the low-resolution canvas is magnified by whole pixels into the
+// back-end's canvas (its native pack order, exact pixel size: partial pixels at the right / bottom are cut, anything beyond the source is
+// transparent black) and handed to the window system. The back-end's canvas is host memory, so the hand-off is: block magnify on the device
+// into a staging image of the canvas's size and pack order, then ONE device-to-host copy into the caller's canvas rows.
+int dfpsr_canvas_show(const dfpsr_image *deviceCanvas, int32_t pixelScale, void *hostCanvas, int32_t hostStrideBytes, int32_t hostWidth, int32_t hostHeight, int32_t hostPackOrder, void *stream) {
+	DFPSR_REQUIRE(deviceCanvas != nullptr && deviceCanvas->data != nullptr && hostCanvas != nullptr, "canvas_show: null argument");
+	DFPSR_REQUIRE(pixelScale >= 1 && hostWidth > 0 && hostHeight > 0 && hostStrideBytes >= hostWidth * 4, "canvas_show: pixel scale %d, canvas %d x %d, stride %d", pixelScale, hostWidth, hostHeight, hostStrideBytes);
+	cudaStream_t s = as_stream(stream);
+	const uint8_t *source = (const uint8_t *)deviceCanvas->data;
+	size_t sourcePitch = (size_t)deviceCanvas->stride;
+	static thread_local DeviceBuffer staging;
+	if (pixelScale > 1 || hostPackOrder != deviceCanvas->packOrder || deviceCanvas->width != hostWidth || deviceCanvas->height != hostHeight) {
+		const int32_t pitch = ((hostWidth * 4 + 255) / 256) * 256;
+		if (staging.reserve((size_t)pitch * (size_t)hostHeight)) { return 1; }
+		const dfpsr_image target{staging.ptr, hostWidth, hostHeight, pitch, hostPackOrder};
+		if (dfpsr_filter_block_magnify(&target, deviceCanvas, pixelScale, pixelScale, stream)) { return 1; }
+		source = (const uint8_t *)staging.ptr; sourcePitch = (size_t)pitch;
+	} else if (verify_pending_frames()) { return 1; } // the canvas may be a frame in flight: the copy below is not queued through DFPSR_LAUNCH
+	DFPSR_CHECK_CUDA(cudaMemcpy2DAsync(hostCanvas, (size_t)hostStrideBytes, source, sourcePitch, (size_t)hostWidth * 4, (size_t)hostHeight, cudaMemcpyDeviceToHost, s));
+	DFPSR_CHECK_CUDA(cudaStreamSynchronize(s)); // the window system reads the canvas next
+	return 0;
+}
+
 } // extern "C"

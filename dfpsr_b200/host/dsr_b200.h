@@ -861,6 +861,13 @@ inline void filter_mapRgbaU8(ImageRgbaU8 &target, int32_t deviceOp, const int32_
 	dfpsr_image t = target.pod(), s = source.pod();
 	b200_check(dfpsr_filter_map(&t, deviceOp, params, paramCount, image_exists(source) ? &s : nullptr, startX, startY, b200_stream())); target.touchedByDevice();
 }
+// ref: implementation/gui/DsrWindow.cpp:255-281 DsrWindow::showCanvas — what a window back-end calls with its own (host) canvas memory:
+// block magnify by pixelScale into the canvas's pack order on the device, one copy into the canvas rows.
+inline void b200_showCanvas(const ImageRgbaU8 &canvas, int32_t pixelScale, void *hostCanvas, int32_t hostStrideBytes, int32_t hostWidth, int32_t hostHeight, PackOrderIndex hostPackOrder) {
+	if (!image_exists(canvas)) { return; }
+	dfpsr_image c = canvas.pod();
+	b200_check(dfpsr_canvas_show(&c, pixelScale, hostCanvas, hostStrideBytes, hostWidth, hostHeight, (int32_t)hostPackOrder, b200_stream()));
+}
 inline void filter_blockMagnify(ImageRgbaU8 &target, const ImageRgbaU8 &source, int32_t pixelWidth, int32_t pixelHeight) {
 	dfpsr_image t = target.pod(), s = source.pod();
 	b200_check(dfpsr_filter_block_magnify(&t, &s, pixelWidth, pixelHeight, b200_stream())); target.touchedByDevice();

@@ -133,6 +133,7 @@ SIGNATURES = {
     "dfpsr_import_ply": (i32, [C.c_char_p, sz, i32, P(abi.Transform3D), P(abi.ImportedModel)]),
     "dfpsr_import_dmf1": (i32, [C.c_char_p, sz, i32, P(abi.ImportedModel)]),
     "dfpsr_import_free": (None, [P(abi.ImportedModel)]),
+    "dfpsr_canvas_show": (i32, [P(abi.Image), i32, vp, i32, i32, i32, i32, vp]),
     "dfpsr_filter_map_program": (i32, [P(abi.Image), C.c_char_p, vp, i32, i32, i32, vp]),
     "dfpsr_peer_alloc": (i32, [P(vp), sz, vp]),
     "dfpsr_peer_free": (i32, [vp]),

@@ -498,6 +498,11 @@ int dfpsr_filter_resize(const dfpsr_image *target, const dfpsr_image *source, in
 int dfpsr_filter_map_program(const dfpsr_image *target, const char *body, const dfpsr_image *sources, int32_t sourceCount, int32_t startX, int32_t startY, void *stream);
 /* ref: api/filterAPI.cpp:759-782 filter_mapRgbaU8 / filter_generateRgbaU8 with one of the pre-compiled device ops above. */
 int dfpsr_filter_map(const dfpsr_image *target, int32_t op, const int32_t *params, int32_t paramCount, const dfpsr_image *source, int32_t startX, int32_t startY, void *stream);
+/* ref: implementation/gui/DsrWindow.cpp:255-281 DsrWindow::showCanvas + the back-end's canvas (windowManagers/X11Window.cpp:838-858): the
+ * device canvas is block-magnified by pixelScale into the window's canvas — HOST memory of hostWidth x hostHeight pixels in the window
+ * system's pack order (BGRA on X11 and Win32) — with the rules of filter_blockMagnify (partial pixels cut, transparent black beyond the
+ * source) and arrives there with one device-to-host copy; the call returns when the canvas rows are complete. */
+int dfpsr_canvas_show(const dfpsr_image *deviceCanvas, int32_t pixelScale, void *hostCanvas, int32_t hostStrideBytes, int32_t hostWidth, int32_t hostHeight, int32_t hostPackOrder, void *stream);
 /* ref: api/filterAPI.cpp:724-757, :872-876 filter_blockMagnify. */
 int dfpsr_filter_block_magnify(const dfpsr_image *target, const dfpsr_image *source, int32_t pixelWidth, int32_t pixelHeight, void *stream);
 

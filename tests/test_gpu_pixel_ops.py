@@ -336,3 +336,19 @@ def test_filter_resize_pack_orders(cuda, oracle, packs):
         e, es = np.zeros((nh, nw), np.uint32), np.zeros(nw * 61 + 4, np.uint32)
         oracle.orc_filter_resize(C.byref(OI(e, packs[1])), C.byref(OI(src, packs[0])), abi.SAMPLER_LINEAR, 0, orcbind.ptr(es))
         assert_same_u32(host_u32(tt), e, f"resize to {nw}x{nh} packs={packs}")
+
+
+def test_canvas_show_is_block_magnify_into_host_memory(cuda, oracle):
+    """dfpsr_canvas_show (DsrWindow::showCanvas): the device canvas arrives in the window's host canvas magnified by whole pixels, in the
+    window's pack order, partial pixels cut and the rest transparent black — exactly filter_blockMagnify of the reference."""
+    rng = np.random.default_rng(12)
+    src = rng.integers(0, 2 ** 32, (37, 53), dtype=np.uint32)
+    ts = lib.to_device(src)
+    for scale, (cw, ch), pack in ((3, (160, 100), abi.PACK_BGRA), (2, (106, 74), abi.PACK_RGBA), (1, (53, 37), abi.PACK_RGBA), (1, (53, 37), abi.PACK_ARGB), (4, (90, 200), abi.PACK_ABGR)):
+        stride = cw * 4 + 32
+        host = np.full((ch, stride // 4), 0xDEADBEEF, np.uint32)
+        lib.check(cuda.dfpsr_canvas_show(C.byref(IM(ts)), scale, host.ctypes.data, stride, cw, ch, pack, lib.stream_ptr()))
+        expected = np.zeros((ch, cw), np.uint32)
+        oracle.orc_filter_block_magnify(C.byref(OI(expected, pack)), C.byref(OI(src)), scale, scale)
+        assert np.array_equal(host[:, :cw], expected), (scale, cw, ch, pack)
+        assert (host[:, cw:] == 0xDEADBEEF).all()  # the row padding of the window's canvas is not touched

@@ -98,6 +98,10 @@ struct TaskParams {
 	int32_t view;
 	int32_t filter, diffuseIndex, lightIndex; // texture table indices or -1
 	int32_t depthOnly;
+	// dfpsr_renderer_give_tasks: the whole-model tests of model_render_threaded (api/modelAPI.cpp:228-234) run on the device, once per set-up CTA
+	int32_t cullOnDevice;
+	int32_t gridOffset;              // first float of this submission's snapshot of the occlusion grid in FrameDev::gridSnapshots, -1: no occluders
+	float minBound[3], maxBound[3];
 	dfpsr_transform3d modelToWorld;
 	dfpsr_camera camera;
 };
@@ -158,6 +162,8 @@ struct FrameDev {
 	int32_t smallRows;               // triangles up to this many rows (and SMALL_WIDTH columns) are scan-converted by their set-up thread
 	const float *occlusionGrid;      // 16-pixel cells of the farthest depth at which something can still be visible; null = no occluders
 	int32_t gridWidth, gridHeight, gridStride;
+	const float *gridSnapshots;      // the grid as it was at every dfpsr_renderer_give_tasks call that found occluders (gridStride x gridRows floats each)
+	int32_t gridRows;
 };
 
 static const int TOTAL_OVERFLOW = 10, TOTAL_TICKET = 11, TOTAL_WORDS = 12;
@@ -609,6 +615,60 @@ __global__ void __launch_bounds__(256) top_rows_kernel(dfpsr_image depth, int32_
 	out[cell] = perspective ? 1.0f / extreme : extreme;
 }
 
+// ------------------------------------------------------------------------------------------------ broad phase on the device
+// ref: api/modelAPI.cpp:228-234 — a model is skipped when its bounding box lies outside of the cull frustum (Camera::isBoxSeen,
+// implementation/render/Camera.h:202-217) or behind the occluders given so far (renderer_isBoxVisible, api/rendererAPI.cpp:302-351, :538-543).
+// The same IEEE operations in the same order as the host versions (dfpsr_camera_is_box_seen in host_math.cpp, box_visible below), so a
+// frame submitted through dfpsr_renderer_give_tasks makes exactly the decisions a loop of dfpsr_renderer_give_task makes. One thread per CTA.
+__device__ bool task_is_culled(const FrameDev &frame, const TaskParams &task) {
+	const dfpsr_camera &c = task.camera;
+	const dfpsr_transform3d &m = task.modelToWorld, &l = c.location;
+	float cs[8][3];
+#pragma unroll
+	for (int p = 0; p < 8; p++) { // corner p takes the maximum on axis k when bit k of p is set (x: bit 0, y: bit 1, z: bit 2)
+		const float px = (p & 1) ? task.maxBound[0] : task.minBound[0], py = (p & 2) ? task.maxBound[1] : task.minBound[1], pz = (p & 4) ? task.maxBound[2] : task.minBound[2];
+		const float wx = (px * m.xAxis[0] + py * m.yAxis[0] + pz * m.zAxis[0]) + m.position[0];
+		const float wy = (px * m.xAxis[1] + py * m.yAxis[1] + pz * m.zAxis[1]) + m.position[1];
+		const float wz = (px * m.xAxis[2] + py * m.yAxis[2] + pz * m.zAxis[2]) + m.position[2];
+		const float dx = wx - l.position[0], dy = wy - l.position[1], dz = wz - l.position[2];
+		cs[p][0] = dx * l.xAxis[0] + dy * l.xAxis[1] + dz * l.xAxis[2];
+		cs[p][1] = dx * l.yAxis[0] + dy * l.yAxis[1] + dz * l.yAxis[2];
+		cs[p][2] = dx * l.zAxis[0] + dy * l.zAxis[1] + dz * l.zAxis[2];
+	}
+	for (int s = 0; s < c.cullPlaneCount; s++) { // isBoxSeen == 0: some plane has every corner outside (a NaN distance counts as outside)
+		const float *pl = c.cullPlanes[s];
+		bool anyInside = false;
+#pragma unroll
+		for (int p = 0; p < 8; p++) { anyInside = anyInside || ((((pl[0] * cs[p][0]) + (pl[1] * cs[p][1]) + (pl[2] * cs[p][2])) - pl[3]) <= 0.0f); }
+		if (!anyInside) { return true; }
+	}
+	if (task.gridOffset < 0) { return false; }
+	// renderer_isBoxVisible against the snapshot of the grid: visible when the box's closest corner is nearer than some cell it may touch
+	const ViewDev &view = frame.views[task.view];
+	const float *grid = frame.gridSnapshots + task.gridOffset;
+	int32_t left = 0, top = 0, right = 0, bottom = 0;
+	float closest = INFINITY;
+#pragma unroll
+	for (int p = 0; p < 8; p++) {
+		const PPoint q = camera_to_screen(c, cs[p][0], cs[p][1], cs[p][2]);
+		const int32_t x = (int32_t)(q.fx / 256), y = (int32_t)(q.fy / 256); // ref: api/rendererAPI.cpp:89-95 getPixelBoundFromProjection
+		if (p == 0) { left = x; top = y; right = x + 1; bottom = y + 1; }
+		else { left = min(left, x); top = min(top, y); right = max(right, x + 1); bottom = max(bottom, y + 1); }
+		if (q.csz < closest) { closest = q.csz; }
+	}
+	const int32_t gridWidth = (view.width + (CELL_SIZE - 1)) / CELL_SIZE, gridHeight = (view.height + (CELL_SIZE - 1)) / CELL_SIZE;
+	const CellBound cells = outer_cell_bound(left, top, right, bottom, gridWidth, gridHeight);
+	for (int32_t cy = cells.y0; cy < cells.y1; cy++) {
+		for (int32_t cx = cells.x0; cx < cells.x1; cx++) {
+			// image_readPixel_clamp on the grid as allocated; a grid that does not exist reads 0
+			float cell = 0.0f;
+			if (frame.gridStride > 0 && frame.gridRows > 0) { cell = grid[(size_t)min(max(cy, 0), frame.gridRows - 1) * frame.gridStride + min(max(cx, 0), frame.gridStride - 1)]; }
+			if (closest < cell) { return false; }
+		}
+	}
+	return true;
+}
+
 // ------------------------------------------------------------------------------------------------ set-up kernel
 
 // A command whose tile counting (counting pass) or rows + tile entries (emit pass) are produced cooperatively by one warp.
@@ -758,6 +818,19 @@ __global__ void __launch_bounds__(SETUP_THREADS, SETUP_MIN_BLOCKS) setup_kernel(
 		if (threadIdx.x == 0) { sBigCount = 0; }
 	}
 	__syncthreads();
+	if (task.cullOnDevice) { // uniform per CTA: the model's bounding box against the cull frustum and the occluders, like model_render_threaded
+		__shared__ int sCulled;
+		if (threadIdx.x == 0) { sCulled = task_is_culled(frame, task) ? 1 : 0; }
+		__syncthreads();
+		if (sCulled) {
+			if (!EMIT) {
+				const int32_t culledSlot = task.slotBase + ((int32_t)blockIdx.x - task.blockBase) * SETUP_THREADS + (int32_t)threadIdx.x;
+				if (culledSlot < task.slotBase + task.slotCount) { frame.slotCounts[culledSlot] = 0u; }
+				if (threadIdx.x == 0) { frame.blockCmds[blockIdx.x] = 0u; frame.blockRows[blockIdx.x] = 0u; }
+			}
+			return;
+		}
+	}
 	const ViewDev &view = frame.views[task.view];
 	const int32_t width = view.width, height = view.height, clipTop = view.clipTop, clipBottom = view.clipBottom;
 	const int32_t tilesX = view.tilesX;
@@ -1059,6 +1132,12 @@ __global__ void __launch_bounds__(SETUP_THREADS) occlude_existing_kernel(FrameDe
 	}
 	__syncthreads();
 	if (task.filter != DFPSR_FILTER_SOLID) { return; }
+	if (task.cullOnDevice) { // a model the broad phase drops has no commands that could occlude
+		__shared__ int sCulled;
+		if (threadIdx.x == 0) { sCulled = task_is_culled(frame, task) ? 1 : 0; }
+		__syncthreads();
+		if (sCulled) { return; }
+	}
 	const ViewDev &view = frame.views[task.view];
 	const int32_t local = ((int32_t)blockIdx.x - task.blockBase) * SETUP_THREADS + threadIdx.x;
 	if (local >= task.slotCount) { return; }
@@ -2200,7 +2279,7 @@ struct PendingFrame {
 	std::vector<ViewDev> views;
 	std::vector<TaskParams> tasks;
 	std::vector<TexDev> textures;
-	std::vector<float> grid;
+	std::vector<float> grid, gridSnapshots;
 	bool depthOnly = false, occluded = false, exact = true;
 	int32_t gridWidth = 0, gridHeight = 0, gridAllocW = 0, gridAllocH = 0;
 	int32_t slots = 0;
@@ -2234,6 +2313,8 @@ struct dfpsr_renderer {
 	int32_t gridWidth = 0, gridHeight = 0, gridAllocW = 0, gridAllocH = 0;
 	bool occluded = false;
 	DeviceBuffer dGrid;
+	std::vector<float> gridSnapshots; // the grid at every dfpsr_renderer_give_tasks call of the frame that found occluders (device broad phase)
+	DeviceBuffer dGridSnapshots;
 
 	~dfpsr_renderer();
 };
@@ -2289,6 +2370,7 @@ static int renderer_begin_internal(dfpsr_renderer *r, bool depthOnly) {
 	r->tasks.clear();
 	r->uploadCount = 0;
 	r->textures.clear();
+	r->gridSnapshots.clear();
 	if (!r->hostTotals) {
 		DFPSR_CHECK_CUDA(cudaHostAlloc((void **)&r->hostTotals, 2 * 16 * sizeof(uint32_t), cudaHostAllocMapped));
 		DFPSR_CHECK_CUDA(cudaHostGetDevicePointer((void **)&r->hostTotalsDevice, r->hostTotals, 0));
@@ -2319,6 +2401,7 @@ static int add_model_task(dfpsr_renderer *r, int32_t view, const dfpsr_model *mo
 	task.depthOnly = r->depthOnly ? 1 : 0;
 	task.diffuseIndex = diffuseIndex;
 	task.lightIndex = lightIndex;
+	task.gridOffset = -1; // tested on the host by the caller
 	return 0;
 }
 
@@ -2370,7 +2453,7 @@ static void forget_pending(dfpsr_renderer *r) {
 dfpsr_renderer::~dfpsr_renderer() {
 	if (pending.active) { cudaEventSynchronize(counted[pending.slot]); forget_pending(this); }
 	for (auto &b : uploads) { b.release(); }
-	DeviceBuffer *all[] = {&dTasks, &dViews, &projected, &slotCounts, &blockCmds, &blockRows, &tileCount, &tileOffset, &tileCursor, &cmds, &rows, &tileList, &chk, &sortTmp, &bigItems, &bigUnits, &dGrid};
+	DeviceBuffer *all[] = {&dTasks, &dViews, &projected, &slotCounts, &blockCmds, &blockRows, &tileCount, &tileOffset, &tileCursor, &cmds, &rows, &tileList, &chk, &sortTmp, &bigItems, &bigUnits, &dGrid, &dGridSnapshots};
 	for (auto *b : all) { b->release(); }
 	if (hostTotals) { cudaFreeHost(hostTotals); }
 	for (cudaEvent_t e : counted) { if (e) { cudaEventDestroy(e); } }
@@ -2500,6 +2583,12 @@ static int run_frame(dfpsr_renderer *r, cudaStream_t stream, bool allowAsync) {
 			frame.occlusionGrid = (const float *)r->dGrid.ptr;
 			frame.gridWidth = r->gridWidth; frame.gridHeight = r->gridHeight; frame.gridStride = r->gridAllocW;
 		}
+		if (!r->gridSnapshots.empty()) { // the broad phase of dfpsr_renderer_give_tasks tests against the grid as it was at each of those calls
+			if (r->dGridSnapshots.reserve(r->gridSnapshots.size() * sizeof(float) + 16)) { return 1; }
+			DFPSR_CHECK_CUDA(cudaMemcpyAsync(r->dGridSnapshots.ptr, r->gridSnapshots.data(), r->gridSnapshots.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
+			frame.gridSnapshots = (const float *)r->dGridSnapshots.ptr;
+			frame.gridStride = r->gridAllocW; frame.gridRows = r->gridAllocH;
+		}
 		// ---- pools of the second half. Without history (first frame, synchronous renderer) the host waits for the counts and sizes the
 		// pools exactly; with history they are grown ahead of the frame (counts of the last verified frame, scaled to this frame's slots
 		// and tiles, doubled) and the frame is launched in one go: the kernels check the pools themselves (FrameDev::checkCaps).
@@ -2561,6 +2650,7 @@ static int run_frame(dfpsr_renderer *r, cudaStream_t stream, bool allowAsync) {
 			p.active = true; p.serial = serial; p.slot = slot; p.stream = stream;
 			p.views = r->views; p.tasks = r->tasks; p.textures = r->textures;
 			p.depthOnly = r->depthOnly; p.occluded = r->occluded; p.exact = r->exact;
+			p.gridSnapshots = r->gridSnapshots;
 			if (r->occluded) { p.grid = r->grid; p.gridWidth = r->gridWidth; p.gridHeight = r->gridHeight; p.gridAllocW = r->gridAllocW; p.gridAllocH = r->gridAllocH; }
 			g_pendingRenderers.push_back(r); g_pendingFrames++;
 			// the grid of the unit kernel follows the most recent frame (scaled to this frame's slots), not the largest one seen
@@ -2618,13 +2708,13 @@ static int verify_frame(dfpsr_renderer *r) {
 	}
 	// ---- the frame was dropped on the device: nothing of it (or behind it) may still be running while its inputs are laid out again
 	DFPSR_CHECK_CUDA(cudaStreamSynchronize(p.stream));
-	std::swap(r->views, p.views); std::swap(r->tasks, p.tasks); std::swap(r->textures, p.textures);
+	std::swap(r->views, p.views); std::swap(r->tasks, p.tasks); std::swap(r->textures, p.textures); std::swap(r->gridSnapshots, p.gridSnapshots);
 	std::swap(r->depthOnly, p.depthOnly); std::swap(r->occluded, p.occluded); std::swap(r->exact, p.exact);
 	if (r->occluded) { std::swap(r->grid, p.grid); std::swap(r->gridWidth, p.gridWidth); std::swap(r->gridHeight, p.gridHeight); std::swap(r->gridAllocW, p.gridAllocW); std::swap(r->gridAllocH, p.gridAllocH); }
 	const bool occludedFrame = r->occluded;
 	const int status = run_frame(r, p.stream, false);
 	if (occludedFrame) { std::swap(r->grid, p.grid); std::swap(r->gridWidth, p.gridWidth); std::swap(r->gridHeight, p.gridHeight); std::swap(r->gridAllocW, p.gridAllocW); std::swap(r->gridAllocH, p.gridAllocH); }
-	std::swap(r->views, p.views); std::swap(r->tasks, p.tasks); std::swap(r->textures, p.textures);
+	std::swap(r->views, p.views); std::swap(r->tasks, p.tasks); std::swap(r->textures, p.textures); std::swap(r->gridSnapshots, p.gridSnapshots);
 	std::swap(r->depthOnly, p.depthOnly); std::swap(r->occluded, p.occluded); std::swap(r->exact, p.exact);
 	r->historySlots = std::max<int64_t>(r->historySlots, 1); // run_frame refreshed the history from the redrawn frame
 	static const bool verbose = getenv("DFPSR_END_TIMING") != nullptr;
@@ -2748,6 +2838,42 @@ int dfpsr_renderer_give_task(dfpsr_renderer *renderer, const dfpsr_model *model,
 	// ref: api/modelAPI.cpp:229-234 — whole models hidden by the occluders given so far are skipped
 	if (renderer->occluded && dfpsr_camera_is_box_seen(camera, model->minBound, model->maxBound, modelToWorld) && !box_visible(renderer, model->minBound, model->maxBound, modelToWorld, camera)) { return 0; }
 	return add_model_task(renderer, 0, model, modelToWorld, camera);
+}
+
+// Many models in one call, the whole-model tests on the device (a broad phase for scenes of thousands of models, where
+// one host test per model per frame serialises the submission). ref: api/modelAPI.cpp:214-281, api/rendererAPI.cpp:302-351, :538-543.
+int dfpsr_renderer_give_tasks(dfpsr_renderer *renderer, const dfpsr_model *models, const dfpsr_transform3d *modelToWorld, int32_t count, const dfpsr_camera *camera, void *stream) {
+	DFPSR_REQUIRE(renderer != nullptr && camera != nullptr, "renderer_giveTasks: null argument");
+	DFPSR_REQUIRE(renderer->receiving, "Cannot call renderer_giveTasks before renderer_begin!");
+	(void)stream;
+	if (count <= 0) { return 0; }
+	DFPSR_REQUIRE(models != nullptr && modelToWorld != nullptr, "renderer_giveTasks: null models");
+	dfpsr_renderer *r = renderer;
+	const ViewDev &v = r->views[0];
+	if (v.width <= 0 || v.height <= 0) { return 0; }
+	int32_t gridOffset = -1;
+	if (r->occluded) { // the models of this call are tested against the occluders given SO FAR, like renderer_giveTask does at its call
+		gridOffset = (int32_t)r->gridSnapshots.size();
+		r->gridSnapshots.insert(r->gridSnapshots.end(), r->grid.begin(), r->grid.end());
+	}
+	for (int32_t i = 0; i < count; i++) {
+		const dfpsr_model &model = models[i];
+		if (model.polygonCount <= 0) { continue; }
+		const int32_t diffuseIndex = r->depthOnly ? -1 : register_texture(r, &model.diffuse);
+		const int32_t lightIndex = r->depthOnly ? -1 : register_texture(r, &model.light);
+		DFPSR_REQUIRE(diffuseIndex != -2 && lightIndex != -2, "more than %d textures in one frame", MAX_TEXTURES);
+		r->tasks.emplace_back();
+		TaskParams &task = r->tasks.back();
+		task.points = model.points; task.polygons = model.polygons;
+		task.pointCount = model.pointCount; task.slotCount = model.polygonCount * 2;
+		task.view = 0;
+		task.modelToWorld = modelToWorld[i]; task.camera = *camera;
+		task.filter = model.filter; task.depthOnly = r->depthOnly ? 1 : 0;
+		task.diffuseIndex = diffuseIndex; task.lightIndex = lightIndex;
+		task.cullOnDevice = 1; task.gridOffset = gridOffset;
+		memcpy(task.minBound, model.minBound, sizeof(task.minBound)); memcpy(task.maxBound, model.maxBound, sizeof(task.maxBound));
+	}
+	return 0;
 }
 
 int dfpsr_renderer_give_task_triangles(dfpsr_renderer *renderer, const dfpsr_triangle *triangles, int32_t count, const dfpsr_texture *diffuse, const dfpsr_texture *light, int32_t filter, const dfpsr_camera *camera, void *stream) {
@@ -2942,7 +3068,12 @@ int dfpsr_renderer_occlude_from_existing_triangles(dfpsr_renderer *renderer, voi
 	memset(&frame, 0, sizeof(frame));
 	frame.tasks = (const TaskParams *)r->dTasks.ptr; frame.views = (const ViewDev *)r->dViews.ptr;
 	frame.taskCount = (int32_t)r->tasks.size(); frame.viewCount = 1; frame.blockCount = blockTotal;
-	frame.gridWidth = r->gridWidth; frame.gridHeight = r->gridHeight; frame.gridStride = r->gridAllocW;
+	frame.gridWidth = r->gridWidth; frame.gridHeight = r->gridHeight; frame.gridStride = r->gridAllocW; frame.gridRows = r->gridAllocH;
+	if (!r->gridSnapshots.empty()) { // tasks of dfpsr_renderer_give_tasks are tested against their own snapshot of the grid here as well
+		if (r->dGridSnapshots.reserve(r->gridSnapshots.size() * sizeof(float) + 16)) { return 1; }
+		DFPSR_CHECK_CUDA(cudaMemcpyAsync(r->dGridSnapshots.ptr, r->gridSnapshots.data(), r->gridSnapshots.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+		frame.gridSnapshots = (const float *)r->dGridSnapshots.ptr;
+	}
 	if (launch_projection(r, frame, s)) { return 1; }
 	DFPSR_LAUNCH(occlude_existing_kernel, blockTotal, SETUP_THREADS, 0, s, frame, (float *)r->dGrid.ptr);
 	DFPSR_CHECK_CUDA(cudaMemcpyAsync(r->grid.data(), r->dGrid.ptr, r->grid.size() * sizeof(float), cudaMemcpyDeviceToHost, s));

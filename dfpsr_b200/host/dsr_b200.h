@@ -536,6 +536,21 @@ inline void model_render_threaded(const Model &model, const Transform3D &modelTo
 	for (const B200Part &part : model->parts) { renderer->keep(part.devicePolygons); renderer->keep(part.diffuseMap.buffer); renderer->keep(part.lightMap.buffer); }
 }
 inline void renderer_giveTask(Renderer &renderer, const Model &model, const Transform3D &modelToWorldTransform, const Camera &camera) { model_render_threaded(model, modelToWorldTransform, renderer, camera); }
+// Many models at once (no counterpart in the reference): the per-model tests of model_render_threaded — isBoxSeen and, with occluders, renderer_isBoxVisible —
+// run on the device instead of one after the other on the host; the frame is identical to a loop of renderer_giveTask.
+inline void renderer_giveTasks(Renderer &renderer, const std::vector<Model> &models, const std::vector<Transform3D> &modelToWorldTransforms, const Camera &camera) {
+	if (!renderer) { throwError("renderer_giveTasks: renderer does not exist"); }
+	if (models.size() != modelToWorldTransforms.size()) { throwError("renderer_giveTasks: one transform per model"); }
+	std::vector<dfpsr_model> parts;
+	std::vector<dfpsr_transform3d> transforms;
+	for (size_t i = 0; i < models.size(); i++) {
+		if (!models[i]) { continue; }
+		for (const dfpsr_model &m : b200_device_models(models[i])) { parts.push_back(m); transforms.push_back(b200_pod(modelToWorldTransforms[i])); }
+		renderer->keep(models[i]->devicePoints);
+		for (const B200Part &part : models[i]->parts) { renderer->keep(part.devicePolygons); renderer->keep(part.diffuseMap.buffer); renderer->keep(part.lightMap.buffer); }
+	}
+	if (!parts.empty()) { b200_check(dfpsr_renderer_give_tasks(renderer->handle, parts.data(), transforms.data(), (int32_t)parts.size(), &camera.pod, b200_stream())); }
+}
 // ref: api/rendererAPI.h:108-129 renderer_giveTask_triangle with points the caller projected (ProjectedPoint, 40 bytes)
 inline void renderer_giveTask_triangle(Renderer &renderer, const dfpsr_projected_point &posA, const dfpsr_projected_point &posB, const dfpsr_projected_point &posC,
   const FVector4D &colorA, const FVector4D &colorB, const FVector4D &colorC, const FVector4D &texCoordA, const FVector4D &texCoordB, const FVector4D &texCoordC,

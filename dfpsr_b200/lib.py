@@ -60,6 +60,7 @@ SIGNATURES = {
     "dfpsr_renderer_set_clip_rows": (i32, [vp, i32, i32]),
     "dfpsr_model_render_depth_batch": (i32, [vp, vp, vp, vp, i32, vp, i32, i32, f32, vp]),
     "dfpsr_renderer_give_task": (i32, [vp, P(abi.Model), P(abi.Transform3D), P(abi.Camera), vp]),
+    "dfpsr_renderer_give_tasks": (i32, [vp, vp, vp, i32, P(abi.Camera), vp]),
     "dfpsr_renderer_give_task_triangles": (i32, [vp, vp, i32, P(abi.Texture), P(abi.Texture), i32, P(abi.Camera), vp]),
     "dfpsr_renderer_end": (i32, [vp, vp]),
     "dfpsr_renderer_last_command_count": (i32, [vp, P(i64), vp]),

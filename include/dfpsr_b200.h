@@ -240,6 +240,11 @@ int dfpsr_renderer_is_box_visible(const dfpsr_renderer *renderer, const float mi
  * until the frame has been drawn (the reference copies the vertex data at submission; dsr_b200.h keeps the buffers alive for its
  * callers). A frame may use up to 4096 textures. */
 int dfpsr_renderer_give_task(dfpsr_renderer *renderer, const dfpsr_model *model, const dfpsr_transform3d *modelToWorld, const dfpsr_camera *camera, void *stream);
+/* Many models in one call with the whole-model tests ON THE DEVICE (a broad phase for scenes of thousands of models):
+ * the tests model_render_threaded makes per model on the host — Camera::isBoxSeen (api/modelAPI.cpp:228) and, when the renderer has occluders,
+ * renderer_isBoxVisible (:229-234; api/rendererAPI.cpp:302-351) against the occluders given BEFORE this call — run once per set-up CTA of
+ * each model with the same arithmetic, so the frame is identical to a loop of dfpsr_renderer_give_task. models / modelToWorld: HOST arrays. */
+int dfpsr_renderer_give_tasks(dfpsr_renderer *renderer, const dfpsr_model *models, const dfpsr_transform3d *modelToWorld, int32_t count, const dfpsr_camera *camera, void *stream);
 /* ref: api/rendererAPI.h:108-116 renderer_giveTask_triangle, batched: `triangles` is a HOST array. */
 int dfpsr_renderer_give_task_triangles(dfpsr_renderer *renderer, const dfpsr_triangle *triangles, int32_t count, const dfpsr_texture *diffuse, const dfpsr_texture *light, int32_t filter, const dfpsr_camera *camera, void *stream);
 /* ref: api/rendererAPI.h:131 renderer_end → CommandQueue::execute (implementation/render/renderCore.cpp:449-480):

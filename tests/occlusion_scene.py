@@ -130,3 +130,36 @@ def run_cuda(cuda, sc):
     lib.check(cuda.dfpsr_renderer_last_command_count(r, C.byref(count), s))
     lib.check(cuda.dfpsr_renderer_destroy(r))
     return {"color": tc.cpu().numpy().view(np.uint32), "depth": td.cpu().numpy(), "visible": visible, "commands": count.value}
+
+
+def run_cuda_batched(cuda, sc):
+    """The same frame with the models handed over through dfpsr_renderer_give_tasks (whole-model tests on the device): one call for the
+    models up to the occludeFromExistingTriangles call, one for the rest — the occluders do not change inside either group."""
+    from dfpsr_b200 import abi, lib
+    cam = lib.camera(sc["camera"])
+    tc, td = lib.to_device(sc["color0"]), lib.to_device(sc["depth0"])
+    wall = lib.DeviceModel(*sc["wall"])
+    models = [lib.DeviceModel(m["points"], m["polygons"]) for m in sc["models"]]
+    r = C.c_void_p()
+    s = lib.stream_ptr()
+    lib.check(cuda.dfpsr_renderer_create(C.byref(r)))
+    lib.check(cuda.dfpsr_renderer_begin(r, C.byref(lib.image(tc)), C.byref(lib.image(td))))
+    lib.check(cuda.dfpsr_renderer_give_task(r, C.byref(wall.desc), C.byref(sc["wall_transform"]), C.byref(cam), s))
+    lo, hi = sc["occluder_box"]
+    lib.check(cuda.dfpsr_renderer_occlude_from_box(r, lo.ctypes.data, hi.ctypes.data, C.byref(sc["wall_transform"]), C.byref(cam)))
+    if sc["top_rows"]:
+        lib.check(cuda.dfpsr_renderer_occlude_from_top_rows(r, C.byref(cam), s))
+    split = sc["existing_after"] + 1 if 0 <= sc["existing_after"] < len(models) else len(models)
+    for first, last in ((0, split), (split, len(models))):
+        n = last - first
+        if n > 0:
+            descs = (abi.Model * n)(*[models[i].desc for i in range(first, last)])
+            transforms = (abi.Transform3D * n)(*[sc["models"][i]["transform"] for i in range(first, last)])
+            lib.check(cuda.dfpsr_renderer_give_tasks(r, descs, transforms, n, C.byref(cam), s))
+        if first == 0 and 0 <= sc["existing_after"] < len(models):
+            lib.check(cuda.dfpsr_renderer_occlude_from_existing_triangles(r, s))
+    lib.check(cuda.dfpsr_renderer_end(r, s))
+    count = C.c_int64()
+    lib.check(cuda.dfpsr_renderer_last_command_count(r, C.byref(count), s))
+    lib.check(cuda.dfpsr_renderer_destroy(r))
+    return {"color": tc.cpu().numpy().view(np.uint32), "depth": td.cpu().numpy(), "commands": count.value}

@@ -388,7 +388,10 @@ def test_session_render_views_host_pipeline(cuda, oracle):
         assert_same_u32(bits(depth[v].numpy()), bits(ed), f"view {v} depth")
 
 
-@pytest.mark.parametrize("variant", [dict(), dict(top_rows=True), dict(perspective=False), dict(seed=11, width=333, height=201, top_rows=True)])
+OCCLUSION_VARIANTS = [dict(), dict(top_rows=True), dict(perspective=False), dict(seed=11, width=333, height=201, top_rows=True)]
+
+
+@pytest.mark.parametrize("variant", OCCLUSION_VARIANTS)
 def test_occlusion_grid_matches_oracle(cuda, oracle, variant):
     """renderer_occludeFromBox / occludeFromExistingTriangles / occludeFromTopRows / isBoxVisible (ref: api/rendererAPI.cpp:181-477):
     same visibility answers as the oracle, same command count, same pixels."""
@@ -397,6 +400,19 @@ def test_occlusion_grid_matches_oracle(cuda, oracle, variant):
     expected = occlusion_scene.run_oracle(oracle, sc)
     got = occlusion_scene.run_cuda(cuda, sc)
     assert got["visible"] == expected["visible"]
+    assert got["commands"] == expected["commands"]
+    assert_same_u32(bits(got["depth"]), bits(expected["depth"]), "depth")
+    assert_same_u32(got["color"], expected["color"], "colour")
+
+
+@pytest.mark.parametrize("variant", OCCLUSION_VARIANTS)
+def test_device_broad_phase_equals_host_tests(cuda, oracle, variant):
+    """dfpsr_renderer_give_tasks: isBoxSeen and renderer_isBoxVisible per model on the device (against the occluders given before the call)
+    draw the same frame, with the same number of commands, as one renderer_giveTask per model with the tests on the host."""
+    import occlusion_scene
+    sc = occlusion_scene.build(**variant)
+    expected = occlusion_scene.run_oracle(oracle, sc)
+    got = occlusion_scene.run_cuda_batched(cuda, sc)
     assert got["commands"] == expected["commands"]
     assert_same_u32(bits(got["depth"]), bits(expected["depth"]), "depth")
     assert_same_u32(got["color"], expected["color"], "colour")

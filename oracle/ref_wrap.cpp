@@ -29,6 +29,15 @@
 
 using namespace dsr;
 
+// The SDK's terrain example, compiled where it lies: its scene generators (bump / light / diffuse / colour maps from the three media images,
+// the grid model) are called by ref_sdk_terrain_scene below exactly in the order of its dsrMain (SDK/terrain/main.cpp:343-373). The window
+// loop of the example is never entered; DSR_MAIN_CALLER is defined away so that the example does not bring its own main().
+namespace sdk_terrain {
+#undef DSR_MAIN_CALLER
+#define DSR_MAIN_CALLER(X)
+#include "SDK/terrain/main.cpp"
+}
+
 // The reference's heap (DFPSR/base/heap.cpp:671-684) writes a new allocation's header through an AllocationHeader
 // pointer, which slices off HeapHeader's own fields (destructor, useCount, flags, binIndex): it relies on every
 // 16 MiB arena from operator new being fresh zero pages from mmap. Inside a long-lived Python process glibc raises
@@ -697,6 +706,36 @@ int ref_import_ply(const char *filename, int flipX, const dfpsr_transform3d *axi
 	ensureStarted();
 	Model model = importer_loadModel(String(filename), flipX != 0, toTransform(axisConversion));
 	g_models.push_back(model);
+	g_importNames.resize(g_models.size());
+	return (int)g_models.size() - 1;
+}
+
+// The scene of SDK/terrain built by the SDK's own code from the media folder's HeightMap.png, Cloud.png and RampIsland.png
+// (SDK/terrain/main.cpp:343-373). Returns the model id; *textureId receives the id of its 5-level colour texture.
+int ref_sdk_terrain_scene(const char *mediaPath, int *textureId) {
+	ensureStarted();
+	using namespace sdk_terrain;
+	const String folder = String(mediaPath);
+	ImageU8 heightMap = image_get_red(image_load_RgbaU8(file_combinePaths(folder, U"HeightMap.png")));
+	ImageU8 genericCloudPattern = image_get_red(image_load_RgbaU8(file_combinePaths(folder, U"Cloud.png")));
+	ImageRgbaU8 heightRamp = image_load_RgbaU8(file_combinePaths(folder, U"RampIsland.png"));
+	const int32_t colorMapWidth = image_getWidth(heightMap) * tileColorDensity, colorMapHeight = image_getHeight(heightMap) * tileColorDensity;
+	ImageF32 bumpMap = image_create_F32(colorMapWidth, colorMapHeight);
+	generateBumpMap(bumpMap, heightMap, genericCloudPattern);
+	ImageF32 lightMap = image_create_F32(colorMapWidth, colorMapHeight);
+	FVector3D sunDirection = normalize(FVector3D(0.3f, -1.0f, 1.0f));
+	float ambient = 0.2f;
+	generateLightMap(lightMap, bumpMap, sunDirection, ambient);
+	ImageRgbaU8 diffuseMap = image_create_RgbaU8(colorMapWidth, colorMapHeight);
+	generateDiffuseMap(diffuseMap, bumpMap, heightRamp);
+	TextureRgbaU8 colorTexture = texture_create_RgbaU8(colorMapWidth, colorMapHeight, 5);
+	ImageRgbaU8 colorMap = texture_getMipLevelImage(colorTexture, 0);
+	updateColorMap(colorMap, diffuseMap, lightMap);
+	texture_generatePyramid(colorTexture);
+	Model ground = createGrid(heightMap, colorTexture);
+	g_textures.push_back(colorTexture);
+	if (textureId) { *textureId = (int)g_textures.size() - 1; }
+	g_models.push_back(ground);
 	g_importNames.resize(g_models.size());
 	return (int)g_models.size() - 1;
 }

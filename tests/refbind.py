@@ -76,6 +76,7 @@ def load(flavour="scalar"):
         "ref_world_move_camera_in_pixels": (None, [i, i, i]), "ref_world_set_camera_direction_index": (None, [i, i]),
         "ref_world_find_ground_at_pixel": (None, [i, i, i, i, p]),
         "ref_import_ply": (i, [C.c_char_p, i, T]), "ref_import_dmf1": (i, [C.c_char_p, i]),
+        "ref_sdk_terrain_scene": (i, [C.c_char_p, p]),
         "ref_model_dump_counts": (None, [i, p]), "ref_model_dump": (None, [i, p, p, p]), "ref_model_dump_name": (None, [i, i, C.c_char_p, i]),
         "ref_world_draw": (None, [i, i]), "ref_world_read_buffers": (None, [i, p, p, p, p]),
     }

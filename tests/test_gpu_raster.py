@@ -226,6 +226,21 @@ def test_terrain_1080p_golden(cuda):
         assert sha(c) == entry["color_sha256"], f"frame {entry['frame']} colour"
 
 
+def test_sdk_terrain_real_media_golden(cuda):
+    """BASELINE config 1 on the SDK's REAL assets: SDK/terrain/media through the SDK's own generators (tests/golden/make_sdk_golden.py), rendered at
+    1920x1080 in exact mode: sha256 of colour and depth equal the unmodified reference's."""
+    golden = json.load(open(os.path.join(os.path.dirname(GOLDEN), "sdk_terrain.json")))
+    data = np.load(os.path.join(os.path.dirname(GOLDEN), "sdk_terrain_scene.npz"))
+    polygons = data["polygons"].view(abi.POLYGON_DTYPE).reshape(-1)
+    assert len(data["points"]) == golden["points"] == 4096 and len(polygons) == golden["polygons"]
+    scene = CudaScene(data["points"], polygons, diffuse_level0=data["texture"], diffuse_levels=int(data["levels"]))
+    for entry in golden["frames"]:
+        cam = scenes.orbit_camera(entry["frame"], 1920, 1080)
+        c, d = scene.render_cuda(cuda, cam, np.zeros((1080, 1920), np.uint32), np.zeros((1080, 1920), np.float32))
+        assert sha(d) == entry["depth_sha256"], f"frame {entry['frame']} depth"
+        assert sha(c) == entry["color_sha256"], f"frame {entry['frame']} colour"
+
+
 def test_tiny_triangles_4k_golden(cuda):
     """BASELINE config 3 (2 M tiny vertex-coloured triangles at 3840x2160) against the reference's hashes."""
     golden = json.load(open(GOLDEN))["tiny_4k"]

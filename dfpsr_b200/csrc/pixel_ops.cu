@@ -578,15 +578,81 @@ __global__ void __launch_bounds__(256) resize_kernel(Img target, Img source, Res
 // the same integers in ONE pass: a thread owns 4 columns x FUSED_ROWS target rows, forms each needed row of the temporary in registers
 // (a row is reused by about targetHeight / sourceHeight consecutive target rows) and never writes it to memory:
 // 4 B x (source + target) of traffic instead of 4 B x (source + 3 x temporary + target).
-static const int FUSED_ROWS = 16;
+#ifndef RESIZE_UP_ROWS
+#define RESIZE_UP_ROWS 16
+#endif
+static const int FUSED_ROWS = RESIZE_UP_ROWS;
 
 #ifndef RESIZE_UP_MIN_BLOCKS
 #define RESIZE_UP_MIN_BLOCKS 6 // 42 registers, 48 warps per SM: 115 us for 4096^2 -> 8192^2 against 121 us unbounded and 128 us at 8 (tools/resize_sweep.py)
 #endif
+// The common thread of the fused up-scale: four whole columns, source and target in the same pack order. Everything that depends on the
+// column only is prepared once — the two clamped source columns and the 16-bit weight pair of each target column — so that a row of the
+// temporary costs eight loads and four lerps and nothing else. A column whose right weight is zero reads its left pixel twice with the
+// weights (65535, 1): (a * 65535 + a) >> 16 == a, the value lerp16_lanes returns for that case, without a select in the loop.
+__device__ __forceinline__ void resize_up_whole_columns(const Img &target, const Img &source, const ResizeParams &rp, int32_t x0, int32_t yFirst) {
+	const int32_t last = source.width - 1;
+	int32_t left[4], right[4];
+	uint32_t weights[4];
+#pragma unroll
+	for (int i = 0; i < 4; i++) {
+		const int32_t readX = rp.startX + (x0 + i) * rp.offsetX;
+		const uint32_t sampleX = (uint32_t)(readX < 0 ? 0 : readX), ratio = sampleX & 65535u;
+		left[i] = min((int32_t)(sampleX >> 16), last);
+		right[i] = ratio == 0u ? left[i] : min((int32_t)(sampleX >> 16) + 1, last);
+		weights[i] = ratio == 0u ? (65535u | (1u << 16)) : ((65536u - ratio) | (ratio << 16));
+	}
+	auto stretch_row = [&](int32_t row, uint32_t *value) {
+		const uint32_t *line = row_ptr<uint32_t>(source.data, source.stride, row);
+		uint32_t a[4], b[4];
+#pragma unroll
+		for (int i = 0; i < 4; i++) { a[i] = __ldg(line + left[i]); b[i] = __ldg(line + right[i]); }
+#pragma unroll
+		for (int i = 0; i < 4; i++) {
+			const uint32_t pair01 = __byte_perm(a[i], b[i], 0x5140), pair23 = __byte_perm(a[i], b[i], 0x7362);
+			const uint32_t s0 = __dp2a_lo(weights[i], pair01, 0u), s1 = __dp2a_hi(weights[i], pair01, 0u);
+			const uint32_t s2 = __dp2a_lo(weights[i], pair23, 0u), s3 = __dp2a_hi(weights[i], pair23, 0u);
+			value[i] = __byte_perm(__byte_perm(s0, s1, 0x4462), __byte_perm(s2, s3, 0x4462), 0x5410);
+		}
+	};
+	const int32_t lastRow = source.height - 1;
+	int32_t upperRow = -1, lowerRow = -1;
+	uint32_t upperValue[4] = {0u, 0u, 0u, 0u}, lowerValue[4] = {0u, 0u, 0u, 0u};
+	const int32_t yEnd = min(yFirst + FUSED_ROWS, target.height);
+	for (int32_t y = yFirst; y < yEnd; y++) {
+		const int32_t readY = rp.startY + y * rp.offsetY;
+		const uint32_t sampleY = (uint32_t)(readY < 0 ? 0 : readY);
+		const int32_t upperY = min((int32_t)(sampleY >> 16), lastRow), lowerY = min((int32_t)(sampleY >> 16) + 1, lastRow);
+		if (upperY != upperRow) {
+			if (upperY == lowerRow) {
+#pragma unroll
+				for (int i = 0; i < 4; i++) { upperValue[i] = lowerValue[i]; }
+			} else {
+				stretch_row(upperY, upperValue);
+			}
+			upperRow = upperY;
+		}
+		if (lowerY != lowerRow) {
+			if (lowerY == upperY) {
+#pragma unroll
+				for (int i = 0; i < 4; i++) { lowerValue[i] = upperValue[i]; }
+			} else {
+				stretch_row(lowerY, lowerValue);
+			}
+			lowerRow = lowerY;
+		}
+		uint32_t out[4];
+#pragma unroll
+		for (int i = 0; i < 4; i++) { out[i] = mix_uniform(upperValue[i], lowerValue[i], sampleY & 65535u); }
+		store4(target, x0, y, 4, out);
+	}
+}
+
 template <bool SAME_ORDER>
 __global__ void __launch_bounds__(256, RESIZE_UP_MIN_BLOCKS) resize_up_fused_kernel(Img target, Img source, ResizeParams rp) {
 	const int32_t x0 = (int32_t)(blockIdx.x * blockDim.x + threadIdx.x) * PX, yFirst = (int32_t)(blockIdx.y * blockDim.y + threadIdx.y) * FUSED_ROWS;
 	if (x0 >= target.width || yFirst >= target.height) { return; }
+	if (SAME_ORDER && target.width - x0 >= PX) { resize_up_whole_columns(target, source, rp, x0, yFirst); return; }
 	const int n = min(PX, target.width - x0);
 	const uint32_t shifts = pack_shifts(target.packOrder);
 	int32_t leftX[4];

@@ -29,7 +29,7 @@ namespace dfpsr {
 
 static const int TILE_W = 32, TILE_H = 4;  // one warp: 16 x 2 quads
 static const int BATCH = 16;               // commands whose checkpoints are prepared together (BATCH x 2 row pairs = 32 lanes)
-static const int SMALL_ROWS = 16;          // triangles up to this many rows and SMALL_WIDTH columns are scan-converted by their set-up thread
+static const int SMALL_ROWS = 4;           // = TILE_H: triangles up to this many rows and SMALL_WIDTH columns are scan-converted by their set-up thread
 static const int SMALL_WIDTH = 128;
 static const int SMALL_TILES = 8;          // counting pass: bounding boxes up to this many tiles are counted by the set-up thread
 #ifndef SETUP_THREADS_N
@@ -2591,11 +2591,11 @@ static int run_frame(dfpsr_renderer *r, cudaStream_t stream, bool allowAsync) {
 	frame.blockCmds = (uint32_t *)r->blockCmds.ptr; frame.blockRows = (uint32_t *)r->blockRows.ptr;
 	frame.tileCount = (uint32_t *)r->tileCount.ptr; frame.tileOffset = (uint32_t *)r->tileOffset.ptr; frame.tileCursor = (uint32_t *)r->tileCursor.ptr;
 	frame.totals = frame.tileCount + tileTotal;
-	// A frame that does not fill the machine (one 1080p terrain frame: 7.6 k slots) is bound by its longest thread: only triangles within one
-	// tile row stay with their set-up thread, everything taller goes to the unit queue (one thread per row pair). Large batches keep the
-	// serial scan conversion of small triangles (less queue and checkpoint traffic per triangle).
+	// Only triangles within one tile row stay with their set-up thread; everything taller goes to the unit queue (one thread per row pair).
+	// A single frame is bound by its longest thread, and the 256-view batch measured 43.45 us per frame at 4 rows against 43.6 (8), 44.0 (16)
+	// and 44.7 (32). DFPSR_SMALL_ROWS overrides for experiments.
 	static const int smallRowsOverride = getenv("DFPSR_SMALL_ROWS") ? atoi(getenv("DFPSR_SMALL_ROWS")) : -1;
-	frame.smallRows = slotTotal <= sm_count() * 1024 ? TILE_H : SMALL_ROWS;
+	frame.smallRows = SMALL_ROWS;
 	if (smallRowsOverride >= 0) { frame.smallRows = smallRowsOverride; }
 
 	if (taskCount == 0) {

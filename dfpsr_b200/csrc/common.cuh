@@ -135,6 +135,41 @@ __device__ __forceinline__ uint32_t pack_rgba_ordered(uint32_t r, uint32_t g, ui
 	return (r << (shifts & 31u)) | (g << ((shifts >> 8) & 31u)) | (b << ((shifts >> 16) & 31u)) | (a << ((shifts >> 24) & 31u));
 }
 
+// ref: api/drawAPI.cpp:176-283 drawLineSuper. Step j along the major axis writes (major0 + j, minor0 + sign * k(j)) where the reference's
+// running error (error += tilt; if error >= maxError { minor += sign; error -= 2 * maxError }) has the closed form
+// k(j) = floor((j * tilt + maxError) / (2 * maxError)). Shared by the 2D line kernels (draw_ops.cu) and the wireframe overlay (raster.cu).
+struct LineParams { int32_t major0, minor0, sign, steps, firstStep; int32_t majorIsY; long long tilt, maxError; };
+__host__ __device__ inline bool line_params(int32_t width, int32_t height, int32_t x1, int32_t y1, int32_t x2, int32_t y2, LineParams &p) {
+	if ((x1 < 0 && x2 < 0) || (y1 < 0 && y2 < 0) || (x1 >= width && x2 >= width) || (y1 >= height && y2 >= height)) { return false; }
+	const long long dx = (long long)x2 - x1, dy = (long long)y2 - y1;
+	const long long adx = dx < 0 ? -dx : dx, ady = dy < 0 ? -dy : dy;
+	long long length;
+	if (ady >= adx) { // vertical, or closer to vertical: walk down (ref: :203-236); a horizontal line has ady == 0 == adx only when both are 0
+		if (y2 < y1) { int32_t t = x1; x1 = x2; x2 = t; t = y1; y1 = y2; y2 = t; }
+		p.majorIsY = 1; p.major0 = y1; p.minor0 = x1; p.sign = x2 > x1 ? 1 : -1; p.tilt = 2 * adx; p.maxError = ady; length = ady;
+	} else { // closer to horizontal: walk right (ref: :237-276)
+		if (x2 < x1) { int32_t t = x1; x1 = x2; x2 = t; t = y1; y1 = y2; y2 = t; }
+		p.majorIsY = 0; p.major0 = x1; p.minor0 = y1; p.sign = y2 > y1 ? 1 : -1; p.tilt = 2 * ady; p.maxError = adx; length = adx;
+	}
+	// only the steps whose major coordinate lies inside the image can write
+	const long long limit = p.majorIsY ? height : width;
+	const long long first = p.major0 < 0 ? -(long long)p.major0 : 0;
+	long long last = limit - 1 - p.major0;
+	if (length < last) { last = length; }
+	if (last < first) { return false; }
+	p.firstStep = (int32_t)first; p.steps = (int32_t)(last - first + 1);
+	return true;
+}
+// Pixel of step i (counted from firstStep) of a line; false when it falls outside the image.
+__device__ __forceinline__ bool line_pixel(const LineParams &p, int32_t i, int32_t width, int32_t height, int32_t &px, int32_t &py) {
+	const long long j = (long long)p.firstStep + i;
+	const long long k = p.maxError > 0 ? (j * p.tilt + p.maxError) / (2 * p.maxError) : 0;
+	const long long major = (long long)p.major0 + j, minor = (long long)p.minor0 + p.sign * k;
+	const long long x = p.majorIsY ? minor : major, y = p.majorIsY ? major : minor;
+	px = (int32_t)x; py = (int32_t)y;
+	return x >= 0 && x < width && y >= 0 && y < height;
+}
+
 template <typename T>
 __device__ __forceinline__ T *row_ptr(void *data, int32_t stride, int32_t y) {
 	return (T *)((uint8_t *)data + (size_t)y * (size_t)stride);

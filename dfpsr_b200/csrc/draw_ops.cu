@@ -46,18 +46,12 @@ __global__ void __launch_bounds__(256) rectangle_kernel(Img target, int32_t left
 	if (x < width && y < height) { *px_u32(target, left + x, top + y) = value; }
 }
 
-// ref: api/drawAPI.cpp:176-283 drawLineSuper. Step j along the major axis writes (major0 + j, minor0 + sign * k(j)) where the reference's
-// running error (error += tilt; if error >= maxError { minor += sign; error -= 2 * maxError }) has the closed form
-// k(j) = floor((j * tilt + maxError) / (2 * maxError)).
-struct LineParams { int32_t major0, minor0, sign, steps, firstStep; int32_t majorIsY; long long tilt, maxError; };
+// ref: api/drawAPI.cpp:176-283 drawLineSuper in closed form (LineParams / line_pixel in common.cuh): one thread per step of the major axis
 __global__ void __launch_bounds__(256) line_kernel(Img target, LineParams p, uint32_t value) {
 	const int32_t i = (int32_t)(blockIdx.x * blockDim.x + threadIdx.x);
 	if (i >= p.steps) { return; }
-	const long long j = (long long)p.firstStep + i;
-	const long long k = p.maxError > 0 ? (j * p.tilt + p.maxError) / (2 * p.maxError) : 0;
-	const long long major = (long long)p.major0 + j, minor = (long long)p.minor0 + p.sign * k;
-	const long long x = p.majorIsY ? minor : major, y = p.majorIsY ? major : minor;
-	if (x >= 0 && x < target.width && y >= 0 && y < target.height) { *px_u32(target, (int32_t)x, (int32_t)y) = value; }
+	int32_t x, y;
+	if (line_pixel(p, i, target.width, target.height, x, y)) { *px_u32(target, x, y) = value; }
 }
 
 enum { OP_ALPHA_FILTER = 0, OP_MAX_ALPHA = 1, OP_MAX_ALPHA_OFFSET = 2, OP_ALPHA_CLIP = 3 };
@@ -128,11 +122,8 @@ __global__ void __launch_bounds__(256) rectangle_mono_kernel(Img target, int32_t
 __global__ void __launch_bounds__(256) line_mono_kernel(Img target, int32_t format, LineParams p, uint32_t value) {
 	const int32_t i = (int32_t)(blockIdx.x * blockDim.x + threadIdx.x);
 	if (i >= p.steps) { return; }
-	const long long j = (long long)p.firstStep + i;
-	const long long k = p.maxError > 0 ? (j * p.tilt + p.maxError) / (2 * p.maxError) : 0;
-	const long long major = (long long)p.major0 + j, minor = (long long)p.minor0 + p.sign * k;
-	const long long x = p.majorIsY ? minor : major, y = p.majorIsY ? major : minor;
-	if (x >= 0 && x < target.width && y >= 0 && y < target.height) { store_mono(target, format, (int32_t)x, (int32_t)y, value); }
+	int32_t x, y;
+	if (line_pixel(p, i, target.width, target.height, x, y)) { store_mono(target, format, x, y, value); }
 }
 
 // ref: api/drawAPI.cpp:476-486 saturateFloat
@@ -210,7 +201,7 @@ int rectangle(const dfpsr_image *image, int32_t left, int32_t top, int32_t width
 	return 0;
 }
 
-bool line_params(const Img &t, int32_t x1, int32_t y1, int32_t x2, int32_t y2, LineParams &p);
+inline bool line_params(const Img &t, int32_t x1, int32_t y1, int32_t x2, int32_t y2, LineParams &p) { return dfpsr::line_params(t.width, t.height, x1, y1, x2, y2, p); }
 int line(const dfpsr_image *image, int32_t x1, int32_t y1, int32_t x2, int32_t y2, uint32_t value, cudaStream_t stream) {
 	if (!exists(image)) { return 0; }
 	const Img t = img_of(image);
@@ -219,26 +210,6 @@ int line(const dfpsr_image *image, int32_t x1, int32_t y1, int32_t x2, int32_t y
 	DFPSR_LAUNCH(line_kernel, (p.steps + 255) / 256, 256, 0, stream, t, p, value);
 	return 0;
 }
-bool line_params(const Img &t, int32_t x1, int32_t y1, int32_t x2, int32_t y2, LineParams &p) {
-	if ((x1 < 0 && x2 < 0) || (y1 < 0 && y2 < 0) || (x1 >= t.width && x2 >= t.width) || (y1 >= t.height && y2 >= t.height)) { return false; }
-	const int64_t dx = (int64_t)x2 - x1, dy = (int64_t)y2 - y1;
-	const int64_t adx = dx < 0 ? -dx : dx, ady = dy < 0 ? -dy : dy;
-	int64_t length;
-	if (ady >= adx) { // vertical, or closer to vertical: walk down (ref: :203-236); a horizontal line has ady == 0 == adx only when both are 0
-		if (y2 < y1) { std::swap(x1, x2); std::swap(y1, y2); }
-		p.majorIsY = 1; p.major0 = y1; p.minor0 = x1; p.sign = x2 > x1 ? 1 : -1; p.tilt = 2 * adx; p.maxError = ady; length = ady;
-	} else { // closer to horizontal: walk right (ref: :237-276)
-		if (x2 < x1) { std::swap(x1, x2); std::swap(y1, y2); }
-		p.majorIsY = 0; p.major0 = x1; p.minor0 = y1; p.sign = y2 > y1 ? 1 : -1; p.tilt = 2 * ady; p.maxError = adx; length = adx;
-	}
-	// only the steps whose major coordinate lies inside the image can write
-	const int64_t limit = p.majorIsY ? t.height : t.width;
-	const int64_t first = p.major0 < 0 ? -(int64_t)p.major0 : 0, last = std::min<int64_t>(length, limit - 1 - p.major0);
-	if (last < first) { return false; }
-	p.firstStep = (int32_t)first; p.steps = (int32_t)(last - first + 1);
-	return true;
-}
-
 uint32_t saturate_and_pack(const dfpsr_image *image, const int32_t rgba[4]) { // ref: api/imageAPI.cpp image_saturateAndPack
 	const uint32_t shifts = pack_shifts(image->packOrder);
 	return (clamp255(rgba[0]) << (shifts & 31u)) | (clamp255(rgba[1]) << ((shifts >> 8) & 31u)) | (clamp255(rgba[2]) << ((shifts >> 16) & 31u)) | (clamp255(rgba[3]) << ((shifts >> 24) & 31u));

@@ -715,6 +715,35 @@ __global__ void __launch_bounds__(256, RESIZE_UP_MIN_BLOCKS) resize_up_fused_ker
 	}
 }
 
+// ref: api/filterAPI.cpp:95-154 resize_reference<*, ImageU8, uint8_t> — one byte per pixel, both axes sampled for every target pixel
+// (16-bit weights, clamped reads). One thread per four target pixels of a row, stored as one word when the address allows.
+__global__ void __launch_bounds__(256) resize_u8_kernel(Img target, Img source, ResizeParams rp) {
+	const int32_t x0 = (blockIdx.x * blockDim.x + threadIdx.x) * PX, y = blockIdx.y * blockDim.y + threadIdx.y;
+	if (x0 >= target.width || y >= target.height) { return; }
+	const int n = min(PX, target.width - x0);
+	const int32_t lastX = source.width - 1, lastY = source.height - 1;
+	const int32_t readY = rp.startY + y * rp.offsetY;
+	const uint32_t sampleY = (uint32_t)(readY < 0 ? 0 : readY), lowerRatio = sampleY & 65535u;
+	const uint8_t *upperLine = row_ptr<uint8_t>(source.data, source.stride, min((int32_t)(sampleY >> 16), lastY));
+	const uint8_t *lowerLine = row_ptr<uint8_t>(source.data, source.stride, min((int32_t)(sampleY >> 16) + 1, lastY));
+	uint32_t out[4] = {0u, 0u, 0u, 0u};
+	for (int i = 0; i < n; i++) {
+		const int32_t readX = rp.startX + (x0 + i) * rp.offsetX;
+		const uint32_t sampleX = (uint32_t)(readX < 0 ? 0 : readX), rightRatio = sampleX & 65535u;
+		const int32_t leftX = min((int32_t)(sampleX >> 16), lastX), rightX = min((int32_t)(sampleX >> 16) + 1, lastX);
+		if (rp.bilinear) {
+			const uint32_t upper = ((uint32_t)__ldg(upperLine + leftX) * (65536u - rightRatio) + (uint32_t)__ldg(upperLine + rightX) * rightRatio) >> 16;
+			const uint32_t lower = ((uint32_t)__ldg(lowerLine + leftX) * (65536u - rightRatio) + (uint32_t)__ldg(lowerLine + rightX) * rightRatio) >> 16;
+			out[i] = (upper * (65536u - lowerRatio) + lower * lowerRatio) >> 16;
+		} else {
+			out[i] = __ldg(upperLine + leftX);
+		}
+	}
+	uint8_t *p = row_ptr<uint8_t>(target.data, target.stride, y) + x0;
+	if (n == 4 && (((uintptr_t)p) & 3u) == 0) { *(uint32_t *)p = out[0] | (out[1] << 8) | (out[2] << 16) | (out[3] << 24); }
+	else { for (int i = 0; i < n; i++) { p[i] = (uint8_t)out[i]; } }
+}
+
 struct MapParams { int32_t op, startX, startY; int32_t p[8]; };
 
 // ref: api/filterAPI.cpp:759-777 with the enumerated device ops of dfpsr_b200.h
@@ -1069,6 +1098,31 @@ int dfpsr_texture_generate_pyramid(const dfpsr_texture *texture, void *stream) {
 size_t dfpsr_filter_resize_scratch_bytes(int32_t sourceWidth, int32_t sourceHeight, int32_t newWidth, int32_t newHeight) {
 	if (newWidth != sourceWidth && newHeight > sourceHeight) { return (size_t)newWidth * (size_t)sourceHeight * 4; }
 	return 0;
+}
+
+static int resize_u8_single(const Img &target, const Img &source, bool bilinear, cudaStream_t stream) {
+	ResizeParams rp;
+	rp.offsetX = (int32_t)(65536u * (uint32_t)source.width / (uint32_t)target.width);
+	rp.offsetY = (int32_t)(65536u * (uint32_t)source.height / (uint32_t)target.height);
+	rp.startX = rp.offsetX / 2 - (bilinear ? 32768 : 0); rp.startY = rp.offsetY / 2 - (bilinear ? 32768 : 0);
+	rp.bilinear = bilinear ? 1 : 0; rp.path = RESIZE_GENERAL;
+	DFPSR_LAUNCH(resize_u8_kernel, grid_for(target.width, target.height, BLOCK), BLOCK, 0, stream, target, source, rp);
+	return 0;
+}
+
+int dfpsr_filter_resize_u8(const dfpsr_image *target, const dfpsr_image *source, int32_t sampler, void *scratch, void *stream) {
+	DFPSR_REQUIRE(exists(target) && exists(source), "filter_resize_u8: null argument");
+	Img t = img_of(target), s = img_of(source);
+	const bool bilinear = sampler == DFPSR_SAMPLER_LINEAR;
+	// ref: api/filterAPI.cpp:298-314 resizeToTarget: two passes (and their two roundings) when the width changes and the height grows
+	if (t.width != s.width && t.height > s.height) {
+		DFPSR_REQUIRE(scratch != nullptr, "filter_resize_u8: up-scaling both dimensions needs a scratch buffer of target.width * source.height bytes");
+		Img temp;
+		temp.data = (uint8_t *)scratch; temp.width = t.width; temp.height = s.height; temp.stride = t.width; temp.packOrder = 0;
+		if (resize_u8_single(temp, s, bilinear, as_stream(stream))) { return 1; }
+		return resize_u8_single(t, temp, bilinear, as_stream(stream));
+	}
+	return resize_u8_single(t, s, bilinear, as_stream(stream));
 }
 
 int dfpsr_filter_resize(const dfpsr_image *target, const dfpsr_image *source, int32_t sampler, int32_t sourceIsSubImage, void *scratch, void *stream) {

@@ -2295,6 +2295,50 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32, (MODE == TILE_DEFERRED ? (E
 	}
 }
 
+// ------------------------------------------------------------------------------------------------ wireframe overlay
+
+// ref: api/rendererAPI.cpp:362-399 — renderer_end(renderer, debugWireframe = true): after the frame is drawn, the three edges of every
+// command the occlusion grid did not remove are drawn on top of the colour buffer as white lines (draw_line between the corners'
+// positions in whole pixels, flat / unitsPerPixel). One thread per input triangle repeats the set-up pass's decisions and walks its lines;
+// every line has the same colour, so the order of the writes does not matter. A debug view: nothing here is tuned.
+__device__ void wireframe_line(const ViewDev &view, int32_t x1, int32_t y1, int32_t x2, int32_t y2) {
+	LineParams p;
+	if (!line_params(view.width, view.height, x1, y1, x2, y2, p)) { return; }
+	for (int32_t i = 0; i < p.steps; i++) {
+		int32_t x, y;
+		if (line_pixel(p, i, view.width, view.height, x, y) && y >= view.clipTop && y < view.clipBottom) { row_ptr<uint32_t>(view.color.data, view.color.stride, y)[x] = 0xFFFFFFFFu; } // white, alpha 255, in every pack order
+	}
+}
+
+__global__ void __launch_bounds__(SETUP_THREADS) wireframe_kernel(FrameDev frame) {
+	__shared__ TaskParams task;
+	__shared__ int sCulled;
+	{
+		int32_t t = frame.blockTask ? frame.blockTask[blockIdx.x] : task_of_block(frame.tasks, frame.taskCount, (int32_t)blockIdx.x);
+		for (uint32_t w = threadIdx.x; w < sizeof(TaskParams) / 4; w += blockDim.x) { ((uint32_t *)&task)[w] = ((const uint32_t *)&frame.tasks[t])[w]; }
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) { sCulled = task.cullOnDevice && task_is_culled(frame, task) ? 1 : 0; }
+	__syncthreads();
+	if (sCulled) { return; }
+	const ViewDev &view = frame.views[task.view];
+	if (view.color.data == nullptr) { return; }
+	const int32_t local = ((int32_t)blockIdx.x - task.blockBase) * SETUP_THREADS + (int32_t)threadIdx.x;
+	PPoint p[3];
+	float colors[3][4], tex[3][4];
+	if (local >= task.slotCount || !load_triangle(task, local, p, colors, tex)) { return; }
+	const float alpha[3] = {colors[0][3], colors[1][3], colors[2][3]};
+	for_each_command(task, p, alpha, [&](const PPoint *q, const float *, const float *) {
+		const Bound bound = raster_bound(q, view.width, view.clipTop, view.clipBottom);
+		if (command_occluded(frame, bound, q)) { return; }
+		int32_t x[3], y[3];
+		for (int k = 0; k < 3; k++) { x[k] = (int32_t)(q[k].fx / 256); y[k] = (int32_t)(q[k].fy / 256); }
+		wireframe_line(view, x[0], y[0], x[1], y[1]);
+		wireframe_line(view, x[1], y[1], x[2], y[2]);
+		wireframe_line(view, x[2], y[2], x[0], y[0]);
+	});
+}
+
 } // namespace dfpsr
 
 // ------------------------------------------------------------------------------------------------ host side
@@ -2332,6 +2376,7 @@ struct dfpsr_renderer {
 	size_t uploadCount = 0;
 	std::vector<TexDev> textures;        // the frame's texture table (uploaded behind the task records)
 	bool exact = true;                   // false: tolerance mode (dfpsr_renderer_set_precision)
+	bool wireframe = false;              // the next renderer_end draws the commands' edges on top of the frame (dfpsr_renderer_set_debug_wireframe)
 	bool async = false;                  // true: renderer_end does not wait for the frame's counts (dfpsr_renderer_set_async)
 	int64_t lastCommands = -1;
 	DeviceBuffer dTasks, dViews, projected, slotCounts, blockCmds, blockRows, tileCount, tileOffset, tileCursor, cmds, rows, tileList, chk, sortTmp, bigItems, bigUnits;
@@ -2720,6 +2765,7 @@ static int run_frame(dfpsr_renderer *r, cudaStream_t stream, bool allowAsync) {
 	else if (immediate) { DFPSR_LAUNCH_CHAINED(tile_kernel_immediate, grid, RASTER_WARPS * 32, 0, stream, frame); }
 	else if (exactFrame) { DFPSR_LAUNCH_CHAINED(tile_kernel_deferred, grid, RASTER_WARPS * 32, 0, stream, frame); }
 	else { DFPSR_LAUNCH_CHAINED(tile_kernel_tolerance, grid, RASTER_WARPS * 32, 0, stream, frame); }
+	if (r->wireframe && !r->depthOnly && taskCount > 0) { DFPSR_LAUNCH(wireframe_kernel, blockTotal, SETUP_THREADS, 0, stream, frame); }
 	if (timing) {
 		fprintf(stderr, "renderer_end: %zu tasks, %zu views | layout+upload %.0f us, first launches %.0f us, wait for totals %.0f us, second launches %.0f us\n",
 		        taskCount, viewCount, tUploaded - tStart, tLaunched - tUploaded, tSynced > 0.0 ? tSynced - tLaunched : 0.0, host_now_us() - (tSynced > 0.0 ? tSynced : tLaunched));
@@ -2776,7 +2822,10 @@ static int renderer_end_internal(dfpsr_renderer *r, cudaStream_t stream) {
 	DFPSR_REQUIRE(r->receiving, "Called renderer_end without renderer_begin!");
 	r->receiving = false;
 	if (verify_frame(r)) { return 1; }
-	return run_frame(r, stream, r->async);
+	// a frame with the wireframe overlay waits for its counts: the overlay is a debug view and is not part of the redraw of a dropped frame
+	const int status = run_frame(r, stream, r->async && !r->wireframe);
+	r->wireframe = false;
+	return status;
 }
 
 extern "C" {
@@ -2819,6 +2868,12 @@ int dfpsr_renderer_flush(dfpsr_renderer *renderer) {
 }
 
 int dfpsr_flush(void) { return dfpsr::verify_pending_frames(); }
+
+int dfpsr_renderer_set_debug_wireframe(dfpsr_renderer *renderer, int32_t enabled) {
+	DFPSR_REQUIRE(renderer != nullptr, "dfpsr_renderer_set_debug_wireframe: null renderer");
+	renderer->wireframe = enabled != 0;
+	return 0;
+}
 
 int dfpsr_renderer_set_precision(dfpsr_renderer *renderer, int32_t precision) {
 	DFPSR_REQUIRE(renderer != nullptr, "renderer_set_precision: renderer does not exist");

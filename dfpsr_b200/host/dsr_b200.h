@@ -593,8 +593,8 @@ inline bool renderer_isBoxVisible(const Renderer &renderer, const FVector3D &min
 	return visible != 0;
 }
 inline void renderer_end(Renderer &renderer, bool debugWireframe = false) {
-	(void)debugWireframe; // the wireframe overlay (rendererAPI.cpp:362-399) is a 2D draw call outside the path
 	if (!renderer) { throwError("renderer_end: renderer does not exist"); }
+	if (debugWireframe) { b200_check(dfpsr_renderer_set_debug_wireframe(renderer->handle, 1)); } // ref: rendererAPI.cpp:362-399, drawn on the device after the frame
 	b200_check(dfpsr_renderer_end(renderer->handle, b200_stream()));
 	renderer->inFlight.swap(renderer->queued); renderer->queued.clear();
 	renderer->colorBuffer.touchedByDevice(); renderer->depthBuffer.touchedByDevice();
@@ -828,6 +828,17 @@ inline ImageRgbaU8 filter_resize(const ImageRgbaU8 &source, Sampler interpolatio
 	std::unique_ptr<B200Buffer> scratch(need > 0 ? new B200Buffer(need) : nullptr);
 	dfpsr_image t = result.pod(), s = source.pod();
 	b200_check(dfpsr_filter_resize(&t, &s, (int32_t)interpolation, source.subImage ? 1 : 0, scratch ? scratch->device : nullptr, b200_stream()));
+	if (scratch) { b200_check(dfpsr_stream_synchronize(b200_stream())); }
+	result.touchedByDevice();
+	return result;
+}
+inline ImageU8 filter_resize(const ImageU8 &source, Sampler interpolation, int32_t newWidth, int32_t newHeight) { // ref: api/filterAPI.h:42, api/filterAPI.cpp:862-870
+	if (!image_exists(source)) { return ImageU8(); }
+	ImageU8 result = b200_image_create<uint8_t>(newWidth, newHeight, PackOrderIndex::RGBA);
+	const bool twoPasses = newWidth != source.width && newHeight > source.height;
+	std::unique_ptr<B200Buffer> scratch(twoPasses ? new B200Buffer((size_t)newWidth * (size_t)source.height) : nullptr);
+	dfpsr_image t = result.pod(), s = source.pod();
+	b200_check(dfpsr_filter_resize_u8(&t, &s, (int32_t)interpolation, scratch ? scratch->device : nullptr, b200_stream()));
 	if (scratch) { b200_check(dfpsr_stream_synchronize(b200_stream())); }
 	result.touchedByDevice();
 	return result;

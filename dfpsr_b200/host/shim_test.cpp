@@ -73,6 +73,17 @@ static int filterSession(const char *outPath) {
 	image_fill(normal, ColorRgbaI32(128, 255, 128, 0));
 	addPointLight(view, IVector2D(32, 32), light, normal, heightBuffer, FVector3D(0.0f, 2.0f, 0.0f), 4.0f, 1.0f, ColorRgbaI32(255, 200, 100, 0));
 	addPointLight(view, IVector2D(32, 32), light, normal, heightBuffer, FVector3D(0.0f, 2.0f, 0.0f), 4.0f, 1.0f, ColorRgbaI32(255, 200, 100, 0), cube);
+	// filter_resize(ImageU8) (ref: api/filterAPI.h:42): a horizontal ramp doubled in both directions stays a ramp; nearest repeats pixels
+	ImageU8 ramp = image_create_U8(32, 8);
+	std::vector<uint8_t> rampRows((size_t)32 * 8);
+	for (int32_t y = 0; y < 8; y++) { for (int32_t x = 0; x < 32; x++) { rampRows[(size_t)y * 32 + x] = (uint8_t)(x * 8); } }
+	image_upload(ramp, rampRows.data(), 32);
+	ImageU8 smooth = filter_resize(ramp, Sampler::Linear, 64, 16), blocky = filter_resize(ramp, Sampler::Nearest, 64, 16);
+	ASSERT(image_getWidth(smooth) == 64 && image_getHeight(smooth) == 16);
+	std::vector<uint8_t> smoothRows((size_t)64 * 16), blockyRows(smoothRows.size());
+	image_download(smooth, smoothRows.data(), 64); image_download(blocky, blockyRows.data(), 64);
+	ASSERT(smoothRows[0] == 0 && smoothRows[(size_t)5 * 64 + 21] == 82 && smoothRows[(size_t)15 * 64 + 63] == 248); // (10*8*0.75 + 11*8*0.25) = 82
+	ASSERT(blockyRows[(size_t)3 * 64 + 20] == 80 && blockyRows[(size_t)3 * 64 + 21] == 80 && blockyRows[(size_t)3 * 64 + 22] == 88);
 	FILE *out = std::fopen(outPath, "wb");
 	ASSERT(out != nullptr);
 	std::fwrite(c.data(), 4, c.size(), out);
@@ -237,6 +248,21 @@ int main(int argc, char **argv) {
 	std::vector<float> d3(c1.size());
 	image_download(depth3, d3.data(), h.width * 4);
 	if (!h.filter) { ASSERT(std::memcmp(d1.data(), d3.data(), d1.size() * 4) == 0); }
+
+	// renderer_end(renderer, debugWireframe = true) (ref: api/rendererAPI.h:134-135): the same depth, white edges on top of the colours
+	ImageRgbaU8 color4 = image_create_RgbaU8(h.width, h.height);
+	ImageF32 depth4 = image_create_F32(h.width, h.height);
+	image_fill(depth4, h.perspective ? 0.0f : 1.0e9f);
+	renderer_begin(worker, color4, depth4);
+	renderer_giveTask(worker, model, Transform3D(), camera);
+	renderer_end(worker, true);
+	std::vector<uint32_t> c4(c1.size());
+	std::vector<float> d4(c1.size());
+	image_download(color4, c4.data(), h.width * 4); image_download(depth4, d4.data(), h.width * 4);
+	ASSERT(std::memcmp(d1.data(), d4.data(), d1.size() * 4) == 0);
+	size_t changed = 0, changedToWhite = 0;
+	for (size_t i = 0; i < c1.size(); i++) { if (c4[i] != c1[i]) { changed++; if (c4[i] == 0xFFFFFFFFu) { changedToWhite++; } } }
+	ASSERT(changed > 0 && changed == changedToWhite);
 
 	FILE *out = std::fopen(argv[2], "wb");
 	ASSERT(out != nullptr);

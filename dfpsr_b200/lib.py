@@ -63,6 +63,7 @@ SIGNATURES = {
     "dfpsr_renderer_give_tasks": (i32, [vp, vp, vp, i32, P(abi.Camera), vp]),
     "dfpsr_renderer_give_task_triangles": (i32, [vp, vp, i32, P(abi.Texture), P(abi.Texture), i32, P(abi.Camera), vp]),
     "dfpsr_renderer_end": (i32, [vp, vp]),
+    "dfpsr_renderer_set_debug_wireframe": (i32, [vp, i32]),
     "dfpsr_renderer_last_command_count": (i32, [vp, P(i64), vp]),
     "dfpsr_model_render": (i32, [P(abi.Model), P(abi.Transform3D), P(abi.Image), P(abi.Image), P(abi.Camera), vp]),
     "dfpsr_model_render_depth": (i32, [P(abi.Model), P(abi.Transform3D), P(abi.Image), P(abi.Camera), vp]),
@@ -92,6 +93,7 @@ SIGNATURES = {
     "dfpsr_light_blend": (i32, [P(abi.Image), P(abi.Image), P(abi.Image), vp]),
     "dfpsr_filter_resize_scratch_bytes": (sz, [i32, i32, i32, i32]),
     "dfpsr_filter_resize": (i32, [P(abi.Image), P(abi.Image), i32, i32, vp, vp]),
+    "dfpsr_filter_resize_u8": (i32, [P(abi.Image), P(abi.Image), i32, vp, vp]),
     "dfpsr_filter_map": (i32, [P(abi.Image), i32, vp, i32, P(abi.Image), i32, i32, vp]),
     "dfpsr_filter_block_magnify": (i32, [P(abi.Image), P(abi.Image), i32, i32, vp]),
     "dfpsr_ortho_system_create": (i32, [P(abi.OrthoSystem), f32, i32]),

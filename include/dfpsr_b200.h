@@ -251,6 +251,11 @@ int dfpsr_renderer_give_task_triangles(dfpsr_renderer *renderer, const dfpsr_tri
  * bins the queued triangles to screen tiles and rasterises/shades every tile in submission order. Everything is queued on `stream`;
  * the call waits for the stream once (for the set-up counts) unless the renderer is asynchronous (dfpsr_renderer_set_async). */
 int dfpsr_renderer_end(dfpsr_renderer *renderer, void *stream);
+/* ref: api/rendererAPI.h:134-135, api/rendererAPI.cpp:362-399 renderer_end(renderer, debugWireframe = true): when enabled, the NEXT
+ * dfpsr_renderer_end draws the edges of every command that the occlusion grid did not remove as white lines on top of the finished colour
+ * buffer (the reference's draw_line between the corners' whole-pixel positions). The flag resets after that frame; such a frame always
+ * waits for its set-up counts. */
+int dfpsr_renderer_set_debug_wireframe(dfpsr_renderer *renderer, int32_t enabled);
 /* Number of draw commands (post-clipping triangles) the last frame produced; synchronises `stream`. */
 int dfpsr_renderer_last_command_count(dfpsr_renderer *renderer, int64_t *count, void *stream);
 
@@ -491,6 +496,10 @@ int dfpsr_sprite_world_get_buffers(const dfpsr_sprite_world *world, dfpsr_image 
  * scratch: device buffer of dfpsr_filter_resize_scratch_bytes() bytes, only used for two-pass up-scaling. */
 size_t dfpsr_filter_resize_scratch_bytes(int32_t sourceWidth, int32_t sourceHeight, int32_t newWidth, int32_t newHeight);
 int dfpsr_filter_resize(const dfpsr_image *target, const dfpsr_image *source, int32_t sampler, int32_t sourceIsSubImage, void *scratch, void *stream);
+/* ref: api/filterAPI.h:42, api/filterAPI.cpp:95-154, :282-314 filter_resize(ImageU8): one byte per pixel (stride in bytes, packOrder
+ * ignored). scratch: device buffer of target.width * source.height BYTES, only used when the width changes and the height grows (the
+ * reference's two passes and their two roundings). */
+int dfpsr_filter_resize_u8(const dfpsr_image *target, const dfpsr_image *source, int32_t sampler, void *scratch, void *stream);
 /* ref: api/filterAPI.h:54-79, api/filterAPI.cpp:759-782 filter_mapRgbaU8 / filter_generateRgbaU8 with ANY per-pixel function.
  * The reference takes a host lambda `ColorRgbaI32 f(int32_t x, int32_t y)`; here the function travels as text: `body` is the body of
  *     int4 pixel(int x, int y)      // (red, green, blue, alpha) as ints, saturated to 0..255 and packed in the target's order afterwards

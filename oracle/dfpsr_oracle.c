@@ -908,6 +908,7 @@ struct orc_renderer {
 	int occluded;
 	queued_command *commands; int64_t count, capacity;
 	int64_t lastOccluded;
+	int wireframe; /* renderer_end(renderer, debugWireframe = true) for the next frame */
 };
 #define CELL_SIZE 16 /* api/rendererAPI.cpp:36 */
 
@@ -1093,6 +1094,7 @@ void orc_renderer_give_task(orc_renderer *r, const dfpsr_model *model, const dfp
 	ctx.queue = r;
 	submit_model(&ctx, model, m2w, camera);
 }
+void orc_renderer_set_debug_wireframe(orc_renderer *r, int enabled) { r->wireframe = enabled; }
 /* api/rendererAPI.cpp:193-217 completeOcclusion + :352-402 endFrame. Returns the queue length; *occludedOut = commands skipped. */
 int64_t orc_renderer_end(orc_renderer *r, int64_t *occludedOut) {
 	r->receiving = 0;
@@ -1121,6 +1123,18 @@ int64_t orc_renderer_end(orc_renderer *r, int64_t *occludedOut) {
 		ctx.shader = c->shader;
 		execute_triangle(&ctx, c->p, c->subB, c->subC);
 	}
+	if (r->wireframe && r->color.data != NULL) { /* api/rendererAPI.cpp:362-399: white edges of every command that was not occluded */
+		static const int32_t white[4] = {255, 255, 255, 255};
+		for (int64_t t = 0; t < r->count; t++) {
+			const queued_command *c = &r->commands[t];
+			if (c->occluded) { continue; }
+			for (int e = 0; e < 3; e++) {
+				const ppoint *a = &c->p[e], *b = &c->p[(e + 1) % 3];
+				orc_draw_line_rgba(&r->color, (int32_t)(a->fx / 256), (int32_t)(a->fy / 256), (int32_t)(b->fx / 256), (int32_t)(b->fy / 256), white);
+			}
+		}
+	}
+	r->wireframe = 0;
 	if (occludedOut != NULL) { *occludedOut = skipped; }
 	r->lastOccluded = skipped;
 	int64_t n = r->count;
@@ -1816,6 +1830,52 @@ void orc_filter_resize(const dfpsr_image *target, const dfpsr_image *source, int
 		resize_single(target, &temp, bilinear, 1);
 	} else {
 		resize_single(target, source, bilinear, !sourceIsSubImage);
+	}
+}
+
+/* api/filterAPI.cpp:95-110 samplePixel(ImageU8) inside :118-154 resize_reference<*, ImageU8, uint8_t>, scaleRegion = whole target */
+static uint32_t u8_clamp(const dfpsr_image *im, int32_t x, int32_t y) { /* api/imageAPI.h image_readPixel_clamp(ImageU8) */
+	if (x < 0) { x = 0; } if (x >= im->width) { x = im->width - 1; }
+	if (y < 0) { y = 0; } if (y >= im->height) { y = im->height - 1; }
+	return ((const uint8_t *)im->data)[(size_t)y * (size_t)im->stride + (size_t)x];
+}
+static void resize_u8_single(const dfpsr_image *target, const dfpsr_image *source, int bilinear) {
+	int32_t offsetX = (int32_t)(65536u * (uint32_t)source->width / (uint32_t)target->width), offsetY = (int32_t)(65536u * (uint32_t)source->height / (uint32_t)target->height);
+	int32_t startX = offsetX / 2, startY = offsetY / 2;
+	if (bilinear) { startX -= 32768; startY -= 32768; }
+	int32_t readY = startY;
+	for (int32_t y = 0; y < target->height; y++) {
+		uint32_t sampleY = (uint32_t)(readY < 0 ? 0 : readY);
+		int32_t upperY = (int32_t)(sampleY >> 16);
+		uint32_t lowerRatio = sampleY & 65535u;
+		int32_t readX = startX;
+		for (int32_t x = 0; x < target->width; x++) {
+			uint32_t sampleX = (uint32_t)(readX < 0 ? 0 : readX);
+			int32_t leftX = (int32_t)(sampleX >> 16);
+			uint32_t rightRatio = sampleX & 65535u, value;
+			if (bilinear) {
+				uint32_t upper = (u8_clamp(source, leftX, upperY) * (65536u - rightRatio) + u8_clamp(source, leftX + 1, upperY) * rightRatio) >> 16;
+				uint32_t lower = (u8_clamp(source, leftX, upperY + 1) * (65536u - rightRatio) + u8_clamp(source, leftX + 1, upperY + 1) * rightRatio) >> 16;
+				value = (upper * (65536u - lowerRatio) + lower * lowerRatio) >> 16;
+			} else {
+				value = u8_clamp(source, leftX, upperY);
+			}
+			((uint8_t *)target->data)[(size_t)y * (size_t)target->stride + (size_t)x] = (uint8_t)value;
+			readX += offsetX;
+		}
+		readY += offsetY;
+	}
+}
+
+/* api/filterAPI.cpp:282-314, :862-870 filter_resize(ImageU8): two passes when the width changes and the height grows */
+void orc_filter_resize_u8(const dfpsr_image *target, const dfpsr_image *source, int32_t sampler, uint8_t *scratch) {
+	int bilinear = sampler == DFPSR_SAMPLER_LINEAR;
+	if (target->width != source->width && target->height > source->height) {
+		dfpsr_image temp = {scratch, target->width, source->height, target->width, 0};
+		resize_u8_single(&temp, source, bilinear);
+		resize_u8_single(target, &temp, bilinear);
+	} else {
+		resize_u8_single(target, source, bilinear);
 	}
 }
 

@@ -51,6 +51,8 @@ void orc_renderer_occlude_from_existing_triangles(orc_renderer *r);
 void orc_renderer_occlude_from_top_rows(orc_renderer *r, const dfpsr_camera *camera);
 int orc_renderer_is_box_visible(const orc_renderer *r, const float *minBound, const float *maxBound, const dfpsr_transform3d *modelToWorld, const dfpsr_camera *camera);
 void orc_renderer_give_task(orc_renderer *r, const dfpsr_model *model, const dfpsr_transform3d *modelToWorld, const dfpsr_camera *camera);
+/* renderer_end(renderer, debugWireframe = true) (api/rendererAPI.cpp:362-399) for the next orc_renderer_end. */
+void orc_renderer_set_debug_wireframe(orc_renderer *r, int enabled);
 int64_t orc_renderer_end(orc_renderer *r, int64_t *occludedOut);
 /* model_renderDepth */
 void orc_model_render_depth(const dfpsr_model *model, const dfpsr_transform3d *modelToWorld, const dfpsr_image *depth, const dfpsr_camera *camera);
@@ -93,6 +95,8 @@ void orc_light_blend(const dfpsr_image *color, const dfpsr_image *diffuse, const
 
 /* filter_resize into an existing RGBA-order target; scratch must hold target.width * source.height u32. */
 void orc_filter_resize(const dfpsr_image *target, const dfpsr_image *source, int32_t sampler, int32_t sourceIsSubImage, uint32_t *scratch);
+/* filter_resize(ImageU8): one byte per pixel, stride in bytes; scratch must hold target.width * source.height bytes. */
+void orc_filter_resize_u8(const dfpsr_image *target, const dfpsr_image *source, int32_t sampler, uint8_t *scratch);
 void orc_filter_map(const dfpsr_image *target, int32_t op, const int32_t *params, const dfpsr_image *source, int32_t startX, int32_t startY);
 void orc_filter_block_magnify(const dfpsr_image *target, const dfpsr_image *source, int32_t pixelWidth, int32_t pixelHeight);
 

@@ -336,6 +336,7 @@ int ref_renderer_is_box_visible(const float *mn, const float *mx, const dfpsr_tr
 }
 int ref_renderer_has_occluders() { return renderer_hasOccluders(stepRenderer()) ? 1 : 0; }
 void ref_renderer_end() { renderer_end(stepRenderer()); }
+void ref_renderer_end_wireframe() { renderer_end(stepRenderer(), true); }
 
 void ref_model_render_depth(int model, const dfpsr_transform3d *modelToWorld, int depthId, const dfpsr_camera *camera) {
 	ImageF32 depth = f32OrNull(depthId);
@@ -465,6 +466,14 @@ int ref_filter_resize(int source, int sampler, int newWidth, int newHeight) {
 	img.rgbaOrdered = filter_resize(g_images[source].rgba, sampler == DFPSR_SAMPLER_LINEAR ? Sampler::Linear : Sampler::Nearest, newWidth, newHeight);
 	img.rgbaAligned = img.rgbaOrdered;
 	img.rgba = img.rgbaOrdered;
+	g_images.push_back(img);
+	return (int)g_images.size() - 1;
+}
+
+int ref_filter_resize_u8(int source, int sampler, int newWidth, int newHeight) {
+	AnyImage img;
+	img.kind = 3;
+	img.u8 = filter_resize(g_images[source].u8, sampler == DFPSR_SAMPLER_LINEAR ? Sampler::Linear : Sampler::Nearest, newWidth, newHeight);
 	g_images.push_back(img);
 	return (int)g_images.size() - 1;
 }

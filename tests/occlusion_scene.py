@@ -46,7 +46,7 @@ def bounds_of(points):
     return lo, hi
 
 
-def run_reference(ref, sc):
+def run_reference(ref, sc, wireframe=False):
     import refbind
     L = ref.lib
     cam = abi.Camera.from_buffer_copy(sc["camera"])
@@ -68,11 +68,14 @@ def run_reference(ref, sc):
         if i == sc["existing_after"]:
             L.ref_renderer_occlude_from_existing_triangles()
     assert L.ref_renderer_has_occluders() == 1
-    L.ref_renderer_end()
+    if wireframe:
+        L.ref_renderer_end_wireframe()
+    else:
+        L.ref_renderer_end()
     return {"color": ref.read_rgba(color), "depth": ref.read_f32(depth), "visible": visible}
 
 
-def run_oracle(lib, sc):
+def run_oracle(lib, sc, wireframe=False):
     import orcbind
     IM = orcbind.image_of
     cam = orcbind.camera(sc["camera"])
@@ -95,12 +98,13 @@ def run_oracle(lib, sc):
             lib.orc_renderer_occlude_from_existing_triangles(r)
     assert lib.orc_renderer_has_occluders(r) == 1
     skipped = C.c_int64()
+    lib.orc_renderer_set_debug_wireframe(r, 1 if wireframe else 0)
     n = lib.orc_renderer_end(r, C.byref(skipped))
     lib.orc_renderer_destroy(r)
     return {"color": color, "depth": depth, "visible": visible, "commands": n, "occluded": skipped.value}
 
 
-def run_cuda(cuda, sc):
+def run_cuda(cuda, sc, wireframe=False):
     from dfpsr_b200 import lib
     cam = lib.camera(sc["camera"])
     tc, td = lib.to_device(sc["color0"]), lib.to_device(sc["depth0"])
@@ -125,6 +129,7 @@ def run_cuda(cuda, sc):
         if i == sc["existing_after"]:
             lib.check(cuda.dfpsr_renderer_occlude_from_existing_triangles(r, s))
     assert cuda.dfpsr_renderer_has_occluders(r) == 1
+    lib.check(cuda.dfpsr_renderer_set_debug_wireframe(r, 1 if wireframe else 0))
     lib.check(cuda.dfpsr_renderer_end(r, s))
     count = C.c_int64()
     lib.check(cuda.dfpsr_renderer_last_command_count(r, C.byref(count), s))

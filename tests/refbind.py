@@ -41,7 +41,7 @@ def load(flavour="scalar"):
         "ref_renderer_begin": (None, [i, i]), "ref_renderer_give_task": (None, [i, T, Cam]),
         "ref_renderer_occlude_from_box": (None, [p, p, T, Cam]), "ref_renderer_occlude_from_top_rows": (None, [Cam]),
         "ref_renderer_occlude_from_existing_triangles": (None, []), "ref_renderer_is_box_visible": (i, [p, p, T, Cam]),
-        "ref_renderer_has_occluders": (i, []), "ref_renderer_end": (None, []),
+        "ref_renderer_has_occluders": (i, []), "ref_renderer_end": (None, []), "ref_renderer_end_wireframe": (None, []),
         "ref_terrain_frame": (d, [i, T, i, i, Cam]),
         "ref_project_points": (None, [p, i, T, Cam, p]),
         "ref_camera_fill": (None, [Cam]), "ref_camera_is_box_seen": (i, [Cam, p, p, T]),
@@ -50,7 +50,7 @@ def load(flavour="scalar"):
         "ref_light_directed": (None, [V, i, i, p, f, p, i]),
         "ref_light_point": (None, [V, p, i, i, i, p, f, f, p, i]),
         "ref_light_blend": (None, [i, i, i]),
-        "ref_filter_resize": (i, [i, i, i, i]), "ref_filter_map": (None, [i, i, p, i, i, i]),
+        "ref_filter_resize": (i, [i, i, i, i]), "ref_filter_resize_u8": (i, [i, i, i, i]), "ref_filter_map": (None, [i, i, p, i, i, i]),
         "ref_filter_block_magnify": (None, [i, i, i, i]),
         "ref_image_create_u8": (i, [i, i, p]),
         "ref_image_create_u16": (i, [i, i, p]), "ref_image_read_mono": (None, [i, p]),

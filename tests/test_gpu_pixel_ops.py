@@ -121,6 +121,23 @@ def test_filter_resize(cuda, oracle, sampler):
             assert_same_u32(host_u32(tt), e, f"resize to {nw}x{nh} sampler={sampler} sub={sub}")
 
 
+@pytest.mark.parametrize("sampler", [0, 1])
+def test_filter_resize_u8(cuda, oracle, sampler):
+    """filter_resize(ImageU8): one byte per pixel, odd strides and unaligned rows included."""
+    import torch
+    rng = np.random.default_rng(16)
+    src = rng.integers(0, 256, (47, 70), dtype=np.uint8)
+    ts = torch.from_numpy(src).cuda()
+    for nw, nh in [(70, 47), (35, 20), (70, 90), (70, 13), (140, 47), (31, 47), (160, 130), (17, 200), (300, 45), (1, 1), (1024, 600)]:
+        tt = torch.zeros((nh, nw), dtype=torch.uint8, device="cuda")
+        scratch = torch.zeros(nw * 47 + 4, dtype=torch.uint8, device="cuda")
+        lib.check(cuda.dfpsr_filter_resize_u8(C.byref(abi.Image(tt.data_ptr(), nw, nh, nw, 0)), C.byref(abi.Image(ts.data_ptr(), 70, 47, 70, 0)), sampler, scratch.data_ptr(), lib.stream_ptr()))
+        e, es = np.zeros((nh, nw), np.uint8), np.zeros(nw * 47 + 4, np.uint8)
+        oracle.orc_filter_resize_u8(C.byref(abi.Image(e.ctypes.data, nw, nh, nw, 0)), C.byref(abi.Image(src.ctypes.data, 70, 47, 70, 0)), sampler, orcbind.ptr(es))
+        got = tt.cpu().numpy()
+        assert np.array_equal(got, e), f"u8 resize to {nw}x{nh} sampler={sampler}: {int((got != e).sum())} bytes differ"
+
+
 def test_filter_map_and_magnify(cuda, oracle):
     rng = np.random.default_rng(7)
     src = rand_rgba(rng, 61, 83)

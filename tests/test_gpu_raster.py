@@ -421,6 +421,22 @@ def test_occlusion_grid_matches_oracle(cuda, oracle, variant):
 
 
 @pytest.mark.parametrize("variant", OCCLUSION_VARIANTS)
+def test_debug_wireframe_matches_oracle(cuda, oracle, variant):
+    """renderer_end(renderer, debugWireframe = true) (api/rendererAPI.cpp:362-399): white edges of every command the occlusion grid left."""
+    import occlusion_scene
+    sc = occlusion_scene.build(**variant)
+    expected = occlusion_scene.run_oracle(oracle, sc, wireframe=True)
+    plain = occlusion_scene.run_oracle(oracle, sc)
+    got = occlusion_scene.run_cuda(cuda, sc, wireframe=True)
+    assert int((expected["color"] != plain["color"]).sum()) > 200
+    assert_same_u32(got["color"], expected["color"], "colour with the overlay")
+    assert_same_u32(bits(got["depth"]), bits(expected["depth"]), "depth")
+    # the flag covers one frame only
+    again = occlusion_scene.run_cuda(cuda, sc)
+    assert_same_u32(again["color"], plain["color"], "colour of the next frame")
+
+
+@pytest.mark.parametrize("variant", OCCLUSION_VARIANTS)
 def test_device_broad_phase_equals_host_tests(cuda, oracle, variant):
     """dfpsr_renderer_give_tasks: isBoxSeen and renderer_isBoxVisible per model on the device (against the occluders given before the call)
     draw the same frame, with the same number of commands, as one renderer_giveTask per model with the tests on the host."""

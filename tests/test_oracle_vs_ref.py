@@ -213,6 +213,22 @@ def test_filter_resize_bit_exact(ref_scalar, oracle, sampler):
     ref_scalar.free_all()
 
 
+@pytest.mark.parametrize("sampler", [0, 1])
+def test_filter_resize_u8_bit_exact(ref_scalar, oracle, sampler):
+    """filter_resize(ImageU8) (api/filterAPI.h:42): the reference's one-byte path has its own roundings (two passes when up-scaling)."""
+    rng = np.random.default_rng(16)
+    src = rng.integers(0, 256, (47, 70), dtype=np.uint8)
+    sid = ref_scalar.lib.ref_image_create_u8(70, 47, src.ctypes.data)
+    for nw, nh in [(70, 47), (35, 20), (70, 90), (70, 13), (140, 47), (31, 47), (160, 130), (17, 200), (300, 45), (1, 1)]:
+        rid = ref_scalar.lib.ref_filter_resize_u8(sid, sampler, nw, nh)
+        expected = np.zeros((nh, nw), np.uint8)
+        ref_scalar.lib.ref_image_read_mono(rid, expected.ctypes.data)
+        got, scratch = np.zeros((nh, nw), np.uint8), np.zeros(nw * 47 + 4, np.uint8)
+        oracle.orc_filter_resize_u8(C.byref(abi.Image(got.ctypes.data, nw, nh, nw, 0)), C.byref(abi.Image(src.ctypes.data, 70, 47, 70, 0)), sampler, orcbind.ptr(scratch))
+        assert np.array_equal(expected, got), (nw, nh)
+    ref_scalar.free_all()
+
+
 def test_filter_map_and_magnify_bit_exact(ref_scalar, oracle):
     rng = np.random.default_rng(7)
     src = rng.integers(0, 2 ** 32, (61, 83), dtype=np.uint32)
@@ -325,6 +341,20 @@ def test_occlusion_grid_bit_exact(ref_scalar, oracle, variant):
         assert got["occluded"] > 0  # triangles of models that passed the box test are still culled one by one at renderer_end
     assert np.array_equal(bits(expected["depth"]), bits(got["depth"]))
     assert np.array_equal(expected["color"], got["color"])
+
+
+@pytest.mark.parametrize("variant", [dict(), dict(perspective=False), dict(seed=11, width=333, height=201, top_rows=True)])
+def test_debug_wireframe_bit_exact(ref_scalar, oracle, variant):
+    """renderer_end(renderer, debugWireframe = true) (api/rendererAPI.cpp:362-399): the edges of every command that was not occluded."""
+    import occlusion_scene
+    sc = occlusion_scene.build(**variant)
+    expected = occlusion_scene.run_reference(ref_scalar, sc, wireframe=True)
+    plain = occlusion_scene.run_reference(ref_scalar, sc)
+    ref_scalar.free_all()
+    got = occlusion_scene.run_oracle(oracle, sc, wireframe=True)
+    assert int((expected["color"] != plain["color"]).sum()) > 200  # the overlay is there
+    assert np.array_equal(expected["color"], got["color"])
+    assert np.array_equal(bits(expected["depth"]), bits(got["depth"]))
 
 
 @pytest.mark.parametrize("size", [(1, 1), (3, 5), (33, 9), (640, 3)])

@@ -29,7 +29,7 @@ namespace dfpsr {
 
 static const int TILE_W = 32, TILE_H = 4;  // one warp: 16 x 2 quads
 static const int BATCH = 16;               // commands whose checkpoints are prepared together (BATCH x 2 row pairs = 32 lanes)
-static const int SMALL_ROWS = 4;           // = TILE_H: triangles up to this many rows and SMALL_WIDTH columns are scan-converted by their set-up thread
+static const int SMALL_ROWS = 8;           // large frames: triangles up to this many rows and SMALL_WIDTH columns are scan-converted by their set-up thread
 static const int SMALL_WIDTH = 128;
 static const int SMALL_TILES = 8;          // counting pass: bounding boxes up to this many tiles are counted by the set-up thread
 #ifndef SETUP_THREADS_N
@@ -235,6 +235,21 @@ __device__ __forceinline__ PPoint world_to_screen(const dfpsr_camera &c, const d
 	return camera_to_screen(c, cx, cy, cz);
 }
 
+// ref: math/FPlane3D.h:39-45
+__device__ __forceinline__ bool plane_outside(const float *pl, const PPoint &p) {
+	return !((((pl[0] * p.csx) + (pl[1] * p.csy) + (pl[2] * p.csz)) - pl[3]) <= 0.0f);
+}
+
+// One bit per frustum plane the point lies outside of: cull planes in bits 0-5, clip planes in bits 16-21. The projection pass leaves the
+// codes in PPoint::pad, so that the set-up threads (three corners, two frustums, up to six planes each: a quarter of their instructions
+// when every thread evaluated the planes itself) only combine bits.
+__device__ __forceinline__ int32_t point_outcodes(const dfpsr_camera &c, const PPoint &p) {
+	uint32_t codes = 0u;
+	for (int s = 0; s < c.cullPlaneCount; s++) { if (plane_outside(c.cullPlanes[s], p)) { codes |= 1u << s; } }
+	for (int s = 0; s < c.clipPlaneCount; s++) { if (plane_outside(c.clipPlanes[s], p)) { codes |= 0x10000u << s; } }
+	return (int32_t)codes;
+}
+
 // One launch for every task of the batch: blockIdx.y = task. Grid rows behind the tasks clear the frame's tile counters and totals
 // (`zeroWords` words at `zero`, 16-byte aligned), which saves the frame a separate memset.
 __global__ void __launch_bounds__(256) project_kernel(const TaskParams *__restrict__ tasks, int32_t taskCount, uint4 *__restrict__ zero, uint32_t zeroWords) {
@@ -250,7 +265,9 @@ __global__ void __launch_bounds__(256) project_kernel(const TaskParams *__restri
 	__syncthreads();
 	if (task.triangles != nullptr) { return; }
 	for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < task.pointCount; i += gridDim.x * blockDim.x) {
-		task.projected[i] = world_to_screen(task.camera, task.modelToWorld, task.points[3 * i], task.points[3 * i + 1], task.points[3 * i + 2]);
+		PPoint p = world_to_screen(task.camera, task.modelToWorld, task.points[3 * i], task.points[3 * i + 1], task.points[3 * i + 2]);
+		p.pad = point_outcodes(task.camera, p);
+		task.projected[i] = p;
 	}
 }
 
@@ -263,22 +280,12 @@ __global__ void __launch_bounds__(256) project_points_kernel(const float *__rest
 
 // ------------------------------------------------------------------------------------------------ set-up helpers
 
-// ref: math/FPlane3D.h:39-45
-__device__ __forceinline__ bool plane_outside(const float *pl, const PPoint &p) {
-	return !((((pl[0] * p.csx) + (pl[1] * p.csy) + (pl[2] * p.csz)) - pl[3]) <= 0.0f);
-}
-
-// ref: implementation/render/renderCore.cpp:172-198. 0 hidden, 1 full, 2 partial.
-__device__ int triangle_visibility(const PPoint *p, const dfpsr_camera &c, bool clipFrustum) {
-	int planeCount = clipFrustum ? c.clipPlaneCount : c.cullPlaneCount;
-	const float (*planes)[4] = clipFrustum ? c.clipPlanes : c.cullPlanes;
-	bool any = false;
-	for (int s = 0; s < planeCount; s++) {
-		bool o0 = plane_outside(planes[s], p[0]), o1 = plane_outside(planes[s], p[1]), o2 = plane_outside(planes[s], p[2]);
-		if (o0 && o1 && o2) { return 0; }
-		any = any || o0 || o1 || o2;
-	}
-	return any ? 2 : 1;
+// ref: implementation/render/renderCore.cpp:172-198 on the corners' codes. 0 hidden, 1 full, 2 partial.
+__device__ __forceinline__ int triangle_visibility_codes(const PPoint *p, bool clipFrustum) {
+	const uint32_t shift = clipFrustum ? 16u : 0u;
+	const uint32_t o0 = ((uint32_t)p[0].pad >> shift) & 0xFFFFu, o1 = ((uint32_t)p[1].pad >> shift) & 0xFFFFu, o2 = ((uint32_t)p[2].pad >> shift) & 0xFFFFu;
+	if ((o0 & o1 & o2) != 0u) { return 0; }
+	return (o0 | o1 | o2) != 0u ? 2 : 1;
 }
 
 // ref: implementation/render/ITriangle2D.cpp:55-60
@@ -538,9 +545,9 @@ __device__ void clip_plane(SubVertex *v, int &count, const float *pl) {
 template <typename Emit>
 __device__ void for_each_command(const TaskParams &task, const PPoint *p, const float *alpha, Emit &&emit) {
 	const dfpsr_camera &c = task.camera;
-	if (triangle_visibility(p, c, false) == 0) { return; }
+	if (triangle_visibility_codes(p, false) == 0) { return; } // the corners carry their plane codes (project_kernel / load_triangle)
 	if (!task.depthOnly && task.filter == DFPSR_FILTER_ALPHA && almost_zero(alpha[0]) && almost_zero(alpha[1]) && almost_zero(alpha[2])) { return; }
-	if (triangle_visibility(p, c, true) == 1) {
+	if (triangle_visibility_codes(p, true) == 1) {
 		if (is_frontfacing(p)) {
 			const float subB[3] = {0.0f, 1.0f, 0.0f}, subC[3] = {0.0f, 0.0f, 1.0f};
 			emit(p, subB, subC);
@@ -575,6 +582,7 @@ __device__ bool load_triangle(const TaskParams &task, int32_t local, PPoint *p, 
 #pragma unroll
 		for (int k = 0; k < 3; k++) {
 			p[k] = *(const PPoint *)&t.pos[k];
+			p[k].pad = point_outcodes(task.camera, p[k]); // pre-projected corners come from the host without codes
 #pragma unroll
 			for (int ch = 0; ch < 4; ch++) { colors[k][ch] = t.colors[k][ch]; tex[k][ch] = t.texCoords[k][ch]; }
 		}
@@ -2636,11 +2644,13 @@ static int run_frame(dfpsr_renderer *r, cudaStream_t stream, bool allowAsync) {
 	frame.blockCmds = (uint32_t *)r->blockCmds.ptr; frame.blockRows = (uint32_t *)r->blockRows.ptr;
 	frame.tileCount = (uint32_t *)r->tileCount.ptr; frame.tileOffset = (uint32_t *)r->tileOffset.ptr; frame.tileCursor = (uint32_t *)r->tileCursor.ptr;
 	frame.totals = frame.tileCount + tileTotal;
-	// Only triangles within one tile row stay with their set-up thread; everything taller goes to the unit queue (one thread per row pair).
-	// A single frame is bound by its longest thread, and the 256-view batch measured 43.45 us per frame at 4 rows against 43.6 (8), 44.0 (16)
-	// and 44.7 (32). DFPSR_SMALL_ROWS overrides for experiments.
+	// A frame that does not fill the machine (one 1080p terrain frame: 7.6 k slots) is bound by its longest thread: only triangles within one
+	// tile row stay with their set-up thread, everything taller goes to the unit queue (one thread per row pair). Large frames keep the
+	// serial scan conversion of triangles up to SMALL_ROWS rows: measured on the 256-view batch 43.45 us per frame at 4 rows, 43.6 at 8,
+	// 44.0 at 16, 44.7 at 32 — but the 2 M tiny triangles of BASELINE config 3 (2-3 pixels tall, up to 6 aligned rows) take 930 us at 4
+	// (a third of them queue a unit each) against 620 us at 8. DFPSR_SMALL_ROWS overrides for experiments.
 	static const int smallRowsOverride = getenv("DFPSR_SMALL_ROWS") ? atoi(getenv("DFPSR_SMALL_ROWS")) : -1;
-	frame.smallRows = SMALL_ROWS;
+	frame.smallRows = slotTotal <= sm_count() * 1024 ? TILE_H : SMALL_ROWS;
 	if (smallRowsOverride >= 0) { frame.smallRows = smallRowsOverride; }
 
 	if (taskCount == 0) {

@@ -120,8 +120,9 @@ def test_renderer_end_returns_before_the_frame_is_drawn(cuda):
     lib.check(cuda.dfpsr_set_default_async(1))
     try:
         call = lambda: lib.check(cuda.dfpsr_model_render_views(C.byref(model.desc), C.byref(ident), ci, di, cams, views, 1, lib.stream_ptr()))
-        call()  # sizes the pools (it waits for its counts unless this thread's renderer already has a history)
-        lib.check(cuda.dfpsr_flush())  # torch reads the targets directly: the frame must have been verified (and redrawn if it outgrew the pools)
+        for _ in range(2):  # the first call waits for its counts and leaves the history, the second grows the pools to their asynchronous head room
+            call()
+            lib.check(cuda.dfpsr_flush())  # torch reads the targets directly: the frame must have been verified (and redrawn if it outgrew the pools)
         torch.cuda.synchronize()
         reference = color[views - 1].clone()
         color.zero_()

@@ -1,1 +1,3 @@
-python -m pytest tests/test_gpu_pixel_ops.py tests/test_gpu_shim.py tests/test_gpu_raster.py tests/test_gpu_draw.py -x -q -m gpu 2>&1 | tail -8
+python tools/tiny_profile.py
+python -m pytest tests -x -q -m gpu 2>&1 | tail -5
+DFPSR_ASYNC=1 python -m pytest tests -x -q -m gpu 2>&1 | tail -5

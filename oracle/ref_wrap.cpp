@@ -626,6 +626,22 @@ int ref_sprite_type_create(int atlas, const char *iniText, const char *folder, c
 }
 
 int ref_sprite_type_count() { return spriteWorld_getSpriteTypeCount(); }
+// Real media: the SDK's own <name>.png + <name>.ini where they lie (SDK/sandbox/media/images), through the reference's own loader.
+int ref_sprite_type_load(const char *folder, const char *name) {
+	ensureStarted();
+	return spriteWorld_loadSpriteTypeFromFile(string_combine(folder), string_combine(name));
+}
+int ref_image_load(const char *path) { // decoded by the reference's image_load_RgbaU8 (stb_image), RGBA order
+	ensureStarted();
+	AnyImage img;
+	img.kind = 1;
+	img.rgba = image_load_RgbaU8(string_combine(path));
+	if (!image_exists(img.rgba)) { return -1; }
+	g_images.push_back(img);
+	return (int)g_images.size() - 1;
+}
+// The reference's own decimal parser (sprite configuration numbers go through it: spriteAPI.cpp:56-101)
+double ref_string_to_double(const char *text) { return string_toDouble(string_combine(text)); }
 
 int ref_model_type_create(int dense, int shadowModel) {
 	ensureStarted();

@@ -50,6 +50,7 @@ def load(flavour="scalar"):
         "ref_light_directed": (None, [V, i, i, p, f, p, i]),
         "ref_light_point": (None, [V, p, i, i, i, p, f, f, p, i]),
         "ref_light_blend": (None, [i, i, i]),
+        "ref_sprite_type_load": (i, [C.c_char_p, C.c_char_p]), "ref_image_load": (i, [C.c_char_p]), "ref_string_to_double": (C.c_double, [C.c_char_p]),
         "ref_filter_resize": (i, [i, i, i, i]), "ref_filter_resize_u8": (i, [i, i, i, i]), "ref_filter_map": (None, [i, i, p, i, i, i]),
         "ref_filter_block_magnify": (None, [i, i, i, i]),
         "ref_image_create_u8": (i, [i, i, p]),

@@ -183,13 +183,15 @@ def _i3(values):
 
 # ------------------------------------------------------------------------------------------------ reference back end
 
-def run_reference(ref, assets, script, folder, shadow_res=SHADOW_RES, keep_frames=True, timing=None):
-    """Returns one dict of buffers per draw."""
+def run_reference(ref, assets, script, folder, shadow_res=SHADOW_RES, keep_frames=True, timing=None, sprite_ids=None):
+    """Returns one dict of buffers per draw. sprite_ids: sprite types the reference has loaded already (real media), else they are made from the assets."""
     lib = ref.lib
-    sprite_ids, model_ids = [], []
-    for k, t in enumerate(assets["sprites"]):
-        atlas = ref.rgba(t["atlas"])
-        sprite_ids.append(lib.ref_sprite_type_create(atlas, sprite_ini(t).encode(), folder.encode(), f"sprite{k}_{lib.ref_sprite_type_count()}".encode()))
+    model_ids = []
+    if sprite_ids is None:
+        sprite_ids = []
+        for k, t in enumerate(assets["sprites"]):
+            atlas = ref.rgba(t["atlas"])
+            sprite_ids.append(lib.ref_sprite_type_create(atlas, sprite_ini(t).encode(), folder.encode(), f"sprite{k}_{lib.ref_sprite_type_count()}".encode()))
     for m in assets["models"]:
         dense = lib.ref_dense_model_create(ref.model(m["points"], m["polygons"]))
         model_ids.append(lib.ref_model_type_create(dense, ref.model(m["shadow_points"], m["shadow_polygons"])))

@@ -47,6 +47,37 @@ def test_sprite_world_session_bit_exact(cuda, oracle, assets):
     assert launches > 0
 
 
+def media_assets():
+    """The Sandbox's real sprite media as decoded and parsed by the reference (tests/golden/make_sandbox_media_golden.py)."""
+    golden_dir = os.path.dirname(GOLDEN)
+    data = np.load(os.path.join(golden_dir, "sandbox_media.npz"))
+    entry = json.load(open(os.path.join(golden_dir, "sandbox_media.json")))
+    sprites = []
+    for name in entry["names"]:
+        atlas, numbers, bounds = data[name + "_atlas"], data[name + "_numbers"], data[name + "_bounds"]
+        frames = int(numbers[2])
+        t = {"atlas": atlas, "frame_w": atlas.shape[1] // 3, "frame_h": atlas.shape[0] // frames, "frames": frames, "center": (int(numbers[0]), int(numbers[1])),
+             "min": [np.float32(v) for v in bounds[:3]], "max": [np.float32(v) for v in bounds[3:]], "points": None, "indices": None}
+        if name + "_points" in data:
+            t["points"], t["indices"] = np.ascontiguousarray(data[name + "_points"], np.float32), np.ascontiguousarray(data[name + "_indices"], np.int32)
+        sprites.append(t)
+    script = [tuple(tuple(v) if isinstance(v, list) else v for v in action) for action in entry["script"]]
+    return {"sprites": sprites, "models": []}, script, entry["frames"]
+
+
+def test_sandbox_real_media_golden(cuda, oracle):
+    """SDK/sandbox/media/images/{Floor,Pillar,WoodenBarrel} (real atlases, real .ini numbers, real shadow shapes) in a lit world: every
+    buffer of both frames equals what the unmodified reference drew from the files themselves, and the oracle replay agrees."""
+    media, script, golden = media_assets()
+    got = sws.run_cuda(cuda, lib, media, script)
+    expected = sws.run_plan_oracle(cuda, lib.check, oracle, media, script)
+    assert len(got) == len(golden) == 2
+    for index, (a, b, entry) in enumerate(zip(got, expected, golden)):
+        for name in BUFFERS:
+            assert np.array_equal(a[name].view(np.uint32), b[name].view(np.uint32)), (index, name)
+        assert sws.frame_hashes(a) == {k: entry[k] for k in BUFFERS}, index
+
+
 def test_sprite_world_draw_host_round_trip(cuda, assets):
     """dfpsr_sprite_world_draw_host returns the same colour image as the device call."""
     import ctypes as C

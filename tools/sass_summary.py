@@ -44,7 +44,7 @@ for key in sorted(usage, key=lambda k: demangled[k]):
     reg, stack, shared, local = usage[key]
     counts = mix.get(key, {})
     total = sum(counts.values())
-    short = demangled[key].replace("dfpsr::", "").split("(")[0].replace("void ", "")
+    short = demangled[key].replace("(anonymous namespace)::", "").replace("dfpsr::", "").split("(")[0].replace("void ", "")
     lines.append(f"| {short} | {reg} | {stack} | {shared} | {total} | " + " | ".join(str(sum(counts.get(op, 0) for op in ops)) for _, ops in groups) + " |")
 text = "\n".join(lines) + "\n"
 if len(sys.argv) > 1:

@@ -4,6 +4,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <atomic>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -34,7 +35,7 @@ extern thread_local char g_error[512];
 	} while (0)
 
 // ---- launch accounting: every kernel launch of this library goes through DFPSR_LAUNCH
-extern unsigned long long g_launches;
+extern std::atomic<unsigned long long> g_launches;
 int check_launch(const char *name);
 
 // Optional per-kernel device timing (dfpsr_profile_enable): CUDA events on the launching stream around each launch.
@@ -54,7 +55,7 @@ int verify_pending_frames();
 		if (dfpsr::g_profile) { dfpsr::profile_begin(#kernel, (stream)); }        \
 		kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);               \
 		if (dfpsr::g_profile) { dfpsr::profile_end((stream)); }                   \
-		dfpsr::g_launches++;                                                      \
+		dfpsr::g_launches.fetch_add(1, std::memory_order_relaxed);                                                      \
 		if (dfpsr::check_launch(#kernel)) { return 1; }                           \
 	} while (0)
 
@@ -85,7 +86,7 @@ inline cudaError_t launch_chained(void (*kernel)(KArgs...), dim3 grid, dim3 bloc
 			cudaError_t chainError_ = dfpsr::launch_chained(kernel, dim3(grid), dim3(block), (smem), (stream), __VA_ARGS__); \
 			if (chainError_ != cudaSuccess) { dfpsr::set_error("launch of %s failed: %s", #kernel, cudaGetErrorString(chainError_)); return 1; } \
 		}                                                                                                                    \
-		dfpsr::g_launches++;                                                                                                 \
+		dfpsr::g_launches.fetch_add(1, std::memory_order_relaxed);                                                                                                 \
 		if (dfpsr::check_launch(#kernel)) { return 1; }                                                                      \
 	} while (0)
 

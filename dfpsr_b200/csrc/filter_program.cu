@@ -186,7 +186,7 @@ int dfpsr_filter_map_program(const dfpsr_image *target, const char *body, const 
 	const cudaError_t launched = cudaLaunchKernel((const void *)compiled.kernel, grid, block, arguments, 0, as_stream(stream));
 	if (g_profile) { profile_end(as_stream(stream)); }
 	DFPSR_REQUIRE(launched == cudaSuccess, "launch of the compiled pixel function failed: %s", cudaGetErrorString(launched));
-	g_launches++;
+	g_launches.fetch_add(1, std::memory_order_relaxed);
 	return check_launch("map_program_kernel");
 }
 

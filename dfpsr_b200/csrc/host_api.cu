@@ -6,13 +6,15 @@
 #include <stdlib.h>
 #include <float.h>
 #include <stdarg.h>
+#include <atomic>
+#include <mutex>
 #include <vector>
 #include <utility>
 
 namespace dfpsr {
 
 thread_local char g_error[512] = "";
-unsigned long long g_launches = 0;
+std::atomic<unsigned long long> g_launches{0}; // launches of every thread (relaxed: a statistic, nothing is ordered by it)
 
 void set_error(const char *fmt, ...) {
 	va_list args;
@@ -37,10 +39,12 @@ bool g_chainLaunches = initial_chain_launches();
 bool g_profile = false;
 namespace {
 struct ProfileEntry { const char *name; std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events; double ms = 0.0; long long launches = 0; };
+// The table is shared by all threads and guarded by g_profileMutex; the launch a thread is in the middle of is its own.
+std::mutex g_profileMutex;
 std::vector<ProfileEntry> g_profileEntries;
-ProfileEntry *g_profileCurrent = nullptr;
-cudaEvent_t g_profileStart;
-void profile_collect() {
+thread_local int g_profileCurrent = -1;
+thread_local cudaEvent_t g_profileStart;
+void profile_collect() { // with g_profileMutex held
 	for (ProfileEntry &e : g_profileEntries) {
 		for (auto &pair : e.events) {
 			cudaEventSynchronize(pair.second);
@@ -53,19 +57,25 @@ void profile_collect() {
 }
 }
 void profile_begin(const char *name, cudaStream_t stream) {
-	g_profileCurrent = nullptr;
-	for (ProfileEntry &e : g_profileEntries) { if (strcmp(e.name, name) == 0) { g_profileCurrent = &e; break; } }
-	if (!g_profileCurrent) { g_profileEntries.push_back(ProfileEntry{name, {}, 0.0, 0}); g_profileCurrent = &g_profileEntries.back(); }
+	{
+		std::lock_guard<std::mutex> lock(g_profileMutex);
+		g_profileCurrent = -1;
+		for (size_t i = 0; i < g_profileEntries.size(); i++) { if (strcmp(g_profileEntries[i].name, name) == 0) { g_profileCurrent = (int)i; break; } }
+		if (g_profileCurrent < 0) { g_profileEntries.push_back(ProfileEntry{name, {}, 0.0, 0}); g_profileCurrent = (int)g_profileEntries.size() - 1; }
+	}
 	cudaEventCreate(&g_profileStart);
 	cudaEventRecord(g_profileStart, stream);
 }
 void profile_end(cudaStream_t stream) {
-	if (!g_profileCurrent) { return; }
+	if (g_profileCurrent < 0) { return; }
 	cudaEvent_t stop;
 	cudaEventCreate(&stop);
 	cudaEventRecord(stop, stream);
-	g_profileCurrent->events.push_back({g_profileStart, stop});
-	if (g_profileCurrent->events.size() >= 4096) { profile_collect(); }
+	std::lock_guard<std::mutex> lock(g_profileMutex);
+	if (g_profileCurrent >= (int)g_profileEntries.size()) { return; } // the table was reset between the two halves of this launch
+	ProfileEntry &entry = g_profileEntries[(size_t)g_profileCurrent];
+	entry.events.push_back({g_profileStart, stop});
+	if (entry.events.size() >= 4096) { profile_collect(); }
 }
 
 int sm_count() {
@@ -165,17 +175,24 @@ int dfpsr_init(int device) {
 }
 
 int dfpsr_profile_enable(int enabled) {
+	std::lock_guard<std::mutex> lock(g_profileMutex);
 	if (!enabled) { profile_collect(); }
 	g_profile = enabled != 0;
 	return 0;
 }
 int dfpsr_profile_reset(void) {
+	std::lock_guard<std::mutex> lock(g_profileMutex);
 	profile_collect();
 	g_profileEntries.clear();
 	return 0;
 }
-int dfpsr_profile_count(void) { profile_collect(); return (int)g_profileEntries.size(); }
+int dfpsr_profile_count(void) {
+	std::lock_guard<std::mutex> lock(g_profileMutex);
+	profile_collect();
+	return (int)g_profileEntries.size();
+}
 int dfpsr_profile_read(int index, const char **name, double *milliseconds, int64_t *launches) {
+	std::lock_guard<std::mutex> lock(g_profileMutex);
 	profile_collect();
 	DFPSR_REQUIRE(index >= 0 && index < (int)g_profileEntries.size(), "profile_read: index out of range");
 	*name = g_profileEntries[index].name;

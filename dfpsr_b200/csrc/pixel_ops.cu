@@ -1237,7 +1237,7 @@ extern "C" int dfpsr_selftest_rsqrt(uint32_t firstBits, uint32_t count, uint64_t
 	cudaError_t err = cudaMemsetAsync(counter, 0, sizeof(unsigned long long), dfpsr::as_stream(stream));
 	if (err == cudaSuccess && count > 0) {
 		dfpsr::selftest_rsqrt_kernel<<<dfpsr::sm_count() * 8, 256, 0, dfpsr::as_stream(stream)>>>(firstBits, count, counter);
-		dfpsr::g_launches++;
+		dfpsr::g_launches.fetch_add(1, std::memory_order_relaxed);
 		err = cudaGetLastError();
 	}
 	unsigned long long result = 0;

@@ -1740,6 +1740,7 @@ __device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.
 
 enum : int { TILE_IMMEDIATE = 0, TILE_DEPTH_ONLY = 1, TILE_DEFERRED = 2, TILE_DEFERRED_RAW = 3 }; // RAW: deferred shading without prepared shading inputs (frames without textures)
 static const uint32_t NO_WINNER = 0xFFFFFFFFu;
+static const uint32_t SHADER_PATTERN = CMD_AFFINE | CMD_HAS_DIFFUSE | CMD_HAS_LIGHT | CMD_HAS_FADE | CMD_COLORLESS | (0xFFFu << 8), PATTERN_TAKEN = 0x80000000u, PATTERN_MIXED = 0xFFFFFFFFu;
 
 // MODE: TILE_IMMEDIATE  commands are shaded quad by quad in submission order (needed when a frame holds alpha-filtered commands)
 //       TILE_DEPTH_ONLY the depth pass of model_renderDepth (renderCore.cpp:343-443)
@@ -1843,6 +1844,9 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32, (MODE == TILE_DEFERRED ? (E
 	uint32_t win[4] = {NO_WINNER, NO_WINNER, NO_WINNER, NO_WINNER};
 	float su[4] = {0.0f, 0.0f, 0.0f, 0.0f}, sv[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 	uint32_t mips = 0u;
+	// the shader pattern (variant flags + diffuse texture) shared by every command that took one of the lane's pixels so far: 0 nothing
+	// taken, PATTERN_MIXED different patterns. Conservative for the shading pass's fast path (a pattern that was overwritten still counts).
+	uint32_t lanePattern = 0u;
 
 	// lists of up to LOCAL_SORT entries are sorted here and kept in shared memory; longer ones were sorted by sort_lists_kernel
 	uint32_t *sKeys = sKeysAll[warp];
@@ -2170,6 +2174,10 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32, (MODE == TILE_DEFERRED ? (E
 				if (vis[2]) { if (repeatUpper) DFPSR_TAKE(0, 2, 0x3214) else DFPSR_TAKE(2, 2, 0x3410) }
 				if (vis[3]) { if (repeatUpper) DFPSR_TAKE(1, 3, 0x3240) else DFPSR_TAKE(3, 3, 0x4210) }
 #undef DFPSR_TAKE
+				{
+					const uint32_t pattern = (flags & SHADER_PATTERN) | PATTERN_TAKEN;
+					lanePattern = (lanePattern == 0u || lanePattern == pattern) ? pattern : PATTERN_MIXED;
+				}
 				dirty = true;
 			} else {
 			// ref: shader/fillerTemplates.h:196-243 — weights
@@ -2252,23 +2260,12 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32, (MODE == TILE_DEFERRED ? (E
 		// ---- shading pass: every pixel that some command won is shaded once, by that command
 		if (hasColor) {
 			const bool valid[4] = {win[0] != NO_WINNER, win[1] != NO_WINNER, win[2] != NO_WINNER, win[3] != NO_WINNER};
-			uint32_t fl[4];
-#pragma unroll
-			for (int l = 0; l < 4; l++) { fl[l] = valid[l] ? __ldg(&frame.cmds[win[l]].flags) : 0u; }
-			// Fast path, chosen by the whole warp: every winner is a plain textured command (diffuse texture, no light map, colourless
-			// vertices: RgbaMultiply.h:75-79) and the lane's winners share one texture. The four pixels are then sampled side by side —
-			// sixteen texel loads in flight — instead of one shader variant dispatch per pixel.
-			const uint32_t PATTERN = CMD_HAS_DIFFUSE | CMD_HAS_LIGHT | CMD_HAS_FADE | CMD_COLORLESS | (0xFFFu << 8);
-			uint32_t common = 0u;
-			bool plain = true;
-#pragma unroll
-			for (int l = 0; l < 4; l++) {
-				if (valid[l]) {
-					const uint32_t pattern = fl[l] & PATTERN;
-					if (common == 0u) { common = pattern; }
-					plain = plain && pattern == common && (pattern & 0xFFu) == (CMD_HAS_DIFFUSE | CMD_COLORLESS);
-				}
-			}
+			// Fast path, chosen by the whole warp: every command that took a pixel of the warp's lanes is a plain textured command (diffuse
+			// texture, no light map, colourless vertices: RgbaMultiply.h:75-79) and each lane saw one texture only (lanePattern, kept by the
+			// visibility pass: no flag loads here). The four pixels are then sampled side by side — sixteen texel loads in flight — instead
+			// of one shader variant dispatch per pixel.
+			const uint32_t common = lanePattern;
+			const bool plain = common == 0u || (common != PATTERN_MIXED && (common & (CMD_HAS_DIFFUSE | CMD_HAS_LIGHT | CMD_HAS_FADE | CMD_COLORLESS)) == (CMD_HAS_DIFFUSE | CMD_COLORLESS));
 			if (__all_sync(0xffffffffu, plain)) {
 				if (common != 0u) {
 					const TexDev t = load_tex(frame.textures, (common >> 8) & 0xFFFu);
@@ -2285,7 +2282,7 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32, (MODE == TILE_DEFERRED ? (E
 									t0 = __ldg(words + 7); t1 = __ldg(words + 8);
 								}
 								float wb, wc;
-								if (fl[l] & CMD_AFFINE) { wb = su[l]; wc = sv[l]; }
+								if (common & CMD_AFFINE) { wb = su[l]; wc = sv[l]; }
 								else { const float linearDepth = reciprocal_w<EXACT>(dep[l]); wb = su[l] * linearDepth; wc = sv[l] * linearDepth; }
 								const float wa = 1.0f - (wb + wc);
 								const float cu[3] = {t0.x, t0.y, t0.z}, cv[3] = {t0.w, t1.x, t1.y};

@@ -119,7 +119,7 @@ struct __align__(16) ViewDev {
 	float clearDepth;
 	uint32_t tileBase;           // index of this view's first tile in the batch
 	int32_t tilesX, tilesY;
-	int32_t pad_[2];
+	uint32_t packShifts, packSelector; // pack_shifts / pack_selector of the colour target's pack order, formed once on the host (44 instructions per tile otherwise)
 };
 static_assert(sizeof(ViewDev) == 96, "ViewDev layout");
 
@@ -1487,7 +1487,7 @@ __device__ __forceinline__ float interpolate3(const float *d, float wa, float wb
 }
 
 // __byte_perm selector that moves the bytes (red, green, blue, alpha) of a texel to the positions pack_shifts() describes
-__device__ __forceinline__ uint32_t pack_selector(uint32_t shifts) {
+__host__ __device__ __forceinline__ uint32_t pack_selector(uint32_t shifts) {
 	uint32_t selector = 0u;
 #pragma unroll
 	for (uint32_t channel = 0; channel < 4; channel++) { selector |= channel << (((shifts >> (8u * channel)) & 31u) >> 1); } // byte position p takes nibble p
@@ -1821,7 +1821,7 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32, (MODE == TILE_DEFERRED ? (E
 	const dfpsr_image color = vw.color, depth = vw.depth;
 	const bool hasColor = !DEPTH_ONLY && color.data != nullptr, hasDepth = depth.data != nullptr;
 	const bool in[4] = {x0 < width && y1 < height, x0 + 1 < width && y1 < height, x0 < width && y2 < height, x0 + 1 < width && y2 < height};
-	const uint32_t shifts = pack_shifts(color.packOrder);
+	const uint32_t shifts = vw.packShifts;
 	// ref: shader/fillerTemplates.h:286-331 — the last row pair of an odd-height target has no lower row and the reference lets its
 	// lower-row pointers repeat the upper row: unclipped quads then read and overwrite lanes 0/1 through lanes 2/3.
 	const bool aliasLower = y2 >= height;
@@ -2295,7 +2295,7 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32, (MODE == TILE_DEFERRED ? (E
 					for (int l = 0; l < 4; l++) { texel[l] = sample_bilinear(t, su[l], sv[l], (mips >> (8 * l)) & 0xFFu); } // (u, v) by now; pixels nobody won sample (0, 0) and are dropped
 					// byte -> float -> min(x, 255.1) -> truncation (RgbaMultiply.h:75-79, PackOrder.h:186-213) is the identity on 0..255: the
 					// texel's bytes only move to the target's pack order, one byte permute per pixel
-					const uint32_t selector = pack_selector(shifts);
+					const uint32_t selector = vw.packSelector;
 #pragma unroll
 					for (int l = 0; l < 4; l++) { if (valid[l]) { col[l] = __byte_perm(texel[l], 0u, selector); } }
 				}
@@ -2474,6 +2474,7 @@ static int make_view(ViewDev &v, const dfpsr_image *color, const dfpsr_image *de
 	v.clear = clear ? 1 : 0; v.clearColor = clearColor; v.clearDepth = clearDepth;
 	v.tilesX = (v.width + TILE_W - 1) / TILE_W;
 	v.tilesY = (v.height + TILE_H - 1) / TILE_H;
+	v.packShifts = pack_shifts(v.color.packOrder); v.packSelector = pack_selector(v.packShifts);
 	return 0;
 }
 

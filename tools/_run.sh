@@ -1,2 +1,1 @@
-python -m pytest tests/test_gpu_raster.py tests/test_gpu_tolerance.py tests/test_gpu_async.py tests/test_gpu_shim.py tests/test_gpu_sprite_world.py tests/test_gpu_pixel_ops.py -x -q -m gpu 2>&1 | tail -4
-python tools/tile_ab.py 256 --tiny 2>&1
+for v in d7 d9 d10; do echo "== $v"; DFPSR_LIB=dfpsr_b200/variants/libdfpsr_b200_$v.so python tools/tile_ab.py 256 2>&1 | grep "exact\] batch"; done

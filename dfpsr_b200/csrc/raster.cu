@@ -777,7 +777,9 @@ __device__ __forceinline__ void chk_store(ChkRec *dst, int32_t mode, const float
 // Walks one row pair of a large triangle like the reference's fillShapeSuper does (shader/fillerTemplates.h:329-372: left-edge quads, the
 // unclipped inner run whose four lanes advance separately, the closing multiplication, right-edge quads) and leaves a checkpoint of the
 // running sums at the row pair's first quad and at every tile column boundary. recs is indexed by tile column - firstColumn.
-__device__ void chk_walk_row_pair(const float *start, const float *dx, const float *dy, int2 upperRow, int2 lowerRow, int32_t y1, ChkRec *recs, int32_t firstColumn) {
+// Kept out of line on purpose: inlined into big_units_kernel, nvcc 12.9 generated code for the tile-wise inner loop below that lost tile
+// entries of some row pairs (the parity tests fail; the same source is bit-identical to the per-step loop on the host and out of line).
+__device__ __noinline__ void chk_walk_row_pair(const float *start, const float *dx, const float *dy, int2 upperRow, int2 lowerRow, int32_t y1, ChkRec *recs, int32_t firstColumn) {
 	const int32_t outerStart = min(upperRow.x, lowerRow.x), outerEnd = max(upperRow.y, lowerRow.y);
 	const int32_t innerStart = max(upperRow.x, lowerRow.x), innerEnd = min(upperRow.y, lowerRow.y);
 	const int32_t obs = outerStart & ~1, obe = (outerEnd + 1) & ~1, ibs = (innerStart + 1) & ~1, ibe = innerEnd & ~1;
@@ -817,11 +819,26 @@ __device__ void chk_walk_row_pair(const float *start, const float *dx, const flo
 			v[15 + k] = lo[k] + (dx2[k] * quadCount);
 		}
 	}
-	while (x < ibe) {
+	// The inner run carries most of a wide row pair (a triangle across a 1080p target: 900 steps of twelve dependent additions, the
+	// longest thread of a single frame's unit kernel). It is walked tile by tile: up to the next tile edge, then whole tiles of sixteen
+	// steps without any per-step test, with the checkpoint of each edge in between.
+	{
+		const int32_t nextEdge = min((x + TILE_W) & ~(TILE_W - 1), ibe);
+		while (x < nextEdge) {
 #pragma unroll
-		for (int i = 0; i < 12; i++) { v[i] += dx2[i / 4]; }
-		x += 2;
-		if ((x & (TILE_W - 1)) == 0 && x < ibe) { chk_store(recs + (x / TILE_W - firstColumn), 1, v, 18, x); if (x >= lastEdge) { return; } }
+			for (int i = 0; i < 12; i++) { v[i] += dx2[i / 4]; }
+			x += 2;
+		}
+	}
+	while (x < ibe) { // x is a tile edge inside the run
+		chk_store(recs + (x / TILE_W - firstColumn), 1, v, 18, x);
+		if (x >= lastEdge) { return; }
+		const int32_t stop = min(x + TILE_W, ibe);
+		while (x < stop) {
+#pragma unroll
+			for (int i = 0; i < 12; i++) { v[i] += dx2[i / 4]; }
+			x += 2;
+		}
 	}
 #pragma unroll
 	for (int k = 0; k < 6; k++) { v[k] = v[12 + k]; }
@@ -2767,6 +2784,14 @@ static int run_frame(dfpsr_renderer *r, cudaStream_t stream, bool allowAsync) {
 				if (unitEstimate > 0 && (grow_pool(r->bigItems, pool_elements(r->cmds, sizeof(Cmd), 0), sizeof(BigItem), 1.0, 0) || grow_pool(r->bigUnits, unitEstimate, 4, slack, 0))) { return 1; }
 				if (maxTile > (uint32_t)SORT_SMEM && grow_pool(r->sortTmp, pool_elements(r->tileList, 4, 16), 4, 1.0, 16)) { return 1; }
 				set_pools();
+				// DFPSR_POISON=1 (tests): the checkpoint and row pools are filled with 0xFF before the emit pass, so that a record the tile
+				// kernel needs and nothing wrote reads as "nothing here" (mode -1, empty rows) and shows up as missing pixels instead of
+				// passing on what an earlier frame left at the same address.
+				static const bool poison = getenv("DFPSR_POISON") != nullptr && atoi(getenv("DFPSR_POISON")) != 0;
+				if (poison) {
+					if (r->chk.ptr && r->chk.capacity > 0) { DFPSR_CHECK_CUDA(cudaMemsetAsync(r->chk.ptr, 0xFF, r->chk.capacity, stream)); }
+					if (r->rows.ptr && r->rows.capacity > 0) { DFPSR_CHECK_CUDA(cudaMemsetAsync(r->rows.ptr, 0xFF, r->rows.capacity, stream)); }
+				}
 			}
 		} else {
 			PendingFrame &p = r->pending;

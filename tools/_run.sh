@@ -1,1 +1,3 @@
-for v in d7 d9 d10; do echo "== $v"; DFPSR_LIB=dfpsr_b200/variants/libdfpsr_b200_$v.so python tools/tile_ab.py 256 2>&1 | grep "exact\] batch"; done
+for i in 1 2 3 4 5 6; do python -m pytest tests/test_gpu_raster.py tests/test_gpu_async.py -x -q -m gpu 2>&1 | tail -1; done
+for i in 1 2 3 4; do DFPSR_ASYNC=1 python -m pytest tests/test_gpu_raster.py tests/test_gpu_shim.py -x -q -m gpu 2>&1 | tail -1; done
+for i in 1 2; do DFPSR_CHAIN=0 python -m pytest tests/test_gpu_raster.py -x -q -m gpu 2>&1 | tail -1; done

@@ -560,3 +560,17 @@ def test_terrain_1080p_view_batch_golden(cuda):
             assert sha(host_u32(color[frame])) == entry["color_sha256"], f"frame {frame} colour"
             checked += 1
     assert checked >= 3
+
+
+def test_parity_does_not_depend_on_what_the_pools_held(cuda):
+    """DFPSR_POISON=1 fills the row-interval and checkpoint pools with 0xFF before every emit pass: a record the tile kernel needs and
+    nothing wrote then reads as 'nothing here' instead of whatever an earlier frame left at the same address. The environment variable is
+    read once per process, so the parity tests that reuse one renderer for many different frames run again in a child process."""
+    import subprocess
+    import sys
+    env = dict(os.environ, DFPSR_POISON="1")
+    result = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider",
+                             "-k", "terrain_matches_oracle or random_soup_matches_oracle or odd_target_sizes or occlusion_grid_matches_oracle"],
+                            env=env, capture_output=True, text=True, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert result.returncode == 0, result.stdout[-3000:] + result.stderr[-2000:]
+    assert " passed" in result.stdout

@@ -1,3 +1,2 @@
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 8 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_r2_n8.json 2> gpurun_out/bench_r2_n8.err; head -c 260 gpurun_out/bench_r2_n8.json; echo
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 4 --steps 10 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/bench_r2_n4.json 2> gpurun_out/bench_r2_n4.err; head -c 260 gpurun_out/bench_r2_n4.json; echo
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 2 --steps 10 --warmup 3 --no-cpu-baseline --no-extras > gpurun_out/bench_r2_n2.json 2> gpurun_out/bench_r2_n2.err; head -c 260 gpurun_out/bench_r2_n2.json; echo
+python -m pytest tests -x -q -m gpu 2>&1 | tail -3
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2

@@ -104,6 +104,25 @@ def run_oracle(lib, sc, wireframe=False):
     return {"color": color, "depth": depth, "visible": visible, "commands": n, "occluded": skipped.value}
 
 
+def run_oracle_without_occluders(lib, sc, wireframe=False):
+    """The same models in the same order through the oracle's renderer with no occluder calls (nothing is skipped)."""
+    import orcbind
+    IM = orcbind.image_of
+    cam = orcbind.camera(sc["camera"])
+    color, depth = sc["color0"].copy(), sc["depth0"].copy()
+    r = lib.orc_renderer_create()
+    wall, keep = orcbind.model_of(*sc["wall"])
+    models = [orcbind.model_of(m["points"], m["polygons"]) for m in sc["models"]]
+    lib.orc_renderer_begin(r, C.byref(IM(color)), C.byref(IM(depth)))
+    lib.orc_renderer_give_task(r, C.byref(wall), C.byref(sc["wall_transform"]), C.byref(cam))
+    for m, (om, _k) in zip(sc["models"], models):
+        lib.orc_renderer_give_task(r, C.byref(om), C.byref(m["transform"]), C.byref(cam))
+    lib.orc_renderer_set_debug_wireframe(r, 1 if wireframe else 0)
+    n = lib.orc_renderer_end(r, None)
+    lib.orc_renderer_destroy(r)
+    return {"color": color, "depth": depth, "commands": n}
+
+
 def run_cuda(cuda, sc, wireframe=False):
     from dfpsr_b200 import lib
     cam = lib.camera(sc["camera"])

@@ -138,6 +138,26 @@ def test_filter_resize_u8(cuda, oracle, sampler):
         assert np.array_equal(got, e), f"u8 resize to {nw}x{nh} sampler={sampler}: {int((got != e).sum())} bytes differ"
 
 
+def test_filter_resize_u8_with_strided_images(cuda, oracle):
+    """Source and target are windows of larger images (row stride > width, unaligned first pixel): only the window is read and written."""
+    import torch
+    rng = np.random.default_rng(17)
+    big_src = rng.integers(0, 256, (60, 101), dtype=np.uint8)
+    big_dst = rng.integers(0, 256, (150, 203), dtype=np.uint8)
+    sx, sy, sw, sh = 3, 5, 70, 47
+    dx, dy, dw, dh = 7, 9, 160, 130
+    ts, td = torch.from_numpy(big_src).cuda(), torch.from_numpy(big_dst).cuda()
+    scratch = torch.zeros(dw * sh + 4, dtype=torch.uint8, device="cuda")
+    lib.check(cuda.dfpsr_filter_resize_u8(C.byref(abi.Image(td.data_ptr() + dy * 203 + dx, dw, dh, 203, 0)), C.byref(abi.Image(ts.data_ptr() + sy * 101 + sx, sw, sh, 101, 0)),
+                                          abi.SAMPLER_LINEAR, scratch.data_ptr(), lib.stream_ptr()))
+    expected, es = big_dst.copy(), np.zeros(dw * sh + 4, np.uint8)
+    oracle.orc_filter_resize_u8(C.byref(abi.Image(expected.ctypes.data + dy * 203 + dx, dw, dh, 203, 0)), C.byref(abi.Image(big_src.ctypes.data + sy * 101 + sx, sw, sh, 101, 0)),
+                                abi.SAMPLER_LINEAR, orcbind.ptr(es))
+    got = td.cpu().numpy()
+    assert np.array_equal(got, expected)
+    assert not np.array_equal(got, big_dst)  # the window changed, and (first assert) nothing outside of it did
+
+
 def test_filter_map_and_magnify(cuda, oracle):
     rng = np.random.default_rng(7)
     src = rand_rgba(rng, 61, 83)

@@ -436,6 +436,36 @@ def test_debug_wireframe_matches_oracle(cuda, oracle, variant):
     assert_same_u32(again["color"], plain["color"], "colour of the next frame")
 
 
+def test_debug_wireframe_in_row_strips(cuda, oracle):
+    """The overlay obeys dfpsr_renderer_set_clip_rows like the frame itself: two strips drawn into one target equal the full frame."""
+    import occlusion_scene
+    from dfpsr_b200 import lib as L
+    sc = occlusion_scene.build()
+    expected = occlusion_scene.run_oracle(oracle, sc, wireframe=True)
+    cam = L.camera(sc["camera"])
+    tc, td = L.to_device(sc["color0"]), L.to_device(sc["depth0"])
+    wall = L.DeviceModel(*sc["wall"])
+    models = [L.DeviceModel(m["points"], m["polygons"]) for m in sc["models"]]
+    height = sc["color0"].shape[0]
+    split = (height // 2) & ~3
+    r = C.c_void_p()
+    s = L.stream_ptr()
+    L.check(cuda.dfpsr_renderer_create(C.byref(r)))
+    for top, bottom in ((0, split), (split, height)):
+        L.check(cuda.dfpsr_renderer_begin(r, C.byref(L.image(tc)), C.byref(L.image(td))))
+        L.check(cuda.dfpsr_renderer_set_clip_rows(r, top, bottom))
+        L.check(cuda.dfpsr_renderer_give_task(r, C.byref(wall.desc), C.byref(sc["wall_transform"]), C.byref(cam), s))
+        for m, dm in zip(sc["models"], models):
+            L.check(cuda.dfpsr_renderer_give_task(r, C.byref(dm.desc), C.byref(m["transform"]), C.byref(cam), s))
+        L.check(cuda.dfpsr_renderer_set_debug_wireframe(r, 1))
+        L.check(cuda.dfpsr_renderer_end(r, s))
+    L.check(cuda.dfpsr_renderer_destroy(r))
+    # no occluders here (every model is drawn): compare with an oracle frame without occlusion
+    plain = occlusion_scene.run_oracle_without_occluders(oracle, sc, wireframe=True)
+    assert_same_u32(tc.cpu().numpy().view(np.uint32), plain["color"], "colour of two strips with the overlay")
+    assert expected["color"].shape == plain["color"].shape
+
+
 @pytest.mark.parametrize("variant", OCCLUSION_VARIANTS)
 def test_device_broad_phase_equals_host_tests(cuda, oracle, variant):
     """dfpsr_renderer_give_tasks: isBoxSeen and renderer_isBoxVisible per model on the device (against the occluders given before the call)

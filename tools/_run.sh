@@ -1,2 +1,1 @@
-python -m pytest tests -x -q -m gpu 2>&1 | tail -3
-python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+python -m pytest tests/test_gpu_pixel_ops.py tests/test_gpu_raster.py -x -q -m gpu -k "strided or wireframe" 2>&1 | tail -15

@@ -577,6 +577,8 @@ __device__ void for_each_command(const TaskParams &task, const PPoint *p, const 
 
 // Loads the three corners of input triangle `slot` of a task. Returns false for an empty slot.
 __device__ bool load_triangle(const TaskParams &task, int32_t local, PPoint *p, float colors[3][4], float tex[3][4]) {
+	// texture coordinates are 64 of a polygon's 144 bytes (and 48 of a command's 160): a task without textures neither reads nor writes them
+	const bool textured = task.diffuseIndex >= 0 || task.lightIndex >= 0;
 	if (task.triangles != nullptr) {
 		const dfpsr_triangle &t = task.triangles[local];
 #pragma unroll
@@ -584,7 +586,7 @@ __device__ bool load_triangle(const TaskParams &task, int32_t local, PPoint *p, 
 			p[k] = *(const PPoint *)&t.pos[k];
 			p[k].pad = point_outcodes(task.camera, p[k]); // pre-projected corners come from the host without codes
 #pragma unroll
-			for (int ch = 0; ch < 4; ch++) { colors[k][ch] = t.colors[k][ch]; tex[k][ch] = t.texCoords[k][ch]; }
+			for (int ch = 0; ch < 4; ch++) { colors[k][ch] = t.colors[k][ch]; tex[k][ch] = textured ? t.texCoords[k][ch] : 0.0f; }
 		}
 		return true;
 	}
@@ -596,7 +598,7 @@ __device__ bool load_triangle(const TaskParams &task, int32_t local, PPoint *p, 
 	for (int k = 0; k < 3; k++) {
 		p[k] = task.projected[poly.pointIndices[corner[k]]];
 #pragma unroll
-		for (int ch = 0; ch < 4; ch++) { colors[k][ch] = poly.colors[corner[k]][ch]; tex[k][ch] = poly.texCoords[corner[k]][ch]; }
+		for (int ch = 0; ch < 4; ch++) { colors[k][ch] = poly.colors[corner[k]][ch]; tex[k][ch] = textured ? poly.texCoords[corner[k]][ch] : 0.0f; }
 	}
 	return true;
 }
@@ -1013,9 +1015,11 @@ __global__ void __launch_bounds__(SETUP_THREADS, SETUP_MIN_BLOCKS) setup_kernel(
 					dst[4] = make_uint4(FU(cmd.red[0]), FU(cmd.red[1]), FU(cmd.red[2]), FU(cmd.green[0]));
 					dst[5] = make_uint4(FU(cmd.green[1]), FU(cmd.green[2]), FU(cmd.blue[0]), FU(cmd.blue[1]));
 					dst[6] = make_uint4(FU(cmd.blue[2]), FU(cmd.alpha[0]), FU(cmd.alpha[1]), FU(cmd.alpha[2]));
-					dst[7] = make_uint4(FU(cmd.u1[0]), FU(cmd.u1[1]), FU(cmd.u1[2]), FU(cmd.v1[0]));
-					dst[8] = make_uint4(FU(cmd.v1[1]), FU(cmd.v1[2]), FU(cmd.u2[0]), FU(cmd.u2[1]));
-					dst[9] = make_uint4(FU(cmd.u2[2]), FU(cmd.v2[0]), FU(cmd.v2[1]), FU(cmd.v2[2]));
+					if (task.diffuseIndex >= 0 || task.lightIndex >= 0) { // words 7..9 are only read for commands with a texture
+						dst[7] = make_uint4(FU(cmd.u1[0]), FU(cmd.u1[1]), FU(cmd.u1[2]), FU(cmd.v1[0]));
+						dst[8] = make_uint4(FU(cmd.v1[1]), FU(cmd.v1[2]), FU(cmd.u2[0]), FU(cmd.u2[1]));
+						dst[9] = make_uint4(FU(cmd.u2[2]), FU(cmd.v2[0]), FU(cmd.v2[1]), FU(cmd.v2[2]));
+					}
 #undef FU
 				}
 				if (rowCount > 0) {

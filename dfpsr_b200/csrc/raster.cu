@@ -1015,8 +1015,10 @@ __global__ void __launch_bounds__(SETUP_THREADS, SETUP_MIN_BLOCKS) setup_kernel(
 					dst[4] = make_uint4(FU(cmd.red[0]), FU(cmd.red[1]), FU(cmd.red[2]), FU(cmd.green[0]));
 					dst[5] = make_uint4(FU(cmd.green[1]), FU(cmd.green[2]), FU(cmd.blue[0]), FU(cmd.blue[1]));
 					dst[6] = make_uint4(FU(cmd.blue[2]), FU(cmd.alpha[0]), FU(cmd.alpha[1]), FU(cmd.alpha[2]));
-					if (task.diffuseIndex >= 0 || task.lightIndex >= 0) { // words 7..9 are only read for commands with a texture
-						dst[7] = make_uint4(FU(cmd.u1[0]), FU(cmd.u1[1]), FU(cmd.u1[2]), FU(cmd.v1[0]));
+					// words 7..9 are only read for commands with a texture; word 7 is written anyway: it shares a 32-byte sector with word 6,
+					// and a sector that is only half written has to be filled from DRAM when it leaves the L2
+					dst[7] = make_uint4(FU(cmd.u1[0]), FU(cmd.u1[1]), FU(cmd.u1[2]), FU(cmd.v1[0]));
+					if (task.diffuseIndex >= 0 || task.lightIndex >= 0) {
 						dst[8] = make_uint4(FU(cmd.v1[1]), FU(cmd.v1[2]), FU(cmd.u2[0]), FU(cmd.u2[1]));
 						dst[9] = make_uint4(FU(cmd.u2[2]), FU(cmd.v2[0]), FU(cmd.v2[1]), FU(cmd.v2[2]));
 					}

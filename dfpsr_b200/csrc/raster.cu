@@ -27,8 +27,13 @@
 
 namespace dfpsr {
 
-static const int TILE_W = 32, TILE_H = 4;  // one warp: 16 x 2 quads
-static const int BATCH = 16;               // commands whose checkpoints are prepared together (BATCH x 2 row pairs = 32 lanes)
+#ifndef DFPSR_TILE_W
+#define DFPSR_TILE_W 32 // pixels per tile row: 32 (a 32 x 4 tile, 16 x 2 quads) or 16 (16 x 8, 8 x 4 quads); one warp owns a tile of 128 pixels either way
+#endif
+static const int TILE_W = DFPSR_TILE_W, TILE_H = 128 / DFPSR_TILE_W;
+static const int QUADS_X = TILE_W / 2, PAIRS_Y = TILE_H / 2; // lane = quad (qx, qy) = (lane % QUADS_X, lane / QUADS_X)
+static const int BATCH = 32 / PAIRS_Y;      // commands whose checkpoints are prepared together (BATCH x PAIRS_Y row pairs = 32 lanes)
+static_assert((TILE_W == 32 || TILE_W == 16) && QUADS_X * PAIRS_Y == 32, "tile shape");
 static const int SMALL_ROWS = 8;           // large frames: triangles up to this many rows and SMALL_WIDTH columns are scan-converted by their set-up thread
 static const int SMALL_WIDTH = 128;
 static const int SMALL_TILES = 8;          // counting pass: bounding boxes up to this many tiles are counted by the set-up thread
@@ -1157,7 +1162,7 @@ __global__ void __launch_bounds__(BIG_UNITS_THREADS) big_units_kernel(FrameDev f
 			ty = it.t / TILE_H + (int32_t)(u - it.unitStart);
 			height = it.ty1; // the view's height travels in ty1 (unused by the emit pass)
 			const int32_t yBegin = max(it.t, ty * TILE_H), yEnd = min(it.t + it.rowCount, ty * TILE_H + TILE_H);
-			const int32_t yFirst = SPLIT ? yBegin + 2 * half : yBegin, yLast = SPLIT ? min(yEnd, yFirst + 2) : yEnd;
+			const int32_t yFirst = SPLIT ? yBegin + (TILE_H / 2) * half : yBegin, yLast = SPLIT ? min(yEnd, yFirst + TILE_H / 2) : yEnd;
 			if (yFirst < yLast) {
 				EdgeSet edges;
 				long long fx[3] = {it.fx[0], it.fx[1], it.fx[2]}, fy[3] = {it.fy[0], it.fy[1], it.fy[2]};
@@ -1818,7 +1823,7 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32, (MODE == TILE_DEFERRED ? (E
 	if (n == 0) {
 		// An empty tile of a cleared target (sky; most tiles of a shadow cube map): nothing to load, sort or shade. Lane = four pixels of
 		// one row, one 16-byte store per buffer when the row allows it.
-		const int32_t x = tileX * TILE_W + 4 * (lane & 7), y = tileY * TILE_H + (lane >> 3);
+		const int32_t x = tileX * TILE_W + 4 * (lane % (TILE_W / 4)), y = tileY * TILE_H + lane / (TILE_W / 4);
 		if (y >= vw.height || x >= vw.width) { return; }
 		const int32_t count = min(4, vw.width - x);
 		if (!DEPTH_ONLY && vw.color.data != nullptr) {
@@ -1839,7 +1844,7 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32, (MODE == TILE_DEFERRED ? (E
 
 	const int32_t width = vw.width, height = vw.height;
 	const int32_t tileLeft = tileX * TILE_W;
-	const int32_t qx = lane & 15, qy = lane >> 4;
+	const int32_t qx = lane % QUADS_X, qy = lane / QUADS_X;
 	const int32_t x0 = tileLeft + 2 * qx, y1 = tileY * TILE_H + 2 * qy, y2 = y1 + 1;
 	const dfpsr_image color = vw.color, depth = vw.depth;
 	const bool hasColor = !DEPTH_ONLY && color.data != nullptr, hasDepth = depth.data != nullptr;
@@ -1896,7 +1901,7 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32, (MODE == TILE_DEFERRED ? (E
 	for (uint32_t batchStart = 0; batchStart < n; batchStart += BATCH) {
 		const uint32_t batchCount = min((uint32_t)BATCH, n - batchStart);
 		// ---- lane (c, r): checkpoint of command c for row pair r of this tile
-		const uint32_t c = (uint32_t)lane & 15u, r = (uint32_t)lane >> 4;
+		const uint32_t c = (uint32_t)lane % (uint32_t)BATCH, r = (uint32_t)lane / (uint32_t)BATCH;
 		uint32_t key;
 		if (localSort) { key = sKeys[(batchStart + c) & (uint32_t)(LOCAL_SORT - 1)]; }
 		else { key = c < batchCount ? __ldg(list + batchStart + c) : 0u; }
@@ -2045,7 +2050,8 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32, (MODE == TILE_DEFERRED ? (E
 				(void)stored;
 				rec.mode = recMode;
 			}
-			sMask[r * BATCH + 2u * (c & 7u) + (c >> 3)] = (uint16_t)((recMode >= 0 && quadEnd > quadFirst) ? ((0xFFFFFFFFu >> (32 - quadEnd)) & ~((1u << quadFirst) - 1u)) : 0u);
+			// commands c and c + BATCH / 2 share one 32-bit word of the row pair's masks
+			sMask[r * BATCH + 2u * (c % (uint32_t)(BATCH / 2)) + c / (uint32_t)(BATCH / 2)] = (uint16_t)((recMode >= 0 && quadEnd > quadFirst) ? ((0xFFFFFFFFu >> (32 - quadEnd)) & ~((1u << quadFirst) - 1u)) : 0u);
 		}
 		__syncwarp();
 		// Every lane collects the commands of the batch that may touch ITS quad and works through them in submission order. Lanes are
@@ -2053,14 +2059,18 @@ __global__ void __launch_bounds__(RASTER_WARPS * 32, (MODE == TILE_DEFERRED ? (E
 		// time instead of idling through each other's commands: the warp needs as many rounds as its busiest quad has commands.
 		uint32_t cover = 0;
 		{
-			static_assert(BATCH == 16, "the coverage masks of commands c and c + 8 share one 32-bit word");
+			constexpr int HALF = BATCH / 2; // words per row pair: word k holds the masks of commands k (low half) and k + HALF (high half)
 			const uint4 *masks = (const uint4 *)(sMask + qy * BATCH);
-			const uint4 m0 = masks[0], m1 = masks[1];
-			const uint32_t words[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
-			uint32_t both = 0u; // bit k: command k, bit 16 + k: command 8 + k
+			uint32_t words[HALF];
+			{
+				const uint4 m0 = masks[0];
+				words[0] = m0.x; words[1] = m0.y; words[2] = m0.z; words[3] = m0.w;
+				if constexpr (HALF == 8) { const uint4 m1 = masks[1]; words[4] = m1.x; words[5] = m1.y; words[6] = m1.z; words[7] = m1.w; }
+			}
+			uint32_t both = 0u; // bit k: command k, bit 16 + k: command HALF + k
 #pragma unroll
-			for (int k = 0; k < 8; k++) { both |= ((words[k] >> qx) & 0x00010001u) << k; }
-			cover = (both & 0xFFu) | ((both >> 8) & 0xFF00u);
+			for (int k = 0; k < HALF; k++) { both |= ((words[k] >> qx) & 0x00010001u) << k; }
+			cover = (both & ((1u << HALF) - 1u)) | ((both >> (16 - HALF)) & (((1u << HALF) - 1u) << HALF));
 		}
 
 		while (__any_sync(0xffffffffu, cover != 0u)) {
@@ -2703,7 +2713,7 @@ static int run_frame(dfpsr_renderer *r, cudaStream_t stream, bool allowAsync) {
 	// 44.0 at 16, 44.7 at 32 — but the 2 M tiny triangles of BASELINE config 3 (2-3 pixels tall, up to 6 aligned rows) take 930 us at 4
 	// (a third of them queue a unit each) against 620 us at 8. DFPSR_SMALL_ROWS overrides for experiments.
 	static const int smallRowsOverride = getenv("DFPSR_SMALL_ROWS") ? atoi(getenv("DFPSR_SMALL_ROWS")) : -1;
-	frame.smallRows = slotTotal <= sm_count() * 1024 ? TILE_H : SMALL_ROWS;
+	frame.smallRows = slotTotal <= sm_count() * 1024 ? 4 : SMALL_ROWS;
 	if (smallRowsOverride >= 0) { frame.smallRows = smallRowsOverride; }
 
 	if (taskCount == 0) {

@@ -1,23 +1,31 @@
-// raster.cu — the triangle pipeline on sm_100a (v2: warp-owned 32x4 tiles, batched views).
+// raster.cu — the triangle pipeline on sm_100a: warp-owned 32x4 pixel tiles, batched views, one launch sequence per frame.
 //
-//   project_kernel       ref: api/modelAPI.cpp:238-242 + implementation/render/Camera.h:157-190 — all tasks of a batch in one launch
+//   project_kernel       ref: api/modelAPI.cpp:238-242 + implementation/render/Camera.h:157-190 — all tasks of a batch in one launch; leaves
+//                        the frustum plane codes of every point in PPoint::pad and clears the frame's counters in its spare grid rows
 //   setup_kernel<false>  ref: implementation/render/renderCore.cpp:172-341 (cull, clip, back-face) — counting pass: commands and rows per
-//                        slot, an upper bound of the entries of every screen tile (bounding box)
-//   scan_blocks_kernel   ordered prefix sums that replace List<TriangleDrawCommand>::push (renderCore.cpp:445): commands keep submission order
-//   tile_alloc_kernel    hands every tile a segment of the entry pool (warp-aggregated atomics; replaces CommandQueue::execute's 12 strips,
-//                        renderCore.cpp:449-480, with per-tile lists)
+//                        slot, an upper bound of the entries of every screen tile (bounding box), units and checkpoints of large commands
+//   counts_kernel        ordered prefix sums that replace List<TriangleDrawCommand>::push (renderCore.cpp:445: commands keep submission
+//                        order), a segment of the entry pool for every tile (replaces CommandQueue::execute's 12 strips, :449-480, with
+//                        per-tile lists) and the frame's totals / verdict for the host — one launch
 //   setup_kernel<true>   emits compact draw commands + their row intervals (implementation/render/ITriangle2D.cpp:31-176) + interpolation
-//                        planes (:182-300) and bins each command to exactly the tiles its row intervals touch. Tall or wide triangles are
-//                        handed to whole warps through a shared-memory queue (one lane per tile row).
-//   sort_lists_kernel    only when a tile holds more than 32 entries: restores submission order inside long tile lists
+//                        planes (:182-300) and bins small commands to exactly the tiles their row intervals touch; large commands are
+//                        queued as (command, tile row) units
+//   big_units_kernel     one thread per unit: row intervals, binning and the interpolation checkpoints at the tile edges a row pair crosses
+//   sort_lists_kernel    only when a tile holds more than 64 entries: restores submission order inside long tile lists
 //   raster_kernel        ref: shader/fillerTemplates.h:108-441 + shader/RgbaMultiply.h:37-175 + api/textureAPI.h:253-495
-//                        one WARP per 32x4 pixel tile, one lane per aligned 2x2 quad, colour and depth of the tile in registers for the whole
-//                        list, commands applied in submission order, no block-wide barrier anywhere. Commands are taken 16 at a time: lane
-//                        (command, row pair) replays the reference's running float sums from the triangle's left edge up to the tile ONCE
-//                        and leaves a checkpoint in shared memory; the quad lanes continue from it with at most 15 additions.
+//                        one WARP per tile, one lane per aligned 2x2 quad, colour and depth of the tile in registers for the whole list,
+//                        no block-wide barrier anywhere. Commands are taken 16 at a time: lane (command, row pair) loads or replays the
+//                        reference's running float sums up to the tile's left edge ONCE and leaves a checkpoint in shared memory; every
+//                        quad lane then works through the commands that touch ITS quad in submission order, continuing from the
+//                        checkpoint with at most 15 additions. Instances: deferred (visibility pass + every pixel shaded once; exact with
+//                        prepared shading inputs, exact raw for frames without textures, tolerance), immediate (alpha-filtered frames),
+//                        depth only.
+//   wireframe_kernel     ref: api/rendererAPI.cpp:362-399 — renderer_end's debug overlay
+//   occlude_existing_kernel / top_rows_kernel   ref: api/rendererAPI.cpp:242-258, :403-477 — the device side of the occlusion grid
 //
 // Exactness: coverage is the reference's int64 row-interval arithmetic; interpolated (1/W, U/W, V/W) replay the reference's chain of float
 // additions from each row pair's outer block start, so colour and depth are bit-identical to the reference's scalar build (exact 1/x).
+// Asynchronous frames, pools sized from history and the verdict protocol with the host: see run_frame / verify_frame below and DESIGN 4.7.
 #include "common.cuh"
 
 #include <algorithm>
